@@ -1,0 +1,491 @@
+"""Pins the CPU oracle against the reference's OWN known-answer tests.
+
+Every test names the reference test it ports as file:line under /root/reference/src.  The
+reference cannot be run here (no rustc), so these known-answer pairs are the anchor for parity;
+the GPU parity tests then compare the CUDA path with this oracle.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from oracle.oracle import (Array, DataFrame, LazyFrame, OracleError, RecordBatch, StreamingPhysicalPlan, col, lit,
+                           EX_BOOLEAN, EX_FLOAT64, EX_INT64, EX_NULL, EX_STRING)
+
+
+# ---------------------------------------------------------------- fixtures (reference builders)
+def df_name_age_score():
+    # physical_plan/plan.rs:295-327, logical_plan/builder.rs:128-160
+    return DataFrame.new([("name", ["Alice", "Bob", "Charlie"]), ("age", [25, 30, 35]), ("score", [85.5, 92.0, 78.5])])
+
+
+def df_name_age_active():
+    # physical_plan/streaming_planner.rs:177-209
+    return DataFrame.new([("name", ["Alice", "Bob", "Charlie"]), ("age", [25, 30, 35]), ("active", [True, False, True])])
+
+
+def rb_id_name_active():
+    # execution/record_batch.rs:585-604 (3 rows, one null string)
+    return RecordBatch.try_new(["id", "name", "active"],
+                               [Array.from_list([1, 2, 3], EX_INT64), Array.from_list(["Alice", None, "Charlie"], EX_STRING),
+                                Array.from_list([True, False, True], EX_BOOLEAN)])
+
+
+def make_batch(id_start):
+    # execution/stream.rs:236-250, physical_plan/streaming.rs:375-389
+    return RecordBatch.try_new(["id", "name", "active"],
+                               [Array.from_list([id_start, id_start + 1], EX_INT64),
+                                Array.from_list([f"name_{id_start}", f"name_{id_start + 1}"], EX_STRING),
+                                Array.from_list([True, False], EX_BOOLEAN)])
+
+
+def pattern(n):
+    # execution/array/bitmap.rs:207-210
+    return [((i % 3 == 0) != (i % 5 == 0)) for i in range(n)]
+
+
+# ---------------------------------------------------------------- datatypes/series.rs
+def test_anyvalue_partial_ord():  # series.rs:349-366
+    assert O.any_partial_cmp(1, 2) == -1
+    assert O.any_partial_cmp(1.0, 2.0) == -1
+    assert O.any_partial_cmp("a", "b") == -1
+    assert O.any_partial_cmp(False, True) == -1
+    assert O.any_partial_cmp(None, 0) == -1          # Null < everything
+    assert O.any_partial_cmp(None, False) == -1
+    assert O.any_partial_cmp(1, "1") is None         # cross-type => None
+
+
+def test_anyvalue_eq_semantics():  # series.rs:87-98 (+ tests :310-335)
+    assert O.any_eq(None, None)
+    assert O.any_eq(42, 42) and not O.any_eq(42, 43)
+    assert not O.any_eq(1, 1.0)                      # no Int<->Float coercion
+    assert O.any_eq(0.0, -0.0)
+    assert not O.any_eq(float("nan"), float("nan"))
+
+
+def test_series_dtype_inference():  # series.rs:400-469, 521-534
+    assert DataFrame.new([("numbers", [1, 2, 3])]).dtypes() == ["Int64"]
+    assert DataFrame.new([("letters", ["a", "b", "c"])]).dtypes() == ["String"]
+    assert DataFrame.new([("with_nulls", [1, None, 3])]).dtypes() == ["Int64"]
+    assert DataFrame.new([("nulls", [None, None])]).dtypes() == ["Null"]
+    assert DataFrame.new([("mixed_numeric", [1, 2.5, 3])]).dtypes() == ["Float64"]
+    with pytest.raises(OracleError, match="Mixed types in series: expected Int64, found String"):
+        DataFrame.new([("mixed", [1, "hello"])])
+    with pytest.raises(OracleError, match="Empty series not allowed"):
+        DataFrame.new([("empty", [])])
+
+
+# ---------------------------------------------------------------- physical_plan/plan.rs (eager)
+def test_execute_filter_gt():  # plan.rs:505-525
+    r = LazyFrame.from_dataframe(df_name_age_score()).filter(col("age").gt(lit(25))).collect()
+    assert (r.height(), r.width()) == (2, 3)
+    assert r.column("age") == [30, 35]
+    assert r.column("name") == ["Bob", "Charlie"]
+
+
+def test_execute_filter_eq():  # plan.rs:528-547
+    r = LazyFrame.from_dataframe(df_name_age_score()).filter(col("name").eq(lit("Bob"))).collect()
+    assert r.height() == 1 and r.column("name") == ["Bob"]
+
+
+def test_execute_filter_lt():  # plan.rs:550-569
+    r = LazyFrame.from_dataframe(df_name_age_score()).filter(col("score").lt(lit(90.0))).collect()
+    assert r.height() == 2 and r.column("name") == ["Alice", "Charlie"]
+
+
+def test_execute_filter_no_matches():  # plan.rs:572-589
+    r = LazyFrame.from_dataframe(df_name_age_score()).filter(col("age").gt(lit(100))).collect()
+    assert (r.height(), r.width()) == (0, 3)
+    assert r.column_names() == ["name", "age", "score"]
+    assert r.dtypes() == ["String", "Int64", "Float64"]     # Series::empty keeps the dtype (plan.rs:140-141)
+
+
+def test_execute_limit():  # plan.rs:615-667
+    lf = LazyFrame.from_dataframe(df_name_age_score())
+    r = lf.limit(2).collect()
+    assert (r.height(), r.width()) == (2, 3) and r.column("name") == ["Alice", "Bob"]
+    r = lf.limit(10).collect()
+    assert r.height() == 3
+    r = lf.limit(0).collect()
+    assert (r.height(), r.width()) == (0, 3)
+
+
+def test_execute_chained_operations():  # plan.rs:672-704
+    r = (LazyFrame.from_dataframe(df_name_age_score()).select([col("name"), col("age"), col("score")])
+         .filter(col("age").gt(lit(25))).limit(1).collect())
+    assert (r.height(), r.width()) == (1, 3) and r.column("name") == ["Bob"]
+
+
+def test_execute_filter_then_select():  # plan.rs:707-735
+    r = (LazyFrame.from_dataframe(df_name_age_score()).filter(col("age").gte(lit(30)))
+         .select([col("name"), col("score")]).collect())
+    assert (r.height(), r.width()) == (2, 2)
+    assert r.column_names() == ["name", "score"] and r.column("name") == ["Bob", "Charlie"]
+    assert r.column("score") == [92.0, 78.5]
+
+
+def test_execute_select_variants():  # plan.rs:424-502
+    lf = LazyFrame.from_dataframe(df_name_age_score())
+    assert lf.select([col("name")]).collect().column_names() == ["name"]
+    assert lf.select([col("score"), col("name")]).collect().column_names() == ["score", "name"]
+    with pytest.raises(OracleError, match="Column not found: 'nonexistent'"):
+        lf.select([col("nonexistent")]).collect()
+
+
+# ---------------------------------------------------------------- logical_plan/builder.rs (end to end)
+def test_collect_simple_select_filter_limit():  # builder.rs:436-473
+    df = df_name_age_score()
+    r = LazyFrame.from_dataframe(df).select([col("name"), col("age")]).collect()
+    assert (r.width(), r.height()) == (2, 3) and r.column_names() == ["name", "age"]
+    r = LazyFrame.from_dataframe(df).filter(col("age").gt(lit(25))).collect()
+    assert (r.height(), r.width()) == (2, 3)
+    r = LazyFrame.from_dataframe(df).limit(2).collect()
+    assert (r.height(), r.width()) == (2, 3)
+
+
+def test_collect_invalid_columns():  # builder.rs:497-532
+    with pytest.raises(OracleError, match=r"Logical plan error: Column not found: 'nonexistent'"):
+        LazyFrame.from_dataframe(df_name_age_score()).select([col("nonexistent")]).collect()
+    with pytest.raises(OracleError, match=r"Logical plan error: Column not found: 'nonexistent'"):
+        LazyFrame.from_dataframe(df_name_age_score()).filter(col("nonexistent").gt(lit(0))).collect()
+
+
+def test_collect_streaming():  # builder.rs:570-614
+    df = df_name_age_score()
+    r = LazyFrame.from_dataframe(df).select([col("name"), col("age")]).collect_streaming()
+    assert (r.num_columns(), r.num_rows()) == (2, 3) and r.column_names() == ["name", "age"]
+    with pytest.raises(OracleError):          # no 'active' column in this frame (builder.rs:584-594)
+        LazyFrame.from_dataframe(df).filter(col("active")).collect_streaming()
+    old = LazyFrame.from_dataframe(df).select([col("name")]).collect()
+    new = LazyFrame.from_dataframe(df).select([col("name")]).collect_streaming()
+    assert (old.width(), old.height()) == (new.num_columns(), new.num_rows())
+
+
+def test_readme_shape_fails_validation():  # README.md:59-63 vs logical_plan/plan.rs:139-146
+    lf = LazyFrame.from_dataframe(df_name_age_score()).select([col("name")]).filter(col("age").gt(lit(25)))
+    assert lf.plan_shape() == "Filter(Select(Source))"
+    with pytest.raises(OracleError, match="Logical plan error: Column not found: 'age'"):
+        lf.collect()
+
+
+def test_optimizer_rewrite():  # optimizer.rs:15-64
+    df = df_name_age_score()
+    # predicate column among the selected ones => Select(Filter) becomes Filter(Select)
+    lf = LazyFrame.from_dataframe(df).filter(col("age").gt(lit(25))).select([col("name"), col("age")])
+    assert lf.plan_shape() == "Filter(Select(Source))"
+    assert lf.collect().to_dict() == {"name": ["Bob", "Charlie"], "age": [30, 35]}
+    # predicate column not selected => unchanged
+    lf = LazyFrame.from_dataframe(df).filter(col("age").gt(lit(25))).select([col("name")])
+    assert lf.plan_shape() == "Select(Filter(Source))"
+    assert lf.collect().to_dict() == {"name": ["Bob", "Charlie"]}
+    # Limit blocks the recursion (optimizer.rs:62)
+    lf = LazyFrame.from_dataframe(df).filter(col("age").lt(lit(40))).select([col("age")]).limit(2)
+    assert lf.plan_shape() == "Limit(Select(Filter(Source)))"
+
+
+def test_planner_rejections():  # planner.rs:134-189 (tests :191-697 duplicate plan.rs's)
+    lf = LazyFrame.from_dataframe(df_name_age_score())
+    with pytest.raises(OracleError, match="Unsupported filter: only simple column comparisons supported"):
+        lf.filter(col("age").gt(lit(1)).and_(col("age").lt(lit(9)))).collect()
+    with pytest.raises(OracleError, match="Unsupported binary operator in filter: Plus"):
+        lf.filter(col("age").add(lit(1))).collect()
+    with pytest.raises(OracleError, match="Filter must be a binary comparison, found: Column"):
+        lf.filter(col("age")).collect()
+    with pytest.raises(OracleError, match="Filter right side must be a literal value"):
+        lf.filter(col("age").gt(col("score"))).collect()
+    with pytest.raises(OracleError, match="Unsupported expression"):
+        lf.select([col("age").add(lit(1))]).collect()
+
+
+# ---------------------------------------------------------------- main.rs demo queries
+def df_main():
+    return DataFrame.new([("name", ["Alice", "Bob", "Charlie", "Diana", "Eve"]), ("age", [25, 30, 35, 28, 42]),
+                          ("score", [85.5, 92.0, 78.5, 94.5, 88.0])])
+
+
+def test_main_demo_queries():  # main.rs:47-94
+    df = df_main()
+    q1 = LazyFrame.from_dataframe(df).select([col("name"), col("age")]).filter(col("age").gt(lit(30))).collect()
+    assert q1.to_dict() == {"name": ["Charlie", "Eve"], "age": [35, 42]}
+    q2 = (LazyFrame.from_dataframe(df).filter(col("score").gte(lit(90.0)))
+          .select([col("name"), col("age").alias("user_age")]).collect())
+    assert q2.to_dict() == {"name": ["Bob", "Diana"], "user_age": [30, 28]}
+    q3 = LazyFrame.from_dataframe(df).filter(col("age").lt(lit(40))).limit(2).collect()
+    assert q3.to_dict() == {"name": ["Alice", "Bob"], "age": [25, 30], "score": [85.5, 92.0]}
+    q4 = LazyFrame.from_dataframe(df).filter(col("age").gt(lit(100))).collect()
+    assert (q4.height(), q4.column_names(), q4.dtypes()) == (0, ["name", "age", "score"], ["String", "Int64", "Float64"])
+    q5 = LazyFrame.from_dataframe(df).select([col("name")]).limit(0).collect()
+    assert (q5.height(), q5.column_names(), q5.dtypes()) == (0, ["name"], ["String"])
+
+
+# ---------------------------------------------------------------- execution/record_batch.rs
+def test_rb_slice():  # record_batch.rs:700-749
+    b = rb_id_name_active()
+    s = b.slice(1, 2)
+    assert (s.num_rows(), s.num_columns()) == (2, 3)
+    assert s.column(0).to_list() == [2, 3]
+    assert b.slice(1, 0).num_rows() == 0 and b.slice(0, 3).num_rows() == 3 and b.slice(2, 1).num_rows() == 1
+    with pytest.raises(OracleError) as ei:
+        b.slice(2, 5)
+    assert ei.value.panic and "Slice out of bounds" in str(ei.value)
+
+
+def test_rb_take():  # record_batch.rs:752-791
+    b = rb_id_name_active()
+    t = b.take([2, 0, 1])
+    assert t.column(0).to_list() == [3, 1, 2]
+    assert t.column(1).to_list() == ["Charlie", "Alice", None]
+    assert b.take([]).num_rows() == 0
+    with pytest.raises(OracleError, match="Index 5 out of bounds for 3 rows"):
+        b.take([0, 5, 1])
+
+
+def test_rb_select_columns():  # record_batch.rs:794-819
+    b = rb_id_name_active()
+    assert b.select_columns([0, 2]).column_names() == ["id", "active"]
+    assert b.select_columns_by_name(["name", "id"]).column_names() == ["name", "id"]
+
+
+def test_rb_filter():  # record_batch.rs:822-879
+    b = rb_id_name_active()
+    f = b.filter(Array.from_list([True, False, True], EX_BOOLEAN))
+    assert (f.num_rows(), f.num_columns()) == (2, 3) and f.column(0).to_list() == [1, 3]
+    assert b.filter(Array.from_list([True, True, True], EX_BOOLEAN)).num_rows() == 3
+    assert b.filter(Array.from_list([False, False, False], EX_BOOLEAN)).num_rows() == 0
+    assert b.filter(Array.from_list([True, None, False], EX_BOOLEAN)).num_rows() == 1   # null mask entry drops the row
+    with pytest.raises(OracleError, match="Predicate must be a BooleanArray"):
+        b.filter(Array.from_list([1, 2, 3], EX_INT64))
+    with pytest.raises(OracleError, match="Predicate length 2 doesn't match batch length 3"):
+        b.filter(Array.from_list([True, False], EX_BOOLEAN))
+
+
+def test_rb_concat():  # record_batch.rs:882-949
+    b1 = RecordBatch.try_new(["id", "name", "active"], [Array.from_list([1, 2], EX_INT64), Array.from_list(["A", None], EX_STRING),
+                                                        Array.from_list([True, False], EX_BOOLEAN)])
+    b2 = RecordBatch.try_new(["id", "name", "active"], [Array.from_list([3, 4], EX_INT64), Array.from_list(["B", "C"], EX_STRING),
+                                                        Array.from_list([True, True], EX_BOOLEAN)])
+    c = RecordBatch.concat([b1, b2])
+    assert (c.num_rows(), c.num_columns()) == (4, 3)
+    assert c.column(0).to_list() == [1, 2, 3, 4]
+    assert c.column(1).to_list() == ["A", None, "B", "C"]
+    e = b1.empty_like()
+    assert RecordBatch.concat([e, e]).num_rows() == 0
+    other = RecordBatch.try_new(["name"], [Array.from_list([], EX_STRING)])
+    idonly = RecordBatch.try_new(["id"], [Array.from_list([], EX_INT64)])
+    with pytest.raises(OracleError, match="All batches must have the same schema"):
+        RecordBatch.concat([idonly, other])
+    with pytest.raises(OracleError, match="Cannot concatenate empty batch list"):
+        RecordBatch.concat([])
+
+
+def test_rb_try_new_errors():  # record_batch.rs:16-58 (tests :620-697)
+    with pytest.raises(OracleError, match="Schema has 2 fields but 1 columns provided"):
+        RecordBatch.try_new(["a"], [Array.from_list([1], EX_INT64)], schema_dtypes=[EX_INT64, EX_INT64], schema_names=["a", "b"])
+    with pytest.raises(OracleError, match="Column 1 has length 2 but expected 3"):
+        RecordBatch.try_new(["a", "b"], [Array.from_list([1, 2, 3], EX_INT64), Array.from_list([1, 2], EX_INT64)])
+    with pytest.raises(OracleError, match="Column 0 has type Int64 but schema expects String"):
+        RecordBatch.try_new(["a"], [Array.from_list([1], EX_INT64)], schema_dtypes=[EX_STRING])
+
+
+def test_output_layout_rules():
+    # primitive.rs:175-185 / record_batch.rs:140-147: placeholder 0 under nulls, bitmap present iff a survivor is null
+    b = RecordBatch.try_new(["v", "w"], [Array.from_list([10, None, 30, None], EX_INT64), Array.from_list([1.5, 2.5, None, 4.5], EX_FLOAT64)])
+    t = b.take([0, 1, 2])
+    v, w = t.column(0), t.column(1)
+    assert v.values.tolist() == [10, 0, 30] and v.validity is not None and v.validity.tolist() == [0b101] and v.offset == 0
+    assert w.values.tolist() == [1.5, 2.5, 0.0] and w.validity.tolist() == [0b011]
+    t2 = b.take([0, 2])
+    assert t2.column(0).validity is None and t2.column(0).null_count == 0        # no nulls => bitmap dropped
+    assert t2.column(1).validity is not None
+
+
+# ---------------------------------------------------------------- arrays / bitmaps
+def test_bitmap_roundtrip_and_slices():  # bitmap.rs:230-241, 255-309, 336-361
+    vals = pattern(37)
+    bits = O.pack_bits(vals)
+    a = Array.boolean(bits, 37)
+    assert a.to_list() == vals
+    assert bits[0] == sum((1 << i) for i in range(8) if vals[i])            # LSB-first
+    vals = pattern(64)
+    a = Array.boolean(O.pack_bits(vals), 64)
+    s = a.slice(7, 25)
+    assert s.export().offset == 7 and s.to_list() == vals[7:32]
+    vals = pattern(91)
+    a = Array.boolean(O.pack_bits(vals), 91)
+    s1, s2 = a.slice(10, 50).slice(7, 20), a.slice(17, 20)
+    assert s1.export().offset == s2.export().offset == 17 and s1.to_list() == s2.to_list() == vals[17:37]
+    vals = [i in (7, 8, 16) for i in range(17)]
+    a = Array.boolean(O.pack_bits(vals), 17)
+    assert a.to_list() == vals and a.slice(6, 6).to_list() == vals[6:12]
+    with pytest.raises(OracleError):
+        Array.boolean(O.pack_bits([False] * 16), 16).slice(9, 8)
+
+
+def test_primitive_slice_with_nulls():  # primitive.rs:283-306
+    a = Array.from_list([1, None, 3, None, 5, None], EX_INT64)
+    s = a.slice(2, 3)
+    e = s.export()
+    assert e.length == 3 and e.offset == 2
+    assert s.to_list() == [3, None, 5] and s.null_count() == 1
+
+
+def test_primitive_builder():  # primitive.rs:546-604
+    b = RecordBatch.try_new(["x"], [Array.from_list([10, None, 20, 30, None], EX_INT64)]).take([0, 1, 2, 3, 4]).column(0)
+    assert b.length == 5 and b.null_count == 2 and b.to_list() == [10, None, 20, 30, None]
+    assert b.values.tolist() == [10, 0, 20, 30, 0]
+    c = RecordBatch.try_new(["x"], [Array.from_list([10, 20, 30, 40, 50], EX_INT64)]).take([0, 1, 2, 3, 4]).column(0)
+    assert c.null_count == 0 and c.validity is None
+
+
+def test_string_layout():  # string.rs:362-381, 574-633, 683-694
+    a = Array.from_list(["hello", "", "world"], EX_STRING).export()
+    assert a.offsets.tolist() == [0, 5, 5, 10] and a.validity is None
+    a = Array.from_list(["hello", None, "world!!!", ""], EX_STRING)
+    e = a.export()
+    assert e.offsets.tolist() == [0, 5, 5, 13, 13] and a.to_list() == ["hello", None, "world!!!", ""]   # nulls zero-length
+    e = Array.from_list(["ascii", "café", "🦀", "🦀🔥", "", None], EX_STRING).export()
+    assert np.diff(e.offsets).tolist() == [5, 5, 4, 8, 0, 0]
+    e = Array.from_list(["hello", "world", None, "test"], EX_STRING).export()
+    assert len(e.data) == 14                                                                           # total_bytes
+    assert Array.from_list([], EX_STRING).export().validity is None
+
+
+# ---------------------------------------------------------------- streams (stream.rs, streaming.rs)
+def test_streaming_plan_memory_source_ops():  # streaming.rs:392-462
+    b1, b2 = make_batch(1), make_batch(3)
+    r = StreamingPhysicalPlan.memory_source([b1, b2]).collect()
+    assert (r.num_rows(), r.num_columns()) == (4, 3)
+    r = StreamingPhysicalPlan.memory_source([b1, b2]).filter("active").collect()
+    assert (r.num_rows(), r.num_columns()) == (2, 3) and r.column(0).to_list() == [1, 3]
+    r = StreamingPhysicalPlan.memory_source([b1, b2]).select(["id", "name"]).collect()
+    assert (r.num_rows(), r.num_columns()) == (4, 2) and r.column_names() == ["id", "name"]
+    r = StreamingPhysicalPlan.memory_source([b1, b2]).limit(3).collect()
+    assert (r.num_rows(), r.num_columns()) == (3, 3)
+    r = StreamingPhysicalPlan.memory_source([b1, b2]).filter("active").select(["name"]).limit(1).collect()
+    assert (r.num_rows(), r.num_columns()) == (1, 1) and r.column_names() == ["name"] and r.column(0).to_list() == ["name_1"]
+
+
+def test_limit_stream_batches():  # streaming.rs:465-498
+    b1, b2 = make_batch(1), make_batch(3)
+    got = StreamingPhysicalPlan.memory_source([b1, b2]).limit(2).collect_batches()
+    assert [b.num_rows() for b in got] == [2]                     # exact batch size: second pull returns None
+    got = StreamingPhysicalPlan.memory_source([b1, b2]).limit(3).collect_batches()
+    assert [b.num_rows() for b in got] == [2, 1]                  # partial batch, then None
+
+
+def test_collect_vs_collect_batches():  # streaming.rs:501-516, stream.rs:535-550
+    b1, b2 = make_batch(1), make_batch(3)
+    assert StreamingPhysicalPlan.memory_source([b1, b2]).collect().num_rows() == 4
+    assert [b.num_rows() for b in StreamingPhysicalPlan.memory_source([b1, b2]).collect_batches()] == [2, 2]
+
+
+def test_filter_select_stream_operators():  # stream.rs:366-432, 437-532
+    b = make_batch(1)
+    got = StreamingPhysicalPlan.memory_source([b]).filter("active").collect_batches()
+    assert [x.num_rows() for x in got] == [1]
+    none = RecordBatch.try_new(["id", "name", "active"], [Array.from_list([1, 2], EX_INT64), Array.from_list(["a", "b"], EX_STRING),
+                                                         Array.from_list([False, False], EX_BOOLEAN)])
+    got = StreamingPhysicalPlan.memory_source([none]).filter("active").collect_batches()
+    assert [x.num_rows() for x in got] == [0]
+    with pytest.raises(OracleError, match="Column 'nonexistent' not found in schema"):
+        StreamingPhysicalPlan.memory_source([b]).filter("nonexistent").collect()
+    with pytest.raises(OracleError, match="Predicate column 'id' is not of boolean type"):
+        StreamingPhysicalPlan.memory_source([b]).filter("id").collect()
+    with pytest.raises(OracleError, match="Column 'nonexistent' not found in schema"):
+        StreamingPhysicalPlan.memory_source([b]).select(["nonexistent"]).collect()
+    r = StreamingPhysicalPlan.memory_source([b]).filter("active").select(["name"]).collect_batches()[0]
+    assert (r.num_columns(), r.num_rows(), r.column_names()) == (1, 1, ["name"])
+    with pytest.raises(OracleError, match="Cannot create stream from empty batch list"):
+        StreamingPhysicalPlan.memory_source([]).collect()
+
+
+# ---------------------------------------------------------------- streaming_planner.rs (from DataFrame)
+def test_streaming_planner_conversions():  # streaming_planner.rs:212-329
+    df = df_name_age_active()
+    r = LazyFrame.from_dataframe(df).collect_streaming()
+    assert (r.num_rows(), r.num_columns()) == (3, 3)
+    r = LazyFrame.from_dataframe(df).select([col("name"), col("age")]).collect_streaming()
+    assert r.column_names() == ["name", "age"]
+    r = LazyFrame.from_dataframe(df).filter(col("active")).collect_streaming()
+    assert r.num_rows() == 2 and r.column(0).to_list() == ["Alice", "Charlie"]
+    r = LazyFrame.from_dataframe(df).limit(2).collect_streaming()
+    assert (r.num_rows(), r.num_columns()) == (2, 3)
+    r = LazyFrame.from_dataframe(df).filter(col("active")).select([col("name")]).limit(1).collect_streaming()
+    assert (r.num_rows(), r.num_columns(), r.column_names()) == (1, 1, ["name"])
+
+
+def test_streaming_planner_rejections():  # streaming_planner.rs:332-381
+    df = df_name_age_active()
+    with pytest.raises(OracleError, match="Expression conversion error"):
+        LazyFrame.from_dataframe(df).select([col("age").add(lit(10))]).collect_streaming()
+    with pytest.raises(OracleError, match="Binary expressions not yet supported"):
+        LazyFrame.from_dataframe(df).filter(col("age").gt(lit(30))).collect_streaming()
+
+
+def test_streaming_alias_dropped_and_null_flattening():  # streaming_planner.rs:110-113; streaming.rs:177,188,212
+    df = DataFrame.new([("name", ["a", None, "c"]), ("age", [1, None, 3]), ("x", [1.5, None, 2.5]), ("ok", [True, None, False])])
+    r = LazyFrame.from_dataframe(df).select([col("name"), col("age").alias("years"), col("x"), col("ok")]).collect_streaming()
+    assert r.column_names() == ["name", "age", "x", "ok"]
+    assert r.to_dict() == {"name": ["a", None, "c"], "age": [1, 0, 3], "x": [1.5, 0.0, 2.5], "ok": [True, False, False]}
+    assert r.column(1).validity is None and r.column(0).validity is not None
+
+
+def test_streaming_batches_of_1024():  # streaming_planner.rs:32 + streaming.rs:144-167
+    n = 2500
+    df = DataFrame.new([("i", list(range(n))), ("flag", [(i % 3 == 0) for i in range(n)])])
+    r = LazyFrame.from_dataframe(df).filter(col("flag")).limit(700).collect_streaming()
+    assert r.num_rows() == 700 and r.column(0).to_list() == [i for i in range(n) if i % 3 == 0][:700]
+
+
+# ---------------------------------------------------------------- not pinned by a reference test ("code reading")
+S1 = {  # (row, literal) -> {op: expected}
+    "null_vs_value": ((None, 30), {"==": False, "!=": True, "<": True, "<=": True, ">": False, ">=": False}),
+    "value_vs_null": ((30, None), {"==": False, "!=": True, "<": False, "<=": False, ">": True, ">=": True}),
+    "null_vs_null": ((None, None), {"==": True, "!=": False, "<": False, "<=": True, ">": False, ">=": True}),
+    "nan_row": ((float("nan"), 1.0), {"==": False, "!=": True, "<": False, "<=": False, ">": False, ">=": False}),
+    "nan_lit": ((1.0, float("nan")), {"==": False, "!=": True, "<": False, "<=": False, ">": False, ">=": False}),
+    "cross_type": ((30, 30.0), {"==": False, "!=": True, "<": False, "<=": False, ">": False, ">=": False}),
+    "neg_zero": ((-0.0, 0.0), {"==": True, "!=": False, "<": False, "<=": True, ">": False, ">=": True}),
+    "bool": ((False, True), {"==": False, "!=": True, "<": True, "<=": True, ">": False, ">=": False}),
+    "str_prefix": (("ab", "abc"), {"==": False, "!=": True, "<": True, "<=": True, ">": False, ">=": False}),
+}
+
+
+@pytest.mark.parametrize("case", sorted(S1))
+def test_truth_table_unpinned(case):  # plan.rs:114-120 over series.rs:87-117
+    (row, literal), exp = S1[case]
+    for op, want in exp.items():
+        assert O.eval_cmp(row, op, literal) is want, (case, op)
+
+
+def test_eager_nulls_dtype_collapse_and_empty_errors():  # SURVEY S2/S3 (plan.rs:140-143, 89-91, 167-169)
+    df = DataFrame.new([("age", [10, None, 30, None]), ("v", [None, None, 7, None])])
+    r = LazyFrame.from_dataframe(df).filter(col("age").lt(lit(20))).collect()     # null ages pass `<`
+    assert r.to_dict() == {"age": [10, None, None], "v": [None, None, None]}
+    assert r.dtypes() == ["Int64", "Null"]                                        # all-null survivors collapse to Null
+    with pytest.raises(OracleError, match="Execution error: Series error: Empty series not allowed"):
+        LazyFrame.from_dataframe(df).filter(col("age").gt(lit(100))).select([col("v")]).collect()
+    # ...but when the optimizer swaps Select below Filter (predicate column selected) the Select sees rows: no error
+    assert LazyFrame.from_dataframe(df).filter(col("age").gt(lit(100))).select([col("age")]).collect().height() == 0
+    with pytest.raises(OracleError, match="Execution error: Series error: Empty series not allowed"):
+        LazyFrame.from_dataframe(df).filter(col("age").gt(lit(100))).limit(5).collect()
+    assert LazyFrame.from_dataframe(df).filter(col("age").gt(lit(100))).limit(0).collect().height() == 0
+
+
+def test_fused_oracle_matches_eager_on_columnar_input():
+    # the fused-operator oracle (used to check the GPU kernel) agrees with the eager engine on the same data
+    rng = np.random.default_rng(7)
+    n = 300
+    k = [None if rng.random() < 0.2 else int(rng.integers(0, 50)) for _ in range(n)]
+    x = [None if rng.random() < 0.2 else float(rng.random()) for _ in range(n)]
+    s = [None if rng.random() < 0.2 else "s%d" % rng.integers(0, 99) for _ in range(n)]
+    df = DataFrame.new([("k", k), ("x", x), ("s", s)])
+    rb = RecordBatch.try_new(["k", "x", "s"], [Array.from_list(k, EX_INT64), Array.from_list(x, EX_FLOAT64), Array.from_list(s, EX_STRING)])
+    for op in ["==", "!=", "<", ">", "<=", ">="]:
+        for literal in (25, None, 25.0):
+            eager = LazyFrame.from_dataframe(df).filter(getattr(col("k"), {"==": "eq", "!=": "neq", "<": "lt", ">": "gt", "<=": "lte", ">=": "gte"}[op])(lit(literal))).collect()
+            fused = rb.filter_project_cmp(0, op, literal, [0, 1, 2])
+            assert fused.num_rows() == eager.height()
+            if eager.height():
+                assert fused.to_dict() == eager.to_dict(), (op, literal)

@@ -1,0 +1,212 @@
+/* rivulus_gpu.h — C ABI of the B200-native filter / project / limit path.
+ *
+ * This is the drop-in boundary: a Rust `-sys` crate (bindgen over this header), or the C++ host
+ * layer in rivulus_b200/host/, binds exactly these entry points.  The reference (CleConor/rivulus)
+ * has no FFI of its own; each entry point below names the Rust-level seam it replaces
+ * (file:line under /root/reference/src).  Conventions:
+ *
+ *   - every function returns an rvl_status (0 = OK); the message for the last failure on the calling
+ *     thread is rvl_last_error().  No exception, abort or panic crosses this boundary: the reference's
+ *     panics (slice/index out of bounds) become RVL_OUT_OF_BOUNDS.
+ *   - plain pointers and sizes only; buffers passed in are borrowed for the duration of the call and
+ *     never freed by the library; handles returned are owned by the caller and released explicitly.
+ *   - layouts are the reference's Arrow layouts: 8-byte values, LSB-first bitmaps where 1 = valid/true
+ *     (bitmap.rs:44-68), int32 string offsets (string.rs:8-16), (offset, length) views over whole
+ *     buffers (primitive.rs:107-117).
+ *   - there is NO CPU fallback: every data-path entry point runs hand-written sm_100a kernels and
+ *     fails with RVL_CUDA when no device is usable.
+ */
+#ifndef RIVULUS_GPU_H
+#define RIVULUS_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RVL_ABI_VERSION 1
+
+typedef enum rvl_status {
+    RVL_OK = 0,
+    RVL_COLUMN_NOT_FOUND = 1,  /* ExecutionError::ColumnNotFound   physical_plan/plan.rs:38 */
+    RVL_TYPE_MISMATCH = 2,     /* ExecutionError::TypeMismatch     physical_plan/plan.rs:44; "Predicate must be a BooleanArray" record_batch.rs:233 */
+    RVL_INVALID_OPERATION = 3, /* ExecutionError::InvalidOperation physical_plan/plan.rs:47 */
+    RVL_LENGTH_MISMATCH = 4,   /* record_batch.rs:33-38, 223-227 */
+    RVL_SCHEMA_MISMATCH = 5,   /* record_batch.rs:253; StreamError::SchemaMismatch stream.rs:12 */
+    RVL_OUT_OF_BOUNDS = 6,     /* replaces the panics at record_batch.rs:93, primitive.rs:49,108 */
+    RVL_OFFSET_OVERFLOW = 7,   /* new: int32 string offsets would wrap (string.rs:31,35 wraps silently) */
+    RVL_CUDA = 8,              /* new: CUDA runtime / launch failure */
+    RVL_INVALID_ARGUMENT = 9,
+    RVL_OUT_OF_MEMORY = 10
+} rvl_status;
+
+/* execution/schema.rs:1-8 — declaration order */
+typedef enum rvl_dtype { RVL_NULL = 0, RVL_BOOLEAN = 1, RVL_INT64 = 2, RVL_FLOAT64 = 3, RVL_STRING = 4 } rvl_dtype;
+
+/* expressions/expr.rs:15-29 — declaration order */
+typedef enum rvl_op {
+    RVL_OP_PLUS = 0, RVL_OP_MINUS = 1, RVL_OP_MULTIPLY = 2, RVL_OP_DIVIDE = 3,
+    RVL_OP_EQ = 4, RVL_OP_NOTEQ = 5, RVL_OP_LT = 6, RVL_OP_GT = 7, RVL_OP_LTEQ = 8, RVL_OP_GTEQ = 9,
+    RVL_OP_AND = 10, RVL_OP_OR = 11
+} rvl_op;
+
+typedef enum rvl_location { RVL_HOST = 0, RVL_DEVICE = 1 } rvl_location;
+
+/* One column = the raw buffers of a PrimitiveArray<i64|f64> (primitive.rs:20-28), BooleanArray
+ * (boolean.rs:9-16), StringArray (string.rs:8-16) or NullArray (null.rs:5-9).  Row i of the view is
+ * element (offset + i) of every buffer.  All buffers of one column live in the same `location`. */
+typedef struct rvl_column {
+    int32_t dtype;           /* rvl_dtype */
+    int32_t location;        /* rvl_location of the buffers below */
+    int64_t length;          /* rows in the view */
+    int64_t offset;          /* first row of the view inside the buffers */
+    const void* values;      /* Int64/Float64: 8-byte values; Boolean: LSB-first value bitmap; else NULL */
+    const uint8_t* validity; /* LSB-first, 1 = valid; NULL = no nulls (the reference drops all-valid bitmaps) */
+    const int32_t* offsets;  /* String: offset+length+1 entries reachable */
+    const uint8_t* data;     /* String bytes */
+    int64_t data_len;        /* String: bytes in `data` */
+    int64_t null_count;      /* filled by the library on views it returns; ignored on input */
+} rvl_column;
+
+typedef enum rvl_pred_mode {
+    RVL_PRED_CMP_LITERAL = 0,   /* eager engine: column <op> literal, truth table of plan.rs:112-130 over series.rs:87-117 */
+    RVL_PRED_BOOL_COLUMN = 1,   /* streaming engine: keep rows where the Boolean column is Some(true), record_batch.rs:235-240 */
+    RVL_PRED_TRUE = 2           /* no filter (Select / Limit only) */
+} rvl_pred_mode;
+
+/* PhysicalPlan::Filter { column, value: AnyValue, op } (physical_plan/plan.rs:17-22) or
+ * FilterStream { predicate_column } (stream.rs:117-120), by column index. */
+typedef struct rvl_predicate {
+    int32_t mode;       /* rvl_pred_mode */
+    int32_t column;     /* index into the input batch */
+    int32_t op;         /* rvl_op, one of EQ..GTEQ (CMP_LITERAL only) */
+    int32_t lit_dtype;  /* rvl_dtype of the literal AnyValue; RVL_NULL = AnyValue::Null */
+    int64_t lit_i64;
+    double lit_f64;
+    const uint8_t* lit_str; /* host pointer, not NUL-terminated */
+    int64_t lit_str_len;
+    int32_t lit_bool;
+    int32_t reserved;
+} rvl_predicate;
+
+typedef struct rvl_ctx rvl_ctx;       /* one per GPU: stream, memory pool, scratch, pinned mailbox */
+typedef struct rvl_batch rvl_batch;   /* device-resident RecordBatch (record_batch.rs:8-13); immutable, ref-counted buffers */
+typedef struct rvl_stream rvl_stream; /* device pipeline behind trait DataStream (stream.rs:25-54) */
+
+/* ---- library ---------------------------------------------------------------------------- */
+int32_t rvl_abi_version(void);
+const char* rvl_last_error(void);
+int32_t rvl_device_count(int32_t* count);
+
+/* ---- context ---------------------------------------------------------------------------- */
+int32_t rvl_ctx_create(int32_t device, rvl_ctx** ctx);
+int32_t rvl_ctx_destroy(rvl_ctx* ctx);
+int32_t rvl_ctx_synchronize(rvl_ctx* ctx);
+/* the cudaStream_t every kernel of this context is launched on (so callers can time with CUDA events on it) */
+int32_t rvl_ctx_cuda_stream(rvl_ctx* ctx, void** cuda_stream);
+int32_t rvl_ctx_device(rvl_ctx* ctx, int32_t* device);
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+int32_t rvl_ctx_launch_count(rvl_ctx* ctx, int64_t* launches);
+/* Kernel-level timing of the fused filter/project kernel: when enabled, every launch of that kernel is
+ * bracketed by CUDA events on the context stream.  read() waits for the recorded launches, returns their
+ * summed device time and count, and resets the accumulators (bench.py's roofline figure). */
+int32_t rvl_ctx_profile_enable(rvl_ctx* ctx, int32_t enable);
+int32_t rvl_ctx_profile_read(rvl_ctx* ctx, double* fused_kernel_ms, int64_t* fused_launches);
+/* per-launch device times (ms, launch order) recorded since the last read; resets like profile_read */
+int32_t rvl_ctx_profile_read_launches(rvl_ctx* ctx, double* ms_out, int64_t cap, int64_t* n);
+
+/* pinned host memory for the H2D/D2H staging of the streaming path (execution: pinned double-buffering) */
+int32_t rvl_host_alloc(size_t bytes, void** ptr);
+int32_t rvl_host_free(void* ptr);
+
+/* ---- batches: RecordBatch (record_batch.rs) --------------------------------------------- */
+/* RecordBatch::try_new (record_batch.rs:16-58) over borrowed host or device buffers: copies the viewed
+ * window to the device (async on the context stream) and keeps the sub-64-row residual offset. */
+int32_t rvl_batch_upload(rvl_ctx* ctx, const rvl_column* cols, int32_t ncols, rvl_batch** out);
+/* wrap caller-owned DEVICE buffers without copying (caller keeps them alive and unmodified) */
+int32_t rvl_batch_wrap_device(rvl_ctx* ctx, const rvl_column* cols, int32_t ncols, rvl_batch** out);
+int32_t rvl_batch_release(rvl_batch* batch);
+int32_t rvl_batch_num_rows(const rvl_batch* batch, int64_t* rows);       /* record_batch.rs:72 */
+int32_t rvl_batch_num_columns(const rvl_batch* batch, int32_t* ncols);  /* record_batch.rs:76 */
+/* device-side view of column i (pointers are DEVICE pointers, valid while the batch lives) */
+int32_t rvl_batch_column(const rvl_batch* batch, int32_t i, rvl_column* view);
+/* copy column i to caller-provided HOST buffers described by `dst` (same dtype; buffers sized from the view:
+ * values length*8 bytes (or ceil(length/8) for Boolean), validity ceil(length/8) if the view has one, offsets
+ * (length+1)*4, data data_len).  The copy is rebased to offset 0 like the reference's freshly built outputs. */
+int32_t rvl_batch_download_column(rvl_ctx* ctx, const rvl_batch* batch, int32_t i, rvl_column* dst);
+
+/* RecordBatch::slice (record_batch.rs:92-106): zero-copy view; RVL_OUT_OF_BOUNDS instead of the panic */
+int32_t rvl_batch_slice(const rvl_batch* batch, int64_t offset, int64_t length, rvl_batch** view);
+/* RecordBatch::select_columns (record_batch.rs:180-206): zero-copy column pick */
+int32_t rvl_batch_select(const rvl_batch* batch, const int32_t* indices, int32_t n, rvl_batch** view);
+/* RecordBatch::concat (record_batch.rs:245-342): freshly built output, offset 0, bitmap iff nulls */
+int32_t rvl_batch_concat(rvl_ctx* ctx, const rvl_batch* const* batches, int32_t n, rvl_batch** out);
+
+/* ---- the hot path ----------------------------------------------------------------------- */
+/* Fused Filter + Select + Limit:
+ *   eager     PhysicalPlan::execute Filter/Select/Limit arms     physical_plan/plan.rs:68-173
+ *   streaming FilterStream/SelectStream/LimitStream::next_batch  stream.rs:136-162,202-212; streaming.rs:268-287
+ *             = RecordBatch::filter -> take -> take_array         record_batch.rs:221-243,108-178
+ * One pass: predicate -> warp ballot/popc -> block scan -> decoupled look-back -> ordered compaction of every
+ * projected column (values, validity and Boolean bitmaps; strings in a second kernel pair).
+ * limit < 0 = no limit.  Output arrays are freshly built (offset 0, placeholder 0 under nulls, validity
+ * present iff at least one surviving row is null), exactly as the reference's builders leave them. */
+int32_t rvl_filter_project(rvl_ctx* ctx, const rvl_batch* in, const rvl_predicate* pred, const int32_t* proj,
+                           int32_t nproj, int64_t limit, rvl_batch** out);
+
+/* Standalone predicate -> BooleanArray-layout selection mask (the K1 kernel on its own): bit i = row i kept. */
+int32_t rvl_predicate_mask(rvl_ctx* ctx, const rvl_batch* in, const rvl_predicate* pred, rvl_batch** mask_out);
+
+/* Same, split in two so a caller can time / graph-capture the device work without the final readback:
+ * launch() enqueues everything on the context stream; finish() waits and builds the output batch. */
+typedef struct rvl_pending rvl_pending;
+int32_t rvl_filter_project_launch(rvl_ctx* ctx, const rvl_batch* in, const rvl_predicate* pred, const int32_t* proj,
+                                  int32_t nproj, int64_t limit, rvl_pending** pending);
+int32_t rvl_filter_project_finish(rvl_ctx* ctx, rvl_pending* pending, rvl_batch** out);
+
+/* ---- streaming executor: trait DataStream (stream.rs:25-54) ------------------------------ */
+typedef struct rvl_stream_config {
+    int64_t batch_rows; /* capacity of one staging slot, rows */
+    int32_t n_staging;  /* pinned/device staging slots (>= 2 for H2D / compute overlap) */
+    int32_t reserved;
+} rvl_stream_config;
+
+/* Opens Filter -> Select -> Limit over batches with the given input schema (dtypes of the pushed columns). */
+int32_t rvl_stream_open(rvl_ctx* ctx, const int32_t* dtypes, int32_t ncols, const rvl_predicate* pred,
+                        const int32_t* proj, int32_t nproj, int64_t limit, const rvl_stream_config* cfg,
+                        rvl_stream** stream);
+/* Feed one HOST batch (MemoryStream::next_batch upstream, stream.rs:105-113).  Asynchronous: H2D on the copy
+ * stream of a free staging slot, fused kernel on the compute stream.  *accepted = 0 when the LIMIT has already
+ * been reached and the batch was not transferred (LimitStream's early termination, streaming.rs:269-271). */
+int32_t rvl_stream_push(rvl_stream* stream, const rvl_column* host_cols, int32_t ncols, int32_t* accepted);
+/* next_batch() -> Option<RecordBatch>: *has_batch = 0 when no finished output batch is pending. */
+int32_t rvl_stream_next(rvl_stream* stream, rvl_batch** out, int32_t* has_batch);
+int32_t rvl_stream_limit_reached(rvl_stream* stream, int32_t* reached);
+/* DataStream::concatenate / collect_stream_batches (stream.rs:41-53, streaming.rs:343-352) */
+int32_t rvl_stream_collect(rvl_stream* stream, rvl_batch** out);
+int32_t rvl_stream_stats(rvl_stream* stream, int64_t* batches_pushed, int64_t* batches_skipped, int64_t* h2d_bytes);
+int32_t rvl_stream_close(rvl_stream* stream);
+
+/* ---- multi-GPU: contiguous row ranges, no collective ---------------------- */
+/* rows [begin, end) of shard `rank` of `world` for an n_rows table; boundaries are multiples of 64 rows */
+int32_t rvl_shard_range(int64_t n_rows, int32_t rank, int32_t world, int64_t* begin, int64_t* end);
+/* per-shard contributions to an ordered result under a global LIMIT: take[g] = clamp(limit - sum_{j<g} counts[j], 0, counts[g]) */
+int32_t rvl_shard_limit_split(const int64_t* counts, int32_t world, int64_t limit, int64_t* take);
+/* one fused call per context (each on its own GPU/stream), all in flight together; outs[g] are in row order */
+int32_t rvl_filter_project_sharded(rvl_ctx* const* ctxs, int32_t n, const rvl_batch* const* shards,
+                                   const rvl_predicate* pred, const int32_t* proj, int32_t nproj, int64_t limit,
+                                   rvl_batch** outs, int64_t* counts);
+
+/* ---- synthetic tables and checksums (bench / test support; include/rivulus_synth.h) ------ */
+/* generate rows [row0, row0+n) of synthetic column (kind, col_id) on the device */
+int32_t rvl_gen_batch(rvl_ctx* ctx, const int32_t* kinds, const uint32_t* col_ids, const uint32_t* null_pct,
+                      int32_t ncols, uint64_t row0, int64_t n, rvl_batch** out);
+/* order-sensitive checksum of column i (values under validity; nulls hash as a fixed tag): rivulus_synth.h */
+int32_t rvl_batch_checksum(rvl_ctx* ctx, const rvl_batch* batch, int32_t i, uint64_t* checksum);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RIVULUS_GPU_H */

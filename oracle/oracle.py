@@ -596,3 +596,19 @@ def time_eager_filter_select_mt(dfs: Sequence[DataFrame], pred_col: str, op: str
     if secs < 0:
         raise OracleError(lib().orc_last_error().decode())
     return secs, rows.value
+
+
+def synth_filter_checksums(n: int, row0: int, pred_kind: int, pred_col_id: int, op: str, literal, proj: Sequence[tuple],
+                           threads: int = 0, limit: int = -1):
+    """(count, [checksum per projected (kind, col_id)]) of the filtered synthetic table, straight from the generator."""
+    if threads <= 0:
+        threads = os.cpu_count() or 1
+    t, i, f, s, sl, b = _lit_args(literal)
+    kinds = (C.c_int * max(len(proj), 1))(*[p[0] for p in proj])
+    ids = (C.c_uint32 * max(len(proj), 1))(*[p[1] for p in proj])
+    count = C.c_int64()
+    sums = (C.c_uint64 * max(len(proj), 1))()
+    _check(lib().orc_synth_filter_checksums(C.c_int64(n), C.c_uint64(row0), pred_kind, C.c_uint32(pred_col_id), OPS[op], t,
+                                            C.c_int64(i), C.c_double(f), len(proj), kinds, ids, threads, C.c_int64(limit),
+                                            C.byref(count), sums))
+    return count.value, [sums[k] for k in range(len(proj))]

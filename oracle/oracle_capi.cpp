@@ -395,3 +395,69 @@ double orc_time_eager_filter_select_mt(void** dfs, int threads, const char* pred
 }
 
 }  // extern "C"
+
+// ----------------------------------------------------------------------------------- full-size property oracle
+// Survivor count and order-sensitive per-column checksums (include/rivulus_synth.h: rvl_checksum_term over the
+// survivor's value bits at its output rank) of  filter(pred_col <op> literal).select(proj...)  over rows
+// [row0, row0+n) of a synthetic no-null table, computed straight from the generator without materialising it.
+// The predicate goes through eval_cmp (plan.rs:114-120) on AnyValues, like the eager engine.
+extern "C" int orc_synth_filter_checksums(int64_t n, uint64_t row0, int pred_kind, uint32_t pred_col_id, int op, int lit_tag,
+                                          int64_t lit_i, double lit_f, int nproj, const int* kinds, const uint32_t* col_ids,
+                                          int threads, int64_t limit, int64_t* count_out, uint64_t* checksums_out) {
+    return guard([&] {
+        if (threads < 1) threads = 1;
+        const AnyValue lit = lit_tag == 1 ? AnyValue::Int64(lit_i) : AnyValue::Float64(lit_f);
+        auto keep = [&](uint64_t row) {
+            const uint64_t u = rvl_synth_u(RVL_SYNTH_SEED, pred_col_id, row);
+            if (pred_kind == RVL_SYNTH_F64) return eval_cmp(AnyValue::Float64(rvl_synth_f64(u)), (BinaryOperator)op, lit);
+            if (pred_kind == RVL_SYNTH_BOOL) return eval_cmp(AnyValue::Boolean((u & 1) != 0), (BinaryOperator)op, lit);
+            return eval_cmp(AnyValue::Int64(rvl_synth_i64(u, pred_kind)), (BinaryOperator)op, lit);
+        };
+        std::vector<int64_t> counts((size_t)threads, 0);
+        const int64_t per = (n + threads - 1) / threads;
+        {
+            std::vector<std::thread> th;
+            for (int t = 0; t < threads; ++t)
+                th.emplace_back([&, t] {
+                    const int64_t b = std::min<int64_t>(n, per * t), e = std::min<int64_t>(n, per * (t + 1));
+                    int64_t c = 0;
+                    for (int64_t r = b; r < e; ++r) c += keep(row0 + (uint64_t)r) ? 1 : 0;
+                    counts[(size_t)t] = c;
+                });
+            for (auto& x : th) x.join();
+        }
+        std::vector<int64_t> prefix((size_t)threads + 1, 0);
+        for (int t = 0; t < threads; ++t) prefix[(size_t)t + 1] = prefix[(size_t)t] + counts[(size_t)t];
+        const int64_t total = prefix[(size_t)threads];
+        const int64_t cap = limit >= 0 ? std::min(limit, total) : total;
+        std::vector<std::vector<uint64_t>> sums((size_t)threads, std::vector<uint64_t>((size_t)nproj, 0));
+        {
+            std::vector<std::thread> th;
+            for (int t = 0; t < threads; ++t)
+                th.emplace_back([&, t] {
+                    const int64_t b = std::min<int64_t>(n, per * t), e = std::min<int64_t>(n, per * (t + 1));
+                    int64_t rank = prefix[(size_t)t];
+                    for (int64_t r = b; r < e && rank < cap; ++r) {
+                        const uint64_t row = row0 + (uint64_t)r;
+                        if (!keep(row)) continue;
+                        for (int c = 0; c < nproj; ++c) {
+                            const uint64_t u = rvl_synth_u(RVL_SYNTH_SEED, col_ids[c], row);
+                            uint64_t bits;
+                            if (kinds[c] == RVL_SYNTH_F64) { const double d = rvl_synth_f64(u); std::memcpy(&bits, &d, 8); }
+                            else if (kinds[c] == RVL_SYNTH_BOOL) bits = u & 1ull;
+                            else bits = (uint64_t)rvl_synth_i64(u, kinds[c]);
+                            sums[(size_t)t][(size_t)c] += rvl_checksum_term(bits, (uint64_t)rank);
+                        }
+                        ++rank;
+                    }
+                });
+            for (auto& x : th) x.join();
+        }
+        *count_out = cap;
+        for (int c = 0; c < nproj; ++c) {
+            uint64_t s = 0;
+            for (int t = 0; t < threads; ++t) s += sums[(size_t)t][(size_t)c];
+            checksums_out[c] = s;
+        }
+    });
+}

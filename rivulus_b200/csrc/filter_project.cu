@@ -1,0 +1,427 @@
+// filter_project.cu — host side of the fused Filter + Select + Limit operator: lowers an rvl_predicate to a
+// kernel predicate plan (the eager truth table of physical_plan/plan.rs:112-130 over datatypes/series.rs:87-117,
+// or the streaming mask rule of execution/record_batch.rs:235-240), sizes the outputs, launches the kernels of
+// fused_filter.cuh / string_kernels.cuh on the context stream and builds the output RecordBatch.
+#include <algorithm>
+#include <cstring>
+
+#include "aux_kernels.cuh"
+#include "filter_project.cuh"
+#include "fused_filter.cuh"
+#include "string_kernels.cuh"
+
+namespace rvl {
+
+// truth masks over {bit0: value < literal, bit1: ==, bit2: >, bit3: unordered/incomparable}
+static uint32_t truth_of(int op) {
+    switch (op) {
+        case RVL_OP_EQ: return 0x2u;     // ==  (PartialEq, series.rs:87-98)
+        case RVL_OP_NOTEQ: return 0xDu;  // !=  true for <, > and incomparable (NaN, cross-type)
+        case RVL_OP_LT: return 0x1u;     // partial_cmp == Some(Less)
+        case RVL_OP_GT: return 0x4u;
+        case RVL_OP_LTEQ: return 0x3u;
+        case RVL_OP_GTEQ: return 0x6u;
+        default: return 0u;
+    }
+}
+
+struct PredPlan {
+    int kind = kPredTrue;
+    uint32_t truth = 0, keep_null = 0, pb_a = 0, pb_b = 0;
+    int64_t lit_bits = 0;
+    const uint64_t* values = nullptr;
+    int vec_ok = 0;
+    BitSrc valid{nullptr, 0, 0};
+    BitSrc pb_vals{nullptr, 0, 0};
+    BufRef tmp_bits;  // string-compare result bitmap
+    BufRef tmp_lit;
+};
+
+static int lower_predicate(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pred, PredPlan* pp) {
+    const int64_t n = in->num_rows;
+    if (pred == nullptr || pred->mode == RVL_PRED_TRUE) { pp->kind = kPredTrue; return RVL_OK; }
+    if (pred->column < 0 || pred->column >= (int32_t)in->cols.size())
+        return fail(RVL_COLUMN_NOT_FOUND, "Column not found: index " + std::to_string(pred->column));
+    const DevColumn& c = in->cols[pred->column];
+    pp->valid = bitsrc_of(c.validity, c.offset, n);
+
+    if (pred->mode == RVL_PRED_BOOL_COLUMN) {
+        // FilterStream: keep only Some(true) (stream.rs:147-153, record_batch.rs:235-240)
+        if (c.dtype != RVL_BOOLEAN) return fail(RVL_TYPE_MISMATCH, "Predicate column is not of boolean type");
+        pp->kind = kPredBits; pp->pb_vals = bitsrc_of(c.values, c.offset, n); pp->pb_a = 1; pp->pb_b = 0; pp->keep_null = 0;
+        return RVL_OK;
+    }
+    if (pred->mode != RVL_PRED_CMP_LITERAL) return fail(RVL_INVALID_ARGUMENT, "unknown predicate mode");
+    const uint32_t truth = truth_of(pred->op);
+    if (truth == 0u) return fail(RVL_INVALID_OPERATION, "Invalid operation: operator " + std::to_string(pred->op) + " is not a comparison");  // plan.rs:121-127
+
+    // constant result on valid rows / on null rows, per the truth table
+    auto constant = [&](uint32_t on_valid, uint32_t on_null) {
+        pp->kind = kPredBits; pp->pb_vals = BitSrc{nullptr, 0, 0}; pp->pb_a = 0; pp->pb_b = on_valid; pp->keep_null = on_null;
+        if (c.dtype == RVL_NULL) { pp->valid = BitSrc{nullptr, 0, 0}; pp->pb_b = on_null; }  // NullArray: every row is null
+        return RVL_OK;
+    };
+    if (pred->lit_dtype == RVL_NULL) {
+        // value vs Null: Greater (series.rs:107); Null vs Null: Equal (:105)
+        return constant((truth >> 2) & 1u, (truth >> 1) & 1u);
+    }
+    const uint32_t null_row = truth & 1u;  // Null vs non-null literal: Less (series.rs:106)
+    if (c.dtype == RVL_NULL || c.dtype != pred->lit_dtype) {
+        // different non-null types never compare (series.rs:95,114): only != holds
+        return constant((truth >> 3) & 1u, null_row);
+    }
+    pp->keep_null = null_row;
+    pp->truth = truth;
+    switch (c.dtype) {
+        case RVL_INT64:
+        case RVL_FLOAT64: {
+            pp->kind = c.dtype == RVL_INT64 ? kPredI64 : kPredF64;
+            pp->values = (const uint64_t*)c.values->ptr + c.offset;
+            pp->vec_ok = (reinterpret_cast<uintptr_t>(pp->values) & 15) == 0;
+            if (c.dtype == RVL_INT64) pp->lit_bits = pred->lit_i64;
+            else std::memcpy(&pp->lit_bits, &pred->lit_f64, 8);
+            return RVL_OK;
+        }
+        case RVL_BOOLEAN: {
+            // false < true (series.rs:112): evaluate the op for value=false and value=true, fold into (vals & a) ^ b
+            const int lit = pred->lit_bool ? 1 : 0;
+            auto code = [&](int v) { return v < lit ? 1u : (v == lit ? 2u : 4u); };
+            const uint32_t keep_f = (truth & code(0)) ? 1u : 0u, keep_t = (truth & code(1)) ? 1u : 0u;
+            pp->kind = kPredBits; pp->pb_vals = bitsrc_of(c.values, c.offset, n);
+            if (keep_t && !keep_f) { pp->pb_a = 1; pp->pb_b = 0; }
+            else if (!keep_t && keep_f) { pp->pb_a = 1; pp->pb_b = 1; }
+            else { pp->pb_a = 0; pp->pb_b = keep_t; }
+            return RVL_OK;
+        }
+        case RVL_STRING: {
+            if (pred->lit_str_len < 0 || pred->lit_str_len > INT32_MAX) return fail(RVL_INVALID_ARGUMENT, "bad string literal length");
+            RVL_TRY(dev_alloc(core, (size_t)pred->lit_str_len + 1, &pp->tmp_lit));
+            if (pred->lit_str_len > 0)
+                RVL_CUDA_TRY(cudaMemcpyAsync(pp->tmp_lit->ptr, pred->lit_str, (size_t)pred->lit_str_len, cudaMemcpyHostToDevice, core->stream));
+            RVL_TRY(dev_alloc_zeroed(core, (size_t)((n + 63) / 64) * 8, &pp->tmp_bits));
+            if (n > 0) {
+                string_predicate_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, core->stream>>>(
+                    n, (const int32_t*)c.offsets->ptr + c.offset, (const uint8_t*)c.data->ptr, (const uint8_t*)pp->tmp_lit->ptr,
+                    (int32_t)pred->lit_str_len, truth, (uint32_t*)pp->tmp_bits->ptr);
+                core->launches++;
+                RVL_CUDA_TRY(cudaGetLastError());
+            }
+            pp->kind = kPredBits; pp->pb_vals = bitsrc_of(pp->tmp_bits, 0, n); pp->pb_a = 1; pp->pb_b = 0;
+            return RVL_OK;
+        }
+        default: return fail(RVL_INVALID_ARGUMENT, "bad dtype");
+    }
+}
+
+static void launch_fused(const CoreRef& core, int kind, const FusedParams& fp, int64_t tiles) {
+    const dim3 grid((unsigned)tiles), block(kBlock);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (core->profile) {
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, core->stream);
+    }
+    switch (kind) {
+        case kPredI64: fused_filter_project_kernel<kPredI64><<<grid, block, 0, core->stream>>>(fp); break;
+        case kPredF64: fused_filter_project_kernel<kPredF64><<<grid, block, 0, core->stream>>>(fp); break;
+        case kPredBits: fused_filter_project_kernel<kPredBits><<<grid, block, 0, core->stream>>>(fp); break;
+        default: fused_filter_project_kernel<kPredTrue><<<grid, block, 0, core->stream>>>(fp); break;
+    }
+    if (core->profile) {
+        cudaEventRecord(e1, core->stream);
+        core->prof_events.emplace_back(e0, e1);
+    }
+    core->launches++;
+}
+
+int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pred, const int32_t* proj, int32_t nproj,
+              int64_t limit, bool want_mask, const unsigned long long* base_in, unsigned long long* total_ext, FpPending** out) {
+    if (!in || !out || (nproj > 0 && !proj)) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    if (in->core->device != core->device) return fail(RVL_INVALID_ARGUMENT, "batch lives on another device than the context");
+    RVL_CUDA_TRY(cudaSetDevice(core->device));
+    for (int i = 0; i < nproj; ++i)
+        if (proj[i] < 0 || proj[i] >= (int32_t)in->cols.size())
+            return fail(RVL_OUT_OF_BOUNDS, "Column index " + std::to_string(proj[i]) + " out of bounds for " + std::to_string(in->cols.size()) + " columns");
+    const int64_t n = in->num_rows;
+    if (limit < 0) limit = -1;
+    const int64_t cap = limit >= 0 ? std::min(n, limit) : n;
+    const int64_t tiles = (n + kTileRows - 1) / kTileRows;
+
+    auto pend = std::make_unique<FpPending>();
+    pend->core = core; pend->n = n; pend->limit = limit; pend->n_launched = 0;
+    PredPlan pp;
+    RVL_TRY(lower_predicate(core, in, pred, &pp));
+    pend->temps.push_back(pp.tmp_bits); pend->temps.push_back(pp.tmp_lit);
+
+    // ---- outputs + work lists
+    std::vector<Col8> col8s;
+    std::vector<BitCol> bitcols;
+    struct StrJob { int out_index; const DevColumn* src; };
+    std::vector<StrJob> strjobs;
+    pend->outs.resize((size_t)nproj);
+    pend->validity_counter.assign((size_t)nproj, -1);
+    pend->bytes_counter.assign((size_t)nproj, -1);
+    int n_counters = 1;  // [0] = total rows
+    for (int j = 0; j < nproj; ++j) {
+        const DevColumn& s = in->cols[proj[j]];
+        DevColumn& d = pend->outs[(size_t)j];
+        d.dtype = s.dtype; d.offset = 0; d.length = 0;
+        const BitSrc sv = bitsrc_of(s.validity, s.offset, n);
+        if (s.validity && s.dtype != RVL_NULL) {
+            RVL_TRY(dev_alloc_zeroed(core, (size_t)(cap + 7) / 8 + 8, &d.validity));
+            bitcols.push_back(BitCol{sv, BitSrc{nullptr, 0, 0}, (uint32_t*)d.validity->ptr});
+            pend->validity_counter[(size_t)j] = n_counters++;
+        }
+        if (s.dtype == RVL_INT64 || s.dtype == RVL_FLOAT64) {
+            RVL_TRY(dev_alloc(core, (size_t)cap * 8, &d.values));
+            Col8 c8{};
+            c8.in = (const uint64_t*)s.values->ptr + s.offset; c8.out = (uint64_t*)d.values->ptr; c8.valid = sv;
+            c8.vec_ok = (reinterpret_cast<uintptr_t>(c8.in) & 15) == 0;
+            col8s.push_back(c8);
+        } else if (s.dtype == RVL_BOOLEAN) {
+            RVL_TRY(dev_alloc_zeroed(core, (size_t)(cap + 7) / 8 + 8, &d.values));
+            bitcols.push_back(BitCol{bitsrc_of(s.values, s.offset, n), sv, (uint32_t*)d.values->ptr});
+        } else if (s.dtype == RVL_STRING) {
+            RVL_TRY(dev_alloc(core, (size_t)(cap + 1) * 4, &d.offsets));
+            RVL_CUDA_TRY(cudaMemsetAsync(d.offsets->ptr, 0, 4, core->stream));
+            // survivors' bytes are a subset of the viewed window; size for the whole buffer
+            RVL_TRY(dev_alloc(core, (size_t)s.data_len, &d.data));
+            strjobs.push_back(StrJob{j, &s});
+            pend->bytes_counter[(size_t)j] = n_counters++;
+        }
+    }
+    RVL_TRY(dev_alloc_zeroed(core, (size_t)(n_counters + 2) * 8, &pend->counters));
+    unsigned long long* dctr = (unsigned long long*)pend->counters->ptr;
+    pend->n_counters = n_counters;
+    // done flag lives right behind the counters
+    uint32_t* done_flag = (uint32_t*)(dctr + n_counters);
+
+    if (n > 0) {
+        const int launches_needed = std::max<int>(1, std::max<int>(((int)col8s.size() + kMaxCol8 - 1) / kMaxCol8, ((int)bitcols.size() + kMaxBitCols - 1) / kMaxBitCols));
+        const bool need_sel = want_mask || !strjobs.empty() || launches_needed > 1;
+        BufRef status, sel, tile_prefix;
+        RVL_TRY(dev_alloc_zeroed(core, (size_t)tiles * 8 * (size_t)launches_needed, &status));
+        pend->temps.push_back(status);
+        if (need_sel) {
+            RVL_TRY(dev_alloc_zeroed(core, (size_t)((n + 63) / 64) * 8, &sel));
+            if (want_mask) pend->mask = sel; else pend->temps.push_back(sel);
+        }
+        if (!strjobs.empty()) { RVL_TRY(dev_alloc(core, (size_t)tiles * 8, &tile_prefix)); pend->temps.push_back(tile_prefix); }
+
+        for (int L = 0; L < launches_needed; ++L) {
+            FusedParams fp{};
+            fp.n_rows = n; fp.limit = limit;
+            int kind = pp.kind;
+            if (L == 0) {
+                fp.pred_values = pp.values; fp.lit_bits = pp.lit_bits; fp.pred_valid = pp.valid; fp.truth = pp.truth;
+                fp.keep_null = pp.keep_null; fp.pred_vec_ok = pp.vec_ok; fp.pb_a = pp.pb_a; fp.pb_b = pp.pb_b; fp.pb_vals = pp.pb_vals;
+                fp.sel_out = need_sel ? (uint32_t*)sel->ptr : nullptr;
+                fp.tile_prefix_out = tile_prefix ? (uint64_t*)tile_prefix->ptr : nullptr;
+                fp.total_out = dctr;
+            } else {
+                // further column groups replay the selection bitmap written by the first launch
+                kind = kPredBits;
+                fp.pb_vals = bitsrc_of(sel, 0, n); fp.pb_a = 1; fp.pb_b = 0; fp.keep_null = 0; fp.pred_valid = BitSrc{nullptr, 0, 0};
+                fp.total_out = dctr + n_counters + 1;  // scratch word
+            }
+            fp.base_in = base_in;
+            fp.done_flag = done_flag;
+            fp.tile_status = (uint64_t*)status->ptr + (size_t)L * (size_t)tiles;
+            const int c0 = L * kMaxCol8, c1 = std::min<int>((int)col8s.size(), c0 + kMaxCol8);
+            fp.n_col8 = std::max(0, c1 - c0);
+            for (int k = 0; k < fp.n_col8; ++k) fp.col8[k] = col8s[(size_t)(c0 + k)];
+            const int b0 = L * kMaxBitCols, b1 = std::min<int>((int)bitcols.size(), b0 + kMaxBitCols);
+            fp.n_bits = std::max(0, b1 - b0);
+            for (int k = 0; k < fp.n_bits; ++k) fp.bits[k] = bitcols[(size_t)(b0 + k)];
+            if (L > 0 && limit >= 0) RVL_CUDA_TRY(cudaMemsetAsync(done_flag, 0, 4, core->stream));
+            launch_fused(core, kind, fp, tiles);
+            RVL_CUDA_TRY(cudaGetLastError());
+        }
+
+        // strings: second kernel pair per column (offset prefix-sum + byte copy)
+        for (const StrJob& job : strjobs) {
+            const DevColumn& s = *job.src;
+            DevColumn& d = pend->outs[(size_t)job.out_index];
+            BufRef sstatus;
+            RVL_TRY(dev_alloc_zeroed(core, (size_t)tiles * 8, &sstatus));
+            pend->temps.push_back(sstatus);
+            StrGatherParams sp{};
+            sp.n_rows = n; sp.limit = limit; sp.sel = (const uint32_t*)sel->ptr; sp.tile_prefix = (const uint64_t*)tile_prefix->ptr; sp.row_base = 0;
+            sp.offsets = (const int32_t*)s.offsets->ptr + s.offset; sp.data = (const uint8_t*)s.data->ptr;
+            sp.valid = bitsrc_of(s.validity, s.offset, n);
+            sp.out_offsets = (int32_t*)d.offsets->ptr; sp.out_data = (uint8_t*)d.data->ptr;
+            sp.tile_status = (uint64_t*)sstatus->ptr; sp.byte_base_in = nullptr; sp.row_base_in = base_in;
+            sp.bytes_total_out = dctr + pend->bytes_counter[(size_t)job.out_index];
+            string_gather_kernel<<<(unsigned)tiles, kBlock, 0, core->stream>>>(sp);
+            core->launches++;
+            RVL_CUDA_TRY(cudaGetLastError());
+        }
+
+        // null counts of the compacted validity bitmaps (device-side row count, no host round trip)
+        for (int j = 0; j < nproj; ++j) {
+            if (pend->validity_counter[(size_t)j] < 0) continue;
+            DevColumn& d = pend->outs[(size_t)j];
+            count_ones_kernel<<<std::max<int>(1, (int)std::min<int64_t>((cap / 32 + 255) / 256, core->sm_count * 8)), 256, 0, core->stream>>>(
+                bitsrc_of(d.validity, 0, cap), 0, dctr, base_in, limit, dctr + pend->validity_counter[(size_t)j]);
+            core->launches++;
+            RVL_CUDA_TRY(cudaGetLastError());
+        }
+        pend->n_launched = 1;
+    } else if (base_in != nullptr) {
+        // empty batch in a chained query: the running total passes through unchanged
+        RVL_CUDA_TRY(cudaMemcpyAsync(dctr, base_in, 8, cudaMemcpyDeviceToDevice, core->stream));
+    }
+    if ((size_t)n_counters + 1 > CtxCore::kSlotWords) return fail(RVL_INVALID_ARGUMENT, "too many projected columns");
+    pend->mailbox = core->next_slot();
+    *reinterpret_cast<volatile uint64_t*>(pend->mailbox) = kMailboxPending;
+    pend->chained = base_in != nullptr;
+    RVL_CUDA_TRY(cudaMemcpyAsync(pend->mailbox, dctr, (size_t)n_counters * 8, cudaMemcpyDeviceToHost, core->stream));
+    if (base_in != nullptr)
+        RVL_CUDA_TRY(cudaMemcpyAsync(pend->mailbox + n_counters, base_in, 8, cudaMemcpyDeviceToHost, core->stream));
+    if (total_ext != nullptr) RVL_CUDA_TRY(cudaMemcpyAsync(total_ext, dctr, 8, cudaMemcpyDeviceToDevice, core->stream));
+    RVL_CUDA_TRY(cudaEventCreateWithFlags(&pend->done_event, cudaEventDisableTiming));
+    RVL_CUDA_TRY(cudaEventRecord(pend->done_event, core->stream));
+    *out = pend.release();
+    return RVL_OK;
+}
+
+int fp_finish(FpPending* pend, rvl_batch** out, rvl_batch** mask_out) {
+    std::unique_ptr<FpPending> guard(pend);
+    const CoreRef& core = pend->core;
+    RVL_CUDA_TRY(cudaSetDevice(core->device));
+    if (pend->done_event) {
+        cudaError_t e = cudaEventSynchronize(pend->done_event);
+        cudaEventDestroy(pend->done_event);
+        pend->done_event = nullptr;
+        if (e != cudaSuccess) return fail(RVL_CUDA, std::string("fused filter/project failed: ") + cudaGetErrorString(e));
+    } else {
+        RVL_CUDA_TRY(cudaStreamSynchronize(core->stream));
+    }
+    const uint64_t* mb = pend->mailbox;
+    int64_t total = (int64_t)mb[0];
+    int64_t base = pend->chained ? (int64_t)mb[pend->n_counters] : 0;
+    if (pend->limit >= 0) { total = std::min(total, pend->limit); base = std::min(base, pend->limit); }
+    const int64_t count = std::max<int64_t>(0, total - base);
+    pend->base_rows = (uint64_t)base;
+    if (out) {
+        auto b = std::make_unique<rvl_batch>();
+        b->core = core; b->num_rows = count;
+        for (size_t j = 0; j < pend->outs.size(); ++j) {
+            DevColumn d = pend->outs[j];
+            d.length = count;
+            if (d.dtype == RVL_NULL) d.null_count = count;
+            else if (pend->validity_counter[j] >= 0) {
+                d.null_count = count - (int64_t)mb[pend->validity_counter[j]];
+                if (d.null_count == 0) d.validity.reset();  // bitmap only when a survivor is null (primitive.rs:180-185)
+            } else d.null_count = 0;
+            if (pend->bytes_counter[j] >= 0) d.data_len = pend->n > 0 ? (int64_t)mb[pend->bytes_counter[j]] : 0;
+            b->cols.push_back(std::move(d));
+        }
+        *out = b.release();
+    }
+    if (mask_out) {
+        auto m = std::make_unique<rvl_batch>();
+        m->core = core; m->num_rows = pend->n;
+        DevColumn d;
+        d.dtype = RVL_BOOLEAN; d.length = pend->n; d.offset = 0; d.null_count = 0;
+        if (pend->mask) d.values = pend->mask;
+        else RVL_TRY(dev_alloc_zeroed(core, 8, &d.values));
+        m->cols.push_back(std::move(d));
+        *mask_out = m.release();
+    }
+    return RVL_OK;
+}
+
+}  // namespace rvl
+
+using namespace rvl;
+
+struct rvl_pending {
+    rvl::FpPending* p;
+};
+
+extern "C" {
+
+int32_t rvl_filter_project_launch(rvl_ctx* ctx, const rvl_batch* in, const rvl_predicate* pred, const int32_t* proj, int32_t nproj,
+                                  int64_t limit, rvl_pending** pending) {
+    if (!ctx || !pending) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    FpPending* p = nullptr;
+    RVL_TRY(fp_launch(ctx->core, in, pred, proj, nproj, limit, false, nullptr, nullptr, &p));
+    *pending = new rvl_pending{p};
+    return RVL_OK;
+}
+
+int32_t rvl_filter_project_finish(rvl_ctx* ctx, rvl_pending* pending, rvl_batch** out) {
+    if (!pending || !out) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    FpPending* p = pending->p;
+    delete pending;
+    return fp_finish(p, out, nullptr);
+}
+
+int32_t rvl_filter_project(rvl_ctx* ctx, const rvl_batch* in, const rvl_predicate* pred, const int32_t* proj, int32_t nproj,
+                           int64_t limit, rvl_batch** out) {
+    if (!ctx || !out) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    FpPending* p = nullptr;
+    RVL_TRY(fp_launch(ctx->core, in, pred, proj, nproj, limit, false, nullptr, nullptr, &p));
+    return fp_finish(p, out, nullptr);
+}
+
+int32_t rvl_predicate_mask(rvl_ctx* ctx, const rvl_batch* in, const rvl_predicate* pred, rvl_batch** mask_out) {
+    if (!ctx || !mask_out) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    FpPending* p = nullptr;
+    RVL_TRY(fp_launch(ctx->core, in, pred, nullptr, 0, -1, true, nullptr, nullptr, &p));
+    return fp_finish(p, nullptr, mask_out);
+}
+
+int32_t rvl_shard_range(int64_t n_rows, int32_t rank, int32_t world, int64_t* begin, int64_t* end) {
+    if (world <= 0 || rank < 0 || rank >= world || n_rows < 0) return fail(RVL_INVALID_ARGUMENT, "bad shard arguments");
+    // ceil(n / world) rounded up to a multiple of 64 rows so bitmap words never straddle two GPUs
+    int64_t per = (n_rows + world - 1) / world;
+    per = (per + 63) / 64 * 64;
+    *begin = std::min<int64_t>(n_rows, per * rank);
+    *end = std::min<int64_t>(n_rows, per * (rank + 1));
+    return RVL_OK;
+}
+
+int32_t rvl_shard_limit_split(const int64_t* counts, int32_t world, int64_t limit, int64_t* take) {
+    int64_t before = 0;
+    for (int g = 0; g < world; ++g) {
+        if (limit < 0) take[g] = counts[g];
+        else take[g] = std::max<int64_t>(0, std::min<int64_t>(counts[g], limit - before));
+        before += counts[g];
+    }
+    return RVL_OK;
+}
+
+int32_t rvl_filter_project_sharded(rvl_ctx* const* ctxs, int32_t n, const rvl_batch* const* shards, const rvl_predicate* pred,
+                                   const int32_t* proj, int32_t nproj, int64_t limit, rvl_batch** outs, int64_t* counts) {
+    if (!ctxs || !shards || !outs || n <= 0) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    // every GPU stops at `limit` local survivors; the ordered result takes clamp(limit - sum_{j<g} count_j, 0, count_g) from shard g
+    std::vector<FpPending*> pend((size_t)n, nullptr);
+    int rc = RVL_OK;
+    for (int g = 0; g < n && rc == RVL_OK; ++g) rc = fp_launch(ctxs[g]->core, shards[g], pred, proj, nproj, limit, false, nullptr, nullptr, &pend[(size_t)g]);
+    std::vector<int64_t> local((size_t)n, 0), take((size_t)n, 0);
+    for (int g = 0; g < n; ++g) {
+        outs[g] = nullptr;
+        if (!pend[(size_t)g]) continue;
+        const int r2 = fp_finish(pend[(size_t)g], &outs[g], nullptr);
+        if (rc == RVL_OK) rc = r2;
+        if (outs[g]) local[(size_t)g] = outs[g]->num_rows;
+    }
+    if (rc != RVL_OK) {
+        for (int g = 0; g < n; ++g) { delete outs[g]; outs[g] = nullptr; }
+        return rc;
+    }
+    rvl_shard_limit_split(local.data(), n, limit, take.data());
+    for (int g = 0; g < n; ++g) {
+        if (take[(size_t)g] < local[(size_t)g]) {
+            rvl_batch* cut = nullptr;
+            RVL_TRY(rvl_batch_slice(outs[g], 0, take[(size_t)g], &cut));
+            delete outs[g];
+            outs[g] = cut;
+        }
+        if (counts) counts[g] = take[(size_t)g];
+    }
+    return RVL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,629 @@
+// runtime.cu — context, memory, device-resident RecordBatch (upload / views / download / slice /
+// select / concat), synthetic generator and checksums behind include/rivulus_gpu.h.
+//
+// Reference seams (under /root/reference/src): execution/record_batch.rs:16-58 (try_new), :92-106 (slice),
+// :180-206 (select_columns), :245-342 (concat); execution/array/*.rs for the buffer layouts.
+#include "runtime.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+#include "aux_kernels.cuh"
+#include "string_kernels.cuh"
+
+namespace rvl {
+
+thread_local std::string g_last_error;
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+CtxCore::~CtxCore() {
+    cudaSetDevice(device);
+    if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
+    if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
+    if (d2h_stream) { cudaStreamSynchronize(d2h_stream); cudaStreamDestroy(d2h_stream); }
+    for (auto& e : prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    if (mailbox) cudaFreeHost(mailbox);
+}
+
+int CtxCore::prof_flush() {
+    for (auto& e : prof_events) {
+        RVL_CUDA_TRY(cudaEventSynchronize(e.second));
+        float ms = 0.f;
+        RVL_CUDA_TRY(cudaEventElapsedTime(&ms, e.first, e.second));
+        prof_ms += ms;
+        prof_launches++;
+        prof_times.push_back((double)ms);
+        cudaEventDestroy(e.first); cudaEventDestroy(e.second);
+    }
+    prof_events.clear();
+    return RVL_OK;
+}
+
+DevBuffer::~DevBuffer() {
+    if (owned && ptr != nullptr && core) {
+        cudaSetDevice(core->device);
+        cudaFreeAsync(ptr, core->stream);
+    }
+}
+
+int dev_alloc(const CoreRef& core, size_t bytes, BufRef* out) {
+    // pad so word / 16-byte vector reads at the tail of a buffer stay inside the allocation
+    const size_t padded = ((bytes + 64 + 255) / 256) * 256;
+    void* p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, padded, core->stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? RVL_OUT_OF_MEMORY : RVL_CUDA,
+                    std::string("cudaMallocAsync(") + std::to_string(padded) + "): " + cudaGetErrorString(e));
+    }
+    auto b = std::make_shared<DevBuffer>();
+    b->ptr = p; b->bytes = padded; b->owned = true; b->core = core;
+    *out = std::move(b);
+    return RVL_OK;
+}
+
+int dev_alloc_zeroed(const CoreRef& core, size_t bytes, BufRef* out) {
+    RVL_TRY(dev_alloc(core, bytes, out));
+    RVL_CUDA_TRY(cudaMemsetAsync((*out)->ptr, 0, (*out)->bytes, core->stream));
+    return RVL_OK;
+}
+
+BufRef wrap_external(const CoreRef& core, const void* ptr, size_t bytes) {
+    auto b = std::make_shared<DevBuffer>();
+    b->ptr = const_cast<void*>(ptr); b->bytes = bytes; b->owned = false; b->core = core;
+    return b;
+}
+
+BitSrc bitsrc_of(const BufRef& buf, int64_t offset, int64_t length) {
+    BitSrc s{nullptr, 0, 0};
+    if (!buf) return s;
+    const uintptr_t p = reinterpret_cast<uintptr_t>(buf->ptr);
+    const uintptr_t aligned = p & ~uintptr_t(3);
+    s.words = reinterpret_cast<const uint32_t*>(aligned);
+    s.bit0 = (uint64_t)(p - aligned) * 8ull + (uint64_t)offset;
+    s.nwords = (s.bit0 + (uint64_t)length + 31ull) / 32ull;
+    return s;
+}
+
+static inline int grid_for(int64_t n, int block, int sm_count) {
+    int64_t g = (n + block - 1) / block;
+    const int64_t cap = (int64_t)sm_count * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace rvl
+
+using namespace rvl;
+
+static const char* dtype_name(int d) {
+    static const char* n[] = {"Null", "Boolean", "Int64", "Float64", "String"};
+    return (d >= 0 && d <= 4) ? n[d] : "?";
+}
+
+extern "C" {
+
+int32_t rvl_abi_version(void) { return RVL_ABI_VERSION; }
+const char* rvl_last_error(void) { return g_last_error.c_str(); }
+
+int32_t rvl_device_count(int32_t* count) {
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) { cudaGetLastError(); *count = 0; return fail(RVL_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)); }
+    *count = c;
+    return RVL_OK;
+}
+
+int32_t rvl_ctx_create(int32_t device, rvl_ctx** ctx) {
+    if (!ctx) return fail(RVL_INVALID_ARGUMENT, "ctx is NULL");
+    int n = 0;
+    RVL_CUDA_TRY(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return fail(RVL_INVALID_ARGUMENT, "device " + std::to_string(device) + " out of range (" + std::to_string(n) + " devices)");
+    RVL_CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RVL_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(RVL_CUDA, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                                                   "; this library carries sm_100a code only (no fallback path)");
+    auto core = std::make_shared<CtxCore>();
+    core->device = device;
+    core->sm_count = prop.multiProcessorCount;
+    RVL_CUDA_TRY(cudaStreamCreateWithFlags(&core->stream, cudaStreamNonBlocking));
+    RVL_CUDA_TRY(cudaStreamCreateWithFlags(&core->copy_stream, cudaStreamNonBlocking));
+    RVL_CUDA_TRY(cudaStreamCreateWithFlags(&core->d2h_stream, cudaStreamNonBlocking));
+    core->mailbox_words = 4096;
+    RVL_CUDA_TRY(cudaHostAlloc((void**)&core->mailbox, core->mailbox_words * sizeof(uint64_t), cudaHostAllocDefault));
+    // keep freed blocks cached in the pool: outputs are sized for the worst case and recycled call to call
+    cudaMemPool_t pool;
+    RVL_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t threshold = UINT64_MAX;
+    RVL_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    *ctx = new rvl_ctx{core};
+    return RVL_OK;
+}
+
+int32_t rvl_ctx_destroy(rvl_ctx* ctx) {
+    if (!ctx) return RVL_OK;
+    cudaSetDevice(ctx->core->device);
+    cudaStreamSynchronize(ctx->core->stream);
+    delete ctx;
+    return RVL_OK;
+}
+
+int32_t rvl_ctx_synchronize(rvl_ctx* ctx) {
+    RVL_CUDA_TRY(cudaSetDevice(ctx->core->device));
+    RVL_CUDA_TRY(cudaStreamSynchronize(ctx->core->copy_stream));
+    RVL_CUDA_TRY(cudaStreamSynchronize(ctx->core->stream));
+    return RVL_OK;
+}
+
+int32_t rvl_ctx_cuda_stream(rvl_ctx* ctx, void** s) { *s = (void*)ctx->core->stream; return RVL_OK; }
+int32_t rvl_ctx_device(rvl_ctx* ctx, int32_t* d) { *d = ctx->core->device; return RVL_OK; }
+int32_t rvl_ctx_launch_count(rvl_ctx* ctx, int64_t* n) { *n = ctx->core->launches.load(); return RVL_OK; }
+
+int32_t rvl_ctx_profile_enable(rvl_ctx* ctx, int32_t enable) {
+    if (!ctx) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    RVL_TRY(ctx->core->prof_flush());
+    ctx->core->profile = enable != 0;
+    ctx->core->prof_ms = 0.0; ctx->core->prof_launches = 0;
+    return RVL_OK;
+}
+int32_t rvl_ctx_profile_read(rvl_ctx* ctx, double* ms, int64_t* launches) {
+    if (!ctx) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    RVL_CUDA_TRY(cudaSetDevice(ctx->core->device));
+    RVL_TRY(ctx->core->prof_flush());
+    if (ms) *ms = ctx->core->prof_ms;
+    if (launches) *launches = ctx->core->prof_launches;
+    ctx->core->prof_ms = 0.0; ctx->core->prof_launches = 0; ctx->core->prof_times.clear();
+    return RVL_OK;
+}
+int32_t rvl_ctx_profile_read_launches(rvl_ctx* ctx, double* ms_out, int64_t cap, int64_t* n) {
+    if (!ctx || !n) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    RVL_CUDA_TRY(cudaSetDevice(ctx->core->device));
+    RVL_TRY(ctx->core->prof_flush());
+    const int64_t have = (int64_t)ctx->core->prof_times.size();
+    *n = have;
+    for (int64_t i = 0; i < have && i < cap && ms_out; ++i) ms_out[i] = ctx->core->prof_times[(size_t)i];
+    ctx->core->prof_ms = 0.0; ctx->core->prof_launches = 0; ctx->core->prof_times.clear();
+    return RVL_OK;
+}
+
+int32_t rvl_host_alloc(size_t bytes, void** ptr) {
+    RVL_CUDA_TRY(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return RVL_OK;
+}
+int32_t rvl_host_free(void* ptr) {
+    if (ptr) RVL_CUDA_TRY(cudaFreeHost(ptr));
+    return RVL_OK;
+}
+
+// ------------------------------------------------------------------------------------------ batches
+static int check_columns(const rvl_column* cols, int32_t ncols, int64_t* rows) {
+    // record_batch.rs:25-40
+    int64_t n = ncols > 0 ? cols[0].length : 0;
+    for (int i = 0; i < ncols; ++i) {
+        if (cols[i].dtype < RVL_NULL || cols[i].dtype > RVL_STRING) return fail(RVL_INVALID_ARGUMENT, "Column " + std::to_string(i) + " has unknown dtype");
+        if (cols[i].length < 0 || cols[i].offset < 0) return fail(RVL_INVALID_ARGUMENT, "negative length/offset");
+        if (cols[i].length != n)
+            return fail(RVL_LENGTH_MISMATCH, "Column " + std::to_string(i) + " has length " + std::to_string(cols[i].length) + " but expected " + std::to_string(n));
+        const bool need_values = cols[i].dtype == RVL_INT64 || cols[i].dtype == RVL_FLOAT64 || cols[i].dtype == RVL_BOOLEAN;
+        if (need_values && cols[i].length > 0 && cols[i].values == nullptr) return fail(RVL_INVALID_ARGUMENT, "Column " + std::to_string(i) + " has no values buffer");
+        if (cols[i].dtype == RVL_STRING && cols[i].offsets == nullptr) return fail(RVL_INVALID_ARGUMENT, "Column " + std::to_string(i) + " has no offsets buffer");
+        if (cols[i].dtype == RVL_STRING && cols[i].data_len > (int64_t)INT32_MAX)
+            return fail(RVL_OFFSET_OVERFLOW, "Column " + std::to_string(i) + ": string data exceeds the int32 offset range; split the batch");
+    }
+    *rows = n;
+    return RVL_OK;
+}
+
+int32_t rvl_batch_upload(rvl_ctx* ctx, const rvl_column* cols, int32_t ncols, rvl_batch** out) {
+    if (!ctx || !out || (ncols > 0 && !cols)) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    const CoreRef& core = ctx->core;
+    RVL_CUDA_TRY(cudaSetDevice(core->device));
+    int64_t n = 0;
+    RVL_TRY(check_columns(cols, ncols, &n));
+    auto b = std::make_unique<rvl_batch>();
+    b->core = core; b->num_rows = n;
+    for (int i = 0; i < ncols; ++i) {
+        const rvl_column& c = cols[i];
+        const cudaMemcpyKind kind = c.location == RVL_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        DevColumn d;
+        d.dtype = c.dtype; d.length = n;
+        const int64_t resid = c.offset % 64;  // keep the sub-64-row residual so bit offsets survive the copy
+        const int64_t start = c.offset - resid;
+        d.offset = resid;
+        const int64_t span = resid + n;
+        if (c.dtype == RVL_INT64 || c.dtype == RVL_FLOAT64) {
+            RVL_TRY(dev_alloc(core, (size_t)span * 8, &d.values));
+            if (span > 0) RVL_CUDA_TRY(cudaMemcpyAsync(d.values->ptr, (const uint8_t*)c.values + start * 8, (size_t)span * 8, kind, core->stream));
+        } else if (c.dtype == RVL_BOOLEAN) {
+            RVL_TRY(dev_alloc_zeroed(core, (size_t)(span + 7) / 8, &d.values));
+            if (span > 0) RVL_CUDA_TRY(cudaMemcpyAsync(d.values->ptr, (const uint8_t*)c.values + start / 8, (size_t)(span + 7) / 8, kind, core->stream));
+        } else if (c.dtype == RVL_STRING) {
+            RVL_TRY(dev_alloc(core, (size_t)(span + 1) * 4, &d.offsets));
+            RVL_CUDA_TRY(cudaMemcpyAsync(d.offsets->ptr, c.offsets + start, (size_t)(span + 1) * 4, kind, core->stream));
+            RVL_TRY(dev_alloc(core, (size_t)c.data_len, &d.data));
+            if (c.data_len > 0) RVL_CUDA_TRY(cudaMemcpyAsync(d.data->ptr, c.data, (size_t)c.data_len, kind, core->stream));
+            d.data_len = c.data_len;
+        }
+        if (c.validity != nullptr && c.dtype != RVL_NULL) {
+            RVL_TRY(dev_alloc_zeroed(core, (size_t)(span + 7) / 8, &d.validity));
+            if (span > 0) RVL_CUDA_TRY(cudaMemcpyAsync(d.validity->ptr, c.validity + start / 8, (size_t)(span + 7) / 8, kind, core->stream));
+        } else {
+            d.null_count = c.dtype == RVL_NULL ? n : 0;
+        }
+        b->cols.push_back(std::move(d));
+    }
+    // the source buffers are only borrowed for the duration of the call
+    RVL_CUDA_TRY(cudaStreamSynchronize(core->stream));
+    *out = b.release();
+    return RVL_OK;
+}
+
+int32_t rvl_batch_wrap_device(rvl_ctx* ctx, const rvl_column* cols, int32_t ncols, rvl_batch** out) {
+    if (!ctx || !out || (ncols > 0 && !cols)) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    int64_t n = 0;
+    RVL_TRY(check_columns(cols, ncols, &n));
+    auto b = std::make_unique<rvl_batch>();
+    b->core = ctx->core; b->num_rows = n;
+    for (int i = 0; i < ncols; ++i) {
+        const rvl_column& c = cols[i];
+        if (c.location != RVL_DEVICE) return fail(RVL_INVALID_ARGUMENT, "rvl_batch_wrap_device needs device buffers");
+        DevColumn d;
+        d.dtype = c.dtype; d.length = n; d.offset = c.offset;
+        const int64_t span = c.offset + n;
+        if (c.dtype == RVL_INT64 || c.dtype == RVL_FLOAT64) {
+            if ((reinterpret_cast<uintptr_t>(c.values) & 7) != 0) return fail(RVL_INVALID_ARGUMENT, "values buffer must be 8-byte aligned");
+            d.values = wrap_external(ctx->core, c.values, (size_t)span * 8);
+        } else if (c.dtype == RVL_BOOLEAN) {
+            d.values = wrap_external(ctx->core, c.values, (size_t)(span + 7) / 8);
+        } else if (c.dtype == RVL_STRING) {
+            if ((reinterpret_cast<uintptr_t>(c.offsets) & 3) != 0) return fail(RVL_INVALID_ARGUMENT, "offsets buffer must be 4-byte aligned");
+            d.offsets = wrap_external(ctx->core, c.offsets, (size_t)(span + 1) * 4);
+            d.data = wrap_external(ctx->core, c.data, (size_t)c.data_len);
+            d.data_len = c.data_len;
+        }
+        if (c.validity != nullptr && c.dtype != RVL_NULL) d.validity = wrap_external(ctx->core, c.validity, (size_t)(span + 7) / 8);
+        else d.null_count = c.dtype == RVL_NULL ? n : 0;
+        b->cols.push_back(std::move(d));
+    }
+    *out = b.release();
+    return RVL_OK;
+}
+
+int32_t rvl_batch_release(rvl_batch* batch) {
+    delete batch;
+    return RVL_OK;
+}
+int32_t rvl_batch_num_rows(const rvl_batch* batch, int64_t* rows) { *rows = batch->num_rows; return RVL_OK; }
+int32_t rvl_batch_num_columns(const rvl_batch* batch, int32_t* n) { *n = (int32_t)batch->cols.size(); return RVL_OK; }
+
+static int ensure_null_count(const rvl_batch* batch, int i) {
+    DevColumn& c = const_cast<DevColumn&>(batch->cols[i]);
+    if (c.null_count >= 0) return RVL_OK;
+    if (!c.validity) { c.null_count = c.dtype == RVL_NULL ? c.length : 0; return RVL_OK; }
+    const CoreRef& core = batch->core;
+    RVL_CUDA_TRY(cudaSetDevice(core->device));
+    BufRef counter;
+    RVL_TRY(dev_alloc_zeroed(core, 8, &counter));
+    count_ones_kernel<<<grid_for((c.length + 31) / 32, 256, core->sm_count), 256, 0, core->stream>>>(
+        bitsrc_of(c.validity, c.offset, c.length), c.length, nullptr, nullptr, -1, (unsigned long long*)counter->ptr);
+    core->launches++;
+    RVL_CUDA_TRY(cudaGetLastError());
+    RVL_CUDA_TRY(cudaMemcpyAsync(core->mailbox, counter->ptr, 8, cudaMemcpyDeviceToHost, core->stream));
+    RVL_CUDA_TRY(cudaStreamSynchronize(core->stream));
+    c.null_count = c.length - (int64_t)core->mailbox[0];
+    return RVL_OK;
+}
+
+int32_t rvl_batch_column(const rvl_batch* batch, int32_t i, rvl_column* view) {
+    if (!batch || !view) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    if (i < 0 || i >= (int32_t)batch->cols.size())
+        return fail(RVL_OUT_OF_BOUNDS, "Column index " + std::to_string(i) + " out of bounds for " + std::to_string(batch->cols.size()) + " columns");
+    RVL_TRY(ensure_null_count(batch, i));
+    const DevColumn& c = batch->cols[i];
+    std::memset(view, 0, sizeof *view);
+    view->dtype = c.dtype; view->location = RVL_DEVICE; view->length = c.length; view->offset = c.offset;
+    view->values = c.values ? c.values->ptr : nullptr;
+    view->validity = c.validity ? (const uint8_t*)c.validity->ptr : nullptr;
+    view->offsets = c.offsets ? (const int32_t*)c.offsets->ptr : nullptr;
+    view->data = c.data ? (const uint8_t*)c.data->ptr : nullptr;
+    view->data_len = c.data_len;
+    view->null_count = c.null_count;
+    return RVL_OK;
+}
+
+// copy `length` bits starting at bit `offset` of `src` to host `dst` rebased to bit 0, padding bits zero
+static int download_bits(const CoreRef& core, const BufRef& src, int64_t offset, int64_t length, uint8_t* dst) {
+    if (length == 0) return RVL_OK;
+    const size_t nbytes = (size_t)(length + 7) / 8;
+    if (offset % 8 == 0) {
+        RVL_CUDA_TRY(cudaMemcpyAsync(dst, (const uint8_t*)src->ptr + offset / 8, nbytes, cudaMemcpyDeviceToHost, core->d2h_stream));
+        RVL_CUDA_TRY(cudaStreamSynchronize(core->d2h_stream));
+    } else {
+        BufRef tmp;
+        RVL_TRY(dev_alloc_zeroed(core, nbytes, &tmp));
+        bitcopy_kernel<<<grid_for((length + 31) / 32 + 1, 256, core->sm_count), 256, 0, core->stream>>>(
+            bitsrc_of(src, offset, length), BitSrc{nullptr, 0, 0}, (uint32_t*)tmp->ptr, 0, length);
+        core->launches++;
+        RVL_CUDA_TRY(cudaGetLastError());
+        RVL_CUDA_TRY(cudaMemcpyAsync(dst, tmp->ptr, nbytes, cudaMemcpyDeviceToHost, core->stream));
+        RVL_CUDA_TRY(cudaStreamSynchronize(core->stream));
+    }
+    if (length % 8 != 0) dst[nbytes - 1] &= (uint8_t)((1u << (length % 8)) - 1u);
+    return RVL_OK;
+}
+
+int32_t rvl_batch_download_column(rvl_ctx* ctx, const rvl_batch* batch, int32_t i, rvl_column* dst) {
+    if (!ctx || !batch || !dst) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    if (i < 0 || i >= (int32_t)batch->cols.size())
+        return fail(RVL_OUT_OF_BOUNDS, "Column index " + std::to_string(i) + " out of bounds for " + std::to_string(batch->cols.size()) + " columns");
+    const CoreRef& core = batch->core;
+    RVL_CUDA_TRY(cudaSetDevice(core->device));
+    const DevColumn& c = batch->cols[i];
+    if (dst->dtype != c.dtype) return fail(RVL_TYPE_MISMATCH, std::string("Column ") + std::to_string(i) + " has type " + dtype_name(c.dtype) + " but destination expects " + dtype_name(dst->dtype));
+    const int64_t n = c.length;
+    if (c.dtype == RVL_INT64 || c.dtype == RVL_FLOAT64) {
+        if (n > 0) {
+            // finished batches are complete on every stream (their producers synchronise), so the copy-back
+            // uses its own stream and overlaps later kernels / H2D staging
+            RVL_CUDA_TRY(cudaMemcpyAsync(const_cast<void*>(dst->values), (const uint8_t*)c.values->ptr + c.offset * 8, (size_t)n * 8, cudaMemcpyDeviceToHost, core->d2h_stream));
+            RVL_CUDA_TRY(cudaStreamSynchronize(core->d2h_stream));
+        }
+    } else if (c.dtype == RVL_BOOLEAN) {
+        RVL_TRY(download_bits(core, c.values, c.offset, n, (uint8_t*)const_cast<void*>(dst->values)));
+    } else if (c.dtype == RVL_STRING) {
+        // rebase offsets to start at 0 and copy the referenced byte window
+        int32_t first_last[2] = {0, 0};
+        RVL_CUDA_TRY(cudaMemcpyAsync(&first_last[0], (const int32_t*)c.offsets->ptr + c.offset, 4, cudaMemcpyDeviceToHost, core->stream));
+        RVL_CUDA_TRY(cudaMemcpyAsync(&first_last[1], (const int32_t*)c.offsets->ptr + c.offset + n, 4, cudaMemcpyDeviceToHost, core->stream));
+        RVL_CUDA_TRY(cudaStreamSynchronize(core->stream));
+        int32_t* hoff = const_cast<int32_t*>(dst->offsets);
+        if (first_last[0] == 0) {
+            RVL_CUDA_TRY(cudaMemcpyAsync(hoff, (const int32_t*)c.offsets->ptr + c.offset, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, core->stream));
+        } else {
+            BufRef tmp;
+            RVL_TRY(dev_alloc(core, (size_t)(n + 1) * 4, &tmp));
+            RVL_CUDA_TRY(cudaMemsetAsync(tmp->ptr, 0, 4, core->stream));
+            if (n > 0) {
+                rebase_offsets_kernel<<<grid_for(n, 256, core->sm_count), 256, 0, core->stream>>>((const int32_t*)c.offsets->ptr + c.offset, (int32_t*)tmp->ptr, n, 0);
+                core->launches++;
+                RVL_CUDA_TRY(cudaGetLastError());
+            }
+            RVL_CUDA_TRY(cudaMemcpyAsync(hoff, tmp->ptr, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, core->stream));
+        }
+        const int64_t nbytes = (int64_t)first_last[1] - first_last[0];
+        if (nbytes > dst->data_len) return fail(RVL_LENGTH_MISMATCH, "destination data buffer too small: need " + std::to_string(nbytes) + " bytes");
+        if (nbytes > 0) RVL_CUDA_TRY(cudaMemcpyAsync(const_cast<uint8_t*>(dst->data), (const uint8_t*)c.data->ptr + first_last[0], (size_t)nbytes, cudaMemcpyDeviceToHost, core->stream));
+        RVL_CUDA_TRY(cudaStreamSynchronize(core->stream));
+        dst->data_len = nbytes;
+    }
+    if (c.validity && dst->validity != nullptr) RVL_TRY(download_bits(core, c.validity, c.offset, n, const_cast<uint8_t*>(dst->validity)));
+    dst->length = n; dst->offset = 0;
+    RVL_TRY(ensure_null_count(batch, i));
+    dst->null_count = c.null_count;
+    return RVL_OK;
+}
+
+int32_t rvl_batch_slice(const rvl_batch* batch, int64_t offset, int64_t length, rvl_batch** view) {
+    if (!batch || !view) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    if (offset < 0 || length < 0 || offset + length > batch->num_rows) return fail(RVL_OUT_OF_BOUNDS, "Slice out of bounds");  // record_batch.rs:93
+    auto b = std::make_unique<rvl_batch>();
+    b->core = batch->core; b->num_rows = length;
+    for (const DevColumn& c : batch->cols) {
+        DevColumn d = c;  // shares the buffers (Arc clone in the reference)
+        d.offset = c.offset + offset; d.length = length;
+        d.null_count = c.dtype == RVL_NULL ? length : (c.validity ? -1 : 0);
+        b->cols.push_back(std::move(d));
+    }
+    *view = b.release();
+    return RVL_OK;
+}
+
+int32_t rvl_batch_select(const rvl_batch* batch, const int32_t* indices, int32_t n, rvl_batch** view) {
+    if (!batch || !view || (n > 0 && !indices)) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    for (int i = 0; i < n; ++i)
+        if (indices[i] < 0 || indices[i] >= (int32_t)batch->cols.size())
+            return fail(RVL_OUT_OF_BOUNDS, "Column index " + std::to_string(indices[i]) + " out of bounds for " + std::to_string(batch->cols.size()) + " columns");  // record_batch.rs:183-187
+    auto b = std::make_unique<rvl_batch>();
+    b->core = batch->core; b->num_rows = batch->num_rows;
+    for (int i = 0; i < n; ++i) b->cols.push_back(batch->cols[indices[i]]);
+    *view = b.release();
+    return RVL_OK;
+}
+
+int32_t rvl_batch_concat(rvl_ctx* ctx, const rvl_batch* const* batches, int32_t n, rvl_batch** out) {
+    if (!ctx || !out) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    if (n <= 0 || !batches) return fail(RVL_INVALID_ARGUMENT, "Cannot concatenate empty batch list");  // record_batch.rs:247
+    const CoreRef& core = ctx->core;
+    RVL_CUDA_TRY(cudaSetDevice(core->device));
+    const size_t ncols = batches[0]->cols.size();
+    int64_t total = 0;
+    for (int b = 0; b < n; ++b) {
+        if (batches[b]->cols.size() != ncols) return fail(RVL_SCHEMA_MISMATCH, "All batches must have the same schema");  // :253
+        for (size_t c = 0; c < ncols; ++c)
+            if (batches[b]->cols[c].dtype != batches[0]->cols[c].dtype) return fail(RVL_SCHEMA_MISMATCH, "All batches must have the same schema");
+        total += batches[b]->num_rows;
+    }
+    auto res = std::make_unique<rvl_batch>();
+    res->core = core; res->num_rows = total;
+    // device counters: [2c] ones in validity of column c, [2c+1] string bytes of column c
+    BufRef counters;
+    RVL_TRY(dev_alloc_zeroed(core, ncols * 16 + 16, &counters));
+    unsigned long long* dctr = (unsigned long long*)counters->ptr;
+    std::vector<BufRef> keep_alive;
+    for (size_t c = 0; c < ncols; ++c) {
+        DevColumn d;
+        d.dtype = batches[0]->cols[c].dtype; d.length = total; d.offset = 0;
+        bool any_validity = false;
+        for (int b = 0; b < n; ++b) any_validity |= (bool)batches[b]->cols[c].validity;
+        if (any_validity && d.dtype != RVL_NULL) RVL_TRY(dev_alloc_zeroed(core, (size_t)(total + 7) / 8, &d.validity));
+        if (d.dtype == RVL_INT64 || d.dtype == RVL_FLOAT64) RVL_TRY(dev_alloc(core, (size_t)total * 8, &d.values));
+        if (d.dtype == RVL_BOOLEAN) RVL_TRY(dev_alloc_zeroed(core, (size_t)(total + 7) / 8, &d.values));
+        BufRef status;
+        if (d.dtype == RVL_STRING) {
+            int64_t cap = 0;
+            for (int b = 0; b < n; ++b) cap += batches[b]->cols[c].data_len;
+            if (cap > (int64_t)INT32_MAX) {
+                // data_len is an upper bound; only fail when the bytes actually referenced overflow
+                int64_t exact = 0;
+                for (int b = 0; b < n; ++b) {
+                    const DevColumn& s = batches[b]->cols[c];
+                    int32_t fl[2];
+                    RVL_CUDA_TRY(cudaMemcpyAsync(&fl[0], (const int32_t*)s.offsets->ptr + s.offset, 4, cudaMemcpyDeviceToHost, core->stream));
+                    RVL_CUDA_TRY(cudaMemcpyAsync(&fl[1], (const int32_t*)s.offsets->ptr + s.offset + s.length, 4, cudaMemcpyDeviceToHost, core->stream));
+                    RVL_CUDA_TRY(cudaStreamSynchronize(core->stream));
+                    exact += (int64_t)fl[1] - fl[0];
+                }
+                if (exact > (int64_t)INT32_MAX) return fail(RVL_OFFSET_OVERFLOW, "concatenated string data (" + std::to_string(exact) + " bytes) exceeds the int32 offset range");
+                cap = exact;
+            }
+            RVL_TRY(dev_alloc(core, (size_t)(total + 1) * 4, &d.offsets));
+            RVL_CUDA_TRY(cudaMemsetAsync(d.offsets->ptr, 0, 4, core->stream));
+            RVL_TRY(dev_alloc(core, (size_t)cap, &d.data));
+            int64_t max_tiles = 1;
+            for (int b = 0; b < n; ++b) max_tiles = std::max<int64_t>(max_tiles, (batches[b]->num_rows + kTileRows - 1) / kTileRows);
+            RVL_TRY(dev_alloc(core, (size_t)max_tiles * 8, &status));
+            keep_alive.push_back(status);
+        }
+        int64_t row_base = 0;
+        for (int b = 0; b < n; ++b) {
+            const DevColumn& s = batches[b]->cols[c];
+            const int64_t m = s.length;
+            if (m == 0) continue;
+            const BitSrc sv = bitsrc_of(s.validity, s.offset, m);
+            if (d.dtype == RVL_INT64 || d.dtype == RVL_FLOAT64) {
+                copy_col8_zero_nulls_kernel<<<grid_for(m, 256, core->sm_count), 256, 0, core->stream>>>(
+                    (const uint64_t*)s.values->ptr + s.offset, sv, (uint64_t*)d.values->ptr + row_base, m);
+                core->launches++;
+            } else if (d.dtype == RVL_BOOLEAN) {
+                bitcopy_kernel<<<grid_for((m + 31) / 32 + 1, 256, core->sm_count), 256, 0, core->stream>>>(
+                    bitsrc_of(s.values, s.offset, m), sv, (uint32_t*)d.values->ptr, (uint64_t)row_base, m);
+                core->launches++;
+            } else if (d.dtype == RVL_STRING) {
+                const int64_t tiles = (m + kTileRows - 1) / kTileRows;
+                RVL_CUDA_TRY(cudaMemsetAsync(status->ptr, 0, (size_t)tiles * 8, core->stream));
+                StrGatherParams sp{};
+                sp.n_rows = m; sp.limit = -1; sp.sel = nullptr; sp.tile_prefix = nullptr; sp.row_base = row_base;
+                sp.offsets = (const int32_t*)s.offsets->ptr + s.offset; sp.data = (const uint8_t*)s.data->ptr; sp.valid = sv;
+                sp.out_offsets = (int32_t*)d.offsets->ptr; sp.out_data = (uint8_t*)d.data->ptr;
+                sp.tile_status = (uint64_t*)status->ptr; sp.byte_base_in = dctr + 2 * c + 1; sp.bytes_total_out = dctr + 2 * c + 1;
+                string_gather_kernel<<<(unsigned)tiles, kBlock, 0, core->stream>>>(sp);
+                core->launches++;
+            }
+            if (d.validity) {
+                bitcopy_kernel<<<grid_for((m + 31) / 32 + 1, 256, core->sm_count), 256, 0, core->stream>>>(
+                    sv, BitSrc{nullptr, 0, 0}, (uint32_t*)d.validity->ptr, (uint64_t)row_base, m);
+                core->launches++;
+            }
+            RVL_CUDA_TRY(cudaGetLastError());
+            row_base += m;
+        }
+        if (d.validity && total > 0) {
+            count_ones_kernel<<<grid_for((total + 31) / 32, 256, core->sm_count), 256, 0, core->stream>>>(
+                bitsrc_of(d.validity, 0, total), total, nullptr, nullptr, -1, dctr + 2 * c);
+            core->launches++;
+            RVL_CUDA_TRY(cudaGetLastError());
+        }
+        res->cols.push_back(std::move(d));
+    }
+    if (ncols * 2 > CtxCore::kSlotBase) return fail(RVL_INVALID_ARGUMENT, "too many columns");
+    RVL_CUDA_TRY(cudaMemcpyAsync(core->mailbox, dctr, ncols * 16, cudaMemcpyDeviceToHost, core->stream));
+    RVL_CUDA_TRY(cudaStreamSynchronize(core->stream));
+    for (size_t c = 0; c < ncols; ++c) {
+        DevColumn& d = res->cols[c];
+        if (d.dtype == RVL_NULL) { d.null_count = total; continue; }
+        if (d.validity) {
+            d.null_count = total - (int64_t)core->mailbox[2 * c];
+            if (d.null_count == 0) d.validity.reset();  // bitmap dropped when nothing is null (primitive.rs:180-185)
+        } else d.null_count = 0;
+        if (d.dtype == RVL_STRING) d.data_len = (int64_t)core->mailbox[2 * c + 1];
+    }
+    *out = res.release();
+    return RVL_OK;
+}
+
+// ------------------------------------------------------------------------------------------ synthetic tables
+int32_t rvl_gen_batch(rvl_ctx* ctx, const int32_t* kinds, const uint32_t* col_ids, const uint32_t* null_pct, int32_t ncols,
+                      uint64_t row0, int64_t n, rvl_batch** out) {
+    if (!ctx || !out || n < 0) return fail(RVL_INVALID_ARGUMENT, "bad argument");
+    const CoreRef& core = ctx->core;
+    RVL_CUDA_TRY(cudaSetDevice(core->device));
+    auto b = std::make_unique<rvl_batch>();
+    b->core = core; b->num_rows = n;
+    const int g8 = grid_for(n, 256, core->sm_count), gw = grid_for((n + 31) / 32, 256, core->sm_count);
+    for (int c = 0; c < ncols; ++c) {
+        DevColumn d;
+        d.length = n; d.offset = 0;
+        const int kind = kinds[c];
+        const uint32_t np = null_pct ? null_pct[c] : 0;
+        if (kind == RVL_SYNTH_BOOL) {
+            d.dtype = RVL_BOOLEAN;
+            RVL_TRY(dev_alloc_zeroed(core, (size_t)(n + 7) / 8, &d.values));
+            if (n > 0) { gen_bits_kernel<<<gw, 256, 0, core->stream>>>((uint32_t*)d.values->ptr, 0, col_ids[c], 0, row0, n); core->launches++; }
+        } else if (kind == RVL_SYNTH_STR) {
+            d.dtype = RVL_STRING;
+            if (n * 40 > (int64_t)INT32_MAX) return fail(RVL_OFFSET_OVERFLOW, "synthetic string column of " + std::to_string(n) + " rows may exceed the int32 offset range; use <= 50M rows per batch");
+            BufRef lens;
+            RVL_TRY(dev_alloc(core, (size_t)n * 4, &lens));
+            RVL_TRY(dev_alloc(core, (size_t)(n + 1) * 4, &d.offsets));
+            RVL_CUDA_TRY(cudaMemsetAsync(d.offsets->ptr, 0, 4, core->stream));
+            if (n > 0) {
+                gen_strlen_kernel<<<g8, 256, 0, core->stream>>>((int32_t*)lens->ptr, col_ids[c], np, row0, n);
+                scan_lengths_kernel<<<1, 1024, 0, core->stream>>>((const int32_t*)lens->ptr, (int32_t*)d.offsets->ptr, n);
+                core->launches += 2;
+            }
+            int32_t total_bytes = 0;
+            RVL_CUDA_TRY(cudaMemcpyAsync(&total_bytes, (const int32_t*)d.offsets->ptr + n, 4, cudaMemcpyDeviceToHost, core->stream));
+            RVL_CUDA_TRY(cudaStreamSynchronize(core->stream));
+            d.data_len = total_bytes;
+            RVL_TRY(dev_alloc(core, (size_t)total_bytes, &d.data));
+            if (n > 0) { gen_strbytes_kernel<<<g8, 256, 0, core->stream>>>((uint8_t*)d.data->ptr, (const int32_t*)d.offsets->ptr, col_ids[c], row0, n); core->launches++; }
+        } else {
+            d.dtype = kind == RVL_SYNTH_F64 ? RVL_FLOAT64 : RVL_INT64;
+            RVL_TRY(dev_alloc(core, (size_t)n * 8, &d.values));
+            if (n > 0) { gen_col8_kernel<<<g8, 256, 0, core->stream>>>((uint64_t*)d.values->ptr, kind, col_ids[c], row0, n); core->launches++; }
+        }
+        if (np > 0) {
+            RVL_TRY(dev_alloc_zeroed(core, (size_t)(n + 7) / 8, &d.validity));
+            if (n > 0) { gen_bits_kernel<<<gw, 256, 0, core->stream>>>((uint32_t*)d.validity->ptr, 1, col_ids[c], np, row0, n); core->launches++; }
+        } else d.null_count = 0;
+        RVL_CUDA_TRY(cudaGetLastError());
+        b->cols.push_back(std::move(d));
+    }
+    RVL_CUDA_TRY(cudaStreamSynchronize(core->stream));
+    *out = b.release();
+    return RVL_OK;
+}
+
+int32_t rvl_batch_checksum(rvl_ctx* ctx, const rvl_batch* batch, int32_t i, uint64_t* checksum) {
+    if (!ctx || !batch || !checksum) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    if (i < 0 || i >= (int32_t)batch->cols.size()) return fail(RVL_OUT_OF_BOUNDS, "Column index out of bounds");
+    const CoreRef& core = batch->core;
+    RVL_CUDA_TRY(cudaSetDevice(core->device));
+    const DevColumn& c = batch->cols[i];
+    const int64_t n = c.length;
+    BufRef counter;
+    RVL_TRY(dev_alloc_zeroed(core, 8, &counter));
+    unsigned long long* out = (unsigned long long*)counter->ptr;
+    const BitSrc v = bitsrc_of(c.validity, c.offset, n);
+    const int g = grid_for(n, 256, core->sm_count);
+    if (n > 0) {
+        if (c.dtype == RVL_INT64 || c.dtype == RVL_FLOAT64)
+            checksum_col8_kernel<<<g, 256, 0, core->stream>>>((const uint64_t*)c.values->ptr + c.offset, v, n, out);
+        else if (c.dtype == RVL_BOOLEAN)
+            checksum_bool_kernel<<<g, 256, 0, core->stream>>>(bitsrc_of(c.values, c.offset, n), v, n, out);
+        else if (c.dtype == RVL_STRING)
+            checksum_str_kernel<<<g, 256, 0, core->stream>>>((const int32_t*)c.offsets->ptr + c.offset, (const uint8_t*)c.data->ptr, v, n, out);
+        if (c.dtype != RVL_NULL) { core->launches++; RVL_CUDA_TRY(cudaGetLastError()); }
+    }
+    RVL_CUDA_TRY(cudaMemcpyAsync(core->mailbox, out, 8, cudaMemcpyDeviceToHost, core->stream));
+    RVL_CUDA_TRY(cudaStreamSynchronize(core->stream));
+    *checksum = core->mailbox[0];
+    return RVL_OK;
+}
+
+}  // extern "C"

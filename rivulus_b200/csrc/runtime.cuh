@@ -1,0 +1,93 @@
+// runtime.cuh — host-side runtime objects behind the C ABI (include/rivulus_gpu.h): context, stream-ordered
+// device memory, device-resident RecordBatch columns.  Internal to librivulus_gpu.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/rivulus_gpu.h"
+#include "device_utils.cuh"
+
+namespace rvl {
+
+extern thread_local std::string g_last_error;
+int fail(int code, const std::string& msg);
+
+#define RVL_CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                     \
+        cudaError_t e__ = (expr);                                                                            \
+        if (e__ != cudaSuccess) return ::rvl::fail(RVL_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+#define RVL_TRY(expr)                 \
+    do {                              \
+        int rc__ = (expr);            \
+        if (rc__ != RVL_OK) return rc__; \
+    } while (0)
+
+// One per rvl_ctx; shared by every buffer allocated from it so frees stay stream-ordered and valid.
+struct CtxCore {
+    int device = 0;
+    cudaStream_t stream = nullptr;   // compute stream: every kernel of the context
+    cudaStream_t copy_stream = nullptr;  // H2D staging of the streaming executor
+    int sm_count = 148;
+    std::atomic<int64_t> launches{0};
+    uint64_t* mailbox = nullptr;     // pinned host words the device counters are copied into
+    size_t mailbox_words = 0;
+    // the upper part of the mailbox is a ring of kSlotWords-word slots, one per in-flight fused launch
+    static constexpr size_t kSlotWords = 64, kSlots = 60, kSlotBase = 256;
+    std::atomic<uint32_t> slot_cursor{0};
+    cudaStream_t d2h_stream = nullptr;   // downloads of finished batches (overlaps H2D staging and kernels)
+    // optional kernel-level timing of the fused kernel (rvl_ctx_profile_*)
+    bool profile = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    double prof_ms = 0.0;
+    int64_t prof_launches = 0;
+    std::vector<double> prof_times;
+    int prof_flush();
+    uint64_t* next_slot() { return mailbox + kSlotBase + (size_t)(slot_cursor.fetch_add(1) % kSlots) * kSlotWords; }
+    ~CtxCore();
+};
+using CoreRef = std::shared_ptr<CtxCore>;
+
+struct DevBuffer {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    bool owned = true;
+    CoreRef core;
+    ~DevBuffer();
+};
+using BufRef = std::shared_ptr<DevBuffer>;
+
+// stream-ordered allocation from the device's default pool (release threshold = keep everything cached)
+int dev_alloc(const CoreRef& core, size_t bytes, BufRef* out);
+int dev_alloc_zeroed(const CoreRef& core, size_t bytes, BufRef* out);
+BufRef wrap_external(const CoreRef& core, const void* ptr, size_t bytes);
+
+struct DevColumn {
+    int32_t dtype = RVL_NULL;
+    int64_t length = 0;
+    int64_t offset = 0;
+    BufRef values;    // 8-byte values or Boolean value bitmap
+    BufRef validity;  // optional
+    BufRef offsets;   // String
+    BufRef data;      // String
+    int64_t data_len = 0;
+    int64_t null_count = -1;  // -1 = not computed yet
+};
+
+BitSrc bitsrc_of(const BufRef& buf, int64_t offset, int64_t length);
+
+}  // namespace rvl
+
+struct rvl_ctx {
+    rvl::CoreRef core;
+};
+struct rvl_batch {
+    rvl::CoreRef core;
+    int64_t num_rows = 0;
+    std::vector<rvl::DevColumn> cols;
+};

@@ -1,0 +1,316 @@
+// stream_exec.cu — the streaming executor: RecordBatches pushed from HOST memory flow through pinned,
+// multi-buffered H2D staging on a copy stream while the fused Filter+Select+Limit kernel of the previous
+// batch runs on the compute stream; LIMIT stops further transfers as soon as the device-side running
+// count (chained from batch to batch through a device word) reaches the limit.
+//
+// Replaces (reference, /root/reference/src): trait DataStream + MemoryStream/FilterStream/SelectStream
+// (execution/stream.rs:25-213), LimitStream (physical_plan/streaming.rs:246-288) and the final
+// collect_stream_batches concat (physical_plan/streaming.rs:343-352).
+#include <algorithm>
+#include <cstring>
+#include <deque>
+
+#include "filter_project.cuh"
+
+using namespace rvl;
+
+namespace {
+
+struct StagingColumn {
+    BufRef values, validity, offsets, data;  // device
+    void *h_values = nullptr, *h_validity = nullptr, *h_offsets = nullptr, *h_data = nullptr;  // pinned host (lazy)
+    size_t data_cap = 0, h_data_cap = 0;
+};
+
+struct Slot {
+    std::vector<StagingColumn> cols;
+    cudaEvent_t copied = nullptr;  // H2D of this slot finished
+    cudaEvent_t free_ev = nullptr; // last kernel reading this slot finished
+    bool used = false;
+};
+
+struct InFlight {
+    FpPending* pend;
+    int slot;
+};
+
+bool is_pinned_or_device(const void* p) {
+    if (p == nullptr) return true;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace
+
+struct rvl_stream {
+    CoreRef core;
+    std::vector<int32_t> dtypes;
+    rvl_predicate pred{};
+    std::string lit_str;
+    std::vector<int32_t> proj;
+    int64_t limit = -1;
+    int64_t batch_rows = 0;
+    std::vector<Slot> slots;
+    int next_slot = 0;
+    std::deque<InFlight> inflight;
+    BufRef cursor;  // two device words, ping-pong: rows emitted so far
+    int64_t pushed = 0, skipped = 0, h2d_bytes = 0;
+    bool limit_hit = false;
+    int64_t rows_out = 0;  // rows handed out through next()/collect()
+};
+
+static int ensure_pinned(void** p, size_t* cap, size_t need) {
+    if (*p != nullptr && (cap == nullptr || *cap >= need)) return RVL_OK;
+    if (*p != nullptr) { cudaFreeHost(*p); *p = nullptr; }
+    RVL_CUDA_TRY(cudaHostAlloc(p, need ? need : 1, cudaHostAllocDefault));
+    if (cap) *cap = need;
+    return RVL_OK;
+}
+
+// copy `bytes` from a caller buffer to the device slot on the copy stream, staging through pinned memory
+// when the caller's memory is pageable (so the caller may reuse its buffer as soon as push() returns)
+static int stage_copy(rvl_stream* s, void* dev_dst, const void* src, size_t bytes, void** pinned, size_t* pinned_cap, size_t pinned_need) {
+    if (bytes == 0) return RVL_OK;
+    const void* from = src;
+    if (!is_pinned_or_device(src)) {
+        RVL_TRY(ensure_pinned(pinned, pinned_cap, std::max(pinned_need, bytes)));
+        std::memcpy(*pinned, src, bytes);
+        from = *pinned;
+    }
+    RVL_CUDA_TRY(cudaMemcpyAsync(dev_dst, from, bytes, cudaMemcpyDefault, s->core->copy_stream));
+    s->h2d_bytes += (int64_t)bytes;
+    return RVL_OK;
+}
+
+static void poll_limit(rvl_stream* s) {
+    if (s->limit < 0 || s->limit_hit) return;
+    for (const InFlight& f : s->inflight) {
+        const uint64_t total = *reinterpret_cast<volatile uint64_t*>(f.pend->mailbox);
+        if (total != kMailboxPending && (int64_t)total >= s->limit) { s->limit_hit = true; return; }
+    }
+}
+
+extern "C" {
+
+int32_t rvl_stream_open(rvl_ctx* ctx, const int32_t* dtypes, int32_t ncols, const rvl_predicate* pred, const int32_t* proj, int32_t nproj,
+                        int64_t limit, const rvl_stream_config* cfg, rvl_stream** stream) {
+    if (!ctx || !stream || (ncols > 0 && !dtypes) || (nproj > 0 && !proj)) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    const CoreRef& core = ctx->core;
+    RVL_CUDA_TRY(cudaSetDevice(core->device));
+    auto s = std::make_unique<rvl_stream>();
+    s->core = core;
+    s->dtypes.assign(dtypes, dtypes + ncols);
+    for (int i = 0; i < nproj; ++i) {
+        if (proj[i] < 0 || proj[i] >= ncols)
+            return fail(RVL_OUT_OF_BOUNDS, "Column index " + std::to_string(proj[i]) + " out of bounds for " + std::to_string(ncols) + " columns");
+        s->proj.push_back(proj[i]);
+    }
+    if (pred) {
+        s->pred = *pred;
+        if (pred->mode != RVL_PRED_TRUE) {
+            if (pred->column < 0 || pred->column >= ncols) return fail(RVL_COLUMN_NOT_FOUND, "Column not found: index " + std::to_string(pred->column));
+            if (pred->mode == RVL_PRED_BOOL_COLUMN && dtypes[pred->column] != RVL_BOOLEAN)
+                return fail(RVL_TYPE_MISMATCH, "Predicate column is not of boolean type");  // stream.rs:147-153
+        }
+        if (pred->lit_str && pred->lit_str_len > 0) { s->lit_str.assign((const char*)pred->lit_str, (size_t)pred->lit_str_len); s->pred.lit_str = (const uint8_t*)s->lit_str.data(); }
+    } else {
+        s->pred.mode = RVL_PRED_TRUE;
+    }
+    s->limit = limit < 0 ? -1 : limit;
+    s->batch_rows = cfg && cfg->batch_rows > 0 ? cfg->batch_rows : (1 << 20);
+    const int n_slots = cfg && cfg->n_staging >= 1 ? cfg->n_staging : 2;
+    s->slots.resize((size_t)n_slots);
+    const size_t rows_cap = (size_t)s->batch_rows + 64;
+    for (Slot& sl : s->slots) {
+        sl.cols.resize((size_t)ncols);
+        for (int c = 0; c < ncols; ++c) {
+            StagingColumn& sc = sl.cols[(size_t)c];
+            if (dtypes[c] == RVL_INT64 || dtypes[c] == RVL_FLOAT64) RVL_TRY(dev_alloc(core, rows_cap * 8, &sc.values));
+            else if (dtypes[c] == RVL_BOOLEAN) RVL_TRY(dev_alloc_zeroed(core, rows_cap / 8 + 8, &sc.values));
+            else if (dtypes[c] == RVL_STRING) RVL_TRY(dev_alloc(core, (rows_cap + 1) * 4, &sc.offsets));
+            if (dtypes[c] != RVL_NULL) RVL_TRY(dev_alloc_zeroed(core, rows_cap / 8 + 8, &sc.validity));
+        }
+        RVL_CUDA_TRY(cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming));
+        RVL_CUDA_TRY(cudaEventCreateWithFlags(&sl.free_ev, cudaEventDisableTiming));
+    }
+    RVL_TRY(dev_alloc_zeroed(core, 16, &s->cursor));
+    RVL_CUDA_TRY(cudaStreamSynchronize(core->stream));
+    *stream = s.release();
+    return RVL_OK;
+}
+
+int32_t rvl_stream_push(rvl_stream* s, const rvl_column* cols, int32_t ncols, int32_t* accepted) {
+    if (!s || !accepted || (ncols > 0 && !cols)) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    const CoreRef& core = s->core;
+    RVL_CUDA_TRY(cudaSetDevice(core->device));
+    *accepted = 0;
+    if (ncols != (int32_t)s->dtypes.size()) return fail(RVL_SCHEMA_MISMATCH, "batch has " + std::to_string(ncols) + " columns but the stream schema has " + std::to_string(s->dtypes.size()));
+    const int64_t n = ncols > 0 ? cols[0].length : 0;
+    for (int c = 0; c < ncols; ++c) {
+        if (cols[c].dtype != s->dtypes[(size_t)c]) return fail(RVL_SCHEMA_MISMATCH, "Column " + std::to_string(c) + " does not match the stream schema");
+        if (cols[c].length != n) return fail(RVL_LENGTH_MISMATCH, "Column " + std::to_string(c) + " has length " + std::to_string(cols[c].length) + " but expected " + std::to_string(n));
+        if (cols[c].location != RVL_HOST) return fail(RVL_INVALID_ARGUMENT, "rvl_stream_push takes host buffers");
+    }
+    if (n > s->batch_rows) return fail(RVL_INVALID_ARGUMENT, "batch of " + std::to_string(n) + " rows exceeds the stream's batch_rows=" + std::to_string(s->batch_rows));
+
+    // LimitStream: once the limit is reached nothing more is pulled (streaming.rs:269-271)
+    poll_limit(s);
+    Slot& sl = s->slots[(size_t)s->next_slot];
+    if (!s->limit_hit && sl.used) {
+        // back-pressure: this slot's previous batch must have been consumed by its kernel; its mailbox is then
+        // visible too, so a tripped limit is noticed before any further byte crosses PCIe
+        RVL_CUDA_TRY(cudaEventSynchronize(sl.free_ev));
+        poll_limit(s);
+    }
+    if (s->limit_hit || s->limit == 0) { s->limit_hit = true; s->skipped++; return RVL_OK; }
+
+    auto view = std::make_unique<rvl_batch>();
+    view->core = core; view->num_rows = n;
+    for (int c = 0; c < ncols; ++c) {
+        const rvl_column& hc = cols[c];
+        StagingColumn& sc = sl.cols[(size_t)c];
+        const int64_t resid = hc.offset % 64, start = hc.offset - resid, span = resid + n;
+        const size_t rows_cap = (size_t)s->batch_rows + 64;
+        DevColumn d;
+        d.dtype = hc.dtype; d.length = n; d.offset = resid;
+        if (hc.dtype == RVL_INT64 || hc.dtype == RVL_FLOAT64) {
+            RVL_TRY(stage_copy(s, sc.values->ptr, (const uint8_t*)hc.values + start * 8, (size_t)span * 8, &sc.h_values, nullptr, rows_cap * 8));
+            d.values = sc.values;
+        } else if (hc.dtype == RVL_BOOLEAN) {
+            RVL_TRY(stage_copy(s, sc.values->ptr, (const uint8_t*)hc.values + start / 8, (size_t)(span + 7) / 8, &sc.h_values, nullptr, rows_cap / 8 + 8));
+            d.values = sc.values;
+        } else if (hc.dtype == RVL_STRING) {
+            RVL_TRY(stage_copy(s, sc.offsets->ptr, hc.offsets + start, (size_t)(span + 1) * 4, &sc.h_offsets, nullptr, (rows_cap + 1) * 4));
+            const int64_t first = hc.offsets[start], last = hc.offsets[start + span];
+            const size_t nbytes = (size_t)(last - first);
+            if (sc.data_cap < nbytes || !sc.data) {
+                // make sure no kernel still reads the old buffer: frees are ordered on the compute stream
+                sc.data.reset();
+                sc.data_cap = std::max(nbytes * 5 / 4 + 256, (size_t)1 << 20);
+                RVL_TRY(dev_alloc(core, sc.data_cap, &sc.data));
+                RVL_CUDA_TRY(cudaStreamSynchronize(core->stream));
+            }
+            RVL_TRY(stage_copy(s, sc.data->ptr, hc.data + first, nbytes, &sc.h_data, &sc.h_data_cap, nbytes));
+            d.offsets = sc.offsets;
+            // offsets stay absolute: present the data pointer shifted back by `first` (never dereferenced below the copy)
+            d.data = wrap_external(core, (const uint8_t*)sc.data->ptr - first, nbytes + (size_t)first);
+            d.data_len = last;
+        }
+        if (hc.validity != nullptr && hc.dtype != RVL_NULL) {
+            RVL_TRY(stage_copy(s, sc.validity->ptr, hc.validity + start / 8, (size_t)(span + 7) / 8, &sc.h_validity, nullptr, rows_cap / 8 + 8));
+            d.validity = sc.validity;
+        } else {
+            d.null_count = hc.dtype == RVL_NULL ? n : 0;
+        }
+        view->cols.push_back(std::move(d));
+    }
+    RVL_CUDA_TRY(cudaEventRecord(sl.copied, core->copy_stream));
+    RVL_CUDA_TRY(cudaStreamWaitEvent(core->stream, sl.copied, 0));
+
+    unsigned long long* cur = (unsigned long long*)s->cursor->ptr;
+    const int k = (int)(s->pushed & 1);
+    FpPending* pend = nullptr;
+    RVL_TRY(fp_launch(core, view.get(), &s->pred, s->proj.data(), (int32_t)s->proj.size(), s->limit, false, cur + k, cur + (k ^ 1), &pend));
+    RVL_CUDA_TRY(cudaEventRecord(sl.free_ev, core->stream));
+    // the next H2D into this slot must not start before this kernel has read it
+    sl.used = true;
+    s->inflight.push_back(InFlight{pend, s->next_slot});
+    s->next_slot = (s->next_slot + 1) % (int)s->slots.size();
+    // make the copy stream wait for the slot it is going to overwrite next
+    Slot& nx = s->slots[(size_t)s->next_slot];
+    if (nx.used) RVL_CUDA_TRY(cudaStreamWaitEvent(core->copy_stream, nx.free_ev, 0));
+    s->pushed++;
+    *accepted = 1;
+    return RVL_OK;
+}
+
+int32_t rvl_stream_next(rvl_stream* s, rvl_batch** out, int32_t* has_batch) {
+    if (!s || !out || !has_batch) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    *has_batch = 0; *out = nullptr;
+    if (s->inflight.empty()) return RVL_OK;
+    InFlight f = s->inflight.front();
+    s->inflight.pop_front();
+    rvl_batch* b = nullptr;
+    RVL_TRY(fp_finish(f.pend, &b, nullptr));
+    s->rows_out += b->num_rows;
+    if (s->limit >= 0 && s->rows_out >= s->limit) s->limit_hit = true;
+    *out = b; *has_batch = 1;
+    return RVL_OK;
+}
+
+int32_t rvl_stream_limit_reached(rvl_stream* s, int32_t* reached) {
+    if (!s || !reached) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    poll_limit(s);
+    *reached = (s->limit_hit || s->limit == 0) ? 1 : 0;
+    return RVL_OK;
+}
+
+int32_t rvl_stream_collect(rvl_stream* s, rvl_batch** out) {
+    if (!s || !out) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    std::vector<rvl_batch*> parts;
+    int rc = RVL_OK;
+    while (!s->inflight.empty()) {
+        rvl_batch* b = nullptr; int32_t has = 0;
+        rc = rvl_stream_next(s, &b, &has);
+        if (rc != RVL_OK) break;
+        // LimitStream stops yielding once the limit is met: later (empty) batches are never produced (streaming.rs:269-271)
+        if (has) parts.push_back(b);
+    }
+    if (rc == RVL_OK) {
+        // drop trailing batches produced after the limit was met (they are empty by construction)
+        if (s->limit >= 0) {
+            int64_t seen = 0; size_t keep = 0;
+            for (; keep < parts.size(); ++keep) { if (seen >= s->limit) break; seen += parts[keep]->num_rows; }
+            for (size_t i = keep; i < parts.size(); ++i) delete parts[i];
+            parts.resize(keep);
+        }
+        rvl_ctx tmp{s->core};
+        if (parts.empty()) {
+            // RecordBatch::empty(schema) (streaming.rs:347-349, record_batch.rs:402-421)
+            auto e = std::make_unique<rvl_batch>();
+            e->core = s->core; e->num_rows = 0;
+            for (int32_t p : s->proj) { DevColumn d; d.dtype = s->dtypes[(size_t)p]; d.null_count = 0; e->cols.push_back(d); }
+            *out = e.release();
+        } else {
+            rc = rvl_batch_concat(&tmp, parts.data(), (int32_t)parts.size(), out);
+        }
+    }
+    for (rvl_batch* b : parts) delete b;
+    return rc;
+}
+
+int32_t rvl_stream_stats(rvl_stream* s, int64_t* pushed, int64_t* skipped, int64_t* h2d_bytes) {
+    if (!s) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    if (pushed) *pushed = s->pushed;
+    if (skipped) *skipped = s->skipped;
+    if (h2d_bytes) *h2d_bytes = s->h2d_bytes;
+    return RVL_OK;
+}
+
+int32_t rvl_stream_close(rvl_stream* s) {
+    if (!s) return RVL_OK;
+    cudaSetDevice(s->core->device);
+    while (!s->inflight.empty()) {
+        rvl_batch* b = nullptr;
+        fp_finish(s->inflight.front().pend, &b, nullptr);
+        delete b;
+        s->inflight.pop_front();
+    }
+    cudaStreamSynchronize(s->core->copy_stream);
+    cudaStreamSynchronize(s->core->stream);
+    for (Slot& sl : s->slots) {
+        if (sl.copied) cudaEventDestroy(sl.copied);
+        if (sl.free_ev) cudaEventDestroy(sl.free_ev);
+        for (StagingColumn& sc : sl.cols) {
+            if (sc.h_values) cudaFreeHost(sc.h_values);
+            if (sc.h_validity) cudaFreeHost(sc.h_validity);
+            if (sc.h_offsets) cudaFreeHost(sc.h_offsets);
+            if (sc.h_data) cudaFreeHost(sc.h_data);
+        }
+    }
+    delete s;
+    return RVL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,336 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+Bit-exact bar: values (raw 64-bit patterns), bitmaps, string offsets/bytes, null counts, bitmap presence.
+
+Reference behaviour under test (files under /root/reference/src): physical_plan/plan.rs:97-173 (eager
+Filter/Select/Limit), execution/record_batch.rs:92-342 (slice/take/filter/concat), execution/stream.rs +
+physical_plan/streaming.rs (FilterStream/SelectStream/LimitStream), datatypes/series.rs:87-117 (truth table).
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from rivulus_b200 import capi
+from tests.parity import Col, assert_batches_equal, oracle_batch, random_col, run_cmp, run_mask, upload
+
+pytestmark = pytest.mark.gpu
+
+OPS = ["==", "!=", "<", ">", "<=", ">="]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+# ------------------------------------------------------------------ reference known-answer tests, through the GPU
+def fixture_cols():
+    # execution/record_batch.rs:594-604: id [1,2,3], name ["Alice", None, "Charlie"], active [T,F,T]
+    return [Col("i64", 3, np.array([1, 2, 3])), Col("str", 3, None, np.array([1, 0, 1], bool), [b"Alice", b"", b"Charlie"]),
+            Col("bool", 3, np.array([True, False, True]))]
+
+
+def test_golden_record_batch_filter(ctx):  # record_batch.rs:822-879
+    cols = fixture_cols()
+    for mask, valid, rows in [([1, 0, 1], None, 2), ([1, 1, 1], None, 3), ([0, 0, 0], None, 0), ([1, 0, 0], [1, 0, 1], 1)]:
+        m = Col("bool", 3, np.array(mask, bool), None if valid is None else np.array(valid, bool))
+        got = run_mask(ctx, cols + [m], 3, [0, 1, 2], tag="rb.filter")
+        assert got.num_rows() == rows
+    got = run_mask(ctx, cols + [Col("bool", 3, np.array([1, 0, 1], bool))], 3, [0, 1, 2])
+    assert got.download_column(0).to_list() == [1, 3] and got.download_column(1).to_list() == ["Alice", "Charlie"]
+
+
+def eager_cols():
+    # physical_plan/plan.rs:295-327: name, age, score
+    return [Col("str", 3, None, None, [b"Alice", b"Bob", b"Charlie"]), Col("i64", 3, np.array([25, 30, 35])),
+            Col("f64", 3, np.array([85.5, 92.0, 78.5]))]
+
+
+def test_golden_eager_filters(ctx):
+    cols = eager_cols()
+    got = run_cmp(ctx, cols, 1, ">", 25, [0, 1, 2], tag="plan.rs:505-525")
+    assert got.download_column(1).to_list() == [30, 35] and got.download_column(0).to_list() == ["Bob", "Charlie"]
+    got = run_cmp(ctx, cols, 0, "==", "Bob", [0, 1, 2], tag="plan.rs:528-547")
+    assert got.download_column(0).to_list() == ["Bob"]
+    got = run_cmp(ctx, cols, 2, "<", 90.0, [0, 1, 2], tag="plan.rs:550-569")
+    assert got.download_column(0).to_list() == ["Alice", "Charlie"]
+    got = run_cmp(ctx, cols, 1, ">", 100, [0, 1, 2], tag="plan.rs:572-589")
+    assert got.num_rows() == 0 and got.num_columns() == 3
+    got = run_cmp(ctx, cols, 1, ">", 25, [0, 1, 2], limit=1, tag="plan.rs:672-704")
+    assert got.download_column(0).to_list() == ["Bob"]
+    got = run_cmp(ctx, cols, 1, ">=", 30, [0, 2], tag="plan.rs:707-735")
+    assert got.download_column(0).to_list() == ["Bob", "Charlie"] and got.download_column(1).to_list() == [92.0, 78.5]
+
+
+def test_golden_limits(ctx):  # plan.rs:615-667
+    cols = eager_cols()
+    gb = upload(ctx, cols)
+    for lim, rows in [(2, 2), (10, 3), (0, 0)]:
+        got = ctx.filter_project(gb, capi.true_predicate(), [0, 1, 2], lim)
+        assert got.num_rows() == rows
+        want = oracle_batch(cols)
+        want = O.RecordBatch.concat([want.slice(0, min(lim, 3))])
+        assert_batches_equal(got, want, f"limit {lim}")
+
+
+# ------------------------------------------------------------------ truth table x column types x sizes
+@pytest.mark.parametrize("n", [0, 1, 63, 64, 65, 2047, 2048, 2049, 5000])
+def test_int64_all_ops_sizes(ctx, n):
+    rng = np.random.default_rng(n)
+    cols = [random_col(rng, "i64", n, 0.0, lo=0, hi=20), random_col(rng, "i64", n), random_col(rng, "f64", n)]
+    for op in OPS:
+        run_cmp(ctx, cols, 0, op, 10, [1, 2, 0], tag=f"n={n}")
+
+
+@pytest.mark.parametrize("op", OPS)
+def test_nulls_everywhere_int_float(ctx, op):
+    rng = np.random.default_rng(11)
+    n = 7001
+    cols = [random_col(rng, "i64", n, 0.2, lo=0, hi=50), random_col(rng, "f64", n, 0.3, specials=True),
+            random_col(rng, "i64", n, 0.15), random_col(rng, "bool", n, 0.25), random_col(rng, "null", n)]
+    for lit in (25, None, 25.0, "x", True):           # same type, Null literal, cross-type literals
+        run_cmp(ctx, cols, 0, op, lit, [0, 1, 2, 3, 4], tag="pred=i64")
+    for lit in (499.5, float("nan"), 0.0, -0.0, None, 7):
+        run_cmp(ctx, cols, 1, op, lit, [1, 0, 3], tag="pred=f64")
+
+
+@pytest.mark.parametrize("op", OPS)
+def test_boolean_string_null_predicate_columns(ctx, op):
+    rng = np.random.default_rng(5)
+    n = 4500
+    cols = [random_col(rng, "bool", n, 0.2), random_col(rng, "str", n, 0.2, maxlen=4, alphabet=b"ab"), random_col(rng, "null", n),
+            random_col(rng, "i64", n, 0.1), random_col(rng, "str", n, 0.3, maxlen=30, alphabet=b"xyz0123456789")]
+    for lit in (True, False, None, 1):
+        run_cmp(ctx, cols, 0, op, lit, [0, 3, 4], tag="pred=bool")
+    for lit in ("ab", "", "b", "abab", None, 3.5):
+        run_cmp(ctx, cols, 1, op, lit, [1, 3, 0], tag="pred=str")
+    for lit in (None, 1, "a"):
+        run_cmp(ctx, cols, 2, op, lit, [2, 3], tag="pred=nullcol")
+
+
+def test_all_null_survivors_and_no_nulls_bitmap_rule(ctx):
+    # bitmap present iff a SURVIVOR is null (primitive.rs:180-185); placeholder 0 under nulls (record_batch.rs:144)
+    n = 300
+    k = np.arange(n)
+    v = np.arange(n) * 10
+    valid = np.ones(n, bool); valid[200:] = False
+    cols = [Col("i64", n, k), Col("i64", n, v, valid), Col("f64", n, v * 0.5, valid), Col("bool", n, (k % 2 == 0), valid)]
+    got = run_cmp(ctx, cols, 0, "<", 100, [1, 2, 3], tag="no null survivor")     # survivors all valid -> no bitmaps
+    assert all(got.view(j).validity is None for j in range(3))
+    got = run_cmp(ctx, cols, 0, ">=", 250, [1, 2, 3], tag="all null survivors")
+    c = got.download_column(0)
+    assert c.null_count == 50 and not c.values.any()
+
+
+def test_sliced_views_with_bit_offsets(ctx):
+    # slices are (buffer, offset, length) views with arbitrary bit offsets (bitmap.rs:104-112, primitive.rs:107-117)
+    rng = np.random.default_rng(3)
+    for off in (1, 7, 8, 31, 33, 64, 67, 129):
+        n = 3000
+        cols = [random_col(rng, "i64", n, 0.2, offset=off, tail=5, lo=0, hi=100), random_col(rng, "f64", n, 0.2, offset=off + 3, tail=9),
+                random_col(rng, "bool", n, 0.2, offset=off + 1, tail=2), random_col(rng, "str", n, 0.2, offset=off, tail=1)]
+        run_cmp(ctx, cols, 0, ">", 50, [0, 1, 2, 3], tag=f"off={off}")
+        run_cmp(ctx, cols, 1, "<=", 500.0, [3, 2, 1, 0], limit=777, tag=f"off={off}")
+        run_mask(ctx, cols, 2, [0, 1, 2, 3], tag=f"off={off}")
+
+
+def test_device_side_slice_then_filter(ctx):
+    rng = np.random.default_rng(8)
+    n = 10000
+    cols = [random_col(rng, "i64", n, 0.1, lo=0, hi=100), random_col(rng, "f64", n, 0.1), random_col(rng, "bool", n, 0.1),
+            random_col(rng, "str", n, 0.1)]
+    gb, ob = upload(ctx, cols), oracle_batch(cols)
+    for off, ln in [(0, n), (1, 100), (37, 5000), (4099, 2048), (n - 1, 1), (500, 0)]:
+        got = ctx.filter_project(gb.slice(off, ln), capi.predicate(0, ">=", 40), [3, 2, 1, 0])
+        want = ob.slice(off, ln).filter_project_cmp(0, ">=", 40, [3, 2, 1, 0])
+        assert_batches_equal(got, want, f"slice({off},{ln})")
+    with pytest.raises(capi.RivulusError) as ei:
+        gb.slice(n - 1, 2)
+    assert ei.value.status == capi.OUT_OF_BOUNDS and "Slice out of bounds" in ei.value.message
+
+
+@pytest.mark.parametrize("sel", [0.001, 0.1, 0.5, 0.9, 1.0])
+def test_million_rows_selectivity(ctx, sel):
+    rng = np.random.default_rng(int(sel * 1000))
+    n = 1_000_003
+    cols = [Col("i64", n, rng.integers(0, 1000, n)), random_col(rng, "i64", n, 0.1, lo=-2**62, hi=2**62), random_col(rng, "f64", n),
+            random_col(rng, "i64", n, lo=-2**62, hi=2**62), random_col(rng, "f64", n, 0.05), random_col(rng, "bool", n, 0.1)]
+    thr = int(round(1000 * (1 - sel))) - 1
+    run_cmp(ctx, cols, 0, ">", thr, [1, 2, 3, 4, 5], tag=f"sel={sel}")
+
+
+def test_many_columns_multi_launch(ctx):
+    # > 8 fixed-width and > 16 bit-packed columns: replays the selection bitmap over several launches
+    rng = np.random.default_rng(21)
+    n = 6000
+    cols = [random_col(rng, "i64", n, lo=0, hi=10)]
+    for i in range(11):
+        cols.append(random_col(rng, "i64" if i % 2 else "f64", n, 0.2))
+    for i in range(9):
+        cols.append(random_col(rng, "bool", n, 0.2))
+    proj = list(range(1, len(cols))) + [0]
+    run_cmp(ctx, cols, 0, ">", 4, proj, tag="21 cols")
+    run_cmp(ctx, cols, 0, ">", 4, proj, limit=1234, tag="21 cols limit")
+
+
+@pytest.mark.parametrize("limit", [0, 1, 31, 32, 33, 1000, 2048, 2049, 100000])
+def test_limit_semantics(ctx, limit):
+    rng = np.random.default_rng(limit)
+    n = 50_000
+    cols = [random_col(rng, "i64", n, 0.1, lo=0, hi=100), random_col(rng, "f64", n, 0.1), random_col(rng, "bool", n, 0.1),
+            random_col(rng, "str", n, 0.1, maxlen=20)]
+    run_cmp(ctx, cols, 0, ">", 49, [0, 1, 2, 3], limit=limit, tag="limit")
+    run_mask(ctx, cols, 2, [3, 1], limit=limit, tag="limit mask")
+
+
+def test_strings_long_and_empty(ctx):
+    rng = np.random.default_rng(99)
+    n = 9000
+    strings = []
+    for i in range(n):
+        L = [0, 1, 5, 24, 40, 200, 1500][int(rng.integers(0, 7))]
+        strings.append(bytes(rng.integers(97, 123, L).astype(np.uint8)))
+    valid = rng.random(n) > 0.1
+    cols = [random_col(rng, "f64", n, 0.1), Col("str", n, None, valid, strings), Col("str", n, None, None, ["ü€🦀".encode()] * n)]
+    run_cmp(ctx, cols, 0, ">", 300.0, [1, 2, 0], tag="strings")
+    run_cmp(ctx, cols, 0, "<", 300.0, [1], tag="strings nulls pass <")
+
+
+def test_predicate_mask_kernel(ctx):
+    rng = np.random.default_rng(4)
+    n = 70_001
+    cols = [random_col(rng, "i64", n, 0.2, lo=0, hi=10), random_col(rng, "f64", n, 0.2)]
+    gb = upload(ctx, cols)
+    for op in OPS:
+        m = ctx.predicate_mask(gb, capi.predicate(0, op, 5)).download_column(0)
+        bits = capi.unpack_bits(m.values, n)
+        want = [O.eval_cmp(None if not cols[0].valid[i] else int(cols[0].values[i]), op, 5) for i in range(0, n, 997)]
+        assert [bool(b) for b in bits[::997]] == want
+
+
+# ------------------------------------------------------------------ batch ops: concat / select / download
+def test_concat_matches_reference(ctx):  # record_batch.rs:245-342, tests :882-949
+    rng = np.random.default_rng(17)
+    parts = []
+    for n, nf in [(100, 0.0), (3000, 0.3), (0, 0.0), (65, 0.5), (2048, 0.0)]:
+        parts.append([random_col(rng, "i64", n, nf, offset=3, tail=2), random_col(rng, "f64", n, nf), random_col(rng, "bool", n, nf, offset=5),
+                      random_col(rng, "str", n, nf, offset=1), random_col(rng, "null", n)])
+    got = ctx.concat([upload(ctx, p) for p in parts])
+    want = O.RecordBatch.concat([oracle_batch(p) for p in parts])
+    assert_batches_equal(got, want, "concat")
+    novalid = [[random_col(rng, "i64", 10)], [random_col(rng, "i64", 20)]]
+    got = ctx.concat([upload(ctx, p) for p in novalid])
+    assert got.view(0).validity is None
+    assert_batches_equal(got, O.RecordBatch.concat([oracle_batch(p) for p in novalid]), "concat no nulls")
+    with pytest.raises(capi.RivulusError) as ei:
+        ctx.concat([upload(ctx, [random_col(rng, "i64", 4)]), upload(ctx, [random_col(rng, "f64", 4)])])
+    assert ei.value.status == capi.SCHEMA_MISMATCH and "All batches must have the same schema" in ei.value.message
+    with pytest.raises(capi.RivulusError) as ei:
+        ctx.concat([])
+    assert "Cannot concatenate empty batch list" in ei.value.message
+
+
+def test_select_and_errors(ctx):
+    cols = fixture_cols()
+    gb = upload(ctx, cols)
+    s = gb.select([2, 0])
+    assert s.num_columns() == 2 and s.download_column(1).to_list() == [1, 2, 3]
+    with pytest.raises(capi.RivulusError) as ei:
+        gb.select([0, 5])
+    assert ei.value.status == capi.OUT_OF_BOUNDS and "Column index 5 out of bounds for 3 columns" in ei.value.message
+    with pytest.raises(capi.RivulusError) as ei:
+        ctx.filter_project(gb, capi.mask_predicate(0), [0])          # stream.rs:147-153
+    assert ei.value.status == capi.TYPE_MISMATCH
+    with pytest.raises(capi.RivulusError) as ei:
+        ctx.upload([cols[0].gpu(), Col("i64", 2, np.array([1, 2])).gpu()])   # record_batch.rs:33-38
+    assert ei.value.status == capi.LENGTH_MISMATCH and "Column 1 has length 2 but expected 3" in ei.value.message
+    p = capi.predicate(0, "==", 1); p.op = capi.OPS["+"]
+    with pytest.raises(capi.RivulusError) as ei:
+        ctx.filter_project(gb, p, [0])                                # plan.rs:121-127
+    assert ei.value.status == capi.INVALID_OPERATION
+
+
+# ------------------------------------------------------------------ streaming executor vs the reference's stream chain
+@pytest.mark.parametrize("limit", [-1, 0, 1, 1000, 5000, 10**7])
+@pytest.mark.parametrize("pinned", [False, True])
+def test_stream_filter_select_limit(ctx, limit, pinned):
+    rng = np.random.default_rng(limit + 7)
+    batches = []
+    for n in [4096, 1, 5000, 0, 2048, 3333]:
+        batches.append([random_col(rng, "i64", n, 0.1, lo=0, hi=100), random_col(rng, "f64", n, 0.1), random_col(rng, "bool", n, 0.2),
+                        random_col(rng, "str", n, 0.1, maxlen=16)])
+    dtypes = [capi.INT64, capi.FLOAT64, capi.BOOLEAN, capi.STRING]
+    st = ctx.open_stream(dtypes, capi.mask_predicate(2), [0, 3, 1], limit, batch_rows=8192, n_staging=2)
+    keep = []
+    for b in batches:
+        gcols = [c.gpu() for c in b]
+        if pinned:   # page-locked sources are copied straight from the caller's buffers (no staging memcpy)
+            for gc in gcols:
+                for f in ("values", "validity", "offsets", "data"):
+                    a = getattr(gc, f)
+                    if a is not None and a.size:
+                        v, owner = capi.pinned_like(a)
+                        setattr(gc, f, v)
+                        keep.append(owner)
+        st.push(gcols)
+    got = st.collect()
+    st.close()
+    plan = O.StreamingPhysicalPlan.memory_source([oracle_batch(b) for b in batches]).filter("c2").select(["c0", "c3", "c1"])
+    if limit >= 0:
+        plan = plan.limit(limit)
+    assert_batches_equal(got, plan.collect(), f"stream limit={limit}")
+
+
+def test_stream_limit_stops_transfers(ctx):
+    rng = np.random.default_rng(2)
+    n = 65536
+    st = ctx.open_stream([capi.INT64, capi.INT64], capi.predicate(0, ">", 899), [1], 1000, batch_rows=n, n_staging=2)
+    accepted = 0
+    cols_all = []
+    for i in range(16):
+        cols = [Col("i64", n, rng.integers(0, 1000, n)), random_col(rng, "i64", n)]
+        cols_all.append(cols)
+        accepted += bool(st.push([c.gpu() for c in cols]))
+    got = st.collect()
+    stats = st.stats()
+    st.close()
+    assert got.num_rows() == 1000
+    assert stats["batches_pushed"] == accepted <= 3 and stats["batches_skipped"] >= 13   # ideal 1; pipeline depth 2 allows <= 3
+    ob = O.RecordBatch.concat([oracle_batch(c) for c in cols_all[:2]]).filter_project_cmp(0, ">", 899, [1], 1000)
+    assert_batches_equal(got, ob, "stream early stop")
+
+
+# ------------------------------------------------------------------ sharded (row-range) execution on one GPU
+def test_sharded_two_contexts_one_gpu(ctx):
+    rng = np.random.default_rng(31)
+    n = 200_000
+    cols = [random_col(rng, "i64", n, 0.05, lo=0, hi=1000), random_col(rng, "f64", n, 0.05), random_col(rng, "bool", n, 0.05)]
+    ob = oracle_batch(cols)
+    ctx2 = capi.Context(0)
+    whole = upload(ctx, cols)
+    for limit in (-1, 5000, 150_000):
+        shards, ranges = [], []
+        for r in range(2):
+            b, e = capi.shard_range(n, r, 2)
+            assert b % 64 == 0
+            ranges.append((b, e))
+            shards.append(whole.slice(b, e - b))
+        outs, counts = capi.filter_project_sharded([ctx, ctx2], shards, capi.predicate(0, ">", 499), [0, 1, 2], limit)
+        got = ctx.concat(outs)
+        want = ob.filter_project_cmp(0, ">", 499, [0, 1, 2], limit)
+        assert sum(counts) == want.num_rows()
+        assert_batches_equal(got, want, f"sharded limit={limit}")
+    ctx2.close()
+
+
+# ------------------------------------------------------------------ full-size properties (count + order-sensitive checksums)
+@pytest.mark.parametrize("thr,n", [(998, 64_000_000), (499, 64_000_000), (99, 32_000_000)])
+def test_large_synthetic_checksums(ctx, thr, n):
+    spec = [(capi.SYNTH_KEY1000, 0, 0), (capi.SYNTH_I64, 1, 0), (capi.SYNTH_F64, 2, 0), (capi.SYNTH_I64, 3, 0), (capi.SYNTH_F64, 4, 0),
+            (capi.SYNTH_BOOL, 5, 0)]
+    gb = ctx.gen_batch(spec, n)
+    got = ctx.filter_project(gb, capi.predicate(0, ">", thr), [1, 2, 3, 4, 5])
+    count, sums = O.synth_filter_checksums(n, 0, capi.SYNTH_KEY1000, 0, ">", thr, [(s[0], s[1]) for s in spec[1:]])
+    assert got.num_rows() == count
+    assert [got.checksum(j) for j in range(5)] == sums

@@ -29,6 +29,8 @@ struct PredPlan {
     int kind = kPredTrue;
     uint32_t truth = 0, keep_null = 0, pb_a = 0, pb_b = 0;
     int64_t lit_bits = 0;
+    uint64_t range_lo = 0, range_span = 0;
+    uint32_t range_neg = 0;
     const uint64_t* values = nullptr;
     int vec_ok = 0;
     BitSrc valid{nullptr, 0, 0};
@@ -78,8 +80,24 @@ static int lower_predicate(const CoreRef& core, const rvl_batch* in, const rvl_p
             pp->kind = c.dtype == RVL_INT64 ? kPredI64 : kPredF64;
             pp->values = (const uint64_t*)c.values->ptr + c.offset;
             pp->vec_ok = (reinterpret_cast<uintptr_t>(pp->values) & 15) == 0;
-            if (c.dtype == RVL_INT64) pp->lit_bits = pred->lit_i64;
-            else std::memcpy(&pp->lit_bits, &pred->lit_f64, 8);
+            if (c.dtype == RVL_INT64) {
+                // every i64 comparison is one unsigned range test in the kernel: keep = ((v - lo) <= span) != neg
+                const int64_t L = pred->lit_i64;
+                const uint64_t umin = (uint64_t)INT64_MIN, umax = (uint64_t)INT64_MAX;
+                auto range = [&](uint64_t lo, uint64_t hi, uint32_t neg) { pp->range_lo = lo; pp->range_span = hi - lo; pp->range_neg = neg; };
+                auto none = [&]() { pp->range_lo = 0; pp->range_span = UINT64_MAX; pp->range_neg = 1; };
+                switch (pred->op) {
+                    case RVL_OP_EQ: range((uint64_t)L, (uint64_t)L, 0); break;
+                    case RVL_OP_NOTEQ: range((uint64_t)L, (uint64_t)L, 1); break;
+                    case RVL_OP_LT: if (L == INT64_MIN) none(); else range(umin, (uint64_t)(L - 1), 0); break;
+                    case RVL_OP_LTEQ: range(umin, (uint64_t)L, 0); break;
+                    case RVL_OP_GT: if (L == INT64_MAX) none(); else range((uint64_t)(L + 1), umax, 0); break;
+                    default: range((uint64_t)L, umax, 0); break;  // GTEQ
+                }
+                pp->lit_bits = L;
+            } else {
+                std::memcpy(&pp->lit_bits, &pred->lit_f64, 8);
+            }
             return RVL_OK;
         }
         case RVL_BOOLEAN: {
@@ -113,18 +131,36 @@ static int lower_predicate(const CoreRef& core, const rvl_batch* in, const rvl_p
     }
 }
 
-static void launch_fused(const CoreRef& core, int kind, const FusedParams& fp, int64_t tiles) {
-    const dim3 grid((unsigned)tiles), block(kBlock);
+template <int PRED>
+static void fused_opt_in_smem(int device) {
+    // one-time per instantiation and device: opt in to > 48 KB dynamic shared memory
+    static bool done[64] = {false};
+    if (!done[device & 63]) {
+        cudaFuncSetAttribute(fused_filter_project_kernel<PRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
+        done[device & 63] = true;
+    }
+}
+
+static void launch_fused(const CoreRef& core, int kind, const FusedParams& fp) {
+    switch (kind) {
+        case kPredI64: fused_opt_in_smem<kPredI64>(core->device); break;
+        case kPredF64: fused_opt_in_smem<kPredF64>(core->device); break;
+        case kPredBits: fused_opt_in_smem<kPredBits>(core->device); break;
+        default: fused_opt_in_smem<kPredTrue>(core->device); break;
+    }
+    // one CTA per super-tile of 8192 rows, taken in blockIdx order (the look-back relies on in-order dispatch)
+    const dim3 grid((unsigned)fp.n_super), block(kBlock);
+    const size_t smem = sizeof(FusedSmem);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (core->profile) {
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0, core->stream);
     }
     switch (kind) {
-        case kPredI64: fused_filter_project_kernel<kPredI64><<<grid, block, 0, core->stream>>>(fp); break;
-        case kPredF64: fused_filter_project_kernel<kPredF64><<<grid, block, 0, core->stream>>>(fp); break;
-        case kPredBits: fused_filter_project_kernel<kPredBits><<<grid, block, 0, core->stream>>>(fp); break;
-        default: fused_filter_project_kernel<kPredTrue><<<grid, block, 0, core->stream>>>(fp); break;
+        case kPredI64: fused_filter_project_kernel<kPredI64><<<grid, block, smem, core->stream>>>(fp); break;
+        case kPredF64: fused_filter_project_kernel<kPredF64><<<grid, block, smem, core->stream>>>(fp); break;
+        case kPredBits: fused_filter_project_kernel<kPredBits><<<grid, block, smem, core->stream>>>(fp); break;
+        default: fused_filter_project_kernel<kPredTrue><<<grid, block, smem, core->stream>>>(fp); break;
     }
     if (core->profile) {
         cudaEventRecord(e1, core->stream);
@@ -199,7 +235,10 @@ int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pre
         const int launches_needed = std::max<int>(1, std::max<int>(((int)col8s.size() + kMaxCol8 - 1) / kMaxCol8, ((int)bitcols.size() + kMaxBitCols - 1) / kMaxBitCols));
         const bool need_sel = want_mask || !strjobs.empty() || launches_needed > 1;
         BufRef status, sel, tile_prefix;
-        RVL_TRY(dev_alloc_zeroed(core, (size_t)tiles * 8 * (size_t)launches_needed, &status));
+        // per launch: one look-back descriptor per super-tile, zeroed together
+        const int64_t n_super = (n + kSuperRows - 1) / kSuperRows;
+        const size_t status_words = (size_t)n_super;
+        RVL_TRY(dev_alloc_zeroed(core, status_words * 8 * (size_t)launches_needed, &status));
         pend->temps.push_back(status);
         if (need_sel) {
             RVL_TRY(dev_alloc_zeroed(core, (size_t)((n + 63) / 64) * 8, &sel));
@@ -209,10 +248,11 @@ int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pre
 
         for (int L = 0; L < launches_needed; ++L) {
             FusedParams fp{};
-            fp.n_rows = n; fp.limit = limit;
+            fp.n_rows = n; fp.n_super = n_super; fp.limit = limit;
             int kind = pp.kind;
             if (L == 0) {
                 fp.pred_values = pp.values; fp.lit_bits = pp.lit_bits; fp.pred_valid = pp.valid; fp.truth = pp.truth;
+                fp.range_lo = pp.range_lo; fp.range_span = pp.range_span; fp.range_neg = pp.range_neg;
                 fp.keep_null = pp.keep_null; fp.pred_vec_ok = pp.vec_ok; fp.pb_a = pp.pb_a; fp.pb_b = pp.pb_b; fp.pb_vals = pp.pb_vals;
                 fp.sel_out = need_sel ? (uint32_t*)sel->ptr : nullptr;
                 fp.tile_prefix_out = tile_prefix ? (uint64_t*)tile_prefix->ptr : nullptr;
@@ -225,7 +265,7 @@ int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pre
             }
             fp.base_in = base_in;
             fp.done_flag = done_flag;
-            fp.tile_status = (uint64_t*)status->ptr + (size_t)L * (size_t)tiles;
+            fp.tile_status = (uint64_t*)status->ptr + (size_t)L * status_words;
             const int c0 = L * kMaxCol8, c1 = std::min<int>((int)col8s.size(), c0 + kMaxCol8);
             fp.n_col8 = std::max(0, c1 - c0);
             for (int k = 0; k < fp.n_col8; ++k) fp.col8[k] = col8s[(size_t)(c0 + k)];
@@ -233,7 +273,7 @@ int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pre
             fp.n_bits = std::max(0, b1 - b0);
             for (int k = 0; k < fp.n_bits; ++k) fp.bits[k] = bitcols[(size_t)(b0 + k)];
             if (L > 0 && limit >= 0) RVL_CUDA_TRY(cudaMemsetAsync(done_flag, 0, 4, core->stream));
-            launch_fused(core, kind, fp, tiles);
+            launch_fused(core, kind, fp);
             RVL_CUDA_TRY(cudaGetLastError());
         }
 

@@ -7,10 +7,27 @@
 //             execution/array/bitmap.rs:142-155 (bit-at-a-time BitmapBuilder::append)
 //
 // Data layout in HBM: Arrow columns — 8-byte values, LSB-first bitmaps (1 = valid / true), any
-// (offset, length) view.  A tile is 2048 consecutive rows; warp w owns rows [256w, 256w+256) of the
-// tile as 4 groups of 64 rows; lane l of a group owns rows 2l and 2l+1, i.e. ONE 128-bit load per
-// 8-byte column per group.  Two ballots per group (even rows / odd rows) give the selection masks;
-// popc of the lower lanes gives each lane its rank in row order.
+// (offset, length) view.
+//
+// Work decomposition.  A CTA (256 threads) owns one SUPER-TILE of 8192 consecutive rows = 4 sub-tiles of
+// 2048 rows.  Inside a sub-tile warp w owns rows [256w, 256w+256) as 4 groups of 64 rows; lane l of a group
+// owns rows 2l and 2l+1, i.e. ONE 128-bit access per 8-byte column per group.  Two ballots per group (even
+// rows / odd rows) give the group's 64-bit selection word in row order.
+//
+//   phase A  the predicate column of the whole super-tile (64 KB) is fetched with four TMA 1-D bulk copies
+//            (cp.async.bulk + mbarrier::complete_tx) issued by one thread at CTA start — 64 KB per CTA and
+//            ~190 KB per SM in flight without holding a single register; each sub-tile is evaluated as its
+//            copy lands; the selection words and per-warp counts stay in shared memory.
+//   order    ONE decoupled look-back per super-tile (256 descriptors per round, run by warp 0) resolves the
+//            global output offset; the other warps meanwhile gather and stage the first sub-tile, which
+//            only needs tile-local ranks.  Super-tiles are taken in blockIdx order, so a CTA only waits on
+//            CTAs that were dispatched before it (resident or finished).
+//   phase B  warp-local: a warp's survivors of a sub-tile form one contiguous output run.  The warp gathers
+//            them with predicated 128-bit loads (two columns in flight), stages them in output order in its
+//            private 8 KB slice of the (by then dead) predicate buffer and writes the run out contiguously;
+//            bit-packed columns are compacted with warp REDUX.OR into staged words and funnel-shifted to the
+//            output bit position (boundary words OR-ed atomically).  No block barrier after the look-back
+//            join, so the warps of a CTA drift apart and loads, staging and stores overlap.
 //
 // HBM roofline: per row the kernel must read the predicate value (8 B [+1 bit
 // validity]), the 32-B sectors of each projected column that hold at least one survivor, and write
@@ -22,8 +39,11 @@
 namespace rvl {
 
 constexpr int kMaxCol8 = 8;      // 8-byte columns compacted per launch
-constexpr int kMaxBitCols = 16;  // bit-packed columns compacted per launch
-constexpr int kSparseTile = 32;  // tiles with <= this many survivors scatter straight from registers
+constexpr int kMaxBitCols = 8;   // bit-packed columns compacted per launch
+constexpr int kWarpBitWords = 256 / 32 + 2;     // a warp emits at most 256 survivors per sub-tile
+constexpr int kSub = 4;                        // sub-tiles per super-tile
+constexpr int kSuperRows = kSub * kTileRows;   // 8192 rows per CTA
+constexpr int kStageBufs = 4;                  // staging buffers (alias the predicate buffer)
 
 enum PredKind : int { kPredI64 = 0, kPredF64 = 1, kPredBits = 2, kPredTrue = 3 };
 
@@ -43,14 +63,19 @@ struct BitCol {
 
 struct FusedParams {
     int64_t n_rows;
-    int64_t limit;  // < 0: none; else survivors whose global output index >= limit are dropped
+    int64_t n_super;  // super-tiles = gridDim.x
+    int64_t limit;    // < 0: none; else survivors whose global output index >= limit are dropped
     // comparison predicate: keep = valid ? truth[cmp(value, literal)] : keep_null
     const uint64_t* pred_values;
-    int64_t lit_bits;
+    int64_t lit_bits;    // Float64: literal bits for the 3-way compare + truth mask
+    // Int64: every comparison is one unsigned range test, keep = ((v - range_lo) <= range_span) != range_neg
+    uint64_t range_lo, range_span;
+    uint32_t range_neg;
+    uint32_t pad1;
     BitSrc pred_valid;
     uint32_t truth;      // bit0: value < lit, bit1: ==, bit2: >, bit3: unordered (NaN)
     uint32_t keep_null;  // 0 / 1: what a null row evaluates to (series.rs:105-107 puts Null below everything)
-    int32_t pred_vec_ok;
+    int32_t pred_vec_ok; // predicate values are 16-byte aligned: TMA bulk copies + 128-bit accesses
     int32_t n_col8;
     int32_t n_bits;
     // bitmap predicate: sel = (valid & ((vals & a) ^ b)) | (~valid & keep_null)
@@ -59,13 +84,27 @@ struct FusedParams {
     BitSrc pb_vals;
     Col8 col8[kMaxCol8];
     BitCol bits[kMaxBitCols];
-    uint64_t* tile_status;               // one descriptor per tile, zeroed before the launch
+    uint64_t* tile_status;               // one descriptor per super-tile, zeroed before the launch
     const unsigned long long* base_in;   // rows already emitted by earlier batches of the same query (streaming), or nullptr.
                                          // The limit applies to base + rank; output buffers are indexed by rank alone.
     unsigned long long* total_out;       // base + survivors of this launch (saturates at >= limit once the limit trips)
-    uint32_t* done_flag;                 // set once some tile's inclusive prefix reaches the limit
+    uint32_t* done_flag;                 // set once some super-tile's inclusive prefix reaches the limit
     uint32_t* sel_out;                   // optional: row-order selection bitmap (n_rows bits, 8-byte aligned)
-    uint64_t* tile_prefix_out;           // optional: exclusive output prefix of every tile
+    uint64_t* tile_prefix_out;           // optional: exclusive output prefix of every 2048-row tile
+};
+
+// dynamic shared memory of the fused kernel
+struct __align__(128) FusedSmem {
+    // phase A: the super-tile's predicate values (TMA destination); phase B: 4 staging buffers of 2048 survivors
+    uint64_t buf[kSub][kTileRows];                // 64 KB
+    uint32_t sel0[kSub][kTileRows / 64];          // per 64-row group: keep mask of the even rows (lane l <-> row 2l)
+    uint32_t sel1[kSub][kTileRows / 64];          //                   keep mask of the odd rows  (lane l <-> row 2l+1)
+    uint32_t wbits[kWarps][kMaxBitCols][kWarpBitWords];  // per warp: compacted bit columns of the run being emitted
+    uint32_t warp_count[kSub][kWarps];
+    uint64_t mbar[kSub];                          // one single-use mbarrier per sub-tile copy
+    uint64_t excl;
+    uint64_t base;
+    uint32_t done;
 };
 
 template <int PRED>
@@ -79,268 +118,411 @@ __device__ __forceinline__ uint32_t cmp_code(uint64_t bits, int64_t lit_bits) {
     }
 }
 
+// ---- TMA 1-D bulk copy + mbarrier (sm_90+/sm_100a) ------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0u;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+
+// 256-descriptor-wide look-back run by one warp (8 predecessors per lane per round)
+__device__ __forceinline__ uint64_t lookback_exclusive_wide(const uint64_t* status, int64_t tile, int lane) {
+    uint64_t exclusive = 0;
+    int64_t base = tile - 1;
+    while (true) {
+        uint64_t s[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int64_t idx = base - (j * 32 + lane);
+            s[j] = idx >= 0 ? ld_relaxed_gpu(status + idx) : kStatusPrefix;  // virtual tile -1: prefix 0
+        }
+        bool found = false;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (!found) {
+                const int64_t idx = base - (j * 32 + lane);
+                while ((s[j] & kStatusMask) == 0) s[j] = ld_relaxed_gpu(status + idx);
+                const uint32_t prefix_lanes = __ballot_sync(0xFFFFFFFFu, (s[j] & kStatusMask) == kStatusPrefix);
+                const int first = __ffs(prefix_lanes) - 1;
+                const uint64_t take = (first < 0 || lane <= first) ? (s[j] & kValueMask) : 0ull;
+                exclusive += warp_sum_u64(take);
+                found = first >= 0;
+            }
+        }
+        if (found) break;
+        base -= 256;
+    }
+    return exclusive;
+}
+
 template <int PRED>
-__global__ void __launch_bounds__(kBlock, 4) fused_filter_project_kernel(const __grid_constant__ FusedParams p) {
-    __shared__ __align__(16) uint64_t s_stage[2][kTileRows];
-    __shared__ uint32_t s_bits[kMaxBitCols][kTileWords + 2];
-    __shared__ uint32_t s_warp_count[kWarps];
-    __shared__ uint64_t s_excl;
-    __shared__ uint64_t s_base;
-    __shared__ uint32_t s_done;
+__global__ void __launch_bounds__(kBlock, 3) fused_filter_project_kernel(const __grid_constant__ FusedParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FusedSmem& sm = *reinterpret_cast<FusedSmem*>(smem_raw);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int64_t tile = blockIdx.x;
-    const int64_t warp_row0 = tile * kTileRows + (int64_t)warp * (kGroups * 64);
+    constexpr bool kNumeric = (PRED == kPredI64 || PRED == kPredF64);
+    constexpr uint32_t kTileBytes = kTileRows * 8;
+    const int64_t super = blockIdx.x;
+    const int64_t super_row0 = super * kSuperRows;
+    const bool use_tma = kNumeric && p.pred_vec_ok != 0;
 
-    // LIMIT early termination (streaming.rs:269-271 / plan.rs:163): once an earlier tile's inclusive
-    // prefix reached the limit, later tiles publish a saturated prefix and leave without touching HBM.
-    if (p.limit >= 0) {
-        if (tid == 0) s_done = ld_relaxed_gpu_u32(p.done_flag);
-        __syncthreads();
-        if (s_done != 0u) {
-            if (tid == 0) {
-                st_relaxed_gpu(p.tile_status + tile, kStatusPrefix | (uint64_t)p.limit);
-                if (p.tile_prefix_out) p.tile_prefix_out[tile] = (uint64_t)p.limit;
-                if (tile == (int64_t)gridDim.x - 1) *p.total_out = (unsigned long long)p.limit;
+    // ---------------------------------------------------------------- start: fetch the whole super-tile's predicate values
+    if (tid == 0) {
+        sm.done = p.limit >= 0 ? ld_relaxed_gpu_u32(p.done_flag) : 0u;
+        if (use_tma) {
+#pragma unroll
+            for (int s = 0; s < kSub; ++s) mbar_init(&sm.mbar[s], 1);
+            mbar_init_fence();
+            if (sm.done == 0u) {
+#pragma unroll
+                for (int s = 0; s < kSub; ++s) {
+                    const int64_t row0 = super_row0 + (int64_t)s * kTileRows;
+                    if (row0 + kTileRows <= p.n_rows) tma_load_1d(sm.buf[s], p.pred_values + row0, kTileBytes, &sm.mbar[s]);
+                }
             }
-            return;
-        }
-    }
-
-    if (p.n_bits > 0) {
-        uint32_t* flat = &s_bits[0][0];
-        for (int i = tid; i < p.n_bits * (kTileWords + 2); i += kBlock) flat[i] = 0u;
-    }
-
-    // ---------------------------------------------------------------- phase 1: predicate + ranks
-    uint32_t kb[kGroups];     // keep bits of this lane's two rows
-    uint32_t rank0[kGroups];  // rank (within the warp's 256 rows) of the lane's first surviving row
-    uint32_t wrun = 0;
-
-    if (PRED == kPredI64 || PRED == kPredF64) {
-        uint64_t v[kGroups][2];
-#pragma unroll
-        for (int g = 0; g < kGroups; ++g) {
-            const int64_t row = warp_row0 + g * 64 + lane * 2;
-            v[g][0] = 0; v[g][1] = 0;
-            if (row + 1 < p.n_rows) {
-                if (p.pred_vec_ok) { const ulonglong2 t = ld_stream_v2(p.pred_values + row); v[g][0] = t.x; v[g][1] = t.y; }
-                else { v[g][0] = ld_stream(p.pred_values + row); v[g][1] = ld_stream(p.pred_values + row + 1); }
-            } else if (row < p.n_rows) {
-                v[g][0] = ld_stream(p.pred_values + row);
-            }
-        }
-#pragma unroll
-        for (int g = 0; g < kGroups; ++g) {
-            const int64_t grow = warp_row0 + g * 64;
-            const int64_t row = grow + lane * 2;
-            const uint32_t exists = (row < p.n_rows ? 1u : 0u) | (row + 1 < p.n_rows ? 2u : 0u);
-            uint32_t vb = 3u;
-            if (p.pred_valid.words != nullptr) vb = (uint32_t)(load_bits64(p.pred_valid, (uint64_t)grow) >> (2 * lane)) & 3u;
-            const uint32_t c0 = (p.truth & cmp_code<PRED>(v[g][0], p.lit_bits)) != 0u ? 1u : 0u;
-            const uint32_t c1 = (p.truth & cmp_code<PRED>(v[g][1], p.lit_bits)) != 0u ? 2u : 0u;
-            const uint32_t kn = p.keep_null ? 3u : 0u;
-            kb[g] = (((c0 | c1) & vb) | (kn & ~vb)) & exists;
-        }
-    } else {
-#pragma unroll
-        for (int g = 0; g < kGroups; ++g) {
-            const int64_t grow = warp_row0 + g * 64;
-            uint64_t sel = ~0ull;
-            if (PRED == kPredBits) {
-                const uint64_t vals = load_bits64(p.pb_vals, (uint64_t)grow);
-                const uint64_t valid = load_bits64(p.pred_valid, (uint64_t)grow);
-                const uint64_t a = p.pb_a ? ~0ull : 0ull, b = p.pb_b ? ~0ull : 0ull, kn = p.keep_null ? ~0ull : 0ull;
-                sel = (valid & ((vals & a) ^ b)) | (~valid & kn);
-            }
-            const int64_t rem = p.n_rows - grow;
-            if (rem < 64) sel = rem <= 0 ? 0ull : (sel & ((1ull << rem) - 1ull));
-            kb[g] = (uint32_t)(sel >> (2 * lane)) & 3u;
-        }
-    }
-
-#pragma unroll
-    for (int g = 0; g < kGroups; ++g) {
-        const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, (kb[g] & 1u) != 0u);
-        const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, (kb[g] & 2u) != 0u);
-        const uint32_t lt = lanemask_lt();
-        rank0[g] = wrun + __popc(m0 & lt) + __popc(m1 & lt);
-        wrun += __popc(m0) + __popc(m1);
-        if (p.sel_out != nullptr && lane == 0) {
-            const int64_t grow = warp_row0 + g * 64;
-            if (grow < p.n_rows) *reinterpret_cast<uint64_t*>(p.sel_out + (grow >> 5)) = interleave_masks(m0, m1);
-        }
-    }
-    if (lane == 0) s_warp_count[warp] = wrun;
-    __syncthreads();
-
-    uint32_t warp_off = 0, cnt = 0;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-        const uint32_t c = s_warp_count[w];
-        warp_off += (w < warp) ? c : 0u;
-        cnt += c;
-    }
-
-    // ---------------------------------------------------------------- global order: decoupled look-back
-    if (warp == 0) {
-        uint64_t excl;
-        const uint64_t base0 = p.base_in != nullptr ? (uint64_t)*p.base_in : 0ull;
-        if (tile == 0) {
-            excl = base0;
-            if (lane == 0) st_relaxed_gpu(p.tile_status, kStatusPrefix | (excl + cnt));
-        } else {
-            if (lane == 0) st_relaxed_gpu(p.tile_status + tile, kStatusAggregate | (uint64_t)cnt);
-            excl = lookback_exclusive(p.tile_status, tile, lane);
-            if (lane == 0) st_relaxed_gpu(p.tile_status + tile, kStatusPrefix | (excl + cnt));
-        }
-        if (lane == 0) {
-            s_excl = excl;
-            s_base = base0;
-            if (p.tile_prefix_out != nullptr) p.tile_prefix_out[tile] = excl;
-            if (tile == (int64_t)gridDim.x - 1) *p.total_out = (unsigned long long)(excl + cnt);
-            if (p.limit >= 0 && excl + cnt >= (uint64_t)p.limit) atomicExch(p.done_flag, 1u);
         }
     }
     __syncthreads();
-    const uint64_t excl = s_excl;
-    uint32_t cnt_lim = cnt;
-    if (p.limit >= 0) cnt_lim = excl >= (uint64_t)p.limit ? 0u : (uint32_t)min((uint64_t)cnt, (uint64_t)p.limit - excl);
-    if (cnt_lim == 0u) return;
-    const uint64_t oexcl = excl - s_base;  // where this tile's survivors start in the output buffers
 
-    // ---------------------------------------------------------------- phase 2a: sparse tile — scatter from registers
-    if (cnt_lim <= (uint32_t)kSparseTile) {
-        for (int b = 0; b < p.n_bits; ++b) {
-            const BitCol bc = p.bits[b];
-#pragma unroll
-            for (int g = 0; g < kGroups; ++g) {
-                if (kb[g] == 0u) continue;
-                const int64_t grow = warp_row0 + g * 64;
-                const uint64_t w = load_bits64(bc.in, (uint64_t)grow) & load_bits64(bc.mask, (uint64_t)grow);
-                const uint32_t lb = (uint32_t)(w >> (2 * lane)) & 3u;
-                uint32_t r = warp_off + rank0[g];
-                if ((kb[g] & 1u) != 0u) {
-                    if ((lb & 1u) != 0u && r < cnt_lim) { const uint64_t pos = oexcl + r; atomicOr(bc.out + (pos >> 5), 1u << (pos & 31)); }
-                    ++r;
+    // LIMIT early termination (streaming.rs:269-271 / plan.rs:163): an earlier super-tile already reached the
+    // limit — publish a saturated prefix and leave without touching HBM.
+    if (sm.done != 0u) {
+        if (tid == 0) {
+            st_relaxed_gpu(p.tile_status + super, kStatusPrefix | (uint64_t)p.limit);
+            if (p.tile_prefix_out) {
+                for (int s = 0; s < kSub; ++s) {
+                    const int64_t t = super * kSub + s;
+                    if (t * kTileRows < p.n_rows) p.tile_prefix_out[t] = (uint64_t)p.limit;
                 }
-                if ((kb[g] & 2u) != 0u && (lb & 2u) != 0u && r < cnt_lim) { const uint64_t pos = oexcl + r; atomicOr(bc.out + (pos >> 5), 1u << (pos & 31)); }
             }
-        }
-        for (int c = 0; c < p.n_col8; ++c) {
-            const Col8 col = p.col8[c];
-#pragma unroll
-            for (int g = 0; g < kGroups; ++g) {
-                if (kb[g] == 0u) continue;
-                const int64_t grow = warp_row0 + g * 64;
-                const int64_t row = grow + lane * 2;
-                uint32_t vb = 3u;
-                if (col.valid.words != nullptr) vb = (uint32_t)(load_bits64(col.valid, (uint64_t)grow) >> (2 * lane)) & 3u;
-                uint32_t r = warp_off + rank0[g];
-                if ((kb[g] & 1u) != 0u) {
-                    if (r < cnt_lim) st_stream(col.out + oexcl + r, (vb & 1u) ? __ldg(col.in + row) : 0ull);
-                    ++r;
-                }
-                if ((kb[g] & 2u) != 0u && r < cnt_lim) st_stream(col.out + oexcl + r, (vb & 2u) ? __ldg(col.in + row + 1) : 0ull);
-            }
+            if (super == p.n_super - 1) *p.total_out = (unsigned long long)p.limit;
         }
         return;
     }
 
-    // ---------------------------------------------------------------- phase 2b: bit-packed columns (K3)
-    if (p.n_bits > 0) {
-        for (int b = 0; b < p.n_bits; ++b) {
-            const BitCol bc = p.bits[b];
+    // ---------------------------------------------------------------- phase A: predicate -> selection masks + counts
+    const uint32_t lt = lanemask_lt();
+#pragma unroll 1
+    for (int s = 0; s < kSub; ++s) {
+        const int64_t sub_row0 = super_row0 + (int64_t)s * kTileRows;
+        const int64_t warp_row0 = sub_row0 + (int64_t)warp * (kGroups * 64);
+        const bool full = sub_row0 + kTileRows <= p.n_rows;  // uniform: no ragged tail in this sub-tile
+        uint32_t kb[kGroups];
+        if (sub_row0 >= p.n_rows) {
 #pragma unroll
-            for (int g = 0; g < kGroups; ++g) {
-                const int64_t grow = warp_row0 + g * 64;
-                const uint32_t gbase = __shfl_sync(0xFFFFFFFFu, rank0[g], 0);  // lane 0 has no lower lanes
-                const uint64_t w = load_bits64(bc.in, (uint64_t)grow) & load_bits64(bc.mask, (uint64_t)grow);
-                const uint32_t lb = (uint32_t)(w >> (2 * lane)) & 3u & kb[g];
-                const uint32_t lp = rank0[g] - gbase;  // rank inside the group, < 64
-                const uint64_t contrib = ((uint64_t)(lb & 1u) << lp) | ((uint64_t)((lb >> 1) & 1u) << (lp + (kb[g] & 1u)));
-                uint32_t lo = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)contrib);
-                uint32_t hi = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)(contrib >> 32));
-                if (lane == 0) {
-                    const uint32_t P = warp_off + gbase;  // tile-local output position of the group's first survivor
-                    if (P < cnt_lim) {
-                        const uint32_t room = cnt_lim - P;
-                        if (room < 64u) {
-                            const uint64_t keep = (1ull << room) - 1ull;
-                            lo &= (uint32_t)keep; hi &= (uint32_t)(keep >> 32);
-                        }
-                        const uint32_t sh = P & 31u;
-                        uint32_t* dst = &s_bits[b][P >> 5];
-                        const uint32_t o0 = lo << sh;
-                        const uint32_t o1 = __funnelshift_l(lo, hi, sh);
-                        const uint32_t o2 = sh != 0u ? (hi >> (32u - sh)) : 0u;
-                        if (o0) atomicOr(dst, o0);
-                        if (o1) atomicOr(dst + 1, o1);
-                        if (o2) atomicOr(dst + 2, o2);
+            for (int g = 0; g < kGroups; ++g) kb[g] = 0u;
+        } else if (kNumeric) {
+            uint64_t v[kGroups][2];
+            if (use_tma && full) {
+                mbar_wait(&sm.mbar[s], 0);
+#pragma unroll
+                for (int g = 0; g < kGroups; ++g) {
+                    const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(&sm.buf[s][warp * (kGroups * 64) + g * 64 + lane * 2]);
+                    v[g][0] = t.x; v[g][1] = t.y;
+                }
+            } else {
+#pragma unroll
+                for (int g = 0; g < kGroups; ++g) {
+                    const int64_t row = warp_row0 + g * 64 + lane * 2;
+                    v[g][0] = 0; v[g][1] = 0;
+                    if (row + 1 < p.n_rows) {
+                        if (p.pred_vec_ok) { const ulonglong2 t = ld_stream_v2(p.pred_values + row); v[g][0] = t.x; v[g][1] = t.y; }
+                        else { v[g][0] = ld_stream(p.pred_values + row); v[g][1] = ld_stream(p.pred_values + row + 1); }
+                    } else if (row < p.n_rows) {
+                        v[g][0] = ld_stream(p.pred_values + row);
                     }
                 }
             }
-        }
-        __syncthreads();
-        // shift the tile's staged bits to the output bit position `oexcl`; words fully owned by this
-        // tile are stored, the (at most two) boundary words shared with neighbours are OR-ed in.
-        const uint32_t sh = (uint32_t)oexcl & 31u;
-        const uint64_t first_word = oexcl >> 5;
-        const uint32_t n_words = (sh + cnt_lim + 31u) >> 5;
-        const uint64_t end_bit = oexcl + cnt_lim;
-        for (int b = 0; b < p.n_bits; ++b) {
-            uint32_t* out = p.bits[b].out;
-            for (uint32_t t = tid; t < n_words; t += kBlock) {
-                const uint32_t cur = s_bits[b][t];
-                const uint32_t prev = t > 0u ? s_bits[b][t - 1] : 0u;
-                const uint32_t val = __funnelshift_l(prev, cur, sh);
-                const uint64_t k = first_word + t;
-                const bool owned = (t > 0u || sh == 0u) && ((k + 1) * 32ull <= end_bit);
-                if (owned) out[k] = val;
-                else if (val != 0u) atomicOr(out + k, val);
+#pragma unroll
+            for (int g = 0; g < kGroups; ++g) {
+                uint32_t c;
+                if (PRED == kPredI64) {
+                    const uint32_t c0 = ((v[g][0] - p.range_lo) <= p.range_span) ? 1u : 0u;
+                    const uint32_t c1 = ((v[g][1] - p.range_lo) <= p.range_span) ? 2u : 0u;
+                    c = (c0 | c1) ^ (p.range_neg ? 3u : 0u);
+                } else {
+                    const uint32_t c0 = (p.truth & cmp_code<PRED>(v[g][0], p.lit_bits)) != 0u ? 1u : 0u;
+                    const uint32_t c1 = (p.truth & cmp_code<PRED>(v[g][1], p.lit_bits)) != 0u ? 2u : 0u;
+                    c = c0 | c1;
+                }
+                if (p.pred_valid.words != nullptr) {
+                    const uint32_t vb = (uint32_t)(load_bits64(p.pred_valid, (uint64_t)(warp_row0 + g * 64)) >> (2 * lane)) & 3u;
+                    c = (c & vb) | ((p.keep_null ? 3u : 0u) & ~vb);
+                }
+                if (!full) {
+                    const int64_t row = warp_row0 + g * 64 + lane * 2;
+                    c &= (row < p.n_rows ? 1u : 0u) | (row + 1 < p.n_rows ? 2u : 0u);
+                }
+                kb[g] = c;
+            }
+        } else {
+#pragma unroll
+            for (int g = 0; g < kGroups; ++g) {
+                const int64_t grow = warp_row0 + g * 64;
+                uint64_t sel = ~0ull;
+                if (PRED == kPredBits) {
+                    const uint64_t vals = load_bits64(p.pb_vals, (uint64_t)grow);
+                    const uint64_t valid = load_bits64(p.pred_valid, (uint64_t)grow);
+                    const uint64_t a = p.pb_a ? ~0ull : 0ull, b = p.pb_b ? ~0ull : 0ull, kn = p.keep_null ? ~0ull : 0ull;
+                    sel = (valid & ((vals & a) ^ b)) | (~valid & kn);
+                }
+                const int64_t rem = p.n_rows - grow;
+                if (rem < 64) sel = rem <= 0 ? 0ull : (sel & ((1ull << rem) - 1ull));
+                kb[g] = (uint32_t)(sel >> (2 * lane)) & 3u;
             }
         }
+        uint32_t wrun = 0;
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {
+            const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, (kb[g] & 1u) != 0u);
+            const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, (kb[g] & 2u) != 0u);
+            wrun += __popc(m0) + __popc(m1);
+            if (lane == 0) {
+                sm.sel0[s][warp * kGroups + g] = m0;
+                sm.sel1[s][warp * kGroups + g] = m1;
+            }
+            if (p.sel_out != nullptr) {  // row-order selection bitmap for the string kernels / mask output
+                const int64_t grow = warp_row0 + g * 64;
+                if (lane == 0 && grow < p.n_rows) *reinterpret_cast<uint64_t*>(p.sel_out + (grow >> 5)) = interleave_masks(m0, m1);
+            }
+        }
+        if (lane == 0) sm.warp_count[s][warp] = wrun;
+    }
+    __syncthreads();  // barrier #1: selection masks and counts of the whole super-tile; predicate buffer is dead
+
+    uint32_t total = 0;
+#pragma unroll
+    for (int s = 0; s < kSub; ++s) {
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) total += sm.warp_count[s][w];
     }
 
-    // ---------------------------------------------------------------- phase 2c: 8-byte columns (K2)
-    for (int c = 0; c < p.n_col8; ++c) {
-        const Col8 col = p.col8[c];
-        uint64_t* stage = s_stage[c & 1];
-        uint64_t v[kGroups][2];
+    // ---------------------------------------------------------------- global order: one decoupled look-back per super-tile (warp 0)
+    if (warp == 0) {
+        uint64_t excl;
+        const uint64_t base0 = p.base_in != nullptr ? (uint64_t)*p.base_in : 0ull;
+        if (super == 0) {
+            excl = base0;
+            if (lane == 0) st_relaxed_gpu(p.tile_status, kStatusPrefix | (excl + total));
+        } else {
+            if (lane == 0) st_relaxed_gpu(p.tile_status + super, kStatusAggregate | (uint64_t)total);
+            excl = lookback_exclusive_wide(p.tile_status, super, lane);
+            if (lane == 0) st_relaxed_gpu(p.tile_status + super, kStatusPrefix | (excl + total));
+        }
+        if (lane == 0) {
+            sm.excl = excl;
+            sm.base = base0;
+            if (super == p.n_super - 1) *p.total_out = (unsigned long long)(excl + total);
+            if (p.limit >= 0 && excl + total >= (uint64_t)p.limit) atomicExch(p.done_flag, 1u);
+        }
+        if (p.tile_prefix_out != nullptr && lane < kSub) {
+            uint64_t off = 0;
+            for (int s = 0; s < lane; ++s)
+                for (int w = 0; w < kWarps; ++w) off += sm.warp_count[s][w];
+            const int64_t t = super * kSub + lane;
+            if (t * kTileRows < p.n_rows) p.tile_prefix_out[t] = excl + off;
+        }
+    }
+    if (total == 0u) return;  // uniform: nothing to emit
+
+    // ---------------------------------------------------------------- phase B: every warp emits its own survivors
+    // A warp's survivors of one sub-tile occupy the contiguous output range [excl + sub_off + warp_off, + my_cnt):
+    // the warp gathers them (predicated loads, two columns in flight), stages them in its private 8 KB slice of the
+    // dead predicate buffer in output order, and writes them out as one contiguous run.  No block barrier is needed
+    // after the look-back join, so the eight warps drift apart and their loads, staging and stores overlap.
+    uint64_t* const wstage = &sm.buf[0][0] + warp * (kStageBufs * 256);  // [kStageBufs][256] survivors
+    uint32_t* const wbits = &sm.wbits[warp][0][0];                       // [kMaxBitCols][kWarpBitWords]
+    bool have_excl = false;
+    uint64_t excl = 0, base0 = 0;
+    uint32_t sub_off = 0;  // survivors of the earlier sub-tiles of this super-tile
+#pragma unroll 1
+    for (int s = 0; s < kSub; ++s) {
+        uint32_t cnt = 0, warp_off = 0, my_cnt = 0;
 #pragma unroll
-        for (int g = 0; g < kGroups; ++g) {
-            v[g][0] = 0; v[g][1] = 0;
-            if (kb[g] != 0u) {
-                const int64_t row = warp_row0 + g * 64 + lane * 2;
-                if (col.vec_ok && row + 1 < p.n_rows) {
-                    const ulonglong2 t = ld_stream_v2(col.in + row); v[g][0] = t.x; v[g][1] = t.y;
-                } else {
-                    if ((kb[g] & 1u) != 0u) v[g][0] = ld_stream(col.in + row);
-                    if ((kb[g] & 2u) != 0u) v[g][1] = ld_stream(col.in + row + 1);
-                }
+        for (int w = 0; w < kWarps; ++w) {
+            const uint32_t c = sm.warp_count[s][w];
+            warp_off += (w < warp) ? c : 0u;
+            my_cnt = (w == warp) ? c : my_cnt;
+            cnt += c;
+        }
+        if (cnt == 0u) continue;  // uniform
+        const int64_t sub_row0 = super_row0 + (int64_t)s * kTileRows;
+        const int64_t warp_row0 = sub_row0 + (int64_t)warp * (kGroups * 64);
+        const bool full = sub_row0 + kTileRows <= p.n_rows;
+
+        // this lane's keep bits and warp-local ranks, rebuilt from the selection masks
+        uint32_t kb[kGroups], rank0[kGroups];
+        {
+            uint32_t run = 0;
+#pragma unroll
+            for (int g = 0; g < kGroups; ++g) {
+                const uint32_t m0 = sm.sel0[s][warp * kGroups + g], m1 = sm.sel1[s][warp * kGroups + g];
+                kb[g] = ((m0 >> lane) & 1u) | (((m1 >> lane) & 1u) << 1);
+                rank0[g] = run + __popc(m0 & lt) + __popc(m1 & lt);
+                run += __popc(m0) + __popc(m1);
             }
         }
+
+        // gather one or two columns: all loads are issued before the first one is consumed
+        auto stage_columns = [&](const Col8& colA, const Col8& colB, uint64_t* stageA, uint64_t* stageB, const bool two) {
+            uint64_t va[kGroups][2], vb2[kGroups][2];
 #pragma unroll
-        for (int g = 0; g < kGroups; ++g) {
-            if (kb[g] != 0u) {
-                uint32_t vb = 3u;
-                if (col.valid.words != nullptr)
-                    vb = (uint32_t)(load_bits64(col.valid, (uint64_t)(warp_row0 + g * 64)) >> (2 * lane)) & 3u;
-                uint32_t r = warp_off + rank0[g];
-                if ((kb[g] & 1u) != 0u) {
-                    if (r < cnt_lim) stage[r] = (vb & 1u) ? v[g][0] : 0ull;  // placeholder 0 under a null (primitive.rs:175-178)
-                    ++r;
+            for (int g = 0; g < kGroups; ++g) {
+                va[g][0] = 0; va[g][1] = 0; vb2[g][0] = 0; vb2[g][1] = 0;
+                if (kb[g] != 0u) {
+                    const int64_t row = warp_row0 + g * 64 + lane * 2;
+                    const bool pair_ok = full || row + 1 < p.n_rows;
+                    if (colA.vec_ok && pair_ok) { const ulonglong2 t = ld_stream_v2(colA.in + row); va[g][0] = t.x; va[g][1] = t.y; }
+                    else {
+                        if ((kb[g] & 1u) != 0u) va[g][0] = ld_stream(colA.in + row);
+                        if ((kb[g] & 2u) != 0u) va[g][1] = ld_stream(colA.in + row + 1);
+                    }
+                    if (two) {
+                        if (colB.vec_ok && pair_ok) { const ulonglong2 t = ld_stream_v2(colB.in + row); vb2[g][0] = t.x; vb2[g][1] = t.y; }
+                        else {
+                            if ((kb[g] & 1u) != 0u) vb2[g][0] = ld_stream(colB.in + row);
+                            if ((kb[g] & 2u) != 0u) vb2[g][1] = ld_stream(colB.in + row + 1);
+                        }
+                    }
                 }
-                if ((kb[g] & 2u) != 0u && r < cnt_lim) stage[r] = (vb & 2u) ? v[g][1] : 0ull;
             }
+#pragma unroll
+            for (int g = 0; g < kGroups; ++g) {
+                if (kb[g] != 0u) {
+                    uint32_t ma = 3u, mb = 3u;
+                    if (colA.valid.words != nullptr) ma = (uint32_t)(load_bits64(colA.valid, (uint64_t)(warp_row0 + g * 64)) >> (2 * lane)) & 3u;
+                    if (two && colB.valid.words != nullptr) mb = (uint32_t)(load_bits64(colB.valid, (uint64_t)(warp_row0 + g * 64)) >> (2 * lane)) & 3u;
+                    uint32_t r = rank0[g];
+                    if ((kb[g] & 1u) != 0u) {  // placeholder 0 under a null (primitive.rs:175-178)
+                        stageA[r] = (ma & 1u) ? va[g][0] : 0ull;
+                        if (two) stageB[r] = (mb & 1u) ? vb2[g][0] : 0ull;
+                        ++r;
+                    }
+                    if ((kb[g] & 2u) != 0u) {
+                        stageA[r] = (ma & 2u) ? va[g][1] : 0ull;
+                        if (two) stageB[r] = (mb & 2u) ? vb2[g][1] : 0ull;
+                    }
+                }
+            }
+        };
+        auto stage_round = [&](int c0, int nc) {  // stage columns [c0, c0 + nc) into the warp's buffers [0, nc)
+            for (int c = 0; c < nc; c += 2) {
+                const bool two = c + 1 < nc;
+                stage_columns(p.col8[c0 + c], p.col8[c0 + (two ? c + 1 : c)], wstage + c * 256, wstage + (two ? c + 1 : c) * 256, two);
+            }
+        };
+        const int nc_first = p.n_col8 < kStageBufs ? p.n_col8 : kStageBufs;
+
+        // ---- stage the bit-packed columns and the first round of 8-byte columns (warp-local ranks only)
+        if (my_cnt != 0u) {
+            for (int b = 0; b < p.n_bits; ++b) {
+                const BitCol bc = p.bits[b];
+                uint32_t* wb = wbits + b * kWarpBitWords;
+                if (lane < kWarpBitWords) wb[lane] = 0u;
+                __syncwarp();
+#pragma unroll
+                for (int g = 0; g < kGroups; ++g) {
+                    const int64_t grow = warp_row0 + g * 64;
+                    const uint32_t gbase = __shfl_sync(0xFFFFFFFFu, rank0[g], 0);  // lane 0 has no lower lanes
+                    const uint64_t w = load_bits64(bc.in, (uint64_t)grow) & load_bits64(bc.mask, (uint64_t)grow);
+                    const uint32_t lb = (uint32_t)(w >> (2 * lane)) & 3u & kb[g];
+                    const uint32_t lp = rank0[g] - gbase;  // rank inside the group, < 64
+                    const uint64_t contrib = ((uint64_t)(lb & 1u) << lp) | ((uint64_t)((lb >> 1) & 1u) << (lp + (kb[g] & 1u)));
+                    const uint32_t lo = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)contrib);
+                    const uint32_t hi = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)(contrib >> 32));
+                    if (lane == 0 && (lo | hi) != 0u) {
+                        const uint32_t sh = gbase & 31u;  // gbase = warp-local position of the group's first survivor
+                        uint32_t* dst = wb + (gbase >> 5);
+                        dst[0] |= lo << sh;
+                        dst[1] |= __funnelshift_l(lo, hi, sh);
+                        if (sh != 0u) dst[2] |= hi >> (32u - sh);
+                    }
+                }
+            }
+            stage_round(0, nc_first);
         }
-        __syncthreads();
-        uint64_t* out = col.out + oexcl;
-        for (uint32_t i = tid; i < cnt_lim; i += kBlock) st_stream(out + i, stage[i]);
-        // no barrier here: the next column stages into the other buffer, and the barrier after that
-        // staging orders this read against the column after next.
+        if (!have_excl) {
+            __syncthreads();  // the one join with warp 0's look-back: the output offset is known from here on
+            excl = sm.excl; base0 = sm.base; have_excl = true;
+        }
+        if (my_cnt != 0u) {
+            __syncwarp();
+            const uint64_t my_excl = excl + sub_off + warp_off;  // global index of this warp's first survivor
+            uint32_t my_lim = my_cnt;
+            if (p.limit >= 0) my_lim = my_excl >= (uint64_t)p.limit ? 0u : (uint32_t)min((uint64_t)my_cnt, (uint64_t)p.limit - my_excl);
+            const uint64_t oexcl = my_excl - base0;  // where this warp's survivors start in the output buffers
+
+            // ---- bit-packed columns: shift the staged bits to output bit `oexcl`; words fully owned by this warp's
+            // run are stored, the (at most two) boundary words shared with neighbours are OR-ed in
+            if (p.n_bits > 0 && my_lim != 0u) {
+                const uint32_t sh = (uint32_t)oexcl & 31u;
+                const uint64_t first_word = oexcl >> 5;
+                const uint32_t n_words = (sh + my_lim + 31u) >> 5;  // <= 9
+                const uint64_t end_bit = oexcl + my_lim;
+                for (int b = 0; b < p.n_bits; ++b) {
+                    const uint32_t* wb = wbits + b * kWarpBitWords;
+                    uint32_t* out = p.bits[b].out;
+                    if ((uint32_t)lane < n_words) {
+                        auto staged = [&](uint32_t i) -> uint32_t {
+                            const uint32_t lo_bit = i * 32u;
+                            if (lo_bit >= my_lim) return 0u;
+                            uint32_t w = wb[i];
+                            if (my_lim - lo_bit < 32u) w &= (1u << (my_lim - lo_bit)) - 1u;
+                            return w;
+                        };
+                        const uint32_t t = (uint32_t)lane;
+                        const uint32_t cur = staged(t);
+                        const uint32_t prev = t > 0u ? staged(t - 1) : 0u;
+                        const uint32_t val = __funnelshift_l(prev, cur, sh);
+                        const uint64_t k = first_word + t;
+                        const bool owned = (t > 0u || sh == 0u) && ((k + 1) * 32ull <= end_bit);
+                        if (owned) out[k] = val;
+                        else if (val != 0u) atomicOr(out + k, val);
+                    }
+                }
+            }
+            // ---- 8-byte columns: contiguous copy-out of the staged survivors, kStageBufs columns per round
+            for (int c0 = 0; c0 < p.n_col8; c0 += kStageBufs) {
+                const int nc = (p.n_col8 - c0) < kStageBufs ? (p.n_col8 - c0) : kStageBufs;
+                if (c0 > 0) {
+                    __syncwarp();  // the warp is done reading the previous round's staging buffers
+                    stage_round(c0, nc);
+                    __syncwarp();
+                }
+                for (int c = 0; c < nc; ++c) {
+                    const uint64_t* stage = wstage + c * 256;
+                    uint64_t* out = p.col8[c0 + c].out + oexcl;
+                    for (uint32_t i = lane; i < my_lim; i += 32) st_stream(out + i, stage[i]);
+                }
+            }
+            __syncwarp();  // staging slices are reused by the warp's next sub-tile
+        }
+        sub_off += cnt;
     }
 }
 

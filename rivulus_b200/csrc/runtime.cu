@@ -141,6 +141,9 @@ int32_t rvl_ctx_create(int32_t device, rvl_ctx** ctx) {
     RVL_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t threshold = UINT64_MAX;
     RVL_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    // the gather of projected columns touches isolated 32-byte sectors at low selectivity: ask L2 not to widen
+    // those misses to 128-byte fetches (measured: 128 B granularity moved 1.8x the algorithmic bytes at 10 %)
+    if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32) != cudaSuccess) cudaGetLastError();
     *ctx = new rvl_ctx{core};
     return RVL_OK;
 }

@@ -270,8 +270,15 @@ int32_t rvl_stream_collect(rvl_stream* s, rvl_batch** out) {
             // RecordBatch::empty(schema) (streaming.rs:347-349, record_batch.rs:402-421)
             auto e = std::make_unique<rvl_batch>();
             e->core = s->core; e->num_rows = 0;
-            for (int32_t p : s->proj) { DevColumn d; d.dtype = s->dtypes[(size_t)p]; d.null_count = 0; e->cols.push_back(d); }
-            *out = e.release();
+            for (int32_t p : s->proj) {
+                DevColumn d;
+                d.dtype = s->dtypes[(size_t)p]; d.null_count = 0;
+                if (d.dtype == RVL_INT64 || d.dtype == RVL_FLOAT64 || d.dtype == RVL_BOOLEAN) rc = dev_alloc_zeroed(s->core, 8, &d.values);
+                if (d.dtype == RVL_STRING) { rc = dev_alloc_zeroed(s->core, 8, &d.offsets); if (rc == RVL_OK) rc = dev_alloc_zeroed(s->core, 8, &d.data); }
+                if (rc != RVL_OK) break;
+                e->cols.push_back(d);
+            }
+            if (rc == RVL_OK) *out = e.release();
         } else {
             rc = rvl_batch_concat(&tmp, parts.data(), (int32_t)parts.size(), out);
         }

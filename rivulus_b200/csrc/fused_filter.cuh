@@ -44,6 +44,7 @@ constexpr int kWarpBitWords = 256 / 32 + 2;     // a warp emits at most 256 surv
 constexpr int kSub = 4;                        // sub-tiles per super-tile
 constexpr int kSuperRows = kSub * kTileRows;   // 8192 rows per CTA
 constexpr int kStageBufs = 4;                  // staging buffers (alias the predicate buffer)
+constexpr int kSparseWarp = 16;                // warps with <= this many survivors in the super-tile use the list path
 
 enum PredKind : int { kPredI64 = 0, kPredF64 = 1, kPredBits = 2, kPredTrue = 3 };
 
@@ -102,9 +103,12 @@ struct __align__(128) FusedSmem {
     uint32_t wbits[kWarps][kMaxBitCols][kWarpBitWords];  // per warp: compacted bit columns of the run being emitted
     uint32_t warp_count[kSub][kWarps];
     uint64_t mbar[kSub];                          // one single-use mbarrier per sub-tile copy
+    uint16_t wl_row[kWarps][kSparseWarp];         // sparse-warp path: survivor rows (within the super-tile) ...
+    uint16_t wl_out[kWarps][kSparseWarp];         // ... and their output positions relative to the super-tile's offset
     uint64_t excl;
     uint64_t base;
     uint32_t done;
+    uint32_t ready;                               // set by warp 0 once excl/base are valid
 };
 
 template <int PRED>
@@ -194,6 +198,7 @@ __global__ void __launch_bounds__(kBlock, 3) fused_filter_project_kernel(const _
     // ---------------------------------------------------------------- start: fetch the whole super-tile's predicate values
     if (tid == 0) {
         sm.done = p.limit >= 0 ? ld_relaxed_gpu_u32(p.done_flag) : 0u;
+        sm.ready = 0u;
         if (use_tma) {
 #pragma unroll
             for (int s = 0; s < kSub; ++s) mbar_init(&sm.mbar[s], 1);
@@ -315,12 +320,29 @@ __global__ void __launch_bounds__(kBlock, 3) fused_filter_project_kernel(const _
     }
     __syncthreads();  // barrier #1: selection masks and counts of the whole super-tile; predicate buffer is dead
 
-    uint32_t total = 0;
+    // per-warp bookkeeping, one sub-tile per lane (lanes 0..kSub-1), broadcast with shuffles when needed
+    uint32_t l_cnt = 0, l_woff = 0, l_mine = 0;  // sub-tile survivors / survivors of lower warps / this warp's survivors
+    if (lane < kSub) {
 #pragma unroll
-    for (int s = 0; s < kSub; ++s) {
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) total += sm.warp_count[s][w];
+        for (int w = 0; w < kWarps; ++w) {
+            const uint32_t c = sm.warp_count[lane][w];
+            l_woff += (w < warp) ? c : 0u;
+            l_mine = (w == warp) ? c : l_mine;
+            l_cnt += c;
+        }
     }
+    uint32_t l_soff = l_cnt;  // exclusive prefix of the sub-tile counts
+#pragma unroll
+    for (int o = 1; o < kSub; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, l_soff, o);
+        if (lane >= o) l_soff += n;
+    }
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, l_soff, kSub - 1);
+    l_soff -= l_cnt;
+    uint32_t warp_total = l_mine;
+    warp_total += __shfl_xor_sync(0xFFFFFFFFu, warp_total, 1);
+    warp_total += __shfl_xor_sync(0xFFFFFFFFu, warp_total, 2);
+    warp_total = __shfl_sync(0xFFFFFFFFu, warp_total, 0);
 
     // ---------------------------------------------------------------- global order: one decoupled look-back per super-tile (warp 0)
     if (warp == 0) {
@@ -337,40 +359,107 @@ __global__ void __launch_bounds__(kBlock, 3) fused_filter_project_kernel(const _
         if (lane == 0) {
             sm.excl = excl;
             sm.base = base0;
+            __threadfence_block();
+            *reinterpret_cast<volatile uint32_t*>(&sm.ready) = 1u;  // releases the warps polling for the output offset
             if (super == p.n_super - 1) *p.total_out = (unsigned long long)(excl + total);
             if (p.limit >= 0 && excl + total >= (uint64_t)p.limit) atomicExch(p.done_flag, 1u);
         }
         if (p.tile_prefix_out != nullptr && lane < kSub) {
-            uint64_t off = 0;
-            for (int s = 0; s < lane; ++s)
-                for (int w = 0; w < kWarps; ++w) off += sm.warp_count[s][w];
             const int64_t t = super * kSub + lane;
-            if (t * kTileRows < p.n_rows) p.tile_prefix_out[t] = excl + off;
+            if (t * kTileRows < p.n_rows) p.tile_prefix_out[t] = excl + l_soff;
         }
     }
-    if (total == 0u) return;  // uniform: nothing to emit
+    if (warp_total == 0u) return;  // this warp has nothing to emit (no block barrier follows)
 
     // ---------------------------------------------------------------- phase B: every warp emits its own survivors
-    // A warp's survivors of one sub-tile occupy the contiguous output range [excl + sub_off + warp_off, + my_cnt):
-    // the warp gathers them (predicated loads, two columns in flight), stages them in its private 8 KB slice of the
-    // dead predicate buffer in output order, and writes them out as one contiguous run.  No block barrier is needed
-    // after the look-back join, so the eight warps drift apart and their loads, staging and stores overlap.
+    // A warp's survivors of one sub-tile occupy the contiguous output range [excl + sub_off + warp_off, + my_cnt).
+    // No block barrier after barrier #1: a warp waits for the output offset (sm.ready) only when it is about to
+    // store, so its gather loads overlap warp 0's look-back, and the eight warps drift apart.
+    auto wait_offset = [&](uint64_t& excl, uint64_t& base0) {
+        while (*reinterpret_cast<volatile uint32_t*>(&sm.ready) == 0u) {}
+        __threadfence_block();
+        __syncwarp();
+        excl = *reinterpret_cast<volatile uint64_t*>(&sm.excl);
+        base0 = *reinterpret_cast<volatile uint64_t*>(&sm.base);
+    };
+    uint64_t excl = 0, base0 = 0;
+
+    if (warp_total <= (uint32_t)kSparseWarp) {
+        // ---- few survivors in this warp (low selectivity): one (survivor, column) pair per lane, so every gather
+        // load of the warp is in flight at once and exactly one memory round trip is exposed
+        uint16_t* wrow = sm.wl_row[warp];
+        uint16_t* wout = sm.wl_out[warp];
+        uint32_t base = 0;
+#pragma unroll 1
+        for (int s = 0; s < kSub; ++s) {
+            const uint32_t mine = __shfl_sync(0xFFFFFFFFu, l_mine, s);
+            if (mine == 0u) continue;
+            const uint32_t pos0 = __shfl_sync(0xFFFFFFFFu, l_soff, s) + __shfl_sync(0xFFFFFFFFu, l_woff, s);
+            uint32_t run = 0;
+#pragma unroll
+            for (int g = 0; g < kGroups; ++g) {
+                const uint32_t m0 = sm.sel0[s][warp * kGroups + g], m1 = sm.sel1[s][warp * kGroups + g];
+                uint32_t r = run + __popc(m0 & lt) + __popc(m1 & lt);
+                const uint32_t row = (uint32_t)(s * kTileRows + warp * (kGroups * 64) + g * 64 + lane * 2);
+                if ((m0 >> lane) & 1u) { wrow[base + r] = (uint16_t)row; wout[base + r] = (uint16_t)(pos0 + r); ++r; }
+                if ((m1 >> lane) & 1u) { wrow[base + r] = (uint16_t)(row + 1); wout[base + r] = (uint16_t)(pos0 + r); }
+                run += __popc(m0) + __popc(m1);
+            }
+            base += mine;
+        }
+        __syncwarp();
+        const uint32_t n_task = warp_total * (uint32_t)p.n_col8;
+        bool have = false;
+        for (uint32_t t0 = 0; t0 < n_task; t0 += 32) {
+            const uint32_t t = t0 + lane;
+            uint64_t v = 0;
+            uint32_t e = 0, c = 0;
+            if (t < n_task) {
+                e = t / (uint32_t)p.n_col8; c = t - e * (uint32_t)p.n_col8;
+                const Col8& col = p.col8[c];
+                const int64_t row = super_row0 + wrow[e];
+                bool ok = true;
+                if (col.valid.words != nullptr) { const uint64_t bit = col.valid.bit0 + (uint64_t)row; ok = (__ldg(col.valid.words + (bit >> 5)) >> (bit & 31)) & 1u; }
+                if (ok) v = ld_stream(col.in + row);  // placeholder 0 under a null (primitive.rs:175-178)
+            }
+            if (!have) { wait_offset(excl, base0); have = true; }
+            if (t < n_task) {
+                const uint64_t gpos = excl + wout[e];
+                if (p.limit < 0 || gpos < (uint64_t)p.limit) st_stream(p.col8[c].out + (gpos - base0), v);
+            }
+        }
+        const uint32_t n_btask = warp_total * (uint32_t)p.n_bits;
+        for (uint32_t t0 = 0; t0 < n_btask; t0 += 32) {
+            const uint32_t t = t0 + lane;
+            bool set = false;
+            uint32_t e = 0, b = 0;
+            if (t < n_btask) {
+                e = t / (uint32_t)p.n_bits; b = t - e * (uint32_t)p.n_bits;
+                const BitCol& bc = p.bits[b];
+                const uint64_t row = (uint64_t)(super_row0 + wrow[e]);
+                set = true;
+                if (bc.in.words != nullptr) { const uint64_t bit = bc.in.bit0 + row; set = (__ldg(bc.in.words + (bit >> 5)) >> (bit & 31)) & 1u; }
+                if (set && bc.mask.words != nullptr) { const uint64_t bit = bc.mask.bit0 + row; set = (__ldg(bc.mask.words + (bit >> 5)) >> (bit & 31)) & 1u; }
+            }
+            if (!have) { wait_offset(excl, base0); have = true; }
+            if (set) {
+                const uint64_t gpos = excl + wout[e];
+                if (p.limit < 0 || gpos < (uint64_t)p.limit) { const uint64_t pos = gpos - base0; atomicOr(p.bits[b].out + (pos >> 5), 1u << (pos & 31)); }
+            }
+        }
+        return;
+    }
+
+    // ---- many survivors: gather with predicated 128-bit loads (two columns in flight), stage in the warp's private
+    // 8 KB slice of the dead predicate buffer in output order, write each run out contiguously
     uint64_t* const wstage = &sm.buf[0][0] + warp * (kStageBufs * 256);  // [kStageBufs][256] survivors
     uint32_t* const wbits = &sm.wbits[warp][0][0];                       // [kMaxBitCols][kWarpBitWords]
     bool have_excl = false;
-    uint64_t excl = 0, base0 = 0;
-    uint32_t sub_off = 0;  // survivors of the earlier sub-tiles of this super-tile
 #pragma unroll 1
     for (int s = 0; s < kSub; ++s) {
-        uint32_t cnt = 0, warp_off = 0, my_cnt = 0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-            const uint32_t c = sm.warp_count[s][w];
-            warp_off += (w < warp) ? c : 0u;
-            my_cnt = (w == warp) ? c : my_cnt;
-            cnt += c;
-        }
-        if (cnt == 0u) continue;  // uniform
+        const uint32_t my_cnt = __shfl_sync(0xFFFFFFFFu, l_mine, s);
+        if (my_cnt == 0u) continue;
+        const uint32_t pos0 = __shfl_sync(0xFFFFFFFFu, l_soff, s) + __shfl_sync(0xFFFFFFFFu, l_woff, s);
         const int64_t sub_row0 = super_row0 + (int64_t)s * kTileRows;
         const int64_t warp_row0 = sub_row0 + (int64_t)warp * (kGroups * 64);
         const bool full = sub_row0 + kTileRows <= p.n_rows;
@@ -439,90 +528,82 @@ __global__ void __launch_bounds__(kBlock, 3) fused_filter_project_kernel(const _
         const int nc_first = p.n_col8 < kStageBufs ? p.n_col8 : kStageBufs;
 
         // ---- stage the bit-packed columns and the first round of 8-byte columns (warp-local ranks only)
-        if (my_cnt != 0u) {
-            for (int b = 0; b < p.n_bits; ++b) {
-                const BitCol bc = p.bits[b];
-                uint32_t* wb = wbits + b * kWarpBitWords;
-                if (lane < kWarpBitWords) wb[lane] = 0u;
-                __syncwarp();
-#pragma unroll
-                for (int g = 0; g < kGroups; ++g) {
-                    const int64_t grow = warp_row0 + g * 64;
-                    const uint32_t gbase = __shfl_sync(0xFFFFFFFFu, rank0[g], 0);  // lane 0 has no lower lanes
-                    const uint64_t w = load_bits64(bc.in, (uint64_t)grow) & load_bits64(bc.mask, (uint64_t)grow);
-                    const uint32_t lb = (uint32_t)(w >> (2 * lane)) & 3u & kb[g];
-                    const uint32_t lp = rank0[g] - gbase;  // rank inside the group, < 64
-                    const uint64_t contrib = ((uint64_t)(lb & 1u) << lp) | ((uint64_t)((lb >> 1) & 1u) << (lp + (kb[g] & 1u)));
-                    const uint32_t lo = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)contrib);
-                    const uint32_t hi = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)(contrib >> 32));
-                    if (lane == 0 && (lo | hi) != 0u) {
-                        const uint32_t sh = gbase & 31u;  // gbase = warp-local position of the group's first survivor
-                        uint32_t* dst = wb + (gbase >> 5);
-                        dst[0] |= lo << sh;
-                        dst[1] |= __funnelshift_l(lo, hi, sh);
-                        if (sh != 0u) dst[2] |= hi >> (32u - sh);
-                    }
-                }
-            }
-            stage_round(0, nc_first);
-        }
-        if (!have_excl) {
-            __syncthreads();  // the one join with warp 0's look-back: the output offset is known from here on
-            excl = sm.excl; base0 = sm.base; have_excl = true;
-        }
-        if (my_cnt != 0u) {
+        for (int b = 0; b < p.n_bits; ++b) {
+            const BitCol bc = p.bits[b];
+            uint32_t* wb = wbits + b * kWarpBitWords;
+            if (lane < kWarpBitWords) wb[lane] = 0u;
             __syncwarp();
-            const uint64_t my_excl = excl + sub_off + warp_off;  // global index of this warp's first survivor
-            uint32_t my_lim = my_cnt;
-            if (p.limit >= 0) my_lim = my_excl >= (uint64_t)p.limit ? 0u : (uint32_t)min((uint64_t)my_cnt, (uint64_t)p.limit - my_excl);
-            const uint64_t oexcl = my_excl - base0;  // where this warp's survivors start in the output buffers
-
-            // ---- bit-packed columns: shift the staged bits to output bit `oexcl`; words fully owned by this warp's
-            // run are stored, the (at most two) boundary words shared with neighbours are OR-ed in
-            if (p.n_bits > 0 && my_lim != 0u) {
-                const uint32_t sh = (uint32_t)oexcl & 31u;
-                const uint64_t first_word = oexcl >> 5;
-                const uint32_t n_words = (sh + my_lim + 31u) >> 5;  // <= 9
-                const uint64_t end_bit = oexcl + my_lim;
-                for (int b = 0; b < p.n_bits; ++b) {
-                    const uint32_t* wb = wbits + b * kWarpBitWords;
-                    uint32_t* out = p.bits[b].out;
-                    if ((uint32_t)lane < n_words) {
-                        auto staged = [&](uint32_t i) -> uint32_t {
-                            const uint32_t lo_bit = i * 32u;
-                            if (lo_bit >= my_lim) return 0u;
-                            uint32_t w = wb[i];
-                            if (my_lim - lo_bit < 32u) w &= (1u << (my_lim - lo_bit)) - 1u;
-                            return w;
-                        };
-                        const uint32_t t = (uint32_t)lane;
-                        const uint32_t cur = staged(t);
-                        const uint32_t prev = t > 0u ? staged(t - 1) : 0u;
-                        const uint32_t val = __funnelshift_l(prev, cur, sh);
-                        const uint64_t k = first_word + t;
-                        const bool owned = (t > 0u || sh == 0u) && ((k + 1) * 32ull <= end_bit);
-                        if (owned) out[k] = val;
-                        else if (val != 0u) atomicOr(out + k, val);
-                    }
+#pragma unroll
+            for (int g = 0; g < kGroups; ++g) {
+                const int64_t grow = warp_row0 + g * 64;
+                const uint32_t gbase = __shfl_sync(0xFFFFFFFFu, rank0[g], 0);  // lane 0 has no lower lanes
+                const uint64_t w = load_bits64(bc.in, (uint64_t)grow) & load_bits64(bc.mask, (uint64_t)grow);
+                const uint32_t lb = (uint32_t)(w >> (2 * lane)) & 3u & kb[g];
+                const uint32_t lp = rank0[g] - gbase;  // rank inside the group, < 64
+                const uint64_t contrib = ((uint64_t)(lb & 1u) << lp) | ((uint64_t)((lb >> 1) & 1u) << (lp + (kb[g] & 1u)));
+                const uint32_t lo = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)contrib);
+                const uint32_t hi = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)(contrib >> 32));
+                if (lane == 0 && (lo | hi) != 0u) {
+                    const uint32_t sh = gbase & 31u;  // gbase = warp-local position of the group's first survivor
+                    uint32_t* dst = wb + (gbase >> 5);
+                    dst[0] |= lo << sh;
+                    dst[1] |= __funnelshift_l(lo, hi, sh);
+                    if (sh != 0u) dst[2] |= hi >> (32u - sh);
                 }
             }
-            // ---- 8-byte columns: contiguous copy-out of the staged survivors, kStageBufs columns per round
-            for (int c0 = 0; c0 < p.n_col8; c0 += kStageBufs) {
-                const int nc = (p.n_col8 - c0) < kStageBufs ? (p.n_col8 - c0) : kStageBufs;
-                if (c0 > 0) {
-                    __syncwarp();  // the warp is done reading the previous round's staging buffers
-                    stage_round(c0, nc);
-                    __syncwarp();
-                }
-                for (int c = 0; c < nc; ++c) {
-                    const uint64_t* stage = wstage + c * 256;
-                    uint64_t* out = p.col8[c0 + c].out + oexcl;
-                    for (uint32_t i = lane; i < my_lim; i += 32) st_stream(out + i, stage[i]);
-                }
-            }
-            __syncwarp();  // staging slices are reused by the warp's next sub-tile
         }
-        sub_off += cnt;
+        stage_round(0, nc_first);
+        if (!have_excl) { wait_offset(excl, base0); have_excl = true; }
+        __syncwarp();
+        const uint64_t my_excl = excl + pos0;  // global index of this warp's first survivor of the sub-tile
+        uint32_t my_lim = my_cnt;
+        if (p.limit >= 0) my_lim = my_excl >= (uint64_t)p.limit ? 0u : (uint32_t)min((uint64_t)my_cnt, (uint64_t)p.limit - my_excl);
+        const uint64_t oexcl = my_excl - base0;  // where this run starts in the output buffers
+
+        // ---- bit-packed columns: shift the staged bits to output bit `oexcl`; words fully owned by this warp's
+        // run are stored, the (at most two) boundary words shared with neighbours are OR-ed in
+        if (p.n_bits > 0 && my_lim != 0u) {
+            const uint32_t sh = (uint32_t)oexcl & 31u;
+            const uint64_t first_word = oexcl >> 5;
+            const uint32_t n_words = (sh + my_lim + 31u) >> 5;  // <= 9
+            const uint64_t end_bit = oexcl + my_lim;
+            for (int b = 0; b < p.n_bits; ++b) {
+                const uint32_t* wb = wbits + b * kWarpBitWords;
+                uint32_t* out = p.bits[b].out;
+                if ((uint32_t)lane < n_words) {
+                    auto staged = [&](uint32_t i) -> uint32_t {
+                        const uint32_t lo_bit = i * 32u;
+                        if (lo_bit >= my_lim) return 0u;
+                        uint32_t w = wb[i];
+                        if (my_lim - lo_bit < 32u) w &= (1u << (my_lim - lo_bit)) - 1u;
+                        return w;
+                    };
+                    const uint32_t t = (uint32_t)lane;
+                    const uint32_t cur = staged(t);
+                    const uint32_t prev = t > 0u ? staged(t - 1) : 0u;
+                    const uint32_t val = __funnelshift_l(prev, cur, sh);
+                    const uint64_t k = first_word + t;
+                    const bool owned = (t > 0u || sh == 0u) && ((k + 1) * 32ull <= end_bit);
+                    if (owned) out[k] = val;
+                    else if (val != 0u) atomicOr(out + k, val);
+                }
+            }
+        }
+        // ---- 8-byte columns: contiguous copy-out of the staged survivors, kStageBufs columns per round
+        for (int c0 = 0; c0 < p.n_col8; c0 += kStageBufs) {
+            const int nc = (p.n_col8 - c0) < kStageBufs ? (p.n_col8 - c0) : kStageBufs;
+            if (c0 > 0) {
+                __syncwarp();  // the warp is done reading the previous round's staging buffers
+                stage_round(c0, nc);
+                __syncwarp();
+            }
+            for (int c = 0; c < nc; ++c) {
+                const uint64_t* stage = wstage + c * 256;
+                uint64_t* out = p.col8[c0 + c].out + oexcl;
+                for (uint32_t i = lane; i < my_lim; i += 32) st_stream(out + i, stage[i]);
+            }
+        }
+        __syncwarp();  // staging slices are reused by the warp's next sub-tile
     }
 }
 

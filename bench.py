@@ -174,6 +174,10 @@ def run_native(args):
             dist.barrier(device_ids=[local_rank])
 
     ctx = capi.Context(local_rank)
+    ctx.set_option(capi.OPT_PLAN, {"auto": capi.PLAN_AUTO, "fused": capi.PLAN_FUSED, "two_pass": capi.PLAN_TWO_PASS}[args.plan])
+    for opt, val in ((capi.OPT_SPARSE_MAX, args.sparse_max), (capi.OPT_DENSE_SLOTS, args.dense_slots), (capi.OPT_DENSE_CTAS_PER_SM, args.dense_ctas)):
+        if val is not None:
+            ctx.set_option(opt, val)
     rows = args.rows
     begin, end = shard_rows(rows * world, rank, world)
     assert end - begin == rows, (begin, end, rows)
@@ -412,6 +416,10 @@ def main():
     ap.add_argument("--e2e-batch-rows", type=int, default=16 << 20)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--plan", default="auto", choices=["auto", "fused", "two_pass"], help="execution plan of rvl_filter_project (rvl_plan)")
+    ap.add_argument("--sparse-max", type=int, default=None)
+    ap.add_argument("--dense-slots", type=int, default=None)
+    ap.add_argument("--dense-ctas", type=int, default=None)
     args = ap.parse_args()
     if args.cpu_rows is None:
         args.cpu_rows = 500_000 if args.impl == "reference" else 4_000_000

@@ -117,6 +117,23 @@ int32_t rvl_ctx_profile_read(rvl_ctx* ctx, double* fused_kernel_ms, int64_t* fus
 /* per-launch device times (ms, launch order) recorded since the last read; resets like profile_read */
 int32_t rvl_ctx_profile_read_launches(rvl_ctx* ctx, double* ms_out, int64_t cap, int64_t* n);
 
+/* Execution plan of rvl_filter_project.  Both plans produce identical bytes; they differ in how the work is laid out:
+ *   FUSED     one kernel: predicate, look-back scan and compaction of a 8192-row super-tile per CTA (one launch; small batches,
+ *             LIMIT early termination inside the kernel)
+ *   TWO_PASS  persistent predicate scan (selection bitmap + per-tile output offsets, no inter-CTA dependency) followed by an
+ *             independent compaction pass that streams dense tiles through a TMA shared-memory ring and gathers sparse tiles
+ *   AUTO      TWO_PASS for unlimited queries over batches of at least RVL_OPT_TWO_PASS_MIN_ROWS rows, else FUSED */
+typedef enum rvl_plan { RVL_PLAN_AUTO = 0, RVL_PLAN_FUSED = 1, RVL_PLAN_TWO_PASS = 2 } rvl_plan;
+typedef enum rvl_option {
+    RVL_OPT_PLAN = 0,               /* rvl_plan */
+    RVL_OPT_TWO_PASS_MIN_ROWS = 1,  /* default 4 Mi rows */
+    RVL_OPT_SPARSE_MAX = 2,         /* two-pass: 2048-row tiles with <= this many survivors are gathered (0..128, default 96) */
+    RVL_OPT_DENSE_SLOTS = 3,        /* two-pass: 16 KB ring slots per CTA of the dense kernel (2..14) */
+    RVL_OPT_DENSE_CTAS_PER_SM = 4,  /* 1 or 2 */
+    RVL_OPT_SCAN_SLOTS = 5          /* two-pass: 8 KB ring slots per warp of the predicate scan (1..3) */
+} rvl_option;
+int32_t rvl_ctx_set_option(rvl_ctx* ctx, int32_t option, int64_t value);
+
 /* pinned host memory for the H2D/D2H staging of the streaming path (execution: pinned double-buffering) */
 int32_t rvl_host_alloc(size_t bytes, void** ptr);
 int32_t rvl_host_free(void* ptr);

@@ -48,6 +48,10 @@ class RvlStreamConfig(C.Structure):
     _fields_ = [("batch_rows", C.c_int64), ("n_staging", C.c_int32), ("reserved", C.c_int32)]
 
 
+PLAN_AUTO, PLAN_FUSED, PLAN_TWO_PASS = 0, 1, 2
+OPT_PLAN, OPT_TWO_PASS_MIN_ROWS, OPT_SPARSE_MAX, OPT_DENSE_SLOTS, OPT_DENSE_CTAS_PER_SM, OPT_SCAN_SLOTS = 0, 1, 2, 3, 4, 5
+
+
 class RivulusError(RuntimeError):
     def __init__(self, status: int, message: str):
         super().__init__(f"[{STATUS_NAMES[status] if 0 <= status < len(STATUS_NAMES) else status}] {message}")
@@ -59,7 +63,7 @@ class RivulusError(RuntimeError):
 ABI_SYMBOLS = [
     "rvl_abi_version", "rvl_last_error", "rvl_device_count",
     "rvl_ctx_create", "rvl_ctx_destroy", "rvl_ctx_synchronize", "rvl_ctx_cuda_stream", "rvl_ctx_device", "rvl_ctx_launch_count",
-    "rvl_ctx_profile_enable", "rvl_ctx_profile_read", "rvl_ctx_profile_read_launches",
+    "rvl_ctx_profile_enable", "rvl_ctx_profile_read", "rvl_ctx_profile_read_launches", "rvl_ctx_set_option",
     "rvl_host_alloc", "rvl_host_free",
     "rvl_batch_upload", "rvl_batch_wrap_device", "rvl_batch_release", "rvl_batch_num_rows", "rvl_batch_num_columns",
     "rvl_batch_column", "rvl_batch_download_column", "rvl_batch_slice", "rvl_batch_select", "rvl_batch_concat",
@@ -227,6 +231,10 @@ class Context:
         n = C.c_int64()
         check(lib().rvl_ctx_launch_count(self._h, C.byref(n)))
         return n.value
+
+    def set_option(self, option: int, value: int):
+        """rvl_ctx_set_option: OPT_PLAN (PLAN_AUTO / PLAN_FUSED / PLAN_TWO_PASS) and the two-pass tuning knobs."""
+        check(lib().rvl_ctx_set_option(self._h, C.c_int32(option), C.c_int64(value)))
 
     def profile_enable(self, on: bool = True):
         check(lib().rvl_ctx_profile_enable(self._h, int(on)))

@@ -1,0 +1,305 @@
+// compact_kernels.cuh — second pass of the two-pass Filter + Select plan used for large batches.
+//
+// Replaces (reference, /root/reference/src) the per-column gather of the survivors:
+//   eager     physical_plan/plan.rs:132-147   (filtered_data.push(col[i].clone()) per kept row, per column)
+//   streaming execution/record_batch.rs:108-178 (take -> take_array: builder append per index, per column)
+//             execution/array/bitmap.rs:142-155 (bit-at-a-time validity append)
+//
+// Pass 1 (fused_filter.cuh launched without columns) has already written, for the whole batch: the row-order
+// selection bitmap, the exclusive output index of every 2048-row tile, and two tile lists — DENSE tiles (more than
+// sparse_max survivors) and SPARSE tiles (1..sparse_max survivors).  No tile of this pass depends on another one.
+//
+//   compact_dense_kernel   persistent, one CTA per SM, warp-specialised.  A producer lane streams every projected
+//                          8-byte column of its tiles through a ring of 16 KB shared-memory slots with TMA 1-D bulk
+//                          copies (cp.async.bulk + mbarrier complete_tx): ~190 KB per SM in flight with no registers
+//                          held, fully coalesced 128-byte DRAM bursts.  Eight consumer warps pick the survivors out of
+//                          each slot (lane <-> row, rank = popc of the selection word below the lane) and store them
+//                          at their final position: a warp store covers consecutive output addresses.
+//                          Why whole tiles: B200 DRAM moves 128-byte lines, so at >= ~5 % selectivity nearly every
+//                          line of a projected column is needed anyway (1 - 0.95^16 = 56 %, 1 - 0.9^16 = 81 %).
+//   gather_sparse_kernel   high occupancy, one warp per sparse tile: survivors are listed in shared memory and the
+//                          (survivor, column) pairs are spread over the lanes so that every gather load of the tile is
+//                          in flight at once; dead lines are never touched.
+//
+// Bit-packed columns (validity bitmaps, Boolean values) are compacted with one warp REDUX.OR per 32 rows into
+// per-lane output words; words owned by a warp's run are stored, the two boundary words are OR-ed atomically.
+#pragma once
+#include "scan_kernels.cuh"
+
+namespace rvl {
+
+constexpr int kCompactWarps = 8;                          // consumer warps of the dense kernel (256 rows each per tile)
+constexpr int kCompactThreads = (kCompactWarps + 1) * 32;  // + 1 producer warp
+constexpr uint32_t kSlotBytes = kTileRows * 8;            // one column tile
+constexpr int kSparseCap = 128;                           // most survivors a "sparse" tile may hold
+
+struct CompactParams {
+    int64_t n_rows;
+    int64_t limit;                       // < 0 none; survivors whose global index >= limit are dropped
+    const uint32_t* sel;                 // row-order selection words, whole tiles readable, zero beyond n_rows
+    const uint64_t* tile_info;           // scan_kernels.cuh: (exclusive count inside the owning range << 12) | survivors
+    const uint64_t* chunk_base;          // global exclusive output index of every range's first tile
+    int64_t tiles_per_chunk;
+    const unsigned long long* base_in;   // rows emitted by earlier batches of the same query (streaming) or nullptr
+    const uint32_t* list;                // tile ids to process
+    const uint32_t* list_count;          // device word: entries in `list`
+    int32_t n_col8, n_bits;
+    int32_t n_slots;                     // dense kernel: ring depth
+    int32_t pad;
+    Col8 col8[kMaxCol8];
+    BitCol bits[kMaxBitCols];
+};
+
+__device__ __forceinline__ uint64_t tile_prefix_of(const CompactParams& p, int64_t tile) {
+    return p.chunk_base[tile / p.tiles_per_chunk] + (p.tile_info[tile] >> kInfoShift);
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Exclusive ranks of the 64 selection words of a tile, computed redundantly by every warp:
+// lane l holds words l (w0) and l + 32 (w1); returns their exclusive survivor offsets inside the tile.
+__device__ __forceinline__ void tile_word_scan(uint32_t w0, uint32_t w1, int lane, uint32_t& e0, uint32_t& e1, uint32_t& total) {
+    const uint32_t c0 = __popc(w0), c1 = __popc(w1);
+    uint32_t i0 = c0, i1 = c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, i0, o), b = __shfl_up_sync(0xFFFFFFFFu, i1, o);
+        if (lane >= o) { i0 += a; i1 += b; }
+    }
+    const uint32_t t0 = __shfl_sync(0xFFFFFFFFu, i0, 31);
+    e0 = i0 - c0;
+    e1 = t0 + i1 - c1;
+    total = t0 + __shfl_sync(0xFFFFFFFFu, i1, 31);
+}
+
+static __global__ void __launch_bounds__(kCompactThreads, 2) compact_dense_kernel(const __grid_constant__ CompactParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* const slots = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* const full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)p.n_slots * kSlotBytes);
+    uint64_t* const empty = full + p.n_slots;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n_list = *p.list_count;
+    if (blockIdx.x >= n_list) return;
+    if (tid == 0) {
+        for (int s = 0; s < p.n_slots; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kCompactWarps); }
+        mbar_init_fence();
+    }
+    __syncthreads();
+
+    if (warp == kCompactWarps) {
+        // ---------------------------------------------------------------- producer: one lane feeds the ring
+        if (lane == 0 && p.n_col8 > 0) {
+            int slot = 0;
+            uint32_t round = 0;
+            uint32_t next_id = p.list[blockIdx.x];
+            for (uint32_t i = blockIdx.x; i < n_list; i += gridDim.x) {
+                const int64_t tile = (int64_t)next_id;
+                if (i + gridDim.x < n_list) next_id = p.list[i + gridDim.x];
+                if (p.limit >= 0 && tile_prefix_of(p, tile) >= (uint64_t)p.limit) continue;  // consumers skip it too
+                const int64_t row0 = tile * kTileRows;
+                const bool whole = row0 + kTileRows <= p.n_rows;
+                for (int c = 0; c < p.n_col8; ++c) {
+                    if (round > 0u) mbar_wait(&empty[slot], (round - 1u) & 1u);  // consumers drained the previous use
+                    if (whole && p.col8[c].vec_ok) tma_load_1d(slots + (size_t)slot * kTileRows, p.col8[c].in + row0, kSlotBytes, &full[slot]);
+                    else mbar_arrive(&full[slot]);  // ragged tail / unaligned view: consumers read global memory themselves
+                    if (++slot == p.n_slots) { slot = 0; ++round; }
+                }
+            }
+        }
+        return;
+    }
+
+    // -------------------------------------------------------------------- consumers
+    const uint32_t lt = lanemask_lt();
+    const uint64_t base0 = p.base_in != nullptr ? (uint64_t)*p.base_in : 0ull;
+    int slot = 0;
+    uint32_t phase = 0;
+    // two-stage software prefetch: the tile id two iterations ahead, the selection words / prefix words one ahead.
+    // Nothing loaded here is touched before the next iteration, so no consumer warp waits on these round trips.
+    uint32_t nw0 = 0, nw1 = 0;
+    uint64_t ninfo = 0, ncbase = 0;
+    int64_t ntile = (int64_t)p.list[blockIdx.x];
+    uint32_t nntile = blockIdx.x + gridDim.x < n_list ? p.list[blockIdx.x + gridDim.x] : 0u;
+    {
+        const uint32_t* sw = p.sel + ntile * kTileWords;
+        nw0 = __ldg(sw + lane); nw1 = __ldg(sw + 32 + lane);
+        ninfo = p.tile_info[ntile]; ncbase = p.chunk_base[ntile / p.tiles_per_chunk];
+    }
+#pragma unroll 1
+    for (uint32_t i = blockIdx.x; i < n_list; i += gridDim.x) {
+        const int64_t tile = ntile;
+        const uint32_t w0 = nw0, w1 = nw1;
+        const uint64_t prefix = ncbase + (ninfo >> kInfoShift);
+        if (i + gridDim.x < n_list) {
+            ntile = (int64_t)nntile;
+            const uint32_t* sw = p.sel + ntile * kTileWords;
+            nw0 = __ldg(sw + lane); nw1 = __ldg(sw + 32 + lane);
+            ninfo = p.tile_info[ntile]; ncbase = p.chunk_base[ntile / p.tiles_per_chunk];
+            if (i + 2 * gridDim.x < n_list) nntile = p.list[i + 2 * gridDim.x];
+        }
+        if (p.limit >= 0 && prefix >= (uint64_t)p.limit) continue;  // tile lies entirely beyond the limit (no slots were filled)
+        const int64_t row0 = tile * kTileRows;
+        const int64_t wrow0 = row0 + (int64_t)warp * 256;  // this warp's 256 rows = 8 selection words
+        const bool whole = row0 + kTileRows <= p.n_rows;
+
+        uint32_t e0, e1, total;
+        tile_word_scan(w0, w1, lane, e0, e1, total);
+        const uint32_t wsel = warp < 4 ? w0 : w1, wexc = warp < 4 ? e0 : e1;
+        uint32_t selw[8];
+        uint32_t rk[8];       // rank of this lane's row (word k) inside the tile
+        uint32_t keep = 0;    // bit k: this lane's row of word k survives (and lies below the limit)
+        uint32_t wcnt = 0;    // survivors of this warp
+        uint32_t wfirst = 0;  // rank of the warp's first survivor inside the tile
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int src = (warp * 8 + k) & 31;
+            selw[k] = __shfl_sync(0xFFFFFFFFu, wsel, src);
+            const uint32_t rb = __shfl_sync(0xFFFFFFFFu, wexc, src);
+            if (k == 0) wfirst = rb;
+            rk[k] = rb + __popc(selw[k] & lt);
+            wcnt += __popc(selw[k]);
+            bool kp = (selw[k] >> lane) & 1u;
+            if (p.limit >= 0 && prefix + rk[k] >= (uint64_t)p.limit) kp = false;
+            keep |= (kp ? 1u : 0u) << k;
+        }
+        const uint64_t obase = prefix - base0;  // output index of the tile's first survivor
+
+        // ---- 8-byte columns: one ring slot each
+        for (int c = 0; c < p.n_col8; ++c) {
+            const Col8& col = p.col8[c];
+            const bool via_tma = whole && col.vec_ok != 0;
+            uint64_t v[8];
+            mbar_wait(&full[slot], phase);
+            if (via_tma) {
+                const uint64_t* src = slots + (size_t)slot * kTileRows + warp * 256 + lane;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = src[k * 32];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[slot]);  // slot may be refilled
+            if (++slot == p.n_slots) { slot = 0; phase ^= 1u; }
+            if (!via_tma) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    v[k] = 0ull;
+                    if ((keep >> k) & 1u) v[k] = ld_stream(col.in + wrow0 + k * 32 + lane);
+                }
+            }
+            if (col.valid.words != nullptr) {  // placeholder 0 under a null (primitive.rs:175-178)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t vm = load_bits32(col.valid, (uint64_t)(wrow0 + k * 32));
+                    if (((vm >> lane) & 1u) == 0u) v[k] = 0ull;
+                }
+            }
+            uint64_t* out = col.out + obase;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if ((keep >> k) & 1u) st_stream(out + rk[k], v[k]);
+        }
+
+        // ---- bit-packed columns: lane j accumulates output word j of this warp's run
+        if (p.n_bits > 0 && wcnt != 0u) {
+            const uint64_t gfirst = prefix + wfirst;  // global index of the warp's first survivor
+            uint32_t lim = wcnt;
+            if (p.limit >= 0) lim = gfirst >= (uint64_t)p.limit ? 0u : (uint32_t)min((uint64_t)wcnt, (uint64_t)p.limit - gfirst);
+            if (lim != 0u) {
+                const uint64_t P = gfirst - base0;
+                const uint32_t sh = (uint32_t)P & 31u;
+                const uint64_t first_word = P >> 5;
+                const uint32_t end = sh + lim;             // bits [sh, end) of the run are ours
+                const uint32_t n_words = (end + 31u) >> 5;  // <= 9
+                for (int b = 0; b < p.n_bits; ++b) {
+                    const BitCol& bc = p.bits[b];
+                    uint32_t acc = 0, q = sh;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint64_t r = (uint64_t)(wrow0 + k * 32);
+                        const uint32_t in = load_bits32(bc.in, r) & load_bits32(bc.mask, r);
+                        const uint32_t bit = (in >> lane) & (selw[k] >> lane) & 1u;
+                        const uint32_t cw = __reduce_or_sync(0xFFFFFFFFu, bit << __popc(selw[k] & lt));
+                        const uint32_t s = q & 31u;
+                        if ((uint32_t)lane == (q >> 5)) acc |= cw << s;
+                        if (s != 0u && (uint32_t)lane == (q >> 5) + 1u) acc |= cw >> (32u - s);
+                        q += __popc(selw[k]);
+                    }
+                    if ((uint32_t)lane < n_words) {
+                        const uint32_t lo = (uint32_t)lane * 32u;
+                        if (end - lo < 32u) acc &= (1u << (end - lo)) - 1u;  // survivors cut off by the limit
+                        const bool owned = (lane > 0 || sh == 0u) && (lo + 32u <= end);
+                        uint32_t* o = bc.out + first_word + lane;
+                        if (owned) *o = acc;
+                        else if (acc != 0u) atomicOr(o, acc);
+                    }
+                }
+            }
+        }
+    }
+}
+
+static __global__ void __launch_bounds__(kBlock) gather_sparse_kernel(const __grid_constant__ CompactParams p) {
+    __shared__ uint16_t s_rows[kWarps][kSparseCap];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n_list = *p.list_count;
+    const uint64_t base0 = p.base_in != nullptr ? (uint64_t)*p.base_in : 0ull;
+    uint16_t* rows = s_rows[warp];
+#pragma unroll 1
+    for (uint32_t i = blockIdx.x * kWarps + warp; i < n_list; i += gridDim.x * kWarps) {
+        const int64_t tile = (int64_t)p.list[i];
+        const int64_t row0 = tile * kTileRows;
+        const uint32_t* sw = p.sel + tile * kTileWords;
+        const uint32_t w0 = __ldg(sw + lane), w1 = __ldg(sw + 32 + lane);
+        const uint64_t prefix = tile_prefix_of(p, tile);
+        uint32_t e0, e1, total;
+        tile_word_scan(w0, w1, lane, e0, e1, total);
+        if (total > (uint32_t)kSparseCap) total = kSparseCap;  // cannot happen: pass 1 classifies with sparse_max <= kSparseCap
+        uint32_t lim = total;
+        if (p.limit >= 0) lim = prefix >= (uint64_t)p.limit ? 0u : (uint32_t)min((uint64_t)total, (uint64_t)p.limit - prefix);
+        __syncwarp();  // previous tile's list is no longer read
+        for (uint32_t w = w0, r = e0; w != 0u; w &= w - 1u, ++r)
+            if (r < (uint32_t)kSparseCap) rows[r] = (uint16_t)(lane * 32 + (__ffs(w) - 1));
+        for (uint32_t w = w1, r = e1; w != 0u; w &= w - 1u, ++r)
+            if (r < (uint32_t)kSparseCap) rows[r] = (uint16_t)((lane + 32) * 32 + (__ffs(w) - 1));
+        __syncwarp();
+        const uint64_t obase = prefix - base0;
+
+        // (column, survivor) pairs over the lanes, four rounds of loads in flight before the first store
+        const uint32_t n_task = lim * (uint32_t)p.n_col8;
+        for (uint32_t t0 = 0; t0 < n_task; t0 += 128) {
+            uint64_t v[4];
+            uint64_t* dst[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t t = t0 + u * 32 + lane;
+                v[u] = 0ull; dst[u] = nullptr;
+                if (t < n_task) {
+                    const uint32_t c = t / lim, e = t - c * lim;
+                    const Col8& col = p.col8[c];
+                    const int64_t row = row0 + rows[e];
+                    bool ok = true;
+                    if (col.valid.words != nullptr) { const uint64_t bit = col.valid.bit0 + (uint64_t)row; ok = (__ldg(col.valid.words + (bit >> 5)) >> (bit & 31)) & 1u; }
+                    if (ok) v[u] = ld_stream(col.in + row);  // placeholder 0 under a null (primitive.rs:175-178)
+                    dst[u] = col.out + obase + e;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (dst[u] != nullptr) st_stream(dst[u], v[u]);
+        }
+        const uint32_t n_btask = lim * (uint32_t)p.n_bits;
+        for (uint32_t t = lane; t < n_btask; t += 32) {
+            const uint32_t b = t / lim, e = t - b * lim;
+            const BitCol& bc = p.bits[b];
+            const uint64_t row = (uint64_t)(row0 + rows[e]);
+            bool set = true;
+            if (bc.in.words != nullptr) { const uint64_t bit = bc.in.bit0 + row; set = (__ldg(bc.in.words + (bit >> 5)) >> (bit & 31)) & 1u; }
+            if (set && bc.mask.words != nullptr) { const uint64_t bit = bc.mask.bit0 + row; set = (__ldg(bc.mask.words + (bit >> 5)) >> (bit & 31)) & 1u; }
+            if (set) { const uint64_t pos = obase + e; atomicOr(bc.out + (pos >> 5), 1u << (pos & 31)); }
+        }
+    }
+}
+
+}  // namespace rvl

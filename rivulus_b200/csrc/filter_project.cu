@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "aux_kernels.cuh"
+#include "compact_kernels.cuh"
 #include "filter_project.cuh"
 #include "fused_filter.cuh"
 #include "string_kernels.cuh"
@@ -151,22 +152,59 @@ static void launch_fused(const CoreRef& core, int kind, const FusedParams& fp) {
     // one CTA per super-tile of 8192 rows, taken in blockIdx order (the look-back relies on in-order dispatch)
     const dim3 grid((unsigned)fp.n_super), block(kBlock);
     const size_t smem = sizeof(FusedSmem);
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (core->profile) {
-        cudaEventCreate(&e0); cudaEventCreate(&e1);
-        cudaEventRecord(e0, core->stream);
-    }
     switch (kind) {
         case kPredI64: fused_filter_project_kernel<kPredI64><<<grid, block, smem, core->stream>>>(fp); break;
         case kPredF64: fused_filter_project_kernel<kPredF64><<<grid, block, smem, core->stream>>>(fp); break;
         case kPredBits: fused_filter_project_kernel<kPredBits><<<grid, block, smem, core->stream>>>(fp); break;
         default: fused_filter_project_kernel<kPredTrue><<<grid, block, smem, core->stream>>>(fp); break;
     }
-    if (core->profile) {
-        cudaEventRecord(e1, core->stream);
-        core->prof_events.emplace_back(e0, e1);
-    }
     core->launches++;
+}
+
+// first pass of the two-pass plan (scan_kernels.cuh)
+template <int PRED>
+static int launch_scan_t(const CoreRef& core, const ScanParams& sp, int ctas) {
+    static bool opted[64] = {false};
+    if (!opted[core->device & 63]) {
+        RVL_CUDA_TRY(cudaFuncSetAttribute(predicate_scan_kernel<PRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanWarps * 3 * (int)(kScanItemBytes + 8)));
+        opted[core->device & 63] = true;
+    }
+    const size_t smem = (size_t)kScanWarps * sp.n_slots * (kScanItemBytes + 8);
+    predicate_scan_kernel<PRED><<<(unsigned)ctas, kScanWarps * 32, smem, core->stream>>>(sp);
+    core->launches++;
+    RVL_CUDA_TRY(cudaGetLastError());
+    return RVL_OK;
+}
+static int launch_scan(const CoreRef& core, int kind, const ScanParams& sp, int ctas) {
+    switch (kind) {
+        case kPredI64: return launch_scan_t<kPredI64>(core, sp, ctas);
+        case kPredF64: return launch_scan_t<kPredF64>(core, sp, ctas);
+        case kPredBits: return launch_scan_t<kPredBits>(core, sp, ctas);
+        default: return launch_scan_t<kPredTrue>(core, sp, ctas);
+    }
+}
+
+// second pass of the two-pass plan (compact_kernels.cuh): dense tiles through the TMA ring, sparse tiles gathered
+static int launch_compaction(const CoreRef& core, CompactParams cp, const uint32_t* dense_list, const uint32_t* sparse_list,
+                             const uint32_t* list_counts) {
+    static bool opted[64] = {false};
+    if (!opted[core->device & 63]) {
+        RVL_CUDA_TRY(cudaFuncSetAttribute(compact_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 14 * (int)(kSlotBytes + 16)));
+        opted[core->device & 63] = true;
+    }
+    const int per_sm = std::max(1, std::min(2, core->dense_ctas_per_sm));
+    const int max_slots = per_sm == 1 ? 14 : 6;
+    cp.n_slots = std::max(2, std::min(max_slots, core->dense_slots));
+    const size_t smem = (size_t)cp.n_slots * (kSlotBytes + 16);
+    cp.list = dense_list; cp.list_count = list_counts;
+    compact_dense_kernel<<<(unsigned)(core->sm_count * per_sm), kCompactThreads, smem, core->stream>>>(cp);
+    core->launches++;
+    RVL_CUDA_TRY(cudaGetLastError());
+    cp.list = sparse_list; cp.list_count = list_counts + 1;
+    gather_sparse_kernel<<<(unsigned)(core->sm_count * 8), kBlock, 0, core->stream>>>(cp);
+    core->launches++;
+    RVL_CUDA_TRY(cudaGetLastError());
+    return RVL_OK;
 }
 
 int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pred, const int32_t* proj, int32_t nproj,
@@ -184,6 +222,13 @@ int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pre
 
     auto pend = std::make_unique<FpPending>();
     pend->core = core; pend->n = n; pend->limit = limit; pend->n_launched = 0;
+    // kernel-level timing (rvl_ctx_profile_*): one bracket around every kernel of this operator invocation
+    struct ProfScope {
+        const CoreRef& core; cudaEvent_t e0 = nullptr;
+        explicit ProfScope(const CoreRef& c) : core(c) { if (core->profile) { cudaEventCreate(&e0); cudaEventRecord(e0, core->stream); } }
+        void end() { if (e0) { cudaEvent_t e1; cudaEventCreate(&e1); cudaEventRecord(e1, core->stream); core->prof_events.emplace_back(e0, e1); e0 = nullptr; } }
+        ~ProfScope() { if (e0) cudaEventDestroy(e0); }
+    } prof(core);
     PredPlan pp;
     RVL_TRY(lower_predicate(core, in, pred, &pp));
     pend->temps.push_back(pp.tmp_bits); pend->temps.push_back(pp.tmp_lit);
@@ -233,20 +278,72 @@ int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pre
 
     if (n > 0) {
         const int launches_needed = std::max<int>(1, std::max<int>(((int)col8s.size() + kMaxCol8 - 1) / kMaxCol8, ((int)bitcols.size() + kMaxBitCols - 1) / kMaxBitCols));
-        const bool need_sel = want_mask || !strjobs.empty() || launches_needed > 1;
-        BufRef status, sel, tile_prefix;
+        // plan: one fused pass (small batches, one launch), or predicate scan + independent compaction pass (large batches)
+        const bool two_pass = (!col8s.empty() || !bitcols.empty()) &&
+                              (core->plan_mode == 2 || (core->plan_mode == 0 && limit < 0 && n >= core->two_pass_min_rows));
+        const bool need_sel = want_mask || !strjobs.empty() || launches_needed > 1 || two_pass;
+        BufRef status, sel, tile_prefix, lists;
         // per launch: one look-back descriptor per super-tile, zeroed together
         const int64_t n_super = (n + kSuperRows - 1) / kSuperRows;
         const size_t status_words = (size_t)n_super;
         RVL_TRY(dev_alloc_zeroed(core, status_words * 8 * (size_t)launches_needed, &status));
         pend->temps.push_back(status);
         if (need_sel) {
-            RVL_TRY(dev_alloc_zeroed(core, (size_t)((n + 63) / 64) * 8, &sel));
+            // whole tiles, so the second-pass kernels can read 64 words per tile unconditionally
+            // (the two-pass scan writes every word of every tile unless a LIMIT lets ranges stop early)
+            if (two_pass && limit < 0) RVL_TRY(dev_alloc(core, (size_t)tiles * kTileWords * 4, &sel));
+            else RVL_TRY(dev_alloc_zeroed(core, (size_t)tiles * kTileWords * 4, &sel));
             if (want_mask) pend->mask = sel; else pend->temps.push_back(sel);
         }
-        if (!strjobs.empty()) { RVL_TRY(dev_alloc(core, (size_t)tiles * 8, &tile_prefix)); pend->temps.push_back(tile_prefix); }
+        if (!strjobs.empty() || two_pass) { RVL_TRY(dev_alloc(core, (size_t)tiles * 8, &tile_prefix)); pend->temps.push_back(tile_prefix); }
 
-        for (int L = 0; L < launches_needed; ++L) {
+        int64_t tiles_per_chunk = 0;
+        BufRef chunk_base;
+        if (two_pass) {
+            // pass 1: persistent predicate scan (scan_kernels.cuh), every warp owns a contiguous range of tiles
+            const int scan_ctas = std::min(384, core->sm_count);
+            const int64_t n_ranges = (int64_t)scan_ctas * kScanWarps;
+            tiles_per_chunk = std::max<int64_t>(1, (tiles + n_ranges - 1) / n_ranges);
+            // [dense tile ids | sparse tile ids | n_dense, n_sparse, CTAs done, pad] and the per-range bases
+            RVL_TRY(dev_alloc(core, (size_t)tiles * 8 + 16, &lists));
+            pend->temps.push_back(lists);
+            RVL_TRY(dev_alloc(core, (size_t)n_ranges * 8, &chunk_base));
+            pend->temps.push_back(chunk_base);
+            uint32_t* dense_list = (uint32_t*)lists->ptr;
+            uint32_t* sparse_list = dense_list + tiles;
+            uint32_t* list_counts = sparse_list + tiles;
+            RVL_CUDA_TRY(cudaMemsetAsync(list_counts, 0, 16, core->stream));
+            if (limit >= 0) RVL_CUDA_TRY(cudaMemsetAsync(tile_prefix->ptr, 0, (size_t)tiles * 8, core->stream));  // ranges may stop early
+            ScanParams sp{};
+            sp.n_rows = n; sp.n_tiles = tiles; sp.tiles_per_warp = tiles_per_chunk; sp.limit = limit;
+            sp.pred_values = pp.values; sp.lit_bits = pp.lit_bits; sp.pred_valid = pp.valid; sp.truth = pp.truth;
+            sp.range_lo = pp.range_lo; sp.range_span = pp.range_span; sp.range_neg = pp.range_neg;
+            sp.keep_null = pp.keep_null; sp.pred_vec_ok = pp.vec_ok; sp.pb_a = pp.pb_a; sp.pb_b = pp.pb_b; sp.pb_vals = pp.pb_vals;
+            sp.n_slots = std::max(1, std::min(3, core->scan_slots));
+            sp.sparse_max = (uint32_t)std::max(0, std::min(kSparseCap, core->sparse_max));
+            sp.base_in = base_in;
+            sp.sel_out = (uint32_t*)sel->ptr;
+            sp.tile_info = (uint64_t*)tile_prefix->ptr;
+            sp.chunk_base = (uint64_t*)chunk_base->ptr;
+            sp.dense_list = dense_list; sp.sparse_list = sparse_list; sp.list_counts = list_counts;
+            sp.total_out = dctr;
+            RVL_TRY(launch_scan(core, pp.kind, sp, scan_ctas));
+            for (int L = 0; L < launches_needed; ++L) {
+                CompactParams cp{};
+                cp.n_rows = n; cp.limit = limit; cp.sel = (const uint32_t*)sel->ptr; cp.tile_info = (const uint64_t*)tile_prefix->ptr;
+                cp.chunk_base = (const uint64_t*)chunk_base->ptr; cp.tiles_per_chunk = tiles_per_chunk;
+                cp.base_in = base_in;
+                const int c0 = L * kMaxCol8, c1 = std::min<int>((int)col8s.size(), c0 + kMaxCol8);
+                cp.n_col8 = std::max(0, c1 - c0);
+                for (int k = 0; k < cp.n_col8; ++k) cp.col8[k] = col8s[(size_t)(c0 + k)];
+                const int b0 = L * kMaxBitCols, b1 = std::min<int>((int)bitcols.size(), b0 + kMaxBitCols);
+                cp.n_bits = std::max(0, b1 - b0);
+                for (int k = 0; k < cp.n_bits; ++k) cp.bits[k] = bitcols[(size_t)(b0 + k)];
+                RVL_TRY(launch_compaction(core, cp, dense_list, sparse_list, list_counts));
+            }
+        }
+
+        for (int L = 0; L < (two_pass ? 0 : launches_needed); ++L) {
             FusedParams fp{};
             fp.n_rows = n; fp.n_super = n_super; fp.limit = limit;
             int kind = pp.kind;
@@ -286,6 +383,7 @@ int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pre
             pend->temps.push_back(sstatus);
             StrGatherParams sp{};
             sp.n_rows = n; sp.limit = limit; sp.sel = (const uint32_t*)sel->ptr; sp.tile_prefix = (const uint64_t*)tile_prefix->ptr; sp.row_base = 0;
+            if (two_pass) { sp.chunk_base = (const uint64_t*)chunk_base->ptr; sp.tiles_per_chunk = tiles_per_chunk; }
             sp.offsets = (const int32_t*)s.offsets->ptr + s.offset; sp.data = (const uint8_t*)s.data->ptr;
             sp.valid = bitsrc_of(s.validity, s.offset, n);
             sp.out_offsets = (int32_t*)d.offsets->ptr; sp.out_data = (uint8_t*)d.data->ptr;
@@ -306,6 +404,7 @@ int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pre
             RVL_CUDA_TRY(cudaGetLastError());
         }
         pend->n_launched = 1;
+        prof.end();
     } else if (base_in != nullptr) {
         // empty batch in a chained query: the running total passes through unchanged
         RVL_CUDA_TRY(cudaMemcpyAsync(dctr, base_in, 8, cudaMemcpyDeviceToDevice, core->stream));

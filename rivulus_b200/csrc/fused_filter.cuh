@@ -92,6 +92,13 @@ struct FusedParams {
     uint32_t* done_flag;                 // set once some super-tile's inclusive prefix reaches the limit
     uint32_t* sel_out;                   // optional: row-order selection bitmap (n_rows bits, 8-byte aligned)
     uint64_t* tile_prefix_out;           // optional: exclusive output prefix of every 2048-row tile
+    // two-pass plan (compact_kernels.cuh): this launch only scans the predicate; every 2048-row tile with survivors is
+    // appended to the dense list (> sparse_max survivors: TMA-streamed compaction) or the sparse list (gathered)
+    uint32_t* dense_list;
+    uint32_t* sparse_list;
+    uint32_t* list_counts;               // [0] dense tiles, [1] sparse tiles (zeroed before the launch)
+    uint32_t sparse_max;
+    uint32_t pad2;
 };
 
 // dynamic shared memory of the fused kernel
@@ -368,7 +375,24 @@ __global__ void __launch_bounds__(kBlock, 3) fused_filter_project_kernel(const _
             const int64_t t = super * kSub + lane;
             if (t * kTileRows < p.n_rows) p.tile_prefix_out[t] = excl + l_soff;
         }
+        if (p.list_counts != nullptr) {
+            // classify this super-tile's tiles for the second pass; tiles entirely beyond the limit are dropped
+            const int64_t t = super * kSub + lane;
+            const bool live = lane < kSub && l_cnt != 0u && (p.limit < 0 || excl + l_soff < (uint64_t)p.limit);
+            const bool dense = live && l_cnt > p.sparse_max;
+            const uint32_t dm = __ballot_sync(0xFFFFFFFFu, dense), sm_ = __ballot_sync(0xFFFFFFFFu, live && !dense);
+            uint32_t db = 0, sb = 0;
+            if (lane == 0) {
+                if (dm != 0u) db = atomicAdd(p.list_counts, (uint32_t)__popc(dm));
+                if (sm_ != 0u) sb = atomicAdd(p.list_counts + 1, (uint32_t)__popc(sm_));
+            }
+            db = __shfl_sync(0xFFFFFFFFu, db, 0);
+            sb = __shfl_sync(0xFFFFFFFFu, sb, 0);
+            if (dense) p.dense_list[db + __popc(dm & lt)] = (uint32_t)t;
+            else if (live) p.sparse_list[sb + __popc(sm_ & lt)] = (uint32_t)t;
+        }
     }
+    if (p.n_col8 == 0 && p.n_bits == 0) return;  // scan-only launch (mask / two-pass plan / string-only projection)
     if (warp_total == 0u) return;  // this warp has nothing to emit (no block barrier follows)
 
     // ---------------------------------------------------------------- phase B: every warp emits its own survivors

@@ -167,6 +167,30 @@ int32_t rvl_ctx_cuda_stream(rvl_ctx* ctx, void** s) { *s = (void*)ctx->core->str
 int32_t rvl_ctx_device(rvl_ctx* ctx, int32_t* d) { *d = ctx->core->device; return RVL_OK; }
 int32_t rvl_ctx_launch_count(rvl_ctx* ctx, int64_t* n) { *n = ctx->core->launches.load(); return RVL_OK; }
 
+int32_t rvl_ctx_set_option(rvl_ctx* ctx, int32_t option, int64_t value) {
+    if (!ctx) return fail(RVL_INVALID_ARGUMENT, "null context");
+    CtxCore& c = *ctx->core;
+    switch (option) {
+        case RVL_OPT_PLAN:
+            if (value < RVL_PLAN_AUTO || value > RVL_PLAN_TWO_PASS) return fail(RVL_INVALID_ARGUMENT, "unknown plan");
+            c.plan_mode = (int)value; return RVL_OK;
+        case RVL_OPT_TWO_PASS_MIN_ROWS: c.two_pass_min_rows = value; return RVL_OK;
+        case RVL_OPT_SPARSE_MAX:
+            if (value < 0 || value > 128) return fail(RVL_INVALID_ARGUMENT, "sparse_max must be in [0, 128]");
+            c.sparse_max = (int)value; return RVL_OK;
+        case RVL_OPT_DENSE_SLOTS:
+            if (value < 2 || value > 14) return fail(RVL_INVALID_ARGUMENT, "dense_slots must be in [2, 14]");
+            c.dense_slots = (int)value; return RVL_OK;
+        case RVL_OPT_DENSE_CTAS_PER_SM:
+            if (value < 1 || value > 2) return fail(RVL_INVALID_ARGUMENT, "dense_ctas_per_sm must be 1 or 2");
+            c.dense_ctas_per_sm = (int)value; return RVL_OK;
+        case RVL_OPT_SCAN_SLOTS:
+            if (value < 1 || value > 3) return fail(RVL_INVALID_ARGUMENT, "scan_slots must be in [1, 3]");
+            c.scan_slots = (int)value; return RVL_OK;
+        default: return fail(RVL_INVALID_ARGUMENT, "unknown option");
+    }
+}
+
 int32_t rvl_ctx_profile_enable(rvl_ctx* ctx, int32_t enable) {
     if (!ctx) return fail(RVL_INVALID_ARGUMENT, "null argument");
     RVL_TRY(ctx->core->prof_flush());

@@ -21,6 +21,8 @@ struct StrGatherParams {
     int64_t limit;                      // < 0 none
     const uint32_t* sel;                // row-order selection words from the fused kernel; nullptr = every row (concat)
     const uint64_t* tile_prefix;        // exclusive output row index of each tile; nullptr = row_base + tile * 2048
+    const uint64_t* chunk_base;         // two-pass plan: tile_prefix holds scan_kernels.cuh tile_info words and the row index is
+    int64_t tiles_per_chunk;            //   chunk_base[tile / tiles_per_chunk] + (tile_prefix[tile] >> 12); nullptr = plain prefixes
     int64_t row_base;
     const unsigned long long* row_base_in;  // rows emitted by earlier batches (streaming): tile_prefix/limit are global, output index = rank - base
     const int32_t* offsets;             // row 0 of the view
@@ -72,7 +74,8 @@ static __global__ void __launch_bounds__(kBlock, 4) string_gather_kernel(const _
         if (p.sel != nullptr) selbyte = reinterpret_cast<const uint8_t*>(p.sel)[tile * (kTileRows / 8) + tid];
         else selbyte = (p.n_rows - row0 >= 8) ? 0xFFu : ((1u << (p.n_rows - row0)) - 1u);
     }
-    const uint64_t rexcl = p.tile_prefix != nullptr ? p.tile_prefix[tile] : (uint64_t)(p.row_base + tile * kTileRows);
+    uint64_t rexcl = p.tile_prefix != nullptr ? p.tile_prefix[tile] : (uint64_t)(p.row_base + tile * kTileRows);
+    if (p.chunk_base != nullptr) rexcl = p.chunk_base[tile / p.tiles_per_chunk] + (rexcl >> 12);
     const uint64_t rbase = p.row_base_in != nullptr ? (uint64_t)*p.row_base_in : 0ull;
 
     uint32_t cnt_total;

@@ -1,0 +1,12 @@
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu9.log 2>&1; echo "pytest rc=$?"
+tail -15 gpurun_out/pytest_gpu9.log
+for plan in two_pass; do
+  python bench.py --steps 5 --warmup 3 --no-e2e --cpu-rows 0 --verify-rows 16000000 --plan $plan > gpurun_out/bench_$plan.json 2> gpurun_out/bench_$plan.err; echo "rc=$?"
+  tail -3 gpurun_out/bench_$plan.err
+  python - <<PY
+import json
+d=json.load(open("gpurun_out/bench_$plan.json"))
+print("$plan", d["ms_per_step"], d["roofline"]["frac"], [ (round(x["kernel_ms"],3), round(x["frac_of_peak"],3)) for x in d["sweep"]])
+PY
+done
+bash scripts/gpu_run2.sh

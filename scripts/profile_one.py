@@ -10,8 +10,16 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--rows", type=int, default=50_000_000)
 ap.add_argument("--thresholds", default="998,899,499,99")
 ap.add_argument("--reps", type=int, default=1)
+ap.add_argument("--plan", default="auto", choices=["auto", "fused", "two_pass"])
+ap.add_argument("--sparse-max", type=int, default=None)
+ap.add_argument("--dense-slots", type=int, default=None)
+ap.add_argument("--dense-ctas", type=int, default=None)
 args = ap.parse_args()
 ctx = capi.Context(0)
+ctx.set_option(capi.OPT_PLAN, {"auto": capi.PLAN_AUTO, "fused": capi.PLAN_FUSED, "two_pass": capi.PLAN_TWO_PASS}[args.plan])
+for opt, val in ((capi.OPT_SPARSE_MAX, args.sparse_max), (capi.OPT_DENSE_SLOTS, args.dense_slots), (capi.OPT_DENSE_CTAS_PER_SM, args.dense_ctas)):
+    if val is not None:
+        ctx.set_option(opt, val)
 spec = [(capi.SYNTH_KEY1000, 0, 0), (capi.SYNTH_I64, 1, 0), (capi.SYNTH_F64, 2, 0), (capi.SYNTH_I64, 3, 0), (capi.SYNTH_F64, 4, 0)]
 t = ctx.gen_batch(spec, args.rows)
 for _ in range(args.reps):

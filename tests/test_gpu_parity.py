@@ -17,9 +17,11 @@ pytestmark = pytest.mark.gpu
 OPS = ["==", "!=", "<", ">", "<=", ">="]
 
 
-@pytest.fixture(scope="module")
-def ctx():
+# every parity test runs under both execution plans of the operator (include/rivulus_gpu.h: rvl_plan) and under AUTO
+@pytest.fixture(scope="module", params=["fused", "two_pass", "auto"])
+def ctx(request):
     c = capi.Context(0)
+    c.set_option(capi.OPT_PLAN, {"fused": capi.PLAN_FUSED, "two_pass": capi.PLAN_TWO_PASS, "auto": capi.PLAN_AUTO}[request.param])
     yield c
     c.close()
 
@@ -334,3 +336,41 @@ def test_large_synthetic_checksums(ctx, thr, n):
     count, sums = O.synth_filter_checksums(n, 0, capi.SYNTH_KEY1000, 0, ">", thr, [(s[0], s[1]) for s in spec[1:]])
     assert got.num_rows() == count
     assert [got.checksum(j) for j in range(5)] == sums
+
+
+# ------------------------------------------------------------------ two-pass plan: dense / sparse tile classification
+@pytest.mark.parametrize("sparse_max", [0, 1, 7, 96, 128])
+@pytest.mark.parametrize("limit", [-1, 12345])
+def test_two_pass_mixed_density_tiles(sparse_max, limit):
+    """Clustered survivors: empty, sparse and dense 2048-row tiles in one batch, nulls in every column, ragged tail,
+    bit-offset views; every classification threshold must give the same bytes as the oracle."""
+    rng = np.random.default_rng(77 + sparse_max)
+    n = 70_001
+    k = rng.integers(0, 1000, n)
+    dens = np.repeat(rng.choice([0.0, 0.002, 0.03, 0.3, 0.95], size=(n + 2047) // 2048), 2048)[:n]
+    k = np.where(rng.random(n) < dens, 2000, k % 500).astype(np.int64)
+    cols = [Col("i64", n, k, rng.random(n) > 0.05), random_col(rng, "f64", n, 0.1, offset=3, tail=5), random_col(rng, "i64", n, 0.0),
+            random_col(rng, "bool", n, 0.2, offset=13), random_col(rng, "f64", n, 0.5)]
+    c = capi.Context(0)
+    c.set_option(capi.OPT_PLAN, capi.PLAN_TWO_PASS)
+    c.set_option(capi.OPT_SPARSE_MAX, sparse_max)
+    try:
+        run_cmp(c, cols, 0, ">", 1000, [1, 2, 3, 4, 0], limit, tag=f"two-pass sparse_max={sparse_max} limit={limit}")
+        run_cmp(c, cols, 0, "<", 100, [4, 3], limit, tag=f"two-pass nulls-pass sparse_max={sparse_max}")
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("slots,per_sm", [(2, 1), (3, 2), (6, 2), (14, 1)])
+def test_two_pass_ring_depths(slots, per_sm):
+    rng = np.random.default_rng(5)
+    n = 1_500_000
+    cols = [random_col(rng, "i64", n, 0.0, lo=0, hi=1000)] + [random_col(rng, "f64" if j % 2 else "i64", n, 0.1 if j == 1 else 0.0) for j in range(5)]
+    c = capi.Context(0)
+    c.set_option(capi.OPT_PLAN, capi.PLAN_TWO_PASS)
+    c.set_option(capi.OPT_DENSE_SLOTS, slots)
+    c.set_option(capi.OPT_DENSE_CTAS_PER_SM, per_sm)
+    try:
+        run_cmp(c, cols, 0, ">", 299, [1, 2, 3, 4, 5], tag=f"ring slots={slots} per_sm={per_sm}")
+    finally:
+        c.close()

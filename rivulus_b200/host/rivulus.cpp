@@ -1,0 +1,1183 @@
+// rivulus.cpp — host layer over the C ABI (see rivulus.hpp).  Pure host logic (plan building, optimizer, validation,
+// lowering, dtype inference, error text) follows the reference line by line; every data-path step is a call into
+// librivulus_gpu.so.  Nothing here computes a query result on the CPU.
+#include "rivulus.hpp"
+
+#include <algorithm>
+#include <charconv>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <set>
+
+namespace rivulus {
+
+// ------------------------------------------------------------------------------------------------- helpers
+static void check(int32_t rc) {
+    if (rc != RVL_OK) {
+        const char* m = rvl_last_error();
+        throw Error(m ? m : "rivulus_gpu: unknown error", rc == RVL_OUT_OF_BOUNDS);
+    }
+}
+static inline bool get_bit(const std::vector<uint8_t>& b, size_t i) { return (b[i >> 3] >> (i & 7)) & 1; }
+static inline void set_bit(std::vector<uint8_t>& b, size_t i) { b[i >> 3] |= (uint8_t)(1u << (i & 7)); }
+static size_t count_valid(const std::vector<uint8_t>& bits, size_t n) {
+    size_t c = 0;
+    for (size_t i = 0; i < n; ++i) c += get_bit(bits, i);
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------------- datatypes/series.rs
+const char* dtype_name(DataType d) {
+    switch (d) {
+        case DataType::Int64: return "Int64";
+        case DataType::Float64: return "Float64";
+        case DataType::String: return "String";
+        case DataType::Boolean: return "Boolean";
+        case DataType::Null: return "Null";
+    }
+    return "?";
+}
+
+DataType AnyValue::data_type() const {
+    switch (tag) {
+        case kNull: return DataType::Null;
+        case kInt64: return DataType::Int64;
+        case kFloat64: return DataType::Float64;
+        case kString: return DataType::String;
+        case kBoolean: return DataType::Boolean;
+    }
+    return DataType::Null;
+}
+
+static std::string f64_text(double v, bool debug) {  // Rust `{}` / `{:?}` of an f64
+    if (std::isnan(v)) return "NaN";
+    if (std::isinf(v)) return v < 0 ? "-inf" : "inf";
+    char buf[400];
+    auto r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::fixed);
+    std::string s(buf, r.ptr);
+    if (debug && s.find('.') == std::string::npos) s += ".0";
+    return s;
+}
+static std::string quoted(const std::string& s) {  // `{:?}` of a str
+    std::string o = "\"";
+    for (char c : s) {
+        if (c == '"') o += "\\\"";
+        else if (c == '\\') o += "\\\\";
+        else if (c == '\n') o += "\\n";
+        else if (c == '\t') o += "\\t";
+        else if (c == '\r') o += "\\r";
+        else o += c;
+    }
+    return o + "\"";
+}
+std::string AnyValue::display() const {
+    switch (tag) {
+        case kNull: return "null";
+        case kInt64: return std::to_string(i);
+        case kFloat64: return f64_text(f, false);
+        case kString: return s;
+        case kBoolean: return b ? "true" : "false";
+    }
+    return "";
+}
+std::string AnyValue::debug() const {
+    switch (tag) {
+        case kNull: return "Null";
+        case kInt64: return "Int64(" + std::to_string(i) + ")";
+        case kFloat64: return "Float64(" + f64_text(f, true) + ")";
+        case kString: return "String(" + quoted(s) + ")";
+        case kBoolean: return std::string("Boolean(") + (b ? "true" : "false") + ")";
+    }
+    return "";
+}
+
+static bool types_compatible(DataType e, DataType f) {  // series.rs:255-264
+    if (e == f) return true;
+    return (e == DataType::Int64 && f == DataType::Float64) || (e == DataType::Float64 && f == DataType::Int64);
+}
+
+Series Series::make(const std::string& name, const std::vector<AnyValue>& data) {  // series.rs:185-221
+    if (data.empty()) throw Error("Empty series not allowed");
+    std::optional<DataType> first;
+    for (const auto& v : data)
+        if (!v.is_null()) { first = v.data_type(); break; }
+    DataType dtype = first.value_or(DataType::Null);
+    bool saw_int = false;
+    for (const auto& v : data) {
+        if (v.is_null()) continue;
+        const DataType cur = v.data_type();
+        if (!types_compatible(dtype, cur))
+            throw Error(std::string("Mixed types in series: expected ") + dtype_name(dtype) + ", found " + dtype_name(cur));
+        if (dtype == DataType::Int64 && cur == DataType::Float64) dtype = DataType::Float64;
+        saw_int |= cur == DataType::Int64;
+    }
+    Series s;
+    s.name_ = name; s.dtype_ = dtype; s.len_ = data.size();
+    const size_t n = data.size();
+    bool any_null = false;
+    for (const auto& v : data) any_null |= v.is_null();
+    if (dtype == DataType::Null) return s;
+    if (any_null) {
+        s.validity_.assign((n + 7) / 8, 0);
+        for (size_t i = 0; i < n; ++i) if (!data[i].is_null()) set_bit(s.validity_, i);
+    }
+    switch (dtype) {
+        case DataType::Int64:
+            s.i64_.resize(n);
+            for (size_t i = 0; i < n; ++i) s.i64_[i] = data[i].tag == AnyValue::kInt64 ? data[i].i : 0;
+            break;
+        case DataType::Float64: {
+            s.f64_.resize(n);
+            const bool mixed = saw_int;
+            if (mixed) { s.int_tag_.assign(n, 0); s.int_vals_.assign(n, 0); }
+            for (size_t i = 0; i < n; ++i) {
+                if (data[i].tag == AnyValue::kFloat64) s.f64_[i] = data[i].f;
+                else { s.f64_[i] = 0.0; if (data[i].tag == AnyValue::kInt64) { s.int_tag_[i] = 1; s.int_vals_[i] = data[i].i; } }
+            }
+            break;
+        }
+        case DataType::Boolean:
+            s.bits_.assign((n + 7) / 8, 0);
+            for (size_t i = 0; i < n; ++i) if (data[i].tag == AnyValue::kBoolean && data[i].b) set_bit(s.bits_, i);
+            break;
+        case DataType::String: {
+            s.offsets_.resize(n + 1);
+            s.offsets_[0] = 0;
+            size_t total = 0;
+            for (size_t i = 0; i < n; ++i) { if (data[i].tag == AnyValue::kString) total += data[i].s.size(); }
+            if (total > (size_t)INT32_MAX) throw Error("String data exceeds int32 offsets");
+            s.data_.reserve(total);
+            for (size_t i = 0; i < n; ++i) {
+                if (data[i].tag == AnyValue::kString) s.data_.insert(s.data_.end(), data[i].s.begin(), data[i].s.end());
+                s.offsets_[i + 1] = (int32_t)s.data_.size();
+            }
+            break;
+        }
+        default: break;
+    }
+    return s;
+}
+
+Series Series::empty(const std::string& name, DataType dtype) {  // series.rs:223-229
+    Series s; s.name_ = name; s.dtype_ = dtype; s.len_ = 0;
+    if (dtype == DataType::String) s.offsets_.assign(1, 0);
+    return s;
+}
+
+void Series::infer_from_validity() {
+    if (len_ == 0) throw Error("Empty series not allowed");
+    if (!validity_.empty()) {
+        const size_t valid = count_valid(validity_, len_);
+        if (valid == len_) validity_.clear();
+        else if (valid == 0) {  // every value null -> DataType::Null (series.rs:190-198)
+            dtype_ = DataType::Null;
+            i64_.clear(); f64_.clear(); bits_.clear(); offsets_.clear(); data_.clear(); validity_.clear();
+        }
+    }
+}
+static void zero_under_nulls_check(const std::vector<uint8_t>& validity, size_t n) {
+    if (!validity.empty() && validity.size() < (n + 7) / 8) throw Error("validity bitmap shorter than the column");
+}
+Series Series::from_i64(const std::string& name, std::vector<int64_t> v, std::vector<uint8_t> validity_bits) {
+    Series s; s.name_ = name; s.dtype_ = DataType::Int64; s.len_ = v.size();
+    zero_under_nulls_check(validity_bits, s.len_);
+    s.i64_ = std::move(v); s.validity_ = std::move(validity_bits);
+    if (!s.validity_.empty()) for (size_t i = 0; i < s.len_; ++i) if (!get_bit(s.validity_, i)) s.i64_[i] = 0;
+    s.infer_from_validity();
+    return s;
+}
+Series Series::from_f64(const std::string& name, std::vector<double> v, std::vector<uint8_t> validity_bits) {
+    Series s; s.name_ = name; s.dtype_ = DataType::Float64; s.len_ = v.size();
+    zero_under_nulls_check(validity_bits, s.len_);
+    s.f64_ = std::move(v); s.validity_ = std::move(validity_bits);
+    if (!s.validity_.empty()) for (size_t i = 0; i < s.len_; ++i) if (!get_bit(s.validity_, i)) s.f64_[i] = 0.0;
+    s.infer_from_validity();
+    return s;
+}
+Series Series::from_bool_bits(const std::string& name, std::vector<uint8_t> value_bits, size_t n, std::vector<uint8_t> validity_bits) {
+    Series s; s.name_ = name; s.dtype_ = DataType::Boolean; s.len_ = n;
+    zero_under_nulls_check(validity_bits, n);
+    if (value_bits.size() < (n + 7) / 8) throw Error("value bitmap shorter than the column");
+    s.bits_ = std::move(value_bits); s.validity_ = std::move(validity_bits);
+    s.bits_.resize((n + 7) / 8);
+    if (n & 7) s.bits_.back() &= (uint8_t)((1u << (n & 7)) - 1u);
+    if (!s.validity_.empty()) for (size_t i = 0; i < (n + 7) / 8; ++i) s.bits_[i] &= s.validity_[i];
+    s.infer_from_validity();
+    return s;
+}
+Series Series::from_strings(const std::string& name, std::vector<int32_t> offsets, std::vector<uint8_t> data, std::vector<uint8_t> validity_bits) {
+    if (offsets.empty()) throw Error("Empty series not allowed");
+    Series s; s.name_ = name; s.dtype_ = DataType::String; s.len_ = offsets.size() - 1;
+    zero_under_nulls_check(validity_bits, s.len_);
+    s.offsets_ = std::move(offsets); s.data_ = std::move(data); s.validity_ = std::move(validity_bits);
+    s.infer_from_validity();
+    return s;
+}
+
+AnyValue Series::at(size_t i) const {  // series.rs:273-288
+    if (i >= len_) throw Error("Index " + std::to_string(i) + " out of bounds for series of length " + std::to_string(len_), true);
+    if (!is_valid(i)) return AnyValue::Null();
+    switch (dtype_) {
+        case DataType::Int64: return AnyValue::Int64(i64_[i]);
+        case DataType::Float64:
+            if (!int_tag_.empty() && int_tag_[i]) return AnyValue::Int64(int_vals_[i]);
+            return AnyValue::Float64(f64_[i]);
+        case DataType::Boolean: return AnyValue::Boolean(get_bit(bits_, i));
+        case DataType::String: return AnyValue::String(std::string(data_.begin() + offsets_[i], data_.begin() + offsets_[i + 1]));
+        case DataType::Null: return AnyValue::Null();
+    }
+    return AnyValue::Null();
+}
+std::optional<AnyValue> Series::get(size_t i) const { return i < len_ ? std::optional<AnyValue>(at(i)) : std::nullopt; }
+std::vector<AnyValue> Series::to_values() const {
+    std::vector<AnyValue> v; v.reserve(len_);
+    for (size_t i = 0; i < len_; ++i) v.push_back(at(i));
+    return v;
+}
+std::string Series::display() const { return std::string("Series: numbers [") + dtype_name(dtype_) + "; " + std::to_string(len_) + "]"; }
+size_t Series::null_count() const {
+    if (dtype_ == DataType::Null) return len_;
+    if (validity_.empty()) return 0;
+    return len_ - count_valid(validity_, len_);
+}
+
+static int32_t rvl_dtype_of(DataType d) {
+    switch (d) {
+        case DataType::Int64: return RVL_INT64;
+        case DataType::Float64: return RVL_FLOAT64;
+        case DataType::String: return RVL_STRING;
+        case DataType::Boolean: return RVL_BOOLEAN;
+        case DataType::Null: return RVL_NULL;
+    }
+    return RVL_NULL;
+}
+static ExecType exec_type_of(DataType d) { return (ExecType)rvl_dtype_of(d); }
+static DataType series_type_of(int32_t rvl) {
+    switch (rvl) {
+        case RVL_INT64: return DataType::Int64;
+        case RVL_FLOAT64: return DataType::Float64;
+        case RVL_STRING: return DataType::String;
+        case RVL_BOOLEAN: return DataType::Boolean;
+        default: return DataType::Null;
+    }
+}
+
+rvl_column Series::as_column(size_t offset, size_t length, bool flatten_nulls) const {
+    rvl_column c{};
+    c.dtype = rvl_dtype_of(dtype_);
+    c.location = RVL_HOST;
+    c.length = (int64_t)length;
+    c.offset = (int64_t)offset;
+    const bool keep_validity = !validity_.empty() && !(flatten_nulls && dtype_ != DataType::String);
+    c.validity = keep_validity ? validity_.data() : nullptr;
+    switch (dtype_) {
+        case DataType::Int64: c.values = i64_.data(); break;
+        case DataType::Float64: c.values = f64_.data(); break;
+        case DataType::Boolean: c.values = bits_.data(); break;
+        case DataType::String: c.offsets = offsets_.data(); c.data = data_.data(); c.data_len = (int64_t)data_.size(); break;
+        case DataType::Null: break;
+    }
+    return c;
+}
+
+Series Series::from_column(const std::string& name, const rvl_column& c, DataType dtype_if_empty) {
+    // the caller downloaded into buffers it owns and passes them here through `c` (host pointers, offset 0)
+    const size_t n = (size_t)c.length;
+    if (n == 0) return Series::empty(name, dtype_if_empty);
+    Series s; s.name_ = name; s.len_ = n; s.dtype_ = series_type_of(c.dtype);
+    if (c.dtype == RVL_NULL || c.null_count == c.length) { s.dtype_ = DataType::Null; return s; }  // series.rs:190-198
+    if (c.validity != nullptr && c.null_count > 0) s.validity_.assign(c.validity, c.validity + (n + 7) / 8);
+    switch (c.dtype) {
+        case RVL_INT64: s.i64_.assign((const int64_t*)c.values, (const int64_t*)c.values + n); break;
+        case RVL_FLOAT64: s.f64_.assign((const double*)c.values, (const double*)c.values + n); break;
+        case RVL_BOOLEAN: s.bits_.assign((const uint8_t*)c.values, (const uint8_t*)c.values + (n + 7) / 8); break;
+        case RVL_STRING:
+            s.offsets_.assign(c.offsets, c.offsets + n + 1);
+            s.data_.assign(c.data, c.data + c.data_len);
+            break;
+        default: break;
+    }
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------- datatypes/dataframe.rs
+DataFrame DataFrame::make(std::vector<Series> columns) {  // dataframe.rs:29-56
+    DataFrame df;
+    if (columns.empty()) return df;
+    std::set<std::string> seen;
+    for (const auto& c : columns)
+        if (!seen.insert(c.name()).second) throw Error("Duplicate column name: '" + c.name() + "'");
+    const size_t expected = columns.front().len();
+    for (const auto& c : columns)
+        if (c.len() != expected)
+            throw Error("Column lengths mismatch: expected " + std::to_string(expected) + ", found " + std::to_string(c.len()) +
+                        " for column '" + c.name() + "'");
+    df.columns_ = std::move(columns);
+    return df;
+}
+const Series* DataFrame::column(const std::string& name) const {
+    for (const auto& s : columns_) if (s.name() == name) return &s;
+    return nullptr;
+}
+std::vector<std::string> DataFrame::column_names() const {
+    std::vector<std::string> n;
+    for (const auto& s : columns_) n.push_back(s.name());
+    return n;
+}
+DataFrame DataFrame::select(const std::vector<std::string>& names) const {  // dataframe.rs:96-110
+    std::vector<Series> cols;
+    for (const auto& n : names) {
+        const Series* s = column(n);
+        if (!s) throw Error("Column not found: '" + n + "'");
+        cols.push_back(*s);
+    }
+    return DataFrame::unchecked(std::move(cols));
+}
+const Series& DataFrame::operator[](const std::string& name) const {
+    const Series* s = column(name);
+    if (!s) throw Error("Column '" + name + "' not found", true);
+    return *s;
+}
+
+// ------------------------------------------------------------------------------------------------- expressions/expr.rs
+const char* op_name(BinaryOperator op) {
+    static const char* n[] = {"Plus", "Minus", "Multiply", "Divide", "Eq", "NotEq", "Lt", "Gt", "LtEq", "GtEq", "And", "Or"};
+    return n[(int)op];
+}
+std::string Expr::debug() const {
+    switch (kind) {
+        case Column: return "Column(" + quoted(name) + ")";
+        case Literal: return "Literal(" + value.debug() + ")";
+        case Alias: return "Alias(" + left->debug() + ", " + quoted(name) + ")";
+        case Binary: return "BinaryExpr { left: " + left->debug() + ", op: " + op_name(op) + ", right: " + right->debug() + " }";
+    }
+    return "";
+}
+
+// ------------------------------------------------------------------------------------------------- context
+Context::Context(int device) { check(rvl_ctx_create(device, &ctx_)); }
+Context::~Context() { if (ctx_) rvl_ctx_destroy(ctx_); }
+std::shared_ptr<Context> Context::shared(int device) {
+    static std::mutex mu;
+    static std::map<int, std::shared_ptr<Context>> all;
+    std::lock_guard<std::mutex> g(mu);
+    auto& c = all[device];
+    if (!c) c = std::make_shared<Context>(device);
+    return c;
+}
+int64_t launch_count(int device) {
+    int64_t n = 0;
+    check(rvl_ctx_launch_count(Context::shared(device)->handle(), &n));
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------- schema
+const char* exec_type_name(ExecType t) {
+    switch (t) {
+        case ExecType::Null: return "Null";
+        case ExecType::Boolean: return "Boolean";
+        case ExecType::Int64: return "Int64";
+        case ExecType::Float64: return "Float64";
+        case ExecType::String: return "String";
+    }
+    return "?";
+}
+std::optional<size_t> Schema::index_of(const std::string& n) const {
+    for (size_t i = 0; i < fields.size(); ++i) if (fields[i].name == n) return i;
+    return std::nullopt;
+}
+const Field* Schema::field_by_name(const std::string& n) const {
+    auto i = index_of(n);
+    return i ? &fields[*i] : nullptr;
+}
+
+AnyValue ArrayData::value(size_t i) const {
+    if (i >= (size_t)length) throw Error("Index " + std::to_string(i) + " out of bounds", true);
+    if (dtype == ExecType::Null) return AnyValue::Null();
+    if (has_validity && !get_bit(validity, i)) return AnyValue::Null();
+    switch (dtype) {
+        case ExecType::Int64: return AnyValue::Int64(i64[i]);
+        case ExecType::Float64: return AnyValue::Float64(f64[i]);
+        case ExecType::Boolean: return AnyValue::Boolean(get_bit(bits, i));
+        case ExecType::String: return AnyValue::String(std::string(data.begin() + offsets[i], data.begin() + offsets[i + 1]));
+        default: return AnyValue::Null();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------- RecordBatch
+RecordBatch::Handle::~Handle() { if (b) rvl_batch_release(b); }
+
+RecordBatch RecordBatch::adopt(const ContextRef& ctx, SchemaRef schema, rvl_batch* handle) {
+    RecordBatch rb; rb.ctx_ = ctx; rb.schema_ = std::move(schema);
+    rb.h_ = std::make_shared<Handle>(); rb.h_->b = handle;
+    return rb;
+}
+
+RecordBatch RecordBatch::try_new(const ContextRef& ctx, SchemaRef schema, const std::vector<rvl_column>& cols) {  // record_batch.rs:16-58
+    if (schema->fields.size() != cols.size())
+        throw Error("Schema has " + std::to_string(schema->fields.size()) + " fields but " + std::to_string(cols.size()) + " columns provided");
+    const int64_t n = cols.empty() ? 0 : cols[0].length;
+    for (size_t i = 0; i < cols.size(); ++i)
+        if (cols[i].length != n)
+            throw Error("Column " + std::to_string(i) + " has length " + std::to_string(cols[i].length) + " but expected " + std::to_string(n));
+    for (size_t i = 0; i < cols.size(); ++i)
+        if ((int32_t)schema->fields[i].data_type != cols[i].dtype)
+            throw Error("Column " + std::to_string(i) + " has type " + exec_type_name((ExecType)cols[i].dtype) + " but schema expects " +
+                        exec_type_name(schema->fields[i].data_type));
+    rvl_batch* b = nullptr;
+    check(rvl_batch_upload(ctx->handle(), cols.data(), (int32_t)cols.size(), &b));
+    return adopt(ctx, std::move(schema), b);
+}
+
+RecordBatch RecordBatch::empty(const ContextRef& ctx, SchemaRef schema) {  // record_batch.rs:402-421
+    std::vector<rvl_column> cols;
+    static const int32_t zero_off[1] = {0};
+    for (const auto& f : schema->fields) {
+        rvl_column c{};
+        c.dtype = (int32_t)f.data_type; c.location = RVL_HOST; c.length = 0;
+        if (f.data_type == ExecType::String) c.offsets = zero_off;
+        cols.push_back(c);
+    }
+    rvl_batch* b = nullptr;
+    check(rvl_batch_upload(ctx->handle(), cols.data(), (int32_t)cols.size(), &b));
+    return adopt(ctx, std::move(schema), b);
+}
+
+size_t RecordBatch::num_rows() const {
+    if (!handle()) return 0;
+    int64_t n = 0; check(rvl_batch_num_rows(handle(), &n));
+    return (size_t)n;
+}
+size_t RecordBatch::num_columns() const {
+    if (!handle()) return 0;
+    int32_t n = 0; check(rvl_batch_num_columns(handle(), &n));
+    return (size_t)n;
+}
+
+RecordBatch RecordBatch::slice(size_t offset, size_t length) const {  // record_batch.rs:92-106
+    if (!(offset + length <= num_rows())) throw Error("Slice out of bounds", true);
+    rvl_batch* v = nullptr;
+    check(rvl_batch_slice(handle(), (int64_t)offset, (int64_t)length, &v));
+    return adopt(ctx_, schema_, v);
+}
+
+RecordBatch RecordBatch::select_columns(const std::vector<size_t>& indices) const {  // record_batch.rs:180-206
+    const size_t nc = num_columns();
+    auto out_schema = std::make_shared<Schema>();
+    std::vector<int32_t> idx;
+    for (size_t i : indices) {
+        if (i >= nc) throw Error("Column index " + std::to_string(i) + " out of bounds for " + std::to_string(nc) + " columns");
+        out_schema->fields.push_back(schema_->fields[i]);
+        idx.push_back((int32_t)i);
+    }
+    rvl_batch* v = nullptr;
+    check(rvl_batch_select(handle(), idx.data(), (int32_t)idx.size(), &v));
+    return adopt(ctx_, out_schema, v);
+}
+
+RecordBatch RecordBatch::select_columns_by_name(const std::vector<std::string>& names) const {  // record_batch.rs:208-219
+    std::vector<size_t> idx;
+    for (const auto& n : names) {
+        auto i = schema_->index_of(n);
+        if (!i) throw Error("Column '" + n + "' not found");
+        idx.push_back(*i);
+    }
+    return select_columns(idx);
+}
+
+RecordBatch RecordBatch::filter(const RecordBatch& pb, size_t pc) const {  // record_batch.rs:221-243
+    const size_t plen = pb.num_rows(), n = num_rows();
+    if (plen != n) throw Error("Predicate length " + std::to_string(plen) + " doesn't match batch length " + std::to_string(n));
+    if (pc >= pb.num_columns() || pb.schema_->fields[pc].data_type != ExecType::Boolean) throw Error("Predicate must be a BooleanArray");
+    // one fused launch over [this batch's columns..., predicate column]: mask mode keeps rows whose mask is Some(true)
+    const size_t nc = num_columns();
+    std::vector<rvl_batch*> owned;
+    const rvl_batch* input = handle();
+    int32_t mask_index;
+    if (pb.handle() == handle()) {
+        mask_index = (int32_t)pc;
+    } else {
+        // the predicate lives in another batch: build a zero-copy view [columns of this batch + the predicate column]
+        // by concatenating column views is not expressible in the ABI, so upload-free path = select on each and re-wrap
+        std::vector<rvl_column> views(nc + 1);
+        for (size_t i = 0; i < nc; ++i) check(rvl_batch_column(handle(), (int32_t)i, &views[i]));
+        check(rvl_batch_column(pb.handle(), (int32_t)pc, &views[nc]));
+        rvl_batch* joined = nullptr;
+        check(rvl_batch_wrap_device(ctx_->handle(), views.data(), (int32_t)views.size(), &joined));
+        owned.push_back(joined);
+        input = joined;
+        mask_index = (int32_t)nc;
+    }
+    rvl_predicate pred{};
+    pred.mode = RVL_PRED_BOOL_COLUMN; pred.column = mask_index;
+    std::vector<int32_t> proj(nc);
+    for (size_t i = 0; i < nc; ++i) proj[i] = (int32_t)i;
+    rvl_batch* out = nullptr;
+    const int32_t rc = rvl_filter_project(ctx_->handle(), input, &pred, proj.data(), (int32_t)nc, -1, &out);
+    for (auto* b : owned) rvl_batch_release(b);
+    check(rc);
+    return adopt(ctx_, schema_, out);
+}
+
+RecordBatch RecordBatch::concat(const std::vector<RecordBatch>& batches) {  // record_batch.rs:245-275
+    if (batches.empty()) throw Error("Cannot concatenate empty batch list");
+    for (size_t i = 1; i < batches.size(); ++i)
+        if (!(*batches[i].schema_ == *batches[0].schema_)) throw Error("All batches must have the same schema");
+    std::vector<const rvl_batch*> hs;
+    for (const auto& b : batches) hs.push_back(b.handle());
+    rvl_batch* out = nullptr;
+    check(rvl_batch_concat(batches[0].ctx_->handle(), hs.data(), (int32_t)hs.size(), &out));
+    return adopt(batches[0].ctx_, batches[0].schema_, out);
+}
+
+int64_t RecordBatch::column_null_count(size_t i) const {
+    rvl_column v{};
+    check(rvl_batch_column(handle(), (int32_t)i, &v));
+    return v.null_count;
+}
+
+ArrayData RecordBatch::column_data(size_t i) const {
+    rvl_column v{};
+    check(rvl_batch_column(handle(), (int32_t)i, &v));
+    ArrayData a;
+    a.dtype = (ExecType)v.dtype; a.length = v.length; a.null_count = v.null_count;
+    const size_t n = (size_t)v.length;
+    rvl_column dst{};
+    dst.dtype = v.dtype; dst.location = RVL_HOST; dst.length = v.length;
+    a.has_validity = v.validity != nullptr && v.dtype != RVL_NULL;
+    if (a.has_validity) { a.validity.assign((n + 7) / 8 + 1, 0); dst.validity = a.validity.data(); }
+    switch (v.dtype) {
+        case RVL_INT64: a.i64.assign(n + 1, 0); dst.values = a.i64.data(); break;
+        case RVL_FLOAT64: a.f64.assign(n + 1, 0.0); dst.values = a.f64.data(); break;
+        case RVL_BOOLEAN: a.bits.assign((n + 7) / 8 + 1, 0); dst.values = a.bits.data(); break;
+        case RVL_STRING: {
+            a.offsets.assign(n + 1, 0); dst.offsets = a.offsets.data();
+            // the view's data_len is the span of the viewed window
+            a.data.assign((size_t)std::max<int64_t>(v.data_len, 0) + 1, 0); dst.data = a.data.data(); dst.data_len = v.data_len;
+            break;
+        }
+        default: break;
+    }
+    check(rvl_batch_download_column(ctx_->handle(), handle(), (int32_t)i, &dst));
+    switch (v.dtype) {
+        case RVL_INT64: a.i64.resize(n); break;
+        case RVL_FLOAT64: a.f64.resize(n); break;
+        case RVL_BOOLEAN: a.bits.resize((n + 7) / 8); break;
+        case RVL_STRING: a.data.resize(n ? (size_t)a.offsets[n] : 0); break;
+        default: break;
+    }
+    if (a.has_validity) a.validity.resize((n + 7) / 8);
+    return a;
+}
+
+// ------------------------------------------------------------------------------------------------- streams
+std::vector<RecordBatch> DataStream::collect() {
+    std::vector<RecordBatch> out;
+    while (auto b = next_batch()) out.push_back(*b);
+    return out;
+}
+
+namespace {
+struct MemoryStream : DataStream {  // stream.rs:58-114
+    SchemaRef schema_; std::vector<RecordBatch> batches; size_t cur = 0;
+    SchemaRef schema() const override { return schema_; }
+    std::optional<RecordBatch> next_batch() override {
+        if (cur < batches.size()) return batches[cur++];
+        return std::nullopt;
+    }
+};
+struct FilterStream : DataStream {  // stream.rs:116-163
+    DataStreamRef input; std::string col;
+    SchemaRef schema() const override { return input->schema(); }
+    std::optional<RecordBatch> next_batch() override {
+        auto b = input->next_batch();
+        if (!b) return std::nullopt;
+        auto idx = b->schema()->index_of(col);
+        if (!idx) throw Error("Stream execution error: Column '" + col + "' not found in schema");
+        if (b->schema()->fields[*idx].data_type != ExecType::Boolean)
+            throw Error("Stream execution error: Predicate column '" + col + "' is not of boolean type");
+        try { return b->filter(*b, *idx); }
+        catch (const Error& e) { if (e.panic) throw; throw Error(std::string("Stream execution error: ") + e.what()); }
+    }
+};
+struct SelectStream : DataStream {  // stream.rs:165-213
+    DataStreamRef input; std::vector<std::string> names; SchemaRef out_schema;
+    SchemaRef schema() const override { return out_schema; }
+    std::optional<RecordBatch> next_batch() override {
+        auto b = input->next_batch();
+        if (!b) return std::nullopt;
+        try { return b->select_columns_by_name(names); }
+        catch (const Error& e) { if (e.panic) throw; throw Error(std::string("Stream execution error: ") + e.what()); }
+    }
+};
+struct LimitStream : DataStream {  // streaming.rs:246-288
+    DataStreamRef input; size_t limit = 0, rows_returned = 0;
+    SchemaRef schema() const override { return input->schema(); }
+    std::optional<RecordBatch> next_batch() override {
+        if (rows_returned >= limit) return std::nullopt;  // :269-271: no upstream pull once the limit is reached
+        auto b = input->next_batch();
+        if (!b) return std::nullopt;
+        const size_t remaining = limit - rows_returned, rows = b->num_rows();
+        if (rows <= remaining) { rows_returned += rows; return b; }
+        auto lb = b->slice(0, remaining);
+        rows_returned += remaining;
+        return lb;
+    }
+};
+}  // namespace
+
+DataStreamRef make_memory_stream(const ContextRef&, SchemaRef schema, std::vector<RecordBatch> batches) {  // stream.rs:66-81
+    for (const auto& b : batches)
+        if (!(*b.schema() == *schema)) throw Error("Schema mismatch: expected <schema>, found <schema>");
+    auto s = std::make_unique<MemoryStream>(); s->schema_ = std::move(schema); s->batches = std::move(batches);
+    return s;
+}
+DataStreamRef make_filter_stream(DataStreamRef in, std::string predicate_column) {
+    auto s = std::make_unique<FilterStream>(); s->input = std::move(in); s->col = std::move(predicate_column); return s;
+}
+DataStreamRef make_select_stream(DataStreamRef in, std::vector<std::string> columns) {  // stream.rs:173-194
+    auto in_schema = in->schema();
+    auto out = std::make_shared<Schema>();
+    for (const auto& c : columns) {
+        auto i = in_schema->index_of(c);
+        if (!i) throw Error("Stream execution error: Column '" + c + "' not found in schema");
+        out->fields.push_back(in_schema->fields[*i]);
+    }
+    auto s = std::make_unique<SelectStream>(); s->input = std::move(in); s->names = std::move(columns); s->out_schema = out;
+    return s;
+}
+DataStreamRef make_limit_stream(DataStreamRef in, size_t limit) {
+    auto s = std::make_unique<LimitStream>(); s->input = std::move(in); s->limit = limit; return s;
+}
+
+std::vector<RecordBatch> collect_all_batches(DataStream& s) {  // streaming.rs:335-341
+    std::vector<RecordBatch> out;
+    while (auto b = s.next_batch()) out.push_back(*b);
+    return out;
+}
+RecordBatch collect_stream_batches(const ContextRef& ctx, DataStream& s) {  // streaming.rs:343-352
+    auto schema = s.schema();
+    auto batches = collect_all_batches(s);
+    if (batches.empty()) return RecordBatch::empty(ctx, schema);
+    try { return RecordBatch::concat(batches); }
+    catch (const Error& e) { if (e.panic) throw; throw Error(std::string("Conversion error: ") + e.what()); }
+}
+
+std::vector<RecordBatch> dataframe_to_batches(const ContextRef& ctx, const DataFrame& df, size_t batch_size) {  // streaming.rs:135-233
+    std::vector<RecordBatch> batches;
+    if (df.is_empty()) return batches;
+    const size_t num_rows = df.height();
+    const size_t num_batches = (num_rows + batch_size - 1) / batch_size;
+    auto schema = std::make_shared<Schema>();
+    for (const auto& s : df.columns()) schema->fields.push_back(Field{s.name(), exec_type_of(s.dtype()), true});  // :148-161
+    for (size_t bi = 0; bi < num_batches; ++bi) {
+        const size_t start = bi * batch_size, end = std::min((bi + 1) * batch_size, num_rows);
+        std::vector<rvl_column> cols;
+        for (const auto& s : df.columns()) {
+            // a Float64 series holding AnyValue::Int64 panics in the reference (streaming.rs:189)
+            if (s.is_mixed())
+                for (size_t i = start; i < end; ++i)
+                    if (s.at(i).tag == AnyValue::kInt64) throw Error("Type mismatch in Float64 series", true);
+            cols.push_back(s.as_column(start, end - start, /*flatten_nulls=*/true));
+        }
+        try { batches.push_back(RecordBatch::try_new(ctx, schema, cols)); }
+        catch (const Error& e) { if (e.panic) throw; throw Error(std::string("Conversion error: ") + e.what()); }
+    }
+    return batches;
+}
+
+// ------------------------------------------------------------------------------------------------- StreamingPhysicalPlan
+StreamingPhysicalPlan StreamingPhysicalPlan::memory_source(std::vector<RecordBatch> b) {
+    StreamingPhysicalPlan p; p.kind = MemorySource;
+    if (!b.empty()) p.ctx = b[0].context();
+    p.batches = std::move(b);
+    return p;
+}
+StreamingPhysicalPlan StreamingPhysicalPlan::dataframe_source(DataFrame df, size_t batch_size, ContextRef ctx) {
+    StreamingPhysicalPlan p; p.kind = DataFrameSource; p.df = std::move(df); p.batch_size = batch_size;
+    p.ctx = std::move(ctx);  // resolved lazily (Context::shared(0)) when the plan executes
+    return p;
+}
+StreamingPhysicalPlan StreamingPhysicalPlan::filter(std::string col) const {
+    StreamingPhysicalPlan p; p.kind = Filter; p.input = std::make_shared<StreamingPhysicalPlan>(*this); p.predicate_column = std::move(col); p.ctx = ctx; return p;
+}
+StreamingPhysicalPlan StreamingPhysicalPlan::select(std::vector<std::string> cols) const {
+    StreamingPhysicalPlan p; p.kind = Select; p.input = std::make_shared<StreamingPhysicalPlan>(*this); p.columns = std::move(cols); p.ctx = ctx; return p;
+}
+StreamingPhysicalPlan StreamingPhysicalPlan::limit(size_t n_) const {
+    StreamingPhysicalPlan p; p.kind = Limit; p.input = std::make_shared<StreamingPhysicalPlan>(*this); p.n = n_; p.ctx = ctx; return p;
+}
+
+static DataStreamRef build_stream(const StreamingPhysicalPlan& p, size_t min_batch_rows) {  // streaming.rs:70-133
+    using K = StreamingPhysicalPlan;
+    switch (p.kind) {
+        case K::MemorySource: {
+            if (p.batches.empty()) throw Error("Invalid operation: Cannot create stream from empty batch list");
+            try { return make_memory_stream(p.ctx, p.batches[0].schema(), p.batches); }
+            catch (const Error& e) { if (e.panic) throw; throw Error(std::string("Stream error: ") + e.what()); }
+        }
+        case K::DataFrameSource: {
+            const ContextRef ctx = p.ctx ? p.ctx : Context::shared(0);
+            auto b = dataframe_to_batches(ctx, p.df, std::max(p.batch_size, min_batch_rows));
+            SchemaRef s = b.empty() ? std::make_shared<Schema>() : b[0].schema();
+            return make_memory_stream(ctx, s, std::move(b));
+        }
+        case K::Filter: return make_filter_stream(build_stream(*p.input, min_batch_rows), p.predicate_column);
+        case K::Select: {
+            auto in = build_stream(*p.input, min_batch_rows);
+            try { return make_select_stream(std::move(in), p.columns); }
+            catch (const Error& e) { if (e.panic) throw; throw Error(std::string("Stream error: ") + e.what()); }
+        }
+        case K::Limit: return make_limit_stream(build_stream(*p.input, min_batch_rows), p.n);
+    }
+    return nullptr;
+}
+DataStreamRef StreamingPhysicalPlan::execute() const { return build_stream(*this, 0); }
+
+static std::string wrap_stream_err(const std::string& w) {
+    // a StreamError raised inside next_batch becomes StreamingExecutionError::Stream via `?` (streaming.rs:12-13)
+    if (w.rfind("Stream execution error:", 0) == 0) return "Stream error: " + w;
+    return w;
+}
+RecordBatch StreamingPhysicalPlan::collect() const {  // streaming.rs:235-238
+    if (batch_size == 0 && kind == DataFrameSource) throw Error("attempt to divide by zero", true);
+    auto s = build_stream(*this, kCollectBatchRows);
+    try { return collect_stream_batches(ctx ? ctx : Context::shared(0), *s); }
+    catch (const Error& e) { if (e.panic) throw; throw Error(wrap_stream_err(e.what())); }
+}
+std::vector<RecordBatch> StreamingPhysicalPlan::collect_batches() const {  // streaming.rs:240-243
+    auto s = execute();
+    try { return collect_all_batches(*s); }
+    catch (const Error& e) { if (e.panic) throw; throw Error(wrap_stream_err(e.what())); }
+}
+
+// ------------------------------------------------------------------------------------------------- logical_plan/plan.rs
+using SchemaVec = std::vector<std::pair<std::string, DataType>>;
+
+static std::pair<std::string, DataType> resolve_expr_schema(const Expr& e, const SchemaVec& in) {  // logical_plan/plan.rs:204-262
+    switch (e.kind) {
+        case Expr::Column:
+            for (const auto& p : in) if (p.first == e.name) return {e.name, p.second};
+            return {e.name, DataType::Null};
+        case Expr::Alias: return {e.name, resolve_expr_schema(*e.left, in).second};
+        case Expr::Binary: {
+            const auto l = resolve_expr_schema(*e.left, in), r = resolve_expr_schema(*e.right, in);
+            DataType res = DataType::Null;
+            switch (e.op) {
+                case BinaryOperator::Eq: case BinaryOperator::NotEq: case BinaryOperator::Lt: case BinaryOperator::Gt:
+                case BinaryOperator::LtEq: case BinaryOperator::GtEq: case BinaryOperator::And: case BinaryOperator::Or:
+                    res = DataType::Boolean; break;
+                default:
+                    if (l.second == DataType::Float64 || r.second == DataType::Float64) res = DataType::Float64;
+                    else if (l.second == DataType::Int64 && r.second == DataType::Int64) res = DataType::Int64;
+                    else if (l.second == DataType::Null) res = r.second;
+                    else if (r.second == DataType::Null) res = l.second;
+            }
+            return {l.first, res};
+        }
+        case Expr::Literal: return {"literal", e.value.data_type()};
+    }
+    return {"", DataType::Null};
+}
+
+SchemaVec LogicalPlan::schema() const {  // logical_plan/plan.rs:63-113
+    switch (kind) {
+        case DataFrameSource: return src_schema;
+        case Select: {
+            const auto in = input->schema();
+            SchemaVec out;
+            for (const auto& e : expressions) out.push_back(resolve_expr_schema(e, in));
+            return out;
+        }
+        case Filter: case Limit: return input->schema();
+    }
+    return {};
+}
+
+static void validate_expr_columns(const Expr& e, const SchemaVec& schema) {  // logical_plan/plan.rs:264-286
+    switch (e.kind) {
+        case Expr::Column: {
+            bool found = false;
+            for (const auto& p : schema) found |= p.first == e.name;
+            if (!found) throw Error("Logical plan error: Column not found: '" + e.name + "'");
+            break;
+        }
+        case Expr::Binary: validate_expr_columns(*e.left, schema); validate_expr_columns(*e.right, schema); break;
+        case Expr::Alias: validate_expr_columns(*e.left, schema); break;
+        case Expr::Literal: break;
+    }
+}
+
+void LogicalPlan::validate() const {  // logical_plan/plan.rs:115-202
+    switch (kind) {
+        case DataFrameSource:
+            for (const auto& p : src_schema)
+                if (!df.column(p.first)) throw Error("Logical plan error: Column not found: '" + p.first + "'");
+            break;
+        case Select: {
+            input->validate();
+            const auto in = input->schema();
+            for (const auto& e : expressions) validate_expr_columns(e, in);
+            break;
+        }
+        case Filter: input->validate(); validate_expr_columns(predicate, input->schema()); break;
+        case Limit: input->validate(); break;
+    }
+}
+
+std::string LogicalPlan::shape() const {
+    switch (kind) {
+        case DataFrameSource: return "Source";
+        case Select: return "Select(" + input->shape() + ")";
+        case Filter: return "Filter(" + input->shape() + ")";
+        case Limit: return "Limit(" + input->shape() + ")";
+    }
+    return "";
+}
+
+// ------------------------------------------------------------------------------------------------- logical_plan/optimizer.rs
+static void extract_column_names(const Expr& e, std::vector<std::string>& out) {  // optimizer.rs:76-87
+    switch (e.kind) {
+        case Expr::Column: out.push_back(e.name); break;
+        case Expr::Binary: extract_column_names(*e.left, out); extract_column_names(*e.right, out); break;
+        case Expr::Alias: extract_column_names(*e.left, out); break;
+        case Expr::Literal: break;
+    }
+}
+static bool predicate_uses_only_selected_columns(const Expr& pred, const std::vector<Expr>& exprs) {  // optimizer.rs:66-74,89-100
+    std::vector<std::string> pc, sc;
+    extract_column_names(pred, pc);
+    for (const auto& e : exprs) {
+        if (e.kind == Expr::Column) sc.push_back(e.name);
+        else if (e.kind == Expr::Alias && e.left->kind == Expr::Column) sc.push_back(e.left->name);
+    }
+    for (const auto& c : pc) if (std::find(sc.begin(), sc.end(), c) == sc.end()) return false;
+    return true;
+}
+LogicalPlan optimize(LogicalPlan plan) {  // optimizer.rs:15-64 (push_predicates_down)
+    switch (plan.kind) {
+        case LogicalPlan::Select: {
+            LogicalPlan& in = *plan.input;
+            if (in.kind == LogicalPlan::Filter) {  // Select(Filter(x)) -> Filter(Select(x)) when the predicate only reads selected columns
+                if (predicate_uses_only_selected_columns(in.predicate, plan.expressions)) {
+                    LogicalPlan sel; sel.kind = LogicalPlan::Select; sel.input = in.input; sel.expressions = plan.expressions;
+                    LogicalPlan fil; fil.kind = LogicalPlan::Filter; fil.predicate = in.predicate;
+                    fil.input = std::make_shared<LogicalPlan>(std::move(sel));
+                    return fil;
+                }
+                return plan;
+            }
+            LogicalPlan out = plan;
+            out.input = std::make_shared<LogicalPlan>(optimize(in));
+            return out;
+        }
+        case LogicalPlan::Filter: {
+            LogicalPlan out = plan;
+            out.input = std::make_shared<LogicalPlan>(optimize(*plan.input));
+            return out;
+        }
+        default: return plan;  // Limit and sources are left untouched (optimizer.rs:62)
+    }
+}
+
+// ------------------------------------------------------------------------------------------------- planner.rs + plan.rs (eager engine, on the GPU)
+static std::pair<std::string, std::string> convert_select_expr(const Expr& e) {  // planner.rs:113-132
+    switch (e.kind) {
+        case Expr::Column: return {e.name, e.name};
+        case Expr::Alias:
+            if (e.left->kind == Expr::Column) return {e.left->name, e.name};
+            throw Error("Unsupported expression: " + quoted(e.debug()));
+        case Expr::Binary: throw Error("Unsupported expression: " + quoted(e.debug()));
+        case Expr::Literal: throw Error("Select expression must be a column or alias, found: " + quoted(e.debug()));
+    }
+    return {};
+}
+struct FilterSpec { std::string column; AnyValue value; BinaryOperator op; };
+static FilterSpec convert_filter_predicate(const Expr& p) {  // planner.rs:134-189
+    if (p.kind != Expr::Binary) {
+        const char* t = p.kind == Expr::Column ? "Column" : (p.kind == Expr::Literal ? "Literal" : "Alias");
+        throw Error(std::string("Filter must be a binary comparison, found: ") + t);
+    }
+    switch (p.op) {
+        case BinaryOperator::Eq: case BinaryOperator::NotEq: case BinaryOperator::Lt:
+        case BinaryOperator::Gt: case BinaryOperator::LtEq: case BinaryOperator::GtEq: break;
+        case BinaryOperator::And: case BinaryOperator::Or:
+            throw Error("Unsupported filter: only simple column comparisons supported, found: " + quoted(p.debug()));
+        default: throw Error(std::string("Unsupported binary operator in filter: ") + op_name(p.op));
+    }
+    if (p.left->kind != Expr::Column) throw Error("Filter left side must be a column reference, found: " + quoted(p.left->debug()));
+    if (p.right->kind != Expr::Literal) throw Error("Filter right side must be a literal value, found: " + quoted(p.right->debug()));
+    return {p.left->name, p.right->value, p.op};
+}
+static void check_lowering(const LogicalPlan& p) {  // logical_to_physical runs over the whole tree before execution
+    switch (p.kind) {
+        case LogicalPlan::DataFrameSource: return;
+        case LogicalPlan::Select: check_lowering(*p.input); for (const auto& e : p.expressions) convert_select_expr(e); return;
+        case LogicalPlan::Filter: check_lowering(*p.input); convert_filter_predicate(p.predicate); return;
+        case LogicalPlan::Limit: check_lowering(*p.input); return;
+    }
+}
+
+namespace {
+// A DataFrame living on the device: the eager engine's intermediate result.
+struct Frame {
+    RecordBatch rb;                    // default-constructed when the frame has no columns
+    std::vector<std::string> names;
+    std::vector<DataType> dtypes;      // eager dtype of each column (may be Null while the device array is typed)
+    size_t rows = 0;
+};
+
+Frame upload_frame(const ContextRef& ctx, const DataFrame& df) {
+    Frame f;
+    f.rows = df.height();
+    if (df.is_empty()) return f;
+    auto schema = std::make_shared<Schema>();
+    std::vector<rvl_column> cols;
+    for (const auto& s : df.columns()) {
+        if (s.is_mixed())
+            throw Error("General execution error: column '" + s.name() + "' holds Int64 values inside a Float64 series; "
+                        "mixed series are not supported by the GPU engine");
+        schema->fields.push_back(Field{s.name(), exec_type_of(s.dtype()), true});
+        cols.push_back(s.as_column(0, s.len(), /*flatten_nulls=*/false));
+        f.names.push_back(s.name());
+        f.dtypes.push_back(s.dtype());
+    }
+    f.rb = RecordBatch::try_new(ctx, schema, cols);
+    return f;
+}
+
+DataFrame download_frame(const Frame& f) {
+    std::vector<Series> out;
+    for (size_t i = 0; i < f.names.size(); ++i) {
+        ArrayData a = f.rb.column_data(i);
+        rvl_column c{};
+        c.dtype = (int32_t)a.dtype; c.location = RVL_HOST; c.length = a.length; c.null_count = a.null_count;
+        c.validity = a.has_validity ? a.validity.data() : nullptr;
+        switch (a.dtype) {
+            case ExecType::Int64: c.values = a.i64.data(); break;
+            case ExecType::Float64: c.values = a.f64.data(); break;
+            case ExecType::Boolean: c.values = a.bits.data(); break;
+            case ExecType::String: c.offsets = a.offsets.data(); c.data = a.data.data(); c.data_len = (int64_t)a.data.size(); break;
+            default: break;
+        }
+        if (f.dtypes[i] == DataType::Null && a.length > 0) { c.dtype = RVL_NULL; c.null_count = a.length; }
+        out.push_back(Series::from_column(f.names[i], c, f.dtypes[i]));
+    }
+    return DataFrame::unchecked(std::move(out));
+}
+
+// dtype the reference's Series::new would infer for column i of `rb` holding `rows` (> 0) rows
+DataType inferred_dtype(const RecordBatch& rb, size_t i, DataType current, size_t rows) {
+    if (current == DataType::Null) return DataType::Null;
+    return (size_t)rb.column_null_count(i) == rows ? DataType::Null : current;
+}
+
+rvl_predicate to_predicate(int32_t column, BinaryOperator op, const AnyValue& lit) {
+    rvl_predicate p{};
+    p.mode = RVL_PRED_CMP_LITERAL; p.column = column; p.op = (int32_t)op;
+    p.lit_dtype = rvl_dtype_of(lit.data_type());
+    p.lit_i64 = lit.i; p.lit_f64 = lit.f; p.lit_bool = lit.b ? 1 : 0;
+    p.lit_str = (const uint8_t*)lit.s.data(); p.lit_str_len = (int64_t)lit.s.size();
+    return p;
+}
+
+// Filter arm (plan.rs:97-150), optionally fused with the Select (:68-96) and Limit (:151-173) arms right above it.
+Frame exec_filter(const ContextRef& ctx, const Frame& in, const FilterSpec& f, const std::vector<std::pair<std::string, std::string>>* select,
+                  std::optional<size_t> limit) {
+    int32_t pc = -1;
+    for (size_t i = 0; i < in.names.size(); ++i) if (in.names[i] == f.column) { pc = (int32_t)i; break; }
+    if (pc < 0) throw Error("Column not found: '" + f.column + "'");  // plan.rs:104-110
+    // projected columns: every input column (plain Filter) or the Select list, by source name
+    std::vector<int32_t> proj;
+    std::vector<std::string> out_names;
+    if (select) {
+        for (const auto& pr : *select) {
+            int32_t idx = -1;
+            for (size_t i = 0; i < in.names.size(); ++i) if (in.names[i] == pr.first) { idx = (int32_t)i; break; }
+            if (idx < 0) throw Error("Column not found: '" + pr.first + "'");  // plan.rs:72-78
+            proj.push_back(idx); out_names.push_back(pr.second);
+        }
+    } else {
+        for (size_t i = 0; i < in.names.size(); ++i) { proj.push_back((int32_t)i); out_names.push_back(in.names[i]); }
+    }
+    // the predicate column of a Null-dtype series is all nulls: compare as such (its device array may still be typed)
+    rvl_predicate pred = to_predicate(pc, f.op, f.value);
+    rvl_batch* out = nullptr;
+    check(rvl_filter_project(ctx->handle(), in.rb.handle(), &pred, proj.data(), (int32_t)proj.size(), limit ? (int64_t)*limit : -1, &out));
+    Frame r;
+    auto schema = std::make_shared<Schema>();
+    for (size_t j = 0; j < proj.size(); ++j) schema->fields.push_back(Field{out_names[j], in.rb.schema()->fields[(size_t)proj[j]].data_type, true});
+    r.rb = RecordBatch::adopt(ctx, schema, out);
+    r.rows = r.rb.num_rows();
+    r.names = out_names;
+    if (r.rows == 0 && (select || limit)) throw Error("Series error: Empty series not allowed");  // Series::new on no data: plan.rs:89-91, :167-169
+    for (size_t j = 0; j < proj.size(); ++j) {
+        const DataType cur = in.dtypes[(size_t)proj[j]];
+        r.dtypes.push_back(r.rows == 0 ? cur : inferred_dtype(r.rb, j, cur, r.rows));  // Series::empty keeps the dtype (plan.rs:140-141)
+    }
+    if (select) {  // DataFrame::new over the renamed series (plan.rs:95): duplicate final names
+        std::set<std::string> seen;
+        for (const auto& n : r.names) if (!seen.insert(n).second) throw Error("DataFrame error: Duplicate column name: '" + n + "'");
+    }
+    return r;
+}
+
+Frame exec_node(const ContextRef& ctx, const LogicalPlan& p) {  // physical_plan/plan.rs:65-173
+    switch (p.kind) {
+        case LogicalPlan::DataFrameSource: return upload_frame(ctx, p.df);
+        case LogicalPlan::Filter: {
+            Frame in = exec_node(ctx, *p.input);
+            FilterSpec f = convert_filter_predicate(p.predicate);
+            if (in.names.empty()) throw Error("Column not found: '" + f.column + "'");
+            return exec_filter(ctx, in, f, nullptr, std::nullopt);
+        }
+        case LogicalPlan::Select: {
+            std::vector<std::pair<std::string, std::string>> sel;
+            for (const auto& e : p.expressions) sel.push_back(convert_select_expr(e));
+            if (p.input->kind == LogicalPlan::Filter && !sel.empty()) {  // Select(Filter(x)): one fused launch
+                Frame in = exec_node(ctx, *p.input->input);
+                FilterSpec f = convert_filter_predicate(p.input->predicate);
+                if (!in.names.empty()) return exec_filter(ctx, in, f, &sel, std::nullopt);
+                throw Error("Column not found: '" + f.column + "'");
+            }
+            Frame in = exec_node(ctx, *p.input);
+            std::vector<size_t> idx;
+            for (const auto& pr : sel) {
+                size_t k = in.names.size();
+                for (size_t i = 0; i < in.names.size(); ++i) if (in.names[i] == pr.first) { k = i; break; }
+                if (k == in.names.size()) throw Error("Column not found: '" + pr.first + "'");
+                idx.push_back(k);
+            }
+            Frame r;
+            if (sel.empty()) return r;  // DataFrame::new(vec![]) = empty frame
+            if (in.rows == 0) throw Error("Series error: Empty series not allowed");  // plan.rs:89-91
+            r.rows = in.rows;
+            r.rb = in.rb.select_columns(idx);
+            auto schema = std::make_shared<Schema>();
+            std::set<std::string> seen;
+            for (size_t j = 0; j < idx.size(); ++j) {
+                r.names.push_back(sel[j].second);
+                r.dtypes.push_back(inferred_dtype(r.rb, j, in.dtypes[idx[j]], r.rows));
+                schema->fields.push_back(Field{sel[j].second, in.rb.schema()->fields[idx[j]].data_type, true});
+            }
+            for (const auto& n : r.names) if (!seen.insert(n).second) throw Error("DataFrame error: Duplicate column name: '" + n + "'");
+            r.rb = r.rb.with_schema(schema);
+            return r;
+        }
+        case LogicalPlan::Limit: {
+            // Limit(Filter) / Limit(Select(Filter)) with n > 0: the limit goes into the fused launch (early termination)
+            if (p.n > 0) {
+                const LogicalPlan* c = p.input.get();
+                if (c->kind == LogicalPlan::Filter) {
+                    Frame in = exec_node(ctx, *c->input);
+                    FilterSpec f = convert_filter_predicate(c->predicate);
+                    if (in.names.empty()) throw Error("Column not found: '" + f.column + "'");
+                    return exec_filter(ctx, in, f, nullptr, p.n);
+                }
+                if (c->kind == LogicalPlan::Select && c->input->kind == LogicalPlan::Filter && !c->expressions.empty()) {
+                    std::vector<std::pair<std::string, std::string>> sel;
+                    for (const auto& e : c->expressions) sel.push_back(convert_select_expr(e));
+                    Frame in = exec_node(ctx, *c->input->input);
+                    FilterSpec f = convert_filter_predicate(c->input->predicate);
+                    if (in.names.empty()) throw Error("Column not found: '" + f.column + "'");
+                    return exec_filter(ctx, in, f, &sel, p.n);
+                }
+            }
+            Frame in = exec_node(ctx, *p.input);
+            if (in.names.empty()) return in;  // width 0: DataFrame::new(vec![])
+            Frame r;
+            r.names = in.names;
+            if (p.n == 0) {  // plan.rs:154-161: empty series keep their dtypes
+                r.rows = 0; r.dtypes = in.dtypes; r.rb = in.rb.slice(0, 0);
+                return r;
+            }
+            if (in.rows == 0) throw Error("Series error: Empty series not allowed");  // plan.rs:167-169
+            const size_t lim = std::min(p.n, in.rows);
+            r.rows = lim;
+            r.rb = in.rb.slice(0, lim);
+            for (size_t j = 0; j < in.names.size(); ++j) r.dtypes.push_back(inferred_dtype(r.rb, j, in.dtypes[j], lim));
+            return r;
+        }
+    }
+    return Frame();
+}
+}  // namespace
+
+DataFrame execute_eager(const LogicalPlan& optimized, const ContextRef& ctx) {
+    check_lowering(optimized);  // logical_to_physical fails before anything executes (builder.rs:99-100)
+    const ContextRef c = ctx ? ctx : Context::shared(0);
+    return download_frame(exec_node(c, optimized));
+}
+
+// ------------------------------------------------------------------------------------------------- streaming_planner.rs
+StreamingPhysicalPlan logical_to_streaming(const LogicalPlan& plan, const ContextRef& ctx) {  // streaming_planner.rs:29-100
+    switch (plan.kind) {
+        case LogicalPlan::DataFrameSource: return StreamingPhysicalPlan::dataframe_source(plan.df, 1024, ctx);  // :31-33
+        case LogicalPlan::Select: {  // :65-69, 102-135
+            auto in = logical_to_streaming(*plan.input, ctx);
+            std::vector<std::string> names;
+            for (const auto& e : plan.expressions) {
+                if (e.kind == Expr::Column) names.push_back(e.name);
+                else if (e.kind == Expr::Alias) {
+                    if (e.left->kind == Expr::Column) names.push_back(e.left->name);  // alias dropped (:110-113)
+                    else throw Error("Streaming planner error: Expression conversion error: Complex expressions with aliases not yet supported: " + e.debug());
+                } else
+                    throw Error("Streaming planner error: Expression conversion error: Complex expressions not yet supported in streaming mode: " + e.debug());
+            }
+            return in.select(names);
+        }
+        case LogicalPlan::Filter: {  // :71-75, 137-168
+            auto in = logical_to_streaming(*plan.input, ctx);
+            const Expr& p = plan.predicate;
+            if (p.kind == Expr::Column) return in.filter(p.name);
+            if (p.kind == Expr::Binary) {
+                if (p.left->kind == Expr::Column)
+                    throw Error("Streaming planner error: Expression conversion error: Binary expressions not yet supported in streaming mode. "
+                                "Found expression on column '" + p.left->name + "'. "
+                                "Currently only simple boolean column references are supported (e.g., .filter(col('is_active')))");
+                throw Error("Streaming planner error: Expression conversion error: Complex binary expressions not supported in streaming mode");
+            }
+            throw Error("Streaming planner error: Expression conversion error: Unsupported filter expression type: " + p.debug());
+        }
+        case LogicalPlan::Limit: return logical_to_streaming(*plan.input, ctx).limit(plan.n);  // :76-79
+    }
+    return StreamingPhysicalPlan();
+}
+
+// ------------------------------------------------------------------------------------------------- logical_plan/builder.rs
+LazyFrame LazyFrame::from_dataframe(const DataFrame& df, ContextRef ctx) {  // builder.rs:27-39
+    LazyFrame lf;
+    lf.plan_.kind = LogicalPlan::DataFrameSource;
+    lf.plan_.df = df;
+    for (const auto& s : df.columns()) lf.plan_.src_schema.emplace_back(s.name(), s.dtype());
+    lf.ctx_ = std::move(ctx);
+    return lf;
+}
+LazyFrame LazyFrame::select(std::vector<Expr> e) const {
+    LazyFrame lf; lf.ctx_ = ctx_; lf.plan_.kind = LogicalPlan::Select; lf.plan_.input = std::make_shared<LogicalPlan>(plan_); lf.plan_.expressions = std::move(e); return lf;
+}
+LazyFrame LazyFrame::filter(Expr p) const {
+    LazyFrame lf; lf.ctx_ = ctx_; lf.plan_.kind = LogicalPlan::Filter; lf.plan_.input = std::make_shared<LogicalPlan>(plan_); lf.plan_.predicate = std::move(p); return lf;
+}
+LazyFrame LazyFrame::limit(size_t n) const {
+    LazyFrame lf; lf.ctx_ = ctx_; lf.plan_.kind = LogicalPlan::Limit; lf.plan_.input = std::make_shared<LogicalPlan>(plan_); lf.plan_.n = n; return lf;
+}
+
+DataFrame LazyFrame::collect() const {  // builder.rs:96-104
+    LogicalPlan opt = optimize(plan_);
+    opt.validate();  // "Logical plan error: …" passes through typed (builder.rs:98)
+    try { return execute_eager(opt, ctx_); }
+    catch (const Error& e) { if (e.panic) throw; throw Error(std::string("Execution error: ") + e.what()); }
+}
+
+RecordBatch LazyFrame::collect_streaming() const {  // builder.rs:106-113
+    LogicalPlan opt = optimize(plan_);
+    opt.validate();
+    StreamingPhysicalPlan sp = logical_to_streaming(opt, ctx_);  // "Streaming planner error: …"
+    try { return sp.collect(); }
+    catch (const Error& e) { if (e.panic) throw; throw Error(std::string("Execution error: ") + e.what()); }
+}
+
+}  // namespace rivulus

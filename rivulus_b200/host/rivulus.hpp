@@ -1,8 +1,8 @@
 // rivulus.hpp — C++17 host layer of the B200-native filter / project / limit path.
 //
-// Mirrors the reference's public API for this path (same names, argument meaning and error text), and drives the
-// GPU exclusively through the C ABI of include/rivulus_gpu.h — exactly what a Rust crate binding that header would
-// do (the image has no rustc, so the host side is C++; see INTEGRATION.md for the Rust-side binding).
+// Mirrors the reference's public API for this path (same names, argument meaning and error text) and drives the GPU
+// exclusively through the C ABI of include/rivulus_gpu.h — exactly what a Rust crate binding that header would do
+// (the image has no rustc, so the host side is C++; INTEGRATION.md shows the Rust-side binding).
 //
 //   reference (under /root/reference/src)                      here
 //   datatypes/series.rs      AnyValue, DataType, Series        rivulus::AnyValue, DataType, Series (columnar storage)
@@ -10,10 +10,10 @@
 //   expressions/expr.rs      Expr, BinaryOperator              rivulus::Expr, BinaryOperator
 //   logical_plan/*           LogicalPlan, QueryOptimizer       rivulus::LogicalPlan, optimize()
 //   logical_plan/builder.rs  LazyFrame                         rivulus::LazyFrame
-//   physical_plan/planner.rs + plan.rs (eager executor)        execute_eager(): Filter+Select fused into one rvl_filter_project
+//   physical_plan/planner.rs + plan.rs (eager executor)        LazyFrame::collect(): Filter [+Select] [+Limit] = ONE rvl_filter_project
 //   execution/record_batch.rs RecordBatch                      rivulus::RecordBatch (device-resident)
-//   execution/stream.rs      DataStream, Memory/Filter/Select  rivulus::DataStream, MemoryStream, FilterStream, SelectStream
-//   physical_plan/streaming.rs StreamingPhysicalPlan, LimitStream  rivulus::StreamingPhysicalPlan, LimitStream
+//   execution/stream.rs      DataStream, Memory/Filter/Select  rivulus::DataStream + make_*_stream
+//   physical_plan/streaming.rs StreamingPhysicalPlan, LimitStream  rivulus::StreamingPhysicalPlan, make_limit_stream
 //
 // Storage differs on purpose: a Series holds Arrow-layout column buffers (values / LSB-first validity / int32
 // offsets + bytes) instead of Vec<AnyValue>, so handing a DataFrame to the device is a plain copy.
@@ -31,8 +31,8 @@
 
 namespace rivulus {
 
-// thrown for every reference `Err(..)`; what() is the reference's Display text.  `panic` marks what the reference
-// reports by panicking (slice / index out of bounds).
+// Thrown for every reference `Err(..)`; what() is the reference's Display text.  `panic` marks what the reference
+// reports by panicking (slice / index out of bounds, type mismatch in dataframe_to_batches).
 struct Error : std::runtime_error {
     bool panic = false;
     explicit Error(const std::string& m, bool p = false) : std::runtime_error(m), panic(p) {}
@@ -40,79 +40,96 @@ struct Error : std::runtime_error {
 
 // ---------------------------------------------------------------------------------------- datatypes/series.rs
 enum class DataType : int { Int64 = 0, Float64 = 1, String = 2, Boolean = 3, Null = 4 };  // series.rs:126-133
-const char* to_string(DataType d);
+const char* dtype_name(DataType d);                                                       // series.rs:162-172
 
 struct AnyValue {  // series.rs:6-13
-    enum Tag : uint8_t { Null = 0, Int64 = 1, Float64 = 2, String = 3, Boolean = 4 };
-    Tag tag = Null;
+    enum Tag : uint8_t { kNull = 0, kInt64 = 1, kFloat64 = 2, kString = 3, kBoolean = 4 };
+    Tag tag = kNull;
     int64_t i = 0;
     double f = 0.0;
     bool b = false;
     std::string s;
-    AnyValue() = default;
-    AnyValue(int64_t v) : tag(Int64), i(v) {}           // From<i64>    series.rs:31-35
-    AnyValue(int v) : tag(Int64), i(v) {}
-    AnyValue(double v) : tag(Float64), f(v) {}           // From<f64>    :37-41
-    AnyValue(const char* v) : tag(String), s(v) {}       // From<&str>   :49-53
-    AnyValue(std::string v) : tag(String), s(std::move(v)) {}
-    AnyValue(bool v) : tag(Boolean), b(v) {}             // From<bool>   :55-59
-    bool is_null() const { return tag == Null; }
-    DataType data_type() const;                          // :20-28
-    std::string display() const;                         // :61-71
-    std::string debug() const;
-    bool operator==(const AnyValue& o) const;            // PartialEq :87-98
+    static AnyValue Null() { return AnyValue(); }
+    static AnyValue Int64(int64_t v) { AnyValue a; a.tag = kInt64; a.i = v; return a; }      // From<i64>  :31-35
+    static AnyValue Float64(double v) { AnyValue a; a.tag = kFloat64; a.f = v; return a; }   // From<f64>  :37-41
+    static AnyValue String(std::string v) { AnyValue a; a.tag = kString; a.s = std::move(v); return a; }  // :43-53
+    static AnyValue Boolean(bool v) { AnyValue a; a.tag = kBoolean; a.b = v; return a; }     // From<bool> :55-59
+    bool is_null() const { return tag == kNull; }   // :16-18
+    DataType data_type() const;                     // :20-28
+    std::string display() const;                    // :61-71
+    std::string debug() const;                      // #[derive(Debug)]
 };
-std::optional<int> partial_cmp(const AnyValue& a, const AnyValue& b);  // series.rs:100-117
 
-// One column in Arrow layout.  `validity` empty = no nulls.
+// One column in Arrow layout.  dtype follows the reference's inference (series.rs:185-221): first non-null value's
+// type, Null when every value is null.  Values under a null are stored as 0 / false / empty.
 class Series {
   public:
-    static Series make(const std::string& name, const std::vector<AnyValue>& data);  // Series::new  series.rs:185-221
-    static Series empty(const std::string& name, DataType dtype);                    // :223-229
+    static Series make(const std::string& name, const std::vector<AnyValue>& data);  // Series::new  :185-221
+    static Series empty(const std::string& name, DataType dtype);                    // Series::empty :223-229
+    // columnar constructors (no reference counterpart: the reference only ingests Vec<AnyValue>); same inference rules.
+    // `validity_bits`: LSB-first, 1 = valid, empty = no nulls.
+    static Series from_i64(const std::string& name, std::vector<int64_t> v, std::vector<uint8_t> validity_bits = {});
+    static Series from_f64(const std::string& name, std::vector<double> v, std::vector<uint8_t> validity_bits = {});
+    static Series from_bool_bits(const std::string& name, std::vector<uint8_t> value_bits, size_t n, std::vector<uint8_t> validity_bits = {});
+    static Series from_strings(const std::string& name, std::vector<int32_t> offsets, std::vector<uint8_t> data, std::vector<uint8_t> validity_bits = {});
+
     const std::string& name() const { return name_; }
     size_t len() const { return len_; }
     bool is_empty() const { return len_ == 0; }
-    const DataType& dtype() const { return dtype_; }
-    AnyValue at(size_t i) const;              // Index<usize> :273-288 (throws Error{panic} out of bounds)
-    std::optional<AnyValue> get(size_t i) const;
+    DataType dtype() const { return dtype_; }
+    AnyValue at(size_t i) const;                       // Index<usize> :273-288 (Error{panic} out of bounds)
+    std::optional<AnyValue> get(size_t i) const;       // :243-245
     std::vector<AnyValue> to_values() const;
-    std::string display() const;              // "Series: numbers [{dtype}; {len}]" :267-271
+    std::string display() const;                       // "Series: numbers [{dtype}; {len}]" :267-271
     Series renamed(const std::string& n) const { Series s = *this; s.name_ = n; return s; }
     size_t null_count() const;
+    bool is_valid(size_t i) const { return dtype_ != DataType::Null && (validity_.empty() || ((validity_[i >> 3] >> (i & 7)) & 1)); }
+    // A Float64-dtype Series may hold Int64 values (series.rs:210-212); such mixed columns are kept on the host but are
+    // rejected by the GPU engines.
+    bool is_mixed() const { return !int_tag_.empty(); }
 
-    // raw buffers (rvl_column view over host memory)
-    rvl_column as_column() const;
-    static Series from_host_column(const std::string& name, const rvl_column& c, DataType dtype_hint);
+    // raw buffers
+    const std::vector<int64_t>& i64_values() const { return i64_; }
+    const std::vector<double>& f64_values() const { return f64_; }
+    const std::vector<uint8_t>& bool_bits() const { return bits_; }
+    const std::vector<int32_t>& str_offsets() const { return offsets_; }
+    const std::vector<uint8_t>& str_data() const { return data_; }
+    const std::vector<uint8_t>& validity_bits() const { return validity_; }
+    // rvl_column view over rows [offset, offset + length) of this Series' host buffers (borrowed).
+    // flatten_nulls: numeric / boolean nulls become valid 0 / false, as dataframe_to_batches does (streaming.rs:177,188,212).
+    rvl_column as_column(size_t offset, size_t length, bool flatten_nulls) const;
+    // Build from a downloaded column (dtype of the device array; `dtype_if_empty` is kept when length == 0).
+    static Series from_column(const std::string& name, const rvl_column& c, DataType dtype_if_empty);
 
   private:
-    friend class RecordBatch;
     std::string name_;
     DataType dtype_ = DataType::Null;
     size_t len_ = 0;
     std::vector<int64_t> i64_;
     std::vector<double> f64_;
     std::vector<uint8_t> bits_;      // Boolean values, LSB-first
-    std::vector<int32_t> offsets_;   // String
+    std::vector<int32_t> offsets_;   // String (len + 1 entries)
     std::vector<uint8_t> data_;      // String
     std::vector<uint8_t> validity_;  // LSB-first, empty = all valid
-    std::vector<uint8_t> int_tag_;   // Float64-dtype series that also holds Int64 values (series.rs:210-212): per-row "is Int64"
+    std::vector<uint8_t> int_tag_;   // mixed Float64 series: per row 1 = the value is an AnyValue::Int64 held in int_vals_
     std::vector<int64_t> int_vals_;
+    void infer_from_validity();      // all null -> dtype Null
 };
 
 // ---------------------------------------------------------------------------------------- datatypes/dataframe.rs
 class DataFrame {
   public:
     static DataFrame make(std::vector<Series> columns);  // DataFrame::new :29-56
-    static DataFrame empty() { return DataFrame(); }
-    size_t height() const { return columns_.empty() ? 0 : columns_[0].len(); }
+    static DataFrame empty() { return DataFrame(); }     // :58-62
+    size_t height() const { return columns_.empty() ? 0 : columns_[0].len(); }  // :64-70
     size_t width() const { return columns_.size(); }
     std::pair<size_t, size_t> shape() const { return {height(), width()}; }
-    bool is_empty() const { return columns_.empty(); }
-    const Series* column(const std::string& name) const;
+    bool is_empty() const { return columns_.empty(); }   // :80-82 (no columns)
+    const Series* column(const std::string& name) const; // :84-86
     std::vector<std::string> column_names() const;
     const std::vector<Series>& columns() const { return columns_; }
     DataFrame select(const std::vector<std::string>& names) const;  // :96-110
-    const Series& operator[](const std::string& name) const;        // Index<&str> :136-149
+    const Series& operator[](const std::string& name) const;        // Index<&str> :136-149 (panics)
     static DataFrame unchecked(std::vector<Series> c) { DataFrame d; d.columns_ = std::move(c); return d; }
 
   private:
@@ -120,23 +137,28 @@ class DataFrame {
 };
 
 // ---------------------------------------------------------------------------------------- expressions/expr.rs
-enum class BinaryOperator : int { Plus = 0, Minus, Multiply, Divide, Eq, NotEq, Lt, Gt, LtEq, GtEq, And, Or };
-const char* to_string(BinaryOperator op);
+enum class BinaryOperator : int { Plus = 0, Minus, Multiply, Divide, Eq, NotEq, Lt, Gt, LtEq, GtEq, And, Or };  // :15-29 (= rvl_op)
+const char* op_name(BinaryOperator op);
 
-struct Expr {
-    enum Kind { Column, Literal, BinaryExpr, Alias } kind = Column;
+struct Expr {  // expr.rs:3-13
+    enum Kind { Column, Literal, Binary, Alias } kind = Column;
     std::string name;
     AnyValue value;
     BinaryOperator op = BinaryOperator::Eq;
     std::shared_ptr<Expr> left, right;  // Alias: inner = left
 
-    static Expr col(const std::string& n) { Expr e; e.kind = Column; e.name = n; return e; }
-    static Expr lit(AnyValue v) { Expr e; e.kind = Literal; e.value = std::move(v); return e; }
+    static Expr col(const std::string& n) { Expr e; e.kind = Column; e.name = n; return e; }       // :31-33
+    static Expr lit(AnyValue v) { Expr e; e.kind = Literal; e.value = std::move(v); return e; }    // :35-37
+    static Expr lit(int64_t v) { return lit(AnyValue::Int64(v)); }
+    static Expr lit(int v) { return lit(AnyValue::Int64(v)); }
+    static Expr lit(double v) { return lit(AnyValue::Float64(v)); }
+    static Expr lit(const char* v) { return lit(AnyValue::String(v)); }
+    static Expr lit(bool v) { return lit(AnyValue::Boolean(v)); }
     Expr alias(const std::string& n) const { Expr e; e.kind = Alias; e.name = n; e.left = std::make_shared<Expr>(*this); return e; }
     Expr binary(BinaryOperator o, const Expr& r) const {
-        Expr e; e.kind = BinaryExpr; e.op = o; e.left = std::make_shared<Expr>(*this); e.right = std::make_shared<Expr>(r); return e;
+        Expr e; e.kind = Binary; e.op = o; e.left = std::make_shared<Expr>(*this); e.right = std::make_shared<Expr>(r); return e;
     }
-    Expr add(const Expr& o) const { return binary(BinaryOperator::Plus, o); }
+    Expr add(const Expr& o) const { return binary(BinaryOperator::Plus, o); }      // :43-121
     Expr sub(const Expr& o) const { return binary(BinaryOperator::Minus, o); }
     Expr mul(const Expr& o) const { return binary(BinaryOperator::Multiply, o); }
     Expr div(const Expr& o) const { return binary(BinaryOperator::Divide, o); }
@@ -146,7 +168,7 @@ struct Expr {
     Expr gt(const Expr& o) const { return binary(BinaryOperator::Gt, o); }
     Expr lte(const Expr& o) const { return binary(BinaryOperator::LtEq, o); }
     Expr gte(const Expr& o) const { return binary(BinaryOperator::GtEq, o); }
-    Expr and_(const Expr& o) const { return binary(BinaryOperator::And, o); }
+    Expr and_(const Expr& o) const { return binary(BinaryOperator::And, o); }     // :124-138
     Expr or_(const Expr& o) const { return binary(BinaryOperator::Or, o); }
     std::string debug() const;
 };
@@ -157,6 +179,7 @@ class Context {
     explicit Context(int device = 0);
     ~Context();
     Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
     rvl_ctx* handle() const { return ctx_; }
     static std::shared_ptr<Context> shared(int device = 0);  // process-wide default context per device
 
@@ -167,48 +190,53 @@ using ContextRef = std::shared_ptr<Context>;
 
 // ---------------------------------------------------------------------------------------- execution/schema.rs
 enum class ExecType : int { Null = 0, Boolean = 1, Int64 = 2, Float64 = 3, String = 4 };  // schema.rs:1-8 (= rvl_dtype)
-struct Field {
-    std::string name; ExecType data_type; bool nullable = true;
+const char* exec_type_name(ExecType t);
+struct Field {  // schema.rs:10-36
+    std::string name; ExecType data_type = ExecType::Null; bool nullable = true;
     bool operator==(const Field& o) const { return name == o.name && data_type == o.data_type && nullable == o.nullable; }
 };
-struct Schema {
+struct Schema {  // schema.rs:38-76
     std::vector<Field> fields;
     std::optional<size_t> index_of(const std::string& n) const;
     const Field* field_by_name(const std::string& n) const;
     size_t num_fields() const { return fields.size(); }
+    bool is_empty() const { return fields.empty(); }
     bool operator==(const Schema& o) const { return fields == o.fields; }
 };
 using SchemaRef = std::shared_ptr<Schema>;
 
-// host copy of one device column (what `value(i)` reads in the reference)
+// Host copy of one device column (what the reference's `value(i)` / `values()` / `null_bitmap()` expose).
 struct ArrayData {
     ExecType dtype = ExecType::Null;
     int64_t length = 0, null_count = 0;
     std::vector<int64_t> i64; std::vector<double> f64; std::vector<uint8_t> bits;
-    std::vector<int32_t> offsets; std::vector<uint8_t> data; std::vector<uint8_t> validity;  // validity empty = bitmap absent
-    AnyValue value(size_t i) const;
+    std::vector<int32_t> offsets; std::vector<uint8_t> data;
+    std::vector<uint8_t> validity;  // empty = bitmap absent
+    bool has_validity = false;
+    AnyValue value(size_t i) const;  // Error{panic} "Index {} out of bounds" (primitive.rs:49 etc.)
 };
 
 // ---------------------------------------------------------------------------------------- execution/record_batch.rs
 class RecordBatch {
   public:
     RecordBatch() = default;
-    // try_new over host columns: uploads (record_batch.rs:16-58)
+    // try_new over HOST columns (record_batch.rs:16-58): checks field count / lengths / dtypes, then uploads
     static RecordBatch try_new(const ContextRef& ctx, SchemaRef schema, const std::vector<rvl_column>& host_columns);
-    static RecordBatch from_series(const ContextRef& ctx, const std::vector<Series>& cols, bool flatten_nulls);
     static RecordBatch adopt(const ContextRef& ctx, SchemaRef schema, rvl_batch* handle);
+    static RecordBatch empty(const ContextRef& ctx, SchemaRef schema);               // :402-421
     const SchemaRef& schema() const { return schema_; }
-    size_t num_rows() const;
-    size_t num_columns() const { return schema_ ? schema_->fields.size() : 0; }
+    size_t num_rows() const;                                                         // :72
+    size_t num_columns() const;                                                      // :76
     bool is_empty() const { return num_rows() == 0; }
-    RecordBatch slice(size_t offset, size_t length) const;                           // :92-106
+    RecordBatch slice(size_t offset, size_t length) const;                           // :92-106 (Error{panic} "Slice out of bounds")
     RecordBatch select_columns(const std::vector<size_t>& indices) const;            // :180-206
     RecordBatch select_columns_by_name(const std::vector<std::string>& names) const; // :208-219
-    RecordBatch filter(const RecordBatch& predicate_batch, size_t predicate_column) const;  // :221-243 (mask = a Boolean column)
-    RecordBatch filter_by_column(size_t mask_column) const;
+    // filter(&self, predicate: &ArrayRef) :221-243 — the predicate array is column `predicate_column` of `predicate_batch`
+    RecordBatch filter(const RecordBatch& predicate_batch, size_t predicate_column) const;
     static RecordBatch concat(const std::vector<RecordBatch>& batches);              // :245-275
-    static RecordBatch empty(const ContextRef& ctx, SchemaRef schema);               // :402-421
-    ArrayData column_data(size_t i) const;   // download
+    RecordBatch with_schema(SchemaRef schema) const { RecordBatch r = *this; r.schema_ = std::move(schema); return r; }  // same buffers, renamed fields
+    ArrayData column_data(size_t i) const;   // device -> host copy of column i (rebased to offset 0)
+    int64_t column_null_count(size_t i) const;
     rvl_batch* handle() const { return h_ ? h_->b : nullptr; }
     const ContextRef& context() const { return ctx_; }
 
@@ -226,13 +254,17 @@ class DataStream {  // trait DataStream  stream.rs:25-54
     virtual SchemaRef schema() const = 0;
     virtual std::optional<RecordBatch> next_batch() = 0;
     std::vector<RecordBatch> collect();     // :30-39
-    RecordBatch concatenate();              // :41-53
 };
 using DataStreamRef = std::unique_ptr<DataStream>;
-DataStreamRef make_memory_stream(SchemaRef schema, std::vector<RecordBatch> batches);        // MemoryStream::new :66-81
+DataStreamRef make_memory_stream(const ContextRef& ctx, SchemaRef schema, std::vector<RecordBatch> batches);  // MemoryStream::new :66-81
 DataStreamRef make_filter_stream(DataStreamRef input, std::string predicate_column);         // FilterStream::new :123-128
 DataStreamRef make_select_stream(DataStreamRef input, std::vector<std::string> columns);     // SelectStream::new :173-194
 DataStreamRef make_limit_stream(DataStreamRef input, size_t limit);                          // LimitStream::new streaming.rs:254-260
+std::vector<RecordBatch> collect_all_batches(DataStream& s);                                 // streaming.rs:335-341
+RecordBatch collect_stream_batches(const ContextRef& ctx, DataStream& s);                    // streaming.rs:343-352
+
+// streaming.rs:135-233: DataFrame -> RecordBatches of `batch_size` rows on the device
+std::vector<RecordBatch> dataframe_to_batches(const ContextRef& ctx, const DataFrame& df, size_t batch_size);
 
 struct StreamingPhysicalPlan {  // streaming.rs:28-68, 290-333
     enum Kind { MemorySource, DataFrameSource, Filter, Select, Limit } kind = MemorySource;
@@ -248,13 +280,16 @@ struct StreamingPhysicalPlan {  // streaming.rs:28-68, 290-333
     StreamingPhysicalPlan filter(std::string col) const;
     StreamingPhysicalPlan select(std::vector<std::string> cols) const;
     StreamingPhysicalPlan limit(size_t n) const;
-    DataStreamRef execute() const;                      // :70-133 (one operator object per node)
-    RecordBatch collect() const;                        // :235-238; DataFrame sources take the fused rvl_stream_* pipeline
-    std::vector<RecordBatch> collect_batches() const;   // :240-243
+    DataStreamRef execute() const;                      // :70-133 (one operator object per node, batches of `batch_size`)
+    // :235-238.  The result is the concatenation of every batch, so it does not depend on the batch size: plans rooted
+    // at a DataFrame source run with batches of at least kCollectBatchRows rows (fewer, larger kernel launches).
+    RecordBatch collect() const;
+    std::vector<RecordBatch> collect_batches() const;   // :240-243 (honours batch_size: batch boundaries are visible)
+    static constexpr size_t kCollectBatchRows = 1 << 20;
 };
 
 // ---------------------------------------------------------------------------------------- logical_plan/*
-struct LogicalPlan {
+struct LogicalPlan {  // logical_plan/plan.rs:8-39 (CsvFileSource / Join: out of scope)
     enum Kind { DataFrameSource, Select, Filter, Limit } kind = DataFrameSource;
     DataFrame df;
     std::vector<std::pair<std::string, DataType>> src_schema;
@@ -263,24 +298,29 @@ struct LogicalPlan {
     Expr predicate;
     size_t n = 0;
     std::vector<std::pair<std::string, DataType>> schema() const;  // logical_plan/plan.rs:63-113
-    void validate() const;                                         // :115-202
-    std::string shape() const;
+    void validate() const;                                         // :115-202 (throws "Logical plan error: …")
+    std::string shape() const;                                     // e.g. "Limit(Select(Filter(Source)))"
 };
-LogicalPlan optimize(LogicalPlan plan);  // optimizer.rs:7-64
+LogicalPlan optimize(LogicalPlan plan);                                   // optimizer.rs:7-64
+StreamingPhysicalPlan logical_to_streaming(const LogicalPlan& plan, const ContextRef& ctx);  // streaming_planner.rs:29-168
+DataFrame execute_eager(const LogicalPlan& optimized, const ContextRef& ctx);  // planner.rs:41-189 + physical_plan/plan.rs:65-173
 
 class LazyFrame {  // logical_plan/builder.rs:11-114
   public:
-    static LazyFrame from_dataframe(const DataFrame& df, ContextRef ctx = nullptr);
-    LazyFrame select(std::vector<Expr> exprs) const;
-    LazyFrame filter(Expr predicate) const;
-    LazyFrame limit(size_t n) const;
-    DataFrame collect() const;               // eager engine semantics on the GPU
-    RecordBatch collect_streaming() const;   // streaming engine semantics on the GPU
+    static LazyFrame from_dataframe(const DataFrame& df, ContextRef ctx = nullptr);  // :27-39
+    LazyFrame select(std::vector<Expr> exprs) const;   // :57-64
+    LazyFrame filter(Expr predicate) const;            // :66-73
+    LazyFrame limit(size_t n) const;                   // :75-82
+    DataFrame collect() const;                         // :96-104   eager engine semantics, on the GPU
+    RecordBatch collect_streaming() const;             // :106-113  streaming engine semantics, on the GPU
     const LogicalPlan& logical_plan() const { return plan_; }
 
   private:
     LogicalPlan plan_;
     ContextRef ctx_;
 };
+
+// kernels launched by the default context of `device` so far (tests assert the GPU actually ran)
+int64_t launch_count(int device = 0);
 
 }  // namespace rivulus

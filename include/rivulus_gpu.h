@@ -130,7 +130,9 @@ typedef enum rvl_option {
     RVL_OPT_SPARSE_MAX = 2,         /* two-pass: 2048-row tiles with <= this many survivors are gathered (0..128, default 96) */
     RVL_OPT_DENSE_SLOTS = 3,        /* two-pass: 16 KB ring slots per CTA of the dense kernel (2..14) */
     RVL_OPT_DENSE_CTAS_PER_SM = 4,  /* 1 or 2 */
-    RVL_OPT_SCAN_SLOTS = 5          /* two-pass: 8 KB ring slots per warp of the predicate scan (1..3) */
+    RVL_OPT_SCAN_SLOTS = 5,         /* two-pass: ring slots per warp of the predicate scan (1..3) */
+    RVL_OPT_SCAN_WARPS = 6,         /* two-pass: warps per CTA of the predicate scan (8 or 16) */
+    RVL_OPT_DENSE_WARPS = 7         /* two-pass: consumer warps per CTA of the dense kernel (8 or 16; 16 implies one CTA per SM) */
 } rvl_option;
 int32_t rvl_ctx_set_option(rvl_ctx* ctx, int32_t option, int64_t value);
 

@@ -49,7 +49,7 @@ class RvlStreamConfig(C.Structure):
 
 
 PLAN_AUTO, PLAN_FUSED, PLAN_TWO_PASS = 0, 1, 2
-OPT_PLAN, OPT_TWO_PASS_MIN_ROWS, OPT_SPARSE_MAX, OPT_DENSE_SLOTS, OPT_DENSE_CTAS_PER_SM, OPT_SCAN_SLOTS = 0, 1, 2, 3, 4, 5
+OPT_PLAN, OPT_TWO_PASS_MIN_ROWS, OPT_SPARSE_MAX, OPT_DENSE_SLOTS, OPT_DENSE_CTAS_PER_SM, OPT_SCAN_SLOTS, OPT_SCAN_WARPS, OPT_DENSE_WARPS = 0, 1, 2, 3, 4, 5, 6, 7
 
 
 class RivulusError(RuntimeError):

@@ -28,8 +28,7 @@
 
 namespace rvl {
 
-constexpr int kCompactWarps = 8;                          // consumer warps of the dense kernel (256 rows each per tile)
-constexpr int kCompactThreads = (kCompactWarps + 1) * 32;  // + 1 producer warp
+constexpr int kCompactMaxWarps = 16;                      // consumer warps of the dense kernel: 8 (256 rows each per tile) or 16 (128 rows)
 constexpr uint32_t kSlotBytes = kTileRows * 8;            // one column tile
 constexpr int kSparseCap = 128;                           // most survivors a "sparse" tile may hold
 
@@ -51,9 +50,31 @@ struct CompactParams {
 };
 
 __device__ __forceinline__ uint64_t tile_prefix_of(const CompactParams& p, int64_t tile) {
-    return p.chunk_base[tile / p.tiles_per_chunk] + (p.tile_info[tile] >> kInfoShift);
+    return p.chunk_base[(uint32_t)tile / (uint32_t)p.tiles_per_chunk] + (p.tile_info[tile] >> kInfoShift);
 }
 
+__device__ __forceinline__ uint64_t lds64(uint32_t addr) {
+    uint64_t v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t bar_addr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar_addr), "r"(parity)
+            : "memory");
+    } while (ok == 0u);
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -74,7 +95,11 @@ __device__ __forceinline__ void tile_word_scan(uint32_t w0, uint32_t w1, int lan
     total = t0 + __shfl_sync(0xFFFFFFFFu, i1, 31);
 }
 
-static __global__ void __launch_bounds__(kCompactThreads, 2) compact_dense_kernel(const __grid_constant__ CompactParams p) {
+template <int CW>
+__global__ void __launch_bounds__((CW + 1) * 32, CW == 8 ? 2 : 1) compact_dense_kernel(const __grid_constant__ CompactParams p) {
+    constexpr int kCompactWarps = CW;
+    constexpr int KW = kTileWords / CW;        // selection words (32-row groups) per consumer warp and tile
+    constexpr int kWarpRows = kTileRows / CW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* const slots = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* const full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)p.n_slots * kSlotBytes);
@@ -115,55 +140,60 @@ static __global__ void __launch_bounds__(kCompactThreads, 2) compact_dense_kerne
     // -------------------------------------------------------------------- consumers
     const uint32_t lt = lanemask_lt();
     const uint64_t base0 = p.base_in != nullptr ? (uint64_t)*p.base_in : 0ull;
+    const uint32_t tpc = (uint32_t)p.tiles_per_chunk;  // tile ids and ranges fit 32 bits (checked by the host)
+    // shared-memory addresses as 32-bit offsets: slot s of the ring, this warp's 256 rows, this lane's row
+    const uint32_t slot_addr0 = smem_u32(slots) + (uint32_t)warp * (kWarpRows * 8u) + (uint32_t)lane * 8u;
+    const uint32_t full_addr0 = smem_u32(full), empty_addr0 = smem_u32(empty);
     int slot = 0;
     uint32_t phase = 0;
     // two-stage software prefetch: the tile id two iterations ahead, the selection words / prefix words one ahead.
     // Nothing loaded here is touched before the next iteration, so no consumer warp waits on these round trips.
     uint32_t nw0 = 0, nw1 = 0;
     uint64_t ninfo = 0, ncbase = 0;
-    int64_t ntile = (int64_t)p.list[blockIdx.x];
+    uint32_t ntile = p.list[blockIdx.x];
     uint32_t nntile = blockIdx.x + gridDim.x < n_list ? p.list[blockIdx.x + gridDim.x] : 0u;
     {
-        const uint32_t* sw = p.sel + ntile * kTileWords;
+        const uint32_t* sw = p.sel + (size_t)ntile * kTileWords;
         nw0 = __ldg(sw + lane); nw1 = __ldg(sw + 32 + lane);
-        ninfo = p.tile_info[ntile]; ncbase = p.chunk_base[ntile / p.tiles_per_chunk];
+        ninfo = p.tile_info[ntile]; ncbase = p.chunk_base[ntile / tpc];
     }
 #pragma unroll 1
     for (uint32_t i = blockIdx.x; i < n_list; i += gridDim.x) {
-        const int64_t tile = ntile;
+        const int64_t tile = (int64_t)ntile;
         const uint32_t w0 = nw0, w1 = nw1;
         const uint64_t prefix = ncbase + (ninfo >> kInfoShift);
         if (i + gridDim.x < n_list) {
-            ntile = (int64_t)nntile;
-            const uint32_t* sw = p.sel + ntile * kTileWords;
+            ntile = nntile;
+            const uint32_t* sw = p.sel + (size_t)ntile * kTileWords;
             nw0 = __ldg(sw + lane); nw1 = __ldg(sw + 32 + lane);
-            ninfo = p.tile_info[ntile]; ncbase = p.chunk_base[ntile / p.tiles_per_chunk];
+            ninfo = p.tile_info[ntile]; ncbase = p.chunk_base[ntile / tpc];
             if (i + 2 * gridDim.x < n_list) nntile = p.list[i + 2 * gridDim.x];
         }
         if (p.limit >= 0 && prefix >= (uint64_t)p.limit) continue;  // tile lies entirely beyond the limit (no slots were filled)
         const int64_t row0 = tile * kTileRows;
-        const int64_t wrow0 = row0 + (int64_t)warp * 256;  // this warp's 256 rows = 8 selection words
+        const int64_t wrow0 = row0 + (int64_t)warp * kWarpRows;  // this warp's rows = KW selection words
         const bool whole = row0 + kTileRows <= p.n_rows;
 
-        uint32_t e0, e1, total;
-        tile_word_scan(w0, w1, lane, e0, e1, total);
-        const uint32_t wsel = warp < 4 ? w0 : w1, wexc = warp < 4 ? e0 : e1;
-        uint32_t selw[8];
-        uint32_t rk[8];       // rank of this lane's row (word k) inside the tile
-        uint32_t keep = 0;    // bit k: this lane's row of word k survives (and lies below the limit)
+        // survivors of the tile in front of this warp's rows: two warp REDUX.ADDs instead of a 64-word scan
+        const uint32_t c0 = __popc(w0), c1 = __popc(w1);
+        uint32_t wfirst;
+        const int first_word = warp * KW;
+        if (first_word < 32) wfirst = __reduce_add_sync(0xFFFFFFFFu, lane < first_word ? c0 : 0u);
+        else wfirst = __reduce_add_sync(0xFFFFFFFFu, c0) + __reduce_add_sync(0xFFFFFFFFu, lane < first_word - 32 ? c1 : 0u);
+        const uint32_t wsel = first_word < 32 ? w0 : w1;
+        // survivors with a tile-local rank >= lim_rel lie beyond the LIMIT
+        const uint32_t lim_rel = p.limit < 0 ? 0xFFFFFFFFu : (uint32_t)min((uint64_t)p.limit - prefix, (uint64_t)0xFFFFFFFFu);
+        uint32_t selw[KW];
+        uint32_t off8[KW];    // byte offset of this lane's row (word k) from the tile's first output element
+        bool kp[KW];          // this lane's row of word k survives (and lies below the limit)
         uint32_t wcnt = 0;    // survivors of this warp
-        uint32_t wfirst = 0;  // rank of the warp's first survivor inside the tile
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int src = (warp * 8 + k) & 31;
-            selw[k] = __shfl_sync(0xFFFFFFFFu, wsel, src);
-            const uint32_t rb = __shfl_sync(0xFFFFFFFFu, wexc, src);
-            if (k == 0) wfirst = rb;
-            rk[k] = rb + __popc(selw[k] & lt);
+        for (int k = 0; k < KW; ++k) {
+            selw[k] = __shfl_sync(0xFFFFFFFFu, wsel, (first_word + k) & 31);
+            const uint32_t r = wfirst + wcnt + __popc(selw[k] & lt);
             wcnt += __popc(selw[k]);
-            bool kp = (selw[k] >> lane) & 1u;
-            if (p.limit >= 0 && prefix + rk[k] >= (uint64_t)p.limit) kp = false;
-            keep |= (kp ? 1u : 0u) << k;
+            kp[k] = ((selw[k] >> lane) & 1u) != 0u && r < lim_rel;
+            off8[k] = r * 8u;
         }
         const uint64_t obase = prefix - base0;  // output index of the tile's first survivor
 
@@ -171,34 +201,36 @@ static __global__ void __launch_bounds__(kCompactThreads, 2) compact_dense_kerne
         for (int c = 0; c < p.n_col8; ++c) {
             const Col8& col = p.col8[c];
             const bool via_tma = whole && col.vec_ok != 0;
-            uint64_t v[8];
-            mbar_wait(&full[slot], phase);
+            uint64_t v[KW];
+            mbar_wait_addr(full_addr0 + (uint32_t)slot * 8u, phase);
             if (via_tma) {
-                const uint64_t* src = slots + (size_t)slot * kTileRows + warp * 256 + lane;
+                const uint32_t src = slot_addr0 + (uint32_t)slot * kSlotBytes;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = src[k * 32];
+                for (int k = 0; k < KW; ++k) v[k] = lds64(src + k * 256);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[slot]);  // slot may be refilled
+            if (lane == 0) mbar_arrive_addr(empty_addr0 + (uint32_t)slot * 8u);  // slot may be refilled
             if (++slot == p.n_slots) { slot = 0; phase ^= 1u; }
             if (!via_tma) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < KW; ++k) {
                     v[k] = 0ull;
-                    if ((keep >> k) & 1u) v[k] = ld_stream(col.in + wrow0 + k * 32 + lane);
+                    if (kp[k]) v[k] = ld_stream(col.in + wrow0 + k * 32 + lane);
                 }
             }
             if (col.valid.words != nullptr) {  // placeholder 0 under a null (primitive.rs:175-178)
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < KW; ++k) {
                     const uint32_t vm = load_bits32(col.valid, (uint64_t)(wrow0 + k * 32));
                     if (((vm >> lane) & 1u) == 0u) v[k] = 0ull;
                 }
             }
-            uint64_t* out = col.out + obase;
+            // one 64-bit base per item, 32-bit byte offsets per row (kept opaque so the adds are not re-associated)
+            char* ob = reinterpret_cast<char*>(col.out + obase);
+            asm volatile("" : "+l"(ob));
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if ((keep >> k) & 1u) st_stream(out + rk[k], v[k]);
+            for (int k = 0; k < KW; ++k)
+                if (kp[k]) st_stream(reinterpret_cast<uint64_t*>(ob + off8[k]), v[k]);
         }
 
         // ---- bit-packed columns: lane j accumulates output word j of this warp's run
@@ -211,12 +243,12 @@ static __global__ void __launch_bounds__(kCompactThreads, 2) compact_dense_kerne
                 const uint32_t sh = (uint32_t)P & 31u;
                 const uint64_t first_word = P >> 5;
                 const uint32_t end = sh + lim;             // bits [sh, end) of the run are ours
-                const uint32_t n_words = (end + 31u) >> 5;  // <= 9
+                const uint32_t n_words = (end + 31u) >> 5;  // <= KW + 1
                 for (int b = 0; b < p.n_bits; ++b) {
                     const BitCol& bc = p.bits[b];
                     uint32_t acc = 0, q = sh;
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
+                    for (int k = 0; k < KW; ++k) {
                         const uint64_t r = (uint64_t)(wrow0 + k * 32);
                         const uint32_t in = load_bits32(bc.in, r) & load_bits32(bc.mask, r);
                         const uint32_t bit = (in >> lane) & (selw[k] >> lane) & 1u;

@@ -162,44 +162,56 @@ static void launch_fused(const CoreRef& core, int kind, const FusedParams& fp) {
 }
 
 // first pass of the two-pass plan (scan_kernels.cuh)
-template <int PRED>
+template <int PRED, int W>
 static int launch_scan_t(const CoreRef& core, const ScanParams& sp, int ctas) {
     static bool opted[64] = {false};
     if (!opted[core->device & 63]) {
-        RVL_CUDA_TRY(cudaFuncSetAttribute(predicate_scan_kernel<PRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanWarps * 3 * (int)(kScanItemBytes + 8)));
+        RVL_CUDA_TRY(cudaFuncSetAttribute(predicate_scan_kernel<PRED, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          W * 3 * (int)(ScanShape<W>::kItemBytes + 8)));
         opted[core->device & 63] = true;
     }
-    const size_t smem = (size_t)kScanWarps * sp.n_slots * (kScanItemBytes + 8);
-    predicate_scan_kernel<PRED><<<(unsigned)ctas, kScanWarps * 32, smem, core->stream>>>(sp);
+    const size_t smem = (size_t)W * sp.n_slots * (ScanShape<W>::kItemBytes + 8);
+    predicate_scan_kernel<PRED, W><<<(unsigned)ctas, W * 32, smem, core->stream>>>(sp);
     core->launches++;
     RVL_CUDA_TRY(cudaGetLastError());
     return RVL_OK;
 }
-static int launch_scan(const CoreRef& core, int kind, const ScanParams& sp, int ctas) {
+template <int W>
+static int launch_scan_w(const CoreRef& core, int kind, const ScanParams& sp, int ctas) {
     switch (kind) {
-        case kPredI64: return launch_scan_t<kPredI64>(core, sp, ctas);
-        case kPredF64: return launch_scan_t<kPredF64>(core, sp, ctas);
-        case kPredBits: return launch_scan_t<kPredBits>(core, sp, ctas);
-        default: return launch_scan_t<kPredTrue>(core, sp, ctas);
+        case kPredI64: return launch_scan_t<kPredI64, W>(core, sp, ctas);
+        case kPredF64: return launch_scan_t<kPredF64, W>(core, sp, ctas);
+        case kPredBits: return launch_scan_t<kPredBits, W>(core, sp, ctas);
+        default: return launch_scan_t<kPredTrue, W>(core, sp, ctas);
     }
+}
+static int launch_scan(const CoreRef& core, int kind, const ScanParams& sp, int ctas, int warps) {
+    return warps == 16 ? launch_scan_w<16>(core, kind, sp, ctas) : launch_scan_w<8>(core, kind, sp, ctas);
 }
 
 // second pass of the two-pass plan (compact_kernels.cuh): dense tiles through the TMA ring, sparse tiles gathered
-static int launch_compaction(const CoreRef& core, CompactParams cp, const uint32_t* dense_list, const uint32_t* sparse_list,
-                             const uint32_t* list_counts) {
+template <int CW>
+static int launch_dense_t(const CoreRef& core, const CompactParams& cp, int per_sm) {
     static bool opted[64] = {false};
     if (!opted[core->device & 63]) {
-        RVL_CUDA_TRY(cudaFuncSetAttribute(compact_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 14 * (int)(kSlotBytes + 16)));
+        RVL_CUDA_TRY(cudaFuncSetAttribute(compact_dense_kernel<CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 14 * (int)(kSlotBytes + 16)));
         opted[core->device & 63] = true;
     }
-    const int per_sm = std::max(1, std::min(2, core->dense_ctas_per_sm));
-    const int max_slots = per_sm == 1 ? 14 : 6;
-    cp.n_slots = std::max(2, std::min(max_slots, core->dense_slots));
     const size_t smem = (size_t)cp.n_slots * (kSlotBytes + 16);
-    cp.list = dense_list; cp.list_count = list_counts;
-    compact_dense_kernel<<<(unsigned)(core->sm_count * per_sm), kCompactThreads, smem, core->stream>>>(cp);
+    compact_dense_kernel<CW><<<(unsigned)(core->sm_count * per_sm), (CW + 1) * 32, smem, core->stream>>>(cp);
     core->launches++;
     RVL_CUDA_TRY(cudaGetLastError());
+    return RVL_OK;
+}
+static int launch_compaction(const CoreRef& core, CompactParams cp, const uint32_t* dense_list, const uint32_t* sparse_list,
+                             const uint32_t* list_counts) {
+    const int warps = core->dense_warps == 16 ? 16 : 8;
+    const int per_sm = warps == 16 ? 1 : std::max(1, std::min(2, core->dense_ctas_per_sm));
+    const int max_slots = per_sm == 1 ? 14 : 6;
+    cp.n_slots = std::max(2, std::min(max_slots, core->dense_slots));
+    cp.list = dense_list; cp.list_count = list_counts;
+    if (warps == 16) RVL_TRY(launch_dense_t<16>(core, cp, per_sm));
+    else RVL_TRY(launch_dense_t<8>(core, cp, per_sm));
     cp.list = sparse_list; cp.list_count = list_counts + 1;
     gather_sparse_kernel<<<(unsigned)(core->sm_count * 8), kBlock, 0, core->stream>>>(cp);
     core->launches++;
@@ -279,7 +291,7 @@ int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pre
     if (n > 0) {
         const int launches_needed = std::max<int>(1, std::max<int>(((int)col8s.size() + kMaxCol8 - 1) / kMaxCol8, ((int)bitcols.size() + kMaxBitCols - 1) / kMaxBitCols));
         // plan: one fused pass (small batches, one launch), or predicate scan + independent compaction pass (large batches)
-        const bool two_pass = (!col8s.empty() || !bitcols.empty()) &&
+        const bool two_pass = (!col8s.empty() || !bitcols.empty()) && tiles < (1ll << 32) &&  // tile ids are 32-bit in the second pass
                               (core->plan_mode == 2 || (core->plan_mode == 0 && limit < 0 && n >= core->two_pass_min_rows));
         const bool need_sel = want_mask || !strjobs.empty() || launches_needed > 1 || two_pass;
         BufRef status, sel, tile_prefix, lists;
@@ -301,8 +313,9 @@ int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pre
         BufRef chunk_base;
         if (two_pass) {
             // pass 1: persistent predicate scan (scan_kernels.cuh), every warp owns a contiguous range of tiles
-            const int scan_ctas = std::min(384, core->sm_count);
-            const int64_t n_ranges = (int64_t)scan_ctas * kScanWarps;
+            const int scan_ctas = std::min(192, core->sm_count);
+            const int scan_warps = core->scan_warps == 16 ? 16 : 8;
+            const int64_t n_ranges = (int64_t)scan_ctas * scan_warps;
             tiles_per_chunk = std::max<int64_t>(1, (tiles + n_ranges - 1) / n_ranges);
             // [dense tile ids | sparse tile ids | n_dense, n_sparse, CTAs done, pad] and the per-range bases
             RVL_TRY(dev_alloc(core, (size_t)tiles * 8 + 16, &lists));
@@ -327,7 +340,7 @@ int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pre
             sp.chunk_base = (uint64_t*)chunk_base->ptr;
             sp.dense_list = dense_list; sp.sparse_list = sparse_list; sp.list_counts = list_counts;
             sp.total_out = dctr;
-            RVL_TRY(launch_scan(core, pp.kind, sp, scan_ctas));
+            RVL_TRY(launch_scan(core, pp.kind, sp, scan_ctas, scan_warps));
             for (int L = 0; L < launches_needed; ++L) {
                 CompactParams cp{};
                 cp.n_rows = n; cp.limit = limit; cp.sel = (const uint32_t*)sel->ptr; cp.tile_info = (const uint64_t*)tile_prefix->ptr;

@@ -51,9 +51,11 @@ struct CtxCore {
     int plan_mode = 0;                      // RVL_PLAN_AUTO / _FUSED / _TWO_PASS
     int64_t two_pass_min_rows = 4 << 20;    // AUTO: batches at least this large take the two-pass plan
     int sparse_max = 96;                    // two-pass: tiles with <= this many survivors (of 2048 rows) are gathered
-    int dense_slots = 12;                   // two-pass: 16 KB ring slots per CTA of the dense compaction kernel
+    int dense_slots = 14;                   // two-pass: 16 KB ring slots per CTA of the dense compaction kernel
     int dense_ctas_per_sm = 1;
-    int scan_slots = 3;                     // two-pass: 8 KB ring slots per warp of the predicate scan (1..3)
+    int dense_warps = 16;                   // two-pass: consumer warps per CTA of the dense kernel (8 or 16)
+    int scan_warps = 16;                    // two-pass: warps per CTA of the predicate scan (8 or 16)
+    int scan_slots = 2;                     // two-pass: 8 KB ring slots per warp of the predicate scan (1..3)
     int prof_flush();
     uint64_t* next_slot() { return mailbox + kSlotBase + (size_t)(slot_cursor.fetch_add(1) % kSlots) * kSlotWords; }
     ~CtxCore();

@@ -26,9 +26,15 @@
 
 namespace rvl {
 
-constexpr int kScanWarps = 8;
-constexpr int kScanItemRows = 1024;                     // one ring slot = half a tile
-constexpr uint32_t kScanItemBytes = kScanItemRows * 8;  // 8 KB
+constexpr int kScanMaxWarps = 16;
+// W warps per CTA, each with its own ring of slots of 8192 / W rows (8 warps: 8 KB slots, 16 warps: 4 KB slots), so a
+// CTA always holds n_slots x 64 KB of predicate values
+template <int W> struct ScanShape {
+    static constexpr int kItemRows = 8192 / W;
+    static constexpr int kItemWords = kItemRows / 32;
+    static constexpr int kItemsPerTile = kTileRows / kItemRows;
+    static constexpr uint32_t kItemBytes = kItemRows * 8;
+};
 constexpr int kInfoShift = 12;                          // tile_info = (prefix << 12) | count, count <= 2048
 
 struct ScanParams {
@@ -64,8 +70,13 @@ __device__ __forceinline__ bool scan_keep(const ScanParams& p, uint64_t v) {
     return (p.truth & cmp_code<PRED>(v, p.lit_bits)) != 0u;
 }
 
-template <int PRED>
-__global__ void __launch_bounds__(kScanWarps * 32, 1) predicate_scan_kernel(const __grid_constant__ ScanParams p) {
+template <int PRED, int W>
+__global__ void __launch_bounds__(W * 32, 1) predicate_scan_kernel(const __grid_constant__ ScanParams p) {
+    constexpr int kScanWarps = W;
+    constexpr int kScanItemRows = ScanShape<W>::kItemRows;
+    constexpr int kItemWords = ScanShape<W>::kItemWords;
+    constexpr int kItemsPerTile = ScanShape<W>::kItemsPerTile;
+    constexpr uint32_t kScanItemBytes = ScanShape<W>::kItemBytes;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t s_part[kScanWarps];
     __shared__ uint32_t s_last;
@@ -79,7 +90,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) predicate_scan_kernel(cons
     const int64_t g = (int64_t)blockIdx.x * kScanWarps + warp;  // this warp's range index, in row order
     const int64_t t0 = min(p.n_tiles, g * p.tiles_per_warp);
     const int64_t t1 = min(p.n_tiles, t0 + p.tiles_per_warp);
-    const int64_t n_items = (t1 - t0) * 2;
+    const int64_t n_items = (t1 - t0) * kItemsPerTile;
     const int64_t range_row0 = t0 * kTileRows;
     const uint64_t base0 = p.base_in != nullptr ? (uint64_t)*p.base_in : 0ull;
     const bool use_tma = kNumeric && p.pred_vec_ok != 0;
@@ -120,7 +131,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) predicate_scan_kernel(cons
         if (p.limit >= 0 && base0 + lprefix >= (uint64_t)p.limit) break;
         uint32_t tcount = 0;
 #pragma unroll 1
-        for (int h = 0; h < 2; ++h, ++j) {
+        for (int h = 0; h < kItemsPerTile; ++h, ++j) {
             const int64_t row0 = t * kTileRows + (int64_t)h * kScanItemRows;
             const bool whole = row0 + kScanItemRows <= p.n_rows;
             const uint32_t wa = nx_a, wb = nx_b;
@@ -132,7 +143,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) predicate_scan_kernel(cons
                 if (tma) mbar_wait(&full[slot], phase);
                 const uint64_t* src = ring + (size_t)slot * kScanItemRows + lane;
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
+                for (int b = 0; b < kItemWords / 8; ++b) {
                     uint64_t v[8];
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
@@ -169,7 +180,8 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) predicate_scan_kernel(cons
                 const int64_t rem = p.n_rows - (row0 + lane * 32);
                 if (rem < 32) myword = rem <= 0 ? 0u : (myword & ((1u << rem) - 1u));
             }
-            p.sel_out[(row0 >> 5) + lane] = myword;
+            if (lane >= kItemWords) myword = 0u;  // lanes beyond the item's words hold nothing
+            if (lane < kItemWords) p.sel_out[(row0 >> 5) + lane] = myword;
             tcount += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(myword));
         }
         if (lane == 0) p.tile_info[t] = (lprefix << kInfoShift) | (uint64_t)tcount;

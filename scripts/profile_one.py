@@ -14,10 +14,14 @@ ap.add_argument("--plan", default="auto", choices=["auto", "fused", "two_pass"])
 ap.add_argument("--sparse-max", type=int, default=None)
 ap.add_argument("--dense-slots", type=int, default=None)
 ap.add_argument("--dense-ctas", type=int, default=None)
+ap.add_argument("--scan-warps", type=int, default=None)
+ap.add_argument("--dense-warps", type=int, default=None)
+ap.add_argument("--scan-slots", type=int, default=None)
 args = ap.parse_args()
 ctx = capi.Context(0)
 ctx.set_option(capi.OPT_PLAN, {"auto": capi.PLAN_AUTO, "fused": capi.PLAN_FUSED, "two_pass": capi.PLAN_TWO_PASS}[args.plan])
-for opt, val in ((capi.OPT_SPARSE_MAX, args.sparse_max), (capi.OPT_DENSE_SLOTS, args.dense_slots), (capi.OPT_DENSE_CTAS_PER_SM, args.dense_ctas)):
+for opt, val in ((capi.OPT_SPARSE_MAX, args.sparse_max), (capi.OPT_DENSE_SLOTS, args.dense_slots), (capi.OPT_DENSE_CTAS_PER_SM, args.dense_ctas),
+                     (capi.OPT_SCAN_WARPS, args.scan_warps), (capi.OPT_DENSE_WARPS, args.dense_warps), (capi.OPT_SCAN_SLOTS, args.scan_slots)):
     if val is not None:
         ctx.set_option(opt, val)
 spec = [(capi.SYNTH_KEY1000, 0, 0), (capi.SYNTH_I64, 1, 0), (capi.SYNTH_F64, 2, 0), (capi.SYNTH_I64, 3, 0), (capi.SYNTH_F64, 4, 0)]

@@ -355,14 +355,16 @@ def test_two_pass_mixed_density_tiles(sparse_max, limit):
     c.set_option(capi.OPT_PLAN, capi.PLAN_TWO_PASS)
     c.set_option(capi.OPT_SPARSE_MAX, sparse_max)
     try:
+        c.set_option(capi.OPT_DENSE_WARPS, 16 if sparse_max % 2 else 8)
         run_cmp(c, cols, 0, ">", 1000, [1, 2, 3, 4, 0], limit, tag=f"two-pass sparse_max={sparse_max} limit={limit}")
         run_cmp(c, cols, 0, "<", 100, [4, 3], limit, tag=f"two-pass nulls-pass sparse_max={sparse_max}")
     finally:
         c.close()
 
 
-@pytest.mark.parametrize("slots,per_sm", [(2, 1), (3, 2), (6, 2), (14, 1)])
-def test_two_pass_ring_depths(slots, per_sm):
+@pytest.mark.parametrize("slots,per_sm,scan_warps,scan_slots,dense_warps",
+                         [(2, 1, 8, 1, 8), (3, 2, 16, 1, 8), (6, 2, 16, 3, 8), (14, 1, 8, 2, 16), (12, 1, 16, 2, 16), (2, 1, 16, 2, 16)])
+def test_two_pass_ring_depths(slots, per_sm, scan_warps, scan_slots, dense_warps):
     rng = np.random.default_rng(5)
     n = 1_500_000
     cols = [random_col(rng, "i64", n, 0.0, lo=0, hi=1000)] + [random_col(rng, "f64" if j % 2 else "i64", n, 0.1 if j == 1 else 0.0) for j in range(5)]
@@ -370,7 +372,16 @@ def test_two_pass_ring_depths(slots, per_sm):
     c.set_option(capi.OPT_PLAN, capi.PLAN_TWO_PASS)
     c.set_option(capi.OPT_DENSE_SLOTS, slots)
     c.set_option(capi.OPT_DENSE_CTAS_PER_SM, per_sm)
+    c.set_option(capi.OPT_SCAN_WARPS, scan_warps)
+    c.set_option(capi.OPT_DENSE_WARPS, dense_warps)
+    c.set_option(capi.OPT_SCAN_SLOTS, scan_slots)
     try:
-        run_cmp(c, cols, 0, ">", 299, [1, 2, 3, 4, 5], tag=f"ring slots={slots} per_sm={per_sm}")
+        run_cmp(c, cols, 0, ">", 299, [1, 2, 3, 4, 5], tag=f"ring slots={slots} per_sm={per_sm} scan={scan_warps}x{scan_slots}")
+        # nulls in the predicate column, Float64 predicate, bitmap predicate, unaligned view, LIMIT: every scan path
+        fcols = [random_col(rng, "f64", 300_001, 0.1, offset=1, specials=True), random_col(rng, "bool", 300_001, 0.1, offset=5),
+                 random_col(rng, "i64", 300_001, 0.2)]
+        run_cmp(c, fcols, 0, "<=", 499.5, [2, 1, 0], tag="scan f64+nulls")
+        run_cmp(c, fcols, 1, "==", True, [0, 2], 70_000, tag="scan bits+limit")
+        run_mask(c, fcols, 1, [2, 0], tag="scan mask")
     finally:
         c.close()

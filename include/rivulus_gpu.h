@@ -160,6 +160,9 @@ int32_t rvl_batch_download_column(rvl_ctx* ctx, const rvl_batch* batch, int32_t 
 int32_t rvl_batch_slice(const rvl_batch* batch, int64_t offset, int64_t length, rvl_batch** view);
 /* RecordBatch::select_columns (record_batch.rs:180-206): zero-copy column pick */
 int32_t rvl_batch_select(const rvl_batch* batch, const int32_t* indices, int32_t n, rvl_batch** view);
+/* RecordBatch::take (record_batch.rs:108-129 -> take_array :131-178): gather rows by HOST indices (any order, repeats allowed);
+ * RVL_OUT_OF_BOUNDS "Index {} out of bounds for {} rows".  Output freshly built like the reference's builders. */
+int32_t rvl_batch_take(rvl_ctx* ctx, const rvl_batch* batch, const int64_t* indices, int64_t n, rvl_batch** out);
 /* RecordBatch::concat (record_batch.rs:245-342): freshly built output, offset 0, bitmap iff nulls */
 int32_t rvl_batch_concat(rvl_ctx* ctx, const rvl_batch* const* batches, int32_t n, rvl_batch** out);
 

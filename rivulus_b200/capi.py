@@ -66,7 +66,7 @@ ABI_SYMBOLS = [
     "rvl_ctx_profile_enable", "rvl_ctx_profile_read", "rvl_ctx_profile_read_launches", "rvl_ctx_set_option",
     "rvl_host_alloc", "rvl_host_free",
     "rvl_batch_upload", "rvl_batch_wrap_device", "rvl_batch_release", "rvl_batch_num_rows", "rvl_batch_num_columns",
-    "rvl_batch_column", "rvl_batch_download_column", "rvl_batch_slice", "rvl_batch_select", "rvl_batch_concat",
+    "rvl_batch_column", "rvl_batch_download_column", "rvl_batch_slice", "rvl_batch_select", "rvl_batch_take", "rvl_batch_concat",
     "rvl_filter_project", "rvl_predicate_mask", "rvl_filter_project_launch", "rvl_filter_project_finish",
     "rvl_stream_open", "rvl_stream_push", "rvl_stream_next", "rvl_stream_limit_reached", "rvl_stream_collect",
     "rvl_stream_stats", "rvl_stream_close",
@@ -340,6 +340,13 @@ class Batch:
     def slice(self, offset: int, length: int) -> "Batch":
         out = C.c_void_p()
         check(lib().rvl_batch_slice(self._h, C.c_int64(offset), C.c_int64(length), C.byref(out)))
+        return Batch(self.ctx, out)
+
+    def take(self, indices: Sequence[int]) -> "Batch":
+        """RecordBatch::take (record_batch.rs:108-129): rows by index."""
+        a = np.ascontiguousarray(indices, dtype=np.int64)
+        out = C.c_void_p()
+        check(lib().rvl_batch_take(self.ctx._h, self._h, a.ctypes.data_as(C.POINTER(C.c_int64)) if a.size else None, C.c_int64(a.size), C.byref(out)))
         return Batch(self.ctx, out)
 
     def select(self, indices: Sequence[int]) -> "Batch":

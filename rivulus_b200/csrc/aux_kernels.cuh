@@ -205,6 +205,60 @@ static __global__ void copy_col8_zero_nulls_kernel(const uint64_t* __restrict__ 
     }
 }
 
+// ---- take (record_batch.rs:108-178): gather rows by index, one output row per thread ------------------------------
+// 8-byte columns: out[i] = valid(idx[i]) ? in[idx[i]] : 0, validity bit i = valid(idx[i]) (one ballot word per warp)
+static __global__ void take_col8_kernel(const uint64_t* __restrict__ in, BitSrc valid, const int64_t* __restrict__ idx, int64_t n,
+                                        uint64_t* __restrict__ out, uint32_t* __restrict__ out_valid) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok = false;
+    if (i < n) {
+        const int64_t r = idx[i];
+        ok = true;
+        if (valid.words != nullptr) { const uint64_t bit = valid.bit0 + (uint64_t)r; ok = (__ldg(valid.words + (bit >> 5)) >> (bit & 31)) & 1u; }
+        out[i] = ok ? in[r] : 0ull;
+    }
+    const uint32_t w = __ballot_sync(0xFFFFFFFFu, ok);
+    if (out_valid != nullptr && (threadIdx.x & 31) == 0 && i < n) out_valid[i >> 5] = w;
+}
+// bit-packed values (Boolean) and/or validity
+static __global__ void take_bits_kernel(BitSrc vals, BitSrc valid, const int64_t* __restrict__ idx, int64_t n, uint32_t* __restrict__ out_vals,
+                                        uint32_t* __restrict__ out_valid) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok = false, v = false;
+    if (i < n) {
+        const uint64_t r = (uint64_t)idx[i];
+        ok = true;
+        if (valid.words != nullptr) { const uint64_t bit = valid.bit0 + r; ok = (__ldg(valid.words + (bit >> 5)) >> (bit & 31)) & 1u; }
+        if (ok && vals.words != nullptr) { const uint64_t bit = vals.bit0 + r; v = (__ldg(vals.words + (bit >> 5)) >> (bit & 31)) & 1u; }
+    }
+    const uint32_t wv = __ballot_sync(0xFFFFFFFFu, v), wk = __ballot_sync(0xFFFFFFFFu, ok);
+    if ((threadIdx.x & 31) == 0 && i < n) {
+        if (out_vals != nullptr) out_vals[i >> 5] = wv;
+        if (out_valid != nullptr) out_valid[i >> 5] = wk;
+    }
+}
+// strings: lens[i] = byte length of the taken string (0 under a null)
+static __global__ void take_strlen_kernel(const int32_t* __restrict__ offsets, BitSrc valid, const int64_t* __restrict__ idx, int64_t n,
+                                          int32_t* __restrict__ lens) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t r = idx[i];
+    bool ok = true;
+    if (valid.words != nullptr) { const uint64_t bit = valid.bit0 + (uint64_t)r; ok = (__ldg(valid.words + (bit >> 5)) >> (bit & 31)) & 1u; }
+    lens[i] = ok ? offsets[r + 1] - offsets[r] : 0;
+}
+// one warp per taken string: copy its bytes to the new offsets
+static __global__ void take_strcopy_kernel(const int32_t* __restrict__ offsets, const uint8_t* __restrict__ data, const int64_t* __restrict__ idx,
+                                           int64_t n, const int32_t* __restrict__ out_offsets, uint8_t* __restrict__ out_data) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const int32_t len = out_offsets[i + 1] - out_offsets[i];
+    const uint8_t* src = data + offsets[idx[i]];
+    uint8_t* dst = out_data + out_offsets[i];
+    for (int32_t j = lane; j < len; j += 32) dst[j] = __ldg(src + j);
+}
+
 // out[i + 1] = in[i + 1] - in[0] + byte_base   for i in [0, n)   (string concat / download rebasing)
 static __global__ void rebase_offsets_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out, int64_t n, int32_t byte_base) {
     const int32_t first = in[0];

@@ -468,6 +468,82 @@ int32_t rvl_batch_select(const rvl_batch* batch, const int32_t* indices, int32_t
     return RVL_OK;
 }
 
+int32_t rvl_batch_take(rvl_ctx* ctx, const rvl_batch* batch, const int64_t* indices, int64_t n, rvl_batch** out) {
+    if (!ctx || !batch || !out || n < 0 || (n > 0 && !indices)) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    const CoreRef& core = ctx->core;
+    RVL_CUDA_TRY(cudaSetDevice(core->device));
+    for (int64_t i = 0; i < n; ++i)
+        if (indices[i] < 0 || indices[i] >= batch->num_rows)
+            return fail(RVL_OUT_OF_BOUNDS, "Index " + std::to_string(indices[i]) + " out of bounds for " + std::to_string(batch->num_rows) + " rows");  // record_batch.rs:111-114
+    auto res = std::make_unique<rvl_batch>();
+    res->core = core; res->num_rows = n;
+    BufRef didx;
+    RVL_TRY(dev_alloc(core, (size_t)std::max<int64_t>(n, 1) * 8, &didx));
+    if (n > 0) RVL_CUDA_TRY(cudaMemcpyAsync(didx->ptr, indices, (size_t)n * 8, cudaMemcpyHostToDevice, core->stream));
+    const int64_t* idx = (const int64_t*)didx->ptr;
+    const size_t wbytes = (size_t)((n + 31) / 32) * 4 + 8;
+    const unsigned grid = (unsigned)std::max<int64_t>(1, (n + 255) / 256);
+    for (const DevColumn& s : batch->cols) {
+        DevColumn d;
+        d.dtype = s.dtype; d.length = n; d.offset = 0; d.null_count = -1;
+        const BitSrc sv = bitsrc_of(s.validity, s.offset, s.length);
+        if (s.validity && s.dtype != RVL_NULL) RVL_TRY(dev_alloc_zeroed(core, wbytes, &d.validity));
+        uint32_t* ov = d.validity ? (uint32_t*)d.validity->ptr : nullptr;
+        if (s.dtype == RVL_INT64 || s.dtype == RVL_FLOAT64) {
+            RVL_TRY(dev_alloc(core, (size_t)std::max<int64_t>(n, 1) * 8, &d.values));
+            if (n > 0) {
+                take_col8_kernel<<<grid, 256, 0, core->stream>>>((const uint64_t*)s.values->ptr + s.offset, sv, idx, n, (uint64_t*)d.values->ptr, ov);
+                core->launches++;
+            }
+        } else if (s.dtype == RVL_BOOLEAN) {
+            RVL_TRY(dev_alloc_zeroed(core, wbytes, &d.values));
+            if (n > 0) {
+                take_bits_kernel<<<grid, 256, 0, core->stream>>>(bitsrc_of(s.values, s.offset, s.length), sv, idx, n, (uint32_t*)d.values->ptr, ov);
+                core->launches++;
+            }
+        } else if (s.dtype == RVL_STRING) {
+            BufRef lens;
+            RVL_TRY(dev_alloc(core, (size_t)std::max<int64_t>(n, 1) * 4, &lens));
+            RVL_TRY(dev_alloc(core, (size_t)(n + 1) * 4, &d.offsets));
+            RVL_CUDA_TRY(cudaMemsetAsync(d.offsets->ptr, 0, 4, core->stream));
+            int32_t total = 0;
+            if (n > 0) {
+                const int32_t* soff = (const int32_t*)s.offsets->ptr + s.offset;
+                take_strlen_kernel<<<grid, 256, 0, core->stream>>>(soff, sv, idx, n, (int32_t*)lens->ptr);
+                scan_lengths_kernel<<<1, 1024, 0, core->stream>>>((const int32_t*)lens->ptr, (int32_t*)d.offsets->ptr, n);
+                core->launches += 2;
+                RVL_CUDA_TRY(cudaMemcpyAsync(&total, (const int32_t*)d.offsets->ptr + n, 4, cudaMemcpyDeviceToHost, core->stream));
+                RVL_CUDA_TRY(cudaStreamSynchronize(core->stream));
+                if (total < 0) return fail(RVL_OFFSET_OVERFLOW, "taken string data exceeds the int32 offset range");
+            }
+            RVL_TRY(dev_alloc(core, (size_t)std::max<int32_t>(total, 1), &d.data));
+            d.data_len = total;
+            if (n > 0 && total > 0) {
+                const int32_t* soff = (const int32_t*)s.offsets->ptr + s.offset;
+                take_strcopy_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, core->stream>>>(soff, (const uint8_t*)s.data->ptr, idx, n,
+                                                                                                    (const int32_t*)d.offsets->ptr, (uint8_t*)d.data->ptr);
+                core->launches++;
+            }
+            if (ov != nullptr && n > 0) {
+                take_bits_kernel<<<grid, 256, 0, core->stream>>>(BitSrc{nullptr, 0, 0}, sv, idx, n, nullptr, ov);
+                core->launches++;
+            }
+        } else {
+            d.null_count = n;
+        }
+        RVL_CUDA_TRY(cudaGetLastError());
+        res->cols.push_back(std::move(d));
+    }
+    RVL_CUDA_TRY(cudaStreamSynchronize(core->stream));  // `indices` (host) and the index buffer may now be released
+    // the reference's builders keep a bitmap only when a taken row is null (primitive.rs:180-185)
+    for (size_t c = 0; c < res->cols.size(); ++c) {
+        RVL_TRY(ensure_null_count(res.get(), (int)c));
+        if (res->cols[c].null_count == 0) res->cols[c].validity.reset();
+    }
+    *out = res.release();
+    return RVL_OK;
+}
+
 int32_t rvl_batch_concat(rvl_ctx* ctx, const rvl_batch* const* batches, int32_t n, rvl_batch** out) {
     if (!ctx || !out) return fail(RVL_INVALID_ARGUMENT, "null argument");
     if (n <= 0 || !batches) return fail(RVL_INVALID_ARGUMENT, "Cannot concatenate empty batch list");  // record_batch.rs:247

@@ -45,7 +45,7 @@ HOST_SYMBOLS = [
     "rvh_lf_from_df", "rvh_lf_select", "rvh_lf_filter", "rvh_lf_limit", "rvh_lf_free", "rvh_lf_collect", "rvh_lf_collect_streaming",
     "rvh_lf_plan_shape",
     "rvh_rb_try_new", "rvh_rb_free", "rvh_rb_num_rows", "rvh_rb_num_columns", "rvh_rb_col_name", "rvh_rb_col_dtype", "rvh_rb_col_export",
-    "rvh_rb_slice", "rvh_rb_select", "rvh_rb_select_by_name", "rvh_rb_filter", "rvh_rb_concat", "rvh_rb_empty_like",
+    "rvh_rb_slice", "rvh_rb_take", "rvh_rb_select", "rvh_rb_select_by_name", "rvh_rb_filter", "rvh_rb_concat", "rvh_rb_empty_like",
     "rvh_sp_memory_source", "rvh_sp_dataframe_source", "rvh_sp_filter", "rvh_sp_select", "rvh_sp_limit", "rvh_sp_free", "rvh_sp_collect",
     "rvh_sp_collect_batches", "rvh_rbv_len", "rvh_rbv_get", "rvh_rbv_free",
 ]
@@ -428,6 +428,11 @@ class RecordBatch:
         return RecordBatch(out.value)
 
     def slice(self, off, length): return self._op(lib().rvh_rb_slice, C.c_int64(off), C.c_int64(length))
+
+    def take(self, idx):
+        """RecordBatch::take (record_batch.rs:108-129)."""
+        a = np.ascontiguousarray(idx, dtype=np.int64)
+        return self._op(lib().rvh_rb_take, _ptr(a, C.c_int64) if a.size else None, C.c_int64(a.size))
 
     def filter(self, predicate_batch: "RecordBatch", predicate_column: int = 0):
         """filter(&self, predicate): the predicate array is column `predicate_column` of `predicate_batch`."""

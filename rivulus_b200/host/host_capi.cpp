@@ -189,6 +189,12 @@ int rvh_rb_col_export(void* rb, int i, ColExport* e) {
 int rvh_rb_slice(void* rb, int64_t off, int64_t len, void** out) {
     return guard([&] { *out = new RbHandle{((RbHandle*)rb)->rb.slice((size_t)off, (size_t)len), {}}; });
 }
+int rvh_rb_take(void* rb, const int64_t* idx, int64_t n, void** out) {
+    return guard([&] {
+        std::vector<size_t> v; for (int64_t i = 0; i < n; ++i) v.push_back((size_t)idx[i]);
+        *out = new RbHandle{((RbHandle*)rb)->rb.take(v), {}};
+    });
+}
 int rvh_rb_select(void* rb, const int32_t* idx, int n, void** out) {
     return guard([&] {
         std::vector<size_t> v; for (int i = 0; i < n; ++i) v.push_back((size_t)idx[i]);

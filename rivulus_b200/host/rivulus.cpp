@@ -463,6 +463,15 @@ RecordBatch RecordBatch::slice(size_t offset, size_t length) const {  // record_
     return adopt(ctx_, schema_, v);
 }
 
+RecordBatch RecordBatch::take(const std::vector<size_t>& indices) const {  // record_batch.rs:108-129
+    std::vector<int64_t> idx(indices.begin(), indices.end());
+    rvl_batch* out = nullptr;
+    const int32_t rc = rvl_batch_take(ctx_->handle(), handle(), idx.data(), (int64_t)idx.size(), &out);
+    if (rc == RVL_OUT_OF_BOUNDS) throw Error(rvl_last_error());  // an Err(String) in the reference, not a panic
+    check(rc);
+    return adopt(ctx_, schema_, out);
+}
+
 RecordBatch RecordBatch::select_columns(const std::vector<size_t>& indices) const {  // record_batch.rs:180-206
     const size_t nc = num_columns();
     auto out_schema = std::make_shared<Schema>();

@@ -229,6 +229,7 @@ class RecordBatch {
     size_t num_columns() const;                                                      // :76
     bool is_empty() const { return num_rows() == 0; }
     RecordBatch slice(size_t offset, size_t length) const;                           // :92-106 (Error{panic} "Slice out of bounds")
+    RecordBatch take(const std::vector<size_t>& indices) const;                      // :108-129 ("Index {} out of bounds for {} rows")
     RecordBatch select_columns(const std::vector<size_t>& indices) const;            // :180-206
     RecordBatch select_columns_by_name(const std::vector<std::string>& names) const; // :208-219
     // filter(&self, predicate: &ArrayRef) :221-243 — the predicate array is column `predicate_column` of `predicate_batch`

@@ -385,3 +385,16 @@ def test_two_pass_ring_depths(slots, per_sm, scan_warps, scan_slots, dense_warps
         run_mask(c, fcols, 1, [2, 0], tag="scan mask")
     finally:
         c.close()
+
+
+# ------------------------------------------------------------------ RecordBatch::take (record_batch.rs:108-178)
+def test_take_matches_reference(ctx):
+    rng = np.random.default_rng(9)
+    n = 10_000
+    cols = [random_col(rng, "i64", n, 0.1, offset=3), random_col(rng, "f64", n, 0.0), random_col(rng, "bool", n, 0.2, offset=7),
+            random_col(rng, "str", n, 0.15, maxlen=20), Col("null", n)]
+    gb, ob = upload(ctx, cols), oracle_batch(cols)
+    for idx in ([], [0], [n - 1, 0, n - 1], rng.integers(0, n, 5000).tolist(), list(range(n - 1, -1, -1))):
+        assert_batches_equal(gb.take(idx), ob.take(idx), f"take {len(idx)} rows")
+    with pytest.raises(capi.RivulusError, match=f"Index {n} out of bounds for {n} rows"):
+        gb.take([0, n, 1])

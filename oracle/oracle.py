@@ -612,3 +612,22 @@ def synth_filter_checksums(n: int, row0: int, pred_kind: int, pred_col_id: int, 
                                             C.c_int64(i), C.c_double(f), len(proj), kinds, ids, threads, C.c_int64(limit),
                                             C.byref(count), sums))
     return count.value, [sums[k] for k in range(len(proj))]
+
+
+def synth_filter_checksums_nulls(n: int, row0: int, pred: tuple, op: str, literal, proj: Sequence[tuple], threads: int = 0, limit: int = -1):
+    """pred = (kind, col_id, null_pct); proj = [(kind, col_id, null_pct)].  Returns (count, checksums, null_counts, string_bytes)
+    of the filtered synthetic table with nulls / strings, straight from the generator (see orc_synth_filter_checksums_nulls)."""
+    if threads <= 0:
+        threads = os.cpu_count() or 1
+    t, i, f, s, sl, b = _lit_args(literal)
+    m = max(len(proj), 1)
+    kinds = (C.c_int * m)(*[p[0] for p in proj])
+    ids = (C.c_uint32 * m)(*[p[1] for p in proj])
+    nulls = (C.c_uint32 * m)(*[p[2] for p in proj])
+    count = C.c_int64()
+    sums = (C.c_uint64 * m)(); nc = (C.c_int64 * m)(); nb = (C.c_int64 * m)()
+    _check(lib().orc_synth_filter_checksums_nulls(C.c_int64(n), C.c_uint64(row0), pred[0], C.c_uint32(pred[1]), C.c_uint32(pred[2]), OPS[op], t,
+                                                  C.c_int64(i), C.c_double(f), len(proj), kinds, ids, nulls, threads, C.c_int64(limit),
+                                                  C.byref(count), sums, nc, nb))
+    k = len(proj)
+    return count.value, [sums[j] for j in range(k)], [nc[j] for j in range(k)], [nb[j] for j in range(k)]

@@ -461,3 +461,80 @@ extern "C" int orc_synth_filter_checksums(int64_t n, uint64_t row0, int pred_kin
         }
     });
 }
+
+// Same, for tables WITH nulls and string columns (BASELINE configs[2] / configs[4] shapes): every column has its own null
+// percentage (rvl_synth_valid); a null predicate row goes through eval_cmp as AnyValue::Null (series.rs:105-107); null
+// survivors contribute the fixed tag kNullTag; strings contribute fold(splitmix64(h ^ byte)) seeded with their length —
+// the definitions rvl_batch_checksum uses on the device.  null_counts_out[c] = null survivors of projected column c.
+extern "C" int orc_synth_filter_checksums_nulls(int64_t n, uint64_t row0, int pred_kind, uint32_t pred_col_id, uint32_t pred_null_pct, int op,
+                                                int lit_tag, int64_t lit_i, double lit_f, int nproj, const int* kinds, const uint32_t* col_ids,
+                                                const uint32_t* null_pcts, int threads, int64_t limit, int64_t* count_out,
+                                                uint64_t* checksums_out, int64_t* null_counts_out, int64_t* str_bytes_out) {
+    return guard([&] {
+        constexpr uint64_t kNullTag = 0x6E756C6C6E756C6Cull;
+        if (threads < 1) threads = 1;
+        const AnyValue lit = lit_tag == 1 ? AnyValue::Int64(lit_i) : (lit_tag == 2 ? AnyValue::Float64(lit_f) : AnyValue::Null());
+        auto keep = [&](uint64_t row) {
+            if (!rvl_synth_valid(RVL_SYNTH_SEED, pred_col_id, row, pred_null_pct)) return eval_cmp(AnyValue::Null(), (BinaryOperator)op, lit);
+            const uint64_t u = rvl_synth_u(RVL_SYNTH_SEED, pred_col_id, row);
+            if (pred_kind == RVL_SYNTH_F64) return eval_cmp(AnyValue::Float64(rvl_synth_f64(u)), (BinaryOperator)op, lit);
+            if (pred_kind == RVL_SYNTH_BOOL) return eval_cmp(AnyValue::Boolean((u & 1) != 0), (BinaryOperator)op, lit);
+            return eval_cmp(AnyValue::Int64(rvl_synth_i64(u, pred_kind)), (BinaryOperator)op, lit);
+        };
+        std::vector<int64_t> counts((size_t)threads, 0);
+        const int64_t per = (n + threads - 1) / threads;
+        {
+            std::vector<std::thread> th;
+            for (int t = 0; t < threads; ++t)
+                th.emplace_back([&, t] {
+                    const int64_t b = std::min<int64_t>(n, per * t), e = std::min<int64_t>(n, per * (t + 1));
+                    int64_t c = 0;
+                    for (int64_t r = b; r < e; ++r) c += keep(row0 + (uint64_t)r) ? 1 : 0;
+                    counts[(size_t)t] = c;
+                });
+            for (auto& x : th) x.join();
+        }
+        std::vector<int64_t> prefix((size_t)threads + 1, 0);
+        for (int t = 0; t < threads; ++t) prefix[(size_t)t + 1] = prefix[(size_t)t] + counts[(size_t)t];
+        const int64_t total = prefix[(size_t)threads];
+        const int64_t cap = limit >= 0 ? std::min(limit, total) : total;
+        std::vector<std::vector<uint64_t>> sums((size_t)threads, std::vector<uint64_t>((size_t)nproj, 0));
+        std::vector<std::vector<int64_t>> nulls((size_t)threads, std::vector<int64_t>((size_t)nproj, 0)), bytes = nulls;
+        {
+            std::vector<std::thread> th;
+            for (int t = 0; t < threads; ++t)
+                th.emplace_back([&, t] {
+                    const int64_t b = std::min<int64_t>(n, per * t), e = std::min<int64_t>(n, per * (t + 1));
+                    int64_t rank = prefix[(size_t)t];
+                    for (int64_t r = b; r < e && rank < cap; ++r) {
+                        const uint64_t row = row0 + (uint64_t)r;
+                        if (!keep(row)) continue;
+                        for (int c = 0; c < nproj; ++c) {
+                            uint64_t bits;
+                            if (!rvl_synth_valid(RVL_SYNTH_SEED, col_ids[c], row, null_pcts[c])) { bits = kNullTag; nulls[(size_t)t][(size_t)c]++; }
+                            else {
+                                const uint64_t u = rvl_synth_u(RVL_SYNTH_SEED, col_ids[c], row);
+                                if (kinds[c] == RVL_SYNTH_F64) { const double d = rvl_synth_f64(u); std::memcpy(&bits, &d, 8); }
+                                else if (kinds[c] == RVL_SYNTH_BOOL) bits = u & 1ull;
+                                else if (kinds[c] == RVL_SYNTH_STR) {
+                                    const uint32_t len = rvl_synth_strlen(u);
+                                    uint64_t h = len;
+                                    for (uint32_t j = 0; j < len; ++j) h = rvl_splitmix64(h ^ (uint64_t)rvl_synth_strbyte(u, j));
+                                    bits = h; bytes[(size_t)t][(size_t)c] += len;
+                                } else bits = (uint64_t)rvl_synth_i64(u, kinds[c]);
+                            }
+                            sums[(size_t)t][(size_t)c] += rvl_checksum_term(bits, (uint64_t)rank);
+                        }
+                        ++rank;
+                    }
+                });
+            for (auto& x : th) x.join();
+        }
+        *count_out = cap;
+        for (int c = 0; c < nproj; ++c) {
+            uint64_t s = 0; int64_t nc = 0, nb = 0;
+            for (int t = 0; t < threads; ++t) { s += sums[(size_t)t][(size_t)c]; nc += nulls[(size_t)t][(size_t)c]; nb += bytes[(size_t)t][(size_t)c]; }
+            checksums_out[c] = s; null_counts_out[c] = nc; str_bytes_out[c] = nb;
+        }
+    });
+}

@@ -1,0 +1,98 @@
+"""The full-size property oracle (survivor count + order-sensitive checksums straight from the counter-based generator,
+with nulls and strings) is itself checked against the eager oracle engine on small tables (CPU), then used on the GPU at
+BASELINE configs[2] / configs[4] shapes (strings + 10 % nulls; Int64/Float64/Boolean with the predicate column projected)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from rivulus_b200 import capi
+
+M64 = (1 << 64) - 1
+GOLDEN = 0x9E3779B97F4A7C15
+NULL_TAG = 0x6E756C6C6E756C6C
+
+
+def splitmix64(x):
+    x = (x + GOLDEN) & M64
+    z = x
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M64
+    return z ^ (z >> 31)
+
+
+def term(bits, pos):
+    return splitmix64((bits + (pos + 1) * GOLDEN) & M64)
+
+
+def column_checksum(values):
+    s = 0
+    for i, v in enumerate(values):
+        if v is None: bits = NULL_TAG
+        elif isinstance(v, bool): bits = int(v)
+        elif isinstance(v, int): bits = v & M64
+        elif isinstance(v, float): bits = int(np.float64(v).view(np.uint64))
+        else:
+            b = v.encode()
+            h = len(b)
+            for ch in b:
+                h = splitmix64(h ^ ch)
+            bits = h
+        s = (s + term(bits, i)) & M64
+    return s
+
+
+@pytest.mark.parametrize("op,lit", [(">", 700.0), ("<", 150.0), ("!=", 3.0), (">=", None)])
+def test_synth_checksum_oracle_matches_eager_engine(op, lit):
+    n, row0 = 4000, 12345
+    spec = [("x", capi.SYNTH_F64, 0, 10), ("name", capi.SYNTH_STR, 1, 10), ("v", capi.SYNTH_I64, 2, 10), ("f", capi.SYNTH_BOOL, 3, 10)]
+    df = O.DataFrame.synth(spec, n, row0=row0)
+    meth = {">": "gt", "<": "lt", "!=": "neq", ">=": "gte"}[op]
+    out = O.LazyFrame.from_dataframe(df).filter(getattr(O.col("x"), meth)(O.lit(lit))).collect()
+    count, sums, nulls, nbytes = O.synth_filter_checksums_nulls(n, row0, (capi.SYNTH_F64, 0, 10), op, lit,
+                                                                [(s[1], s[2], s[3]) for s in spec], threads=3)
+    assert count == out.height()
+    for j, (name, *_rest) in enumerate(spec):
+        vals = out.column(name)
+        assert sums[j] == column_checksum(vals), name
+        assert nulls[j] == sum(v is None for v in vals), name
+    assert nbytes[1] == sum(len(v) for v in out.column("name") if v is not None)
+
+
+def _gpu_check(ctx, n, row0, pred, op, lit, proj_spec, limit=-1):
+    spec = [pred] + list(proj_spec)
+    gb = ctx.gen_batch(spec, n, row0)
+    got = ctx.filter_project(gb, capi.predicate(0, op, lit), list(range(len(spec))), limit)   # the predicate column is projected too
+    count, sums, nulls, nbytes = O.synth_filter_checksums_nulls(n, row0, pred, op, lit, spec, limit=limit)
+    assert got.num_rows() == count
+    for j in range(len(spec)):
+        v = got.view(j)
+        assert v.null_count == nulls[j], f"column {j} null count"
+        assert (v.validity is not None) == (nulls[j] > 0), f"column {j}: bitmap present iff a survivor is null"
+        assert got.checksum(j) == sums[j], f"column {j} checksum"
+        if spec[j][0] == capi.SYNTH_STR:
+            assert v.data_len == nbytes[j]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("plan", [capi.PLAN_FUSED, capi.PLAN_TWO_PASS])
+@pytest.mark.parametrize("op,lit", [(">", 900.0), (">", 500.0), ("<", 100.0)])
+def test_config3_strings_and_nulls_at_scale(plan, op, lit):
+    """configs[2] shape: filter on Float64, project a variable-length StringArray (avg 24 B) and an Int64, 10 % nulls everywhere."""
+    ctx = capi.Context(0)
+    ctx.set_option(capi.OPT_PLAN, plan)
+    try:
+        _gpu_check(ctx, 6_000_000, 7_000_000_000, (capi.SYNTH_F64, 0, 10), op, lit, [(capi.SYNTH_STR, 1, 10), (capi.SYNTH_I64, 2, 10)])
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("op,lit,limit", [(">", 899, -1), (">", 499, -1), ("<=", 99, -1), (">", 499, 1_000_000)])
+def test_config5_int_float_bool_at_scale(op, lit, limit):
+    """configs[4] shape (one shard): {k: Int64, v: Float64, f: Boolean}, every column projected, row range deep inside a 4 B-row table."""
+    ctx = capi.Context(0)
+    try:
+        _gpu_check(ctx, 48_000_000, 3_500_000_000, (capi.SYNTH_KEY1000, 0, 0), op, lit, [(capi.SYNTH_F64, 1, 0), (capi.SYNTH_BOOL, 2, 0)], limit)
+        _gpu_check(ctx, 16_000_000, 3_500_000_000, (capi.SYNTH_KEY1000, 0, 5), op, lit, [(capi.SYNTH_F64, 1, 5), (capi.SYNTH_BOOL, 2, 5)], limit)
+    finally:
+        ctx.close()

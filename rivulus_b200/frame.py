@@ -39,7 +39,7 @@ OPS = {"+": 0, "-": 1, "*": 2, "/": 3, "==": 4, "!=": 5, "<": 6, ">": 7, "<=": 8
 HOST_SYMBOLS = [
     "rvh_last_error", "rvh_launch_count",
     "rvh_dfb_new", "rvh_dfb_add_series", "rvh_dfb_add_empty_series", "rvh_dfb_add_i64", "rvh_dfb_add_f64", "rvh_dfb_add_bool_bits",
-    "rvh_dfb_add_strings", "rvh_dfb_finish", "rvh_df_free", "rvh_df_width", "rvh_df_height", "rvh_df_col_name", "rvh_df_col_dtype",
+    "rvh_dfb_add_strings", "rvh_dfb_finish", "rvh_synth_df", "rvh_df_free", "rvh_df_width", "rvh_df_height", "rvh_df_col_name", "rvh_df_col_dtype",
     "rvh_df_col_len", "rvh_df_col_str_bytes", "rvh_df_col_export", "rvh_df_col_buffers",
     "rvh_expr_col", "rvh_expr_lit", "rvh_expr_binary", "rvh_expr_alias", "rvh_expr_free",
     "rvh_lf_from_df", "rvh_lf_select", "rvh_lf_filter", "rvh_lf_limit", "rvh_lf_free", "rvh_lf_collect", "rvh_lf_collect_streaming",
@@ -203,6 +203,18 @@ class DataFrame:
             _check(rc)
         out = C.c_void_p()
         _check(L.rvh_dfb_finish(_vp(b), C.byref(out)))
+        return DataFrame(out.value)
+
+    @staticmethod
+    def synth(cols: Sequence[tuple], n: int, row0: int = 0) -> "DataFrame":
+        """cols: [(name, kind, col_id, null_pct)] from include/rivulus_synth.h's counter-based generator (BASELINE configs)."""
+        L = lib()
+        names = (C.c_char_p * len(cols))(*[c[0].encode() for c in cols])
+        kinds = (C.c_int * len(cols))(*[c[1] for c in cols])
+        ids = (C.c_uint32 * len(cols))(*[c[2] for c in cols])
+        nulls = (C.c_uint32 * len(cols))(*[c[3] for c in cols])
+        out = C.c_void_p()
+        _check(L.rvh_synth_df(len(cols), names, kinds, ids, nulls, C.c_uint64(row0), C.c_int64(n), C.byref(out)))
         return DataFrame(out.value)
 
     def width(self):

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 
+#include "../../include/rivulus_synth.h"
 #include "rivulus.hpp"
 
 using namespace rivulus;
@@ -78,6 +79,61 @@ int rvh_dfb_finish(void* h, void** out) {
     int rc = guard([&] { *out = new DataFrame(DataFrame::make(std::move(b->cols))); });
     delete b;
     return rc;
+}
+// Synthetic DataFrame from the counter-based generator of include/rivulus_synth.h (BASELINE configs): columns are
+// built directly in Arrow layout.  kinds[] = rvl_synth_kind, null_pct per column.
+int rvh_synth_df(int ncols, const char** names, const int* kinds, const uint32_t* col_ids, const uint32_t* null_pct, uint64_t row0, int64_t n,
+                 void** out) {
+    return guard([&] {
+        std::vector<Series> cols;
+        for (int c = 0; c < ncols; ++c) {
+            std::vector<uint8_t> validity;
+            if (null_pct[c] > 0) {
+                validity.assign((size_t)(n + 7) / 8, 0);
+                for (int64_t r = 0; r < n; ++r)
+                    if (rvl_synth_valid(RVL_SYNTH_SEED, col_ids[c], row0 + (uint64_t)r, null_pct[c])) validity[(size_t)r >> 3] |= (uint8_t)(1u << (r & 7));
+            }
+            auto valid = [&](int64_t r) { return validity.empty() || ((validity[(size_t)r >> 3] >> (r & 7)) & 1); };
+            switch (kinds[c]) {
+                case RVL_SYNTH_KEY1000: case RVL_SYNTH_I64: case RVL_SYNTH_AGE100: {
+                    std::vector<int64_t> v((size_t)n);
+                    for (int64_t r = 0; r < n; ++r) v[(size_t)r] = rvl_synth_i64(rvl_synth_u(RVL_SYNTH_SEED, col_ids[c], row0 + (uint64_t)r), kinds[c]);
+                    cols.push_back(Series::from_i64(names[c], std::move(v), std::move(validity)));
+                    break;
+                }
+                case RVL_SYNTH_F64: {
+                    std::vector<double> v((size_t)n);
+                    for (int64_t r = 0; r < n; ++r) v[(size_t)r] = rvl_synth_f64(rvl_synth_u(RVL_SYNTH_SEED, col_ids[c], row0 + (uint64_t)r));
+                    cols.push_back(Series::from_f64(names[c], std::move(v), std::move(validity)));
+                    break;
+                }
+                case RVL_SYNTH_BOOL: {
+                    std::vector<uint8_t> bits((size_t)(n + 7) / 8, 0);
+                    for (int64_t r = 0; r < n; ++r)
+                        if (rvl_synth_u(RVL_SYNTH_SEED, col_ids[c], row0 + (uint64_t)r) & 1ull) bits[(size_t)r >> 3] |= (uint8_t)(1u << (r & 7));
+                    cols.push_back(Series::from_bool_bits(names[c], std::move(bits), (size_t)n, std::move(validity)));
+                    break;
+                }
+                case RVL_SYNTH_STR: {
+                    std::vector<int32_t> off((size_t)n + 1, 0);
+                    std::vector<uint8_t> data;
+                    data.reserve((size_t)n * 24);
+                    for (int64_t r = 0; r < n; ++r) {
+                        if (valid(r)) {
+                            const uint64_t u = rvl_synth_u(RVL_SYNTH_SEED, col_ids[c], row0 + (uint64_t)r);
+                            const uint32_t len = rvl_synth_strlen(u);
+                            for (uint32_t j = 0; j < len; ++j) data.push_back(rvl_synth_strbyte(u, j));
+                        }
+                        off[(size_t)r + 1] = (int32_t)data.size();
+                    }
+                    cols.push_back(Series::from_strings(names[c], std::move(off), std::move(data), std::move(validity)));
+                    break;
+                }
+                default: throw Error("unknown synthetic column kind");
+            }
+        }
+        *out = new DataFrame(DataFrame::make(std::move(cols)));
+    });
 }
 void rvh_df_free(void* df) { delete (DataFrame*)df; }
 int rvh_df_width(void* df) { return (int)((DataFrame*)df)->width(); }

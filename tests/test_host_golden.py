@@ -203,3 +203,35 @@ def test_random_streaming_queries_match_oracle(seed):
         want = _outcome(O, O.OracleError, build)
         got = _outcome(F, F.RivulusError, build)
         assert got == want, (seed, q, sel, lim, fcol, shape)
+
+
+# ------------------------------------------------------------------ BASELINE configs[0] at full size through the user API
+def test_config1_dataframe_ingest_matches_oracle_cpu():
+    """Host side only: the synthetic configs[0] DataFrame built columnar by the host layer equals the oracle's AnyValue DataFrame."""
+    from oracle import oracle as O
+    spec = [("name", capi.SYNTH_STR, 0, 0), ("age", capi.SYNTH_AGE100, 1, 0), ("x", capi.SYNTH_F64, 2, 10), ("f", capi.SYNTH_BOOL, 3, 10)]
+    a, b = F.DataFrame.synth(spec, 3000, row0=77), O.DataFrame.synth(spec, 3000, row0=77)
+    assert a.dtypes() == b.dtypes() and _canon(a.to_dict()) == _canon(b.to_dict())
+
+
+@pytest.mark.gpu
+def test_config1_one_million_rows_select_name_where_age_gt_25():
+    """configs[0]: 1 M-row {name: String, age: Int64}; SELECT name WHERE age > 25, issued filter-then-select (SURVEY S4);
+    collect() on the GPU must equal the reference engine's result row for row."""
+    from oracle import oracle as O
+    spec = [("name", capi.SYNTH_STR, 0, 0), ("age", capi.SYNTH_AGE100, 1, 0)]
+    n = 1_000_000
+
+    def q(mod):
+        return mod.LazyFrame.from_dataframe(mod.DataFrame.synth(spec, n)).filter(mod.col("age").gt(mod.lit(25))).select([mod.col("name")]).collect()
+
+    got, want = q(F), q(O)
+    assert (got.height(), got.column_names(), got.dtypes()) == (want.height(), want.column_names(), want.dtypes())
+    assert 0.73 * n < got.height() < 0.75 * n
+    gt, gi, gf, gb, goff, gdata = got.column_raw(0)
+    wt, wi, wf, wb, woff, wdata = want.column_raw(0)
+    assert np.array_equal(gt, wt) and np.array_equal(goff, woff) and np.array_equal(gdata, wdata)
+    # the README spelling (select then filter) fails validation in both (logical_plan/plan.rs:139-146)
+    for mod, err in ((F, F.RivulusError), (O, O.OracleError)):
+        with pytest.raises(err, match="Logical plan error: Column not found: 'age'"):
+            mod.LazyFrame.from_dataframe(mod.DataFrame.synth(spec, 1000)).select([mod.col("name")]).filter(mod.col("age").gt(mod.lit(25))).collect()

@@ -96,3 +96,47 @@ def test_config5_int_float_bool_at_scale(op, lit, limit):
         _gpu_check(ctx, 16_000_000, 3_500_000_000, (capi.SYNTH_KEY1000, 0, 5), op, lit, [(capi.SYNTH_F64, 1, 5), (capi.SYNTH_BOOL, 2, 5)], limit)
     finally:
         ctx.close()
+
+
+@pytest.mark.gpu
+def test_full_size_one_billion_rows_properties():
+    """BASELINE configs[1] at its full size (10^9 rows x {k, a, b, c, d}): exact count + order-sensitive checksums from the oracle at
+    0.1 %, and size-independent properties at 50 %: complement counts add up to N, both execution plans agree bit for bit
+    (checksums of every projected column), filtering the result again with the same predicate keeps every row (idempotence),
+    and the ordered concatenation of two row-range shards equals the whole."""
+    n = 1_000_000_000
+    spec = [(capi.SYNTH_KEY1000, 0, 0), (capi.SYNTH_I64, 1, 0), (capi.SYNTH_F64, 2, 0), (capi.SYNTH_I64, 3, 0), (capi.SYNTH_F64, 4, 0)]
+    ctx = capi.Context(0)
+    try:
+        table = ctx.gen_batch(spec, n)
+        # exact, against the generator-derived oracle
+        out = ctx.filter_project(table, capi.predicate(0, ">", 998), [1, 2, 3, 4])
+        count, sums = O.synth_filter_checksums(n, 0, capi.SYNTH_KEY1000, 0, ">", 998, [(s[0], s[1]) for s in spec[1:]])
+        assert out.num_rows() == count and [out.checksum(j) for j in range(4)] == sums
+        out.release()
+        # properties at 50 %
+        res = {}
+        for plan in (capi.PLAN_TWO_PASS, capi.PLAN_FUSED):
+            ctx.set_option(capi.OPT_PLAN, plan)
+            o = ctx.filter_project(table, capi.predicate(0, ">", 499), [0, 1, 2, 3, 4])
+            res[plan] = (o.num_rows(), [o.checksum(j) for j in range(5)])
+            if plan == capi.PLAN_FUSED:
+                again = ctx.filter_project(o, capi.predicate(0, ">", 499), [0, 1, 2, 3, 4])
+                assert (again.num_rows(), [again.checksum(j) for j in range(5)]) == res[plan]      # idempotent
+                again.release()
+            o.release()
+        assert res[capi.PLAN_TWO_PASS] == res[capi.PLAN_FUSED]
+        ctx.set_option(capi.OPT_PLAN, capi.PLAN_AUTO)
+        comp = ctx.filter_project(table, capi.predicate(0, "<=", 499), [0])
+        assert comp.num_rows() + res[capi.PLAN_FUSED][0] == n
+        comp.release()
+        # two row-range shards (rvl_shard_range), concatenated in rank order, equal the whole (checked on the narrow 10 % query)
+        whole = ctx.filter_project(table, capi.predicate(0, ">", 899), [2])
+        parts = []
+        for r in range(2):
+            b, e = capi.shard_range(n, r, 2)
+            parts.append(ctx.filter_project(table.slice(b, e - b), capi.predicate(0, ">", 899), [2]))
+        cat = ctx.concat(parts)
+        assert cat.num_rows() == whole.num_rows() and cat.checksum(0) == whole.checksum(0)
+    finally:
+        ctx.close()

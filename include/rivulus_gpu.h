@@ -88,7 +88,11 @@ typedef struct rvl_predicate {
     const uint8_t* lit_str; /* host pointer, not NUL-terminated */
     int64_t lit_str_len;
     int32_t lit_bool;
-    int32_t reserved;
+    /* 0 = the predicate column is a plain array.  k + 1 = Boolean column k of the input batch tags the rows of a Float64-dtype
+     * Series whose value is an AnyValue::Int64 (datatypes/series.rs:210-212 lets Int64 and Float64 share a Series): for tagged
+     * rows `values` holds the int64 bit pattern and the row compares as an Int64 — i.e. against a Float64 literal it is a
+     * different type and only != holds (series.rs:95,114); CMP_LITERAL mode, Float64-typed predicate column only. */
+    int32_t tag_column;
 } rvl_predicate;
 
 typedef struct rvl_ctx rvl_ctx;       /* one per GPU: stream, memory pool, scratch, pinned mailbox */
@@ -155,6 +159,9 @@ int32_t rvl_batch_column(const rvl_batch* batch, int32_t i, rvl_column* view);
  * values length*8 bytes (or ceil(length/8) for Boolean), validity ceil(length/8) if the view has one, offsets
  * (length+1)*4, data data_len).  The copy is rebased to offset 0 like the reference's freshly built outputs. */
 int32_t rvl_batch_download_column(rvl_ctx* ctx, const rvl_batch* batch, int32_t i, rvl_column* dst);
+
+/* BooleanArray::count_true (array/boolean.rs: count_true): rows of Boolean column i that are Some(true) */
+int32_t rvl_batch_count_true(rvl_ctx* ctx, const rvl_batch* batch, int32_t i, int64_t* count);
 
 /* RecordBatch::slice (record_batch.rs:92-106): zero-copy view; RVL_OUT_OF_BOUNDS instead of the panic */
 int32_t rvl_batch_slice(const rvl_batch* batch, int64_t offset, int64_t length, rvl_batch** view);

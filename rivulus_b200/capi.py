@@ -41,7 +41,7 @@ class RvlColumn(C.Structure):
 class RvlPredicate(C.Structure):
     _fields_ = [("mode", C.c_int32), ("column", C.c_int32), ("op", C.c_int32), ("lit_dtype", C.c_int32),
                 ("lit_i64", C.c_int64), ("lit_f64", C.c_double), ("lit_str", C.c_char_p), ("lit_str_len", C.c_int64),
-                ("lit_bool", C.c_int32), ("reserved", C.c_int32)]
+                ("lit_bool", C.c_int32), ("tag_column", C.c_int32)]
 
 
 class RvlStreamConfig(C.Structure):
@@ -66,7 +66,7 @@ ABI_SYMBOLS = [
     "rvl_ctx_profile_enable", "rvl_ctx_profile_read", "rvl_ctx_profile_read_launches", "rvl_ctx_set_option",
     "rvl_host_alloc", "rvl_host_free",
     "rvl_batch_upload", "rvl_batch_wrap_device", "rvl_batch_release", "rvl_batch_num_rows", "rvl_batch_num_columns",
-    "rvl_batch_column", "rvl_batch_download_column", "rvl_batch_slice", "rvl_batch_select", "rvl_batch_take", "rvl_batch_concat",
+    "rvl_batch_column", "rvl_batch_download_column", "rvl_batch_count_true", "rvl_batch_slice", "rvl_batch_select", "rvl_batch_take", "rvl_batch_concat",
     "rvl_filter_project", "rvl_predicate_mask", "rvl_filter_project_launch", "rvl_filter_project_finish",
     "rvl_stream_open", "rvl_stream_push", "rvl_stream_next", "rvl_stream_limit_reached", "rvl_stream_collect",
     "rvl_stream_stats", "rvl_stream_close",
@@ -336,6 +336,12 @@ class Batch:
         v = RvlColumn()
         check(lib().rvl_batch_column(self._h, i, C.byref(v)))
         return v
+
+    def count_true(self, i: int) -> int:
+        """BooleanArray::count_true of column i."""
+        n = C.c_int64()
+        check(lib().rvl_batch_count_true(self.ctx._h, self._h, i, C.byref(n)))
+        return n.value
 
     def slice(self, offset: int, length: int) -> "Batch":
         out = C.c_void_p()

@@ -58,6 +58,30 @@ static int lower_predicate(const CoreRef& core, const rvl_batch* in, const rvl_p
     const uint32_t truth = truth_of(pred->op);
     if (truth == 0u) return fail(RVL_INVALID_OPERATION, "Invalid operation: operator " + std::to_string(pred->op) + " is not a comparison");  // plan.rs:121-127
 
+    if (pred->tag_column != 0) {
+        // Float64-dtype Series holding Int64 values: evaluate row by row with the row's own type, into a bitmap
+        const int32_t tc = pred->tag_column - 1;
+        if (tc < 0 || tc >= (int32_t)in->cols.size()) return fail(RVL_COLUMN_NOT_FOUND, "Column not found: tag index " + std::to_string(tc));
+        const DevColumn& t = in->cols[tc];
+        if (t.dtype != RVL_BOOLEAN || c.dtype != RVL_FLOAT64) return fail(RVL_TYPE_MISMATCH, "tag_column needs a Float64 predicate column and a Boolean tag column");
+        RVL_TRY(dev_alloc_zeroed(core, (size_t)((n + 63) / 64) * 8, &pp->tmp_bits));
+        int lit_kind = 3;
+        int64_t lit_bits = 0;
+        if (pred->lit_dtype == RVL_NULL) lit_kind = 0;
+        else if (pred->lit_dtype == RVL_INT64) { lit_kind = 1; lit_bits = pred->lit_i64; }
+        else if (pred->lit_dtype == RVL_FLOAT64) { lit_kind = 2; std::memcpy(&lit_bits, &pred->lit_f64, 8); }
+        if (n > 0) {
+            mixed_predicate_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, core->stream>>>(
+                n, (const uint64_t*)c.values->ptr + c.offset, pp->valid, bitsrc_of(t.values, t.offset, n), lit_kind, lit_bits, truth,
+                (uint32_t*)pp->tmp_bits->ptr);
+            core->launches++;
+            RVL_CUDA_TRY(cudaGetLastError());
+        }
+        pp->kind = kPredBits; pp->pb_vals = bitsrc_of(pp->tmp_bits, 0, n); pp->pb_a = 1; pp->pb_b = 0; pp->keep_null = 0;
+        pp->valid = BitSrc{nullptr, 0, 0};
+        return RVL_OK;
+    }
+
     // constant result on valid rows / on null rows, per the truth table
     auto constant = [&](uint32_t on_valid, uint32_t on_null) {
         pp->kind = kPredBits; pp->pb_vals = BitSrc{nullptr, 0, 0}; pp->pb_a = 0; pp->pb_b = on_valid; pp->keep_null = on_null;

@@ -441,6 +441,37 @@ int32_t rvl_batch_download_column(rvl_ctx* ctx, const rvl_batch* batch, int32_t 
     return RVL_OK;
 }
 
+int32_t rvl_batch_count_true(rvl_ctx* ctx, const rvl_batch* batch, int32_t i, int64_t* count) {
+    if (!ctx || !batch || !count) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    if (i < 0 || i >= (int32_t)batch->cols.size())
+        return fail(RVL_OUT_OF_BOUNDS, "Column index " + std::to_string(i) + " out of bounds for " + std::to_string(batch->cols.size()) + " columns");
+    const DevColumn& c = batch->cols[i];
+    if (c.dtype != RVL_BOOLEAN) return fail(RVL_TYPE_MISMATCH, std::string("Column ") + std::to_string(i) + " has type " + dtype_name(c.dtype) + " but count_true expects Boolean");
+    const CoreRef& core = batch->core;
+    RVL_CUDA_TRY(cudaSetDevice(core->device));
+    *count = 0;
+    if (c.length == 0) return RVL_OK;
+    BufRef counter, tmp;
+    RVL_TRY(dev_alloc_zeroed(core, 8, &counter));
+    BitSrc src = bitsrc_of(c.values, c.offset, c.length);
+    if (c.validity) {
+        // values AND validity, rebased to bit 0 (a null is never Some(true))
+        RVL_TRY(dev_alloc_zeroed(core, (size_t)((c.length + 63) / 64) * 8, &tmp));
+        bitcopy_kernel<<<grid_for((c.length + 31) / 32 + 1, 256, core->sm_count), 256, 0, core->stream>>>(
+            src, bitsrc_of(c.validity, c.offset, c.length), (uint32_t*)tmp->ptr, 0, c.length);
+        core->launches++;
+        src = bitsrc_of(tmp, 0, c.length);
+    }
+    count_ones_kernel<<<grid_for((c.length + 31) / 32, 256, core->sm_count), 256, 0, core->stream>>>(src, c.length, nullptr, nullptr, -1,
+                                                                                                      (unsigned long long*)counter->ptr);
+    core->launches++;
+    RVL_CUDA_TRY(cudaGetLastError());
+    RVL_CUDA_TRY(cudaMemcpyAsync(core->mailbox, counter->ptr, 8, cudaMemcpyDeviceToHost, core->stream));
+    RVL_CUDA_TRY(cudaStreamSynchronize(core->stream));
+    *count = (int64_t)core->mailbox[0];
+    return RVL_OK;
+}
+
 int32_t rvl_batch_slice(const rvl_batch* batch, int64_t offset, int64_t length, rvl_batch** view) {
     if (!batch || !view) return fail(RVL_INVALID_ARGUMENT, "null argument");
     if (offset < 0 || length < 0 || offset + length > batch->num_rows) return fail(RVL_OUT_OF_BOUNDS, "Slice out of bounds");  // record_batch.rs:93

@@ -176,4 +176,34 @@ static __global__ void __launch_bounds__(kBlock) string_predicate_kernel(int64_t
     if ((threadIdx.x & 31) == 0 && (row - (row & 31)) < ((n_rows + 63) & ~63ll)) out_words[row >> 5] = w;
 }
 
+// Predicate over a Float64-dtype Series that also holds Int64 values (series.rs:210-212): per row the tag bit says which
+// AnyValue variant `values` holds; the truth table of plan.rs:112-130 is applied with the row's own type.
+// lit_kind: 0 = Null literal, 1 = Int64, 2 = Float64, 3 = any other type.  Output: final keep bits (null rule included).
+static __global__ void __launch_bounds__(kBlock) mixed_predicate_kernel(int64_t n_rows, const uint64_t* __restrict__ values, BitSrc valid, BitSrc tag,
+                                                                        int lit_kind, int64_t lit_bits, uint32_t truth,
+                                                                        uint32_t* __restrict__ out_words) {
+    const int64_t row = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    bool keep = false;
+    if (row < n_rows) {
+        bool ok = true;
+        if (valid.words != nullptr) { const uint64_t bit = valid.bit0 + (uint64_t)row; ok = (__ldg(valid.words + (bit >> 5)) >> (bit & 31)) & 1u; }
+        uint32_t code;
+        if (!ok) code = lit_kind == 0 ? 2u : 1u;          // Null vs Null: Equal; Null vs value: Less (series.rs:105-106)
+        else if (lit_kind == 0) code = 4u;                // value vs Null: Greater (series.rs:107)
+        else {
+            bool is_int = false;
+            if (tag.words != nullptr) { const uint64_t bit = tag.bit0 + (uint64_t)row; is_int = (__ldg(tag.words + (bit >> 5)) >> (bit & 31)) & 1u; }
+            const uint64_t v = values[row];
+            if (is_int && lit_kind == 1) { const int64_t a = (int64_t)v; code = a < lit_bits ? 1u : (a == lit_bits ? 2u : 4u); }
+            else if (!is_int && lit_kind == 2) {
+                const double a = __longlong_as_double((long long)v), b = __longlong_as_double(lit_bits);
+                code = a < b ? 1u : (a == b ? 2u : (a > b ? 4u : 8u));
+            } else code = 8u;                             // different non-null types never compare (series.rs:95,114)
+        }
+        keep = (truth & code) != 0u;
+    }
+    const uint32_t w = __ballot_sync(0xFFFFFFFFu, keep);
+    if ((threadIdx.x & 31) == 0 && (row - (row & 31)) < ((n_rows + 63) & ~63ll)) out_words[row >> 5] = w;
+}
+
 }  // namespace rvl

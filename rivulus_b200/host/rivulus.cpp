@@ -131,10 +131,13 @@ Series Series::make(const std::string& name, const std::vector<AnyValue>& data) 
         case DataType::Float64: {
             s.f64_.resize(n);
             const bool mixed = saw_int;
-            if (mixed) { s.int_tag_.assign(n, 0); s.int_vals_.assign(n, 0); }
+            if (mixed) s.int_tag_.assign((n + 7) / 8, 0);
             for (size_t i = 0; i < n; ++i) {
                 if (data[i].tag == AnyValue::kFloat64) s.f64_[i] = data[i].f;
-                else { s.f64_[i] = 0.0; if (data[i].tag == AnyValue::kInt64) { s.int_tag_[i] = 1; s.int_vals_[i] = data[i].i; } }
+                else {
+                    s.f64_[i] = 0.0;
+                    if (data[i].tag == AnyValue::kInt64) { set_bit(s.int_tag_, i); std::memcpy(&s.f64_[i], &data[i].i, 8); }
+                }
             }
             break;
         }
@@ -222,7 +225,7 @@ AnyValue Series::at(size_t i) const {  // series.rs:273-288
     switch (dtype_) {
         case DataType::Int64: return AnyValue::Int64(i64_[i]);
         case DataType::Float64:
-            if (!int_tag_.empty() && int_tag_[i]) return AnyValue::Int64(int_vals_[i]);
+            if (!int_tag_.empty() && get_bit(int_tag_, i)) { int64_t v; std::memcpy(&v, &f64_[i], 8); return AnyValue::Int64(v); }
             return AnyValue::Float64(f64_[i]);
         case DataType::Boolean: return AnyValue::Boolean(get_bit(bits_, i));
         case DataType::String: return AnyValue::String(std::string(data_.begin() + offsets_[i], data_.begin() + offsets_[i + 1]));
@@ -280,6 +283,30 @@ rvl_column Series::as_column(size_t offset, size_t length, bool flatten_nulls) c
         case DataType::Null: break;
     }
     return c;
+}
+
+rvl_column Series::tag_column(size_t offset, size_t length) const {
+    rvl_column c{};
+    c.dtype = RVL_BOOLEAN; c.location = RVL_HOST; c.length = (int64_t)length; c.offset = (int64_t)offset;
+    c.values = int_tag_.data();
+    return c;
+}
+
+Series Series::from_mixed(const std::string& name, const rvl_column& v, const rvl_column& t, DataType dtype) {
+    const size_t n = (size_t)v.length;
+    if (n == 0 || dtype == DataType::Null) { rvl_column c = v; if (dtype == DataType::Null) { c.dtype = RVL_NULL; c.null_count = c.length; } return from_column(name, c, dtype); }
+    Series s; s.name_ = name; s.len_ = n; s.dtype_ = dtype;
+    if (v.validity != nullptr && v.null_count > 0) s.validity_.assign(v.validity, v.validity + (n + 7) / 8);
+    const uint8_t* tags = (const uint8_t*)t.values;
+    if (dtype == DataType::Int64) {  // only Int64 survivors: an ordinary Int64 series
+        s.i64_.assign((const int64_t*)v.values, (const int64_t*)v.values + n);
+        return s;
+    }
+    s.f64_.assign((const double*)v.values, (const double*)v.values + n);
+    bool any_int = false;
+    for (size_t i = 0; i < (n + 7) / 8; ++i) any_int |= tags[i] != 0;
+    if (any_int) s.int_tag_.assign(tags, tags + (n + 7) / 8);
+    return s;
 }
 
 Series Series::from_column(const std::string& name, const rvl_column& c, DataType dtype_if_empty) {
@@ -932,9 +959,10 @@ static void check_lowering(const LogicalPlan& p) {  // logical_to_physical runs 
 namespace {
 // A DataFrame living on the device: the eager engine's intermediate result.
 struct Frame {
-    RecordBatch rb;                    // default-constructed when the frame has no columns
+    RecordBatch rb;                    // default-constructed when the frame has no columns; visible columns first, then hidden tags
     std::vector<std::string> names;
     std::vector<DataType> dtypes;      // eager dtype of each column (may be Null while the device array is typed)
+    std::vector<int> tag_col;          // per visible column: index in `rb` of its hidden Int64-tag column (mixed series), or -1
     size_t rows = 0;
 };
 
@@ -945,13 +973,18 @@ Frame upload_frame(const ContextRef& ctx, const DataFrame& df) {
     auto schema = std::make_shared<Schema>();
     std::vector<rvl_column> cols;
     for (const auto& s : df.columns()) {
-        if (s.is_mixed())
-            throw Error("General execution error: column '" + s.name() + "' holds Int64 values inside a Float64 series; "
-                        "mixed series are not supported by the GPU engine");
         schema->fields.push_back(Field{s.name(), exec_type_of(s.dtype()), true});
         cols.push_back(s.as_column(0, s.len(), /*flatten_nulls=*/false));
         f.names.push_back(s.name());
         f.dtypes.push_back(s.dtype());
+        f.tag_col.push_back(-1);
+    }
+    for (size_t i = 0; i < df.columns().size(); ++i) {  // hidden tag columns of mixed Float64/Int64 series
+        const Series& s = df.columns()[i];
+        if (!s.is_mixed()) continue;
+        f.tag_col[i] = (int)cols.size();
+        schema->fields.push_back(Field{"__int64_tag(" + s.name() + ")", ExecType::Boolean, true});
+        cols.push_back(s.tag_column(0, s.len()));
     }
     f.rb = RecordBatch::try_new(ctx, schema, cols);
     return f;
@@ -972,15 +1005,29 @@ DataFrame download_frame(const Frame& f) {
             default: break;
         }
         if (f.dtypes[i] == DataType::Null && a.length > 0) { c.dtype = RVL_NULL; c.null_count = a.length; }
+        if (f.tag_col[i] >= 0 && a.length > 0) {
+            ArrayData t = f.rb.column_data((size_t)f.tag_col[i]);
+            rvl_column tc{};
+            tc.dtype = RVL_BOOLEAN; tc.location = RVL_HOST; tc.length = t.length; tc.values = t.bits.data();
+            out.push_back(Series::from_mixed(f.names[i], c, tc, f.dtypes[i]));
+            continue;
+        }
         out.push_back(Series::from_column(f.names[i], c, f.dtypes[i]));
     }
     return DataFrame::unchecked(std::move(out));
 }
 
 // dtype the reference's Series::new would infer for column i of `rb` holding `rows` (> 0) rows
-DataType inferred_dtype(const RecordBatch& rb, size_t i, DataType current, size_t rows) {
+DataType inferred_dtype(const RecordBatch& rb, size_t i, DataType current, size_t rows, int tag = -1) {
     if (current == DataType::Null) return DataType::Null;
-    return (size_t)rb.column_null_count(i) == rows ? DataType::Null : current;
+    const size_t nulls = (size_t)rb.column_null_count(i);
+    if (nulls == rows) return DataType::Null;
+    if (tag >= 0) {  // Int64 + Float64 survivors => Float64; only Int64 survivors => Int64 (series.rs:190-214)
+        int64_t ints = 0;
+        if (rvl_batch_count_true(rb.context()->handle(), rb.handle(), tag, &ints) != RVL_OK) throw Error(rvl_last_error());
+        return (size_t)ints + nulls == rows ? DataType::Int64 : DataType::Float64;
+    }
+    return current;
 }
 
 rvl_predicate to_predicate(int32_t column, BinaryOperator op, const AnyValue& lit) {
@@ -1013,18 +1060,27 @@ Frame exec_filter(const ContextRef& ctx, const Frame& in, const FilterSpec& f, c
     }
     // the predicate column of a Null-dtype series is all nulls: compare as such (its device array may still be typed)
     rvl_predicate pred = to_predicate(pc, f.op, f.value);
+    if (in.tag_col[(size_t)pc] >= 0) pred.tag_column = in.tag_col[(size_t)pc] + 1;  // mixed series: rows compare with their own type
+    // hidden tag columns of the projected mixed columns ride along behind the visible ones
+    const size_t nvis = proj.size();
+    Frame r;
+    r.tag_col.assign(nvis, -1);
+    for (size_t j = 0; j < nvis; ++j) {
+        const int t = in.tag_col[(size_t)proj[j]];
+        if (t >= 0) { r.tag_col[j] = (int)proj.size(); proj.push_back(t); }
+    }
     rvl_batch* out = nullptr;
     check(rvl_filter_project(ctx->handle(), in.rb.handle(), &pred, proj.data(), (int32_t)proj.size(), limit ? (int64_t)*limit : -1, &out));
-    Frame r;
     auto schema = std::make_shared<Schema>();
-    for (size_t j = 0; j < proj.size(); ++j) schema->fields.push_back(Field{out_names[j], in.rb.schema()->fields[(size_t)proj[j]].data_type, true});
+    for (size_t j = 0; j < proj.size(); ++j)
+        schema->fields.push_back(Field{j < nvis ? out_names[j] : in.rb.schema()->fields[(size_t)proj[j]].name, in.rb.schema()->fields[(size_t)proj[j]].data_type, true});
     r.rb = RecordBatch::adopt(ctx, schema, out);
     r.rows = r.rb.num_rows();
     r.names = out_names;
     if (r.rows == 0 && (select || limit)) throw Error("Series error: Empty series not allowed");  // Series::new on no data: plan.rs:89-91, :167-169
-    for (size_t j = 0; j < proj.size(); ++j) {
+    for (size_t j = 0; j < nvis; ++j) {
         const DataType cur = in.dtypes[(size_t)proj[j]];
-        r.dtypes.push_back(r.rows == 0 ? cur : inferred_dtype(r.rb, j, cur, r.rows));  // Series::empty keeps the dtype (plan.rs:140-141)
+        r.dtypes.push_back(r.rows == 0 ? cur : inferred_dtype(r.rb, j, cur, r.rows, r.tag_col[j]));  // Series::empty keeps the dtype (plan.rs:140-141)
     }
     if (select) {  // DataFrame::new over the renamed series (plan.rs:95): duplicate final names
         std::set<std::string> seen;
@@ -1063,14 +1119,20 @@ Frame exec_node(const ContextRef& ctx, const LogicalPlan& p) {  // physical_plan
             if (sel.empty()) return r;  // DataFrame::new(vec![]) = empty frame
             if (in.rows == 0) throw Error("Series error: Empty series not allowed");  // plan.rs:89-91
             r.rows = in.rows;
-            r.rb = in.rb.select_columns(idx);
+            const size_t nvis = idx.size();
+            r.tag_col.assign(nvis, -1);
+            std::vector<size_t> all = idx;
+            for (size_t j = 0; j < nvis; ++j)
+                if (in.tag_col[idx[j]] >= 0) { r.tag_col[j] = (int)all.size(); all.push_back((size_t)in.tag_col[idx[j]]); }
+            r.rb = in.rb.select_columns(all);
             auto schema = std::make_shared<Schema>();
             std::set<std::string> seen;
-            for (size_t j = 0; j < idx.size(); ++j) {
+            for (size_t j = 0; j < nvis; ++j) {
                 r.names.push_back(sel[j].second);
-                r.dtypes.push_back(inferred_dtype(r.rb, j, in.dtypes[idx[j]], r.rows));
+                r.dtypes.push_back(inferred_dtype(r.rb, j, in.dtypes[idx[j]], r.rows, r.tag_col[j]));
                 schema->fields.push_back(Field{sel[j].second, in.rb.schema()->fields[idx[j]].data_type, true});
             }
+            for (size_t j = nvis; j < all.size(); ++j) schema->fields.push_back(in.rb.schema()->fields[all[j]]);
             for (const auto& n : r.names) if (!seen.insert(n).second) throw Error("DataFrame error: Duplicate column name: '" + n + "'");
             r.rb = r.rb.with_schema(schema);
             return r;
@@ -1098,6 +1160,7 @@ Frame exec_node(const ContextRef& ctx, const LogicalPlan& p) {  // physical_plan
             if (in.names.empty()) return in;  // width 0: DataFrame::new(vec![])
             Frame r;
             r.names = in.names;
+            r.tag_col = in.tag_col;
             if (p.n == 0) {  // plan.rs:154-161: empty series keep their dtypes
                 r.rows = 0; r.dtypes = in.dtypes; r.rb = in.rb.slice(0, 0);
                 return r;
@@ -1106,7 +1169,7 @@ Frame exec_node(const ContextRef& ctx, const LogicalPlan& p) {  // physical_plan
             const size_t lim = std::min(p.n, in.rows);
             r.rows = lim;
             r.rb = in.rb.slice(0, lim);
-            for (size_t j = 0; j < in.names.size(); ++j) r.dtypes.push_back(inferred_dtype(r.rb, j, in.dtypes[j], lim));
+            for (size_t j = 0; j < in.names.size(); ++j) r.dtypes.push_back(inferred_dtype(r.rb, j, in.dtypes[j], lim, in.tag_col[j]));
             return r;
         }
     }

@@ -84,9 +84,13 @@ class Series {
     Series renamed(const std::string& n) const { Series s = *this; s.name_ = n; return s; }
     size_t null_count() const;
     bool is_valid(size_t i) const { return dtype_ != DataType::Null && (validity_.empty() || ((validity_[i >> 3] >> (i & 7)) & 1)); }
-    // A Float64-dtype Series may hold Int64 values (series.rs:210-212); such mixed columns are kept on the host but are
-    // rejected by the GPU engines.
+    // A Float64-dtype Series may hold Int64 values (series.rs:210-212).  Such a mixed column keeps ONE 8-byte buffer (the f64
+    // or the i64 bit pattern of each row) plus a tag bitmap (1 = the row is an AnyValue::Int64); on the device the tag travels
+    // as a hidden Boolean column and the predicate kernels compare each row with its own type (rvl_predicate::tag_column).
     bool is_mixed() const { return !int_tag_.empty(); }
+    rvl_column tag_column(size_t offset, size_t length) const;   // Boolean column over the tag bitmap (mixed series only)
+    // Build from a downloaded (values, tag) pair; `dtype` is what Series::new infers for the survivors (Null / Int64 / Float64)
+    static Series from_mixed(const std::string& name, const rvl_column& values, const rvl_column& tags, DataType dtype);
 
     // raw buffers
     const std::vector<int64_t>& i64_values() const { return i64_; }
@@ -111,8 +115,7 @@ class Series {
     std::vector<int32_t> offsets_;   // String (len + 1 entries)
     std::vector<uint8_t> data_;      // String
     std::vector<uint8_t> validity_;  // LSB-first, empty = all valid
-    std::vector<uint8_t> int_tag_;   // mixed Float64 series: per row 1 = the value is an AnyValue::Int64 held in int_vals_
-    std::vector<int64_t> int_vals_;
+    std::vector<uint8_t> int_tag_;   // mixed Float64 series: LSB-first bitmap, 1 = f64_[i] holds the bit pattern of an AnyValue::Int64
     void infer_from_validity();      // all null -> dtype Null
 };
 

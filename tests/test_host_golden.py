@@ -118,6 +118,8 @@ def _random_frame(rng, n):
         ("b", [maybe(bool(rng.integers(0, 2)), 0.15) for _ in range(n)]),
         ("z", [None] * n),                                     # dtype Null
         ("d", [int(i) for i in range(n)]),                     # no nulls
+        # Float64-dtype Series that also holds Int64 values (series.rs:210-212): rows compare with their own type
+        ("m", [maybe(float(rng.integers(0, 50)) if rng.random() < 0.5 else int(rng.integers(0, 50)), 0.15) for _ in range(n)]),
     ]
     return cols
 
@@ -183,7 +185,7 @@ def test_random_streaming_queries_match_oracle(seed):
     from oracle import oracle as O
     rng = np.random.default_rng(100 + seed)
     n = int(rng.choice([1, 100, 1024, 2500, 5000]))
-    cols = [c for c in _random_frame(rng, n) if c[0] != "z"] + [("flag", [bool(v) for v in rng.integers(0, 2, n)])]
+    cols = [c for c in _random_frame(rng, n) if c[0] not in ("z", "m")] + [("flag", [bool(v) for v in rng.integers(0, 2, n)])]
     names = [c[0] for c in cols]
     for q in range(12):
         sel = [str(x) for x in rng.choice(names, size=int(rng.integers(1, 4)), replace=False)]
@@ -235,3 +237,25 @@ def test_config1_one_million_rows_select_name_where_age_gt_25():
     for mod, err in ((F, F.RivulusError), (O, O.OracleError)):
         with pytest.raises(err, match="Logical plan error: Column not found: 'age'"):
             mod.LazyFrame.from_dataframe(mod.DataFrame.synth(spec, 1000)).select([mod.col("name")]).filter(mod.col("age").gt(mod.lit(25))).collect()
+
+
+@pytest.mark.gpu
+def test_mixed_int_float_series_semantics():
+    """A Float64-dtype Series holding Int64 values: per-row typed comparison, dtype re-inference of the survivors
+    (only Int64 left => Int64; none => Null), and the streaming engine's panic (streaming.rs:189)."""
+    from oracle import oracle as O
+    cols = [("m", [1, 2.5, None, 3, 4.0, 7, None, 2.0]), ("i", list(range(8)))]
+    cases = [("m", "gt", 2), ("m", "gt", 2.0), ("m", "lt", 3.0), ("m", "lte", 3), ("m", "neq", 2.5), ("m", "eq", 2), ("m", "gte", None),
+             ("m", "lt", None), ("m", "eq", "x"), ("i", "gte", 3), ("i", "lt", 2)]
+    for pc, m, litv in cases:
+        for shape in range(3):
+            def build(mod):
+                lf = mod.LazyFrame.from_dataframe(mod.DataFrame.new(cols)).filter(getattr(mod.col(pc), m)(mod.lit(litv)))
+                if shape == 1: lf = lf.select([mod.col("m").alias("mm"), mod.col("m")])
+                if shape == 2: lf = lf.filter(mod.col("m").lt(mod.lit(5))).limit(3)
+                return lf.collect()
+            assert _outcome(F, F.RivulusError, build) == _outcome(O, O.OracleError, build), (pc, m, litv, shape)
+    for mod, err in ((F, F.RivulusError), (O, O.OracleError)):
+        with pytest.raises(err, match="Type mismatch in Float64 series") as ei:
+            mod.LazyFrame.from_dataframe(mod.DataFrame.new(cols)).select([mod.col("m")]).collect_streaming()
+        assert ei.value.panic

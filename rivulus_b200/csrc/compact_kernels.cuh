@@ -30,7 +30,7 @@ namespace rvl {
 
 constexpr int kCompactMaxWarps = 16;                      // consumer warps of the dense kernel: 8 (256 rows each per tile) or 16 (128 rows)
 constexpr uint32_t kSlotBytes = kTileRows * 8;            // one column tile
-constexpr int kSparseCap = 128;                           // most survivors a "sparse" tile may hold
+constexpr int kSparseCap = 256;                           // most survivors a "sparse" tile may hold
 
 struct CompactParams {
     int64_t n_rows;

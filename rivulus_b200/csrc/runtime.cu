@@ -176,7 +176,7 @@ int32_t rvl_ctx_set_option(rvl_ctx* ctx, int32_t option, int64_t value) {
             c.plan_mode = (int)value; return RVL_OK;
         case RVL_OPT_TWO_PASS_MIN_ROWS: c.two_pass_min_rows = value; return RVL_OK;
         case RVL_OPT_SPARSE_MAX:
-            if (value < 0 || value > 128) return fail(RVL_INVALID_ARGUMENT, "sparse_max must be in [0, 128]");
+            if (value < 0 || value > 256) return fail(RVL_INVALID_ARGUMENT, "sparse_max must be in [0, 256]");
             c.sparse_max = (int)value; return RVL_OK;
         case RVL_OPT_DENSE_SLOTS:
             if (value < 2 || value > 14) return fail(RVL_INVALID_ARGUMENT, "dense_slots must be in [2, 14]");

@@ -50,7 +50,7 @@ struct CtxCore {
     // execution plan of the fused operator (rvl_ctx_set_option)
     int plan_mode = 0;                      // RVL_PLAN_AUTO / _FUSED / _TWO_PASS
     int64_t two_pass_min_rows = 4 << 20;    // AUTO: batches at least this large take the two-pass plan
-    int sparse_max = 96;                    // two-pass: tiles with <= this many survivors (of 2048 rows) are gathered
+    int sparse_max = 224;                   // two-pass: tiles with <= this many survivors (of 2048 rows) are gathered
     int dense_slots = 14;                   // two-pass: 16 KB ring slots per CTA of the dense compaction kernel
     int dense_ctas_per_sm = 1;
     int dense_warps = 16;                   // two-pass: consumer warps per CTA of the dense kernel (8 or 16)

@@ -26,8 +26,10 @@ for opt, val in ((capi.OPT_SPARSE_MAX, args.sparse_max), (capi.OPT_DENSE_SLOTS, 
         ctx.set_option(opt, val)
 spec = [(capi.SYNTH_KEY1000, 0, 0), (capi.SYNTH_I64, 1, 0), (capi.SYNTH_F64, 2, 0), (capi.SYNTH_I64, 3, 0), (capi.SYNTH_F64, 4, 0)]
 t = ctx.gen_batch(spec, args.rows)
+ctx.profile_enable(True)
 for _ in range(args.reps):
     for thr in [int(x) for x in args.thresholds.split(",")]:
         out = ctx.filter_project(t, capi.predicate(0, ">", thr), [1, 2, 3, 4])
-        print(thr, out.num_rows())
+        ms = ctx.profile_read_launches()
+        print(thr, out.num_rows(), "device ms", [round(x, 3) for x in ms])
         out.release()

@@ -339,7 +339,7 @@ def test_large_synthetic_checksums(ctx, thr, n):
 
 
 # ------------------------------------------------------------------ two-pass plan: dense / sparse tile classification
-@pytest.mark.parametrize("sparse_max", [0, 1, 7, 96, 128])
+@pytest.mark.parametrize("sparse_max", [0, 1, 7, 96, 128, 255, 256])
 @pytest.mark.parametrize("limit", [-1, 12345])
 def test_two_pass_mixed_density_tiles(sparse_max, limit):
     """Clustered survivors: empty, sparse and dense 2048-row tiles in one batch, nulls in every column, ragged tail,

@@ -163,6 +163,12 @@ int32_t rvl_batch_download_column(rvl_ctx* ctx, const rvl_batch* batch, int32_t 
 /* BooleanArray::count_true (array/boolean.rs: count_true): rows of Boolean column i that are Some(true) */
 int32_t rvl_batch_count_true(rvl_ctx* ctx, const rvl_batch* batch, int32_t i, int64_t* count);
 
+/* BooleanArray::{and, or, not} (array/boolean.rs:120-165), strict-null: the result is null wherever an input is null.  Inputs are
+ * Boolean columns of device batches (any views); the result is a one-column batch built like BooleanArrayBuilder::finish leaves it.
+ * RVL_LENGTH_MISMATCH "Array lengths must match for logical operations".  Masks combined this way feed RVL_PRED_BOOL_COLUMN. */
+typedef enum rvl_bool_op { RVL_BOOL_AND = 0, RVL_BOOL_OR = 1, RVL_BOOL_NOT = 2 } rvl_bool_op;
+int32_t rvl_boolean_op(rvl_ctx* ctx, int32_t op, const rvl_batch* a, int32_t a_col, const rvl_batch* b, int32_t b_col, rvl_batch** out);
+
 /* RecordBatch::slice (record_batch.rs:92-106): zero-copy view; RVL_OUT_OF_BOUNDS instead of the panic */
 int32_t rvl_batch_slice(const rvl_batch* batch, int64_t offset, int64_t length, rvl_batch** view);
 /* RecordBatch::select_columns (record_batch.rs:180-206): zero-copy column pick */

@@ -66,7 +66,7 @@ ABI_SYMBOLS = [
     "rvl_ctx_profile_enable", "rvl_ctx_profile_read", "rvl_ctx_profile_read_launches", "rvl_ctx_set_option",
     "rvl_host_alloc", "rvl_host_free",
     "rvl_batch_upload", "rvl_batch_wrap_device", "rvl_batch_release", "rvl_batch_num_rows", "rvl_batch_num_columns",
-    "rvl_batch_column", "rvl_batch_download_column", "rvl_batch_count_true", "rvl_batch_slice", "rvl_batch_select", "rvl_batch_take", "rvl_batch_concat",
+    "rvl_batch_column", "rvl_batch_download_column", "rvl_batch_count_true", "rvl_boolean_op", "rvl_batch_slice", "rvl_batch_select", "rvl_batch_take", "rvl_batch_concat",
     "rvl_filter_project", "rvl_predicate_mask", "rvl_filter_project_launch", "rvl_filter_project_finish",
     "rvl_stream_open", "rvl_stream_push", "rvl_stream_next", "rvl_stream_limit_reached", "rvl_stream_collect",
     "rvl_stream_stats", "rvl_stream_close",
@@ -259,6 +259,16 @@ class Context:
         check(lib().rvl_batch_upload(self._h, arr, len(cols), C.byref(out)))
         return Batch(self, out)
 
+    def wrap_device(self, views: Sequence[RvlColumn]) -> "Batch":
+        """rvl_batch_wrap_device: a batch over caller-owned DEVICE buffers (e.g. column views of other batches), no copy.
+        The caller keeps the owning batches alive."""
+        arr = (RvlColumn * max(len(views), 1))(*views)
+        out = C.c_void_p()
+        check(lib().rvl_batch_wrap_device(self._h, arr, len(views), C.byref(out)))
+        b = Batch(self, out)
+        b._keep = list(views)
+        return b
+
     def gen_batch(self, cols: Sequence[tuple], n: int, row0: int = 0) -> "Batch":
         """cols: [(kind, col_id, null_pct)] — synthetic columns generated on the device (rivulus_synth.h)."""
         kinds = (C.c_int32 * len(cols))(*[c[0] for c in cols])
@@ -297,6 +307,12 @@ class Context:
     def predicate_mask(self, batch: "Batch", pred: RvlPredicate) -> "Batch":
         out = C.c_void_p()
         check(lib().rvl_predicate_mask(self._h, batch._h, C.byref(pred), C.byref(out)))
+        return Batch(self, out)
+
+    def boolean_op(self, op: str, a: "Batch", a_col: int, b: Optional["Batch"] = None, b_col: int = 0) -> "Batch":
+        """BooleanArray::and / or / not (array/boolean.rs:120-165) on device columns; returns a one-column batch."""
+        out = C.c_void_p()
+        check(lib().rvl_boolean_op(self._h, {"and": 0, "or": 1, "not": 2}[op], a._h, a_col, b._h if b is not None else None, b_col, C.byref(out)))
         return Batch(self, out)
 
     def open_stream(self, dtypes: Sequence[int], pred, proj: Sequence[int], limit: int = -1, batch_rows: int = 1 << 20,

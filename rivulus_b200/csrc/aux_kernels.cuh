@@ -205,6 +205,30 @@ static __global__ void copy_col8_zero_nulls_kernel(const uint64_t* __restrict__ 
     }
 }
 
+// ---- BooleanArray::{and, or, not} (array/boolean.rs:120-165): strict-null — the result is null where either input is null.
+// One 32-row word per thread; inputs may be bit-offset views.  op: 0 = and, 1 = or, 2 = not (b ignored).
+static __global__ void boolean_op_kernel(BitSrc a_vals, BitSrc a_valid, BitSrc b_vals, BitSrc b_valid, int op, int64_t n,
+                                         uint32_t* __restrict__ out_vals, uint32_t* __restrict__ out_valid) {
+    const int64_t nwords = (n + 31) / 32;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += stride) {
+        const uint64_t row = (uint64_t)w * 32;
+        uint32_t valid = load_bits32(a_valid, row);
+        const uint32_t av = load_bits32(a_vals, row);
+        uint32_t r;
+        if (op == 2) r = ~av;
+        else {
+            valid &= load_bits32(b_valid, row);
+            const uint32_t bv = load_bits32(b_vals, row);
+            r = op == 0 ? (av & bv) : (av | bv);
+        }
+        const int64_t rem = n - w * 32;
+        if (rem < 32) valid &= (1u << rem) - 1u;
+        out_vals[w] = r & valid;  // append_null stores false under a null (boolean.rs:275-278)
+        out_valid[w] = valid;
+    }
+}
+
 // ---- take (record_batch.rs:108-178): gather rows by index, one output row per thread ------------------------------
 // 8-byte columns: out[i] = valid(idx[i]) ? in[idx[i]] : 0, validity bit i = valid(idx[i]) (one ballot word per warp)
 static __global__ void take_col8_kernel(const uint64_t* __restrict__ in, BitSrc valid, const int64_t* __restrict__ idx, int64_t n,

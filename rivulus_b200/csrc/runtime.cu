@@ -472,6 +472,40 @@ int32_t rvl_batch_count_true(rvl_ctx* ctx, const rvl_batch* batch, int32_t i, in
     return RVL_OK;
 }
 
+int32_t rvl_boolean_op(rvl_ctx* ctx, int32_t op, const rvl_batch* a, int32_t a_col, const rvl_batch* b, int32_t b_col, rvl_batch** out) {
+    if (!ctx || !a || !out || (op != RVL_BOOL_NOT && !b)) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    if (op < RVL_BOOL_AND || op > RVL_BOOL_NOT) return fail(RVL_INVALID_ARGUMENT, "unknown boolean operation");
+    if (a_col < 0 || a_col >= (int32_t)a->cols.size() || (op != RVL_BOOL_NOT && (b_col < 0 || b_col >= (int32_t)b->cols.size())))
+        return fail(RVL_OUT_OF_BOUNDS, "Column index out of bounds");
+    const DevColumn& ca = a->cols[a_col];
+    const DevColumn* cb = op != RVL_BOOL_NOT ? &b->cols[b_col] : nullptr;
+    if (ca.dtype != RVL_BOOLEAN || (cb && cb->dtype != RVL_BOOLEAN)) return fail(RVL_TYPE_MISMATCH, "logical operations need Boolean arrays");
+    if (cb && cb->length != ca.length) return fail(RVL_LENGTH_MISMATCH, "Array lengths must match for logical operations");  // boolean.rs:121-123
+    const CoreRef& core = ctx->core;
+    RVL_CUDA_TRY(cudaSetDevice(core->device));
+    const int64_t n = ca.length;
+    auto res = std::make_unique<rvl_batch>();
+    res->core = core; res->num_rows = n;
+    DevColumn d;
+    d.dtype = RVL_BOOLEAN; d.length = n; d.offset = 0; d.null_count = -1;
+    const size_t bytes = (size_t)((n + 31) / 32) * 4 + 8;
+    RVL_TRY(dev_alloc_zeroed(core, bytes, &d.values));
+    RVL_TRY(dev_alloc_zeroed(core, bytes, &d.validity));
+    if (n > 0) {
+        boolean_op_kernel<<<grid_for((n + 31) / 32, 256, core->sm_count), 256, 0, core->stream>>>(
+            bitsrc_of(ca.values, ca.offset, n), bitsrc_of(ca.validity, ca.offset, n),
+            cb ? bitsrc_of(cb->values, cb->offset, n) : BitSrc{nullptr, 0, 0}, cb ? bitsrc_of(cb->validity, cb->offset, n) : BitSrc{nullptr, 0, 0},
+            op, n, (uint32_t*)d.values->ptr, (uint32_t*)d.validity->ptr);
+        core->launches++;
+        RVL_CUDA_TRY(cudaGetLastError());
+    }
+    res->cols.push_back(std::move(d));
+    RVL_TRY(ensure_null_count(res.get(), 0));
+    if (res->cols[0].null_count == 0) res->cols[0].validity.reset();  // BooleanArrayBuilder::finish keeps a bitmap only with nulls (boolean.rs:280-286)
+    *out = res.release();
+    return RVL_OK;
+}
+
 int32_t rvl_batch_slice(const rvl_batch* batch, int64_t offset, int64_t length, rvl_batch** view) {
     if (!batch || !view) return fail(RVL_INVALID_ARGUMENT, "null argument");
     if (offset < 0 || length < 0 || offset + length > batch->num_rows) return fail(RVL_OUT_OF_BOUNDS, "Slice out of bounds");  // record_batch.rs:93

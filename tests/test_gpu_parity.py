@@ -398,3 +398,65 @@ def test_take_matches_reference(ctx):
         assert_batches_equal(gb.take(idx), ob.take(idx), f"take {len(idx)} rows")
     with pytest.raises(capi.RivulusError, match=f"Index {n} out of bounds for {n} rows"):
         gb.take([0, n, 1])
+
+
+# ------------------------------------------------------------------ BooleanArray::{and, or, not, count_true} (array/boolean.rs:120-178)
+def _bool_batch(ctx, vals):
+    return ctx.upload([capi.Column.from_list(vals, capi.BOOLEAN)])
+
+
+def test_golden_boolean_logical_ops(ctx):  # boolean.rs:626-691
+    a = _bool_batch(ctx, [True, False, True, None, False])
+    assert ctx.boolean_op("and", a, 0, _bool_batch(ctx, [True, True, False, True, None]), 0).download_column(0).to_list() == [True, False, False, None, None]
+    assert ctx.boolean_op("or", a, 0, _bool_batch(ctx, [False, True, False, True, None]), 0).download_column(0).to_list() == [True, True, True, None, None]
+    assert ctx.boolean_op("not", _bool_batch(ctx, [True, False, None, True]), 0).download_column(0).to_list() == [False, True, None, False]
+    c = _bool_batch(ctx, [True, False, True, None, False, True])
+    assert c.count_true(0) == 3                                            # nulls count in neither (boolean.rs:669-682)
+    assert ctx.boolean_op("not", c, 0).count_true(0) == 2                  # count_false
+    with pytest.raises(capi.RivulusError, match="Array lengths must match for logical operations"):
+        ctx.boolean_op("and", _bool_batch(ctx, [True, False]), 0, _bool_batch(ctx, [True]), 0)
+
+
+def test_boolean_ops_random_views_and_compound_predicate(ctx):
+    """Strict-null and/or/not over bit-offset views, checked against the definition (value(i) pairs, boolean.rs:127-132), then used
+    as a compound predicate: (k > 300) AND NOT (x < 500.0) -> mask column -> RecordBatch::filter."""
+    rng = np.random.default_rng(21)
+    n = 100_003
+    ca, cb = random_col(rng, "bool", n, 0.2, offset=5, tail=3), random_col(rng, "bool", n, 0.1, offset=37)
+    ga, gb = upload(ctx, [ca]), upload(ctx, [cb])
+
+    def logical(c):
+        vals = c.values[c.offset:c.offset + n].astype(bool)
+        valid = np.ones(n, bool) if c.valid is None else c.valid[c.offset:c.offset + n]
+        return vals, valid
+
+    (av, ak), (bv, bk) = logical(ca), logical(cb)
+    for op, fn in (("and", np.logical_and), ("or", np.logical_or)):
+        got = ctx.boolean_op(op, ga, 0, gb, 0).download_column(0)
+        valid = ak & bk
+        want_vals = fn(av, bv) & valid
+        assert np.array_equal(capi.unpack_bits(got.values, n), want_vals), op
+        assert got.null_count == int((~valid).sum()) and np.array_equal(capi.unpack_bits(got.validity, n), valid), op
+    got = ctx.boolean_op("not", ga, 0).download_column(0)
+    assert np.array_equal(capi.unpack_bits(got.values, n), ~av & ak) and np.array_equal(capi.unpack_bits(got.validity, n), ak)
+    nonull = ctx.boolean_op("and", upload(ctx, [Col("bool", 70, np.ones(70, bool))]), 0, upload(ctx, [Col("bool", 70, np.zeros(70, bool))]), 0)
+    assert nonull.view(0).validity is None and nonull.count_true(0) == 0   # bitmap only when a result is null (boolean.rs:280-286)
+
+    # compound predicate through masks
+    cols = [random_col(rng, "i64", n, 0.1, lo=0, hi=1000), random_col(rng, "f64", n, 0.1), random_col(rng, "str", n, 0.1, maxlen=9)]
+    batch = upload(ctx, cols)
+    m1 = ctx.predicate_mask(batch, capi.predicate(0, ">", 300))
+    m2 = ctx.predicate_mask(batch, capi.predicate(1, "<", 500.0))
+    mask = ctx.boolean_op("and", m1, 0, ctx.boolean_op("not", m2, 0), 0)
+    # expected keep set from the eager truth table: nulls pass `<` (so NOT(x < 500) drops them), nulls fail `>`
+    kv = cols[0].values[:n]; kok = cols[0].valid[:n]
+    xv = cols[1].values[:n]; xok = cols[1].valid[:n]
+    keep = (kok & (kv > 300)) & ~(~xok | (xv < 500.0))
+    joined = ctx.upload([c.gpu() for c in cols] + [capi.Column(capi.BOOLEAN, n, 0, capi.pack_bits(keep))])
+    want = ctx.filter_project(joined, capi.mask_predicate(3), [0, 1, 2])
+    views = [batch.view(i) for i in range(3)] + [mask.view(0)]
+    got = ctx.filter_project(ctx.wrap_device(views), capi.mask_predicate(3), [0, 1, 2])
+    assert got.num_rows() == want.num_rows() == int(keep.sum())
+    for j in range(3):
+        assert got.checksum(j) == want.checksum(j)
+

@@ -31,6 +31,7 @@ namespace rvl {
 constexpr int kCompactMaxWarps = 16;                      // consumer warps of the dense kernel: 8 (256 rows each per tile) or 16 (128 rows)
 constexpr uint32_t kSlotBytes = kTileRows * 8;            // one column tile
 constexpr int kSparseCap = 256;                           // most survivors a "sparse" tile may hold
+constexpr int kMaxBitSrc = kMaxCol8 + 2 * kMaxBitCols;    // bitmaps a dense launch may read: validity per 8-byte column, in + mask per bit column
 
 struct CompactParams {
     int64_t n_rows;
@@ -47,6 +48,13 @@ struct CompactParams {
     int32_t pad;
     Col8 col8[kMaxCol8];
     BitCol bits[kMaxBitCols];
+    // dense kernel: every bitmap it reads, listed once; consumer warps stage the next tile's words of each through cp.async
+    int32_t n_bsrc;
+    int8_t col8_vsrc[kMaxCol8];          // index into bsrc of col8[c].valid, or -1 (no nulls)
+    int8_t bit_in_src[kMaxBitCols];      // ... of bits[b].in   (-1: all ones)
+    int8_t bit_mask_src[kMaxBitCols];    // ... of bits[b].mask (-1: all ones)
+    int32_t pad2;
+    BitSrc bsrc[kMaxBitSrc];
 };
 
 __device__ __forceinline__ uint64_t tile_prefix_of(const CompactParams& p, int64_t tile) {
@@ -58,6 +66,17 @@ __device__ __forceinline__ uint64_t lds64(uint32_t addr) {
     asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+// 4-byte asynchronous global -> shared copy; src_bytes = 0 zero-fills (words beyond the end of a bitmap)
+__device__ __forceinline__ void cp_async_4(uint32_t smem_addr, const void* gmem, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_addr), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_addr(uint32_t bar_addr) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
 }
@@ -104,6 +123,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, CW == 8 ? 2 : 1) compact_dense_
     uint64_t* const slots = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* const full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)p.n_slots * kSlotBytes);
     uint64_t* const empty = full + p.n_slots;
+    // bitmap staging: [consumer warp][2 halves][n_bsrc][KW + 1 words]
+    constexpr int kPer = KW + 1;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t n_list = *p.list_count;
@@ -146,6 +167,30 @@ __global__ void __launch_bounds__((CW + 1) * 32, CW == 8 ? 2 : 1) compact_dense_
     const uint32_t full_addr0 = smem_u32(full), empty_addr0 = smem_u32(empty);
     int slot = 0;
     uint32_t phase = 0;
+    // Bitmap words (validity of the 8-byte columns, values / validity of the bit-packed columns) of this warp's rows are staged
+    // one tile ahead with 4-byte cp.async copies into a per-warp double buffer: no register is held and no consumer ever waits
+    // on a dependent global load of a bitmap word.  Word j of source s covers bits [32 j, 32 j + 32) from the 32-bit word that
+    // holds the warp's first row; a funnel shift by (bit0 & 31) aligns it (the warp's first row is a multiple of 32).
+    const uint32_t bst_half = (uint32_t)p.n_bsrc * kPer * 4u;
+    const uint32_t bst_addr0 = smem_u32(empty + p.n_slots) + (uint32_t)warp * 2u * bst_half;
+    auto stage_bits = [&](uint32_t tile_id, uint32_t half) {
+        const uint64_t wr0 = (uint64_t)tile_id * kTileRows + (uint64_t)warp * kWarpRows;
+        const int n_task = p.n_bsrc * kPer;
+        for (int t = lane; t < n_task; t += 32) {
+            const int s = t / kPer, j = t - s * kPer;
+            const BitSrc& b = p.bsrc[s];
+            const uint64_t w = ((b.bit0 + wr0) >> 5) + (uint64_t)j;
+            const bool ok = w < b.nwords;
+            cp_async_4(bst_addr0 + half * bst_half + (uint32_t)t * 4u, b.words + (ok ? w : 0ull), ok ? 4u : 0u);
+        }
+        cp_async_commit();
+    };
+    auto staged32 = [&](int s, int k, uint32_t half) -> uint32_t {
+        if (s < 0) return 0xFFFFFFFFu;
+        const uint32_t a = bst_addr0 + half * bst_half + (uint32_t)(s * kPer + k) * 4u;
+        return __funnelshift_r(lds32(a), lds32(a + 4u), (uint32_t)p.bsrc[s].bit0 & 31u);
+    };
+    uint32_t half = 0;
     // two-stage software prefetch: the tile id two iterations ahead, the selection words / prefix words one ahead.
     // Nothing loaded here is touched before the next iteration, so no consumer warp waits on these round trips.
     uint32_t nw0 = 0, nw1 = 0;
@@ -156,18 +201,26 @@ __global__ void __launch_bounds__((CW + 1) * 32, CW == 8 ? 2 : 1) compact_dense_
         const uint32_t* sw = p.sel + (size_t)ntile * kTileWords;
         nw0 = __ldg(sw + lane); nw1 = __ldg(sw + 32 + lane);
         ninfo = p.tile_info[ntile]; ncbase = p.chunk_base[ntile / tpc];
+        if (p.n_bsrc > 0) stage_bits(ntile, 0u);
     }
 #pragma unroll 1
     for (uint32_t i = blockIdx.x; i < n_list; i += gridDim.x) {
         const int64_t tile = (int64_t)ntile;
         const uint32_t w0 = nw0, w1 = nw1;
         const uint64_t prefix = ncbase + (ninfo >> kInfoShift);
+        const uint32_t cur = half;
+        if (p.n_bsrc > 0) {
+            cp_async_wait_all();   // this tile's bitmap words (issued one iteration ago)
+            __syncwarp();          // ... of every lane; and nobody still reads the other half
+            half ^= 1u;
+        }
         if (i + gridDim.x < n_list) {
             ntile = nntile;
             const uint32_t* sw = p.sel + (size_t)ntile * kTileWords;
             nw0 = __ldg(sw + lane); nw1 = __ldg(sw + 32 + lane);
             ninfo = p.tile_info[ntile]; ncbase = p.chunk_base[ntile / tpc];
             if (i + 2 * gridDim.x < n_list) nntile = p.list[i + 2 * gridDim.x];
+            if (p.n_bsrc > 0) stage_bits(ntile, half);
         }
         if (p.limit >= 0 && prefix >= (uint64_t)p.limit) continue;  // tile lies entirely beyond the limit (no slots were filled)
         const int64_t row0 = tile * kTileRows;
@@ -218,10 +271,11 @@ __global__ void __launch_bounds__((CW + 1) * 32, CW == 8 ? 2 : 1) compact_dense_
                     if (kp[k]) v[k] = ld_stream(col.in + wrow0 + k * 32 + lane);
                 }
             }
-            if (col.valid.words != nullptr) {  // placeholder 0 under a null (primitive.rs:175-178)
+            const int vsrc = p.col8_vsrc[c];
+            if (vsrc >= 0) {  // placeholder 0 under a null (primitive.rs:175-178)
 #pragma unroll
                 for (int k = 0; k < KW; ++k) {
-                    const uint32_t vm = load_bits32(col.valid, (uint64_t)(wrow0 + k * 32));
+                    const uint32_t vm = staged32(vsrc, k, cur);
                     if (((vm >> lane) & 1u) == 0u) v[k] = 0ull;
                 }
             }
@@ -246,11 +300,11 @@ __global__ void __launch_bounds__((CW + 1) * 32, CW == 8 ? 2 : 1) compact_dense_
                 const uint32_t n_words = (end + 31u) >> 5;  // <= KW + 1
                 for (int b = 0; b < p.n_bits; ++b) {
                     const BitCol& bc = p.bits[b];
+                    const int s_in = p.bit_in_src[b], s_mask = p.bit_mask_src[b];
                     uint32_t acc = 0, q = sh;
 #pragma unroll
                     for (int k = 0; k < KW; ++k) {
-                        const uint64_t r = (uint64_t)(wrow0 + k * 32);
-                        const uint32_t in = load_bits32(bc.in, r) & load_bits32(bc.mask, r);
+                        const uint32_t in = staged32(s_in, k, cur) & staged32(s_mask, k, cur);
                         const uint32_t bit = (in >> lane) & (selw[k] >> lane) & 1u;
                         const uint32_t cw = __reduce_or_sync(0xFFFFFFFFu, bit << __popc(selw[k] & lt));
                         const uint32_t s = q & 31u;

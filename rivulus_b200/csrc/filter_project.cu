@@ -214,14 +214,17 @@ static int launch_scan(const CoreRef& core, int kind, const ScanParams& sp, int 
 }
 
 // second pass of the two-pass plan (compact_kernels.cuh): dense tiles through the TMA ring, sparse tiles gathered
+constexpr int kDenseSmemMax = 227 * 1024;
+// bitmap staging area of the dense kernel: [consumer warps][2 halves][n_bsrc][words per warp and tile + 1] 32-bit words
+static size_t dense_stage_bytes(int warps, int n_bsrc) { return (size_t)warps * 2 * (size_t)n_bsrc * (size_t)(kTileWords / warps + 1) * 4; }
 template <int CW>
 static int launch_dense_t(const CoreRef& core, const CompactParams& cp, int per_sm) {
     static bool opted[64] = {false};
     if (!opted[core->device & 63]) {
-        RVL_CUDA_TRY(cudaFuncSetAttribute(compact_dense_kernel<CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 14 * (int)(kSlotBytes + 16)));
+        RVL_CUDA_TRY(cudaFuncSetAttribute(compact_dense_kernel<CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmemMax));
         opted[core->device & 63] = true;
     }
-    const size_t smem = (size_t)cp.n_slots * (kSlotBytes + 16);
+    const size_t smem = (size_t)cp.n_slots * (kSlotBytes + 16) + dense_stage_bytes(CW, cp.n_bsrc);
     compact_dense_kernel<CW><<<(unsigned)(core->sm_count * per_sm), (CW + 1) * 32, smem, core->stream>>>(cp);
     core->launches++;
     RVL_CUDA_TRY(cudaGetLastError());
@@ -231,7 +234,20 @@ static int launch_compaction(const CoreRef& core, CompactParams cp, const uint32
                              const uint32_t* list_counts) {
     const int warps = core->dense_warps == 16 ? 16 : 8;
     const int per_sm = warps == 16 ? 1 : std::max(1, std::min(2, core->dense_ctas_per_sm));
-    const int max_slots = per_sm == 1 ? 14 : 6;
+    // every bitmap the dense kernel reads, listed once (staged ahead by its consumer warps)
+    cp.n_bsrc = 0;
+    auto add_src = [&](const BitSrc& b) -> int8_t {
+        if (b.words == nullptr) return (int8_t)-1;
+        cp.bsrc[cp.n_bsrc] = b;
+        return (int8_t)cp.n_bsrc++;
+    };
+    for (int c = 0; c < kMaxCol8; ++c) cp.col8_vsrc[c] = c < cp.n_col8 ? add_src(cp.col8[c].valid) : (int8_t)-1;
+    for (int b = 0; b < kMaxBitCols; ++b) {
+        cp.bit_in_src[b] = b < cp.n_bits ? add_src(cp.bits[b].in) : (int8_t)-1;
+        cp.bit_mask_src[b] = b < cp.n_bits ? add_src(cp.bits[b].mask) : (int8_t)-1;
+    }
+    const int smem_budget = (per_sm == 1 ? kDenseSmemMax : 110 * 1024) - (int)dense_stage_bytes(warps, cp.n_bsrc);
+    const int max_slots = std::min(14, smem_budget / (int)(kSlotBytes + 16));
     cp.n_slots = std::max(2, std::min(max_slots, core->dense_slots));
     cp.list = dense_list; cp.list_count = list_counts;
     if (warps == 16) RVL_TRY(launch_dense_t<16>(core, cp, per_sm));

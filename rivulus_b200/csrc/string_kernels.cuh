@@ -58,10 +58,12 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
     return woff + incl - v;
 }
 
-static __global__ void __launch_bounds__(kBlock, 4) string_gather_kernel(const __grid_constant__ StrGatherParams p) {
-    __shared__ int32_t s_src[kTileRows];
-    __shared__ int32_t s_dst[kTileRows];
-    __shared__ int32_t s_len[kTileRows];
+constexpr uint32_t kStrChunk = 24 * 1024;   // staging bytes per pass (a 2048-row tile of ~24-byte strings at 50 % fits in one)
+
+static __global__ void __launch_bounds__(kBlock, 5) string_gather_kernel(const __grid_constant__ StrGatherParams p) {
+    __shared__ int32_t s_src[kTileRows];        // survivor r: first source byte
+    __shared__ uint32_t s_dst[kTileRows + 1];   // survivor r: first destination byte inside the tile's dense range; [count] = total
+    __shared__ __align__(16) uint8_t s_stage[kStrChunk + 16];
     __shared__ uint32_t s_warp[kWarps];
     __shared__ uint64_t s_bexcl;
 
@@ -119,35 +121,91 @@ static __global__ void __launch_bounds__(kBlock, 4) string_gather_kernel(const _
             if (tile == (int64_t)gridDim.x - 1) *p.bytes_total_out = (unsigned long long)(bexcl + bytes_total);
         }
     }
-    __syncthreads();
-    if (cnt_lim == 0u) return;
-    const uint64_t bexcl = s_bexcl;
-
-    // new offsets (rank order) + copy descriptors
+    // copy descriptors (independent of the global prefix, so they are built while warp 0 looks back)
     if (selbyte != 0u) {
         uint32_t r = r0, b = b0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             if ((selbyte >> i) & 1u) {
                 if (r < cnt_lim) {
-                    const int32_t len = ((vbits >> i) & 1u) ? (off[i + 1] - off[i]) : 0;
-                    s_src[r] = off[i]; s_dst[r] = (int32_t)b; s_len[r] = len;
-                    b += (uint32_t)len;
-                    p.out_offsets[rexcl - rbase + r + 1] = (int32_t)(bexcl + b);
+                    s_src[r] = off[i]; s_dst[r] = b;
+                    b += ((vbits >> i) & 1u) ? (uint32_t)(off[i + 1] - off[i]) : 0u;
                 }
                 ++r;
             }
         }
     }
+    if (tid == 0) s_dst[cnt_lim] = bytes_total;
     __syncthreads();
+    if (cnt_lim == 0u) return;
+    const uint64_t bexcl = s_bexcl;
 
-    // byte copy: one warp per string, lanes stride the bytes (destination range of the tile is dense)
-    uint8_t* dst_base = p.out_data + bexcl;
-    for (uint32_t q = warp; q < cnt_lim; q += kWarps) {
-        const int32_t len = s_len[q];
-        const uint8_t* src = p.data + s_src[q];
-        uint8_t* dst = dst_base + s_dst[q];
-        for (int32_t j = lane; j < len; j += 32) dst[j] = __ldg(src + j);
+    // new offsets, in rank order: out_offsets[first survivor of the tile + r + 1] = end of survivor r (coalesced)
+    {
+        int32_t* oo = p.out_offsets + (rexcl - rbase) + 1;
+        for (uint32_t r = tid; r < cnt_lim; r += kBlock) oo[r] = (int32_t)(bexcl + s_dst[r + 1]);
+    }
+
+    // Byte copy, staged through shared memory.  The tile's destination range is dense, so it is assembled in a staging buffer
+    // laid out like the destination modulo 16 bytes and flushed with aligned 16-byte stores; only the first and last unit of
+    // a tile (shared with the neighbouring tiles) are written byte-wise.  Gather side: every lane holds the descriptor of one
+    // survivor of a 256-survivor group; the warp walks its 32 descriptors by shuffle, four strings (<= 64 bytes each) in
+    // flight, lanes over the bytes of a string.  Ranges longer than the staging buffer take several chunks.
+    const uint32_t pad = (uint32_t)(reinterpret_cast<uintptr_t>(p.out_data + bexcl) & 15u);
+    uint32_t g_lo = 0;
+#pragma unroll 1
+    for (uint32_t c0 = 0; c0 < bytes_total; c0 += kStrChunk) {
+        const uint32_t c1 = min(bytes_total, c0 + kStrChunk);
+        uint32_t g = g_lo;
+#pragma unroll 1
+        for (; g * kBlock < cnt_lim && s_dst[g * kBlock] < c1; ++g) {
+            const uint32_t q = g * kBlock + (uint32_t)tid;
+            uint32_t my_d = 0, my_n = 0, my_s = 0;
+            if (q < cnt_lim) {
+                const uint32_t d = s_dst[q], e = s_dst[q + 1];
+                const uint32_t lo = max(d, c0), hi = min(e, c1);
+                if (lo < hi) { my_n = hi - lo; my_d = lo - c0 + pad; my_s = (uint32_t)s_src[q] + (lo - d); }
+            }
+            if (__ballot_sync(0xFFFFFFFFu, my_n != 0u) == 0u) continue;
+#pragma unroll 1
+            for (int j = 0; j < 32; j += 4) {
+                uint32_t n[4], d[4], lo[4], hi[4];
+                const uint8_t* src[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    n[u] = __shfl_sync(0xFFFFFFFFu, my_n, j + u);
+                    d[u] = __shfl_sync(0xFFFFFFFFu, my_d, j + u);
+                    src[u] = p.data + __shfl_sync(0xFFFFFFFFu, my_s, j + u);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    lo[u] = (uint32_t)lane < n[u] ? __ldg(src[u] + lane) : 0u;
+                    hi[u] = (uint32_t)lane + 32u < n[u] ? __ldg(src[u] + 32 + lane) : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if ((uint32_t)lane < n[u]) s_stage[d[u] + lane] = (uint8_t)lo[u];
+                    if ((uint32_t)lane + 32u < n[u]) s_stage[d[u] + 32 + lane] = (uint8_t)hi[u];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    for (uint32_t k = 64u + lane; k < n[u]; k += 32u) s_stage[d[u] + k] = __ldg(src[u] + k);  // long strings: the rest
+            }
+        }
+        g_lo = g > g_lo ? g - 1u : g_lo;  // the last group may straddle the chunk boundary
+        __syncthreads();
+        uint8_t* const gbase = p.out_data + bexcl + c0 - pad;  // 16-byte aligned
+        const uint32_t end = pad + (c1 - c0);
+        for (uint32_t u = tid; u * 16u < end; u += kBlock) {
+            const uint32_t b0 = u * 16u, b1 = b0 + 16u;
+            if (b0 >= pad && b1 <= end) {
+                const uint4 v = *reinterpret_cast<const uint4*>(s_stage + b0);
+                asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(gbase + b0), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+            } else {
+                for (uint32_t k = max(b0, pad); k < min(b1, end); ++k) gbase[k] = s_stage[k];
+            }
+        }
+        __syncthreads();
     }
 }
 

@@ -58,6 +58,55 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
     return woff + incl - v;
 }
 
+// predicated byte moves with the predicate, the immediate offset and the 32-bit shared address spelled out: left to the compiler
+// the address arithmetic is re-done under every predicate and the shared pointer goes through a generic-address conversion
+template <int IMM>
+__device__ __forceinline__ uint32_t ldg_u8_lt(const uint8_t* p, uint32_t k, uint32_t n) {
+    uint32_t v;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %2, %3;\n\t@q ld.global.nc.u8 %0, [%1+%4];\n\t}" : "=r"(v) : "l"(p), "r"(k), "r"(n), "n"(IMM));
+    return v;
+}
+template <int IMM>
+__device__ __forceinline__ void sts_u8_lt(uint32_t addr, uint32_t v, uint32_t k, uint32_t n) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %2, %3;\n\t@q st.shared.u8 [%0+%4], %1;\n\t}" ::"r"(addr), "r"(v), "r"(k), "r"(n), "n"(IMM) : "memory");
+}
+
+// One warp copies the (clipped) strings described by its 32 lanes — lane i: my_n bytes from data + my_s to shared address
+// stage_addr + my_d — with L lanes per string: 32 / L strings per step, lane `sub` of a string moves bytes sub, sub + L, ...;
+// the first five rounds are unrolled with every load issued before the first store (5 x 32/L sectors in flight per warp),
+// longer strings loop on.
+template <int L>
+__device__ __forceinline__ void copy_descriptors(const uint8_t* __restrict__ data, uint32_t stage_addr, uint32_t my_n, uint32_t my_d, uint32_t my_s, int lane) {
+    constexpr int S = 32 / L;   // strings per step
+    const uint32_t sub = (uint32_t)lane % L;
+    const int which = lane / L;
+    const uint32_t k1 = sub + L, k2 = sub + 2 * L, k3 = sub + 3 * L, k4 = sub + 4 * L;
+#pragma unroll 1
+    for (int j = 0; j < 32; j += S) {
+        const uint32_t n = __shfl_sync(0xFFFFFFFFu, my_n, j + which);
+        const uint32_t nmax = __reduce_max_sync(0xFFFFFFFFu, n);
+        if (nmax == 0u) continue;
+        const uint32_t d = stage_addr + __shfl_sync(0xFFFFFFFFu, my_d, j + which) + sub;
+        const uint8_t* const src = data + __shfl_sync(0xFFFFFFFFu, my_s, j + which) + sub;
+        const uint32_t v0 = ldg_u8_lt<0>(src, sub, n);
+        const uint32_t v1 = ldg_u8_lt<L>(src, k1, n);
+        const uint32_t v2 = ldg_u8_lt<2 * L>(src, k2, n);
+        const uint32_t v3 = ldg_u8_lt<3 * L>(src, k3, n);
+        const uint32_t v4 = ldg_u8_lt<4 * L>(src, k4, n);
+        sts_u8_lt<0>(d, v0, sub, n);
+        sts_u8_lt<L>(d, v1, k1, n);
+        sts_u8_lt<2 * L>(d, v2, k2, n);
+        sts_u8_lt<3 * L>(d, v3, k3, n);
+        sts_u8_lt<4 * L>(d, v4, k4, n);
+        if (nmax > (uint32_t)(5 * L)) {
+            for (uint32_t k = sub + 5 * L; k < n; k += L) {
+                const uint32_t v = ldg_u8_lt<0>(src + (k - sub), 0u, 1u);
+                sts_u8_lt<0>(d + (k - sub), v, 0u, 1u);
+            }
+        }
+    }
+}
+
 constexpr uint32_t kStrChunk = 24 * 1024;   // staging bytes per pass (a 2048-row tile of ~24-byte strings at 50 % fits in one)
 
 static __global__ void __launch_bounds__(kBlock, 5) string_gather_kernel(const __grid_constant__ StrGatherParams p) {
@@ -149,9 +198,13 @@ static __global__ void __launch_bounds__(kBlock, 5) string_gather_kernel(const _
     // Byte copy, staged through shared memory.  The tile's destination range is dense, so it is assembled in a staging buffer
     // laid out like the destination modulo 16 bytes and flushed with aligned 16-byte stores; only the first and last unit of
     // a tile (shared with the neighbouring tiles) are written byte-wise.  Gather side: every lane holds the descriptor of one
-    // survivor of a 256-survivor group; the warp walks its 32 descriptors by shuffle, four strings (<= 64 bytes each) in
-    // flight, lanes over the bytes of a string.  Ranges longer than the staging buffer take several chunks.
+    // survivor of a 256-survivor group and the warp walks its 32 descriptors by shuffle, L lanes per string (L chosen from
+    // the tile's mean survivor length), 32 / L strings and five byte rounds in flight per step (copy_descriptors).
+    // Ranges longer than the staging buffer take several chunks.
+    const uint32_t mean_len = bytes_total / cnt_lim;
+    const int lanes_per_string = mean_len <= 10u ? 4 : (mean_len <= 28u ? 8 : (mean_len <= 80u ? 16 : 32));
     const uint32_t pad = (uint32_t)(reinterpret_cast<uintptr_t>(p.out_data + bexcl) & 15u);
+    const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(s_stage);
     uint32_t g_lo = 0;
 #pragma unroll 1
     for (uint32_t c0 = 0; c0 < bytes_total; c0 += kStrChunk) {
@@ -167,30 +220,10 @@ static __global__ void __launch_bounds__(kBlock, 5) string_gather_kernel(const _
                 if (lo < hi) { my_n = hi - lo; my_d = lo - c0 + pad; my_s = (uint32_t)s_src[q] + (lo - d); }
             }
             if (__ballot_sync(0xFFFFFFFFu, my_n != 0u) == 0u) continue;
-#pragma unroll 1
-            for (int j = 0; j < 32; j += 4) {
-                uint32_t n[4], d[4], lo[4], hi[4];
-                const uint8_t* src[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    n[u] = __shfl_sync(0xFFFFFFFFu, my_n, j + u);
-                    d[u] = __shfl_sync(0xFFFFFFFFu, my_d, j + u);
-                    src[u] = p.data + __shfl_sync(0xFFFFFFFFu, my_s, j + u);
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    lo[u] = (uint32_t)lane < n[u] ? __ldg(src[u] + lane) : 0u;
-                    hi[u] = (uint32_t)lane + 32u < n[u] ? __ldg(src[u] + 32 + lane) : 0u;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if ((uint32_t)lane < n[u]) s_stage[d[u] + lane] = (uint8_t)lo[u];
-                    if ((uint32_t)lane + 32u < n[u]) s_stage[d[u] + 32 + lane] = (uint8_t)hi[u];
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    for (uint32_t k = 64u + lane; k < n[u]; k += 32u) s_stage[d[u] + k] = __ldg(src[u] + k);  // long strings: the rest
-            }
+            if (lanes_per_string == 8) copy_descriptors<8>(p.data, stage_addr, my_n, my_d, my_s, lane);
+            else if (lanes_per_string == 16) copy_descriptors<16>(p.data, stage_addr, my_n, my_d, my_s, lane);
+            else if (lanes_per_string == 4) copy_descriptors<4>(p.data, stage_addr, my_n, my_d, my_s, lane);
+            else copy_descriptors<32>(p.data, stage_addr, my_n, my_d, my_s, lane);
         }
         g_lo = g > g_lo ? g - 1u : g_lo;  // the last group may straddle the chunk boundary
         __syncthreads();

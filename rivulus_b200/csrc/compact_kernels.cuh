@@ -21,8 +21,11 @@
 //                          (survivor, column) pairs are spread over the lanes so that every gather load of the tile is
 //                          in flight at once; dead lines are never touched.
 //
-// Bit-packed columns (validity bitmaps, Boolean values) are compacted with one warp REDUX.OR per 32 rows into
-// per-lane output words; words owned by a warp's run are stored, the two boundary words are OR-ed atomically.
+//   compact_bits_kernel    bit-packed columns (validity bitmaps, Boolean values) of ALL tiles: one warp per tile, lane <-> two
+//                          32-row words.  Every lane compresses its own words with a branch-free parallel-suffix bit compress
+//                          (the five move masks depend only on the selection word, so they are built once per tile and shared
+//                          by all bit columns), the 64 variable-length pieces are merged at their bit offsets in a per-warp
+//                          shared buffer, interior output words are stored, the two boundary words OR-ed atomically.
 #pragma once
 #include "scan_kernels.cuh"
 
@@ -31,7 +34,7 @@ namespace rvl {
 constexpr int kCompactMaxWarps = 16;                      // consumer warps of the dense kernel: 8 (256 rows each per tile) or 16 (128 rows)
 constexpr uint32_t kSlotBytes = kTileRows * 8;            // one column tile
 constexpr int kSparseCap = 256;                           // most survivors a "sparse" tile may hold
-constexpr int kMaxBitSrc = kMaxCol8 + 2 * kMaxBitCols;    // bitmaps a dense launch may read: validity per 8-byte column, in + mask per bit column
+constexpr int kMaxBitSrc = kMaxCol8;                      // bitmaps a dense launch reads: the validity of each 8-byte column
 
 struct CompactParams {
     int64_t n_rows;
@@ -51,8 +54,6 @@ struct CompactParams {
     // dense kernel: every bitmap it reads, listed once; consumer warps stage the next tile's words of each through cp.async
     int32_t n_bsrc;
     int8_t col8_vsrc[kMaxCol8];          // index into bsrc of col8[c].valid, or -1 (no nulls)
-    int8_t bit_in_src[kMaxBitCols];      // ... of bits[b].in   (-1: all ones)
-    int8_t bit_mask_src[kMaxBitCols];    // ... of bits[b].mask (-1: all ones)
     int32_t pad2;
     BitSrc bsrc[kMaxBitSrc];
 };
@@ -287,42 +288,6 @@ __global__ void __launch_bounds__((CW + 1) * 32, CW == 8 ? 2 : 1) compact_dense_
                 if (kp[k]) st_stream(reinterpret_cast<uint64_t*>(ob + off8[k]), v[k]);
         }
 
-        // ---- bit-packed columns: lane j accumulates output word j of this warp's run
-        if (p.n_bits > 0 && wcnt != 0u) {
-            const uint64_t gfirst = prefix + wfirst;  // global index of the warp's first survivor
-            uint32_t lim = wcnt;
-            if (p.limit >= 0) lim = gfirst >= (uint64_t)p.limit ? 0u : (uint32_t)min((uint64_t)wcnt, (uint64_t)p.limit - gfirst);
-            if (lim != 0u) {
-                const uint64_t P = gfirst - base0;
-                const uint32_t sh = (uint32_t)P & 31u;
-                const uint64_t first_word = P >> 5;
-                const uint32_t end = sh + lim;             // bits [sh, end) of the run are ours
-                const uint32_t n_words = (end + 31u) >> 5;  // <= KW + 1
-                for (int b = 0; b < p.n_bits; ++b) {
-                    const BitCol& bc = p.bits[b];
-                    const int s_in = p.bit_in_src[b], s_mask = p.bit_mask_src[b];
-                    uint32_t acc = 0, q = sh;
-#pragma unroll
-                    for (int k = 0; k < KW; ++k) {
-                        const uint32_t in = staged32(s_in, k, cur) & staged32(s_mask, k, cur);
-                        const uint32_t bit = (in >> lane) & (selw[k] >> lane) & 1u;
-                        const uint32_t cw = __reduce_or_sync(0xFFFFFFFFu, bit << __popc(selw[k] & lt));
-                        const uint32_t s = q & 31u;
-                        if ((uint32_t)lane == (q >> 5)) acc |= cw << s;
-                        if (s != 0u && (uint32_t)lane == (q >> 5) + 1u) acc |= cw >> (32u - s);
-                        q += __popc(selw[k]);
-                    }
-                    if ((uint32_t)lane < n_words) {
-                        const uint32_t lo = (uint32_t)lane * 32u;
-                        if (end - lo < 32u) acc &= (1u << (end - lo)) - 1u;  // survivors cut off by the limit
-                        const bool owned = (lane > 0 || sh == 0u) && (lo + 32u <= end);
-                        uint32_t* o = bc.out + first_word + lane;
-                        if (owned) *o = acc;
-                        else if (acc != 0u) atomicOr(o, acc);
-                    }
-                }
-            }
-        }
     }
 }
 
@@ -375,15 +340,97 @@ static __global__ void __launch_bounds__(kBlock) gather_sparse_kernel(const __gr
             for (int u = 0; u < 4; ++u)
                 if (dst[u] != nullptr) st_stream(dst[u], v[u]);
         }
-        const uint32_t n_btask = lim * (uint32_t)p.n_bits;
-        for (uint32_t t = lane; t < n_btask; t += 32) {
-            const uint32_t b = t / lim, e = t - b * lim;
+    }
+}
+
+// ---- bit-packed columns ---------------------------------------------------------------------------------------------------
+// Branch-free bit compress (parallel suffix, Hacker's Delight 7-4): mv[i] are the bits that move right by 2^i in round i.
+struct CompressPlan {
+    uint32_t m;
+    uint32_t mv[5];
+};
+__device__ __forceinline__ CompressPlan compress_plan(uint32_t m) {
+    CompressPlan c;
+    c.m = m;
+    uint32_t mk = ~m << 1;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        uint32_t mp = mk ^ (mk << 1);
+        mp ^= mp << 2; mp ^= mp << 4; mp ^= mp << 8; mp ^= mp << 16;
+        const uint32_t mv = mp & m;
+        c.mv[i] = mv;
+        m = (m ^ mv) | (mv >> (1 << i));
+        mk &= ~mp;
+    }
+    return c;
+}
+// the bits of x selected by the plan's mask, packed towards bit 0 in order
+__device__ __forceinline__ uint32_t compress_bits(uint32_t x, const CompressPlan& c) {
+    x &= c.m;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const uint32_t t = x & c.mv[i];
+        x = (x ^ t) | (t >> (1 << i));
+    }
+    return x;
+}
+
+static __global__ void __launch_bounds__(kBlock) compact_bits_kernel(const __grid_constant__ CompactParams p) {
+    __shared__ uint32_t s_out[kWarps][kTileWords + 2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n_tiles = (p.n_rows + kTileRows - 1) / kTileRows;
+    const uint64_t base0 = p.base_in != nullptr ? (uint64_t)*p.base_in : 0ull;
+    uint32_t* const buf = s_out[warp];
+#pragma unroll 1
+    for (int64_t tile = (int64_t)blockIdx.x * kWarps + warp; tile < n_tiles; tile += (int64_t)gridDim.x * kWarps) {
+        const uint64_t info = p.tile_info[tile];
+        if ((info & ((1ull << kInfoShift) - 1ull)) == 0ull) continue;  // no survivor in this tile
+        const uint64_t prefix = p.chunk_base[(uint32_t)tile / (uint32_t)p.tiles_per_chunk] + (info >> kInfoShift);
+        if (p.limit >= 0 && prefix >= (uint64_t)p.limit) continue;
+        const uint32_t* sw = p.sel + tile * kTileWords;
+        const uint32_t w0 = __ldg(sw + lane), w1 = __ldg(sw + 32 + lane);
+        uint32_t e0, e1, total;
+        tile_word_scan(w0, w1, lane, e0, e1, total);
+        // survivors with a tile-local rank >= lim_rel lie beyond the LIMIT
+        const uint32_t lim_rel = p.limit < 0 ? 0xFFFFFFFFu : (uint32_t)min((uint64_t)p.limit - prefix, (uint64_t)0xFFFFFFFFu);
+        const uint32_t n0 = e0 >= lim_rel ? 0u : min((uint32_t)__popc(w0), lim_rel - e0);
+        const uint32_t n1 = e1 >= lim_rel ? 0u : min((uint32_t)__popc(w1), lim_rel - e1);
+        const uint32_t tot = min(total, lim_rel);
+        const uint64_t obase = prefix - base0;            // output bit index of the tile's first survivor
+        const uint32_t sh = (uint32_t)obase & 31u;
+        const uint64_t first_word = obase >> 5;
+        const uint32_t end = sh + tot;                    // bits [sh, end) of the tile's output words are ours
+        const uint32_t n_words = (end + 31u) >> 5;        // <= 65
+        const CompressPlan c0 = compress_plan(w0), c1 = compress_plan(w1);
+        const uint64_t r0 = (uint64_t)tile * kTileRows + (uint64_t)lane * 32u, r1 = r0 + 1024u;
+        for (int b = 0; b < p.n_bits; ++b) {
             const BitCol& bc = p.bits[b];
-            const uint64_t row = (uint64_t)(row0 + rows[e]);
-            bool set = true;
-            if (bc.in.words != nullptr) { const uint64_t bit = bc.in.bit0 + row; set = (__ldg(bc.in.words + (bit >> 5)) >> (bit & 31)) & 1u; }
-            if (set && bc.mask.words != nullptr) { const uint64_t bit = bc.mask.bit0 + row; set = (__ldg(bc.mask.words + (bit >> 5)) >> (bit & 31)) & 1u; }
-            if (set) { const uint64_t pos = obase + e; atomicOr(bc.out + (pos >> 5), 1u << (pos & 31)); }
+            uint32_t x0 = compress_bits(load_bits32(bc.in, r0) & load_bits32(bc.mask, r0), c0);
+            uint32_t x1 = compress_bits(load_bits32(bc.in, r1) & load_bits32(bc.mask, r1), c1);
+            if (n0 < 32u) x0 &= (1u << n0) - 1u;
+            if (n1 < 32u) x1 &= (1u << n1) - 1u;
+            buf[lane] = 0u; buf[lane + 32] = 0u;
+            if (lane < 2) buf[64 + lane] = 0u;
+            __syncwarp();
+            if (x0 != 0u) {
+                const uint32_t q = sh + e0, s = q & 31u;
+                atomicOr(&buf[q >> 5], x0 << s);
+                if (s != 0u && (x0 >> (32u - s)) != 0u) atomicOr(&buf[(q >> 5) + 1u], x0 >> (32u - s));
+            }
+            if (x1 != 0u) {
+                const uint32_t q = sh + e1, s = q & 31u;
+                atomicOr(&buf[q >> 5], x1 << s);
+                if (s != 0u && (x1 >> (32u - s)) != 0u) atomicOr(&buf[(q >> 5) + 1u], x1 >> (32u - s));
+            }
+            __syncwarp();
+            for (uint32_t w = (uint32_t)lane; w < n_words; w += 32u) {
+                const uint32_t v = buf[w], lo = w * 32u;
+                const bool owned = (w > 0u || sh == 0u) && (lo + 32u <= end);
+                uint32_t* o = bc.out + first_word + w;
+                if (owned) *o = v;
+                else if (v != 0u) atomicOr(o, v);
+            }
+            __syncwarp();
         }
     }
 }

@@ -242,20 +242,26 @@ static int launch_compaction(const CoreRef& core, CompactParams cp, const uint32
         return (int8_t)cp.n_bsrc++;
     };
     for (int c = 0; c < kMaxCol8; ++c) cp.col8_vsrc[c] = c < cp.n_col8 ? add_src(cp.col8[c].valid) : (int8_t)-1;
-    for (int b = 0; b < kMaxBitCols; ++b) {
-        cp.bit_in_src[b] = b < cp.n_bits ? add_src(cp.bits[b].in) : (int8_t)-1;
-        cp.bit_mask_src[b] = b < cp.n_bits ? add_src(cp.bits[b].mask) : (int8_t)-1;
-    }
     const int smem_budget = (per_sm == 1 ? kDenseSmemMax : 110 * 1024) - (int)dense_stage_bytes(warps, cp.n_bsrc);
     const int max_slots = std::min(14, smem_budget / (int)(kSlotBytes + 16));
     cp.n_slots = std::max(2, std::min(max_slots, core->dense_slots));
-    cp.list = dense_list; cp.list_count = list_counts;
-    if (warps == 16) RVL_TRY(launch_dense_t<16>(core, cp, per_sm));
-    else RVL_TRY(launch_dense_t<8>(core, cp, per_sm));
-    cp.list = sparse_list; cp.list_count = list_counts + 1;
-    gather_sparse_kernel<<<(unsigned)(core->sm_count * 8), kBlock, 0, core->stream>>>(cp);
-    core->launches++;
-    RVL_CUDA_TRY(cudaGetLastError());
+    if (cp.n_col8 > 0) {
+        cp.list = dense_list; cp.list_count = list_counts;
+        if (warps == 16) RVL_TRY(launch_dense_t<16>(core, cp, per_sm));
+        else RVL_TRY(launch_dense_t<8>(core, cp, per_sm));
+        cp.list = sparse_list; cp.list_count = list_counts + 1;
+        gather_sparse_kernel<<<(unsigned)(core->sm_count * 8), kBlock, 0, core->stream>>>(cp);
+        core->launches++;
+        RVL_CUDA_TRY(cudaGetLastError());
+    }
+    if (cp.n_bits > 0) {
+        // bit-packed columns (validity bitmaps, Boolean values) of every tile: one warp per tile
+        const int64_t n_tiles = (cp.n_rows + kTileRows - 1) / kTileRows;
+        const int64_t ctas = std::max<int64_t>(1, std::min<int64_t>((n_tiles + kWarps - 1) / kWarps, (int64_t)core->sm_count * 8));
+        compact_bits_kernel<<<(unsigned)ctas, kBlock, 0, core->stream>>>(cp);
+        core->launches++;
+        RVL_CUDA_TRY(cudaGetLastError());
+    }
     return RVL_OK;
 }
 

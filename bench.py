@@ -350,6 +350,9 @@ def run_e2e(args, ctx, table, preds, proj, rank, world, local_rank, barrier):
         return arr
     structs = [make_structs(b) for b in range(n_batches)]
     d2h = 0
+    staged = 0
+    per_query = []
+    transfer = {"auto": capi.TRANSFER_AUTO, "staged": capi.TRANSFER_STAGED, "zero_copy": capi.TRANSFER_ZERO_COPY}[args.e2e_transfer]
 
     def drain(st, out_rows):
         nonlocal d2h
@@ -365,9 +368,12 @@ def run_e2e(args, ctx, table, preds, proj, rank, world, local_rank, barrier):
         return out_rows + n
 
     def e2e_step():
+        nonlocal staged
         total = []
+        per_query.clear()
         for p in preds:
-            st = ctx.open_stream(dtypes, p, proj, -1, batch_rows=batch_rows, n_staging=3)
+            tq = time.perf_counter()
+            st = ctx.open_stream(dtypes, p, proj, -1, batch_rows=batch_rows, n_staging=3, transfer=transfer)
             out_rows, inflight = 0, 0
             for b in range(n_batches):
                 st.push_structs(structs[b], 5)
@@ -376,7 +382,9 @@ def run_e2e(args, ctx, table, preds, proj, rank, world, local_rank, barrier):
                     out_rows = drain(st, out_rows); inflight -= 1
             while inflight > 0:
                 out_rows = drain(st, out_rows); inflight -= 1
+            staged += st.stats()["h2d_bytes"]
             st.close()
+            per_query.append((time.perf_counter() - tq) * 1e3)
             total.append(out_rows)
         return total
 
@@ -384,6 +392,7 @@ def run_e2e(args, ctx, table, preds, proj, rank, world, local_rank, barrier):
     e2e_step()  # warm-up (allocations, pool growth)
     barrier(); torch.cuda.synchronize()
     d2h = 0
+    staged = 0
     t0 = time.perf_counter()
     stream = torch.cuda.ExternalStream(ctx.cuda_stream(), device=torch.device("cuda", local_rank))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -402,9 +411,15 @@ def run_e2e(args, ctx, table, preds, proj, rank, world, local_rank, barrier):
     h2d = e2e_rows * BYTES_PER_ROW_IN * len(THRESHOLDS)
     for b in host_bufs + out_bufs:
         b.free()
+    in_place = staged // steps < h2d
     return {"value": value, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h // steps, "steps": steps,
             "rows_per_gpu": e2e_rows, "batch_rows": batch_rows, "ms_per_step": wall * 1000.0 / steps,
-            "h2d_gbs": h2d * steps / wall / 1e9, "survivors": totals,
+            "h2d_gbs": h2d * steps / wall / 1e9, "survivors": totals, "transfer": args.e2e_transfer, "per_query_ms_last_step": [round(x, 2) for x in per_query],
+            "h2d_copy_engine_bytes_per_step": staged // steps,
+            "h2d_note": ("h2d_bytes_per_step = the host-resident input of the step (every column of every query); the predicate column "
+                         "crosses on the copy engine (h2d_copy_engine_bytes_per_step), the projected columns are read in place by the "
+                         "kernels over PCIe, which fetch only the lines holding survivors (dense tiles whole)") if in_place else
+                        "every input byte crosses on the copy engine",
             "path": "rvl_stream_open/push/next + rvl_batch_download_column, pinned host buffers, 3 staging slots",
             "timing": "host wall clock around the synchronised region (H2D, kernels, D2H all inside)"}
 
@@ -422,6 +437,7 @@ def main():
     ap.add_argument("--e2e-batch-rows", type=int, default=16 << 20)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-transfer", default="auto", choices=["auto", "staged", "zero_copy"], help="rvl_stream_config.transfer of the e2e leg")
     ap.add_argument("--plan", default="auto", choices=["auto", "fused", "two_pass"], help="execution plan of rvl_filter_project (rvl_plan)")
     ap.add_argument("--sparse-max", type=int, default=None)
     ap.add_argument("--dense-slots", type=int, default=None)

@@ -45,7 +45,10 @@ class RvlPredicate(C.Structure):
 
 
 class RvlStreamConfig(C.Structure):
-    _fields_ = [("batch_rows", C.c_int64), ("n_staging", C.c_int32), ("reserved", C.c_int32)]
+    _fields_ = [("batch_rows", C.c_int64), ("n_staging", C.c_int32), ("transfer", C.c_int32)]
+
+
+TRANSFER_AUTO, TRANSFER_STAGED, TRANSFER_ZERO_COPY = 0, 1, 2
 
 
 PLAN_AUTO, PLAN_FUSED, PLAN_TWO_PASS = 0, 1, 2
@@ -316,8 +319,8 @@ class Context:
         return Batch(self, out)
 
     def open_stream(self, dtypes: Sequence[int], pred, proj: Sequence[int], limit: int = -1, batch_rows: int = 1 << 20,
-                    n_staging: int = 2) -> "Stream":
-        return Stream(self, dtypes, pred, proj, limit, batch_rows, n_staging)
+                    n_staging: int = 2, transfer: int = TRANSFER_AUTO) -> "Stream":
+        return Stream(self, dtypes, pred, proj, limit, batch_rows, n_staging, transfer)
 
 
 class Batch:
@@ -413,12 +416,12 @@ class Batch:
 class Stream:
     """trait DataStream over host batches (execution/stream.rs:25-54) with pinned, overlapped H2D."""
 
-    def __init__(self, ctx: Context, dtypes, pred, proj, limit, batch_rows, n_staging):
+    def __init__(self, ctx: Context, dtypes, pred, proj, limit, batch_rows, n_staging, transfer=TRANSFER_AUTO):
         self.ctx = ctx
         self._h = C.c_void_p()
         d = (C.c_int32 * max(len(dtypes), 1))(*dtypes)
         p = (C.c_int32 * max(len(proj), 1))(*proj)
-        cfg = RvlStreamConfig(batch_rows, n_staging, 0)
+        cfg = RvlStreamConfig(batch_rows, n_staging, transfer)
         check(lib().rvl_stream_open(ctx._h, d, len(dtypes), C.byref(pred) if pred is not None else None, p, len(proj),
                                     C.c_int64(limit), C.byref(cfg), C.byref(self._h)))
 

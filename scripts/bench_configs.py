@@ -11,6 +11,7 @@ Every figure is device time from CUDA events on the library stream (rvl_ctx_prof
 region for the streaming runs.  Prints one JSON object.  Not a bench.py line: these are the per-config numbers DESIGN.md §5 quotes.
 """
 import argparse
+import ctypes as C
 import json
 import os
 import sys
@@ -94,7 +95,7 @@ def run_c5(ctx, rows, reps):
     return out
 
 
-def run_c4(ctx, n_batches, reps):
+def run_c4(ctx, n_batches, reps, transfer=0):
     out = []
     rng = np.random.default_rng(7)
     for batch_rows in (65536, 262144, 1048576):
@@ -111,6 +112,7 @@ def run_c4(ctx, n_batches, reps):
             return [capi.Column(capi.INT64, batch_rows, o, k), capi.Column(capi.INT64, batch_rows, o, a),
                     capi.Column(capi.FLOAT64, batch_rows, o, b), capi.Column(capi.BOOLEAN, batch_rows, o, f)]
 
+        out_pin = [capi.PinnedBuffer(n * 8), capi.PinnedBuffer(n * 8)]
         structs = []
         for i in range(n_batches):
             cs = cols(i)
@@ -122,7 +124,7 @@ def run_c4(ctx, n_batches, reps):
         for label, pred, proj, limit in queries:
             walls, stats, rows_out = [], None, 0
             for r in range(reps + 1):
-                st = ctx.open_stream(dtypes, pred, proj, limit, batch_rows, 3)
+                st = ctx.open_stream(dtypes, pred, proj, limit, batch_rows, 3, transfer)
                 ctx.synchronize()
                 t0 = time.perf_counter()
                 for arr, _keep in structs:
@@ -130,7 +132,12 @@ def run_c4(ctx, n_batches, reps):
                         break
                 res = st.collect()
                 rows_out = res.num_rows()
-                got = [res.download_column(j) for j in range(len(proj))]   # D2H of the result inside the timed region
+                nres = rows_out
+                for j in range(len(proj)):                                 # D2H of the result (pinned destination) inside the timed region
+                    sct = capi.Column(capi.INT64 if res.view(j).dtype == capi.INT64 else capi.FLOAT64, nres, 0,
+                                      out_pin[j].view(np.int64 if res.view(j).dtype == capi.INT64 else np.float64, max(nres, 1))).as_struct()
+                    capi.check(capi.lib().rvl_batch_download_column(ctx._h, res._h, j, C.byref(sct)))
+                got = None
                 ctx.synchronize()
                 t1 = time.perf_counter()
                 stats = st.stats()
@@ -153,7 +160,7 @@ def run_c4(ctx, n_batches, reps):
                         "batches_transferred": stats["batches_pushed"], "batches_ideal": ideal, "h2d_bytes": stats["h2d_bytes"],
                         "h2d_gbs": stats["h2d_bytes"] / ms / 1e6, "stream_bytes_total": batch_bytes * n_batches})
         del structs
-        for x in (kb, ab, bb, fb):
+        for x in (kb, ab, bb, fb, *out_pin):
             x.free()
     return out
 
@@ -167,6 +174,7 @@ def main():
     ap.add_argument("--c4-batches", type=int, default=64)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--plan", default="auto", choices=["auto", "fused", "two_pass"])
+    ap.add_argument("--transfer", default="auto", choices=["auto", "staged", "zero_copy"])
     args = ap.parse_args()
     ctx = capi.Context(0)
     ctx.set_option(capi.OPT_PLAN, {"auto": capi.PLAN_AUTO, "fused": capi.PLAN_FUSED, "two_pass": capi.PLAN_TWO_PASS}[args.plan])
@@ -179,7 +187,8 @@ def main():
         res["c5"] = run_c5(ctx, args.c5_rows, args.reps)
     if "c4" in which:
         ctx.profile_enable(False)
-        res["c4"] = run_c4(ctx, args.c4_batches, max(2, args.reps // 2))
+        res["c4"] = run_c4(ctx, args.c4_batches, max(2, args.reps // 2), {"auto": 0, "staged": 1, "zero_copy": 2}[args.transfer])
+        res["c4_transfer"] = args.transfer
     print(json.dumps(res))
 
 

@@ -303,6 +303,49 @@ def test_stream_limit_stops_transfers(ctx):
     assert_batches_equal(got, ob, "stream early stop")
 
 
+@pytest.mark.parametrize("plan", [capi.PLAN_FUSED, capi.PLAN_TWO_PASS])
+@pytest.mark.parametrize("limit", [-1, 700])
+@pytest.mark.parametrize("op,lit", [(">", 950), (">", 500), ("<=", 100)])
+def test_stream_zero_copy_transfer(plan, limit, op, lit):
+    """rvl_transfer = ZERO_COPY: projected fixed-width columns are read in place from pinned host memory (the predicate column and
+    strings are staged, the unused column never crosses the bus); same rows, order, nulls and bitmap rule as the staged path and
+    as the oracle.  Sliced pushes (bit offsets that are not multiples of 8) included."""
+    ctx = capi.Context(0)
+    ctx.set_option(capi.OPT_PLAN, plan)
+    try:
+        rng = np.random.default_rng(1234 + limit)
+        batches, keep = [], []
+        for n in [40_000, 1, 65_536, 0, 12_345]:
+            batches.append([random_col(rng, "i64", n, 0.1, lo=0, hi=1000), random_col(rng, "f64", n, 0.1), random_col(rng, "bool", n, 0.2),
+                            random_col(rng, "i64", n, 0.0), random_col(rng, "str", n, 0.1, maxlen=12), random_col(rng, "f64", n, 0.5)])
+        dtypes = [capi.INT64, capi.FLOAT64, capi.BOOLEAN, capi.INT64, capi.STRING, capi.FLOAT64]
+        proj = [1, 2, 3, 4, 0]        # column 5 is never looked at; column 0 is predicate + projected (staged once)
+        outs = {}
+        for mode in (capi.TRANSFER_STAGED, capi.TRANSFER_ZERO_COPY):
+            st = ctx.open_stream(dtypes, capi.predicate(0, op, lit), proj, limit, batch_rows=65_536, n_staging=2, transfer=mode)
+            for b in batches:
+                gcols = [c.gpu() for c in b]
+                for gc in gcols:
+                    for f in ("values", "validity", "offsets", "data"):
+                        a = getattr(gc, f)
+                        if a is not None and a.size:
+                            v, owner = capi.pinned_like(a)
+                            setattr(gc, f, v)
+                            keep.append(owner)
+                st.push(gcols)
+            outs[mode] = st.collect()
+            stats = st.stats()
+            st.close()
+            if mode == capi.TRANSFER_ZERO_COPY and limit < 0:
+                staged_rows = sum(b[0].length for b in batches)
+                assert stats["h2d_bytes"] < staged_rows * (8 + 4 + 12 + 2), "only the predicate column and the strings are staged"
+        want = O.RecordBatch.concat([oracle_batch(b) for b in batches if b[0].length > 0]).filter_project_cmp(0, op, lit, proj, limit)
+        assert_batches_equal(outs[capi.TRANSFER_ZERO_COPY], want, f"zero-copy stream {op} {lit} limit={limit}")
+        assert_batches_equal(outs[capi.TRANSFER_STAGED], want, f"staged stream {op} {lit} limit={limit}")
+    finally:
+        ctx.close()
+
+
 # ------------------------------------------------------------------ sharded (row-range) execution on one GPU
 def test_sharded_two_contexts_one_gpu(ctx):
     rng = np.random.default_rng(31)

@@ -777,8 +777,87 @@ static std::string wrap_stream_err(const std::string& w) {
     if (w.rfind("Stream execution error:", 0) == 0) return "Stream error: " + w;
     return w;
 }
+// collect() of [Limit] -> [Select] -> [Filter] -> DataFrame source as ONE device pipeline (rvl_stream_*): batches are pushed
+// straight from the Series' host buffers through pinned multi-slot staging, H2D overlaps the fused Filter + Select + Limit
+// kernel of the previous batch, the running row count stays on the device and a reached LIMIT stops further transfers
+// (LimitStream, streaming.rs:269-271).  Rows, order, nulls and schema are those of the operator chain below (execute());
+// any plan shape or error case outside the pattern takes that chain, so every reference error surfaces unchanged.
+static bool g_stream_fusion = true;
+void set_stream_fusion(bool on) { g_stream_fusion = on; }
+
+static std::optional<RecordBatch> try_fused_collect(const StreamingPhysicalPlan& top) {
+    using K = StreamingPhysicalPlan;
+    if (!g_stream_fusion) return std::nullopt;
+    const K* p = &top;
+    std::optional<size_t> limit;
+    const std::vector<std::string>* sel = nullptr;
+    const std::string* pred = nullptr;
+    if (p->kind == K::Limit) { if (p->n == 0) return std::nullopt; limit = p->n; p = p->input.get(); }
+    if (p->kind == K::Select) { sel = &p->columns; p = p->input.get(); }
+    if (p->kind == K::Filter) { pred = &p->predicate_column; p = p->input.get(); }
+    if (p->kind != K::DataFrameSource || p->df.is_empty() || p->batch_size == 0) return std::nullopt;
+    if (!limit && !sel && !pred) return std::nullopt;
+    const DataFrame& df = p->df;
+    const size_t ncols = df.columns().size();
+    auto in_schema = std::make_shared<Schema>();
+    std::vector<int32_t> dtypes;
+    for (const auto& s : df.columns()) {
+        in_schema->fields.push_back(Field{s.name(), exec_type_of(s.dtype()), true});
+        dtypes.push_back(rvl_dtype_of(s.dtype()));
+        if (s.dtype() == DataType::Null) return std::nullopt;
+    }
+    rvl_predicate rp{};
+    rp.mode = RVL_PRED_TRUE;
+    if (pred) {
+        auto i = in_schema->index_of(*pred);
+        if (!i || in_schema->fields[*i].data_type != ExecType::Boolean) return std::nullopt;  // the chain raises the reference's error
+        rp.mode = RVL_PRED_BOOL_COLUMN; rp.column = (int32_t)*i;
+    }
+    std::vector<int32_t> proj;
+    auto out_schema = std::make_shared<Schema>();
+    if (sel) {
+        std::set<std::string> seen;
+        for (const auto& name : *sel) {
+            auto i = in_schema->index_of(name);
+            if (!i || !seen.insert(name).second) return std::nullopt;
+            proj.push_back((int32_t)*i);
+            out_schema->fields.push_back(in_schema->fields[*i]);
+        }
+        if (proj.empty()) return std::nullopt;
+    } else {
+        for (size_t i = 0; i < ncols; ++i) proj.push_back((int32_t)i);
+        out_schema = in_schema;
+    }
+    // dataframe_to_batches converts every batch before the first one is pulled: a Float64 series holding an Int64 panics (streaming.rs:189)
+    for (const auto& s : df.columns())
+        if (s.is_mixed())
+            for (size_t i = 0; i < s.len(); ++i)
+                if (s.at(i).tag == AnyValue::kInt64) throw Error("Type mismatch in Float64 series", true);
+
+    const ContextRef ctx = p->ctx ? p->ctx : Context::shared(0);
+    const size_t rows = df.height(), batch = std::max(p->batch_size, K::kCollectBatchRows);
+    rvl_stream_config cfg{};
+    cfg.batch_rows = (int64_t)std::min(batch, rows); cfg.n_staging = 3; cfg.transfer = RVL_TRANSFER_AUTO;
+    rvl_stream* st = nullptr;
+    check(rvl_stream_open(ctx->handle(), dtypes.data(), (int32_t)ncols, &rp, proj.data(), (int32_t)proj.size(),
+                          limit ? (int64_t)*limit : -1, &cfg, &st));
+    struct Closer { rvl_stream* s; ~Closer() { rvl_stream_close(s); } } closer{st};
+    std::vector<rvl_column> cols(ncols);
+    for (size_t start = 0; start < rows; start += batch) {
+        const size_t len = std::min(batch, rows - start);
+        for (size_t c = 0; c < ncols; ++c) cols[c] = df.columns()[c].as_column(start, len, /*flatten_nulls=*/true);
+        int32_t accepted = 0;
+        check(rvl_stream_push(st, cols.data(), (int32_t)ncols, &accepted));
+        if (!accepted) break;  // LIMIT reached on the device: nothing more is transferred
+    }
+    rvl_batch* out = nullptr;
+    check(rvl_stream_collect(st, &out));
+    return RecordBatch::adopt(ctx, out_schema, out);
+}
+
 RecordBatch StreamingPhysicalPlan::collect() const {  // streaming.rs:235-238
     if (batch_size == 0 && kind == DataFrameSource) throw Error("attempt to divide by zero", true);
+    if (auto fused = try_fused_collect(*this)) return *fused;
     auto s = build_stream(*this, kCollectBatchRows);
     try { return collect_stream_batches(ctx ? ctx : Context::shared(0), *s); }
     catch (const Error& e) { if (e.panic) throw; throw Error(wrap_stream_err(e.what())); }

@@ -287,6 +287,7 @@ struct StreamingPhysicalPlan {  // streaming.rs:28-68, 290-333
     DataStreamRef execute() const;                      // :70-133 (one operator object per node, batches of `batch_size`)
     // :235-238.  The result is the concatenation of every batch, so it does not depend on the batch size: plans rooted
     // at a DataFrame source run with batches of at least kCollectBatchRows rows (fewer, larger kernel launches).
+    // [Limit] -> [Select] -> [Filter] over a DataFrame source runs as one pinned, overlapped device pipeline (rvl_stream_*).
     RecordBatch collect() const;
     std::vector<RecordBatch> collect_batches() const;   // :240-243 (honours batch_size: batch boundaries are visible)
     static constexpr size_t kCollectBatchRows = 1 << 20;
@@ -323,6 +324,9 @@ class LazyFrame {  // logical_plan/builder.rs:11-114
     LogicalPlan plan_;
     ContextRef ctx_;
 };
+
+// collect() of streaming plans: fuse the operator chain into one rvl_stream pipeline (default on; off = one operator per node)
+void set_stream_fusion(bool on);
 
 // kernels launched by the default context of `device` so far (tests assert the GPU actually ran)
 int64_t launch_count(int device = 0);

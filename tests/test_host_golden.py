@@ -207,6 +207,28 @@ def test_random_streaming_queries_match_oracle(seed):
         assert got == want, (seed, q, sel, lim, fcol, shape)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("fusion", [True, False])
+def test_streaming_fused_pipeline_equals_operator_chain(fusion):
+    """collect_streaming() over a DataFrame larger than one staging batch (3.2 M rows, 1 Mi-row batches), with LIMIT inside the
+    second batch and with none: the fused rvl_stream pipeline and the reference-shaped operator chain give the oracle's rows."""
+    from oracle import oracle as O
+    spec = [("k", capi.SYNTH_KEY1000, 0, 10), ("x", capi.SYNTH_F64, 1, 10), ("flag", capi.SYNTH_BOOL, 2, 10), ("name", capi.SYNTH_STR, 3, 10)]
+    n = 2_400_000
+    F.set_stream_fusion(fusion)
+    try:
+        launches = F.launch_count()
+        for lim in (None, 700_000, 1):
+            def build(mod, lim=lim):
+                lf = mod.LazyFrame.from_dataframe(mod.DataFrame.synth(spec, n, row0=5)).filter(mod.col("flag")).select([mod.col("name"), mod.col("k"), mod.col("x")])
+                return (lf.limit(lim) if lim is not None else lf).collect_streaming()
+            got, want = _outcome(F, F.RivulusError, build), _outcome(O, O.OracleError, build)
+            assert got[0] == "ok" and got == want, (fusion, lim, got[:3], want[:3])
+        assert F.launch_count() > launches
+    finally:
+        F.set_stream_fusion(True)
+
+
 # ------------------------------------------------------------------ BASELINE configs[0] at full size through the user API
 def test_config1_dataframe_ingest_matches_oracle_cpu():
     """Host side only: the synthetic configs[0] DataFrame built columnar by the host layer equals the oracle's AnyValue DataFrame."""

@@ -107,6 +107,54 @@ __device__ __forceinline__ void copy_descriptors(const uint8_t* __restrict__ dat
     }
 }
 
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
+// Short strings (the common case: tens of bytes): ONE LANE PER STRING.  The lane walks the 32-bit words of its destination
+// range in the staging buffer; destination word i is the funnel shift of two consecutive aligned source words (the phase between
+// source and destination alignment is constant along a string), so a whole word moves with one LDG.32 + SHF + STS.32 and the 32
+// lanes of a warp move 32 strings at once — ~4 warp instructions per string instead of ~11 with lanes over bytes.  Only the first
+// and the last word of a string (shared with its neighbours) are written byte-wise.  Source words are read only if they hold
+// one of the string's bytes, so nothing outside the data buffer's words is touched.
+__device__ __forceinline__ void copy_descriptor_per_lane(const uint8_t* __restrict__ data, uint32_t stage_addr, uint32_t n, uint32_t d_off, uint32_t s_off) {
+    const uint32_t d = stage_addr + d_off;           // shared address of our first destination byte
+    const uint32_t head = d & 3u;                    // bytes of destination word 0 in front of it
+    const uint32_t dw = d - head;
+    const uint32_t end = head + n;                   // one past our last byte, relative to dw
+    const uint32_t nw = n != 0u ? (end + 3u) >> 2 : 0u;                       // destination words touched
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(data) + s_off - head;    // source address of destination word 0, byte 0
+    const uint32_t ph = (uint32_t)a0 & 3u;
+    const uint32_t sh = ph * 8u;
+    const uint32_t* const src = reinterpret_cast<const uint32_t*>(a0 - ph);
+    const uint32_t jl = (ph + head) >> 2;                                     // first aligned source word holding one of our bytes
+    const uint32_t nl = n != 0u ? (ph + end + 3u) >> 2 : 0u;                  // one past the last
+    auto L = [&](uint32_t j) -> uint32_t { return (j - jl) < (nl - jl) ? __ldg(src + j) : 0u; };
+    auto put_full = [&](uint32_t i, uint32_t w) {
+        const uint32_t lo = i * 4u;
+        if (lo >= head && lo + 4u <= end) sts_u32(dw + lo, w);
+    };
+    auto put_partial = [&](uint32_t i, uint32_t w) {
+        const uint32_t lo = i * 4u;
+#pragma unroll
+        for (uint32_t b = 0; b < 4u; ++b)
+            if (lo + b >= head && lo + b < end) sts_u8(dw + lo + b, w >> (8u * b));
+    };
+    const uint32_t nmax = __reduce_max_sync(0xFFFFFFFFu, nw);
+    uint32_t prev = nl > jl && jl == 0u ? __ldg(src) : 0u;
+#pragma unroll 1
+    for (uint32_t i0 = 0; i0 < nmax; i0 += 4u) {
+        const uint32_t l1 = L(i0 + 1u), l2 = L(i0 + 2u), l3 = L(i0 + 3u), l4 = L(i0 + 4u);
+        put_full(i0, __funnelshift_r(prev, l1, sh));
+        put_full(i0 + 1u, __funnelshift_r(l1, l2, sh));
+        put_full(i0 + 2u, __funnelshift_r(l2, l3, sh));
+        put_full(i0 + 3u, __funnelshift_r(l3, l4, sh));
+        prev = l4;
+    }
+    // the two boundary words
+    if (nw != 0u && (head != 0u || end < 4u)) put_partial(0u, __funnelshift_r(L(0u), L(1u), sh));
+    if (nw > 1u && (end & 3u) != 0u) put_partial(nw - 1u, __funnelshift_r(L(nw - 1u), L(nw), sh));
+}
+
 constexpr uint32_t kStrChunk = 24 * 1024;   // staging bytes per pass (a 2048-row tile of ~24-byte strings at 50 % fits in one)
 
 static __global__ void __launch_bounds__(kBlock, 5) string_gather_kernel(const __grid_constant__ StrGatherParams p) {
@@ -198,11 +246,10 @@ static __global__ void __launch_bounds__(kBlock, 5) string_gather_kernel(const _
     // Byte copy, staged through shared memory.  The tile's destination range is dense, so it is assembled in a staging buffer
     // laid out like the destination modulo 16 bytes and flushed with aligned 16-byte stores; only the first and last unit of
     // a tile (shared with the neighbouring tiles) are written byte-wise.  Gather side: every lane holds the descriptor of one
-    // survivor of a 256-survivor group and the warp walks its 32 descriptors by shuffle, L lanes per string (L chosen from
-    // the tile's mean survivor length), 32 / L strings and five byte rounds in flight per step (copy_descriptors).
+    // survivor of a 256-survivor group; short strings are moved one lane per string, word-wise (copy_descriptor_per_lane), long
+    // ones cooperatively, the warp walking its 32 descriptors with all lanes over the bytes of one string (copy_descriptors<32>).
     // Ranges longer than the staging buffer take several chunks.
-    const uint32_t mean_len = bytes_total / cnt_lim;
-    const int lanes_per_string = mean_len <= 10u ? 4 : (mean_len <= 28u ? 8 : (mean_len <= 80u ? 16 : 32));
+    const bool per_lane = bytes_total / cnt_lim <= 96u;   // mean survivor length: short strings go one lane per string
     const uint32_t pad = (uint32_t)(reinterpret_cast<uintptr_t>(p.out_data + bexcl) & 15u);
     const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(s_stage);
     uint32_t g_lo = 0;
@@ -220,9 +267,7 @@ static __global__ void __launch_bounds__(kBlock, 5) string_gather_kernel(const _
                 if (lo < hi) { my_n = hi - lo; my_d = lo - c0 + pad; my_s = (uint32_t)s_src[q] + (lo - d); }
             }
             if (__ballot_sync(0xFFFFFFFFu, my_n != 0u) == 0u) continue;
-            if (lanes_per_string == 8) copy_descriptors<8>(p.data, stage_addr, my_n, my_d, my_s, lane);
-            else if (lanes_per_string == 16) copy_descriptors<16>(p.data, stage_addr, my_n, my_d, my_s, lane);
-            else if (lanes_per_string == 4) copy_descriptors<4>(p.data, stage_addr, my_n, my_d, my_s, lane);
+            if (per_lane) copy_descriptor_per_lane(p.data, stage_addr, my_n, my_d, my_s);
             else copy_descriptors<32>(p.data, stage_addr, my_n, my_d, my_s, lane);
         }
         g_lo = g > g_lo ? g - 1u : g_lo;  // the last group may straddle the chunk boundary

@@ -197,6 +197,11 @@ def test_strings_long_and_empty(ctx):
     cols = [random_col(rng, "f64", n, 0.1), Col("str", n, None, valid, strings), Col("str", n, None, None, ["ü€🦀".encode()] * n)]
     run_cmp(ctx, cols, 0, ">", 300.0, [1, 2, 0], tag="strings")
     run_cmp(ctx, cols, 0, "<", 300.0, [1], tag="strings nulls pass <")
+    # medium strings (0..90 bytes, every alignment phase): the one-lane-per-string word copy, tiles spanning several staging chunks
+    mid = [bytes(rng.integers(97, 123, int(rng.integers(0, 91))).astype(np.uint8)) for _ in range(n)]
+    cols = [random_col(rng, "f64", n, 0.1), Col("str", n, None, valid, mid)]
+    for op, lit in ((">", 100.0), (">", 700.0), ("<", 980.0)):
+        run_cmp(ctx, cols, 0, op, lit, [1], tag=f"medium strings {op} {lit}")
 
 
 def test_predicate_mask_kernel(ctx):

@@ -157,11 +157,34 @@ __device__ __forceinline__ void copy_descriptor_per_lane(const uint8_t* __restri
 
 constexpr uint32_t kStrChunk = 24 * 1024;   // staging bytes per pass (a 2048-row tile of ~24-byte strings at 50 % fits in one)
 
+// the same for two values at once (one pair of barriers instead of two)
+__device__ __forceinline__ void block_exclusive_scan2(uint32_t a, uint32_t b, uint32_t* s_wa, uint32_t* s_wb, uint32_t& ea, uint32_t& eb,
+                                                      uint32_t& ta, uint32_t& tb) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t ia = a, ib = b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t na = __shfl_up_sync(0xFFFFFFFFu, ia, o), nb = __shfl_up_sync(0xFFFFFFFFu, ib, o);
+        if (lane >= o) { ia += na; ib += nb; }
+    }
+    if (lane == 31) { s_wa[warp] = ia; s_wb[warp] = ib; }
+    __syncthreads();
+    uint32_t oa = 0, ob = 0, sa = 0, sb = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+        const uint32_t ca = s_wa[w], cb = s_wb[w];
+        oa += (w < warp) ? ca : 0u; ob += (w < warp) ? cb : 0u;
+        sa += ca; sb += cb;
+    }
+    __syncthreads();
+    ea = oa + ia - a; eb = ob + ib - b; ta = sa; tb = sb;
+}
+
 static __global__ void __launch_bounds__(kBlock, 5) string_gather_kernel(const __grid_constant__ StrGatherParams p) {
     __shared__ int32_t s_src[kTileRows];        // survivor r: first source byte
     __shared__ uint32_t s_dst[kTileRows + 1];   // survivor r: first destination byte inside the tile's dense range; [count] = total
     __shared__ __align__(16) uint8_t s_stage[kStrChunk + 16];
-    __shared__ uint32_t s_warp[kWarps];
+    __shared__ uint32_t s_warp[kWarps], s_warp2[kWarps];
     __shared__ uint64_t s_bexcl;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -177,11 +200,6 @@ static __global__ void __launch_bounds__(kBlock, 5) string_gather_kernel(const _
     if (p.chunk_base != nullptr) rexcl = p.chunk_base[tile / p.tiles_per_chunk] + (rexcl >> 12);
     const uint64_t rbase = p.row_base_in != nullptr ? (uint64_t)*p.row_base_in : 0ull;
 
-    uint32_t cnt_total;
-    const uint32_t r0 = block_exclusive_scan(__popc(selbyte), s_warp, cnt_total);
-    uint32_t cnt_lim = cnt_total;
-    if (p.limit >= 0) cnt_lim = rexcl >= (uint64_t)p.limit ? 0u : (uint32_t)min((uint64_t)cnt_total, (uint64_t)p.limit - rexcl);
-
     // survivor lengths of this thread's rows (nulls are zero-length: string.rs:33-36)
     int32_t off[9];
     uint32_t my_bytes = 0;
@@ -190,6 +208,18 @@ static __global__ void __launch_bounds__(kBlock, 5) string_gather_kernel(const _
 #pragma unroll
         for (int i = 0; i < 9; ++i) off[i] = (row0 + i <= p.n_rows) ? __ldg(p.offsets + row0 + i) : 0;
         if (p.valid.words != nullptr) vbits = load_bits32(p.valid, (uint64_t)row0) & 0xFFu;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if ((selbyte >> i) & (vbits >> i) & 1u) my_bytes += (uint32_t)(off[i + 1] - off[i]);
+    }
+    // ranks and byte offsets in one block scan
+    uint32_t r0, b0, cnt_total, bytes_total;
+    block_exclusive_scan2(__popc(selbyte), my_bytes, s_warp, s_warp2, r0, b0, cnt_total, bytes_total);
+    uint32_t cnt_lim = cnt_total;
+    if (p.limit >= 0) cnt_lim = rexcl >= (uint64_t)p.limit ? 0u : (uint32_t)min((uint64_t)cnt_total, (uint64_t)p.limit - rexcl);
+    if (cnt_lim != cnt_total) {
+        // the LIMIT cuts this tile: only the first cnt_lim survivors count (at most one such tile per query does real work)
+        my_bytes = 0;
         uint32_t r = r0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -198,9 +228,8 @@ static __global__ void __launch_bounds__(kBlock, 5) string_gather_kernel(const _
                 ++r;
             }
         }
+        b0 = block_exclusive_scan(my_bytes, s_warp, bytes_total);
     }
-    uint32_t bytes_total;
-    const uint32_t b0 = block_exclusive_scan(my_bytes, s_warp, bytes_total);
 
     // global byte prefix: second decoupled look-back
     if (warp == 0) {

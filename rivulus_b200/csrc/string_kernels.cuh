@@ -155,7 +155,7 @@ __device__ __forceinline__ void copy_descriptor_per_lane(const uint8_t* __restri
     if (nw > 1u && (end & 3u) != 0u) put_partial(nw - 1u, __funnelshift_r(L(nw - 1u), L(nw), sh));
 }
 
-constexpr uint32_t kStrChunk = 24 * 1024;   // staging bytes per pass (a 2048-row tile of ~24-byte strings at 50 % fits in one)
+constexpr uint32_t kStrChunk = 16 * 1024;   // staging bytes per pass (a 2048-row tile of ~24-byte strings at 50 % fits in one)
 
 // the same for two values at once (one pair of barriers instead of two)
 __device__ __forceinline__ void block_exclusive_scan2(uint32_t a, uint32_t b, uint32_t* s_wa, uint32_t* s_wb, uint32_t& ea, uint32_t& eb,
@@ -180,7 +180,7 @@ __device__ __forceinline__ void block_exclusive_scan2(uint32_t a, uint32_t b, ui
     ea = oa + ia - a; eb = ob + ib - b; ta = sa; tb = sb;
 }
 
-static __global__ void __launch_bounds__(kBlock, 5) string_gather_kernel(const __grid_constant__ StrGatherParams p) {
+static __global__ void __launch_bounds__(kBlock, 6) string_gather_kernel(const __grid_constant__ StrGatherParams p) {
     __shared__ int32_t s_src[kTileRows];        // survivor r: first source byte
     __shared__ uint32_t s_dst[kTileRows + 1];   // survivor r: first destination byte inside the tile's dense range; [count] = total
     __shared__ __align__(16) uint8_t s_stage[kStrChunk + 16];
@@ -209,8 +209,14 @@ static __global__ void __launch_bounds__(kBlock, 5) string_gather_kernel(const _
         for (int i = 0; i < 9; ++i) off[i] = (row0 + i <= p.n_rows) ? __ldg(p.offsets + row0 + i) : 0;
         if (p.valid.words != nullptr) vbits = load_bits32(p.valid, (uint64_t)row0) & 0xFFu;
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if ((selbyte >> i) & (vbits >> i) & 1u) my_bytes += (uint32_t)(off[i + 1] - off[i]);
+        for (int i = 0; i < 8; ++i) {
+            if ((selbyte >> i) & (vbits >> i) & 1u) {
+                my_bytes += (uint32_t)(off[i + 1] - off[i]);
+                // pull the survivor's bytes towards L2 now: the copy phase is two block scans and a look-back away
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.data + off[i]));
+                if (((off[i] & 127) + (off[i + 1] - off[i])) > 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.data + off[i + 1] - 1));
+            }
+        }
     }
     // ranks and byte offsets in one block scan
     uint32_t r0, b0, cnt_total, bytes_total;

@@ -237,6 +237,10 @@ int32_t rvl_stream_close(rvl_stream* stream);
 int32_t rvl_shard_range(int64_t n_rows, int32_t rank, int32_t world, int64_t* begin, int64_t* end);
 /* per-shard contributions to an ordered result under a global LIMIT: take[g] = clamp(limit - sum_{j<g} counts[j], 0, counts[g]) */
 int32_t rvl_shard_limit_split(const int64_t* counts, int32_t world, int64_t limit, int64_t* take);
+/* Ordered physical concatenation of per-GPU results (outs[] of rvl_filter_project_sharded, in shard order) on dst's device: the
+ * concat kernels read the peers' buffers in place over NVLink (peer mappings are set up on first use); the order-preserving
+ * concatenation of record_batch.rs:245-342 across devices.  Blocks until the result is complete. */
+int32_t rvl_gather_to(rvl_ctx* dst, const rvl_batch* const* parts, int32_t n, rvl_batch** out);
 /* one fused call per context (each on its own GPU/stream), all in flight together; outs[g] are in row order */
 int32_t rvl_filter_project_sharded(rvl_ctx* const* ctxs, int32_t n, const rvl_batch* const* shards,
                                    const rvl_predicate* pred, const int32_t* proj, int32_t nproj, int64_t limit,

@@ -73,7 +73,7 @@ ABI_SYMBOLS = [
     "rvl_filter_project", "rvl_predicate_mask", "rvl_filter_project_launch", "rvl_filter_project_finish",
     "rvl_stream_open", "rvl_stream_push", "rvl_stream_next", "rvl_stream_limit_reached", "rvl_stream_collect",
     "rvl_stream_stats", "rvl_stream_close",
-    "rvl_shard_range", "rvl_shard_limit_split", "rvl_filter_project_sharded",
+    "rvl_shard_range", "rvl_shard_limit_split", "rvl_filter_project_sharded", "rvl_gather_to",
     "rvl_gen_batch", "rvl_batch_checksum",
 ]
 
@@ -533,3 +533,11 @@ def filter_project_sharded(ctxs: Sequence[Context], shards: Sequence[Batch], pre
     check(lib().rvl_filter_project_sharded(ca, n, sa, C.byref(pred) if pred is not None else None, p, len(proj), C.c_int64(limit),
                                            outs, counts))
     return [Batch(ctxs[g], C.c_void_p(outs[g])) for g in range(n)], list(counts)
+
+
+def gather_to(dst: Context, parts: Sequence[Batch]) -> Batch:
+    """rvl_gather_to: ordered physical concatenation of per-GPU results on dst's device (peer reads over NVLink)."""
+    arr = (C.c_void_p * max(len(parts), 1))(*[b._h.value for b in parts])
+    out = C.c_void_p()
+    check(lib().rvl_gather_to(dst._h, arr, len(parts), C.byref(out)))
+    return Batch(dst, out)

@@ -721,6 +721,49 @@ int32_t rvl_batch_concat(rvl_ctx* ctx, const rvl_batch* const* batches, int32_t 
 }
 
 // ------------------------------------------------------------------------------------------ synthetic tables
+// Ordered physical concatenation of per-GPU results on one device (SURVEY.md 8(e) form (2)): the concat kernels of the destination
+// context read the other GPUs' buffers in place through NVLink peer mappings — no staging copy, bit offsets handled by the same
+// bit-granular kernels as a local concat, string offsets rebased by each part's byte prefix.
+int32_t rvl_gather_to(rvl_ctx* dst, const rvl_batch* const* parts, int32_t n, rvl_batch** out) {
+    if (!dst || !out) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    if (n <= 0 || !parts) return fail(RVL_INVALID_ARGUMENT, "Cannot concatenate empty batch list");
+    const CoreRef& core = dst->core;
+    for (int i = 0; i < n; ++i) {
+        if (!parts[i]) return fail(RVL_INVALID_ARGUMENT, "null batch");
+        const CoreRef& src = parts[i]->core;
+        if (src->device != core->device) {
+            int can = 0;
+            RVL_CUDA_TRY(cudaDeviceCanAccessPeer(&can, core->device, src->device));
+            if (!can) return fail(RVL_CUDA, "device " + std::to_string(core->device) + " cannot map the memory of device " + std::to_string(src->device));
+            RVL_CUDA_TRY(cudaSetDevice(core->device));
+            cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(RVL_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+            cudaGetLastError();
+            // stream-ordered allocations come from the source device's default pool: grant the destination device access to it
+            cudaMemPool_t pool = nullptr;
+            RVL_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, src->device));
+            cudaMemAccessDesc desc{};
+            desc.location.type = cudaMemLocationTypeDevice; desc.location.id = core->device; desc.flags = cudaMemAccessFlagsProtReadWrite;
+            RVL_CUDA_TRY(cudaMemPoolSetAccess(pool, &desc, 1));
+        }
+        if (src.get() != core.get()) {
+            // the part's producing kernels run on its own context's stream: order the gather behind them
+            RVL_CUDA_TRY(cudaSetDevice(src->device));
+            cudaEvent_t ev;
+            RVL_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            RVL_CUDA_TRY(cudaEventRecord(ev, src->stream));
+            RVL_CUDA_TRY(cudaSetDevice(core->device));
+            RVL_CUDA_TRY(cudaStreamWaitEvent(core->stream, ev, 0));
+            RVL_CUDA_TRY(cudaEventDestroy(ev));
+        }
+    }
+    RVL_TRY(rvl_batch_concat(dst, parts, n, out));
+    // the parts may be released by the caller as soon as this returns
+    RVL_CUDA_TRY(cudaSetDevice(core->device));
+    RVL_CUDA_TRY(cudaStreamSynchronize(core->stream));
+    return RVL_OK;
+}
+
 int32_t rvl_gen_batch(rvl_ctx* ctx, const int32_t* kinds, const uint32_t* col_ids, const uint32_t* null_pct, int32_t ncols,
                       uint64_t row0, int64_t n, rvl_batch** out) {
     if (!ctx || !out || n < 0) return fail(RVL_INVALID_ARGUMENT, "bad argument");

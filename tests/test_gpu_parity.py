@@ -371,7 +371,39 @@ def test_sharded_two_contexts_one_gpu(ctx):
         want = ob.filter_project_cmp(0, ">", 499, [0, 1, 2], limit)
         assert sum(counts) == want.num_rows()
         assert_batches_equal(got, want, f"sharded limit={limit}")
+        assert_batches_equal(capi.gather_to(ctx2, outs), want, f"sharded + gather_to limit={limit}")
     ctx2.close()
+
+
+def test_sharded_across_gpus_with_peer_gather():
+    """configs[4] for real: every visible GPU owns a contiguous row range ({k: Int64, v: Float64, f: Boolean, s: String} with nulls),
+    one process drives one context per GPU, and the ordered result is gathered onto GPU 0 by concat kernels that read the peers'
+    buffers over NVLink.  Needs >= 2 GPUs (gpurun --gpus 2); the same code path runs on one GPU in the test above."""
+    g = capi.device_count()
+    if g < 2:
+        pytest.skip("needs at least 2 GPUs")
+    g = min(g, 8)
+    rng = np.random.default_rng(77)
+    n = 300_007
+    cols = [random_col(rng, "i64", n, 0.05, lo=0, hi=1000), random_col(rng, "f64", n, 0.05), random_col(rng, "bool", n, 0.05),
+            random_col(rng, "str", n, 0.1, maxlen=20)]
+    ob = oracle_batch(cols)
+    ctxs = [capi.Context(d) for d in range(g)]
+    try:
+        for limit in (-1, 40_000):
+            shards = []
+            for r in range(g):
+                b, e = capi.shard_range(n, r, g)
+                part = [Col(c.dtype, e - b, c.values[b:e] if c.values is not None else None, c.valid[b:e] if c.valid is not None else None,
+                            c.strings[b:e] if c.strings is not None else None) for c in cols]
+                shards.append(upload(ctxs[r], part))
+            outs, counts = capi.filter_project_sharded(ctxs, shards, capi.predicate(0, ">", 499), [3, 0, 1, 2], limit)
+            want = ob.filter_project_cmp(0, ">", 499, [3, 0, 1, 2], limit)
+            assert sum(counts) == want.num_rows()
+            assert_batches_equal(capi.gather_to(ctxs[0], outs), want, f"{g}-GPU sharded + peer gather limit={limit}")
+    finally:
+        for c in ctxs:
+            c.close()
 
 
 # ------------------------------------------------------------------ full-size properties (count + order-sensitive checksums)

@@ -158,35 +158,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }
 
-// 256-descriptor-wide look-back run by one warp (8 predecessors per lane per round)
-__device__ __forceinline__ uint64_t lookback_exclusive_wide(const uint64_t* status, int64_t tile, int lane) {
-    uint64_t exclusive = 0;
-    int64_t base = tile - 1;
-    while (true) {
-        uint64_t s[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int64_t idx = base - (j * 32 + lane);
-            s[j] = idx >= 0 ? ld_relaxed_gpu(status + idx) : kStatusPrefix;  // virtual tile -1: prefix 0
-        }
-        bool found = false;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (!found) {
-                const int64_t idx = base - (j * 32 + lane);
-                while ((s[j] & kStatusMask) == 0) s[j] = ld_relaxed_gpu(status + idx);
-                const uint32_t prefix_lanes = __ballot_sync(0xFFFFFFFFu, (s[j] & kStatusMask) == kStatusPrefix);
-                const int first = __ffs(prefix_lanes) - 1;
-                const uint64_t take = (first < 0 || lane <= first) ? (s[j] & kValueMask) : 0ull;
-                exclusive += warp_sum_u64(take);
-                found = first >= 0;
-            }
-        }
-        if (found) break;
-        base -= 256;
-    }
-    return exclusive;
-}
 
 template <int PRED>
 __global__ void __launch_bounds__(kBlock, 3) fused_filter_project_kernel(const __grid_constant__ FusedParams p) {

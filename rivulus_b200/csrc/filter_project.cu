@@ -437,17 +437,21 @@ int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pre
         for (const StrJob& job : strjobs) {
             const DevColumn& s = *job.src;
             DevColumn& d = pend->outs[(size_t)job.out_index];
-            BufRef sstatus;
-            RVL_TRY(dev_alloc_zeroed(core, (size_t)tiles * 8, &sstatus));
-            pend->temps.push_back(sstatus);
+            BufRef tbytes;   // per-tile survivor bytes -> exclusive prefixes; last word = ticket counter of the sizes kernel
+            RVL_TRY(dev_alloc(core, (size_t)(tiles + 1) * 8, &tbytes));
+            RVL_CUDA_TRY(cudaMemsetAsync((uint64_t*)tbytes->ptr + tiles, 0, 8, core->stream));
+            pend->temps.push_back(tbytes);
             StrGatherParams sp{};
             sp.n_rows = n; sp.limit = limit; sp.sel = (const uint32_t*)sel->ptr; sp.tile_prefix = (const uint64_t*)tile_prefix->ptr; sp.row_base = 0;
             if (two_pass) { sp.chunk_base = (const uint64_t*)chunk_base->ptr; sp.tiles_per_chunk = tiles_per_chunk; }
             sp.offsets = (const int32_t*)s.offsets->ptr + s.offset; sp.data = (const uint8_t*)s.data->ptr;
             sp.valid = bitsrc_of(s.validity, s.offset, n);
             sp.out_offsets = (int32_t*)d.offsets->ptr; sp.out_data = (uint8_t*)d.data->ptr;
-            sp.tile_status = (uint64_t*)sstatus->ptr; sp.byte_base_in = nullptr; sp.row_base_in = base_in;
+            sp.tile_bytes = (uint64_t*)tbytes->ptr; sp.byte_base_in = nullptr; sp.row_base_in = base_in;
             sp.bytes_total_out = dctr + pend->bytes_counter[(size_t)job.out_index];
+            string_sizes_kernel<<<(unsigned)tiles, kBlock, 0, core->stream>>>(sp);
+            core->launches++;
+            RVL_CUDA_TRY(cudaGetLastError());
             string_gather_kernel<<<(unsigned)tiles, kBlock, 0, core->stream>>>(sp);
             core->launches++;
             RVL_CUDA_TRY(cudaGetLastError());

@@ -637,7 +637,8 @@ int32_t rvl_batch_concat(rvl_ctx* ctx, const rvl_batch* const* batches, int32_t 
         if (any_validity && d.dtype != RVL_NULL) RVL_TRY(dev_alloc_zeroed(core, (size_t)(total + 7) / 8, &d.validity));
         if (d.dtype == RVL_INT64 || d.dtype == RVL_FLOAT64) RVL_TRY(dev_alloc(core, (size_t)total * 8, &d.values));
         if (d.dtype == RVL_BOOLEAN) RVL_TRY(dev_alloc_zeroed(core, (size_t)(total + 7) / 8, &d.values));
-        BufRef status;
+        BufRef status, chain;
+        int chain_k = 0;
         if (d.dtype == RVL_STRING) {
             int64_t cap = 0;
             for (int b = 0; b < n; ++b) cap += batches[b]->cols[c].data_len;
@@ -660,8 +661,10 @@ int32_t rvl_batch_concat(rvl_ctx* ctx, const rvl_batch* const* batches, int32_t 
             RVL_TRY(dev_alloc(core, (size_t)cap, &d.data));
             int64_t max_tiles = 1;
             for (int b = 0; b < n; ++b) max_tiles = std::max<int64_t>(max_tiles, (batches[b]->num_rows + kTileRows - 1) / kTileRows);
-            RVL_TRY(dev_alloc(core, (size_t)max_tiles * 8, &status));
+            RVL_TRY(dev_alloc(core, (size_t)(max_tiles + 1) * 8, &status));   // per-tile byte prefixes + the sizes kernel's ticket word
             keep_alive.push_back(status);
+            RVL_TRY(dev_alloc_zeroed(core, (size_t)(n + 1) * 8, &chain));      // bytes emitted before each part
+            keep_alive.push_back(chain);
         }
         int64_t row_base = 0;
         for (int b = 0; b < n; ++b) {
@@ -679,12 +682,16 @@ int32_t rvl_batch_concat(rvl_ctx* ctx, const rvl_batch* const* batches, int32_t 
                 core->launches++;
             } else if (d.dtype == RVL_STRING) {
                 const int64_t tiles = (m + kTileRows - 1) / kTileRows;
-                RVL_CUDA_TRY(cudaMemsetAsync(status->ptr, 0, (size_t)tiles * 8, core->stream));
+                RVL_CUDA_TRY(cudaMemsetAsync((uint64_t*)status->ptr + tiles, 0, 8, core->stream));
                 StrGatherParams sp{};
                 sp.n_rows = m; sp.limit = -1; sp.sel = nullptr; sp.tile_prefix = nullptr; sp.row_base = row_base;
                 sp.offsets = (const int32_t*)s.offsets->ptr + s.offset; sp.data = (const uint8_t*)s.data->ptr; sp.valid = sv;
                 sp.out_offsets = (int32_t*)d.offsets->ptr; sp.out_data = (uint8_t*)d.data->ptr;
-                sp.tile_status = (uint64_t*)status->ptr; sp.byte_base_in = dctr + 2 * c + 1; sp.bytes_total_out = dctr + 2 * c + 1;
+                unsigned long long* ch = (unsigned long long*)chain->ptr;
+                sp.tile_bytes = (uint64_t*)status->ptr; sp.byte_base_in = ch + chain_k; sp.bytes_total_out = ch + chain_k + 1;
+                ++chain_k;
+                string_sizes_kernel<<<(unsigned)tiles, kBlock, 0, core->stream>>>(sp);
+                core->launches++;
                 string_gather_kernel<<<(unsigned)tiles, kBlock, 0, core->stream>>>(sp);
                 core->launches++;
             }
@@ -696,6 +703,8 @@ int32_t rvl_batch_concat(rvl_ctx* ctx, const rvl_batch* const* batches, int32_t 
             RVL_CUDA_TRY(cudaGetLastError());
             row_base += m;
         }
+        if (d.dtype == RVL_STRING && chain)   // total string bytes = the last link of the per-part chain
+            RVL_CUDA_TRY(cudaMemcpyAsync(dctr + 2 * c + 1, (unsigned long long*)chain->ptr + chain_k, 8, cudaMemcpyDeviceToDevice, core->stream));
         if (d.validity && total > 0) {
             count_ones_kernel<<<grid_for((total + 31) / 32, 256, core->sm_count), 256, 0, core->stream>>>(
                 bitsrc_of(d.validity, 0, total), total, nullptr, nullptr, -1, dctr + 2 * c);

@@ -6,10 +6,14 @@
 //   execution/array/string.rs:19-58    StringArray::new: second copy + offsets rebuild + UTF-8 re-validation
 //   datatypes/series.rs:111            str ordering for `col <op> "literal"` (byte-wise lexicographic)
 //
-// The fused kernel leaves a row-order selection bitmap and each tile's exclusive output prefix; this
-// kernel walks the same 2048-row tiles: thread t owns rows [8t, 8t+8) (one selection byte), a block
-// scan ranks the survivors, a second scan + decoupled look-back over survivor byte lengths yields the
-// new int32 offsets in one pass, then the tile's strings are copied into its dense destination range.
+// The predicate pass leaves a row-order selection bitmap and each tile's exclusive output row prefix.  Two kernels follow,
+// the north star's "offset prefix-sum, then a byte copy staged through shared memory":
+//   string_sizes_kernel   one warp per 2048-row tile, lane <-> row: survivor byte total of every tile; the last CTA to finish
+//                         (ticket) turns the totals into exclusive prefixes.  No tile waits on another one.
+//   string_gather_kernel  one CTA per tile: survivors ranked from the selection words, lengths -> byte offsets by one block scan,
+//                         new int32 offsets written in rank order, bytes copied through a shared staging buffer.
+// (A single-pass version with a decoupled look-back over the byte totals was measured first: with ~900 tiles in flight and
+// ~10 us per tile, every tile waited on the slowest of its predecessors — the look-back cost 0.2 ms of a 0.65 ms launch.)
 // UTF-8 validity is preserved by construction (whole strings are copied), so no re-validation pass.
 #pragma once
 #include "device_utils.cuh"
@@ -30,7 +34,8 @@ struct StrGatherParams {
     BitSrc valid;
     int32_t* out_offsets;               // out_offsets[0] preset; this kernel writes [rank + 1]
     uint8_t* out_data;
-    uint64_t* tile_status;              // descriptors for the byte prefix (zeroed before launch)
+    uint64_t* tile_bytes;               // [n_tiles + 1]: string_sizes_kernel leaves each tile's exclusive byte prefix here; the last
+                                        //   word is the ticket counter of that kernel (zeroed before launch)
     const unsigned long long* byte_base_in;  // bytes already emitted before this launch (concat), or nullptr
     unsigned long long* bytes_total_out;     // byte base + bytes emitted by this launch
 };
@@ -155,6 +160,102 @@ __device__ __forceinline__ void copy_descriptor_per_lane(const uint8_t* __restri
     if (nw > 1u && (end & 3u) != 0u) put_partial(nw - 1u, __funnelshift_r(L(nw - 1u), L(nw), sh));
 }
 
+// Survivor byte total of every tile, then (last CTA, by ticket) their exclusive prefix scan in place.
+//   tile_bytes[t]        <- sum over the tile's survivors (rank below the LIMIT, not null) of their byte lengths, then its prefix
+//   *bytes_total_out     <- byte base + all survivor bytes
+// One CTA per tile, thread t <-> rows [8t, 8t + 8): one selection byte, nine offsets, one validity byte per thread, so a tile is
+// two dependent round trips deep and 8 CTAs per SM keep ~70 KB of loads in flight.
+static __global__ void __launch_bounds__(kBlock, 6) string_sizes_kernel(const __grid_constant__ StrGatherParams p) {
+    __shared__ uint32_t s_warp[kWarps];
+    __shared__ uint64_t s_part[kWarps];
+    __shared__ uint32_t s_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t n_tiles = gridDim.x;
+    const int64_t tile = blockIdx.x;
+    const int64_t row0 = tile * kTileRows + (int64_t)tid * 8;
+    uint32_t selbyte = 0;
+    if (row0 < p.n_rows) {
+        if (p.sel != nullptr) selbyte = reinterpret_cast<const uint8_t*>(p.sel)[tile * (kTileRows / 8) + tid];
+        else selbyte = (p.n_rows - row0 >= 8) ? 0xFFu : ((1u << (p.n_rows - row0)) - 1u);
+    }
+    uint64_t rexcl = 0;
+    if (p.limit >= 0) {
+        rexcl = p.tile_prefix != nullptr ? p.tile_prefix[tile] : (uint64_t)(p.row_base + tile * kTileRows);
+        if (p.chunk_base != nullptr) rexcl = p.chunk_base[tile / p.tiles_per_chunk] + (rexcl >> 12);
+    }
+    int32_t off[9];
+    uint32_t vbits = 0xFFu, my_bytes = 0;
+    if (selbyte != 0u) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) off[i] = (row0 + i <= p.n_rows) ? __ldg(p.offsets + row0 + i) : 0;
+        if (p.valid.words != nullptr) vbits = load_bits32(p.valid, (uint64_t)row0) & 0xFFu;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if ((selbyte >> i) & (vbits >> i) & 1u) my_bytes += (uint32_t)(off[i + 1] - off[i]);
+    }
+    if (p.limit >= 0) {
+        // survivors whose global rank reaches the LIMIT do not count (uniform branch: at most one tile per query is cut)
+        uint32_t cnt_total;
+        const uint32_t r0 = block_exclusive_scan(__popc(selbyte), s_warp, cnt_total);
+        const uint32_t lim = rexcl >= (uint64_t)p.limit ? 0u : (uint32_t)min((uint64_t)cnt_total, (uint64_t)p.limit - rexcl);
+        if (lim != cnt_total) {
+            my_bytes = 0;
+            uint32_t r = r0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if ((selbyte >> i) & 1u) {
+                    if (r < lim && ((vbits >> i) & 1u)) my_bytes += (uint32_t)(off[i + 1] - off[i]);
+                    ++r;
+                }
+            }
+        }
+    }
+    const uint32_t wsum = __reduce_add_sync(0xFFFFFFFFu, my_bytes);
+    if (lane == 0) s_part[warp] = wsum;
+    __syncthreads();
+    if (tid == 0) {
+        uint64_t tb = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) tb += s_part[w];
+        st_relaxed_gpu(p.tile_bytes + tile, tb);
+        __threadfence();
+        s_last = atomicAdd(reinterpret_cast<unsigned int*>(p.tile_bytes + n_tiles), 1u) == gridDim.x - 1 ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last == 0u) return;
+    // ---- last CTA to finish: exclusive prefix over the tiles, in place, 2048 tiles a round (8 independent loads per thread)
+    __threadfence();
+    uint64_t carry = 0;
+#pragma unroll 1
+    for (int64_t base = 0; base < n_tiles; base += kBlock * 8) {
+        const int64_t lo = base + (int64_t)tid * 8;
+        uint64_t v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = lo + i < n_tiles ? ld_relaxed_gpu(p.tile_bytes + lo + i) : 0ull;
+        uint64_t mine = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const uint64_t t = v[i]; v[i] = mine; mine += t; }
+        uint64_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t nb = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += nb;
+        }
+        __syncthreads();   // s_part of the previous round has been read
+        if (lane == 31) s_part[warp] = incl;
+        __syncthreads();
+        uint64_t woff = 0, all = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) { const uint64_t c = s_part[w]; woff += (w < warp) ? c : 0ull; all += c; }
+        const uint64_t excl = carry + woff + incl - mine;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (lo + i < n_tiles) p.tile_bytes[lo + i] = excl + v[i];
+        carry += all;
+    }
+    if (tid == 0) *p.bytes_total_out = (unsigned long long)((p.byte_base_in != nullptr ? (uint64_t)*p.byte_base_in : 0ull) + carry);
+}
+
 constexpr uint32_t kStrChunk = 16 * 1024;   // staging bytes per pass (a 2048-row tile of ~24-byte strings at 50 % fits in one)
 
 // the same for two values at once (one pair of barriers instead of two)
@@ -181,96 +282,96 @@ __device__ __forceinline__ void block_exclusive_scan2(uint32_t a, uint32_t b, ui
 }
 
 static __global__ void __launch_bounds__(kBlock, 6) string_gather_kernel(const __grid_constant__ StrGatherParams p) {
-    __shared__ int32_t s_src[kTileRows];        // survivor r: first source byte
-    __shared__ uint32_t s_dst[kTileRows + 1];   // survivor r: first destination byte inside the tile's dense range; [count] = total
+    __shared__ __align__(16) int32_t s_src[kTileRows];        // survivor r: first source byte
+    __shared__ __align__(16) uint32_t s_dst[kTileRows + 8];   // survivor r: length, then first destination byte inside the tile's dense range; [count..] = total
     __shared__ __align__(16) uint8_t s_stage[kStrChunk + 16];
-    __shared__ uint32_t s_warp[kWarps], s_warp2[kWarps];
-    __shared__ uint64_t s_bexcl;
+    __shared__ uint32_t s_warp[kWarps];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t tile = blockIdx.x;
-    const int64_t row0 = tile * kTileRows + (int64_t)tid * 8;
+    const int64_t tile_row0 = tile * kTileRows;
+    const uint32_t lt = lanemask_lt();
 
-    uint32_t selbyte = 0;
-    if (row0 < p.n_rows) {
-        if (p.sel != nullptr) selbyte = reinterpret_cast<const uint8_t*>(p.sel)[tile * (kTileRows / 8) + tid];
-        else selbyte = (p.n_rows - row0 >= 8) ? 0xFFu : ((1u << (p.n_rows - row0)) - 1u);
-    }
+    // ---- A. the tile's 64 selection words, every warp redundantly (lane holds words lane and lane + 32): survivor counts in
+    //         front of any warp are two warp reductions away, no barrier
+    auto tail_mask = [&](int64_t r) -> uint32_t {   // rows [r, r + 32) that exist
+        const int64_t rem = p.n_rows - r;
+        return rem >= 32 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+    };
+    uint32_t w0, w1;
+    if (p.sel != nullptr) { const uint32_t* sw = p.sel + tile * kTileWords; w0 = __ldg(sw + lane); w1 = __ldg(sw + 32 + lane); }
+    else { w0 = tail_mask(tile_row0 + 32 * lane); w1 = tail_mask(tile_row0 + 32 * (lane + 32)); }
     uint64_t rexcl = p.tile_prefix != nullptr ? p.tile_prefix[tile] : (uint64_t)(p.row_base + tile * kTileRows);
     if (p.chunk_base != nullptr) rexcl = p.chunk_base[tile / p.tiles_per_chunk] + (rexcl >> 12);
     const uint64_t rbase = p.row_base_in != nullptr ? (uint64_t)*p.row_base_in : 0ull;
-
-    // survivor lengths of this thread's rows (nulls are zero-length: string.rs:33-36)
-    int32_t off[9];
-    uint32_t my_bytes = 0;
-    uint32_t vbits = 0xFFu;
-    if (selbyte != 0u) {
-#pragma unroll
-        for (int i = 0; i < 9; ++i) off[i] = (row0 + i <= p.n_rows) ? __ldg(p.offsets + row0 + i) : 0;
-        if (p.valid.words != nullptr) vbits = load_bits32(p.valid, (uint64_t)row0) & 0xFFu;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if ((selbyte >> i) & (vbits >> i) & 1u) {
-                my_bytes += (uint32_t)(off[i + 1] - off[i]);
-                // pull the survivor's bytes towards L2 now: the copy phase is two block scans and a look-back away
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.data + off[i]));
-                if (((off[i] & 127) + (off[i + 1] - off[i])) > 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.data + off[i + 1] - 1));
-            }
-        }
-    }
-    // ranks and byte offsets in one block scan
-    uint32_t r0, b0, cnt_total, bytes_total;
-    block_exclusive_scan2(__popc(selbyte), my_bytes, s_warp, s_warp2, r0, b0, cnt_total, bytes_total);
+    const uint32_t c0 = __popc(w0), c1 = __popc(w1);
+    const uint32_t cnt_total = __reduce_add_sync(0xFFFFFFFFu, c0 + c1);
+    const int first_word = warp * 8;               // this warp's rows are selection words [first_word, first_word + 8)
+    uint32_t run = first_word < 32 ? __reduce_add_sync(0xFFFFFFFFu, lane < first_word ? c0 : 0u)
+                                   : __reduce_add_sync(0xFFFFFFFFu, c0) + __reduce_add_sync(0xFFFFFFFFu, lane < first_word - 32 ? c1 : 0u);
+    const uint32_t wsel = first_word < 32 ? w0 : w1;
     uint32_t cnt_lim = cnt_total;
     if (p.limit >= 0) cnt_lim = rexcl >= (uint64_t)p.limit ? 0u : (uint32_t)min((uint64_t)cnt_total, (uint64_t)p.limit - rexcl);
-    if (cnt_lim != cnt_total) {
-        // the LIMIT cuts this tile: only the first cnt_lim survivors count (at most one such tile per query does real work)
-        my_bytes = 0;
-        uint32_t r = r0;
+
+    // ---- B. lane <-> row: offsets read coalesced, (source offset, length) of every survivor stored at its rank
+    //         (nulls are zero-length: string.rs:33-36; survivors beyond the LIMIT are simply not stored)
+    const int64_t wrow0 = tile_row0 + (int64_t)warp * 256;
+    uint32_t vwv = 0xFFFFFFFFu;
+    if (p.valid.words != nullptr && lane < 8) vwv = load_bits32(p.valid, (uint64_t)(wrow0 + 32 * lane));
+    int32_t o0[8], oend[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if ((selbyte >> i) & 1u) {
-                if (r < cnt_lim && ((vbits >> i) & 1u)) my_bytes += (uint32_t)(off[i + 1] - off[i]);
-                ++r;
+    for (int g = 0; g < 8; ++g) {
+        const uint32_t selw = __shfl_sync(0xFFFFFFFFu, wsel, (first_word + g) & 31);
+        o0[g] = 0; oend[g] = 0;
+        if (selw != 0u) {
+            const int64_t row = wrow0 + 32 * g + lane;
+            o0[g] = row <= p.n_rows ? __ldg(p.offsets + row) : 0;
+            oend[g] = __ldg(p.offsets + min(wrow0 + 32 * g + 32, p.n_rows));   // one address for the whole warp
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        const uint32_t selw = __shfl_sync(0xFFFFFFFFu, wsel, (first_word + g) & 31);
+        if (selw == 0u) continue;
+        const uint32_t vw = __shfl_sync(0xFFFFFFFFu, vwv, g);
+        int32_t o1 = __shfl_down_sync(0xFFFFFFFFu, o0[g], 1);
+        if (lane == 31) o1 = oend[g];
+        const uint32_t r = run + __popc(selw & lt);
+        run += __popc(selw);
+        if (((selw >> lane) & 1u) != 0u && r < cnt_lim) {
+            const uint32_t len = ((vw >> lane) & 1u) ? (uint32_t)(o1 - o0[g]) : 0u;
+            s_src[r] = o0[g]; s_dst[r] = len;
+            if (len != 0u) {
+                // pull the survivor's bytes towards L2 now: the copy phase is a block scan and a look-back away
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.data + o0[g]));
+                if (((uint32_t)o0[g] & 127u) + len > 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.data + o1 - 1));
             }
         }
-        b0 = block_exclusive_scan(my_bytes, s_warp, bytes_total);
+    }
+    __syncthreads();
+
+    // ---- C. lengths -> exclusive byte offsets, in place: 8 ranks per thread, one block scan
+    uint32_t b0, bytes_total;
+    {
+        const uint32_t base = (uint32_t)tid * 8u;
+        uint32_t v[8];
+        const uint4 x = *reinterpret_cast<const uint4*>(&s_dst[base]), y = *reinterpret_cast<const uint4*>(&s_dst[base + 4]);
+        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+        uint32_t sum = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const uint32_t t = base + i < cnt_lim ? v[i] : 0u; v[i] = sum; sum += t; }
+        b0 = block_exclusive_scan(sum, s_warp, bytes_total);
+        uint4 ox, oy;
+        ox.x = b0 + v[0]; ox.y = b0 + v[1]; ox.z = b0 + v[2]; ox.w = b0 + v[3];
+        oy.x = b0 + v[4]; oy.y = b0 + v[5]; oy.z = b0 + v[6]; oy.w = b0 + v[7];
+        *reinterpret_cast<uint4*>(&s_dst[base]) = ox; *reinterpret_cast<uint4*>(&s_dst[base + 4]) = oy;
+        if (tid == kBlock - 1) s_dst[kTileRows] = bytes_total;   // entries at and beyond cnt_lim hold the total
     }
 
-    // global byte prefix: second decoupled look-back
-    if (warp == 0) {
-        uint64_t bexcl;
-        if (tile == 0) {
-            bexcl = p.byte_base_in != nullptr ? (uint64_t)*p.byte_base_in : 0ull;
-            if (lane == 0) st_relaxed_gpu(p.tile_status, kStatusPrefix | (bexcl + bytes_total));
-        } else {
-            if (lane == 0) st_relaxed_gpu(p.tile_status + tile, kStatusAggregate | (uint64_t)bytes_total);
-            bexcl = lookback_exclusive(p.tile_status, tile, lane);
-            if (lane == 0) st_relaxed_gpu(p.tile_status + tile, kStatusPrefix | (bexcl + bytes_total));
-        }
-        if (lane == 0) {
-            s_bexcl = bexcl;
-            if (tile == (int64_t)gridDim.x - 1) *p.bytes_total_out = (unsigned long long)(bexcl + bytes_total);
-        }
-    }
-    // copy descriptors (independent of the global prefix, so they are built while warp 0 looks back)
-    if (selbyte != 0u) {
-        uint32_t r = r0, b = b0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if ((selbyte >> i) & 1u) {
-                if (r < cnt_lim) {
-                    s_src[r] = off[i]; s_dst[r] = b;
-                    b += ((vbits >> i) & 1u) ? (uint32_t)(off[i + 1] - off[i]) : 0u;
-                }
-                ++r;
-            }
-        }
-    }
-    if (tid == 0) s_dst[cnt_lim] = bytes_total;
+    // global byte prefix of the tile: computed by string_sizes_kernel, so tiles do not wait on each other
+    const uint64_t bexcl = (p.byte_base_in != nullptr ? (uint64_t)*p.byte_base_in : 0ull) + p.tile_bytes[tile];
     __syncthreads();
     if (cnt_lim == 0u) return;
-    const uint64_t bexcl = s_bexcl;
 
     // new offsets, in rank order: out_offsets[first survivor of the tile + r + 1] = end of survivor r (coalesced)
     {

@@ -320,9 +320,11 @@ def test_stream_zero_copy_transfer(plan, limit, op, lit):
     try:
         rng = np.random.default_rng(1234 + limit)
         batches, keep = [], []
-        for n in [40_000, 1, 65_536, 0, 12_345]:
-            batches.append([random_col(rng, "i64", n, 0.1, lo=0, hi=1000), random_col(rng, "f64", n, 0.1), random_col(rng, "bool", n, 0.2),
-                            random_col(rng, "i64", n, 0.0), random_col(rng, "str", n, 0.1, maxlen=12), random_col(rng, "f64", n, 0.5)])
+        for n, off in [(40_000, 0), (1, 5), (65_536, 0), (0, 0), (12_345, 77), (30_000, 64 * 3 + 13)]:
+            # off > 0: the pushed columns are (offset, length) windows of larger pinned buffers, bit offsets not multiples of 8
+            batches.append([random_col(rng, "i64", n, 0.1, offset=off, tail=9, lo=0, hi=1000), random_col(rng, "f64", n, 0.1, offset=off, tail=9),
+                            random_col(rng, "bool", n, 0.2, offset=off, tail=9), random_col(rng, "i64", n, 0.0, offset=off, tail=9),
+                            random_col(rng, "str", n, 0.1, offset=off, tail=9, maxlen=12), random_col(rng, "f64", n, 0.5, offset=off, tail=9)])
         dtypes = [capi.INT64, capi.FLOAT64, capi.BOOLEAN, capi.INT64, capi.STRING, capi.FLOAT64]
         proj = [1, 2, 3, 4, 0]        # column 5 is never looked at; column 0 is predicate + projected (staged once)
         outs = {}

@@ -166,6 +166,27 @@ def run_native(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the native arm has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # multi-rank runs: keep each rank (and the pinned host table it allocates for the e2e leg) on the NUMA node of its own GPU, so
+    # eight ranks do not pull their PCIe traffic through one socket
+    numa = "unbound"
+    if world > 1:
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+            h = None
+            for cand in (uuid, "GPU-" + uuid):
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(cand.encode())
+                    break
+                except Exception:
+                    h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            pynvml.nvmlDeviceSetCpuAffinity(h)
+            numa = f"bound to the GPU's CPU set ({len(os.sched_getaffinity(0))} cores)"
+        except Exception as e:   # best effort: affinity is an optimisation, never a requirement
+            numa = f"unbound ({type(e).__name__})"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -272,7 +293,7 @@ def run_native(args):
         "config": {"workload": "configs[1]: filter(k > T).select([a,b,c,d]) over {k,a:Int64,b:Float64,c:Int64,d:Float64}, "
                                "T in 998/899/499/99 (0.1/10/50/90 %), one rvl_filter_project call per query, 4 queries per step",
                    "plan": args.plan,
-                   "rows_per_gpu": rows, "global_rows": rows * world, "partitioning": f"row-range x{world}",
+                   "rows_per_gpu": rows, "global_rows": rows * world, "partitioning": f"row-range x{world}", "host_affinity": numa,
                    "l2": "inputs (40 B/row x rows) far exceed the 126 MB L2; no flush needed",
                    "timing": "CUDA events on the library stream around K steps incl. count readback; max over ranks"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

@@ -148,7 +148,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.time() - t0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -318,7 +318,7 @@ def run_native(args):
         line["e2e"] = run_e2e(args, ctx, table, preds, proj, rank, world, local_rank, barrier)
 
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -445,6 +445,27 @@ def run_e2e(args, ctx, table, preds, proj, rank, world, local_rank, barrier):
             "timing": "host wall clock around the synchronised region (H2D, kernels, D2H all inside)"}
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything libraries print to fd 1 (NCCL's version banner, ...) goes to stderr; emit() writes the ONE JSON line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -467,6 +488,7 @@ def main():
     ap.add_argument("--dense-warps", type=int, default=None)
     ap.add_argument("--scan-slots", type=int, default=None)
     args = ap.parse_args()
+    quiet_stdout()
     if args.cpu_rows is None:
         args.cpu_rows = 500_000 if args.impl == "reference" else 4_000_000
     if args.impl == "reference":

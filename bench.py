@@ -166,10 +166,10 @@ def run_native(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the native arm has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    # multi-rank runs: keep each rank (and the pinned host table it allocates for the e2e leg) on the NUMA node of its own GPU, so
-    # eight ranks do not pull their PCIe traffic through one socket
+    # optional (RVL_BENCH_AFFINITY=1): keep each rank (and the pinned host table it allocates for the e2e leg) on the NUMA node of
+    # its own GPU, so that on a multi-socket host eight ranks do not pull their PCIe traffic through one socket
     numa = "unbound"
-    if world > 1:
+    if world > 1 and os.environ.get("RVL_BENCH_AFFINITY", "0") == "1":   # opt-in: no benefit measured on this pool's single-NUMA-node hosts
         try:
             import pynvml
             pynvml.nvmlInit()

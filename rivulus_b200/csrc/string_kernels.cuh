@@ -314,37 +314,37 @@ static __global__ void __launch_bounds__(kBlock, 6) string_gather_kernel(const _
     if (p.limit >= 0) cnt_lim = rexcl >= (uint64_t)p.limit ? 0u : (uint32_t)min((uint64_t)cnt_total, (uint64_t)p.limit - rexcl);
 
     // ---- B. lane <-> row: offsets read coalesced, (source offset, length) of every survivor stored at its rank
-    //         (nulls are zero-length: string.rs:33-36; survivors beyond the LIMIT are simply not stored)
+    //         (nulls are zero-length: string.rs:33-36; survivors beyond the LIMIT are simply not stored).
+    //         A warp whose 256 rows hold no survivor skips its loads; otherwise it reads its 257 offsets in nine coalesced
+    //         loads (lane <-> row of each 32-row group; the end of a group is lane 0 of the next one).
     const int64_t wrow0 = tile_row0 + (int64_t)warp * 256;
-    uint32_t vwv = 0xFFFFFFFFu;
-    if (p.valid.words != nullptr && lane < 8) vwv = load_bits32(p.valid, (uint64_t)(wrow0 + 32 * lane));
-    int32_t o0[8], oend[8];
+    const uint32_t wany = __ballot_sync(0xFFFFFFFFu, lane >= (first_word & 31) && lane < (first_word & 31) + 8 && wsel != 0u);
+    if (wany != 0u) {
+        uint32_t vwv = 0xFFFFFFFFu;
+        if (p.valid.words != nullptr && lane < 8) vwv = load_bits32(p.valid, (uint64_t)(wrow0 + 32 * lane));
+        int32_t o[9];
+        const int32_t* const offw = p.offsets + wrow0 + lane;
+        if (wrow0 + 256 + 32 <= p.n_rows) {
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-        const uint32_t selw = __shfl_sync(0xFFFFFFFFu, wsel, (first_word + g) & 31);
-        o0[g] = 0; oend[g] = 0;
-        if (selw != 0u) {
-            const int64_t row = wrow0 + 32 * g + lane;
-            o0[g] = row <= p.n_rows ? __ldg(p.offsets + row) : 0;
-            oend[g] = __ldg(p.offsets + min(wrow0 + 32 * g + 32, p.n_rows));   // one address for the whole warp
+            for (int g = 0; g < 9; ++g) o[g] = __ldg(offw + 32 * g);
+        } else {
+#pragma unroll
+            for (int g = 0; g < 9; ++g) o[g] = wrow0 + 32 * g + lane <= p.n_rows ? __ldg(offw + 32 * g) : 0;
         }
-    }
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-        const uint32_t selw = __shfl_sync(0xFFFFFFFFu, wsel, (first_word + g) & 31);
-        if (selw == 0u) continue;
-        const uint32_t vw = __shfl_sync(0xFFFFFFFFu, vwv, g);
-        int32_t o1 = __shfl_down_sync(0xFFFFFFFFu, o0[g], 1);
-        if (lane == 31) o1 = oend[g];
-        const uint32_t r = run + __popc(selw & lt);
-        run += __popc(selw);
-        if (((selw >> lane) & 1u) != 0u && r < cnt_lim) {
-            const uint32_t len = ((vw >> lane) & 1u) ? (uint32_t)(o1 - o0[g]) : 0u;
-            s_src[r] = o0[g]; s_dst[r] = len;
-            if (len != 0u) {
-                // pull the survivor's bytes towards L2 now: the copy phase is a block scan and a look-back away
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.data + o0[g]));
-                if (((uint32_t)o0[g] & 127u) + len > 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.data + o1 - 1));
+        for (int g = 0; g < 8; ++g) {
+            const uint32_t selw = __shfl_sync(0xFFFFFFFFu, wsel, (first_word + g) & 31);
+            const uint32_t vw = __shfl_sync(0xFFFFFFFFu, vwv, g);
+            int32_t o1 = __shfl_down_sync(0xFFFFFFFFu, o[g], 1);
+            const int32_t onext = __shfl_sync(0xFFFFFFFFu, o[g + 1], 0);
+            if (lane == 31) o1 = onext;
+            const uint32_t r = run + __popc(selw & lt);
+            run += __popc(selw);
+            if (((selw >> lane) & 1u) != 0u && r < cnt_lim) {
+                const uint32_t len = ((vw >> lane) & 1u) ? (uint32_t)(o1 - o[g]) : 0u;
+                s_src[r] = o[g]; s_dst[r] = len;
+                // pull the survivor's first line towards L2 now: the copy phase is a block scan away
+                if (len != 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.data + o[g]));
             }
         }
     }

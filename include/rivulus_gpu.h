@@ -130,7 +130,7 @@ int32_t rvl_ctx_profile_read_launches(rvl_ctx* ctx, double* ms_out, int64_t cap,
 typedef enum rvl_plan { RVL_PLAN_AUTO = 0, RVL_PLAN_FUSED = 1, RVL_PLAN_TWO_PASS = 2 } rvl_plan;
 typedef enum rvl_option {
     RVL_OPT_PLAN = 0,               /* rvl_plan */
-    RVL_OPT_TWO_PASS_MIN_ROWS = 1,  /* default 4 Mi rows */
+    RVL_OPT_TWO_PASS_MIN_ROWS = 1,  /* default 2 Mi rows */
     RVL_OPT_SPARSE_MAX = 2,         /* two-pass: 2048-row tiles with <= this many survivors are gathered (0..256, default 224 = 11 %) */
     RVL_OPT_DENSE_SLOTS = 3,        /* two-pass: 16 KB ring slots per CTA of the dense kernel (2..14) */
     RVL_OPT_DENSE_CTAS_PER_SM = 4,  /* 1 or 2 */

@@ -49,7 +49,7 @@ struct CtxCore {
     std::vector<double> prof_times;
     // execution plan of the fused operator (rvl_ctx_set_option)
     int plan_mode = 0;                      // RVL_PLAN_AUTO / _FUSED / _TWO_PASS
-    int64_t two_pass_min_rows = 4 << 20;    // AUTO: batches at least this large take the two-pass plan
+    int64_t two_pass_min_rows = 2 << 20;    // AUTO: batches at least this large take the two-pass plan (measured crossover: equal at 2 Mi rows, 1.3x at 4 Mi)
     int sparse_max = 224;                   // two-pass: tiles with <= this many survivors (of 2048 rows) are gathered
     int dense_slots = 14;                   // two-pass: 16 KB ring slots per CTA of the dense compaction kernel
     int dense_ctas_per_sm = 1;

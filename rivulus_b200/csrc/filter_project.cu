@@ -210,6 +210,7 @@ static int launch_scan_w(const CoreRef& core, int kind, const ScanParams& sp, in
     }
 }
 static int launch_scan(const CoreRef& core, int kind, const ScanParams& sp, int ctas, int warps) {
+    if (warps == 32) return launch_scan_w<32>(core, kind, sp, ctas);
     return warps == 16 ? launch_scan_w<16>(core, kind, sp, ctas) : launch_scan_w<8>(core, kind, sp, ctas);
 }
 
@@ -360,7 +361,7 @@ int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pre
         if (two_pass) {
             // pass 1: persistent predicate scan (scan_kernels.cuh), every warp owns a contiguous range of tiles
             const int scan_ctas = std::min(192, core->sm_count);
-            const int scan_warps = core->scan_warps == 16 ? 16 : 8;
+            const int scan_warps = core->scan_warps == 32 ? 32 : (core->scan_warps == 16 ? 16 : 8);
             const int64_t n_ranges = (int64_t)scan_ctas * scan_warps;
             tiles_per_chunk = std::max<int64_t>(1, (tiles + n_ranges - 1) / n_ranges);
             // [dense tile ids | sparse tile ids | n_dense, n_sparse, CTAs done, pad] and the per-range bases

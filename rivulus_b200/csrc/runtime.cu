@@ -188,7 +188,7 @@ int32_t rvl_ctx_set_option(rvl_ctx* ctx, int32_t option, int64_t value) {
             if (value < 1 || value > 3) return fail(RVL_INVALID_ARGUMENT, "scan_slots must be in [1, 3]");
             c.scan_slots = (int)value; return RVL_OK;
         case RVL_OPT_SCAN_WARPS:
-            if (value != 8 && value != 16) return fail(RVL_INVALID_ARGUMENT, "scan_warps must be 8 or 16");
+            if (value != 8 && value != 16 && value != 32) return fail(RVL_INVALID_ARGUMENT, "scan_warps must be 8, 16 or 32");
             c.scan_warps = (int)value; return RVL_OK;
         case RVL_OPT_DENSE_WARPS:
             if (value != 8 && value != 16) return fail(RVL_INVALID_ARGUMENT, "dense_warps must be 8 or 16");

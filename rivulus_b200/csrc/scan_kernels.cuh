@@ -26,7 +26,7 @@
 
 namespace rvl {
 
-constexpr int kScanMaxWarps = 16;
+constexpr int kScanMaxWarps = 32;
 // W warps per CTA, each with its own ring of slots of 8192 / W rows (8 warps: 8 KB slots, 16 warps: 4 KB slots), so a
 // CTA always holds n_slots x 64 KB of predicate values
 template <int W> struct ScanShape {

@@ -445,7 +445,7 @@ def test_two_pass_mixed_density_tiles(sparse_max, limit):
 
 
 @pytest.mark.parametrize("slots,per_sm,scan_warps,scan_slots,dense_warps",
-                         [(2, 1, 8, 1, 8), (3, 2, 16, 1, 8), (6, 2, 16, 3, 8), (14, 1, 8, 2, 16), (12, 1, 16, 2, 16), (2, 1, 16, 2, 16)])
+                         [(2, 1, 8, 1, 8), (3, 2, 16, 1, 8), (6, 2, 16, 3, 8), (14, 1, 8, 2, 16), (12, 1, 16, 2, 16), (2, 1, 16, 2, 16), (14, 1, 32, 3, 16), (8, 1, 32, 1, 16)])
 def test_two_pass_ring_depths(slots, per_sm, scan_warps, scan_slots, dense_warps):
     rng = np.random.default_rng(5)
     n = 1_500_000

@@ -87,6 +87,18 @@ def test_config3_strings_and_nulls_at_scale(plan, op, lit):
 
 
 @pytest.mark.gpu
+def test_config3_one_full_size_batch():
+    """configs[2] at the size of one of its RecordBatches: the LAST 50 M-row batch of the 200 M-row table (1.08 GB of string bytes, the
+    largest a batch may hold under int32 offsets is 2 GiB), 10 % nulls in every column, filter on Float64 at 50 %: survivor count,
+    order-sensitive checksums, null counts, bitmap rule and surviving string bytes equal the oracle's, under the AUTO plan."""
+    ctx = capi.Context(0)
+    try:
+        _gpu_check(ctx, 50_000_000, 150_000_000, (capi.SYNTH_F64, 0, 10), ">", 500.0, [(capi.SYNTH_STR, 1, 10), (capi.SYNTH_I64, 2, 10)])
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("op,lit,limit", [(">", 899, -1), (">", 499, -1), ("<=", 99, -1), (">", 499, 1_000_000)])
 def test_config5_int_float_bool_at_scale(op, lit, limit):
     """configs[4] shape (one shard): {k: Int64, v: Float64, f: Boolean}, every column projected, row range deep inside a 4 B-row table."""
@@ -94,6 +106,17 @@ def test_config5_int_float_bool_at_scale(op, lit, limit):
     try:
         _gpu_check(ctx, 48_000_000, 3_500_000_000, (capi.SYNTH_KEY1000, 0, 0), op, lit, [(capi.SYNTH_F64, 1, 0), (capi.SYNTH_BOOL, 2, 0)], limit)
         _gpu_check(ctx, 16_000_000, 3_500_000_000, (capi.SYNTH_KEY1000, 0, 5), op, lit, [(capi.SYNTH_F64, 1, 5), (capi.SYNTH_BOOL, 2, 5)], limit)
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
+def test_config5_one_full_size_shard():
+    """configs[4] at the size of one of its shards: the LAST 500 M-row shard (rows 3.5 B .. 4 B) of the 4 B-row {k: Int64, v: Float64,
+    f: Boolean} table at 8 GPUs, every column projected, 50 %: count + order-sensitive checksums (the Boolean column included)."""
+    ctx = capi.Context(0)
+    try:
+        _gpu_check(ctx, 500_000_000, 3_500_000_000, (capi.SYNTH_KEY1000, 0, 0), ">", 499, [(capi.SYNTH_F64, 1, 0), (capi.SYNTH_BOOL, 2, 0)])
     finally:
         ctx.close()
 

@@ -210,6 +210,18 @@ int32_t rvl_stream_push(rvl_stream* s, const rvl_column* cols, int32_t ncols, in
         RVL_CUDA_TRY(cudaEventSynchronize(sl.free_ev));
         poll_limit(s);
     }
+    if (!s->limit_hit && s->limit > 0 && s->pushed >= 1) {
+        // LIMIT streams start slowly: batch 1 waits for batch 0's count, batches 2 and 3 for the batch two before them; only then
+        // does the pipeline run at its full depth.  A limit that the first batches already satisfy (LIMIT 1000 over 64 K..1 M-row
+        // batches) then costs exactly the batches a LimitStream would pull (streaming.rs:269-271), not pipeline-depth more.
+        const int64_t i = s->pushed, n_slots = (int64_t)s->slots.size();
+        const int64_t window = i <= 1 ? 1 : (i <= 3 ? 2 : n_slots);
+        if (window < n_slots) {
+            Slot& w = s->slots[(size_t)((i - window) % n_slots)];
+            if (w.used) RVL_CUDA_TRY(cudaEventSynchronize(w.free_ev));
+            poll_limit(s);
+        }
+    }
     if (s->limit_hit || s->limit == 0) { s->limit_hit = true; s->skipped++; return RVL_OK; }
 
     // AUTO: a dense stream (more than one survivor in four rows: every PCIe line is needed anyway) goes through the copy engine,

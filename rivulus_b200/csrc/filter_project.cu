@@ -329,24 +329,25 @@ int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pre
             pend->bytes_counter[(size_t)j] = n_counters++;
         }
     }
-    RVL_TRY(dev_alloc_zeroed(core, (size_t)(n_counters + 2) * 8, &pend->counters));
+    const int launches_needed = std::max<int>(1, std::max<int>(((int)col8s.size() + kMaxCol8 - 1) / kMaxCol8, ((int)bitcols.size() + kMaxBitCols - 1) / kMaxBitCols));
+    // plan: one fused pass (small batches, one launch), or predicate scan + independent compaction pass (large batches)
+    const bool two_pass = n > 0 && (!col8s.empty() || !bitcols.empty()) && tiles < (1ll << 32) &&  // tile ids are 32-bit in the second pass
+                          (core->plan_mode == 2 || (core->plan_mode == 0 && limit < 0 && n >= core->two_pass_min_rows));
+    // per fused launch: one look-back descriptor per super-tile
+    const int64_t n_super = (n + kSuperRows - 1) / kSuperRows;
+    const size_t status_words = (size_t)n_super;
+    const size_t counter_words = ((size_t)n_counters + 2 + 1) & ~(size_t)1;
+    RVL_TRY(dev_alloc_zeroed(core, (counter_words + (two_pass || n == 0 ? 0 : status_words * (size_t)launches_needed)) * 8, &pend->counters));
     unsigned long long* dctr = (unsigned long long*)pend->counters->ptr;
     pend->n_counters = n_counters;
     // done flag lives right behind the counters
     uint32_t* done_flag = (uint32_t*)(dctr + n_counters);
 
     if (n > 0) {
-        const int launches_needed = std::max<int>(1, std::max<int>(((int)col8s.size() + kMaxCol8 - 1) / kMaxCol8, ((int)bitcols.size() + kMaxBitCols - 1) / kMaxBitCols));
-        // plan: one fused pass (small batches, one launch), or predicate scan + independent compaction pass (large batches)
-        const bool two_pass = (!col8s.empty() || !bitcols.empty()) && tiles < (1ll << 32) &&  // tile ids are 32-bit in the second pass
-                              (core->plan_mode == 2 || (core->plan_mode == 0 && limit < 0 && n >= core->two_pass_min_rows));
         const bool need_sel = want_mask || !strjobs.empty() || launches_needed > 1 || two_pass;
-        BufRef status, sel, tile_prefix, lists;
-        // per launch: one look-back descriptor per super-tile, zeroed together
-        const int64_t n_super = (n + kSuperRows - 1) / kSuperRows;
-        const size_t status_words = (size_t)n_super;
-        RVL_TRY(dev_alloc_zeroed(core, status_words * 8 * (size_t)launches_needed, &status));
-        pend->temps.push_back(status);
+        BufRef sel, tile_prefix, lists;
+        // look-back descriptors live behind the counters in the same zeroed allocation (one malloc + one memset per invocation)
+        uint64_t* const status_base = two_pass ? nullptr : (uint64_t*)pend->counters->ptr + counter_words;
         if (need_sel) {
             // whole tiles, so the second-pass kernels can read 64 words per tile unconditionally
             // (the two-pass scan writes every word of every tile unless a LIMIT lets ranges stop early)
@@ -422,7 +423,7 @@ int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pre
             }
             fp.base_in = base_in;
             fp.done_flag = done_flag;
-            fp.tile_status = (uint64_t*)status->ptr + (size_t)L * status_words;
+            fp.tile_status = status_base + (size_t)L * status_words;
             const int c0 = L * kMaxCol8, c1 = std::min<int>((int)col8s.size(), c0 + kMaxCol8);
             fp.n_col8 = std::max(0, c1 - c0);
             for (int k = 0; k < fp.n_col8; ++k) fp.col8[k] = col8s[(size_t)(c0 + k)];
@@ -481,7 +482,8 @@ int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pre
     if (base_in != nullptr)
         RVL_CUDA_TRY(cudaMemcpyAsync(pend->mailbox + n_counters, base_in, 8, cudaMemcpyDeviceToHost, core->stream));
     if (total_ext != nullptr) RVL_CUDA_TRY(cudaMemcpyAsync(total_ext, dctr, 8, cudaMemcpyDeviceToDevice, core->stream));
-    RVL_CUDA_TRY(cudaEventCreateWithFlags(&pend->done_event, cudaEventDisableTiming));
+    pend->done_event = core->take_event();
+    if (pend->done_event == nullptr) return fail(RVL_CUDA, "cudaEventCreate failed");
     RVL_CUDA_TRY(cudaEventRecord(pend->done_event, core->stream));
     *out = pend.release();
     return RVL_OK;
@@ -493,7 +495,7 @@ int fp_finish(FpPending* pend, rvl_batch** out, rvl_batch** mask_out) {
     RVL_CUDA_TRY(cudaSetDevice(core->device));
     if (pend->done_event) {
         cudaError_t e = cudaEventSynchronize(pend->done_event);
-        cudaEventDestroy(pend->done_event);
+        core->give_event(pend->done_event);
         pend->done_event = nullptr;
         if (e != cudaSuccess) return fail(RVL_CUDA, std::string("fused filter/project failed: ") + cudaGetErrorString(e));
     } else {

@@ -25,6 +25,7 @@ CtxCore::~CtxCore() {
     if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
     if (d2h_stream) { cudaStreamSynchronize(d2h_stream); cudaStreamDestroy(d2h_stream); }
     for (auto& e : prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    for (cudaEvent_t e : event_pool) cudaEventDestroy(e);
     if (mailbox) cudaFreeHost(mailbox);
 }
 

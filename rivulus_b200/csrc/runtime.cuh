@@ -56,6 +56,15 @@ struct CtxCore {
     int dense_warps = 16;                   // two-pass: consumer warps per CTA of the dense kernel (8 or 16)
     int scan_warps = 16;                    // two-pass: warps per CTA of the predicate scan (8 or 16)
     int scan_slots = 2;                     // two-pass: 8 KB ring slots per warp of the predicate scan (1..3)
+    // pooled timing-less events (one per in-flight operator invocation): create / destroy per batch costs microseconds
+    std::vector<cudaEvent_t> event_pool;
+    cudaEvent_t take_event() {
+        if (!event_pool.empty()) { cudaEvent_t e = event_pool.back(); event_pool.pop_back(); return e; }
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        return e;
+    }
+    void give_event(cudaEvent_t e) { if (e) event_pool.push_back(e); }
     int prof_flush();
     uint64_t* next_slot() { return mailbox + kSlotBase + (size_t)(slot_cursor.fetch_add(1) % kSlots) * kSlotWords; }
     ~CtxCore();

@@ -77,7 +77,7 @@ GPU_TESTS = [
     "test_execute_filter_gt", "test_execute_filter_eq", "test_execute_filter_lt", "test_execute_filter_no_matches", "test_execute_limit",
     "test_execute_chained_operations", "test_execute_filter_then_select", "test_execute_select_variants",
     "test_collect_simple_select_filter_limit", "test_collect_streaming", "test_optimizer_rewrite", "test_main_demo_queries",
-    "test_rb_slice", "test_rb_take", "test_output_layout_rules", "test_rb_select_columns", "test_rb_filter", "test_rb_concat",
+    "test_rb_slice", "test_rb_take", "test_rb_mixed_types_null_column_and_chained_ops", "test_output_layout_rules", "test_rb_select_columns", "test_rb_filter", "test_rb_concat",
     "test_rb_try_new_errors",
     "test_streaming_plan_memory_source_ops", "test_limit_stream_batches", "test_collect_vs_collect_batches",
     "test_filter_select_stream_operators", "test_streaming_planner_conversions", "test_streaming_alias_dropped_and_null_flattening",

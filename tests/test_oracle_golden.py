@@ -241,6 +241,31 @@ def test_rb_take():  # record_batch.rs:752-791
         b.take([0, 5, 1])
 
 
+def test_rb_mixed_types_null_column_and_chained_ops():  # record_batch.rs:1049-1073, 1076-1103, 1106-1130, 1133-1151
+    # test_mixed_column_types: one column of every array type, a null string among them
+    m = RecordBatch.try_new(["int_col", "float_col", "string_col", "bool_col", "null_col"],
+                            [Array.from_list([1, 2, 3], EX_INT64), Array.from_list([1.1, 2.2, 3.3], EX_FLOAT64),
+                             Array.from_list(["A", None, "C"], EX_STRING), Array.from_list([True, False, True], EX_BOOLEAN),
+                             Array.from_list([None, None, None], EX_NULL)])
+    assert (m.num_rows(), m.num_columns()) == (3, 5)
+    # test_null_column_handling: the NullArray column reports dtype Null and null_count == len
+    nb = RecordBatch.try_new(["id", "null_col"], [Array.from_list([1, 2, 3], EX_INT64), Array.from_list([None, None, None], EX_NULL)])
+    assert (nb.num_rows(), nb.num_columns()) == (3, 2)
+    assert nb.column(1).dtype == EX_NULL and nb.column(1).null_count == 3
+    # test_large_batch_performance (the assertions, not the timings): 10 000 rows, slice(1000, 5000)
+    size = 10_000
+    big = RecordBatch.try_new(["id", "value"], [Array.from_list(list(range(size)), EX_INT64), Array.from_list([i * 1.5 for i in range(size)], EX_FLOAT64)])
+    assert big.num_rows() == size
+    sl = big.slice(1000, 5000)
+    assert sl.num_rows() == 5000 and sl.column(0).to_list()[:2] == [1000, 1001] and sl.column(1).to_list()[-1] == 5999 * 1.5
+    # test_slice_preserves_schema
+    b = rb_id_name_active()
+    assert b.slice(1, 1).column_names() == ["id", "name", "active"]
+    # test_chained_operations: slice -> select -> filter
+    f = b.slice(0, 3).select_columns([0, 2]).filter(Array.from_list([True, False, True], EX_BOOLEAN))
+    assert (f.num_rows(), f.num_columns()) == (2, 2) and f.column(0).to_list() == [1, 3] and f.column(1).to_list() == [True, True]
+
+
 def test_rb_select_columns():  # record_batch.rs:794-819
     b = rb_id_name_active()
     assert b.select_columns([0, 2]).column_names() == ["id", "active"]

@@ -381,14 +381,30 @@ static __global__ void __launch_bounds__(kBlock) compact_bits_kernel(const __gri
     const int64_t n_tiles = (p.n_rows + kTileRows - 1) / kTileRows;
     const uint64_t base0 = p.base_in != nullptr ? (uint64_t)*p.base_in : 0ull;
     uint32_t* const buf = s_out[warp];
-#pragma unroll 1
-    for (int64_t tile = (int64_t)blockIdx.x * kWarps + warp; tile < n_tiles; tile += (int64_t)gridDim.x * kWarps) {
-        const uint64_t info = p.tile_info[tile];
-        if ((info & ((1ull << kInfoShift) - 1ull)) == 0ull) continue;  // no survivor in this tile
-        const uint64_t prefix = p.chunk_base[(uint32_t)tile / (uint32_t)p.tiles_per_chunk] + (info >> kInfoShift);
-        if (p.limit >= 0 && prefix >= (uint64_t)p.limit) continue;
+    // software prefetch: the next tile's info word, range base and selection words are requested one iteration ahead
+    const int64_t stride = (int64_t)gridDim.x * kWarps;
+    int64_t tile = (int64_t)blockIdx.x * kWarps + warp;
+    uint64_t ninfo = 0, nbase = 0;
+    uint32_t nw0 = 0, nw1 = 0;
+    if (tile < n_tiles) {
+        ninfo = p.tile_info[tile]; nbase = p.chunk_base[(uint32_t)tile / (uint32_t)p.tiles_per_chunk];
         const uint32_t* sw = p.sel + tile * kTileWords;
-        const uint32_t w0 = __ldg(sw + lane), w1 = __ldg(sw + 32 + lane);
+        nw0 = __ldg(sw + lane); nw1 = __ldg(sw + 32 + lane);
+    }
+#pragma unroll 1
+    for (; tile < n_tiles; tile += stride) {
+        const uint64_t info = ninfo;
+        const uint64_t cbase = nbase;
+        const uint32_t w0 = nw0, w1 = nw1;
+        if (tile + stride < n_tiles) {
+            const int64_t nt = tile + stride;
+            ninfo = p.tile_info[nt]; nbase = p.chunk_base[(uint32_t)nt / (uint32_t)p.tiles_per_chunk];
+            const uint32_t* sw = p.sel + nt * kTileWords;
+            nw0 = __ldg(sw + lane); nw1 = __ldg(sw + 32 + lane);
+        }
+        if ((info & ((1ull << kInfoShift) - 1ull)) == 0ull) continue;  // no survivor in this tile
+        const uint64_t prefix = cbase + (info >> kInfoShift);
+        if (p.limit >= 0 && prefix >= (uint64_t)p.limit) continue;
         uint32_t e0, e1, total;
         tile_word_scan(w0, w1, lane, e0, e1, total);
         // survivors with a tile-local rank >= lim_rel lie beyond the LIMIT

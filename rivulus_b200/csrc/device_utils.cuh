@@ -111,28 +111,9 @@ constexpr uint64_t kStatusPrefix = 2ull << 62;
 constexpr uint64_t kStatusMask = 3ull << 62;
 constexpr uint64_t kValueMask = ~kStatusMask;
 
-// Called by all 32 lanes of one warp of tile `tile` (> 0): sums the aggregates of the predecessor
-// tiles back to the nearest published inclusive prefix.  Tiles are processed in blockIdx order, so a
-// predecessor is always resident or finished (same forward-progress argument as CUB's scan).
-__device__ __forceinline__ uint64_t lookback_exclusive(const uint64_t* status, int64_t tile, int lane) {
-    uint64_t exclusive = 0;
-    int64_t base = tile - 1;
-    while (true) {
-        const int64_t idx = base - lane;
-        uint64_t s = kStatusPrefix;  // virtual tile -1: inclusive prefix 0
-        if (idx >= 0) {
-            do { s = ld_relaxed_gpu(status + idx); } while ((s & kStatusMask) == 0);
-        }
-        const uint32_t prefix_lanes = __ballot_sync(0xFFFFFFFFu, (s & kStatusMask) == kStatusPrefix);
-        const int first = __ffs(prefix_lanes) - 1;  // nearest predecessor holding an inclusive prefix
-        const uint64_t take = (first < 0 || lane <= first) ? (s & kValueMask) : 0ull;
-        exclusive += warp_sum_u64(take);
-        if (first >= 0) break;
-        base -= 32;
-    }
-    return exclusive;
-}
-
+// Decoupled look-back of one warp of tile `tile` (> 0): sums the aggregates of the predecessor tiles back to the nearest published
+// inclusive prefix.  Tiles are processed in blockIdx order, so a predecessor is always resident or finished (same forward-progress
+// argument as CUB's scan).
 // 256-descriptor-wide look-back run by one warp (8 predecessors per lane per round)
 __device__ __forceinline__ uint64_t lookback_exclusive_wide(const uint64_t* status, int64_t tile, int lane) {
     uint64_t exclusive = 0;

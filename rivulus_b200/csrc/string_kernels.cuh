@@ -258,29 +258,6 @@ static __global__ void __launch_bounds__(kBlock, 6) string_sizes_kernel(const __
 
 constexpr uint32_t kStrChunk = 16 * 1024;   // staging bytes per pass (a 2048-row tile of ~24-byte strings at 50 % fits in one)
 
-// the same for two values at once (one pair of barriers instead of two)
-__device__ __forceinline__ void block_exclusive_scan2(uint32_t a, uint32_t b, uint32_t* s_wa, uint32_t* s_wb, uint32_t& ea, uint32_t& eb,
-                                                      uint32_t& ta, uint32_t& tb) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t ia = a, ib = b;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t na = __shfl_up_sync(0xFFFFFFFFu, ia, o), nb = __shfl_up_sync(0xFFFFFFFFu, ib, o);
-        if (lane >= o) { ia += na; ib += nb; }
-    }
-    if (lane == 31) { s_wa[warp] = ia; s_wb[warp] = ib; }
-    __syncthreads();
-    uint32_t oa = 0, ob = 0, sa = 0, sb = 0;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-        const uint32_t ca = s_wa[w], cb = s_wb[w];
-        oa += (w < warp) ? ca : 0u; ob += (w < warp) ? cb : 0u;
-        sa += ca; sb += cb;
-    }
-    __syncthreads();
-    ea = oa + ia - a; eb = ob + ib - b; ta = sa; tb = sb;
-}
-
 static __global__ void __launch_bounds__(kBlock, 6) string_gather_kernel(const __grid_constant__ StrGatherParams p) {
     __shared__ __align__(16) int32_t s_src[kTileRows];        // survivor r: first source byte
     __shared__ __align__(16) uint32_t s_dst[kTileRows + 8];   // survivor r: length, then first destination byte inside the tile's dense range; [count..] = total

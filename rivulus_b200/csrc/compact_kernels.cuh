@@ -297,13 +297,33 @@ static __global__ void __launch_bounds__(kBlock) gather_sparse_kernel(const __gr
     const uint32_t n_list = *p.list_count;
     const uint64_t base0 = p.base_in != nullptr ? (uint64_t)*p.base_in : 0ull;
     uint16_t* rows = s_rows[warp];
+    // two-stage software prefetch (as in the dense kernel): the tile id two iterations ahead, its selection words and prefix words
+    // one ahead — a sparse tile is a chain of dependent round trips (id -> words -> rows -> values), the first two now overlap
+    // with the previous tile's gather
+    const uint32_t stride = gridDim.x * kWarps;
+    uint32_t i = blockIdx.x * kWarps + warp;
+    uint32_t ntile = i < n_list ? p.list[i] : 0u;
+    uint32_t nntile = i + stride < n_list ? p.list[i + stride] : 0u;
+    uint32_t nw0 = 0, nw1 = 0;
+    uint64_t ninfo = 0, ncbase = 0;
+    if (i < n_list) {
+        const uint32_t* sw = p.sel + (size_t)ntile * kTileWords;
+        nw0 = __ldg(sw + lane); nw1 = __ldg(sw + 32 + lane);
+        ninfo = p.tile_info[ntile]; ncbase = p.chunk_base[ntile / (uint32_t)p.tiles_per_chunk];
+    }
 #pragma unroll 1
-    for (uint32_t i = blockIdx.x * kWarps + warp; i < n_list; i += gridDim.x * kWarps) {
-        const int64_t tile = (int64_t)p.list[i];
+    for (; i < n_list; i += stride) {
+        const int64_t tile = (int64_t)ntile;
         const int64_t row0 = tile * kTileRows;
-        const uint32_t* sw = p.sel + tile * kTileWords;
-        const uint32_t w0 = __ldg(sw + lane), w1 = __ldg(sw + 32 + lane);
-        const uint64_t prefix = tile_prefix_of(p, tile);
+        const uint32_t w0 = nw0, w1 = nw1;
+        const uint64_t prefix = ncbase + (ninfo >> kInfoShift);
+        if (i + stride < n_list) {
+            ntile = nntile;
+            const uint32_t* sw = p.sel + (size_t)ntile * kTileWords;
+            nw0 = __ldg(sw + lane); nw1 = __ldg(sw + 32 + lane);
+            ninfo = p.tile_info[ntile]; ncbase = p.chunk_base[ntile / (uint32_t)p.tiles_per_chunk];
+            if (i + 2 * stride < n_list) nntile = p.list[i + 2 * stride];
+        }
         uint32_t e0, e1, total;
         tile_word_scan(w0, w1, lane, e0, e1, total);
         if (total > (uint32_t)kSparseCap) total = kSparseCap;  // cannot happen: pass 1 classifies with sparse_max <= kSparseCap

@@ -142,30 +142,32 @@ __global__ void __launch_bounds__(W * 32, 1) predicate_scan_kernel(const __grid_
                 const bool has_valid = p.pred_valid.words != nullptr;
                 if (tma) mbar_wait(&full[slot], phase);
                 const uint64_t* src = ring + (size_t)slot * kScanItemRows + lane;
+                // one body, instantiated for the two (warp-uniform) sources so the inner loop carries no branch: the TMA ring
+                // (LDS.64, conflict-free) or, for a ragged tail / unaligned view, the column itself
+                auto evaluate = [&](auto load) {
 #pragma unroll
-                for (int b = 0; b < kItemWords / 8; ++b) {
-                    uint64_t v[8];
+                    for (int b = 0; b < kItemWords / 8; ++b) {
+                        uint64_t v[8];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int w = b * 8 + k;
-                        if (tma) v[k] = src[w * 32];
-                        else {
-                            const int64_t row = row0 + w * 32 + lane;
-                            v[k] = row < p.n_rows ? ld_stream(p.pred_values + row) : 0ull;
+                        for (int k = 0; k < 8; ++k) v[k] = load(b * 8 + k);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const int w = b * 8 + k;
+                            bool c = scan_keep<PRED>(p, v[k]);
+                            if (has_valid) {
+                                const uint32_t vw = __shfl_sync(0xFFFFFFFFu, wa, w);
+                                c = ((vw >> lane) & 1u) ? c : (p.keep_null != 0u);
+                            }
+                            const uint32_t m = __ballot_sync(0xFFFFFFFFu, c);
+                            if (lane == w) myword = m;
                         }
                     }
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int w = b * 8 + k;
-                        bool c = scan_keep<PRED>(p, v[k]);
-                        if (has_valid) {
-                            const uint32_t vw = __shfl_sync(0xFFFFFFFFu, wa, w);
-                            c = ((vw >> lane) & 1u) ? c : (p.keep_null != 0u);
-                        }
-                        const uint32_t m = __ballot_sync(0xFFFFFFFFu, c);
-                        if (lane == w) myword = m;
-                    }
-                }
+                };
+                if (tma) evaluate([&](int w) -> uint64_t { return src[w * 32]; });
+                else evaluate([&](int w) -> uint64_t {
+                    const int64_t row = row0 + w * 32 + lane;
+                    return row < p.n_rows ? ld_stream(p.pred_values + row) : 0ull;
+                });
                 // every value of the slot has been consumed: re-arm it with the item D steps ahead
                 if (lane == 0 && j + D < n_items && item_tma(j + D))
                     tma_load_1d(ring + (size_t)slot * kScanItemRows, p.pred_values + range_row0 + (j + D) * kScanItemRows, kScanItemBytes, &full[slot]);

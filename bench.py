@@ -488,6 +488,13 @@ def main():
     ap.add_argument("--dense-warps", type=int, default=None)
     ap.add_argument("--scan-slots", type=int, default=None)
     args = ap.parse_args()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # `python bench.py --gpus N` without a launcher: start one rank per GPU ourselves, exactly as the driver would
+        import subprocess
+        port = 29500 + (os.getpid() % 2000)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
     quiet_stdout()
     if args.cpu_rows is None:
         args.cpu_rows = 500_000 if args.impl == "reference" else 4_000_000

@@ -107,6 +107,24 @@ def test_reference_known_answers_on_gpu(name):
                                                       "test_collect_vs_collect_batches"), "no CUDA kernel ran"
 
 
+@pytest.mark.gpu
+def test_cpp_demo_program_runs_the_reference_demo_queries():
+    """rivulus_b200/host/demo_main.cpp: the reference's main.rs queries written against the C++ host API (LazyFrame / Expr / DataFrame /
+    collect / collect_streaming), compiled by build() and executed on the GPU; expected rows from SURVEY.md Appendix B."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(_HERE), "rivulus_b200", "lib", "rivulus_demo")
+    assert os.path.exists(exe), "build() did not produce rivulus_b200/lib/rivulus_demo"
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    assert lines[0] == "q1 rows=2 | name:[Charlie,Eve] age:[35,42]"
+    assert lines[1] == "q2 rows=2 | name:[Bob,Diana] user_age:[30,28]"
+    assert lines[2] == "q3 rows=2 | name:[Alice,Bob] age:[25,30] score:[85.5,92]"
+    assert lines[3] == "q4 rows=0 | name:[] age:[] score:[]"
+    m = re.match(r"q5 rows=1 cols=2 launches=(\d+)$", lines[4])
+    assert m and int(m.group(1)) > 0, lines[4]
+
+
 # ------------------------------------------------------------------ randomized differential test against the oracle
 def _random_frame(rng, n):
     def maybe(v, p):

@@ -26,6 +26,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 THRESHOLDS = [(998, 0.001), (899, 0.10), (499, 0.50), (99, 0.90)]
+# the workload both arms run (BASELINE.json configs[1]); the same string goes into config.workload of both JSON lines
+WORKLOAD = ("configs[1]: filter(k > T).select([a,b,c,d]) over {k,a:Int64,b:Float64,c:Int64,d:Float64}, "
+            "T in 998/899/499/99 (0.1/10/50/90 %), 4 queries per step")
 N_PROJ = 4
 BYTES_PER_ROW_IN = 40  # 5 x 8-byte columns
 
@@ -139,8 +142,8 @@ def run_reference(args):
         "impl": "reference", "metric": "rows_per_sec", "value": value, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": min(args.warmup, 1), "ms_per_step": secs * 1000.0 / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": "filter(k > T).select([a,b,c,d]) over {k,a:Int64,b:Float64,c:Int64,d:Float64}, T in 998/899/499/99 "
-                               "(0.1/10/50/90 %), reference eager engine collect()", "rows_per_gpu": args.rows,
+        "config": {"workload": WORKLOAD, "rows_per_gpu": args.rows, "global_rows": args.rows * max(args.gpus, 1),
+                   "engine": "reference eager engine: LazyFrame.filter(..).select(..).collect() per query",
                    "note": "the reference is single-threaded Rust and cannot be compiled in this image (no rustc); this arm runs "
                            "oracle/ — the C++ restatement of its eager engine — as one instance per host core on row-range shards"},
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": threads, "kind": "port",
@@ -290,9 +293,7 @@ def run_native(args):
         "metric": "rows_per_sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int64", "data": "synthetic",
-        "config": {"workload": "configs[1]: filter(k > T).select([a,b,c,d]) over {k,a:Int64,b:Float64,c:Int64,d:Float64}, "
-                               "T in 998/899/499/99 (0.1/10/50/90 %), one rvl_filter_project call per query, 4 queries per step",
-                   "plan": args.plan,
+        "config": {"workload": WORKLOAD, "engine": "one rvl_filter_project call per query", "plan": args.plan,
                    "rows_per_gpu": rows, "global_rows": rows * world, "partitioning": f"row-range x{world}", "host_affinity": numa,
                    "l2": "inputs (40 B/row x rows) far exceed the 126 MB L2; no flush needed",
                    "timing": "CUDA events on the library stream around K steps incl. count readback; max over ranks"},

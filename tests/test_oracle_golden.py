@@ -77,6 +77,23 @@ def test_series_dtype_inference():  # series.rs:400-469, 521-534
 
 
 # ---------------------------------------------------------------- physical_plan/plan.rs (eager)
+def test_dataframe_construction_rules():  # datatypes/dataframe.rs tests: creation :41-63, length mismatch :84-118, duplicate :120-150, edge cases :end
+    df = df_name_age_score()
+    assert (df.height(), df.width(), df.column_names()) == (3, 3, ["name", "age", "score"])
+    e = DataFrame.new([])                                                     # test_dataframe_creation_empty_columns_list
+    assert (e.height(), e.width()) == (0, 0)
+    one = DataFrame.new([("name", ["Alice", "Bob"])])                         # test_dataframe_creation_single_column
+    assert (one.height(), one.width()) == (2, 1)
+    with pytest.raises(OracleError, match="Column lengths mismatch: expected 2, found 3 for column 'age'"):
+        DataFrame.new([("name", ["Alice", "Bob"]), ("age", [25, 30, 35])])
+    with pytest.raises(OracleError, match="Duplicate column name: 'name'"):
+        DataFrame.new([("name", ["Alice", "Bob"]), ("name", ["Charlie", "David"])])
+    nulls = DataFrame.new([("nulls", [None, None, None]), ("numbers", [1, 2, 3])])   # test_dataframe_with_all_null_column
+    assert (nulls.height(), nulls.width(), nulls.dtypes()) == (3, 2, ["Null", "Int64"])
+    mixed = DataFrame.new([("mixed", [1, 2.5, 3])])                           # test_dataframe_with_mixed_numeric_column
+    assert mixed.dtypes() == ["Float64"]
+
+
 def test_execute_filter_gt():  # plan.rs:505-525
     r = LazyFrame.from_dataframe(df_name_age_score()).filter(col("age").gt(lit(25))).collect()
     assert (r.height(), r.width()) == (2, 3)

@@ -380,6 +380,27 @@ def test_primitive_builder():  # primitive.rs:546-604
     assert c.null_count == 0 and c.validity is None
 
 
+def test_array_slices_and_null_counts():  # boolean.rs / string.rs test_slice_operation, primitive.rs test_multiple_slices_consistency,
+    # test_new_with_some_nulls / test_all_nulls / test_empty_array of the three array types
+    b = Array.from_list([True, None, False, None, True, False], EX_BOOLEAN).slice(2, 3)
+    assert (b.len(), b.export().offset, b.to_list(), b.null_count()) == (3, 2, [False, None, True], 1)
+    st = Array.from_list(["a", None, "b", None, "c", "d"], EX_STRING).slice(2, 3)
+    assert (st.len(), st.export().offset, st.to_list(), st.null_count()) == (3, 2, ["b", None, "c"], 1)
+    vals = list(range(20))
+    arr = Array.from_list([v if v % 3 != 0 else None for v in vals], EX_INT64)     # every third is null
+    s1, s2, s3 = arr.slice(0, 10), arr.slice(5, 10), arr.slice(10, 10)
+    assert s1.null_count() + s3.null_count() == arr.null_count() == 7
+    assert s1.to_list()[5:10] == s2.to_list()[0:5]
+    for dtype, some, alln in ((EX_INT64, [1, None, 3], [None, None]), (EX_FLOAT64, [1.5, None, 2.5], [None, None]),
+                              (EX_BOOLEAN, [True, None, False], [None, None]), (EX_STRING, ["x", None, ""], [None, None])):
+        a = Array.from_list(some, dtype)
+        assert (a.len(), a.null_count(), a.to_list()) == (3, 1, some)
+        n = Array.from_list(alln, dtype)
+        assert (n.len(), n.null_count(), n.to_list()) == (2, 2, alln)
+        e = Array.from_list([], dtype)
+        assert (e.len(), e.null_count(), e.to_list()) == (0, 0, [])
+
+
 def test_string_layout():  # string.rs:362-381, 574-633, 683-694
     a = Array.from_list(["hello", "", "world"], EX_STRING).export()
     assert a.offsets.tolist() == [0, 5, 5, 10] and a.validity is None

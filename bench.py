@@ -11,6 +11,16 @@ Multi-GPU (torchrun, one rank per GPU): weak scaling — rank g owns rows [g*R, 
 (row-range sharding); no data-path collective, torch.distributed only for the barrier and the
 max-over-ranks of the device time.
 
+Sub-records of the same JSON line (each bounded to a few seconds, each checked against the oracle / golden checksums):
+  c5  BASELINE configs[4] at every N: the 4 B-row {k: Int64, v: Float64, f: Boolean} table row-range sharded over the N ranks
+      (strong scaling), filter(k > T).select([k, v, f]) at 10 % / 50 %, per-rank device time, B_alg fraction, and the
+      order-preserving physical concatenation onto rank 0 timed separately (rvl_gather_to at N = 1, the CUDA-IPC
+      rvl_gather_* push over NVLink at N > 1); count + order-sensitive checksums vs tests/golden/synth_checksums.json
+  c1  configs[0] (N = 1): 1 M-row {name, age}, LazyFrame.from_dataframe(df).filter(age > 25).select([name]).collect() through
+      rivulus_b200.frame (host layer -> C ABI), wall clock, against the oracle's eager engine at the same 1 M rows on 1 core
+  c3  configs[2] (N = 1): 200 M rows, String projection + 10 % nulls
+  c4  configs[3] (N = 1): collect_streaming() shape, 64 K - 1 M-row host batches, LIMIT 1000 early stop, pinned H2D overlap
+
     python bench.py [--gpus N] [--steps K] [--warmup W] [--rows R] [--impl native|reference]
 """
 import argparse
@@ -280,11 +290,15 @@ def run_native(args):
                       "rows_per_s": rows / (avg_ms / 1e3) if avg_ms > 0 else None,
                       "b_scan_gb": (BYTES_PER_ROW_IN * rows + N_PROJ * 8 * counts[qi]) / 1e9})
     achieved = alg_total / 1e9 / (kern_total / 1e3) if kern_total > 0 else 0.0
-    traffic = None
+    # dram__bytes_read + dram__bytes_write per operator invocation from the committed `ncu --set full` capture (profiles/traffic.json):
+    # a STATIC figure measured once on one GPU at this workload, not re-measured by this run — labelled so, and left out at N > 1
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if world == 1 and rows == 1_000_000_000 and os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic = tj.get("dram_bytes_per_launch")
+            traffic_src = "static, not re-measured by this run: " + str(tj.get("source", "profiles/traffic.json"))
         except Exception:
             traffic = None
 
@@ -298,7 +312,7 @@ def run_native(args):
                    "l2": "inputs (40 B/row x rows) far exceed the 126 MB L2; no flush needed",
                    "timing": "CUDA events on the library stream around K steps incl. count readback; max over ranks"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": peak_src,
+                     "traffic_source": traffic_src, "peak_source": peak_src,
                      "kernel": ("fused_filter_project_kernel<kPredI64>" if args.plan == "fused" else
                                 "predicate_scan_kernel<kPredI64> + compact_dense_kernel + gather_sparse_kernel (one operator invocation)"),
                      "definition": "sum of algorithmic bytes (SURVEY 8(d): 8.16/22.2/54.0/68.8 B per row at 0.1/10/50/90 %, x rows) of the timed "
@@ -307,22 +321,378 @@ def run_native(args):
         "sweep": sweep, "gpu_launches": int(total_launches.item()), "clocks": clocks, "parity": parity,
     }
 
-    # ---- CPU baseline (rank 0, N=1 only): the oracle's eager engine on a bounded sample, 1 core like the reference
-    if rank == 0 and world == 1 and args.cpu_rows > 0:
-        t0 = time.time()
+    # ---- full-size parity (rank 0 owns rows [0, R)): survivor count + order-sensitive checksum of every projected column of
+    # every query against the values the CPU oracle computed from the generator (tests/golden/synth_checksums.json)
+    if rank == 0 and not args.no_golden:
+        line["parity_full"] = golden_check(ctx, table, rows, begin, preds, proj)
+
+    # ---- CPU baseline (rank 0, every N): the oracle's eager engine on a bounded sample, 1 core like the reference
+    if rank == 0 and args.cpu_rows > 0:
         v, secs = cpu_eager_sweep(args.cpu_rows, 1, 1, 0)
         line["cpu_baseline"] = {"value": v, "unit": "rows/s", "cores": 1, "kind": "port",
                                 "sample": f"{args.cpu_rows} rows x 4 queries, eager collect() restatement ({secs:.1f} s)"}
+    barrier()
 
     # ---- end to end through the streaming C ABI with HOST buffers
     if not args.no_e2e:
         line["e2e"] = run_e2e(args, ctx, table, preds, proj, rank, world, local_rank, barrier)
+
+    # ---- the other BASELINE configs as sub-records (each guarded: a failure is reported in the record, not by losing the line)
+    table.release()
+    del table
+    ctx.trim()
+    if not args.no_configs:
+        peak, _ = load_peaks()
+        line["c5"] = guarded(run_c5, args, ctx, rank, world, local_rank, barrier, peak)
+        if world == 1:
+            ctx.trim()
+            line["c3"] = guarded(run_c3, args, ctx, peak)
+            ctx.trim()
+            line["c4"] = guarded(run_c4, args, ctx)
+            line["c1"] = guarded(run_c1, args)
 
     if rank == 0:
         emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def guarded(fn, *a):
+    try:
+        return fn(*a)
+    except Exception as e:   # noqa: BLE001 — the record says what failed; the headline line survives
+        import traceback
+        traceback.print_exc(file=sys.stderr)
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
+def load_golden():
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "synth_checksums.json")) as f:
+            return json.load(f)["cases"]
+    except Exception:
+        return []
+
+
+def golden_case(workload, rows, row0, thr):
+    for c in load_golden():
+        if c["workload"] == workload and c["rows"] == rows and c["row0"] == row0 and c["pred"]["literal"] == thr:
+            return c["count"], [int(x) for x in c["checksums"]]
+    return None
+
+
+def golden_check(ctx, table, rows, row0, preds, proj):
+    from rivulus_b200 import capi  # noqa: F401
+    checked = 0
+    for (thr, _), p in zip(THRESHOLDS, preds):
+        g = golden_case("configs[1]", rows, row0, thr)
+        if g is None:
+            continue
+        out = ctx.filter_project(table, p, proj)
+        got = (out.num_rows(), [out.checksum(j) for j in range(len(proj))])
+        out.release()
+        if got != (g[0], g[1]):
+            raise SystemExit(f"bench.py: GPU result at {rows} rows, T={thr} differs from the oracle's golden count/checksums: {got} vs {g}")
+        checked += 1
+    if checked == 0:
+        return f"no golden values for rows={rows} row0={row0}"
+    return f"count + 4 column checksums == oracle golden at all {rows} rows for {checked}/4 queries"
+
+
+def p_sector(s, w):
+    return 1.0 - (1.0 - s) ** (32.0 / w)
+
+
+def median(xs):
+    xs = sorted(xs)
+    return xs[len(xs) // 2]
+
+
+# ------------------------------------------------------------------------------------------ c5: BASELINE configs[4]
+C5_ROWS = 4_000_000_000
+C5_THRESHOLDS = [(899, "10%"), (499, "50%")]
+
+
+def run_c5(args, ctx, rank, world, local_rank, barrier, peak):
+    """4 B-row {k, v, f: Boolean}, contiguous row ranges over the ranks (strong scaling), filter(k > T).select([k, v, f]),
+    survivors concatenated in row order on rank 0 (record_batch.rs:245-342 across GPUs)."""
+    import torch
+    import torch.distributed as dist
+    from rivulus_b200 import capi, sharding
+
+    total_rows = args.c5_rows
+    begin, end = sharding.shard_rows(total_rows, rank, world)
+    n = end - begin
+    spec = [(capi.SYNTH_KEY1000, 0, 0), (capi.SYNTH_F64, 1, 0), (capi.SYNTH_BOOL, 2, 0)]
+    table = ctx.gen_batch(spec, n, begin)
+    dev = torch.device("cuda", local_rank)
+    rec = {"workload": "configs[4]: filter(k > T).select([k, v, f]) over {k: Int64, v: Float64, f: Boolean}, row-range sharded, ordered concat on rank 0",
+           "rows_total": total_rows, "rows_per_gpu": n, "n_gpus": world, "scaling": "strong", "queries": []}
+    ctx.profile_enable(True)
+    for thr, label in C5_THRESHOLDS:
+        pred = capi.predicate(0, ">", thr)
+        times, out = [], None
+        for r in range(args.c5_reps + 1):
+            if out is not None:
+                out.release()
+            ctx.profile_read_launches()
+            barrier()
+            out = ctx.filter_project(table, pred, [0, 1, 2])
+            t = sum(ctx.profile_read_launches())
+            if r > 0:
+                times.append(t)
+        ms = median(times)
+        t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+        cnt = torch.tensor([out.num_rows()], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        ms_max, survivors = float(t_ms.item()), int(cnt.item())
+        s_act = survivors / total_rows
+        # SURVEY 8(d): k read once (predicate AND projected), v and f by 32-byte sector, survivors written
+        b_alg = total_rows * 8 + total_rows * 8 * p_sector(s_act, 8) + total_rows / 8 * p_sector(s_act, 1 / 8) + survivors * (16 + 1 / 8)
+        q = {"threshold": thr, "label": label, "survivors": survivors, "selectivity": s_act, "device_ms": ms_max,
+             "rows_per_s": total_rows / (ms_max / 1e3), "b_alg_gb": b_alg / 1e9,
+             "alg_gbs_per_gpu": b_alg / world / 1e9 / (ms_max / 1e3), "frac": b_alg / world / 1e9 / (ms_max / 1e3) / peak}
+
+        # ---- ordered physical concatenation on rank 0, timed on its own
+        marks = {}
+
+        def timer(label_):
+            ctx.synchronize()
+            marks[label_] = time.perf_counter()
+        if world == 1:
+            ctx.synchronize()
+            t0 = time.perf_counter()
+            gathered = capi.gather_to(ctx, [out])
+            ctx.synchronize()
+            g_ms = (time.perf_counter() - t0) * 1e3
+            how = "rvl_gather_to (one part: device-local concat kernels)"
+        else:
+            gathered = sharding.gather_ordered(ctx, out, 0, dev, timer)
+            g_ms = (marks["push_end"] - marks["push_begin"]) * 1e3
+            how = "rvl_gather_dest_create/open/push/finish: CUDA IPC, every rank writes its rows into rank 0's memory over NVLink"
+        t_g = torch.tensor([g_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_g, op=dist.ReduceOp.MAX)
+        g_ms = float(t_g.item())
+        g_bytes = survivors * 16 + survivors / 8
+        q["gather"] = {"ms": g_ms, "bytes": g_bytes, "gbs": g_bytes / 1e9 / (g_ms / 1e3) if g_ms > 0 else None, "how": how,
+                       "timing": "host wall clock between stream synchronisations around the push phase, max over ranks"}
+        if rank == 0:
+            gold = golden_case("configs[4]", total_rows, 0, thr)
+            got = (gathered.num_rows(), [gathered.checksum(j) for j in range(3)])
+            if gold is None:
+                q["parity"] = f"no golden values for {total_rows} rows (count {got[0]})"
+            elif got != (gold[0], gold[1]):
+                raise SystemExit(f"bench.py: c5 gathered result at T={thr} differs from the oracle's golden count/checksums: {got} vs {gold}")
+            else:
+                q["parity"] = "gathered count + checksums of k, v, f (order-sensitive) == oracle golden at 4e9 rows"
+            gathered.release()
+        out.release()
+        barrier()
+        ctx.trim()
+        rec["queries"].append(q)
+    ctx.profile_enable(False)
+    table.release()
+    return rec
+
+
+# ------------------------------------------------------------------------------------------ c3: BASELINE configs[2]
+def run_c3(args, ctx, peak):
+    """200 M rows {x: Float64, name: String (8..40 B), v: Int64}, 10 % nulls in every column, batches of <= 50 M rows (int32 string
+    offsets), filter(x > T).select([name, v]) at 10 % / 50 % and one `<` run (nulls pass).  B_alg per SURVEY.md 8(d)."""
+    from oracle import oracle as O
+    from rivulus_b200 import capi
+    rows, batch_rows, reps = args.c3_rows, 50_000_000, args.c3_reps
+    nb = (rows + batch_rows - 1) // batch_rows
+    spec = [(capi.SYNTH_F64, 0, 10), (capi.SYNTH_STR, 1, 10), (capi.SYNTH_I64, 2, 10)]
+    batches = [ctx.gen_batch(spec, min(batch_rows, rows - i * batch_rows), i * batch_rows) for i in range(nb)]
+    in_str_bytes = sum(b.view(1).data_len for b in batches)
+    ctx.profile_enable(True)
+    out = {"workload": "configs[2]: filter(x <op> T).select([name, v]) over {x: Float64, name: String, v: Int64}, 10 % nulls each",
+           "rows": rows, "batches": nb, "queries": []}
+    for op, lit, label in ((">", 900.0, "10%"), (">", 500.0, "50%"), ("<", 100.0, "lt: 10% + nulls pass")):
+        times, surv, sbytes = [], 0, 0
+        for r in range(reps + 1):
+            ctx.profile_read_launches()
+            surv = sbytes = 0
+            for b in batches:
+                o = ctx.filter_project(b, capi.predicate(0, op, lit), [1, 2])
+                surv += o.num_rows(); sbytes += o.view(0).data_len
+                o.release()
+            t = sum(ctx.profile_read_launches())
+            if r > 0:
+                times.append(t)
+        ms = median(times)
+        s = surv / rows
+        b_alg = rows * (8 + 1 / 8)                                                        # x + validity
+        b_alg += rows * (4 * p_sector(s, 4) + (1 / 8) * p_sector(s, 1 / 8))              # name offsets + validity sectors
+        b_alg += sbytes + surv * 4 + sbytes + surv / 8                                    # survivor bytes read; offsets, bytes, validity written
+        b_alg += rows * (8 * p_sector(s, 8) + (1 / 8) * p_sector(s, 1 / 8)) + surv * (8 + 1 / 8)   # v
+        out["queries"].append({"query": f"filter(x {op} {lit}).select([name, v])", "label": label, "survivors": surv, "selectivity": s,
+                               "survivor_string_bytes": sbytes, "device_ms": ms, "rows_per_s": rows / ms * 1e3, "b_alg_gb": b_alg / 1e9,
+                               "alg_gbs": b_alg / ms / 1e6, "frac": b_alg / ms / 1e6 / peak})
+    # parity on a bounded prefix (the string / null checksum oracle is ~10 M rows/s): count, checksums, null counts, string bytes
+    vr = min(args.c3_verify_rows, batches[0].num_rows())
+    sl = batches[0].slice(0, vr)
+    o = ctx.filter_project(sl, capi.predicate(0, ">", 500.0), [1, 2])
+    cnt, sums, nulls, nbytes = O.synth_filter_checksums_nulls(vr, 0, (capi.SYNTH_F64, 0, 10), ">", 500.0, [(capi.SYNTH_STR, 1, 10), (capi.SYNTH_I64, 2, 10)])
+    got = (o.num_rows(), [o.checksum(0), o.checksum(1)], [o.view(0).null_count, o.view(1).null_count], o.view(0).data_len)
+    if got != (cnt, sums, nulls, nbytes[0]):
+        raise SystemExit(f"bench.py: c3 GPU result differs from the oracle on the first {vr} rows: {got} vs {(cnt, sums, nulls, nbytes[0])}")
+    out["parity"] = f"count, string + int checksums, null counts, string bytes == oracle on the first {vr} rows (50 %)"
+    out["input_string_bytes"] = in_str_bytes
+    o.release(); sl.release()
+    ctx.profile_enable(False)
+    for b in batches:
+        b.release()
+    return out
+
+
+# ------------------------------------------------------------------------------------------ c4: BASELINE configs[3]
+def pinned_copy_gbs(ctx, nbytes=256 << 20):
+    """The box's pinned H2D rate, measured here and now (denominator of the c4 H2D figures)."""
+    import numpy as np
+    import torch
+    from rivulus_b200 import capi
+    buf = capi.PinnedBuffer(nbytes)
+    arr = buf.view(np.int64)
+    col = capi.Column(capi.INT64, arr.size, 0, arr)
+    best = 0.0
+    for _ in range(4):
+        t0 = time.perf_counter()
+        b = ctx.upload([col])
+        dt = time.perf_counter() - t0
+        b.release()
+        best = max(best, nbytes / dt / 1e9)
+    buf.free()
+    return best
+
+
+def run_c4(args, ctx):
+    """collect_streaming() shape: a host-resident stream of {k, a, b: 8 B, flag: Boolean} batches of 64 K / 256 K / 1 M rows.
+    LIMIT 1000 runs report the batches that crossed PCIe against what a LimitStream would pull (streaming.rs:269-271); the
+    un-limited run reports the H2D rate (STAGED: every needed byte on the copy engine) and how much kernel time hid under it."""
+    import ctypes as C
+    import numpy as np
+    from rivulus_b200 import capi
+    rng = np.random.default_rng(7)
+    n_batches, reps = args.c4_batches, 3
+    slot_rows = 1 << 20
+    copy_gbs = pinned_copy_gbs(ctx)
+    out = {"workload": "configs[3]: host batches {k, a: Int64, b: Float64, flag: Boolean} -> rvl_stream_push/collect, LIMIT 1000 and un-limited",
+           "pinned_copy_gbs": copy_gbs, "slot_rows": slot_rows, "n_batches": n_batches, "runs": []}
+    for batch_rows in (65536, 262144, 1048576):
+        n = batch_rows * n_batches
+        k, kb = capi.pinned_like(rng.integers(0, 1000, n).astype(np.int64))
+        a, ab = capi.pinned_like(rng.integers(-2**62, 2**62, n).astype(np.int64))
+        b, bb = capi.pinned_like(rng.random(n) * 1000.0)
+        f, fb = capi.pinned_like(np.packbits(rng.integers(0, 2, n).astype(np.uint8), bitorder="little"))
+        dtypes = [capi.INT64, capi.INT64, capi.FLOAT64, capi.BOOLEAN]
+        out_pin = [capi.PinnedBuffer(n * 8), capi.PinnedBuffer(n * 8)]
+        structs = []
+        for i in range(n_batches):
+            o = i * batch_rows
+            cs = [capi.Column(capi.INT64, batch_rows, o, k), capi.Column(capi.INT64, batch_rows, o, a),
+                  capi.Column(capi.FLOAT64, batch_rows, o, b), capi.Column(capi.BOOLEAN, batch_rows, o, f)]
+            structs.append(((capi.RvlColumn * 4)(*[c.as_struct() for c in cs]), cs))
+        queries = [("filter(flag).select([k,a]).limit(1000)", capi.mask_predicate(3), [0, 1], 1000, capi.TRANSFER_AUTO),
+                   ("filter(k > 998).select([a,b]).limit(1000)", capi.predicate(0, ">", 998), [1, 2], 1000, capi.TRANSFER_AUTO),
+                   ("filter(k > 899).select([a,b]).limit(1000)", capi.predicate(0, ">", 899), [1, 2], 1000, capi.TRANSFER_AUTO),
+                   ("filter(k > 899).select([a,b])  (no limit, STAGED)", capi.predicate(0, ">", 899), [1, 2], -1, capi.TRANSFER_STAGED),
+                   ("filter(k > 899).select([a,b])  (no limit, AUTO)", capi.predicate(0, ">", 899), [1, 2], -1, capi.TRANSFER_AUTO)]
+        for label, pred, proj, limit, transfer in queries:
+            walls, stats, rows_out, launches, kern_ms = [], None, 0, 0, 0.0
+            for r in range(reps + 1):
+                st = ctx.open_stream(dtypes, pred, proj, limit, slot_rows, 3, transfer)
+                ctx.synchronize()
+                ctx.profile_enable(True)
+                t0 = time.perf_counter()
+                for arr, _keep in structs:
+                    if not st.push_structs(arr, 4):
+                        break
+                res = st.collect()
+                rows_out = res.num_rows()
+                for j in range(len(proj)):                                 # D2H of the result (pinned destination) inside the timed region
+                    dt = np.int64 if res.view(j).dtype == capi.INT64 else np.float64
+                    sct = capi.Column(capi.INT64 if dt == np.int64 else capi.FLOAT64, rows_out, 0, out_pin[j].view(dt, max(rows_out, 1))).as_struct()
+                    capi.check(capi.lib().rvl_batch_download_column(ctx._h, res._h, j, C.byref(sct)))
+                ctx.synchronize()
+                t1 = time.perf_counter()
+                kern_ms = sum(ctx.profile_read_launches())
+                ctx.profile_enable(False)
+                stats, launches = st.stats(), st.launches()
+                st.close(); res.release()
+                if r > 0:
+                    walls.append((t1 - t0) * 1e3)
+            ms = median(walls)
+            rec = {"batch_rows": batch_rows, "query": label, "rows_out": rows_out, "wall_ms": ms, "batches_transferred": stats["batches_pushed"],
+                   "operator_launches": launches, "h2d_copy_engine_bytes": stats["h2d_bytes"]}
+            kk = np.asarray(k)
+            keep = np.unpackbits(np.asarray(f), bitorder="little")[:n].astype(bool) if pred.mode == capi.PRED_BOOL_COLUMN else kk > pred.lit_i64
+            if limit >= 0:
+                # batches a perfect LimitStream pulls: until the running survivor count reaches the limit
+                idx = int(np.searchsorted(np.cumsum(keep), limit))
+                rec["batches_ideal"] = min(n_batches, idx // batch_rows + 1)
+                if rows_out != min(limit, int(keep.sum())):
+                    raise SystemExit(f"bench.py: c4 {label}: {rows_out} rows out")
+            else:
+                if rows_out != int(keep.sum()):
+                    raise SystemExit(f"bench.py: c4 {label}: {rows_out} rows out, expected {int(keep.sum())}")
+                needed = n * 24   # k, a, b (flag is neither predicate nor projected: it never crosses)
+                rec["input_gbs"] = needed / ms / 1e6
+                if transfer == capi.TRANSFER_STAGED:
+                    copy_ms = stats["h2d_bytes"] / copy_gbs / 1e6
+                    rec["h2d_gbs"] = stats["h2d_bytes"] / ms / 1e6
+                    rec["h2d_frac_of_pinned_copy"] = rec["h2d_gbs"] / copy_gbs
+                    rec["kernel_ms"] = kern_ms
+                    # kernel time hidden under the transfers / total kernel time (1 = perfectly overlapped, 0 = serialised)
+                    rec["overlap_ratio"] = max(0.0, min(1.0, (kern_ms + copy_ms - ms) / kern_ms)) if kern_ms > 0 else None
+            out["runs"].append(rec)
+        del structs
+        for x in (kb, ab, bb, fb, *out_pin):
+            x.free()
+    return out
+
+
+# ------------------------------------------------------------------------------------------ c1: BASELINE configs[0]
+def run_c1(args):
+    """1 M-row {name: String, age: Int64}: LazyFrame.from_dataframe(df).filter(age > 25).select([name]).collect() through the host
+    layer (logical_plan/builder.rs:96-104 -> physical_plan/plan.rs:97-150 shapes), wall clock including the DataFrame clone, the
+    upload, the kernels and the download into a host DataFrame; the oracle's eager engine runs the same call on 1 core."""
+    import numpy as np
+    from oracle import oracle as O
+    from rivulus_b200 import capi
+    from rivulus_b200 import frame as F
+    n = 1_000_000
+    spec = [("name", capi.SYNTH_STR, 0, 0), ("age", capi.SYNTH_AGE100, 1, 0)]
+
+    def q(mod, df):
+        return mod.LazyFrame.from_dataframe(df).filter(mod.col("age").gt(mod.lit(25))).select([mod.col("name")]).collect()
+    gdf, cdf = F.DataFrame.synth(spec, n), O.DataFrame.synth(spec, n)
+    gt, got = [], None
+    for r in range(6):
+        t0 = time.perf_counter()
+        got = q(F, gdf)
+        if r > 0:
+            gt.append(time.perf_counter() - t0)
+    ct, want = [], None
+    for r in range(3):
+        t0 = time.perf_counter()
+        want = q(O, cdf)
+        ct.append(time.perf_counter() - t0)
+    g, w = got.column_raw(0), want.column_raw(0)
+    if (got.height(), got.column_names(), got.dtypes()) != (want.height(), want.column_names(), want.dtypes()) or \
+            not all(np.array_equal(x, y) for x, y in zip(g, w)):
+        raise SystemExit("bench.py: c1 GPU collect() differs from the oracle's")
+    gs, cs = median(gt), median(ct)
+    return {"workload": "configs[0]: 1 M rows {name: String, age: Int64}; from_dataframe(df).filter(age > 25).select([name]).collect()",
+            "rows": n, "survivors": got.height(), "gpu_wall_ms": gs * 1e3, "gpu_rows_per_s": n / gs,
+            "cpu_wall_ms": cs * 1e3, "cpu_rows_per_s": n / cs, "cpu_cores": 1, "cpu_kind": "port (oracle eager engine)",
+            "speedup": cs / gs, "parity": "tags, offsets and bytes of the result column == oracle collect()",
+            "timing": "host wall clock around the whole collect() call: DataFrame clone, H2D, kernels, D2H into a host DataFrame"}
 
 
 def host_mem_available_bytes():
@@ -345,8 +715,12 @@ def run_e2e(args, ctx, table, preds, proj, rank, world, local_rank, barrier):
     import ctypes as C
 
     rows = args.rows
-    budget = host_mem_available_bytes() * 0.30 / max(world, 1)
-    e2e_rows = args.e2e_rows if args.e2e_rows > 0 else int(min(rows, budget // (BYTES_PER_ROW_IN + 32 * 0.9)))
+    # the same host-resident table size per GPU at every N (so the 1 -> 8 curve compares like with like); only a host that cannot
+    # pin world x that much shrinks it, and the record says so
+    budget = host_mem_available_bytes() * 0.60 / max(world, 1)
+    want = min(rows, args.e2e_rows)
+    e2e_rows = int(min(want, budget // (BYTES_PER_ROW_IN + 1)))
+    rows_reduced = e2e_rows < want
     e2e_rows = max(e2e_rows // 64 * 64, 64)
     batch_rows = min(args.e2e_batch_rows, e2e_rows)
     sub = table.slice(0, e2e_rows)
@@ -435,7 +809,7 @@ def run_e2e(args, ctx, table, preds, proj, rank, world, local_rank, barrier):
         b.free()
     in_place = staged // steps < h2d
     return {"value": value, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h // steps, "steps": steps,
-            "rows_per_gpu": e2e_rows, "batch_rows": batch_rows, "ms_per_step": wall * 1000.0 / steps,
+            "rows_per_gpu": e2e_rows, "rows_reduced_by_host_ram": rows_reduced, "batch_rows": batch_rows, "ms_per_step": wall * 1000.0 / steps,
             "h2d_gbs": h2d * steps / wall / 1e9, "survivors": totals, "transfer": args.e2e_transfer, "per_query_ms_last_step": [round(x, 2) for x in per_query],
             "h2d_copy_engine_bytes_per_step": staged // steps,
             "h2d_note": ("h2d_bytes_per_step = the host-resident input of the step (every column of every query); the predicate column "
@@ -476,7 +850,15 @@ def main():
     ap.add_argument("--rows", type=int, default=1_000_000_000, help="rows per GPU (BASELINE configs[1]: 1e9)")
     ap.add_argument("--cpu-rows", type=int, default=None, help="rows of the bounded CPU sample (per shard)")
     ap.add_argument("--verify-rows", type=int, default=16_000_000)
-    ap.add_argument("--e2e-rows", type=int, default=0, help="rows of the host-resident table (default: as many of --rows as fit in 30%% of host RAM)")
+    ap.add_argument("--e2e-rows", type=int, default=512_000_000, help="rows per GPU of the host-resident table of the e2e leg (the same at every N)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the c1/c3/c4/c5 sub-records")
+    ap.add_argument("--no-golden", action="store_true", help="skip the full-size golden checksum comparison")
+    ap.add_argument("--c5-rows", type=int, default=C5_ROWS)
+    ap.add_argument("--c5-reps", type=int, default=3)
+    ap.add_argument("--c3-rows", type=int, default=200_000_000)
+    ap.add_argument("--c3-reps", type=int, default=3)
+    ap.add_argument("--c3-verify-rows", type=int, default=4_000_000)
+    ap.add_argument("--c4-batches", type=int, default=64)
     ap.add_argument("--e2e-batch-rows", type=int, default=16 << 20)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")

@@ -108,6 +108,9 @@ int32_t rvl_device_count(int32_t* count);
 int32_t rvl_ctx_create(int32_t device, rvl_ctx** ctx);
 int32_t rvl_ctx_destroy(rvl_ctx* ctx);
 int32_t rvl_ctx_synchronize(rvl_ctx* ctx);
+/* Return the cached (freed, kept for reuse) blocks of the context's device memory pool to the driver.  The pool keeps everything it
+ * has ever held so steady-state queries never call cudaMalloc; call this between workloads of very different footprints. */
+int32_t rvl_ctx_trim(rvl_ctx* ctx);
 /* the cudaStream_t every kernel of this context is launched on (so callers can time with CUDA events on it) */
 int32_t rvl_ctx_cuda_stream(rvl_ctx* ctx, void** cuda_stream);
 int32_t rvl_ctx_device(rvl_ctx* ctx, int32_t* device);
@@ -136,7 +139,10 @@ typedef enum rvl_option {
     RVL_OPT_DENSE_CTAS_PER_SM = 4,  /* 1 or 2 */
     RVL_OPT_SCAN_SLOTS = 5,         /* two-pass: ring slots per warp of the predicate scan (1..3) */
     RVL_OPT_SCAN_WARPS = 6,         /* two-pass: warps per CTA of the predicate scan (8 or 16) */
-    RVL_OPT_DENSE_WARPS = 7         /* two-pass: consumer warps per CTA of the dense kernel (8 or 16; 16 implies one CTA per SM) */
+    RVL_OPT_DENSE_WARPS = 7,        /* two-pass: consumer warps per CTA of the dense kernel (8 or 16; 16 implies one CTA per SM) */
+    RVL_OPT_BITS_OVERLAP = 8,       /* two-pass: run the bit-packed compaction kernel on a forked stream under the 8-byte kernels (default 1) */
+    RVL_OPT_EXACT_ALLOC = 9         /* blocking rvl_filter_project, two-pass plan: read the survivor count (and string bytes) back after the
+                                       predicate scan and allocate the outputs at their exact size instead of min(n, limit) rows (default 1) */
 } rvl_option;
 int32_t rvl_ctx_set_option(rvl_ctx* ctx, int32_t option, int64_t value);
 
@@ -211,7 +217,10 @@ int32_t rvl_filter_project_finish(rvl_ctx* ctx, rvl_pending* pending, rvl_batch*
  * rvl_stream_next / rvl_stream_collect. */
 typedef enum rvl_transfer { RVL_TRANSFER_AUTO = 0, RVL_TRANSFER_STAGED = 1, RVL_TRANSFER_ZERO_COPY = 2 } rvl_transfer;
 typedef struct rvl_stream_config {
-    int64_t batch_rows; /* capacity of one staging slot, rows */
+    int64_t batch_rows; /* capacity of one staging slot, rows.  Pushed batches smaller than this are appended to the open slot and one
+                           operator launch covers the whole group (a group needs 64-row-aligned joins, no String column, and — for
+                           columns read in place — adjacent caller buffers; otherwise every batch is its own group).  LIMIT streams
+                           grow their groups 1, 1, 2, 4, ... batches.  Set it to the batch size for one launch per pushed batch. */
     int32_t n_staging;  /* pinned/device staging slots (>= 2 for H2D / compute overlap) */
     int32_t transfer;   /* rvl_transfer */
 } rvl_stream_config;
@@ -222,14 +231,24 @@ int32_t rvl_stream_open(rvl_ctx* ctx, const int32_t* dtypes, int32_t ncols, cons
                         rvl_stream** stream);
 /* Feed one HOST batch (MemoryStream::next_batch upstream, stream.rs:105-113).  Asynchronous: H2D on the copy
  * stream of a free staging slot, fused kernel on the compute stream.  *accepted = 0 when the LIMIT has already
- * been reached and the batch was not transferred (LimitStream's early termination, streaming.rs:269-271). */
+ * been reached and the batch was not transferred (LimitStream's early termination, streaming.rs:269-271).
+ * Buffer lifetime: PAGEABLE sources are copied into the slot's pinned staging memory before push() returns and may be reused at
+ * once.  PAGE-LOCKED sources (rvl_host_alloc / cudaHostAlloc / cudaHostRegister) are read asynchronously — by the copy engine, or
+ * in place by the kernels (ZERO_COPY / AUTO) — and must stay valid and unchanged until the output covering the batch has been
+ * returned by rvl_stream_next / rvl_stream_collect, or the stream is closed.
+ * Any number of batches may be pushed before the first rvl_stream_next: beyond 32 outstanding launches push() finishes the oldest
+ * ones itself and folds their outputs, 16 at a time, into exact-size batches that rvl_stream_next later hands out in order. */
 int32_t rvl_stream_push(rvl_stream* stream, const rvl_column* host_cols, int32_t ncols, int32_t* accepted);
-/* next_batch() -> Option<RecordBatch>: *has_batch = 0 when no finished output batch is pending. */
+/* launch the operator over the batches appended to the open slot so far (next / collect do this implicitly) */
+int32_t rvl_stream_flush(rvl_stream* stream);
+/* next_batch() -> Option<RecordBatch>: *has_batch = 0 when no output is pending.  One output covers one group of pushed batches. */
 int32_t rvl_stream_next(rvl_stream* stream, rvl_batch** out, int32_t* has_batch);
 int32_t rvl_stream_limit_reached(rvl_stream* stream, int32_t* reached);
 /* DataStream::concatenate / collect_stream_batches (stream.rs:41-53, streaming.rs:343-352) */
 int32_t rvl_stream_collect(rvl_stream* stream, rvl_batch** out);
 int32_t rvl_stream_stats(rvl_stream* stream, int64_t* batches_pushed, int64_t* batches_skipped, int64_t* h2d_bytes);
+/* operator launches issued so far (= groups of pushed batches) */
+int32_t rvl_stream_launches(rvl_stream* stream, int64_t* groups);
 int32_t rvl_stream_close(rvl_stream* stream);
 
 /* ---- multi-GPU: contiguous row ranges, no collective ---------------------- */
@@ -241,6 +260,29 @@ int32_t rvl_shard_limit_split(const int64_t* counts, int32_t world, int64_t limi
  * concat kernels read the peers' buffers in place over NVLink (peer mappings are set up on first use); the order-preserving
  * concatenation of record_batch.rs:245-342 across devices.  Blocks until the result is complete. */
 int32_t rvl_gather_to(rvl_ctx* dst, const rvl_batch* const* parts, int32_t n, rvl_batch** out);
+/* The same ordered concatenation when every GPU is driven by its OWN process (torchrun, one rank per GPU).  The destination rank
+ * creates the result (cudaMalloc-backed, zero-filled) and gets one CUDA IPC handle set per column; the handle array is plain bytes —
+ * ship it to the other ranks by any means (torch.distributed broadcast in bench.py).  Every rank, the destination included, then
+ * writes its part at its row offset (exclusive scan of the per-shard survivor counts; for String columns also its byte offset per
+ * column) with rvl_gather_push — peer writes over NVLink, all ranks concurrently, bitmaps at any bit offset.  After a barrier the
+ * destination calls rvl_gather_dest_finish (null counts; bitmaps kept only if something is null, primitive.rs:180-185).
+ * Non-destination ranks open the handles with rvl_gather_dest_open and release the view with rvl_batch_release. */
+#define RVL_IPC_HANDLE_BYTES 64
+typedef struct rvl_gather_handle {
+    int32_t dtype;
+    int32_t has_validity;
+    int64_t rows;
+    int64_t data_bytes;
+    uint8_t values[RVL_IPC_HANDLE_BYTES];
+    uint8_t validity[RVL_IPC_HANDLE_BYTES];
+    uint8_t offsets[RVL_IPC_HANDLE_BYTES];
+    uint8_t data[RVL_IPC_HANDLE_BYTES];
+} rvl_gather_handle;
+int32_t rvl_gather_dest_create(rvl_ctx* ctx, const int32_t* dtypes, const int32_t* has_validity, const int64_t* data_bytes /* per column,
+                               String only, may be NULL */, int32_t ncols, int64_t total_rows, rvl_batch** dest, rvl_gather_handle* handles);
+int32_t rvl_gather_dest_open(rvl_ctx* ctx, const rvl_gather_handle* handles, int32_t ncols, rvl_batch** dest_view);
+int32_t rvl_gather_push(rvl_ctx* ctx, const rvl_batch* part, rvl_batch* dest, int64_t row_offset, const int64_t* byte_offsets /* per column */);
+int32_t rvl_gather_dest_finish(rvl_ctx* ctx, rvl_batch* dest);
 /* one fused call per context (each on its own GPU/stream), all in flight together; outs[g] are in row order */
 int32_t rvl_filter_project_sharded(rvl_ctx* const* ctxs, int32_t n, const rvl_batch* const* shards,
                                    const rvl_predicate* pred, const int32_t* proj, int32_t nproj, int64_t limit,

@@ -50,9 +50,19 @@ class RvlStreamConfig(C.Structure):
 
 TRANSFER_AUTO, TRANSFER_STAGED, TRANSFER_ZERO_COPY = 0, 1, 2
 
+IPC_HANDLE_BYTES = 64
+
+
+class RvlGatherHandle(C.Structure):
+    """rvl_gather_handle: the CUDA IPC handles of one destination column (plain bytes, shipped between ranks as they are)."""
+    _fields_ = [("dtype", C.c_int32), ("has_validity", C.c_int32), ("rows", C.c_int64), ("data_bytes", C.c_int64),
+                ("values", C.c_uint8 * IPC_HANDLE_BYTES), ("validity", C.c_uint8 * IPC_HANDLE_BYTES),
+                ("offsets", C.c_uint8 * IPC_HANDLE_BYTES), ("data", C.c_uint8 * IPC_HANDLE_BYTES)]
+
 
 PLAN_AUTO, PLAN_FUSED, PLAN_TWO_PASS = 0, 1, 2
-OPT_PLAN, OPT_TWO_PASS_MIN_ROWS, OPT_SPARSE_MAX, OPT_DENSE_SLOTS, OPT_DENSE_CTAS_PER_SM, OPT_SCAN_SLOTS, OPT_SCAN_WARPS, OPT_DENSE_WARPS = 0, 1, 2, 3, 4, 5, 6, 7
+OPT_PLAN, OPT_TWO_PASS_MIN_ROWS, OPT_SPARSE_MAX, OPT_DENSE_SLOTS, OPT_DENSE_CTAS_PER_SM, OPT_SCAN_SLOTS, OPT_SCAN_WARPS, OPT_DENSE_WARPS, \
+    OPT_BITS_OVERLAP, OPT_EXACT_ALLOC = range(10)
 
 
 class RivulusError(RuntimeError):
@@ -65,15 +75,16 @@ class RivulusError(RuntimeError):
 # every symbol include/rivulus_gpu.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
     "rvl_abi_version", "rvl_last_error", "rvl_device_count",
-    "rvl_ctx_create", "rvl_ctx_destroy", "rvl_ctx_synchronize", "rvl_ctx_cuda_stream", "rvl_ctx_device", "rvl_ctx_launch_count",
+    "rvl_ctx_create", "rvl_ctx_destroy", "rvl_ctx_synchronize", "rvl_ctx_trim", "rvl_ctx_cuda_stream", "rvl_ctx_device", "rvl_ctx_launch_count",
     "rvl_ctx_profile_enable", "rvl_ctx_profile_read", "rvl_ctx_profile_read_launches", "rvl_ctx_set_option",
     "rvl_host_alloc", "rvl_host_free",
     "rvl_batch_upload", "rvl_batch_wrap_device", "rvl_batch_release", "rvl_batch_num_rows", "rvl_batch_num_columns",
     "rvl_batch_column", "rvl_batch_download_column", "rvl_batch_count_true", "rvl_boolean_op", "rvl_batch_slice", "rvl_batch_select", "rvl_batch_take", "rvl_batch_concat",
     "rvl_filter_project", "rvl_predicate_mask", "rvl_filter_project_launch", "rvl_filter_project_finish",
-    "rvl_stream_open", "rvl_stream_push", "rvl_stream_next", "rvl_stream_limit_reached", "rvl_stream_collect",
-    "rvl_stream_stats", "rvl_stream_close",
+    "rvl_stream_open", "rvl_stream_push", "rvl_stream_flush", "rvl_stream_next", "rvl_stream_limit_reached", "rvl_stream_collect",
+    "rvl_stream_stats", "rvl_stream_launches", "rvl_stream_close",
     "rvl_shard_range", "rvl_shard_limit_split", "rvl_filter_project_sharded", "rvl_gather_to",
+    "rvl_gather_dest_create", "rvl_gather_dest_open", "rvl_gather_push", "rvl_gather_dest_finish",
     "rvl_gen_batch", "rvl_batch_checksum",
 ]
 
@@ -224,6 +235,10 @@ class Context:
 
     def synchronize(self):
         check(lib().rvl_ctx_synchronize(self._h))
+
+    def trim(self):
+        """rvl_ctx_trim: give the pool's cached blocks back to the driver (between workloads of different footprints)."""
+        check(lib().rvl_ctx_trim(self._h))
 
     def cuda_stream(self) -> int:
         s = C.c_void_p()
@@ -424,22 +439,39 @@ class Stream:
         cfg = RvlStreamConfig(batch_rows, n_staging, transfer)
         check(lib().rvl_stream_open(ctx._h, d, len(dtypes), C.byref(pred) if pred is not None else None, p, len(proj),
                                     C.c_int64(limit), C.byref(cfg), C.byref(self._h)))
+        # page-locked sources are read asynchronously (copy engine, or in place by the kernels): the pushed columns are kept
+        # alive here until the stream has handed out everything in flight (include/rivulus_gpu.h: rvl_stream_push)
+        self._held = []
+        self._pred = pred
 
     def push(self, cols: Sequence[Column]) -> bool:
         arr = (RvlColumn * max(len(cols), 1))(*[c.as_struct() for c in cols])
         acc = C.c_int32()
         check(lib().rvl_stream_push(self._h, arr, len(cols), C.byref(acc)))
+        if acc.value:
+            self._held.append((arr, list(cols)))
         return bool(acc.value)
 
     def push_structs(self, arr, n) -> bool:
+        """Push a prebuilt rvl_column array; the caller keeps the buffers it points into alive."""
         acc = C.c_int32()
         check(lib().rvl_stream_push(self._h, arr, n, C.byref(acc)))
         return bool(acc.value)
+
+    def flush(self):
+        check(lib().rvl_stream_flush(self._h))
+
+    def launches(self) -> int:
+        n = C.c_int64()
+        check(lib().rvl_stream_launches(self._h, C.byref(n)))
+        return n.value
 
     def next_batch(self) -> Optional[Batch]:
         out = C.c_void_p()
         has = C.c_int32()
         check(lib().rvl_stream_next(self._h, C.byref(out), C.byref(has)))
+        if not has.value:
+            self._held.clear()   # nothing is in flight any more
         return Batch(self.ctx, out) if has.value else None
 
     def limit_reached(self) -> bool:
@@ -450,6 +482,7 @@ class Stream:
     def collect(self) -> Batch:
         out = C.c_void_p()
         check(lib().rvl_stream_collect(self._h, C.byref(out)))
+        self._held.clear()
         return Batch(self.ctx, out)
 
     def stats(self):
@@ -461,6 +494,7 @@ class Stream:
         if self._h:
             lib().rvl_stream_close(self._h)
             self._h = C.c_void_p()
+        self._held = []
 
     def __del__(self):
         try:
@@ -533,6 +567,39 @@ def filter_project_sharded(ctxs: Sequence[Context], shards: Sequence[Batch], pre
     check(lib().rvl_filter_project_sharded(ca, n, sa, C.byref(pred) if pred is not None else None, p, len(proj), C.c_int64(limit),
                                            outs, counts))
     return [Batch(ctxs[g], C.c_void_p(outs[g])) for g in range(n)], list(counts)
+
+
+def gather_dest_create(ctx: Context, dtypes: Sequence[int], has_validity: Sequence[bool], total_rows: int, data_bytes: Optional[Sequence[int]] = None):
+    """rvl_gather_dest_create: (destination batch, handle bytes to ship to the other ranks)."""
+    n = len(dtypes)
+    d = (C.c_int32 * max(n, 1))(*dtypes)
+    v = (C.c_int32 * max(n, 1))(*[int(bool(x)) for x in has_validity])
+    nb = (C.c_int64 * max(n, 1))(*([int(x) for x in data_bytes] if data_bytes is not None else [0] * n))
+    handles = (RvlGatherHandle * max(n, 1))()
+    out = C.c_void_p()
+    check(lib().rvl_gather_dest_create(ctx._h, d, v, nb, n, C.c_int64(total_rows), C.byref(out), handles))
+    return Batch(ctx, out), bytes(handles)[:C.sizeof(RvlGatherHandle) * n]
+
+
+def gather_dest_open(ctx: Context, handle_bytes: bytes) -> Batch:
+    """rvl_gather_dest_open: map another rank's destination buffers (peer access over NVLink)."""
+    n = len(handle_bytes) // C.sizeof(RvlGatherHandle)
+    handles = (RvlGatherHandle * max(n, 1)).from_buffer_copy(handle_bytes.ljust(C.sizeof(RvlGatherHandle) * max(n, 1), b"\0"))
+    out = C.c_void_p()
+    check(lib().rvl_gather_dest_open(ctx._h, handles, n, C.byref(out)))
+    return Batch(ctx, out)
+
+
+def gather_push(ctx: Context, part: Batch, dest: Batch, row_offset: int, byte_offsets: Optional[Sequence[int]] = None):
+    """rvl_gather_push: write `part` into rows [row_offset, row_offset + part.num_rows()) of the destination."""
+    bo = None
+    if byte_offsets is not None:
+        bo = (C.c_int64 * max(len(byte_offsets), 1))(*[int(x) for x in byte_offsets])
+    check(lib().rvl_gather_push(ctx._h, part._h, dest._h, C.c_int64(row_offset), bo))
+
+
+def gather_dest_finish(ctx: Context, dest: Batch):
+    check(lib().rvl_gather_dest_finish(ctx._h, dest._h))
 
 
 def gather_to(dst: Context, parts: Sequence[Batch]) -> Batch:

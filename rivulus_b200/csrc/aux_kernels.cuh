@@ -58,7 +58,10 @@ static __global__ void gen_strbytes_kernel(uint8_t* __restrict__ data, const int
 
 // single-block exclusive scan of int32 lengths into offsets[0..n] (offsets[0] = 0); n up to a few 10^8
 // is handled by the chunk loop.  Only used by the generator (test/bench input), not by the hot path.
-static __global__ void __launch_bounds__(1024) scan_lengths_kernel(const int32_t* __restrict__ lens, int32_t* __restrict__ offsets, int64_t n) {
+// *overflow (optional, zeroed by the caller) is set when a prefix exceeds INT32_MAX — the reference's `as i32` wraps silently there
+// (string.rs:31); callers turn it into RVL_OFFSET_OVERFLOW.
+static __global__ void __launch_bounds__(1024) scan_lengths_kernel(const int32_t* __restrict__ lens, int32_t* __restrict__ offsets, int64_t n,
+                                                                   int32_t* __restrict__ overflow = nullptr) {
     __shared__ long long s_warp[32];
     __shared__ long long s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -78,7 +81,10 @@ static __global__ void __launch_bounds__(1024) scan_lengths_kernel(const int32_t
         long long woff = 0;
         for (int w = 0; w < warp; ++w) woff += s_warp[w];
         const long long carry = s_carry;
-        if (i < n) offsets[i + 1] = (int32_t)(carry + woff + incl);
+        if (i < n) {
+            offsets[i + 1] = (int32_t)(carry + woff + incl);
+            if (overflow != nullptr && carry + woff + incl > 2147483647ll) *overflow = 1;
+        }
         __syncthreads();
         if (tid == 1023) s_carry = carry + woff + incl;
         __syncthreads();

@@ -23,14 +23,28 @@ struct FpPending {
     cudaEvent_t done_event = nullptr;   // recorded after the mailbox copy
     uint64_t base_rows = 0;             // filled at finish for chained (streaming) launches
     bool chained = false;               // base_in was used: mailbox[n_counters] carries the base
+    cudaStream_t side_stream = nullptr; // borrowed: bit-packed compaction runs here, joined before the mailbox copy
+    // the slot and the event go back to the context's pools; a slot is never recycled while a copy into it may be in flight
+    bool completed = false;             // fp_finish has waited for the launch
+    ~FpPending() {
+        if (!core) return;
+        if (done_event) { cudaEventSynchronize(done_event); core->give_event(done_event); }
+        else if (mailbox && !completed) { cudaSetDevice(core->device); cudaStreamSynchronize(core->stream); }
+        core->give_slot(mailbox);
+    }
 };
 
 constexpr uint64_t kMailboxPending = ~0ull;
 
 // base_in:   device word holding the rows already emitted by earlier launches of the same query (or nullptr)
 // total_ext: device word that receives base + survivors after this launch (or nullptr); must differ from base_in
+// exact:     (blocking callers only) with the two-pass plan, wait for the predicate scan's survivor count (and the string
+//            sizes pass) and allocate the outputs at their exact size instead of the worst case `min(n, limit)` rows
 int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pred, const int32_t* proj, int32_t nproj,
-              int64_t limit, bool want_mask, const unsigned long long* base_in, unsigned long long* total_ext, FpPending** out);
+              int64_t limit, bool want_mask, const unsigned long long* base_in, unsigned long long* total_ext, FpPending** out,
+              bool exact = false);
+// one-time per device: opt every kernel instantiation in to its dynamic shared memory size (called by rvl_ctx_create)
+int fp_init_device(int device);
 // waits for the launch, builds the output batch (and/or the mask batch); deletes `pend`
 int fp_finish(FpPending* pend, rvl_batch** out, rvl_batch** mask_out);
 // device word holding base + survivors after this launch (valid until the pending object is finished)

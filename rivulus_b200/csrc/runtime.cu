@@ -9,6 +9,7 @@
 #include <cstring>
 
 #include "aux_kernels.cuh"
+#include "filter_project.cuh"
 #include "string_kernels.cuh"
 
 namespace rvl {
@@ -24,13 +25,33 @@ CtxCore::~CtxCore() {
     if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
     if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
     if (d2h_stream) { cudaStreamSynchronize(d2h_stream); cudaStreamDestroy(d2h_stream); }
+    if (side_stream) { cudaStreamSynchronize(side_stream); cudaStreamDestroy(side_stream); }
     for (auto& e : prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (cudaEvent_t e : event_pool) cudaEventDestroy(e);
     if (mailbox) cudaFreeHost(mailbox);
+    for (uint64_t* c : slot_chunks) cudaFreeHost(c);
+}
+
+uint64_t* CtxCore::take_slot() {
+    std::lock_guard<std::mutex> g(mu);
+    if (slot_free.empty()) {
+        uint64_t* chunk = nullptr;
+        if (cudaHostAlloc((void**)&chunk, kSlotsPerChunk * kSlotWords * sizeof(uint64_t), cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        slot_chunks.push_back(chunk);
+        for (size_t i = kSlotsPerChunk; i-- > 0;) slot_free.push_back(chunk + i * kSlotWords);
+    }
+    uint64_t* s = slot_free.back();
+    slot_free.pop_back();
+    return s;
 }
 
 int CtxCore::prof_flush() {
-    for (auto& e : prof_events) {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evs;
+    { std::lock_guard<std::mutex> g(mu); evs.swap(prof_events); }
+    for (auto& e : evs) {
         RVL_CUDA_TRY(cudaEventSynchronize(e.second));
         float ms = 0.f;
         RVL_CUDA_TRY(cudaEventElapsedTime(&ms, e.first, e.second));
@@ -39,14 +60,17 @@ int CtxCore::prof_flush() {
         prof_times.push_back((double)ms);
         cudaEventDestroy(e.first); cudaEventDestroy(e.second);
     }
-    prof_events.clear();
     return RVL_OK;
 }
 
 DevBuffer::~DevBuffer() {
     if (owned && ptr != nullptr && core) {
         cudaSetDevice(core->device);
-        cudaFreeAsync(ptr, core->stream);
+        if (kind == 0) cudaFreeAsync(ptr, core->stream);
+        else {
+            cudaStreamSynchronize(core->stream);
+            if (kind == 1) cudaFree(ptr); else cudaIpcCloseMemHandle(ptr);
+        }
     }
 }
 
@@ -135,7 +159,9 @@ int32_t rvl_ctx_create(int32_t device, rvl_ctx** ctx) {
     RVL_CUDA_TRY(cudaStreamCreateWithFlags(&core->stream, cudaStreamNonBlocking));
     RVL_CUDA_TRY(cudaStreamCreateWithFlags(&core->copy_stream, cudaStreamNonBlocking));
     RVL_CUDA_TRY(cudaStreamCreateWithFlags(&core->d2h_stream, cudaStreamNonBlocking));
-    core->mailbox_words = 4096;
+    RVL_CUDA_TRY(cudaStreamCreateWithFlags(&core->side_stream, cudaStreamNonBlocking));
+    RVL_TRY(fp_init_device(device));
+    core->mailbox_words = CtxCore::kSlotBase;
     RVL_CUDA_TRY(cudaHostAlloc((void**)&core->mailbox, core->mailbox_words * sizeof(uint64_t), cudaHostAllocDefault));
     // keep freed blocks cached in the pool: outputs are sized for the worst case and recycled call to call
     cudaMemPool_t pool;
@@ -161,6 +187,16 @@ int32_t rvl_ctx_synchronize(rvl_ctx* ctx) {
     RVL_CUDA_TRY(cudaSetDevice(ctx->core->device));
     RVL_CUDA_TRY(cudaStreamSynchronize(ctx->core->copy_stream));
     RVL_CUDA_TRY(cudaStreamSynchronize(ctx->core->stream));
+    return RVL_OK;
+}
+
+int32_t rvl_ctx_trim(rvl_ctx* ctx) {
+    if (!ctx) return fail(RVL_INVALID_ARGUMENT, "null context");
+    RVL_CUDA_TRY(cudaSetDevice(ctx->core->device));
+    RVL_CUDA_TRY(cudaStreamSynchronize(ctx->core->stream));
+    cudaMemPool_t pool;
+    RVL_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, ctx->core->device));
+    RVL_CUDA_TRY(cudaMemPoolTrimTo(pool, 0));
     return RVL_OK;
 }
 
@@ -194,6 +230,8 @@ int32_t rvl_ctx_set_option(rvl_ctx* ctx, int32_t option, int64_t value) {
         case RVL_OPT_DENSE_WARPS:
             if (value != 8 && value != 16) return fail(RVL_INVALID_ARGUMENT, "dense_warps must be 8 or 16");
             c.dense_warps = (int)value; return RVL_OK;
+        case RVL_OPT_BITS_OVERLAP: c.bits_overlap = value != 0; return RVL_OK;
+        case RVL_OPT_EXACT_ALLOC: c.exact_alloc = value != 0; return RVL_OK;
         default: return fail(RVL_INVALID_ARGUMENT, "unknown option");
     }
 }
@@ -282,6 +320,7 @@ int32_t rvl_batch_upload(rvl_ctx* ctx, const rvl_column* cols, int32_t ncols, rv
             RVL_TRY(dev_alloc(core, (size_t)c.data_len, &d.data));
             if (c.data_len > 0) RVL_CUDA_TRY(cudaMemcpyAsync(d.data->ptr, c.data, (size_t)c.data_len, kind, core->stream));
             d.data_len = c.data_len;
+            if (c.location != RVL_DEVICE) d.window_bytes = (int64_t)c.offsets[c.offset + n] - (int64_t)c.offsets[c.offset];
         }
         if (c.validity != nullptr && c.dtype != RVL_NULL) {
             RVL_TRY(dev_alloc_zeroed(core, (size_t)(span + 7) / 8, &d.validity));
@@ -515,6 +554,7 @@ int32_t rvl_batch_slice(const rvl_batch* batch, int64_t offset, int64_t length, 
     for (const DevColumn& c : batch->cols) {
         DevColumn d = c;  // shares the buffers (Arc clone in the reference)
         d.offset = c.offset + offset; d.length = length;
+        if (length != c.length) d.window_bytes = -1;   // the narrower window's byte span is not known on the host
         d.null_count = c.dtype == RVL_NULL ? length : (c.validity ? -1 : 0);
         b->cols.push_back(std::move(d));
     }
@@ -575,12 +615,18 @@ int32_t rvl_batch_take(rvl_ctx* ctx, const rvl_batch* batch, const int64_t* indi
             int32_t total = 0;
             if (n > 0) {
                 const int32_t* soff = (const int32_t*)s.offsets->ptr + s.offset;
+                BufRef oflow;
+                RVL_TRY(dev_alloc_zeroed(core, 4, &oflow));
                 take_strlen_kernel<<<grid, 256, 0, core->stream>>>(soff, sv, idx, n, (int32_t*)lens->ptr);
-                scan_lengths_kernel<<<1, 1024, 0, core->stream>>>((const int32_t*)lens->ptr, (int32_t*)d.offsets->ptr, n);
+                scan_lengths_kernel<<<1, 1024, 0, core->stream>>>((const int32_t*)lens->ptr, (int32_t*)d.offsets->ptr, n, (int32_t*)oflow->ptr);
                 core->launches += 2;
+                int32_t over = 0;
                 RVL_CUDA_TRY(cudaMemcpyAsync(&total, (const int32_t*)d.offsets->ptr + n, 4, cudaMemcpyDeviceToHost, core->stream));
+                RVL_CUDA_TRY(cudaMemcpyAsync(&over, oflow->ptr, 4, cudaMemcpyDeviceToHost, core->stream));
                 RVL_CUDA_TRY(cudaStreamSynchronize(core->stream));
-                if (total < 0) return fail(RVL_OFFSET_OVERFLOW, "taken string data exceeds the int32 offset range");
+                // the reference wraps silently here (string.rs:31: `as i32`); a wrapped prefix can even come out positive, so the
+                // scan itself reports the overflow
+                if (over != 0 || total < 0) return fail(RVL_OFFSET_OVERFLOW, "taken string data exceeds the int32 offset range");
             }
             RVL_TRY(dev_alloc(core, (size_t)std::max<int32_t>(total, 1), &d.data));
             d.data_len = total;
@@ -674,9 +720,14 @@ int32_t rvl_batch_concat(rvl_ctx* ctx, const rvl_batch* const* batches, int32_t 
             if (m == 0) continue;
             const BitSrc sv = bitsrc_of(s.validity, s.offset, m);
             if (d.dtype == RVL_INT64 || d.dtype == RVL_FLOAT64) {
-                copy_col8_zero_nulls_kernel<<<grid_for(m, 256, core->sm_count), 256, 0, core->stream>>>(
-                    (const uint64_t*)s.values->ptr + s.offset, sv, (uint64_t*)d.values->ptr + row_base, m);
-                core->launches++;
+                if (!s.validity) {
+                    // nothing to zero: a plain device copy (copy engine / peer copy over NVLink for rvl_gather_to parts)
+                    RVL_CUDA_TRY(cudaMemcpyAsync((uint64_t*)d.values->ptr + row_base, (const uint64_t*)s.values->ptr + s.offset, (size_t)m * 8, cudaMemcpyDefault, core->stream));
+                } else {
+                    copy_col8_zero_nulls_kernel<<<grid_for(m, 256, core->sm_count), 256, 0, core->stream>>>(
+                        (const uint64_t*)s.values->ptr + s.offset, sv, (uint64_t*)d.values->ptr + row_base, m);
+                    core->launches++;
+                }
             } else if (d.dtype == RVL_BOOLEAN) {
                 bitcopy_kernel<<<grid_for((m + 31) / 32 + 1, 256, core->sm_count), 256, 0, core->stream>>>(
                     bitsrc_of(s.values, s.offset, m), sv, (uint32_t*)d.values->ptr, (uint64_t)row_base, m);
@@ -774,6 +825,169 @@ int32_t rvl_gather_to(rvl_ctx* dst, const rvl_batch* const* parts, int32_t n, rv
     return RVL_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------ multi-process ordered gather
+// One process per GPU (torchrun): the destination rank allocates the result with cudaMalloc and exports each buffer as a CUDA IPC
+// handle; every rank maps them and WRITES its own rows at its row offset over NVLink / NVSwitch, all ranks at once — the
+// destination's ingest link is the only shared resource.  The row offsets are the exclusive scan of the per-shard survivor
+// counts; bitmaps continue at arbitrary bit offsets (boundary words are OR-ed with peer atomics), string
+// offsets are rebased by the shard's byte prefix.  Same output as RecordBatch::concat of the parts (record_batch.rs:245-342).
+static int alloc_ipc(const CoreRef& core, size_t bytes, BufRef* out) {
+    const size_t padded = ((bytes + 64 + 255) / 256) * 256;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, padded);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? RVL_OUT_OF_MEMORY : RVL_CUDA, std::string("cudaMalloc(") + std::to_string(padded) + "): " + cudaGetErrorString(e));
+    }
+    RVL_CUDA_TRY(cudaMemsetAsync(p, 0, padded, core->stream));
+    auto b = std::make_shared<DevBuffer>();
+    b->ptr = p; b->bytes = padded; b->owned = true; b->kind = 1; b->core = core;
+    *out = std::move(b);
+    return RVL_OK;
+}
+
+static_assert(sizeof(cudaIpcMemHandle_t) == RVL_IPC_HANDLE_BYTES, "rvl_gather_handle layout");
+
+int32_t rvl_gather_dest_create(rvl_ctx* ctx, const int32_t* dtypes, const int32_t* has_validity, const int64_t* data_bytes, int32_t ncols,
+                               int64_t total_rows, rvl_batch** dest, rvl_gather_handle* handles) {
+    if (!ctx || !dest || !handles || (ncols > 0 && (!dtypes || !has_validity)) || total_rows < 0) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    const CoreRef& core = ctx->core;
+    RVL_CUDA_TRY(cudaSetDevice(core->device));
+    auto b = std::make_unique<rvl_batch>();
+    b->core = core; b->num_rows = total_rows;
+    std::memset(handles, 0, sizeof(rvl_gather_handle) * (size_t)ncols);
+    auto export_buf = [&](const BufRef& buf, uint8_t* h) -> int {
+        cudaIpcMemHandle_t ih;
+        RVL_CUDA_TRY(cudaIpcGetMemHandle(&ih, buf->ptr));
+        std::memcpy(h, &ih, sizeof ih);
+        return RVL_OK;
+    };
+    for (int c = 0; c < ncols; ++c) {
+        DevColumn d;
+        d.dtype = dtypes[c]; d.length = total_rows; d.offset = 0; d.null_count = -1;
+        rvl_gather_handle& h = handles[c];
+        if (d.dtype == RVL_INT64 || d.dtype == RVL_FLOAT64) { RVL_TRY(alloc_ipc(core, (size_t)total_rows * 8, &d.values)); RVL_TRY(export_buf(d.values, h.values)); }
+        else if (d.dtype == RVL_BOOLEAN) { RVL_TRY(alloc_ipc(core, (size_t)(total_rows + 7) / 8, &d.values)); RVL_TRY(export_buf(d.values, h.values)); }
+        else if (d.dtype == RVL_STRING) {
+            const int64_t nb = data_bytes ? data_bytes[c] : 0;
+            if (nb > (int64_t)INT32_MAX) return fail(RVL_OFFSET_OVERFLOW, "gathered string data (" + std::to_string(nb) + " bytes) exceeds the int32 offset range");
+            RVL_TRY(alloc_ipc(core, (size_t)(total_rows + 1) * 4, &d.offsets)); RVL_TRY(export_buf(d.offsets, h.offsets));
+            RVL_TRY(alloc_ipc(core, (size_t)nb, &d.data)); RVL_TRY(export_buf(d.data, h.data));
+            d.data_len = nb; d.window_bytes = nb;
+        } else if (d.dtype != RVL_NULL) return fail(RVL_INVALID_ARGUMENT, "unknown dtype");
+        if (has_validity[c] && d.dtype != RVL_NULL) { RVL_TRY(alloc_ipc(core, (size_t)(total_rows + 7) / 8, &d.validity)); RVL_TRY(export_buf(d.validity, h.validity)); h.has_validity = 1; }
+        else d.null_count = d.dtype == RVL_NULL ? total_rows : 0;
+        h.dtype = d.dtype; h.rows = total_rows; h.data_bytes = d.data_len;
+        b->cols.push_back(std::move(d));
+    }
+    RVL_CUDA_TRY(cudaStreamSynchronize(core->stream));   // zero-filled before any peer writes
+    *dest = b.release();
+    return RVL_OK;
+}
+
+int32_t rvl_gather_dest_open(rvl_ctx* ctx, const rvl_gather_handle* handles, int32_t ncols, rvl_batch** dest_view) {
+    if (!ctx || !handles || !dest_view) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    const CoreRef& core = ctx->core;
+    RVL_CUDA_TRY(cudaSetDevice(core->device));
+    auto b = std::make_unique<rvl_batch>();
+    b->core = core; b->num_rows = ncols > 0 ? handles[0].rows : 0;
+    auto open_buf = [&](const uint8_t* h, size_t bytes, BufRef* out) -> int {
+        cudaIpcMemHandle_t ih;
+        std::memcpy(&ih, h, sizeof ih);
+        void* p = nullptr;
+        RVL_CUDA_TRY(cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess));
+        auto buf = std::make_shared<DevBuffer>();
+        buf->ptr = p; buf->bytes = bytes; buf->owned = true; buf->kind = 2; buf->core = core;
+        *out = std::move(buf);
+        return RVL_OK;
+    };
+    for (int c = 0; c < ncols; ++c) {
+        const rvl_gather_handle& h = handles[c];
+        DevColumn d;
+        d.dtype = h.dtype; d.length = h.rows; d.offset = 0; d.null_count = -1;
+        if (d.dtype == RVL_INT64 || d.dtype == RVL_FLOAT64) RVL_TRY(open_buf(h.values, (size_t)h.rows * 8, &d.values));
+        else if (d.dtype == RVL_BOOLEAN) RVL_TRY(open_buf(h.values, (size_t)(h.rows + 7) / 8, &d.values));
+        else if (d.dtype == RVL_STRING) {
+            RVL_TRY(open_buf(h.offsets, (size_t)(h.rows + 1) * 4, &d.offsets));
+            RVL_TRY(open_buf(h.data, (size_t)h.data_bytes, &d.data));
+            d.data_len = h.data_bytes;
+        }
+        if (h.has_validity) RVL_TRY(open_buf(h.validity, (size_t)(h.rows + 7) / 8, &d.validity));
+        b->cols.push_back(std::move(d));
+    }
+    *dest_view = b.release();
+    return RVL_OK;
+}
+
+int32_t rvl_gather_push(rvl_ctx* ctx, const rvl_batch* part, rvl_batch* dest, int64_t row_offset, const int64_t* byte_offsets) {
+    if (!ctx || !part || !dest) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    const CoreRef& core = ctx->core;
+    RVL_CUDA_TRY(cudaSetDevice(core->device));
+    if (part->cols.size() != dest->cols.size()) return fail(RVL_SCHEMA_MISMATCH, "All batches must have the same schema");
+    const int64_t m = part->num_rows;
+    if (row_offset < 0 || row_offset + m > dest->num_rows) return fail(RVL_OUT_OF_BOUNDS, "gather: rows [" + std::to_string(row_offset) + ", " + std::to_string(row_offset + m) + ") outside the destination's " + std::to_string(dest->num_rows) + " rows");
+    if (part->core.get() != core.get()) {
+        // the part's producing kernels ran on its own context's stream
+        cudaEvent_t ev = core->take_event();
+        if (!ev) return fail(RVL_CUDA, "cudaEventCreate failed");
+        cudaSetDevice(part->core->device);
+        cudaError_t e = cudaEventRecord(ev, part->core->stream);
+        cudaSetDevice(core->device);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(core->stream, ev, 0);
+        core->give_event(ev);
+        RVL_CUDA_TRY(e);
+    }
+    for (size_t c = 0; c < part->cols.size(); ++c) {
+        const DevColumn& s = part->cols[c];
+        DevColumn& d = dest->cols[c];
+        if (s.dtype != d.dtype) return fail(RVL_SCHEMA_MISMATCH, "All batches must have the same schema");
+        if (m == 0) continue;
+        const BitSrc sv = bitsrc_of(s.validity, s.offset, m);
+        if (s.validity && !d.validity) return fail(RVL_INVALID_ARGUMENT, "gather: column " + std::to_string(c) + " carries nulls but the destination was created without a validity bitmap");
+        if (d.dtype == RVL_INT64 || d.dtype == RVL_FLOAT64) {
+            uint64_t* dst = (uint64_t*)d.values->ptr + row_offset;
+            const uint64_t* src = (const uint64_t*)s.values->ptr + s.offset;
+            if (!s.validity) RVL_CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)m * 8, cudaMemcpyDefault, core->stream));   // copy engine, peer write
+            else { copy_col8_zero_nulls_kernel<<<grid_for(m, 256, core->sm_count), 256, 0, core->stream>>>(src, sv, dst, m); core->launches++; }
+        } else if (d.dtype == RVL_BOOLEAN) {
+            bitcopy_kernel<<<grid_for((m + 31) / 32 + 1, 256, core->sm_count), 256, 0, core->stream>>>(bitsrc_of(s.values, s.offset, m), sv, (uint32_t*)d.values->ptr, (uint64_t)row_offset, m);
+            core->launches++;
+        } else if (d.dtype == RVL_STRING) {
+            if (!byte_offsets) return fail(RVL_INVALID_ARGUMENT, "gather: byte_offsets is required for String columns");
+            int32_t fl[2];
+            RVL_CUDA_TRY(cudaMemcpyAsync(&fl[0], (const int32_t*)s.offsets->ptr + s.offset, 4, cudaMemcpyDeviceToHost, core->stream));
+            RVL_CUDA_TRY(cudaMemcpyAsync(&fl[1], (const int32_t*)s.offsets->ptr + s.offset + m, 4, cudaMemcpyDeviceToHost, core->stream));
+            RVL_CUDA_TRY(cudaStreamSynchronize(core->stream));
+            const int64_t nb = (int64_t)fl[1] - fl[0], bo = byte_offsets[c];
+            if (bo < 0 || bo + nb > d.data_len) return fail(RVL_OUT_OF_BOUNDS, "gather: string bytes outside the destination's data buffer");
+            rebase_offsets_kernel<<<grid_for(m, 256, core->sm_count), 256, 0, core->stream>>>((const int32_t*)s.offsets->ptr + s.offset, (int32_t*)d.offsets->ptr + row_offset, m, (int32_t)bo);
+            core->launches++;
+            if (nb > 0) RVL_CUDA_TRY(cudaMemcpyAsync((uint8_t*)d.data->ptr + bo, (const uint8_t*)s.data->ptr + fl[0], (size_t)nb, cudaMemcpyDefault, core->stream));
+        }
+        if (d.validity) {
+            // a part without nulls still owns its bits of the destination bitmap: all ones
+            bitcopy_kernel<<<grid_for((m + 31) / 32 + 1, 256, core->sm_count), 256, 0, core->stream>>>(sv, BitSrc{nullptr, 0, 0}, (uint32_t*)d.validity->ptr, (uint64_t)row_offset, m);
+            core->launches++;
+        }
+        RVL_CUDA_TRY(cudaGetLastError());
+    }
+    RVL_CUDA_TRY(cudaStreamSynchronize(core->stream));   // the rows are in the destination's memory when this returns
+    return RVL_OK;
+}
+
+int32_t rvl_gather_dest_finish(rvl_ctx* ctx, rvl_batch* dest) {
+    if (!ctx || !dest) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    RVL_CUDA_TRY(cudaSetDevice(ctx->core->device));
+    for (size_t c = 0; c < dest->cols.size(); ++c) {
+        DevColumn& d = dest->cols[c];
+        d.null_count = d.dtype == RVL_NULL ? d.length : (d.validity ? -1 : 0);
+        RVL_TRY(ensure_null_count(dest, (int)c));
+        if (d.validity && d.null_count == 0) d.validity.reset();   // bitmap dropped when nothing is null (primitive.rs:180-185)
+    }
+    return RVL_OK;
+}
+
 int32_t rvl_gen_batch(rvl_ctx* ctx, const int32_t* kinds, const uint32_t* col_ids, const uint32_t* null_pct, int32_t ncols,
                       uint64_t row0, int64_t n, rvl_batch** out) {
     if (!ctx || !out || n < 0) return fail(RVL_INVALID_ARGUMENT, "bad argument");
@@ -806,7 +1020,7 @@ int32_t rvl_gen_batch(rvl_ctx* ctx, const int32_t* kinds, const uint32_t* col_id
             int32_t total_bytes = 0;
             RVL_CUDA_TRY(cudaMemcpyAsync(&total_bytes, (const int32_t*)d.offsets->ptr + n, 4, cudaMemcpyDeviceToHost, core->stream));
             RVL_CUDA_TRY(cudaStreamSynchronize(core->stream));
-            d.data_len = total_bytes;
+            d.data_len = total_bytes; d.window_bytes = total_bytes;
             RVL_TRY(dev_alloc(core, (size_t)total_bytes, &d.data));
             if (n > 0) { gen_strbytes_kernel<<<g8, 256, 0, core->stream>>>((uint8_t*)d.data->ptr, (const int32_t*)d.offsets->ptr, col_ids[c], row0, n); core->launches++; }
         } else {

@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cstdint>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -35,12 +36,22 @@ struct CtxCore {
     cudaStream_t copy_stream = nullptr;  // H2D staging of the streaming executor
     int sm_count = 148;
     std::atomic<int64_t> launches{0};
-    uint64_t* mailbox = nullptr;     // pinned host words the device counters are copied into
+    uint64_t* mailbox = nullptr;     // pinned host words the synchronous entry points (counts, checksums, concat) read back into
     size_t mailbox_words = 0;
-    // the upper part of the mailbox is a ring of kSlotWords-word slots, one per in-flight fused launch
-    static constexpr size_t kSlotWords = 64, kSlots = 60, kSlotBase = 256;
-    std::atomic<uint32_t> slot_cursor{0};
+    static constexpr size_t kSlotBase = 256;   // words of `mailbox` those synchronous readbacks may use
+    // Every in-flight operator invocation (FpPending) owns one pinned kSlotWords-word slot from a free list until it is
+    // finished; the list grows by whole pinned chunks, so any number of launches may be outstanding without two of them
+    // ever sharing a slot (a fixed ring aliased once more than its size were in flight).
+    static constexpr size_t kSlotWords = 64, kSlotsPerChunk = 64;
+    std::mutex mu;                             // guards slot_free / slot_chunks / event_pool / prof_events
+    std::vector<uint64_t*> slot_free;
+    std::vector<uint64_t*> slot_chunks;
+    uint64_t* take_slot();
+    void give_slot(uint64_t* s) { if (s) { std::lock_guard<std::mutex> g(mu); slot_free.push_back(s); } }
     cudaStream_t d2h_stream = nullptr;   // downloads of finished batches (overlaps H2D staging and kernels)
+    cudaStream_t side_stream = nullptr;  // forked from `stream` for the bit-packed compaction kernel (runs under the HBM-bound ones)
+    bool bits_overlap = true;            // RVL_OPT_BITS_OVERLAP
+    bool exact_alloc = true;             // RVL_OPT_EXACT_ALLOC: blocking rvl_filter_project sizes two-pass outputs from the scan's count
     // optional kernel-level timing of the fused kernel (rvl_ctx_profile_*)
     bool profile = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -59,14 +70,16 @@ struct CtxCore {
     // pooled timing-less events (one per in-flight operator invocation): create / destroy per batch costs microseconds
     std::vector<cudaEvent_t> event_pool;
     cudaEvent_t take_event() {
-        if (!event_pool.empty()) { cudaEvent_t e = event_pool.back(); event_pool.pop_back(); return e; }
+        {
+            std::lock_guard<std::mutex> g(mu);
+            if (!event_pool.empty()) { cudaEvent_t e = event_pool.back(); event_pool.pop_back(); return e; }
+        }
         cudaEvent_t e = nullptr;
         if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
         return e;
     }
-    void give_event(cudaEvent_t e) { if (e) event_pool.push_back(e); }
+    void give_event(cudaEvent_t e) { if (e) { std::lock_guard<std::mutex> g(mu); event_pool.push_back(e); } }
     int prof_flush();
-    uint64_t* next_slot() { return mailbox + kSlotBase + (size_t)(slot_cursor.fetch_add(1) % kSlots) * kSlotWords; }
     ~CtxCore();
 };
 using CoreRef = std::shared_ptr<CtxCore>;
@@ -74,7 +87,9 @@ using CoreRef = std::shared_ptr<CtxCore>;
 struct DevBuffer {
     void* ptr = nullptr;
     size_t bytes = 0;
-    bool owned = true;
+    bool owned = true;      // freed by the destructor (how: `kind`)
+    int kind = 0;           // 0 = stream-ordered pool allocation (cudaFreeAsync), 1 = cudaMalloc (exportable over CUDA IPC: cudaFree),
+                            // 2 = another process's allocation mapped through CUDA IPC (cudaIpcCloseMemHandle)
     CoreRef core;
     ~DevBuffer();
 };
@@ -94,6 +109,8 @@ struct DevColumn {
     BufRef offsets;   // String
     BufRef data;      // String
     int64_t data_len = 0;
+    int64_t window_bytes = -1;  // String: bytes referenced by the viewed rows (offsets[offset+length] - offsets[offset]) when the host
+                                //   knows it, else -1 (then data_len bounds it); sizes the output of a filter over this view
     int64_t null_count = -1;  // -1 = not computed yet
 };
 

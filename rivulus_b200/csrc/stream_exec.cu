@@ -1,7 +1,15 @@
 // stream_exec.cu — the streaming executor: RecordBatches pushed from HOST memory flow through pinned,
 // multi-buffered H2D staging on a copy stream while the fused Filter+Select+Limit kernel of the previous
-// batch runs on the compute stream; LIMIT stops further transfers as soon as the device-side running
-// count (chained from batch to batch through a device word) reaches the limit.
+// group runs on the compute stream; LIMIT stops further transfers as soon as the device-side running
+// count (chained from launch to launch through a device word) reaches the limit.
+//
+// Groups.  A staging slot holds `batch_rows` rows.  Pushed batches smaller than that are APPENDED to the open slot (their H2D
+// copies are enqueued immediately, back to back on the copy engine) and one operator launch covers the whole group — for 64 K-row
+// batches that is 1 kernel, 1 count readback and 1 set of output buffers per 16 batches instead of per batch, which is what bounded
+// small-batch streaming in round 1 (~25 us of API work + a 20 us kernel on 8 SMs per 1.5 MB batch).  LIMIT streams grow their
+// groups 1, 1, 2, 4, ... batches, so a limit the first batch satisfies still costs exactly the transfers a LimitStream would pull
+// (physical_plan/streaming.rs:269-271).  A group is launched when it is full, when the next batch cannot be appended (ragged row
+// count, String columns, non-adjacent in-place buffers), or when the consumer asks for output.
 //
 // Transfer modes (rvl_stream_config::transfer).  STAGED: every needed column crosses PCIe on the copy engine.
 // ZERO_COPY: only the predicate column is staged; the fixed-width projected columns stay in the caller's pinned
@@ -13,6 +21,8 @@
 // Replaces (reference, /root/reference/src): trait DataStream + MemoryStream/FilterStream/SelectStream
 // (execution/stream.rs:25-213), LimitStream (physical_plan/streaming.rs:246-288) and the final
 // collect_stream_batches concat (physical_plan/streaming.rs:343-352).
+#include <cuda.h>
+
 #include <algorithm>
 #include <cstring>
 #include <deque>
@@ -39,22 +49,42 @@ struct Slot {
 struct InFlight {
     FpPending* pend;
     int slot;
-    int64_t rows;  // input rows of the batch
+    int64_t rows;  // input rows of the group
 };
 
-bool is_pinned_or_device(const void* p) {
-    if (p == nullptr) return true;
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
-}
+// how one input column of the open group reaches the kernels
+struct GroupCol {
+    int mode = 0;                          // 0 = not needed (never transferred), 1 = staged into the slot, 2 = read in place
+    bool has_validity = false;
+    int64_t resid = 0;                     // sub-64-row residual of the first batch's view offset (bit offsets survive the copy)
+    const uint8_t* ip_values = nullptr;    // in place: device view of the group's first row, rounded down to a 64-row boundary
+    const uint8_t* ip_validity = nullptr;
+    int64_t str_first = 0, str_last = 0;   // staged String: byte window of the batch
+};
 
-// the address kernels can use to read caller memory in place (mapped pinned host memory, or device memory), else nullptr
-const void* device_view_of(const void* p) {
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    if (a.type != cudaMemoryTypeHost && a.type != cudaMemoryTypeDevice && a.type != cudaMemoryTypeManaged) return nullptr;
-    return a.devicePointer;
+// What the driver says about a caller pointer, remembered per allocation: a streamed table is normally a handful of large pinned
+// buffers sliced into many batches, so the (microsecond) attribute query is paid once per buffer instead of once per pushed column.
+struct PtrRange {
+    uintptr_t lo = 0, hi = 0;
+    bool reachable = false;   // pinned host / device / managed: cudaMemcpyAsync from it is truly asynchronous
+    bool has_dev = false;     // kernels can read it through host address + dev_delta
+    intptr_t dev_delta = 0;
+};
+
+typedef CUresult (*PfnPointerGetAttribute)(void*, CUpointer_attribute, CUdeviceptr);
+
+PfnPointerGetAttribute pointer_attr_fn() {
+    // resolved through the runtime, so the library does not link libcuda
+    static PfnPointerGetAttribute fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuPointerGetAttribute", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            f = nullptr;
+        }
+        return (PfnPointerGetAttribute)f;
+    }();
+    return fn;
 }
 
 }  // namespace
@@ -70,18 +100,53 @@ struct rvl_stream {
     std::vector<Slot> slots;
     int next_slot = 0;
     std::deque<InFlight> inflight;
-    BufRef cursor;  // two device words, ping-pong: rows emitted so far
+    std::deque<rvl_batch*> parts;      // outputs finished ahead of the consumer (a producer that pushes without draining)
+    BufRef cursor;                     // two device words, ping-pong: rows emitted so far
     int64_t zero_copy_cols = 0;        // columns handed to the kernels in place so far
-    bool adaptive = false;             // AUTO: batches go back to the copy engine while the stream is dense (recent_sel)
-    double recent_sel = 0.0;           // survivors / rows of the most recent batch whose count has arrived
+    bool adaptive = false;             // AUTO: groups go back to the copy engine while the stream is dense (recent_sel)
+    double recent_sel = 0.0;           // survivors / rows of the most recent group whose count has arrived
     bool zero_copy = false;            // fixed-width projected columns are read in place from pinned host memory
     std::vector<uint8_t> needed;       // per input column: predicate (1) / projected (2) — anything else is not transferred
-    int64_t pushed = 0, skipped = 0, h2d_bytes = 0;
+    bool any_string = false;           // a needed column is a String: batches are never coalesced (offsets would need rebasing)
+    int64_t pushed = 0, skipped = 0, h2d_bytes = 0, groups = 0;
     bool limit_hit = false;
-    int64_t rows_out = 0;  // rows handed out through next()/collect()
+    int64_t rows_out = 0;              // rows of the finished outputs
+    // the open group: pushed batches appended to slot `next_slot`, operator not launched yet
+    bool open = false;
+    int64_t open_rows = 0, open_target = 0;
+    std::vector<GroupCol> gcols;
+    std::vector<PtrRange> ptr_cache;
 };
 
-static int ensure_pinned(void** p, size_t* cap, size_t need) {
+namespace {
+
+constexpr size_t kMaxInflight = 32;   // launches outstanding before push() starts finishing the oldest ones itself
+constexpr size_t kMergeParts = 16;    // finished-ahead outputs are concatenated (at their exact size) this many at a time
+
+PtrRange classify(rvl_stream* s, const void* p) {
+    PtrRange r;
+    if (p == nullptr) { r.reachable = true; return r; }
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    for (const PtrRange& c : s->ptr_cache)
+        if (a >= c.lo && a < c.hi) return c;
+    r.lo = a; r.hi = a + 1;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return r; }
+    if (at.type != cudaMemoryTypeHost && at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) return r;  // pageable
+    r.reachable = true;
+    if (at.devicePointer != nullptr) { r.has_dev = true; r.dev_delta = (intptr_t)reinterpret_cast<uintptr_t>(at.devicePointer) - (intptr_t)a; }
+    if (PfnPointerGetAttribute fn = pointer_attr_fn()) {
+        CUdeviceptr start = 0; size_t size = 0;
+        if (fn(&start, CU_POINTER_ATTRIBUTE_RANGE_START_ADDR, (CUdeviceptr)a) == CUDA_SUCCESS &&
+            fn(&size, CU_POINTER_ATTRIBUTE_RANGE_SIZE, (CUdeviceptr)a) == CUDA_SUCCESS && size > 0 && (uintptr_t)start <= a && a < (uintptr_t)start + size) {
+            r.lo = (uintptr_t)start; r.hi = (uintptr_t)start + size;
+            if (s->ptr_cache.size() < 256) s->ptr_cache.push_back(r);
+        }
+    }
+    return r;
+}
+
+int ensure_pinned(void** p, size_t* cap, size_t need) {
     if (*p != nullptr && (cap == nullptr || *cap >= need)) return RVL_OK;
     if (*p != nullptr) { cudaFreeHost(*p); *p = nullptr; }
     RVL_CUDA_TRY(cudaHostAlloc(p, need ? need : 1, cudaHostAllocDefault));
@@ -89,22 +154,23 @@ static int ensure_pinned(void** p, size_t* cap, size_t need) {
     return RVL_OK;
 }
 
-// copy `bytes` from a caller buffer to the device slot on the copy stream, staging through pinned memory
-// when the caller's memory is pageable (so the caller may reuse its buffer as soon as push() returns)
-static int stage_copy(rvl_stream* s, void* dev_dst, const void* src, size_t bytes, void** pinned, size_t* pinned_cap, size_t pinned_need) {
+// copy `bytes` from a caller buffer to the device slot on the copy stream.  Pageable sources are staged through the slot's pinned
+// buffer first (at byte `pinned_off`), so the caller may reuse them as soon as push() returns; page-locked sources are read by the
+// copy engine directly and must stay valid until the batch's output has been returned (include/rivulus_gpu.h).
+int stage_copy(rvl_stream* s, void* dev_dst, const void* src, size_t bytes, void** pinned, size_t* pinned_cap, size_t pinned_need, size_t pinned_off) {
     if (bytes == 0) return RVL_OK;
     const void* from = src;
-    if (!is_pinned_or_device(src)) {
-        RVL_TRY(ensure_pinned(pinned, pinned_cap, std::max(pinned_need, bytes)));
-        std::memcpy(*pinned, src, bytes);
-        from = *pinned;
+    if (!classify(s, src).reachable) {
+        RVL_TRY(ensure_pinned(pinned, pinned_cap, std::max(pinned_need, pinned_off + bytes)));
+        std::memcpy((uint8_t*)*pinned + pinned_off, src, bytes);
+        from = (uint8_t*)*pinned + pinned_off;
     }
     RVL_CUDA_TRY(cudaMemcpyAsync(dev_dst, from, bytes, cudaMemcpyDefault, s->core->copy_stream));
     s->h2d_bytes += (int64_t)bytes;
     return RVL_OK;
 }
 
-static void poll_limit(rvl_stream* s) {
+void poll_limit(rvl_stream* s) {
     if (s->limit < 0 || s->limit_hit) return;
     for (const InFlight& f : s->inflight) {
         const uint64_t total = *reinterpret_cast<volatile uint64_t*>(f.pend->mailbox);
@@ -112,8 +178,8 @@ static void poll_limit(rvl_stream* s) {
     }
 }
 
-// selectivity of the newest batch whose counters have already landed in its mailbox (non-blocking)
-static void poll_selectivity(rvl_stream* s) {
+// selectivity of the newest group whose counters have already landed in its mailbox (non-blocking)
+void poll_selectivity(rvl_stream* s) {
     for (auto it = s->inflight.rbegin(); it != s->inflight.rend(); ++it) {
         const volatile uint64_t* mb = reinterpret_cast<volatile uint64_t*>(it->pend->mailbox);
         const uint64_t total = mb[0];
@@ -124,6 +190,99 @@ static void poll_selectivity(rvl_stream* s) {
         return;
     }
 }
+
+// waits for the oldest launch and builds its output batch
+int finish_oldest(rvl_stream* s, rvl_batch** out) {
+    InFlight f = s->inflight.front();
+    s->inflight.pop_front();
+    rvl_batch* b = nullptr;
+    RVL_TRY(fp_finish(f.pend, &b, nullptr));
+    if (f.rows > 0) s->recent_sel = (double)b->num_rows / (double)f.rows;
+    s->rows_out += b->num_rows;
+    if (s->limit >= 0 && s->rows_out >= s->limit) s->limit_hit = true;
+    *out = b;
+    return RVL_OK;
+}
+
+// A producer that never drains: finish the oldest launches ourselves and fold their (worst-case sized) outputs into exact-size
+// batches, so neither the in-flight bookkeeping nor device memory grows with the number of pushed batches.
+int retire_ahead(rvl_stream* s) {
+    while (s->inflight.size() >= kMaxInflight) {
+        rvl_batch* b = nullptr;
+        RVL_TRY(finish_oldest(s, &b));
+        s->parts.push_back(b);
+    }
+    if (s->parts.size() >= kMergeParts) {
+        std::vector<const rvl_batch*> v(s->parts.begin(), s->parts.end());
+        rvl_ctx tmp{s->core};
+        rvl_batch* merged = nullptr;
+        RVL_TRY(rvl_batch_concat(&tmp, v.data(), (int32_t)v.size(), &merged));
+        for (rvl_batch* b : s->parts) delete b;
+        s->parts.clear();
+        s->parts.push_back(merged);
+    }
+    return RVL_OK;
+}
+
+// launch the operator over the open group
+int flush_group(rvl_stream* s) {
+    if (!s->open) return RVL_OK;
+    const CoreRef& core = s->core;
+    Slot& sl = s->slots[(size_t)s->next_slot];
+    const int64_t n = s->open_rows;
+    const int ncols = (int)s->dtypes.size();
+    auto view = std::make_unique<rvl_batch>();
+    view->core = core; view->num_rows = n;
+    for (int c = 0; c < ncols; ++c) {
+        const GroupCol& g = s->gcols[(size_t)c];
+        StagingColumn& sc = sl.cols[(size_t)c];
+        const int64_t span = g.resid + n;
+        DevColumn d;
+        d.dtype = s->dtypes[(size_t)c]; d.length = n; d.offset = g.resid;
+        if (g.mode == 0) {
+            // neither the predicate nor projected: the operator never looks at it, nothing crossed the bus
+            d.dtype = RVL_NULL; d.null_count = n; d.offset = 0;
+        } else if (g.mode == 2) {
+            if (d.dtype == RVL_BOOLEAN) d.values = wrap_external(core, g.ip_values, (size_t)(span + 7) / 8);
+            else d.values = wrap_external(core, g.ip_values, (size_t)span * 8);
+            if (g.has_validity) d.validity = wrap_external(core, g.ip_validity, (size_t)(span + 7) / 8);
+            else d.null_count = 0;
+        } else {
+            if (d.dtype == RVL_INT64 || d.dtype == RVL_FLOAT64 || d.dtype == RVL_BOOLEAN) d.values = sc.values;
+            else if (d.dtype == RVL_STRING) {
+                d.offsets = sc.offsets;
+                // offsets stay absolute: present the data pointer shifted back by `first` (never dereferenced below the copy)
+                const size_t nbytes = (size_t)(g.str_last - g.str_first);
+                d.data = wrap_external(core, (const uint8_t*)sc.data->ptr - g.str_first, nbytes + (size_t)g.str_first);
+                d.data_len = g.str_last;
+                d.window_bytes = (int64_t)nbytes;   // sizes the output: the survivors' bytes are a subset of this window
+            }
+            if (g.has_validity) d.validity = sc.validity;
+            else d.null_count = d.dtype == RVL_NULL ? n : 0;
+        }
+        view->cols.push_back(std::move(d));
+    }
+    RVL_CUDA_TRY(cudaEventRecord(sl.copied, core->copy_stream));
+    RVL_CUDA_TRY(cudaStreamWaitEvent(core->stream, sl.copied, 0));
+
+    unsigned long long* cur = (unsigned long long*)s->cursor->ptr;
+    const int k = (int)(s->groups & 1);
+    FpPending* pend = nullptr;
+    RVL_TRY(fp_launch(core, view.get(), &s->pred, s->proj.data(), (int32_t)s->proj.size(), s->limit, false, cur + k, cur + (k ^ 1), &pend));
+    RVL_CUDA_TRY(cudaEventRecord(sl.free_ev, core->stream));
+    // the next H2D into this slot must not start before this kernel has read it
+    sl.used = true;
+    s->inflight.push_back(InFlight{pend, s->next_slot, n});
+    s->next_slot = (s->next_slot + 1) % (int)s->slots.size();
+    // make the copy stream wait for the slot it is going to overwrite next
+    Slot& nx = s->slots[(size_t)s->next_slot];
+    if (nx.used) RVL_CUDA_TRY(cudaStreamWaitEvent(core->copy_stream, nx.free_ev, 0));
+    s->groups++;
+    s->open = false; s->open_rows = 0;
+    return RVL_OK;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -159,14 +318,15 @@ int32_t rvl_stream_open(rvl_ctx* ctx, const int32_t* dtypes, int32_t ncols, cons
         s->needed[(size_t)s->pred.column] |= 1;
         if (s->pred.mode == RVL_PRED_CMP_LITERAL && s->pred.tag_column > 0 && s->pred.tag_column <= ncols) s->needed[(size_t)s->pred.tag_column - 1] |= 1;
     }
+    for (int c = 0; c < ncols; ++c) s->any_string |= s->needed[(size_t)c] != 0 && dtypes[c] == RVL_STRING;
     const int transfer = cfg ? cfg->transfer : RVL_TRANSFER_AUTO;
     if (transfer != RVL_TRANSFER_AUTO && transfer != RVL_TRANSFER_STAGED && transfer != RVL_TRANSFER_ZERO_COPY)
         return fail(RVL_INVALID_ARGUMENT, "unknown transfer mode");
-    // AUTO: batches large enough for the two-pass plan (whose gather / TMA kernels touch only what they need) read in place
     s->zero_copy = transfer != RVL_TRANSFER_STAGED;
     s->adaptive = transfer == RVL_TRANSFER_AUTO;
     const int n_slots = cfg && cfg->n_staging >= 1 ? cfg->n_staging : 2;
     s->slots.resize((size_t)n_slots);
+    s->gcols.resize((size_t)ncols);
     const size_t rows_cap = (size_t)s->batch_rows + 64;
     for (Slot& sl : s->slots) {
         sl.cols.resize((size_t)ncols);
@@ -203,70 +363,110 @@ int32_t rvl_stream_push(rvl_stream* s, const rvl_column* cols, int32_t ncols, in
 
     // LimitStream: once the limit is reached nothing more is pulled (streaming.rs:269-271)
     poll_limit(s);
-    Slot& sl = s->slots[(size_t)s->next_slot];
-    if (!s->limit_hit && sl.used) {
-        // back-pressure: this slot's previous batch must have been consumed by its kernel; its mailbox is then
-        // visible too, so a tripped limit is noticed before any further byte crosses PCIe
-        RVL_CUDA_TRY(cudaEventSynchronize(sl.free_ev));
-        poll_limit(s);
-    }
-    if (!s->limit_hit && s->limit > 0 && s->pushed >= 1) {
-        // LIMIT streams start slowly: batch 1 waits for batch 0's count, batches 2 and 3 for the batch two before them; only then
-        // does the pipeline run at its full depth.  A limit that the first batches already satisfy (LIMIT 1000 over 64 K..1 M-row
-        // batches) then costs exactly the batches a LimitStream would pull (streaming.rs:269-271), not pipeline-depth more.
-        const int64_t i = s->pushed, n_slots = (int64_t)s->slots.size();
-        const int64_t window = i <= 1 ? 1 : (i <= 3 ? 2 : n_slots);
-        if (window < n_slots) {
-            Slot& w = s->slots[(size_t)((i - window) % n_slots)];
-            if (w.used) RVL_CUDA_TRY(cudaEventSynchronize(w.free_ev));
-            poll_limit(s);
-        }
-    }
     if (s->limit_hit || s->limit == 0) { s->limit_hit = true; s->skipped++; return RVL_OK; }
 
-    // AUTO: a dense stream (more than one survivor in four rows: every PCIe line is needed anyway) goes through the copy engine,
-    // which moves whole columns ~8 % faster than SM-issued reads; a selective one is read in place
-    if (s->adaptive) poll_selectivity(s);
-    const bool in_place = s->zero_copy && !(s->adaptive && s->recent_sel > 0.25);
-    auto view = std::make_unique<rvl_batch>();
-    view->core = core; view->num_rows = n;
-    for (int c = 0; c < ncols; ++c) {
+    // ---- can this batch join the open group?  Its rows land behind the group's rows in the same slot, so every needed column must
+    // continue on a 64-row boundary (bitmap words), presence of validity must match the group's, and columns read in place must be
+    // adjacent in the caller's memory.
+    bool append = s->open && n > 0 && s->open_rows > 0 && !s->any_string && s->open_rows + n <= s->batch_rows && s->open_rows < s->open_target;
+    for (int c = 0; c < ncols && append; ++c) {
+        const GroupCol& g = s->gcols[(size_t)c];
+        if (g.mode == 0) continue;
         const rvl_column& hc = cols[c];
-        StagingColumn& sc = sl.cols[(size_t)c];
-        const int64_t resid = hc.offset % 64, start = hc.offset - resid, span = resid + n;
-        const size_t rows_cap = (size_t)s->batch_rows + 64;
-        DevColumn d;
-        d.dtype = hc.dtype; d.length = n; d.offset = resid;
-        if (s->needed[(size_t)c] == 0) {
-            // neither the predicate nor projected: the operator never looks at it, nothing crosses the bus
-            d.dtype = RVL_NULL; d.null_count = n;
-            view->cols.push_back(std::move(d));
-            continue;
-        }
-        if (in_place && (s->needed[(size_t)c] & 1) == 0 && (hc.dtype == RVL_INT64 || hc.dtype == RVL_FLOAT64 || hc.dtype == RVL_BOOLEAN)) {
-            // projected fixed-width column: the kernels read the caller's pinned memory in place
-            const void* dv = device_view_of(hc.values);
-            const void* dm = hc.validity != nullptr ? device_view_of(hc.validity) : nullptr;
-            if (dv != nullptr && (hc.validity == nullptr || dm != nullptr)) {
-                if (hc.dtype == RVL_BOOLEAN) d.values = wrap_external(core, (const uint8_t*)dv + start / 8, (size_t)(span + 7) / 8);
-                else d.values = wrap_external(core, (const uint8_t*)dv + start * 8, (size_t)span * 8);
-                if (dm != nullptr) d.validity = wrap_external(core, (const uint8_t*)dm + start / 8, (size_t)(span + 7) / 8);
-                else d.null_count = 0;
-                s->zero_copy_cols++;
-                view->cols.push_back(std::move(d));
-                continue;
+        const int64_t pos = g.resid + s->open_rows;
+        if (pos % 64 != 0 || hc.offset % 64 != 0 || (hc.validity != nullptr && hc.dtype != RVL_NULL) != g.has_validity) { append = false; break; }
+        if (g.mode == 2) {
+            const PtrRange r = classify(s, hc.values);
+            const uint8_t* have = (const uint8_t*)hc.values + r.dev_delta + (hc.dtype == RVL_BOOLEAN ? hc.offset / 8 : hc.offset * 8);
+            const uint8_t* want = g.ip_values + (hc.dtype == RVL_BOOLEAN ? pos / 8 : pos * 8);
+            if (!r.reachable || !r.has_dev || want != have) append = false;
+            if (append && g.has_validity) {
+                const PtrRange rv = classify(s, hc.validity);
+                if (!rv.reachable || !rv.has_dev || g.ip_validity + pos / 8 != hc.validity + rv.dev_delta + hc.offset / 8) append = false;
             }
         }
+    }
+    if (s->open && !append) RVL_TRY(flush_group(s));
+
+    if (!s->open) {
+        // ---- start a group in the next slot
+        RVL_TRY(retire_ahead(s));
+        Slot& sl0 = s->slots[(size_t)s->next_slot];
+        if (sl0.used) {
+            // back-pressure: this slot's previous group must have been consumed by its kernel; its mailbox is then
+            // visible too, so a tripped limit is noticed before any further byte crosses PCIe
+            RVL_CUDA_TRY(cudaEventSynchronize(sl0.free_ev));
+            poll_limit(s);
+        }
+        if (!s->limit_hit && s->limit > 0 && s->groups >= 1) {
+            // LIMIT streams start slowly: group 1 waits for group 0's count, groups 2 and 3 for the group two before them; only then
+            // does the pipeline run at its full depth.  A limit that the first batches already satisfy (LIMIT 1000 over 64 K..1 M-row
+            // batches) then costs exactly the batches a LimitStream would pull (streaming.rs:269-271), not pipeline-depth more.
+            const int64_t i = s->groups, n_slots = (int64_t)s->slots.size();
+            const int64_t window = i <= 1 ? 1 : (i <= 3 ? 2 : n_slots);
+            if (window < n_slots) {
+                Slot& w = s->slots[(size_t)((((int64_t)s->next_slot - window) % n_slots + n_slots) % n_slots)];
+                if (w.used) RVL_CUDA_TRY(cudaEventSynchronize(w.free_ev));
+                poll_limit(s);
+            }
+        }
+        if (s->limit_hit) { s->skipped++; return RVL_OK; }
+        // AUTO: a dense stream (more than one survivor in four rows: every PCIe line is needed anyway) goes through the copy engine,
+        // which moves whole columns ~8 % faster than SM-issued reads; a selective one is read in place
+        if (s->adaptive) poll_selectivity(s);
+        const bool in_place = s->zero_copy && !(s->adaptive && s->recent_sel > 0.25);
+        s->open = true; s->open_rows = 0;
+        // group size: the whole slot, except that LIMIT streams grow 1, 1, 2, 4, ... batches
+        s->open_target = s->batch_rows;
+        if (s->limit > 0) {
+            const int64_t g = s->groups;
+            const int64_t nb = g <= 1 ? 1 : (g >= 40 ? ((int64_t)1 << 39) : ((int64_t)1 << (g - 1)));
+            s->open_target = std::min<int64_t>(s->batch_rows, std::max<int64_t>(n, 1) * nb);
+        }
+        for (int c = 0; c < ncols; ++c) {
+            GroupCol& g = s->gcols[(size_t)c];
+            g = GroupCol{};
+            const rvl_column& hc = cols[c];
+            if (s->needed[(size_t)c] == 0) continue;
+            g.mode = 1;
+            g.resid = hc.offset % 64;
+            g.has_validity = hc.validity != nullptr && hc.dtype != RVL_NULL;
+            if (in_place && (s->needed[(size_t)c] & 1) == 0 && (hc.dtype == RVL_INT64 || hc.dtype == RVL_FLOAT64 || hc.dtype == RVL_BOOLEAN) && hc.values != nullptr) {
+                // projected fixed-width column: the kernels read the caller's pinned memory in place
+                const PtrRange r = classify(s, hc.values);
+                const PtrRange rv = classify(s, hc.validity);
+                if (r.reachable && r.has_dev && (!g.has_validity || (rv.reachable && rv.has_dev))) {
+                    const int64_t start = hc.offset - g.resid;
+                    g.mode = 2;
+                    g.ip_values = (const uint8_t*)hc.values + r.dev_delta + (hc.dtype == RVL_BOOLEAN ? start / 8 : start * 8);
+                    if (g.has_validity) g.ip_validity = hc.validity + rv.dev_delta + start / 8;
+                    s->zero_copy_cols++;
+                }
+            }
+        }
+    }
+
+    // ---- append this batch's rows to the open group: the H2D copies are enqueued now, back to back on the copy engine
+    Slot& sl = s->slots[(size_t)s->next_slot];
+    const size_t rows_cap = (size_t)s->batch_rows + 64;
+    const bool first = s->open_rows == 0;
+    for (int c = 0; c < ncols; ++c) {
+        GroupCol& g = s->gcols[(size_t)c];
+        if (g.mode != 1) continue;
+        const rvl_column& hc = cols[c];
+        StagingColumn& sc = sl.cols[(size_t)c];
+        // the first batch of a group keeps its sub-64-row residual; appended batches start on a 64-row boundary of the slot
+        const int64_t resid = first ? g.resid : 0;
+        const int64_t start = hc.offset - resid, span = resid + n;
+        const int64_t at = first ? 0 : g.resid + s->open_rows;   // slot row the copy starts at
         if (hc.dtype == RVL_INT64 || hc.dtype == RVL_FLOAT64) {
-            RVL_TRY(stage_copy(s, sc.values->ptr, (const uint8_t*)hc.values + start * 8, (size_t)span * 8, &sc.h_values, nullptr, rows_cap * 8));
-            d.values = sc.values;
+            RVL_TRY(stage_copy(s, (uint8_t*)sc.values->ptr + at * 8, (const uint8_t*)hc.values + start * 8, (size_t)span * 8, &sc.h_values, nullptr, rows_cap * 8, (size_t)at * 8));
         } else if (hc.dtype == RVL_BOOLEAN) {
-            RVL_TRY(stage_copy(s, sc.values->ptr, (const uint8_t*)hc.values + start / 8, (size_t)(span + 7) / 8, &sc.h_values, nullptr, rows_cap / 8 + 8));
-            d.values = sc.values;
+            RVL_TRY(stage_copy(s, (uint8_t*)sc.values->ptr + at / 8, (const uint8_t*)hc.values + start / 8, (size_t)(span + 7) / 8, &sc.h_values, nullptr, rows_cap / 8 + 8, (size_t)at / 8));
         } else if (hc.dtype == RVL_STRING) {
-            RVL_TRY(stage_copy(s, sc.offsets->ptr, hc.offsets + start, (size_t)(span + 1) * 4, &sc.h_offsets, nullptr, (rows_cap + 1) * 4));
-            const int64_t first = hc.offsets[start], last = hc.offsets[start + span];
-            const size_t nbytes = (size_t)(last - first);
+            RVL_TRY(stage_copy(s, sc.offsets->ptr, hc.offsets + start, (size_t)(span + 1) * 4, &sc.h_offsets, nullptr, (rows_cap + 1) * 4, 0));
+            const int64_t b0 = hc.offsets[start], b1 = hc.offsets[start + span];
+            const size_t nbytes = (size_t)(b1 - b0);
             if (sc.data_cap < nbytes || !sc.data) {
                 // make sure no kernel still reads the old buffer: frees are ordered on the compute stream
                 sc.data.reset();
@@ -274,51 +474,38 @@ int32_t rvl_stream_push(rvl_stream* s, const rvl_column* cols, int32_t ncols, in
                 RVL_TRY(dev_alloc(core, sc.data_cap, &sc.data));
                 RVL_CUDA_TRY(cudaStreamSynchronize(core->stream));
             }
-            RVL_TRY(stage_copy(s, sc.data->ptr, hc.data + first, nbytes, &sc.h_data, &sc.h_data_cap, nbytes));
-            d.offsets = sc.offsets;
-            // offsets stay absolute: present the data pointer shifted back by `first` (never dereferenced below the copy)
-            d.data = wrap_external(core, (const uint8_t*)sc.data->ptr - first, nbytes + (size_t)first);
-            d.data_len = last;
+            RVL_TRY(stage_copy(s, sc.data->ptr, hc.data + b0, nbytes, &sc.h_data, &sc.h_data_cap, nbytes, 0));
+            g.str_first = b0; g.str_last = b1;
         }
-        if (hc.validity != nullptr && hc.dtype != RVL_NULL) {
-            RVL_TRY(stage_copy(s, sc.validity->ptr, hc.validity + start / 8, (size_t)(span + 7) / 8, &sc.h_validity, nullptr, rows_cap / 8 + 8));
-            d.validity = sc.validity;
-        } else {
-            d.null_count = hc.dtype == RVL_NULL ? n : 0;
-        }
-        view->cols.push_back(std::move(d));
+        if (g.has_validity)
+            RVL_TRY(stage_copy(s, (uint8_t*)sc.validity->ptr + at / 8, hc.validity + start / 8, (size_t)(span + 7) / 8, &sc.h_validity, nullptr, rows_cap / 8 + 8, (size_t)at / 8));
     }
-    RVL_CUDA_TRY(cudaEventRecord(sl.copied, core->copy_stream));
-    RVL_CUDA_TRY(cudaStreamWaitEvent(core->stream, sl.copied, 0));
-
-    unsigned long long* cur = (unsigned long long*)s->cursor->ptr;
-    const int k = (int)(s->pushed & 1);
-    FpPending* pend = nullptr;
-    RVL_TRY(fp_launch(core, view.get(), &s->pred, s->proj.data(), (int32_t)s->proj.size(), s->limit, false, cur + k, cur + (k ^ 1), &pend));
-    RVL_CUDA_TRY(cudaEventRecord(sl.free_ev, core->stream));
-    // the next H2D into this slot must not start before this kernel has read it
-    sl.used = true;
-    s->inflight.push_back(InFlight{pend, s->next_slot, n});
-    s->next_slot = (s->next_slot + 1) % (int)s->slots.size();
-    // make the copy stream wait for the slot it is going to overwrite next
-    Slot& nx = s->slots[(size_t)s->next_slot];
-    if (nx.used) RVL_CUDA_TRY(cudaStreamWaitEvent(core->copy_stream, nx.free_ev, 0));
+    s->open_rows += n;
     s->pushed++;
     *accepted = 1;
+    // launch as soon as the group is complete: full, or a shape nothing can be appended to
+    if (n == 0 || s->any_string || s->open_rows >= s->open_target || s->open_rows + n > s->batch_rows) RVL_TRY(flush_group(s));
     return RVL_OK;
+}
+
+int32_t rvl_stream_flush(rvl_stream* s) {
+    if (!s) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    RVL_CUDA_TRY(cudaSetDevice(s->core->device));
+    return flush_group(s);
 }
 
 int32_t rvl_stream_next(rvl_stream* s, rvl_batch** out, int32_t* has_batch) {
     if (!s || !out || !has_batch) return fail(RVL_INVALID_ARGUMENT, "null argument");
     *has_batch = 0; *out = nullptr;
+    RVL_CUDA_TRY(cudaSetDevice(s->core->device));
+    if (!s->parts.empty()) {
+        *out = s->parts.front(); s->parts.pop_front(); *has_batch = 1;
+        return RVL_OK;
+    }
+    if (s->inflight.empty()) RVL_TRY(flush_group(s));   // the consumer is waiting on the open group
     if (s->inflight.empty()) return RVL_OK;
-    InFlight f = s->inflight.front();
-    s->inflight.pop_front();
     rvl_batch* b = nullptr;
-    RVL_TRY(fp_finish(f.pend, &b, nullptr));
-    if (f.rows > 0) s->recent_sel = (double)b->num_rows / (double)f.rows;
-    s->rows_out += b->num_rows;
-    if (s->limit >= 0 && s->rows_out >= s->limit) s->limit_hit = true;
+    RVL_TRY(finish_oldest(s, &b));
     *out = b; *has_batch = 1;
     return RVL_OK;
 }
@@ -332,9 +519,11 @@ int32_t rvl_stream_limit_reached(rvl_stream* s, int32_t* reached) {
 
 int32_t rvl_stream_collect(rvl_stream* s, rvl_batch** out) {
     if (!s || !out) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    RVL_CUDA_TRY(cudaSetDevice(s->core->device));
+    RVL_TRY(flush_group(s));
     std::vector<rvl_batch*> parts;
     int rc = RVL_OK;
-    while (!s->inflight.empty()) {
+    while (!s->parts.empty() || !s->inflight.empty()) {
         rvl_batch* b = nullptr; int32_t has = 0;
         rc = rvl_stream_next(s, &b, &has);
         if (rc != RVL_OK) break;
@@ -379,15 +568,24 @@ int32_t rvl_stream_stats(rvl_stream* s, int64_t* pushed, int64_t* skipped, int64
     return RVL_OK;
 }
 
+int32_t rvl_stream_launches(rvl_stream* s, int64_t* groups) {
+    if (!s || !groups) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    *groups = s->groups;
+    return RVL_OK;
+}
+
 int32_t rvl_stream_close(rvl_stream* s) {
     if (!s) return RVL_OK;
     cudaSetDevice(s->core->device);
+    s->open = false;   // rows copied into the open slot are simply dropped
     while (!s->inflight.empty()) {
         rvl_batch* b = nullptr;
         fp_finish(s->inflight.front().pend, &b, nullptr);
         delete b;
         s->inflight.pop_front();
     }
+    for (rvl_batch* b : s->parts) delete b;
+    s->parts.clear();
     cudaStreamSynchronize(s->core->copy_stream);
     cudaStreamSynchronize(s->core->stream);
     for (Slot& sl : s->slots) {

@@ -353,6 +353,112 @@ def test_stream_zero_copy_transfer(plan, limit, op, lit):
         ctx.close()
 
 
+@pytest.mark.parametrize("limit", [-1, 30_000])
+def test_stream_many_batches_pushed_before_draining(ctx, limit):
+    """every in-flight launch owns its pinned mailbox slot, so pushing far more batches than any fixed ring
+    held (200 here, one launch each) before the first drain returns the same rows as the oracle — no aliased counters.  Beyond
+    32 outstanding launches push() retires the oldest ones itself and merges their outputs 16 at a time."""
+    rng = np.random.default_rng(99)
+    n_batches, n = 200, 1024
+    batches = [[Col("i64", n, rng.integers(0, 1000, n)), random_col(rng, "f64", n, 0.1), random_col(rng, "bool", n, 0.1)] for _ in range(n_batches)]
+    st = ctx.open_stream([capi.INT64, capi.FLOAT64, capi.BOOLEAN], capi.predicate(0, ">", 799), [1, 0, 2], limit, batch_rows=n, n_staging=3)
+    for b in batches:
+        st.push([c.gpu() for c in b])
+    assert limit >= 0 or st.launches() == n_batches
+    got = st.collect()
+    st.close()
+    want = O.RecordBatch.concat([oracle_batch(b) for b in batches]).filter_project_cmp(0, ">", 799, [1, 0, 2], limit)
+    assert_batches_equal(got, want, f"200 pushed batches limit={limit}")
+
+
+@pytest.mark.parametrize("transfer", [capi.TRANSFER_STAGED, capi.TRANSFER_ZERO_COPY, capi.TRANSFER_AUTO])
+@pytest.mark.parametrize("limit", [-1, 5_000])
+def test_stream_coalesces_small_batches(transfer, limit):
+    """Batches smaller than the slot are appended to the open group: one operator launch per group, same rows / order / nulls as
+    one launch per batch and as the oracle.  Windows of two big pinned tables (adjacent, so in-place columns can join a group),
+    a ragged batch that forces a flush, validity that appears mid-stream, an empty batch, and next() interleaved with push()."""
+    ctx = capi.Context(0)
+    try:
+        rng = np.random.default_rng(4242 + limit)
+        rows = 40 * 4096 + 777
+        k = rng.integers(0, 1000, rows).astype(np.int64)
+        a = rng.integers(-2**62, 2**62, rows).astype(np.int64)
+        b = rng.random(rows) * 1000.0
+        f = rng.random(rows) < 0.5
+        va = rng.random(rows) > 0.1
+        va[:12 * 4096] = True                   # the first windows of `a` carry no validity buffer at all
+        keep = []
+
+        def pin(x):
+            v, owner = capi.pinned_like(x)
+            keep.append(owner)
+            return v
+        pk, pa, pb = pin(k), pin(a), pin(b)
+        pf, pva = pin(capi.pack_bits(f)), pin(capi.pack_bits(va))
+        sizes = [4096] * 12 + [4096] * 10 + [1000, 0, 4096, 4096, 64, 4096 * 3, 4096 * 8] + [4096] * 3
+        sizes.append(rows - sum(sizes) - 13)     # a window that does not start on a 64-row boundary comes last
+        windows, off = [], 0
+        for i, n in enumerate(sizes):
+            if i == len(sizes) - 1:
+                off += 13
+            windows.append((off, n))
+            off += n
+        assert off == rows
+        dtypes = [capi.INT64, capi.INT64, capi.FLOAT64, capi.BOOLEAN]
+
+        def cols_of(o, n):
+            with_valid = o >= 12 * 4096
+            return [capi.Column(capi.INT64, n, o, pk), capi.Column(capi.INT64, n, o, pa, pva if with_valid else None),
+                    capi.Column(capi.FLOAT64, n, o, pb), capi.Column(capi.BOOLEAN, n, o, pf)]
+
+        outs = {}
+        for cap in (4096 * 8, 4096 * 3):         # capacity of a slot: groups of up to 8 / 3 batches
+            st = ctx.open_stream(dtypes, capi.predicate(0, ">", 699), [1, 2, 3, 0], limit, batch_rows=max(cap, max(sizes)), n_staging=3, transfer=transfer)
+            got_parts = []
+            for i, (o, n) in enumerate(windows):
+                st.push(cols_of(o, n))
+                if i == 20:                      # a consumer that drains mid-stream: flushes the open group if nothing else is pending
+                    while True:
+                        bt = st.next_batch()
+                        if bt is None:
+                            break
+                        got_parts.append(bt)
+            launches = st.launches()
+            got_parts.append(st.collect())
+            st.close()
+            assert limit >= 0 or launches < len(sizes) // 2, f"batches were not coalesced: {launches} launches for {len(sizes)} pushes"
+            outs[cap] = ctx.concat(got_parts) if len(got_parts) > 1 else got_parts[0]
+        whole = [Col("i64", rows, k), Col("i64", rows, a, va), Col("f64", rows, b), Col("bool", rows, f)]
+        parts = []
+        for (o, n) in windows:
+            if n > 0:
+                parts.append(oracle_batch([Col(c.dtype, n, c.values[o:o + n], None if c.valid is None else c.valid[o:o + n]) for c in whole]))
+        want = O.RecordBatch.concat(parts).filter_project_cmp(0, ">", 699, [1, 2, 3, 0], limit)
+        for cap, got in outs.items():
+            assert_batches_equal(got, want, f"coalesced stream cap={cap} transfer={transfer} limit={limit}")
+    finally:
+        ctx.close()
+
+
+@pytest.mark.parametrize("exact,overlap", [(0, 0), (1, 0), (0, 1), (1, 1)])
+def test_two_pass_exact_allocation_and_forked_bits(exact, overlap):
+    """RVL_OPT_EXACT_ALLOC (outputs sized from the scan's count / the string sizes pass) and RVL_OPT_BITS_OVERLAP (bit-packed
+    compaction on the forked stream) change where and when the bytes are written, never which bytes."""
+    rng = np.random.default_rng(17)
+    n = 300_123
+    cols = [random_col(rng, "i64", n, 0.1, lo=0, hi=1000), random_col(rng, "f64", n, 0.2), random_col(rng, "bool", n, 0.1, offset=9),
+            random_col(rng, "str", n, 0.1, maxlen=18), random_col(rng, "i64", n, 0.0)]
+    c = capi.Context(0)
+    c.set_option(capi.OPT_PLAN, capi.PLAN_TWO_PASS)
+    c.set_option(capi.OPT_EXACT_ALLOC, exact)
+    c.set_option(capi.OPT_BITS_OVERLAP, overlap)
+    try:
+        for op, lit, limit in ((">", 899, -1), (">", 499, -1), ("<", 3, -1), (">", 2000, -1), (">", 499, 1234)):
+            run_cmp(c, cols, 0, op, lit, [3, 1, 2, 4, 0], limit, tag=f"exact={exact} overlap={overlap} {op}{lit} limit={limit}")
+    finally:
+        c.close()
+
+
 # ------------------------------------------------------------------ sharded (row-range) execution on one GPU
 def test_sharded_two_contexts_one_gpu(ctx):
     rng = np.random.default_rng(31)

@@ -73,3 +73,14 @@ def test_two_rank_row_range_sharding(limit):
     want = (lf.limit(limit) if limit >= 0 else lf).collect().to_dict()
     assert sum(counts) == O.LazyFrame.from_dataframe(df).filter(O.col("k").gt(O.lit(499))).collect().height()
     assert merged == want
+
+
+def test_gather_plan_offsets_match_sequential_concat():
+    """plan_gather: row / byte offsets of every shard in the ordered result, with and without a global LIMIT."""
+    from rivulus_b200.sharding import plan_gather
+    per_rank = [[5, 50, 7], [0, 0, 0], [3, 31, 2], [9, 90, 11]]
+    take, row_off, byte_off, total, totals = plan_gather(per_rank)
+    assert take == [5, 0, 3, 9] and row_off == [0, 5, 5, 8] and total == 17
+    assert byte_off == [[0, 0], [50, 7], [50, 7], [81, 9]] and totals == [171, 20]
+    take, row_off, _, total, _ = plan_gather(per_rank, limit=7)
+    assert take == [5, 0, 2, 0] and row_off == [0, 5, 5, 7] and total == 7

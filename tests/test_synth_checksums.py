@@ -58,6 +58,30 @@ def test_synth_checksum_oracle_matches_eager_engine(op, lit):
     assert nbytes[1] == sum(len(v) for v in out.column("name") if v is not None)
 
 
+def _golden_cases(workload, rows):
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "synth_checksums.json")
+    return [c for c in json.load(open(path))["cases"] if c["workload"] == workload and c["rows"] == rows]
+
+
+def test_golden_checksum_file_matches_the_oracle():
+    """tests/golden/synth_checksums.json (scripts/gen_golden_checksums.py) is what the oracle computes: the cheapest full-size case
+    (0.1 % of 10^9 rows) is recomputed here, and a prefix property ties the rest: the count of `k > T` over the first 10^8 rows is
+    monotone in T and bounded by the committed full-size counts."""
+    cases = _golden_cases("configs[1]", 1_000_000_000)
+    assert [c["pred"]["literal"] for c in cases] == [998, 899, 499, 99] and len(_golden_cases("configs[4]", 4_000_000_000)) == 2
+    c = cases[0]
+    count, sums = O.synth_filter_checksums(c["rows"], c["row0"], c["pred"]["kind"], c["pred"]["col_id"], c["pred"]["op"], c["pred"]["literal"],
+                                           [tuple(p) for p in c["proj"]])
+    assert count == c["count"] and sums == [int(x) for x in c["checksums"]]
+    prev = 0
+    for c in cases:
+        part, _ = O.synth_filter_checksums(100_000_000, 0, 0, 0, ">", c["pred"]["literal"], [(capi.SYNTH_I64, 1)])
+        assert prev <= part <= c["count"]
+        prev = part
+
+
 def _gpu_check(ctx, n, row0, pred, op, lit, proj_spec, limit=-1):
     spec = [pred] + list(proj_spec)
     gb = ctx.gen_batch(spec, n, row0)
@@ -137,6 +161,12 @@ def test_full_size_one_billion_rows_properties():
         count, sums = O.synth_filter_checksums(n, 0, capi.SYNTH_KEY1000, 0, ">", 998, [(s[0], s[1]) for s in spec[1:]])
         assert out.num_rows() == count and [out.checksum(j) for j in range(4)] == sums
         out.release()
+        # exact at every selectivity of the sweep, against the values the same oracle computed offline (tests/golden/synth_checksums.json)
+        for case in _golden_cases("configs[1]", n):
+            o = ctx.filter_project(table, capi.predicate(0, case["pred"]["op"], case["pred"]["literal"]), [1, 2, 3, 4])
+            assert o.num_rows() == case["count"], case["pred"]
+            assert [o.checksum(j) for j in range(4)] == [int(x) for x in case["checksums"]], case["pred"]
+            o.release()
         # properties at 50 %
         res = {}
         for plan in (capi.PLAN_TWO_PASS, capi.PLAN_FUSED):
@@ -161,5 +191,41 @@ def test_full_size_one_billion_rows_properties():
             parts.append(ctx.filter_project(table.slice(b, e - b), capi.predicate(0, ">", 899), [2]))
         cat = ctx.concat(parts)
         assert cat.num_rows() == whole.num_rows() and cat.checksum(0) == whole.checksum(0)
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
+def test_offset_overflow_is_reported_not_wrapped():
+    """The one deliberate deviation from the reference: where `StringArray::new` wraps int32 offsets silently (string.rs:31),
+    upload / concat / take report RVL_OFFSET_OVERFLOW (status 7)."""
+    import ctypes as C
+    ctx = capi.Context(0)
+    try:
+        # upload: a column whose data buffer exceeds the int32 range is refused before anything is copied
+        off = np.zeros(2, np.int32)
+        col = capi.Column(capi.STRING, 1, 0, None, None, off, np.zeros(1, np.uint8)).as_struct()
+        col.data_len = (1 << 31) + 5
+        arr = (capi.RvlColumn * 1)(col)
+        out = C.c_void_p()
+        assert capi.lib().rvl_batch_upload(ctx._h, arr, 1, C.byref(out)) == capi.OFFSET_OVERFLOW
+        # concat: two batches of ~1.1 GB of string bytes each are fine alone, their concatenation is not
+        spec = [(capi.SYNTH_STR, 1, 0)]
+        a = ctx.gen_batch(spec, 46_000_000, 0)
+        b = ctx.gen_batch(spec, 46_000_000, 46_000_000)
+        assert a.view(0).data_len + b.view(0).data_len > (1 << 31)
+        with pytest.raises(capi.RivulusError) as ei:
+            ctx.concat([a, b])
+        assert ei.value.status == capi.OFFSET_OVERFLOW
+        # ... while a concatenation that references fewer bytes than the buffers hold succeeds (data_len is only an upper bound)
+        ok = ctx.concat([a.slice(0, 1000), b.slice(5, 1000)])
+        assert ok.num_rows() == 2000
+        b.release()
+        # take: indices that repeat rows until the gathered bytes pass 2 GiB (the wrapped int32 total would be positive again)
+        small = a.slice(0, 1_000_000)
+        idx = np.tile(np.arange(1_000_000, dtype=np.int64), 190)     # ~190 x 24 MB = 4.5 GB
+        with pytest.raises(capi.RivulusError) as ei:
+            small.take(idx)
+        assert ei.value.status == capi.OFFSET_OVERFLOW
     finally:
         ctx.close()

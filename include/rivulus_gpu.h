@@ -134,15 +134,21 @@ typedef enum rvl_plan { RVL_PLAN_AUTO = 0, RVL_PLAN_FUSED = 1, RVL_PLAN_TWO_PASS
 typedef enum rvl_option {
     RVL_OPT_PLAN = 0,               /* rvl_plan */
     RVL_OPT_TWO_PASS_MIN_ROWS = 1,  /* default 2 Mi rows */
-    RVL_OPT_SPARSE_MAX = 2,         /* two-pass: 2048-row tiles with <= this many survivors are gathered (0..256, default 224 = 11 %) */
+    RVL_OPT_SPARSE_MAX = 2,         /* two-pass: 2048-row tiles with <= this many survivors are gathered (0..640) */
     RVL_OPT_DENSE_SLOTS = 3,        /* two-pass: 16 KB ring slots per CTA of the dense kernel (2..14) */
     RVL_OPT_DENSE_CTAS_PER_SM = 4,  /* 1 or 2 */
     RVL_OPT_SCAN_SLOTS = 5,         /* two-pass: ring slots per warp of the predicate scan (1..3) */
     RVL_OPT_SCAN_WARPS = 6,         /* two-pass: warps per CTA of the predicate scan (8 or 16) */
     RVL_OPT_DENSE_WARPS = 7,        /* two-pass: consumer warps per CTA of the dense kernel (8 or 16; 16 implies one CTA per SM) */
     RVL_OPT_BITS_OVERLAP = 8,       /* two-pass: run the bit-packed compaction kernel on a forked stream under the 8-byte kernels (default 1) */
-    RVL_OPT_EXACT_ALLOC = 9         /* blocking rvl_filter_project, two-pass plan: read the survivor count (and string bytes) back after the
-                                       predicate scan and allocate the outputs at their exact size instead of min(n, limit) rows (default 1) */
+    RVL_OPT_STRING_KERNEL = 10,     /* String compaction kernels: 1 = round-1 pair (CTA-per-tile sizes + gather from global memory),
+                                       2 = persistent ranges sizes pass + TMA-staged gather (default) */
+    RVL_OPT_STRING_DENSE_MIN = 11,  /* kernel 2: 1024-row sub-tiles with at least this many survivors fetch their whole source byte block
+                                       with one TMA bulk copy (default 128); sparser ones read only the survivors' words */
+    RVL_OPT_EXACT_ALLOC = 9,        /* blocking rvl_filter_project, two-pass plan: read the survivor count (and string bytes) back after the
+                                       predicate scan and allocate the outputs at their exact size instead of min(n, limit) rows.
+                                       0 = never, 1 = always, 2 = only when the worst case exceeds a quarter of device memory (default) */
+    RVL_OPT__COUNT = 12
 } rvl_option;
 int32_t rvl_ctx_set_option(rvl_ctx* ctx, int32_t option, int64_t value);
 

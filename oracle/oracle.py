@@ -238,6 +238,12 @@ class Expr:
     def or_(self, o): return self._bin("or", o)
 
 
+def set_extensions(on: bool) -> None:
+    """Opt-in extension (off = reference behaviour): And / Or over comparison leaves in collect() and collect_streaming(),
+    comparison predicates in collect_streaming().  See rivulus_oracle.hpp for the definition the oracle restates."""
+    lib().orc_set_extensions(1 if on else 0)
+
+
 def col(name) -> Expr:
     return Expr(lib().orc_expr_col(name.encode()))
 

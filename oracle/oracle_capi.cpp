@@ -115,6 +115,7 @@ void* orc_lf_select(void* lf, int n, void** exprs) {
 void* orc_lf_filter(void* lf, void* pred) { return new LazyFrame(((LazyFrame*)lf)->filter(*(Expr*)pred)); }
 void* orc_lf_limit(void* lf, int64_t n) { return new LazyFrame(((LazyFrame*)lf)->limit((size_t)n)); }
 void orc_lf_free(void* lf) { delete (LazyFrame*)lf; }
+void orc_set_extensions(int on) { set_extensions(on != 0); }
 int orc_lf_collect(void* lf, void** df_out) {
     return guard([&] { *df_out = new DataFrame(((LazyFrame*)lf)->collect()); });
 }

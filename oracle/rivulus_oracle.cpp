@@ -926,12 +926,40 @@ static FilterSpec convert_filter_predicate(const Expr& p) {  // planner.rs:134-1
     return {p.left->name, p.right->value, p.op};
 }
 
+// ---- extension: And / Or over comparison leaves (see rivulus_oracle.hpp)
+static bool g_extensions = false;
+void set_extensions(bool on) { g_extensions = on; }
+bool extensions_enabled() { return g_extensions; }
+static bool is_compound(const Expr& p) { return p.kind == Expr::Binary && (p.op == BinaryOperator::And || p.op == BinaryOperator::Or); }
+// every leaf must have the shape the reference accepts for a whole predicate (planner.rs:152-186): same checks, same errors
+static void check_predicate_tree(const Expr& p) {
+    if (is_compound(p)) { check_predicate_tree(*p.left); check_predicate_tree(*p.right); return; }
+    convert_filter_predicate(p);
+}
+static void leaf_columns(const Expr& p, std::vector<std::string>& out) {
+    if (is_compound(p)) { leaf_columns(*p.left, out); leaf_columns(*p.right, out); return; }
+    out.push_back(p.left->name);
+}
+// value_of(column) -> AnyValue of the current row
+template <class F>
+static bool eval_predicate_tree(const Expr& p, F&& value_of) {
+    if (is_compound(p)) {
+        const bool l = eval_predicate_tree(*p.left, value_of), r = eval_predicate_tree(*p.right, value_of);
+        return p.op == BinaryOperator::And ? (l && r) : (l || r);
+    }
+    return eval_cmp(value_of(p.left->name), p.op, p.right->value);
+}
+
 // Lowering checks happen for the whole tree before any execution (planner.rs:41-111 runs first).
 static void check_lowering(const LogicalPlan& p) {
     switch (p.kind) {
         case LogicalPlan::DataFrameSource: return;
         case LogicalPlan::Select: check_lowering(*p.input); for (const auto& e : p.expressions) convert_select_expr(e); return;
-        case LogicalPlan::Filter: check_lowering(*p.input); convert_filter_predicate(p.predicate); return;
+        case LogicalPlan::Filter:
+            check_lowering(*p.input);
+            if (g_extensions && is_compound(p.predicate)) check_predicate_tree(p.predicate);
+            else convert_filter_predicate(p.predicate);
+            return;
         case LogicalPlan::Limit: check_lowering(*p.input); return;
     }
 }
@@ -956,11 +984,19 @@ static DataFrame exec_node(const LogicalPlan& p) {  // physical_plan/plan.rs:65-
         }
         case LogicalPlan::Filter: {                      // :97-150
             DataFrame in = exec_node(*p.input);
+            std::vector<bool> mask; mask.reserve(in.height());
+            if (g_extensions && is_compound(p.predicate)) {
+                std::vector<std::string> cols;
+                leaf_columns(p.predicate, cols);
+                for (const auto& c : cols) if (!in.column(c)) throw OracleError("Column not found: '" + c + "'");
+                for (size_t i = 0; i < in.height(); ++i)
+                    mask.push_back(eval_predicate_tree(p.predicate, [&](const std::string& c) -> const AnyValue& { return in.column(c)->data()[i]; }));
+            } else {
             FilterSpec f = convert_filter_predicate(p.predicate);
             const Series* fs = in.column(f.column);
             if (!fs) throw OracleError("Column not found: '" + f.column + "'");
-            std::vector<bool> mask; mask.reserve(in.height());
             for (const auto& rv : fs->data()) mask.push_back(eval_cmp(rv, f.op, f.value));  // :112-130
+            }
             std::vector<Series> out;
             for (const auto& s : in.columns()) {         // :132-147
                 std::vector<AnyValue> kept;
@@ -1011,9 +1047,34 @@ StreamingPhysicalPlan StreamingPhysicalPlan::dataframe_source(DataFrame df, size
 StreamingPhysicalPlan StreamingPhysicalPlan::filter(std::string col) const {
     StreamingPhysicalPlan p; p.kind = Filter; p.input = std::make_shared<StreamingPhysicalPlan>(*this); p.predicate_column = std::move(col); return p;
 }
+StreamingPhysicalPlan StreamingPhysicalPlan::filter_expr(Expr predicate) const {
+    StreamingPhysicalPlan p; p.kind = FilterExpr; p.input = std::make_shared<StreamingPhysicalPlan>(*this); p.predicate = std::move(predicate); return p;
+}
 StreamingPhysicalPlan StreamingPhysicalPlan::select(std::vector<std::string> cols) const {
     StreamingPhysicalPlan p; p.kind = Select; p.input = std::make_shared<StreamingPhysicalPlan>(*this); p.columns = std::move(cols); return p;
 }
+
+namespace {
+// extension: FilterStream over a predicate tree instead of a Boolean column; the mask it builds has no nulls
+struct FilterExprStream : DataStream {
+    DataStreamRef input; Expr pred;
+    SchemaRef schema() const override { return input->schema(); }
+    std::optional<RecordBatch> next_batch() override {
+        auto b = input->next_batch();
+        if (!b) return std::nullopt;
+        std::vector<std::string> cols;
+        leaf_columns(pred, cols);
+        for (const auto& c : cols)
+            if (!b->schema->index_of(c)) throw OracleError("Stream execution error: Column '" + c + "' not found in schema");
+        std::vector<std::optional<bool>> mask;
+        mask.reserve(b->num_rows);
+        for (size_t i = 0; i < b->num_rows; ++i)
+            mask.push_back(eval_predicate_tree(pred, [&](const std::string& c) { return array_value(*b->columns[*b->schema->index_of(c)], i); }));
+        try { return b->filter(BooleanArray::make(mask)); }
+        catch (const OracleError& e) { throw OracleError(std::string("Stream execution error: ") + e.what()); }
+    }
+};
+}  // namespace
 StreamingPhysicalPlan StreamingPhysicalPlan::limit(size_t n) const {
     StreamingPhysicalPlan p; p.kind = Limit; p.input = std::make_shared<StreamingPhysicalPlan>(*this); p.n = n; return p;
 }
@@ -1031,6 +1092,7 @@ DataStreamRef StreamingPhysicalPlan::execute() const {  // streaming.rs:70-133
             return memory_stream(s, std::move(b));
         }
         case Filter: return filter_stream(input->execute(), predicate_column);
+        case FilterExpr: { auto st = std::make_unique<FilterExprStream>(); st->input = input->execute(); st->pred = predicate; return st; }
         case Select: {
             auto in = input->execute();
             try { return select_stream(std::move(in), columns); }
@@ -1078,6 +1140,12 @@ StreamingPhysicalPlan logical_to_streaming(const LogicalPlan& plan) {  // stream
             auto in = logical_to_streaming(*plan.input);
             const Expr& p = plan.predicate;
             if (p.kind == Expr::Column) return in.filter(p.name);
+            if (p.kind == Expr::Binary && g_extensions) {
+                // extension: comparison leaves and And / Or over them; a malformed leaf raises the eager planner's message
+                try { check_predicate_tree(p); }
+                catch (const OracleError& e) { throw OracleError(std::string("Streaming planner error: Expression conversion error: ") + e.what()); }
+                return in.filter_expr(p);
+            }
             if (p.kind == Expr::Binary) {
                 if (p.left->kind == Expr::Column)
                     throw OracleError("Streaming planner error: Expression conversion error: Binary expressions not yet supported in streaming mode. "

@@ -280,8 +280,22 @@ LogicalPlan optimize(LogicalPlan plan);  // optimizer.rs:7-64
 DataFrame execute_eager(const LogicalPlan& optimized);       // planner.rs:41-189 + physical_plan/plan.rs:65-173
 
 // physical_plan/streaming.rs:28-133, 235-243, 290-333
+// ---------------------------------------------------------------------------------------------
+// OPT-IN EXTENSION, off by default: both reference executors reject And / Or predicates
+// (planner.rs:146-150) and the streaming planner rejects every comparison (streaming_planner.rs:137-168).  With
+// set_extensions(true) a filter predicate may be a tree of And / Or over `column <op> literal` leaves, in collect() and in
+// collect_streaming().  Each leaf is evaluated with the eager truth table (plan.rs:114-120 over series.rs:87-117: a Null row
+// is Less than any literal, different types never compare) and yields true / false; And / Or combine those two-valued results.
+// The streaming engine evaluates the leaves on the RecordBatch arrays as dataframe_to_batches left them (numeric / Boolean
+// nulls already flattened to 0 / false, streaming.rs:177,188,212).  There is no reference behaviour to match here: this
+// oracle restates the DEFINITION above so the GPU host layer can be checked against it.
+// ---------------------------------------------------------------------------------------------
+void set_extensions(bool on);
+bool extensions_enabled();
+
 struct StreamingPhysicalPlan {
-    enum Kind { MemorySource, DataFrameSource, Filter, Select, Limit } kind = MemorySource;
+    enum Kind { MemorySource, DataFrameSource, Filter, Select, Limit, FilterExpr } kind = MemorySource;
+    Expr predicate;                            // FilterExpr (extension)
     std::vector<RecordBatch> batches;          // MemorySource
     DataFrame df; size_t batch_size = 0;       // DataFrameSource
     std::shared_ptr<StreamingPhysicalPlan> input;
@@ -291,6 +305,7 @@ struct StreamingPhysicalPlan {
     static StreamingPhysicalPlan memory_source(std::vector<RecordBatch> b);
     static StreamingPhysicalPlan dataframe_source(DataFrame df, size_t batch_size);
     StreamingPhysicalPlan filter(std::string col) const;
+    StreamingPhysicalPlan filter_expr(Expr predicate) const;   // extension
     StreamingPhysicalPlan select(std::vector<std::string> cols) const;
     StreamingPhysicalPlan limit(size_t n) const;
     DataStreamRef execute() const;                    // :70-133

@@ -33,7 +33,7 @@ namespace rvl {
 
 constexpr int kCompactMaxWarps = 16;                      // consumer warps of the dense kernel: 8 (256 rows each per tile) or 16 (128 rows)
 constexpr uint32_t kSlotBytes = kTileRows * 8;            // one column tile
-constexpr int kSparseCap = 256;                           // most survivors a "sparse" tile may hold
+constexpr int kSparseCap = 640;                           // most survivors a "sparse" tile may hold
 constexpr int kMaxBitSrc = kMaxCol8;                      // bitmaps a dense launch reads: the validity of each 8-byte column
 
 struct CompactParams {
@@ -352,7 +352,7 @@ static __global__ void __launch_bounds__(kBlock) gather_sparse_kernel(const __gr
                     const int64_t row = row0 + rows[e];
                     bool ok = true;
                     if (col.valid.words != nullptr) { const uint64_t bit = col.valid.bit0 + (uint64_t)row; ok = (__ldg(col.valid.words + (bit >> 5)) >> (bit & 31)) & 1u; }
-                    if (ok) v[u] = ld_stream(col.in + row);  // placeholder 0 under a null (primitive.rs:175-178)
+                    if (ok) v[u] = ld_gather(col.in + row);  // 64-byte DRAM granule; placeholder 0 under a null (primitive.rs:175-178)
                     dst[u] = col.out + obase + e;
                 }
             }

@@ -29,6 +29,14 @@ __device__ __forceinline__ uint64_t ld_stream(const uint64_t* p) {
     asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(r) : "l"(p));
     return r;
 }
+// Isolated gather load: B200 fetches the whole 128-byte line from DRAM for an ordinary load that misses L2, and 64 bytes when the
+// load carries the .L2::64B prefetch-size qualifier (profiles/r02_microbench_sector.txt: 128 / 64 bytes of dram__bytes_read per
+// touched sector; nothing fetches a lone 32-byte sector).  Sparse survivors therefore cost half the DRAM traffic through this one.
+__device__ __forceinline__ uint64_t ld_gather(const uint64_t* p) {
+    uint64_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.u64 %0, [%1];" : "=l"(r) : "l"(p));
+    return r;
+}
 // streaming (evict-first) stores for outputs that are never re-read by this kernel
 __device__ __forceinline__ void st_stream(uint64_t* p, uint64_t v) {
     asm volatile("st.global.cs.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");

@@ -224,11 +224,12 @@ int fp_init_device(int device) {
     RVL_TRY(scan_opt_in<kPredTrue>());
     RVL_CUDA_TRY(cudaFuncSetAttribute(compact_dense_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmemMax));
     RVL_CUDA_TRY(cudaFuncSetAttribute(compact_dense_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmemMax));
+    RVL_CUDA_TRY(cudaFuncSetAttribute(string_gather_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StrSmem)));
     return RVL_OK;
 }
 
 static int launch_compaction(const CoreRef& core, CompactParams cp, const uint32_t* dense_list, const uint32_t* sparse_list,
-                             const uint32_t* list_counts) {
+                             const uint32_t* list_counts, cudaStream_t bits_stream) {
     const int warps = core->dense_warps == 16 ? 16 : 8;
     const int per_sm = warps == 16 ? 1 : std::max(1, std::min(2, core->dense_ctas_per_sm));
     // every bitmap the dense kernel reads, listed once (staged ahead by its consumer warps)
@@ -242,22 +243,9 @@ static int launch_compaction(const CoreRef& core, CompactParams cp, const uint32
     const int smem_budget = (per_sm == 1 ? kDenseSmemMax : 110 * 1024) - (int)dense_stage_bytes(warps, cp.n_bsrc);
     const int max_slots = std::min(14, smem_budget / (int)(kSlotBytes + 16));
     cp.n_slots = std::max(2, std::min(max_slots, core->dense_slots));
-    // The bit-packed columns (validity bitmaps, Boolean values) are compacted by an instruction-bound kernel that barely touches
-    // DRAM; the 8-byte columns by HBM-bound ones.  They write disjoint buffers and both only read what pass 1 left, so the bit kernel
-    // is forked onto the context's side stream and runs underneath the dense / sparse kernels instead of after them.
-    const bool fork = cp.n_bits > 0 && cp.n_col8 > 0 && core->side_stream != nullptr && core->bits_overlap;
-    cudaStream_t bits_stream = core->stream;
-    if (fork) {
-        cudaEvent_t ev = core->take_event();
-        if (ev == nullptr) return fail(RVL_CUDA, "cudaEventCreate failed");
-        cudaError_t e = cudaEventRecord(ev, core->stream);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(core->side_stream, ev, 0);
-        core->give_event(ev);
-        RVL_CUDA_TRY(e);
-        bits_stream = core->side_stream;
-    }
     if (cp.n_bits > 0) {
-        // one warp per tile
+        // bit-packed columns (validity bitmaps, Boolean values) of every tile: one warp per tile; instruction-bound, barely touches
+        // DRAM, so the caller forks it onto the side stream where it runs underneath the HBM-bound kernels below
         const int64_t n_tiles = (cp.n_rows + kTileRows - 1) / kTileRows;
         const int64_t ctas = std::max<int64_t>(1, std::min<int64_t>((n_tiles + kWarps - 1) / kWarps, (int64_t)core->sm_count * 8));
         compact_bits_kernel<<<(unsigned)ctas, kBlock, 0, bits_stream>>>(cp);
@@ -273,14 +261,70 @@ static int launch_compaction(const CoreRef& core, CompactParams cp, const uint32
         core->launches++;
         RVL_CUDA_TRY(cudaGetLastError());
     }
-    if (fork) {
-        cudaEvent_t ev = core->take_event();
-        if (ev == nullptr) return fail(RVL_CUDA, "cudaEventCreate failed");
-        cudaError_t e = cudaEventRecord(ev, core->side_stream);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(core->stream, ev, 0);
-        core->give_event(ev);
-        RVL_CUDA_TRY(e);
+    return RVL_OK;
+}
+
+// order `to` behind everything enqueued on `from` so far
+static int stream_after(const CoreRef& core, cudaStream_t from, cudaStream_t to) {
+    cudaEvent_t ev = core->take_event();
+    if (ev == nullptr) return fail(RVL_CUDA, "cudaEventCreate failed");
+    cudaError_t e = cudaEventRecord(ev, from);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(to, ev, 0);
+    core->give_event(ev);
+    RVL_CUDA_TRY(e);
+    return RVL_OK;
+}
+
+int str_prepare_sizes(const CoreRef& core, StrGatherParams& sp, const DevColumn& src, std::vector<BufRef>* keep) {
+    const int64_t tiles = (sp.n_rows + kTileRows - 1) / kTileRows;
+    if (tiles <= 0) return RVL_OK;
+    if (core->string_kernel == 1) {
+        BufRef tbytes;   // per-tile survivor bytes -> exclusive prefixes; last word = ticket counter of the sizes kernel
+        RVL_TRY(dev_alloc(core, (size_t)(tiles + 1) * 8, &tbytes));
+        RVL_CUDA_TRY(cudaMemsetAsync((uint64_t*)tbytes->ptr + tiles, 0, 8, core->stream));
+        keep->push_back(tbytes);
+        sp.tile_bytes = (uint64_t*)tbytes->ptr;
+    } else {
+        // every warp of a persistent grid owns a contiguous range of tiles
+        const int ctas = (int)std::max<int64_t>(1, std::min<int64_t>((tiles + kWarps - 1) / kWarps, std::min(384, 2 * core->sm_count)));
+        sp.n_ranges = ctas * kWarps;
+        sp.tiles_per_range = std::max<int64_t>(1, (tiles + sp.n_ranges - 1) / sp.n_ranges);
+        BufRef sub, ranges;
+        RVL_TRY(dev_alloc(core, (size_t)tiles * 16, &sub));
+        RVL_TRY(dev_alloc(core, (size_t)(sp.n_ranges + 1) * 8, &ranges));
+        RVL_CUDA_TRY(cudaMemsetAsync((uint64_t*)ranges->ptr + sp.n_ranges, 0, 8, core->stream));
+        keep->push_back(sub); keep->push_back(ranges);
+        sp.sub_bytes = (uint64_t*)sub->ptr; sp.range_bytes = (uint64_t*)ranges->ptr;
+        sp.dense_min = (uint32_t)std::max(0, core->string_dense_min);
+        // bytes around the data buffer that may be read: the block a sub-tile stages is rounded to 16-byte boundaries
+        sp.data_lo = src.data ? (const uint8_t*)src.data->ptr : nullptr;
+        sp.data_hi = src.data ? (const uint8_t*)src.data->ptr + src.data->bytes : nullptr;
     }
+    return RVL_OK;
+}
+
+int str_launch_sizes(const CoreRef& core, const StrGatherParams& sp, cudaStream_t stream) {
+    const int64_t tiles = (sp.n_rows + kTileRows - 1) / kTileRows;
+    if (tiles <= 0) return RVL_OK;
+    if (core->string_kernel == 1) string_sizes_kernel<<<(unsigned)tiles, kBlock, 0, stream>>>(sp);
+    else string_sizes_ranges_kernel<<<(unsigned)(sp.n_ranges / kWarps), kBlock, 0, stream>>>(sp);
+    core->launches++;
+    RVL_CUDA_TRY(cudaGetLastError());
+    return RVL_OK;
+}
+
+int str_launch_gather(const CoreRef& core, const StrGatherParams& sp) {
+    const int64_t tiles = (sp.n_rows + kTileRows - 1) / kTileRows;
+    if (tiles <= 0) return RVL_OK;
+    if (core->string_kernel == 1) string_gather_kernel<<<(unsigned)tiles, kBlock, 0, core->stream>>>(sp);
+    else {
+        // persistent: three CTAs per SM, each walks sub-tiles blockIdx.x, blockIdx.x + gridDim.x, ... one iteration ahead of its loads
+        const int64_t subs = (sp.n_rows + kStrRows - 1) / kStrRows;
+        const int64_t ctas = std::max<int64_t>(1, std::min<int64_t>(subs, (int64_t)core->sm_count * 3));
+        string_gather_staged_kernel<<<(unsigned)ctas, kBlock, sizeof(StrSmem), core->stream>>>(sp);
+    }
+    core->launches++;
+    RVL_CUDA_TRY(cudaGetLastError());
     return RVL_OK;
 }
 
@@ -349,10 +393,10 @@ int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pre
     // ---- outputs + work lists.  Sized for `cap` rows; string bytes for the viewed window (or, in exact mode, the survivors' bytes).
     std::vector<Col8> col8s;
     std::vector<BitCol> bitcols;
-    struct StrJob { int out_index; const DevColumn* src; BufRef tbytes; };
+    struct StrJob { int out_index; const DevColumn* src; StrGatherParams sp; };
     std::vector<StrJob> strjobs;
     for (int j = 0; j < nproj; ++j)
-        if (in->cols[proj[j]].dtype == RVL_STRING) strjobs.push_back(StrJob{j, &in->cols[proj[j]], nullptr});
+        if (in->cols[proj[j]].dtype == RVL_STRING) strjobs.push_back(StrJob{j, &in->cols[proj[j]], StrGatherParams{}});
     int64_t cap_alloc = cap_worst;
     auto alloc_outputs = [&](int64_t cap, const uint64_t* exact_counters) -> int {
         cap_alloc = cap;
@@ -401,36 +445,30 @@ int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pre
         if (!strjobs.empty() || two_pass) { RVL_TRY(dev_alloc(core, (size_t)tiles * 8, &tile_prefix)); pend->temps.push_back(tile_prefix); }
 
         // string columns: the per-tile byte prefixes (first kernel of the pair) only need pass 1's selection bitmap
-        auto str_params = [&](const StrJob& job, int64_t tiles_per_chunk, const BufRef& chunk_base) {
+        auto str_params = [&](StrJob& job, int64_t tiles_per_chunk, const BufRef& chunk_base) {
             const DevColumn& s = *job.src;
             DevColumn& d = pend->outs[(size_t)job.out_index];
-            StrGatherParams sp{};
+            StrGatherParams& sp = job.sp;
             sp.n_rows = n; sp.limit = limit; sp.sel = (const uint32_t*)sel->ptr; sp.tile_prefix = (const uint64_t*)tile_prefix->ptr; sp.row_base = 0;
             if (two_pass) { sp.chunk_base = (const uint64_t*)chunk_base->ptr; sp.tiles_per_chunk = tiles_per_chunk; }
             sp.offsets = (const int32_t*)s.offsets->ptr + s.offset; sp.data = (const uint8_t*)s.data->ptr;
             sp.valid = bitsrc_of(s.validity, s.offset, n);
             sp.out_offsets = d.offsets ? (int32_t*)d.offsets->ptr : nullptr; sp.out_data = d.data ? (uint8_t*)d.data->ptr : nullptr;
-            sp.tile_bytes = (uint64_t*)job.tbytes->ptr; sp.byte_base_in = nullptr; sp.row_base_in = base_in;
+            sp.byte_base_in = nullptr; sp.row_base_in = base_in;
             sp.bytes_total_out = dctr + pend->bytes_counter[(size_t)job.out_index];
-            return sp;
         };
-        auto launch_str_sizes = [&](StrJob& job, int64_t tiles_per_chunk, const BufRef& chunk_base) -> int {
-            // per-tile survivor bytes -> exclusive prefixes; last word = ticket counter of the sizes kernel
-            RVL_TRY(dev_alloc(core, (size_t)(tiles + 1) * 8, &job.tbytes));
-            RVL_CUDA_TRY(cudaMemsetAsync((uint64_t*)job.tbytes->ptr + tiles, 0, 8, core->stream));
-            pend->temps.push_back(job.tbytes);
-            const StrGatherParams sp = str_params(job, tiles_per_chunk, chunk_base);
-            string_sizes_kernel<<<(unsigned)tiles, kBlock, 0, core->stream>>>(sp);
-            core->launches++;
-            RVL_CUDA_TRY(cudaGetLastError());
-            return RVL_OK;
+        // scratch of the sizes pass is allocated on the main stream; the kernel itself may run on the side stream
+        auto prepare_str_sizes = [&](StrJob& job, int64_t tiles_per_chunk, const BufRef& chunk_base) -> int {
+            str_params(job, tiles_per_chunk, chunk_base);
+            return str_prepare_sizes(core, job.sp, *job.src, &pend->temps);
         };
-        auto launch_str_gather = [&](const StrJob& job, int64_t tiles_per_chunk, const BufRef& chunk_base) -> int {
-            const StrGatherParams sp = str_params(job, tiles_per_chunk, chunk_base);
-            string_gather_kernel<<<(unsigned)tiles, kBlock, 0, core->stream>>>(sp);
-            core->launches++;
-            RVL_CUDA_TRY(cudaGetLastError());
-            return RVL_OK;
+        auto launch_str_sizes = [&](StrJob& job, int64_t tiles_per_chunk, const BufRef& chunk_base, cudaStream_t stream) -> int {
+            str_params(job, tiles_per_chunk, chunk_base);
+            return str_launch_sizes(core, job.sp, stream);
+        };
+        auto launch_str_gather = [&](StrJob& job, int64_t tiles_per_chunk, const BufRef& chunk_base) -> int {
+            str_params(job, tiles_per_chunk, chunk_base);   // the output pointers may have been allocated since the sizes launch
+            return str_launch_gather(core, job.sp);
         };
 
         int64_t tiles_per_chunk = 0;
@@ -469,12 +507,23 @@ int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pre
                 // The survivor count (and every string column's survivor bytes) is known after pass 1: read it back and allocate the
                 // outputs at their exact size.  One host round trip (~15 us) against a scan of megabytes to gigabytes; a 0.1 % query
                 // over 10^9 rows then holds 32 MB of output instead of reserving 32 GB.
-                for (StrJob& job : strjobs) RVL_TRY(launch_str_sizes(job, tiles_per_chunk, chunk_base));
+                for (StrJob& job : strjobs) {
+                    RVL_TRY(prepare_str_sizes(job, tiles_per_chunk, chunk_base));
+                    RVL_TRY(launch_str_sizes(job, tiles_per_chunk, chunk_base, core->stream));
+                }
                 RVL_CUDA_TRY(cudaMemcpyAsync(core->mailbox, dctr, (size_t)n_counters * 8, cudaMemcpyDeviceToHost, core->stream));
                 RVL_CUDA_TRY(cudaStreamSynchronize(core->stream));
                 const int64_t total = (int64_t)core->mailbox[0];
                 RVL_TRY(alloc_outputs(std::min(cap_worst, total), core->mailbox));
             }
+            // Everything below only reads what pass 1 left and writes its own buffers.  The HBM-bound kernels (dense / sparse compaction
+            // of the 8-byte columns) stay on the main stream; the instruction- and latency-bound ones — bit-packed columns, the string
+            // sizes pass — are forked onto the side stream and run underneath them; the main stream joins before the string gather.
+            const bool fork = core->bits_overlap && core->side_stream != nullptr && !col8s.empty() && (!bitcols.empty() || (!strjobs.empty() && !exact));
+            if (!exact) for (StrJob& job : strjobs) RVL_TRY(prepare_str_sizes(job, tiles_per_chunk, chunk_base));
+            const cudaStream_t side = fork ? core->side_stream : core->stream;
+            if (fork) RVL_TRY(stream_after(core, core->stream, side));
+            if (!exact) for (StrJob& job : strjobs) RVL_TRY(launch_str_sizes(job, tiles_per_chunk, chunk_base, side));
             for (int L = 0; L < launches_needed; ++L) {
                 CompactParams cp{};
                 cp.n_rows = n; cp.limit = limit; cp.sel = (const uint32_t*)sel->ptr; cp.tile_info = (const uint64_t*)tile_prefix->ptr;
@@ -486,8 +535,9 @@ int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pre
                 const int b0 = L * kMaxBitCols, b1 = std::min<int>((int)bitcols.size(), b0 + kMaxBitCols);
                 cp.n_bits = std::max(0, b1 - b0);
                 for (int k = 0; k < cp.n_bits; ++k) cp.bits[k] = bitcols[(size_t)(b0 + k)];
-                RVL_TRY(launch_compaction(core, cp, dense_list, sparse_list, list_counts));
+                RVL_TRY(launch_compaction(core, cp, dense_list, sparse_list, list_counts, side));
             }
+            if (fork) RVL_TRY(stream_after(core, side, core->stream));
         }
 
         for (int L = 0; L < (two_pass ? 0 : launches_needed); ++L) {
@@ -523,7 +573,10 @@ int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pre
 
         // strings: second kernel pair per column (offset prefix-sum + byte copy)
         for (StrJob& job : strjobs) {
-            if (!exact) RVL_TRY(launch_str_sizes(job, tiles_per_chunk, chunk_base));
+            if (!two_pass) {
+                RVL_TRY(prepare_str_sizes(job, tiles_per_chunk, chunk_base));
+                RVL_TRY(launch_str_sizes(job, tiles_per_chunk, chunk_base, core->stream));
+            }
             RVL_TRY(launch_str_gather(job, tiles_per_chunk, chunk_base));
         }
 
@@ -637,7 +690,23 @@ int32_t rvl_filter_project(rvl_ctx* ctx, const rvl_batch* in, const rvl_predicat
                            int64_t limit, rvl_batch** out) {
     if (!ctx || !out) return fail(RVL_INVALID_ARGUMENT, "null argument");
     FpPending* p = nullptr;
-    RVL_TRY(fp_launch(ctx->core, in, pred, proj, nproj, limit, false, nullptr, nullptr, &p, ctx->core->exact_alloc));
+    // Blocking call: the two-pass plan may wait for the survivor count and size the outputs exactly.  That costs one host round trip
+    // in the middle of the operator (~50 us of idle device), so AUTO only pays it when the worst case — min(n, limit) rows of every
+    // projected column — would pin more than a quarter of the device's memory.
+    bool exact = ctx->core->exact_alloc == 1;
+    if (ctx->core->exact_alloc == 2 && in != nullptr) {
+        const int64_t cap = limit >= 0 ? std::min<int64_t>(in->num_rows, limit) : in->num_rows;
+        size_t worst = 0;
+        for (int j = 0; j < nproj && proj; ++j) {
+            if (proj[j] < 0 || proj[j] >= (int32_t)in->cols.size()) continue;
+            const DevColumn& s = in->cols[proj[j]];
+            if (s.dtype == RVL_INT64 || s.dtype == RVL_FLOAT64) worst += (size_t)cap * 8;
+            else if (s.dtype == RVL_STRING) worst += (size_t)cap * 4 + (size_t)(s.window_bytes >= 0 ? s.window_bytes : s.data_len);
+            else worst += (size_t)cap / 8;
+        }
+        exact = worst > ctx->core->device_bytes / 4;
+    }
+    RVL_TRY(fp_launch(ctx->core, in, pred, proj, nproj, limit, false, nullptr, nullptr, &p, exact));
     return fp_finish(p, out, nullptr);
 }
 

@@ -45,6 +45,14 @@ int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pre
               bool exact = false);
 // one-time per device: opt every kernel instantiation in to its dynamic shared memory size (called by rvl_ctx_create)
 int fp_init_device(int device);
+
+// String compaction = a sizes pass (per-tile survivor byte prefixes) + a gather pass (new offsets + byte copy), string_kernels.cuh.
+// `sp` carries the inputs; the sizes launch allocates the pass's scratch (kept alive through `keep`) and fills the matching fields
+// of `sp`, which the gather launch then reads.  core->string_kernel picks the round-1 pair (1) or the round-2 pair (2).
+struct StrGatherParams;
+int str_prepare_sizes(const CoreRef& core, StrGatherParams& sp, const DevColumn& src, std::vector<BufRef>* keep);   // scratch, on core->stream
+int str_launch_sizes(const CoreRef& core, const StrGatherParams& sp, cudaStream_t stream);
+int str_launch_gather(const CoreRef& core, const StrGatherParams& sp);
 // waits for the launch, builds the output batch (and/or the mask batch); deletes `pend`
 int fp_finish(FpPending* pend, rvl_batch** out, rvl_batch** mask_out);
 // device word holding base + survivors after this launch (valid until the pending object is finished)

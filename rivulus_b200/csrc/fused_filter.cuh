@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(kBlock, 3) fused_filter_project_kernel(const _
                 const int64_t row = super_row0 + wrow[e];
                 bool ok = true;
                 if (col.valid.words != nullptr) { const uint64_t bit = col.valid.bit0 + (uint64_t)row; ok = (__ldg(col.valid.words + (bit >> 5)) >> (bit & 31)) & 1u; }
-                if (ok) v = ld_stream(col.in + row);  // placeholder 0 under a null (primitive.rs:175-178)
+                if (ok) v = ld_gather(col.in + row);  // 64-byte DRAM granule; placeholder 0 under a null (primitive.rs:175-178)
             }
             if (!have) { wait_offset(excl, base0); have = true; }
             if (t < n_task) {

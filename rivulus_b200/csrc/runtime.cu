@@ -156,6 +156,7 @@ int32_t rvl_ctx_create(int32_t device, rvl_ctx** ctx) {
     auto core = std::make_shared<CtxCore>();
     core->device = device;
     core->sm_count = prop.multiProcessorCount;
+    core->device_bytes = prop.totalGlobalMem;
     RVL_CUDA_TRY(cudaStreamCreateWithFlags(&core->stream, cudaStreamNonBlocking));
     RVL_CUDA_TRY(cudaStreamCreateWithFlags(&core->copy_stream, cudaStreamNonBlocking));
     RVL_CUDA_TRY(cudaStreamCreateWithFlags(&core->d2h_stream, cudaStreamNonBlocking));
@@ -213,7 +214,7 @@ int32_t rvl_ctx_set_option(rvl_ctx* ctx, int32_t option, int64_t value) {
             c.plan_mode = (int)value; return RVL_OK;
         case RVL_OPT_TWO_PASS_MIN_ROWS: c.two_pass_min_rows = value; return RVL_OK;
         case RVL_OPT_SPARSE_MAX:
-            if (value < 0 || value > 256) return fail(RVL_INVALID_ARGUMENT, "sparse_max must be in [0, 256]");
+            if (value < 0 || value > 640) return fail(RVL_INVALID_ARGUMENT, "sparse_max must be in [0, 640]");
             c.sparse_max = (int)value; return RVL_OK;
         case RVL_OPT_DENSE_SLOTS:
             if (value < 2 || value > 14) return fail(RVL_INVALID_ARGUMENT, "dense_slots must be in [2, 14]");
@@ -231,7 +232,15 @@ int32_t rvl_ctx_set_option(rvl_ctx* ctx, int32_t option, int64_t value) {
             if (value != 8 && value != 16) return fail(RVL_INVALID_ARGUMENT, "dense_warps must be 8 or 16");
             c.dense_warps = (int)value; return RVL_OK;
         case RVL_OPT_BITS_OVERLAP: c.bits_overlap = value != 0; return RVL_OK;
-        case RVL_OPT_EXACT_ALLOC: c.exact_alloc = value != 0; return RVL_OK;
+        case RVL_OPT_STRING_KERNEL:
+            if (value != 1 && value != 2) return fail(RVL_INVALID_ARGUMENT, "string_kernel must be 1 or 2");
+            c.string_kernel = (int)value; return RVL_OK;
+        case RVL_OPT_STRING_DENSE_MIN:
+            if (value < 0 || value > 1025) return fail(RVL_INVALID_ARGUMENT, "string_dense_min must be in [0, 1025]");
+            c.string_dense_min = (int)value; return RVL_OK;
+        case RVL_OPT_EXACT_ALLOC:
+            if (value < 0 || value > 2) return fail(RVL_INVALID_ARGUMENT, "exact_alloc must be 0 (never), 1 (always) or 2 (auto)");
+            c.exact_alloc = (int)value; return RVL_OK;
         default: return fail(RVL_INVALID_ARGUMENT, "unknown option");
     }
 }
@@ -684,7 +693,7 @@ int32_t rvl_batch_concat(rvl_ctx* ctx, const rvl_batch* const* batches, int32_t 
         if (any_validity && d.dtype != RVL_NULL) RVL_TRY(dev_alloc_zeroed(core, (size_t)(total + 7) / 8, &d.validity));
         if (d.dtype == RVL_INT64 || d.dtype == RVL_FLOAT64) RVL_TRY(dev_alloc(core, (size_t)total * 8, &d.values));
         if (d.dtype == RVL_BOOLEAN) RVL_TRY(dev_alloc_zeroed(core, (size_t)(total + 7) / 8, &d.values));
-        BufRef status, chain;
+        BufRef chain;
         int chain_k = 0;
         if (d.dtype == RVL_STRING) {
             int64_t cap = 0;
@@ -706,10 +715,6 @@ int32_t rvl_batch_concat(rvl_ctx* ctx, const rvl_batch* const* batches, int32_t 
             RVL_TRY(dev_alloc(core, (size_t)(total + 1) * 4, &d.offsets));
             RVL_CUDA_TRY(cudaMemsetAsync(d.offsets->ptr, 0, 4, core->stream));
             RVL_TRY(dev_alloc(core, (size_t)cap, &d.data));
-            int64_t max_tiles = 1;
-            for (int b = 0; b < n; ++b) max_tiles = std::max<int64_t>(max_tiles, (batches[b]->num_rows + kTileRows - 1) / kTileRows);
-            RVL_TRY(dev_alloc(core, (size_t)(max_tiles + 1) * 8, &status));   // per-tile byte prefixes + the sizes kernel's ticket word
-            keep_alive.push_back(status);
             RVL_TRY(dev_alloc_zeroed(core, (size_t)(n + 1) * 8, &chain));      // bytes emitted before each part
             keep_alive.push_back(chain);
         }
@@ -733,19 +738,16 @@ int32_t rvl_batch_concat(rvl_ctx* ctx, const rvl_batch* const* batches, int32_t 
                     bitsrc_of(s.values, s.offset, m), sv, (uint32_t*)d.values->ptr, (uint64_t)row_base, m);
                 core->launches++;
             } else if (d.dtype == RVL_STRING) {
-                const int64_t tiles = (m + kTileRows - 1) / kTileRows;
-                RVL_CUDA_TRY(cudaMemsetAsync((uint64_t*)status->ptr + tiles, 0, 8, core->stream));
                 StrGatherParams sp{};
                 sp.n_rows = m; sp.limit = -1; sp.sel = nullptr; sp.tile_prefix = nullptr; sp.row_base = row_base;
                 sp.offsets = (const int32_t*)s.offsets->ptr + s.offset; sp.data = (const uint8_t*)s.data->ptr; sp.valid = sv;
                 sp.out_offsets = (int32_t*)d.offsets->ptr; sp.out_data = (uint8_t*)d.data->ptr;
                 unsigned long long* ch = (unsigned long long*)chain->ptr;
-                sp.tile_bytes = (uint64_t*)status->ptr; sp.byte_base_in = ch + chain_k; sp.bytes_total_out = ch + chain_k + 1;
+                sp.byte_base_in = ch + chain_k; sp.bytes_total_out = ch + chain_k + 1;
                 ++chain_k;
-                string_sizes_kernel<<<(unsigned)tiles, kBlock, 0, core->stream>>>(sp);
-                core->launches++;
-                string_gather_kernel<<<(unsigned)tiles, kBlock, 0, core->stream>>>(sp);
-                core->launches++;
+                RVL_TRY(str_prepare_sizes(core, sp, s, &keep_alive));
+                RVL_TRY(str_launch_sizes(core, sp, core->stream));
+                RVL_TRY(str_launch_gather(core, sp));
             }
             if (d.validity) {
                 bitcopy_kernel<<<grid_for((m + 31) / 32 + 1, 256, core->sm_count), 256, 0, core->stream>>>(

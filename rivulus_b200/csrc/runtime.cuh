@@ -51,7 +51,10 @@ struct CtxCore {
     cudaStream_t d2h_stream = nullptr;   // downloads of finished batches (overlaps H2D staging and kernels)
     cudaStream_t side_stream = nullptr;  // forked from `stream` for the bit-packed compaction kernel (runs under the HBM-bound ones)
     bool bits_overlap = true;            // RVL_OPT_BITS_OVERLAP
-    bool exact_alloc = true;             // RVL_OPT_EXACT_ALLOC: blocking rvl_filter_project sizes two-pass outputs from the scan's count
+    int string_kernel = 2;               // RVL_OPT_STRING_KERNEL: 1 = round-1 kernel pair, 2 = ranges sizes pass + TMA-staged gather
+    int string_dense_min = 128;          // RVL_OPT_STRING_DENSE_MIN: survivors per 1024-row sub-tile from which the source block is TMA-staged
+    int exact_alloc = 2;                 // RVL_OPT_EXACT_ALLOC: 0 never, 1 always, 2 when the worst case exceeds a quarter of device memory
+    size_t device_bytes = 0;
     // optional kernel-level timing of the fused kernel (rvl_ctx_profile_*)
     bool profile = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -61,7 +64,8 @@ struct CtxCore {
     // execution plan of the fused operator (rvl_ctx_set_option)
     int plan_mode = 0;                      // RVL_PLAN_AUTO / _FUSED / _TWO_PASS
     int64_t two_pass_min_rows = 2 << 20;    // AUTO: batches at least this large take the two-pass plan (measured crossover: equal at 2 Mi rows, 1.3x at 4 Mi)
-    int sparse_max = 224;                   // two-pass: tiles with <= this many survivors (of 2048 rows) are gathered
+    int sparse_max = 384;                   // two-pass: tiles with <= this many survivors (of 2048 rows) are gathered (64-byte-granule loads;
+                                            //   measured crossover ~20 % with them, profiles/r02_sparse_max_sweep.txt; 11 % without)
     int dense_slots = 14;                   // two-pass: 16 KB ring slots per CTA of the dense compaction kernel
     int dense_ctas_per_sm = 1;
     int dense_warps = 16;                   // two-pass: consumer warps per CTA of the dense kernel (8 or 16)

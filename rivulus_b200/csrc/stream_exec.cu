@@ -111,6 +111,7 @@ struct rvl_stream {
     int64_t pushed = 0, skipped = 0, h2d_bytes = 0, groups = 0;
     bool limit_hit = false;
     int64_t rows_out = 0;              // rows of the finished outputs
+    int64_t rows_seen = 0;             // newest running survivor total that has landed in a mailbox (LIMIT group sizing)
     // the open group: pushed batches appended to slot `next_slot`, operator not launched yet
     bool open = false;
     int64_t open_rows = 0, open_target = 0;
@@ -187,6 +188,7 @@ void poll_selectivity(rvl_stream* s) {
         const uint64_t base = it->pend->chained ? mb[it->pend->n_counters] : 0ull;
         if (base == kMailboxPending || base > total) continue;
         s->recent_sel = (double)(total - base) / (double)it->rows;
+        s->rows_seen = std::max<int64_t>(s->rows_seen, (int64_t)total);
         return;
     }
 }
@@ -199,6 +201,7 @@ int finish_oldest(rvl_stream* s, rvl_batch** out) {
     RVL_TRY(fp_finish(f.pend, &b, nullptr));
     if (f.rows > 0) s->recent_sel = (double)b->num_rows / (double)f.rows;
     s->rows_out += b->num_rows;
+    s->rows_seen = std::max(s->rows_seen, s->rows_out);
     if (s->limit >= 0 && s->rows_out >= s->limit) s->limit_hit = true;
     *out = b;
     return RVL_OK;
@@ -398,6 +401,19 @@ int32_t rvl_stream_push(rvl_stream* s, const rvl_column* cols, int32_t ncols, in
             RVL_CUDA_TRY(cudaEventSynchronize(sl0.free_ev));
             poll_limit(s);
         }
+        if (!s->limit_hit && s->limit > 0 && s->groups >= 1 && s->recent_sel > 0.0) {
+            // the groups still in flight are expected to satisfy the limit on their own: wait for their counts instead of
+            // transferring another group that a LimitStream would never have pulled
+            int64_t pending_rows = 0;
+            for (const InFlight& f : s->inflight)
+                if (*reinterpret_cast<volatile uint64_t*>(f.pend->mailbox) == kMailboxPending) pending_rows += f.rows;
+            if (pending_rows > 0 && (double)s->rows_seen + 0.8 * s->recent_sel * (double)pending_rows >= (double)s->limit) {
+                const int64_t n_slots = (int64_t)s->slots.size();
+                Slot& w = s->slots[(size_t)((((int64_t)s->next_slot - 1) % n_slots + n_slots) % n_slots)];
+                if (w.used) RVL_CUDA_TRY(cudaEventSynchronize(w.free_ev));
+                poll_limit(s);
+            }
+        }
         if (!s->limit_hit && s->limit > 0 && s->groups >= 1) {
             // LIMIT streams start slowly: group 1 waits for group 0's count, groups 2 and 3 for the group two before them; only then
             // does the pipeline run at its full depth.  A limit that the first batches already satisfy (LIMIT 1000 over 64 K..1 M-row
@@ -421,7 +437,16 @@ int32_t rvl_stream_push(rvl_stream* s, const rvl_column* cols, int32_t ncols, in
         if (s->limit > 0) {
             const int64_t g = s->groups;
             const int64_t nb = g <= 1 ? 1 : (g >= 40 ? ((int64_t)1 << 39) : ((int64_t)1 << (g - 1)));
-            s->open_target = std::min<int64_t>(s->batch_rows, std::max<int64_t>(n, 1) * nb);
+            int64_t target = std::max<int64_t>(n, 1) * nb;
+            // once a count has arrived the rows still needed are known to within the selectivity's noise: ask for 1.25x that,
+            // so a 0.1 % stream over 64 K-row batches pulls ~17 batches for LIMIT 1000 instead of doubling past it
+            poll_selectivity(s);
+            if (s->recent_sel > 0.0) {
+                const double need = (double)std::max<int64_t>(s->limit - s->rows_seen, 1) / s->recent_sel * 1.25;
+                if (need < (double)target) target = std::max<int64_t>((int64_t)need, n);
+                else if (need < 4.0e18) target = std::max<int64_t>(target, std::min<int64_t>((int64_t)need, s->batch_rows));
+            }
+            s->open_target = std::min<int64_t>(s->batch_rows, target);
         }
         for (int c = 0; c < ncols; ++c) {
             GroupCol& g = s->gcols[(size_t)c];

@@ -16,7 +16,7 @@
 // ~10 us per tile, every tile waited on the slowest of its predecessors — the look-back cost 0.2 ms of a 0.65 ms launch.)
 // UTF-8 validity is preserved by construction (whole strings are copied), so no re-validation pass.
 #pragma once
-#include "device_utils.cuh"
+#include "fused_filter.cuh"   // TMA 1-D bulk copy + mbarrier helpers
 
 namespace rvl {
 
@@ -38,6 +38,14 @@ struct StrGatherParams {
                                         //   word is the ticket counter of that kernel (zeroed before launch)
     const unsigned long long* byte_base_in;  // bytes already emitted before this launch (concat), or nullptr
     unsigned long long* bytes_total_out;     // byte base + bytes emitted by this launch
+    // ---- round-2 kernels (string_sizes_ranges_kernel / string_gather_staged_kernel): 1024-row sub-tiles
+    uint64_t* sub_bytes;                // [2 * n_tiles]: survivor bytes in front of each sub-tile inside its warp range
+    uint64_t* range_bytes;              // [n_ranges + 1]: global byte base of each warp range (last CTA scans them); [n_ranges] = ticket
+    int64_t tiles_per_range;            // sizes kernel: tiles per warp range
+    int32_t n_ranges;
+    uint32_t dense_min;                 // sub-tiles with at least this many survivors stream their whole source block through shared memory
+    const uint8_t* data_lo;             // readable bounds of the data buffer (the TMA block is rounded to 16 bytes inside them)
+    const uint8_t* data_hi;
 };
 
 // exclusive scan of one uint32 per thread across the 256-thread block; returns the thread's prefix, sets total
@@ -397,6 +405,477 @@ static __global__ void __launch_bounds__(kBlock, 6) string_gather_kernel(const _
             }
         }
         __syncthreads();
+    }
+}
+
+// =====================================================================================================================
+// Round-2 string kernels.  What round 1's ncu said about the pair above: the gather is instruction- and LSU-bound (~1000 warp
+// instructions per warp and tile, every source word a divergent, bounds-checked LDG), the sizes pass is 24 K short CTAs plus a serial
+// ticketed prefix tail.  Changes:
+//   string_sizes_ranges_kernel   persistent; every warp owns a contiguous range of tiles (the predicate scan's shape), streams the
+//                                offsets lane <-> row and leaves per-sub-tile byte prefixes inside its range; the last CTA scans
+//                                the <= 2368 range totals once.  No tile waits on another, no serial tail.
+//   string_gather_staged_kernel  persistent, three CTAs per SM, each walking 1024-row sub-tiles one iteration ahead of its global loads
+//                                (selection words, prefixes and the 1025 offsets of the NEXT sub-tile sit in registers while the
+//                                current one is processed; the first version, one CTA per sub-tile, spent 8 us per CTA on four
+//                                dependent round trips: 670 us per 50 M rows whatever the selectivity).
+//                                The sub-tile's source bytes are ONE contiguous block of the data
+//                                buffer (consecutive rows are adjacent), so dense sub-tiles fetch it with a single TMA bulk copy
+//                                (cp.async.bulk + mbarrier) into shared memory while the ranks / lengths / byte offsets are being
+//                                computed from the offsets (also staged in shared memory); the word-wise funnel-shift copy then
+//                                runs shared -> shared (unguarded LDS instead of guarded, divergent LDG), string boundaries are
+//                                merged with shared-memory atomic ORs into a zeroed staging buffer instead of byte-wise
+//                                predicated stores, and the dense destination range is flushed with 16-byte stores.
+//                                Sparse sub-tiles (few survivors) and blocks larger than the buffer read the survivors' words from
+//                                global memory with the same routine.  Strings longer than 64 bytes are copied by the whole warp.
+constexpr int kStrRows = 1024;                 // rows per string sub-tile: half a selection tile
+constexpr int kStrWords = kStrRows / 32;
+constexpr uint32_t kStrSrcCap = 32 * 1024;     // source block buffer (a 1024-row sub-tile of ~24-byte strings is ~22 KB)
+constexpr uint32_t kStrStage = 11 * 1024;      // destination staging chunk
+constexpr uint32_t kStrLong = 64;              // longer strings are copied cooperatively
+
+struct __align__(128) StrSmem {
+    uint8_t src[kStrSrcCap + 64];              // [16 bytes slack][block, 16-byte aligned][slack]
+    uint8_t stage[kStrStage + 32];
+    int32_t offs[2][kStrRows + 8];             // offsets of the current / the next sub-tile's rows (+ the end)
+    int32_t s_src[kStrRows];                   // survivor r: first source byte (absolute offset into the data buffer)
+    uint32_t s_dst[kStrRows + 8];              // survivor r: length, then first destination byte inside the sub-tile's dense range
+    uint32_t s_warp[kWarps];
+    uint64_t mbar;
+};
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void atom_or_shared(uint32_t addr, uint32_t v) {
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// bytes [blo, bhi) of a little-endian word, 0 <= blo < bhi <= 4
+__device__ __forceinline__ uint32_t byte_mask(uint32_t blo, uint32_t bhi) {
+    const uint32_t hi = bhi >= 4u ? 0xFFFFFFFFu : ((1u << (8u * bhi)) - 1u);
+    return hi & ~((1u << (8u * blo)) - 1u);
+}
+
+// One lane, one string: n bytes from `src` (shared-memory byte address when SMEM, else a global pointer) to the ZEROED staging buffer
+// at shared byte address dst.  Destination word i is the funnel shift of two consecutive aligned source words; interior words are
+// stored, the first / last word (shared with neighbouring strings) are OR-ed in.  All 32 lanes run the loop to the warp's longest string.
+template <bool SMEM>
+__device__ __forceinline__ void copy_string_lane(uint32_t src_smem, const uint8_t* __restrict__ src_gmem, uint32_t dst, uint32_t n) {
+    const uint32_t head = dst & 3u;
+    const uint32_t dw = dst - head;
+    const uint32_t end = head + n;
+    const uint32_t nw = n != 0u ? (end + 3u) >> 2 : 0u;
+    uint32_t sh, sa = 0;
+    const uint32_t* gsrc = nullptr;
+    uint32_t jl = 0, nl = 0;
+    if (SMEM) {
+        const uint32_t a0 = src_smem - head;      // shared address of the byte that lands in destination word 0, byte 0 (slack in front)
+        sh = (a0 & 3u) * 8u;
+        sa = a0 & ~3u;
+    } else {
+        const uintptr_t a0 = reinterpret_cast<uintptr_t>(src_gmem) - head;
+        const uint32_t ph = (uint32_t)a0 & 3u;
+        sh = ph * 8u;
+        gsrc = reinterpret_cast<const uint32_t*>(a0 - ph);
+        jl = (ph + head) >> 2;                    // first aligned source word holding one of our bytes
+        nl = n != 0u ? (ph + end + 3u) >> 2 : 0u; // one past the last: nothing outside [jl, nl) is dereferenced
+    }
+    auto load = [&](uint32_t j) -> uint32_t {
+        if (SMEM) return lds_u32(sa + 4u * j);
+        return (j - jl) < (nl - jl) ? __ldg(gsrc + j) : 0u;
+    };
+    const uint32_t nmax = __reduce_max_sync(0xFFFFFFFFu, nw);
+    uint32_t prev = nw != 0u ? load(0u) : 0u;
+#pragma unroll 1
+    for (uint32_t i0 = 0; i0 < nmax; i0 += 2u) {
+        // two words per round: both loads are issued before the first is used
+        const uint32_t c1 = i0 < nw ? load(i0 + 1u) : 0u;
+        const uint32_t c2 = i0 + 1u < nw ? load(i0 + 2u) : 0u;
+        const uint32_t v0 = __funnelshift_r(prev, c1, sh), v1 = __funnelshift_r(c1, c2, sh);
+        prev = c2;
+        if (i0 < nw) {
+            const uint32_t lo = i0 * 4u;
+            if (lo >= head && lo + 4u <= end) sts_u32(dw + lo, v0);
+            else atom_or_shared(dw + lo, v0 & byte_mask(lo >= head ? 0u : head - lo, min(end - lo, 4u)));
+        }
+        if (i0 + 1u < nw) {
+            const uint32_t lo = i0 * 4u + 4u;
+            if (lo + 4u <= end) sts_u32(dw + lo, v1);
+            else atom_or_shared(dw + lo, v1 & byte_mask(0u, end - lo));
+        }
+    }
+}
+
+// The whole warp copies ONE long string: lane l moves destination words l, l + 32, ...
+template <bool SMEM>
+__device__ __forceinline__ void copy_string_warp(uint32_t src_smem, const uint8_t* __restrict__ src_gmem, uint32_t dst, uint32_t n, int lane) {
+    const uint32_t head = dst & 3u;
+    const uint32_t dw = dst - head;
+    const uint32_t end = head + n;
+    const uint32_t nw = (end + 3u) >> 2;
+    uint32_t sh, sa = 0, jl = 0, nl = 0;
+    const uint32_t* gsrc = nullptr;
+    if (SMEM) {
+        const uint32_t a0 = src_smem - head;
+        sh = (a0 & 3u) * 8u; sa = a0 & ~3u;
+    } else {
+        const uintptr_t a0 = reinterpret_cast<uintptr_t>(src_gmem) - head;
+        const uint32_t ph = (uint32_t)a0 & 3u;
+        sh = ph * 8u; gsrc = reinterpret_cast<const uint32_t*>(a0 - ph);
+        jl = (ph + head) >> 2; nl = (ph + end + 3u) >> 2;
+    }
+    auto load = [&](uint32_t j) -> uint32_t {
+        if (SMEM) return lds_u32(sa + 4u * j);
+        return (j - jl) < (nl - jl) ? __ldg(gsrc + j) : 0u;
+    };
+    for (uint32_t i = (uint32_t)lane; i < nw; i += 32u) {
+        const uint32_t v = __funnelshift_r(load(i), load(i + 1u), sh);
+        const uint32_t lo = i * 4u;
+        if (lo >= head && lo + 4u <= end) sts_u32(dw + lo, v);
+        else atom_or_shared(dw + lo, v & byte_mask(lo >= head ? 0u : head - lo, min(end - lo, 4u)));
+    }
+}
+
+// keep the lowest k set bits of w
+__device__ __forceinline__ uint32_t keep_lowest_set(uint32_t w, uint32_t k) {
+    while ((uint32_t)__popc(w) > k) w &= ~(0x80000000u >> __clz(w));
+    return w;
+}
+
+// Survivor bytes of every 1024-row sub-tile as an exclusive prefix inside the owning warp's range of tiles, the range totals, and
+// (last CTA, by ticket) the ranges' global byte bases + the grand total.
+//   sub_bytes[2 t + h]   bytes of the range's survivors in front of half h of tile t
+//   range_bytes[g]       byte base of range g (byte_base_in included)
+static __global__ void __launch_bounds__(kBlock) string_sizes_ranges_kernel(const __grid_constant__ StrGatherParams p) {
+    __shared__ uint64_t s_part[kWarps];
+    __shared__ uint32_t s_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t n_tiles = (p.n_rows + kTileRows - 1) / kTileRows;
+    const int64_t g = (int64_t)blockIdx.x * kWarps + warp;
+    const int64_t t0 = min(n_tiles, g * p.tiles_per_range), t1 = min(n_tiles, t0 + p.tiles_per_range);
+    uint64_t run = 0;
+#pragma unroll 1
+    for (int64_t t = t0; t < t1; ++t) {
+        const int64_t row0 = t * kTileRows;
+        uint32_t w0, w1;
+        if (p.sel != nullptr) { const uint32_t* sw = p.sel + t * kTileWords; w0 = __ldg(sw + lane); w1 = __ldg(sw + 32 + lane); }
+        else {
+            const int64_t r0 = p.n_rows - (row0 + 32 * lane), r1 = r0 - 1024;
+            w0 = r0 >= 32 ? 0xFFFFFFFFu : (r0 <= 0 ? 0u : ((1u << r0) - 1u));
+            w1 = r1 >= 32 ? 0xFFFFFFFFu : (r1 <= 0 ? 0u : ((1u << r1) - 1u));
+        }
+        if (p.limit >= 0) {
+            // survivors whose global rank reaches the LIMIT do not count (at most one tile per query is cut)
+            uint64_t rexcl = p.tile_prefix != nullptr ? p.tile_prefix[t] : (uint64_t)(p.row_base + row0);
+            if (p.chunk_base != nullptr) rexcl = p.chunk_base[t / p.tiles_per_chunk] + (rexcl >> 12);
+            const uint32_t c0 = __popc(w0), c1 = __popc(w1);
+            uint32_t i0 = c0, i1 = c1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, i0, o), b = __shfl_up_sync(0xFFFFFFFFu, i1, o);
+                if (lane >= o) { i0 += a; i1 += b; }
+            }
+            const uint32_t h0 = __shfl_sync(0xFFFFFFFFu, i0, 31);
+            const uint32_t total = h0 + __shfl_sync(0xFFFFFFFFu, i1, 31);
+            if (rexcl >= (uint64_t)p.limit) { w0 = 0u; w1 = 0u; }
+            else if (rexcl + total > (uint64_t)p.limit) {
+                const uint32_t lim = (uint32_t)((uint64_t)p.limit - rexcl);
+                const uint32_t e0 = i0 - c0, e1 = h0 + i1 - c1;
+                w0 = e0 >= lim ? 0u : keep_lowest_set(w0, lim - e0);
+                w1 = e1 >= lim ? 0u : keep_lowest_set(w1, lim - e1);
+            }
+        }
+        // nulls are zero-length (string.rs:33-36)
+        if (p.valid.words != nullptr) { w0 &= load_bits32(p.valid, (uint64_t)(row0 + 32 * lane)); w1 &= load_bits32(p.valid, (uint64_t)(row0 + 1024 + 32 * lane)); }
+        uint32_t half_bytes[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t wh = h == 0 ? w0 : w1;
+            uint32_t bytes = 0;
+            if (__ballot_sync(0xFFFFFFFFu, wh != 0u) != 0u) {
+                // lane <-> row of every 32-row group: all 33 loads of the half are issued before the first is used (one round trip);
+                // a row's end is the next lane's start (lane 31: lane 0 of the next group)
+                const int64_t hrow0 = row0 + h * 1024;
+                const int32_t* const off = p.offsets + hrow0 + lane;
+                int32_t a[33];
+#pragma unroll
+                for (int k = 0; k < 33; ++k) a[k] = hrow0 + k * 32 + lane <= p.n_rows ? __ldg(off + k * 32) : 0;
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    const uint32_t m = __shfl_sync(0xFFFFFFFFu, wh, k);
+                    int32_t e = __shfl_down_sync(0xFFFFFFFFu, a[k], 1);
+                    const int32_t e31 = __shfl_sync(0xFFFFFFFFu, a[k + 1], 0);
+                    if (lane == 31) e = e31;
+                    if ((m >> lane) & 1u) bytes += (uint32_t)(e - a[k]);
+                }
+            }
+            half_bytes[h] = __reduce_add_sync(0xFFFFFFFFu, bytes);
+        }
+        if (lane == 0) { p.sub_bytes[2 * t] = run; p.sub_bytes[2 * t + 1] = run + half_bytes[0]; }
+        run += (uint64_t)half_bytes[0] + half_bytes[1];
+    }
+    if (lane == 0 && g < p.n_ranges) p.range_bytes[g] = run;
+
+    // ---- last CTA to finish: range totals -> global exclusive bases
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        s_last = atomicAdd(reinterpret_cast<unsigned int*>(p.range_bytes + p.n_ranges), 1u) == gridDim.x - 1 ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last == 0u) return;
+    __threadfence();
+    const int G = p.n_ranges;
+    const int per = (G + kBlock - 1) / kBlock;   // <= 10
+    uint64_t vals[12];
+    uint64_t mine = 0;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        const int idx = tid * per + i;
+        vals[i] = (i < per && idx < G) ? ld_relaxed_gpu(p.range_bytes + idx) : 0ull;
+        mine += vals[i];
+    }
+    uint64_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t nb = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += nb;
+    }
+    if (lane == 31) s_part[warp] = incl;
+    __syncthreads();
+    uint64_t woff = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) { const uint64_t c = s_part[w]; woff += (w < warp) ? c : 0ull; total += c; }
+    const uint64_t base0 = p.byte_base_in != nullptr ? (uint64_t)*p.byte_base_in : 0ull;
+    uint64_t acc = base0 + woff + incl - mine;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        const int idx = tid * per + i;
+        if (i < per && idx < G) { p.range_bytes[idx] = acc; acc += vals[i]; }
+    }
+    if (tid == 0) *p.bytes_total_out = (unsigned long long)(base0 + total);
+}
+
+// Everything a sub-tile needs from global memory before its first instruction of real work, requested a whole iteration ahead
+// and parked in registers: one selection word per lane (+ the first half's word for the second half's rank), the tile's row
+// prefix words, the byte prefix words, and the sub-tile's 1025 offsets (thread t: entries t, t + 256, t + 512, t + 768; thread 0
+// also entry 1024).
+struct StrPrefetch {
+    uint32_t w, wf;
+    uint64_t tp, cb, rb, sb;
+    int32_t o[5];
+};
+// what phase A derives from it (uniform across the CTA except `w`)
+struct StrSub {
+    int64_t row0;
+    uint64_t rexcl, bexcl;
+    uint32_t w, cnt_lim, src_bias;
+    int rows_here;
+    bool staged;
+};
+
+static __global__ void __launch_bounds__(kBlock, 3) string_gather_staged_kernel(const __grid_constant__ StrGatherParams p) {
+    extern __shared__ __align__(128) unsigned char str_smem_raw[];
+    StrSmem& sm = *reinterpret_cast<StrSmem*>(str_smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t n_subs = (p.n_rows + kStrRows - 1) / kStrRows;
+    const uint32_t lt = lanemask_lt();
+    const uint64_t rbase = p.row_base_in != nullptr ? (uint64_t)*p.row_base_in : 0ull;
+    uint8_t* const src_blk = sm.src + 16;   // 16-byte aligned (the struct is 128-byte aligned)
+    const uint32_t stage_addr = smem_u32(sm.stage);
+
+    auto prefetch = [&](int64_t sub) -> StrPrefetch {
+        StrPrefetch f;
+        const int64_t tile = sub >> 1, row0 = sub * kStrRows;
+        const int half = (int)(sub & 1);
+        const int rows_here = (int)min((int64_t)kStrRows, p.n_rows - row0);
+        if (p.sel != nullptr) {
+            const uint32_t* sw = p.sel + tile * kTileWords;
+            f.w = __ldg(sw + half * 32 + lane);
+            f.wf = half ? __ldg(sw + lane) : 0u;
+        } else {
+            const int64_t rem = p.n_rows - (row0 + 32 * lane);
+            f.w = rem >= 32 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+            f.wf = half ? 0xFFFFFFFFu : 0u;
+        }
+        f.tp = p.tile_prefix != nullptr ? __ldg(p.tile_prefix + tile) : (uint64_t)(p.row_base + tile * kTileRows);
+        f.cb = p.chunk_base != nullptr ? __ldg(p.chunk_base + (uint32_t)tile / (uint32_t)p.tiles_per_chunk) : 0ull;
+        f.rb = __ldg(p.range_bytes + (uint32_t)tile / (uint32_t)p.tiles_per_range);
+        f.sb = __ldg(p.sub_bytes + sub);
+        const int32_t* const off = p.offsets + row0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) f.o[j] = j * kBlock + tid <= rows_here ? __ldg(off + j * kBlock + tid) : 0;
+        f.o[4] = (tid == 0 && rows_here == kStrRows) ? __ldg(off + kStrRows) : 0;
+        return f;
+    };
+    auto park_offsets = [&](const StrPrefetch& f, int buf) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sm.offs[buf][j * kBlock + tid] = f.o[j];
+        if (tid == 0) sm.offs[buf][kStrRows] = f.o[4];
+    };
+    // phase A of a sub-tile whose offsets are already in sm.offs[buf] (visible): ranks in front, LIMIT cut, byte prefix, and the
+    // TMA bulk copy of its source block when it is dense enough, fits the buffer and lies inside the readable bounds
+    auto phase_a = [&](const StrPrefetch& f, int64_t sub, int buf) -> StrSub {
+        StrSub s;
+        s.row0 = sub * kStrRows;
+        s.rows_here = (int)min((int64_t)kStrRows, p.n_rows - s.row0);
+        s.w = f.w;
+        s.rexcl = (p.chunk_base != nullptr ? f.cb + (f.tp >> 12) : f.tp) + __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(f.wf));
+        const uint32_t cnt_total = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(f.w));
+        s.cnt_lim = cnt_total;
+        if (p.limit >= 0) s.cnt_lim = s.rexcl >= (uint64_t)p.limit ? 0u : (uint32_t)min((uint64_t)cnt_total, (uint64_t)p.limit - s.rexcl);
+        s.bexcl = f.rb + f.sb;
+        const int32_t first = sm.offs[buf][0], last = sm.offs[buf][s.rows_here];
+        const uint8_t* const g0 = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(p.data + first) & ~uintptr_t(15));
+        const uint8_t* const g1 = reinterpret_cast<const uint8_t*>((reinterpret_cast<uintptr_t>(p.data + last) + 15) & ~uintptr_t(15));
+        const uint32_t blk = (uint32_t)(g1 - g0);
+        s.staged = s.cnt_lim >= p.dense_min && s.cnt_lim != 0u && last > first && blk <= kStrSrcCap && g0 >= p.data_lo && g1 <= p.data_hi;
+        // shared address of data byte `o` once staged: src_blk + (p.data + o - g0)
+        s.src_bias = smem_u32(src_blk) - (uint32_t)(reinterpret_cast<uintptr_t>(g0) - reinterpret_cast<uintptr_t>(p.data));
+        if (s.staged && tid == 0) {
+            // the buffer was last read through the generic proxy (LDS of the previous sub-tile's copy): order those before the bulk write
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tma_load_1d(src_blk, g0, blk, &sm.mbar);
+        }
+        return s;
+    };
+
+    int64_t sub = blockIdx.x;
+    if (sub >= n_subs) return;
+    if (tid == 0) { mbar_init(&sm.mbar, 1); mbar_init_fence(); }
+    int buf = 0;
+    uint32_t tma_phase = 0;
+    StrPrefetch pf = prefetch(sub);
+    park_offsets(pf, 0);
+    __syncthreads();
+    StrSub cur = phase_a(pf, sub, 0);
+    int64_t nsub = sub + gridDim.x;
+    if (nsub < n_subs) pf = prefetch(nsub);
+
+#pragma unroll 1
+    while (true) {
+        // the next sub-tile's inputs were requested an iteration ago: park its offsets now, request the one after it
+        const bool has_next = nsub < n_subs;
+        StrPrefetch nf = pf;
+        if (has_next) {
+            park_offsets(nf, buf ^ 1);
+            if (nsub + gridDim.x < n_subs) pf = prefetch(nsub + gridDim.x);
+        }
+        StrSub nxt{};
+        bool next_issued = false;
+        const int32_t* const offs = sm.offs[buf];
+        uint32_t bytes_total = 0;
+
+        if (cur.cnt_lim != 0u) {
+            // ---- B. lane <-> row: (source offset, length) of every survivor stored at its rank; nulls are zero-length (string.rs:33-36)
+            {
+                const int first_word = warp * 4;               // this warp's 128 rows = 4 selection words
+                uint32_t run = __reduce_add_sync(0xFFFFFFFFu, lane < first_word ? (uint32_t)__popc(cur.w) : 0u);
+                uint32_t vwv = 0xFFFFFFFFu;
+                if (p.valid.words != nullptr && lane < 4) vwv = load_bits32(p.valid, (uint64_t)(cur.row0 + warp * 128 + 32 * lane));
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const uint32_t selw = __shfl_sync(0xFFFFFFFFu, cur.w, first_word + g);
+                    const uint32_t vw = __shfl_sync(0xFFFFFFFFu, vwv, g);
+                    const int r_in = warp * 128 + g * 32 + lane;
+                    const uint32_t r = run + __popc(selw & lt);
+                    run += __popc(selw);
+                    if (((selw >> lane) & 1u) != 0u && r < cur.cnt_lim) {
+                        const int32_t o = offs[r_in], o1 = offs[r_in + 1];
+                        sm.s_src[r] = o;
+                        sm.s_dst[r] = ((vw >> lane) & 1u) ? (uint32_t)(o1 - o) : 0u;
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- C. lengths -> exclusive byte offsets, in place: 4 ranks per thread, one block scan
+            {
+                const uint32_t base = (uint32_t)tid * 4u;
+                const uint4 x = *reinterpret_cast<const uint4*>(&sm.s_dst[base]);
+                uint32_t v[4] = {x.x, x.y, x.z, x.w};
+                uint32_t sum = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { const uint32_t t = base + i < cur.cnt_lim ? v[i] : 0u; v[i] = sum; sum += t; }
+                const uint32_t b0 = block_exclusive_scan(sum, sm.s_warp, bytes_total);
+                uint4 ox; ox.x = b0 + v[0]; ox.y = b0 + v[1]; ox.z = b0 + v[2]; ox.w = b0 + v[3];
+                *reinterpret_cast<uint4*>(&sm.s_dst[base]) = ox;
+                if (tid == kBlock - 1) sm.s_dst[kStrRows] = bytes_total;   // entries at and beyond cnt_lim hold the total
+            }
+            __syncthreads();
+            // new offsets, in rank order: out_offsets[first survivor of the sub-tile + r + 1] = end of survivor r (coalesced)
+            {
+                int32_t* oo = p.out_offsets + (cur.rexcl - rbase) + 1;
+                for (uint32_t r = tid; r < cur.cnt_lim; r += kBlock) oo[r] = (int32_t)(cur.bexcl + sm.s_dst[r + 1]);
+            }
+        }
+        if (cur.staged) { mbar_wait(&sm.mbar, tma_phase); tma_phase ^= 1u; }
+
+        // ---- byte copy through the staging buffer, laid out like the destination modulo 16 bytes, in chunks
+        if (bytes_total != 0u) {
+            const uint32_t pad = (uint32_t)(reinterpret_cast<uintptr_t>(p.out_data + cur.bexcl) & 15u);
+            uint32_t g_lo = 0;
+#pragma unroll 1
+            for (uint32_t c0 = 0; c0 < bytes_total; c0 += kStrStage) {
+                const uint32_t c1 = min(bytes_total, c0 + kStrStage);
+                // zero the staging buffer: string boundaries are OR-ed in
+                for (uint32_t u = tid; u < (kStrStage + 32) / 16; u += kBlock) *reinterpret_cast<uint4*>(sm.stage + u * 16u) = make_uint4(0u, 0u, 0u, 0u);
+                __syncthreads();
+                uint32_t g = g_lo;
+#pragma unroll 1
+                for (; g * kBlock < cur.cnt_lim && sm.s_dst[g * kBlock] < c1; ++g) {
+                    const uint32_t q = g * kBlock + (uint32_t)tid;
+                    uint32_t my_d = 0, my_n = 0, my_s = 0;
+                    if (q < cur.cnt_lim) {
+                        const uint32_t d = sm.s_dst[q], e = sm.s_dst[q + 1];
+                        const uint32_t lo = max(d, c0), hi = min(e, c1);
+                        if (lo < hi) { my_n = hi - lo; my_d = lo - c0 + pad; my_s = (uint32_t)sm.s_src[q] + (lo - d); }
+                    }
+                    const uint32_t any = __ballot_sync(0xFFFFFFFFu, my_n != 0u);
+                    if (any == 0u) continue;
+                    uint32_t longs = __ballot_sync(0xFFFFFFFFu, my_n > kStrLong);
+                    const uint32_t n_lane = my_n > kStrLong ? 0u : my_n;
+                    if (cur.staged) copy_string_lane<true>(cur.src_bias + my_s, nullptr, stage_addr + my_d, n_lane);
+                    else copy_string_lane<false>(0u, p.data + my_s, stage_addr + my_d, n_lane);
+                    while (longs != 0u) {
+                        const int l = __ffs(longs) - 1;
+                        longs &= longs - 1u;
+                        const uint32_t n = __shfl_sync(0xFFFFFFFFu, my_n, l), d = __shfl_sync(0xFFFFFFFFu, my_d, l), s0 = __shfl_sync(0xFFFFFFFFu, my_s, l);
+                        if (cur.staged) copy_string_warp<true>(cur.src_bias + s0, nullptr, stage_addr + d, n, lane);
+                        else copy_string_warp<false>(0u, p.data + s0, stage_addr + d, n, lane);
+                    }
+                }
+                g_lo = g > g_lo ? g - 1u : g_lo;  // the last group may straddle the chunk boundary
+                __syncthreads();
+                if (c1 == bytes_total && has_next) {
+                    // the source buffer is free: the next sub-tile's block starts flowing while this chunk is flushed
+                    nxt = phase_a(nf, nsub, buf ^ 1);
+                    next_issued = true;
+                }
+                uint8_t* const gbase = p.out_data + cur.bexcl + c0 - pad;  // 16-byte aligned
+                const uint32_t end = pad + (c1 - c0);
+                for (uint32_t u = tid; u * 16u < end; u += kBlock) {
+                    const uint32_t b0 = u * 16u, b1 = b0 + 16u;
+                    if (b0 >= pad && b1 <= end) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(sm.stage + b0);
+                        asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(gbase + b0), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+                    } else {
+                        for (uint32_t k = max(b0, pad); k < min(b1, end); ++k) gbase[k] = sm.stage[k];
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        if (!has_next) break;
+        if (!next_issued) {
+            __syncthreads();   // everyone is done with this sub-tile's offsets, tables and source block
+            nxt = phase_a(nf, nsub, buf ^ 1);
+        }
+        cur = nxt;
+        sub = nsub;
+        nsub += gridDim.x;
+        buf ^= 1;
     }
 }
 

@@ -34,6 +34,7 @@ extern "C" {
 
 const char* rvh_last_error() { return g_err.c_str(); }
 void rvh_set_stream_fusion(int on) { set_stream_fusion(on != 0); }
+void rvh_set_extensions(int on) { set_extensions(on != 0); }
 int64_t rvh_launch_count(int device) { int64_t n = -1; guard([&] { n = launch_count(device); }); return n; }
 
 // ----------------------------------------------------------------------------------- DataFrame

@@ -739,6 +739,9 @@ StreamingPhysicalPlan StreamingPhysicalPlan::dataframe_source(DataFrame df, size
 StreamingPhysicalPlan StreamingPhysicalPlan::filter(std::string col) const {
     StreamingPhysicalPlan p; p.kind = Filter; p.input = std::make_shared<StreamingPhysicalPlan>(*this); p.predicate_column = std::move(col); p.ctx = ctx; return p;
 }
+StreamingPhysicalPlan StreamingPhysicalPlan::filter_expr(Expr pred) const {
+    StreamingPhysicalPlan p; p.kind = FilterExpr; p.input = std::make_shared<StreamingPhysicalPlan>(*this); p.predicate = std::move(pred); p.ctx = ctx; return p;
+}
 StreamingPhysicalPlan StreamingPhysicalPlan::select(std::vector<std::string> cols) const {
     StreamingPhysicalPlan p; p.kind = Select; p.input = std::make_shared<StreamingPhysicalPlan>(*this); p.columns = std::move(cols); p.ctx = ctx; return p;
 }
@@ -761,6 +764,7 @@ static DataStreamRef build_stream(const StreamingPhysicalPlan& p, size_t min_bat
             return make_memory_stream(ctx, s, std::move(b));
         }
         case K::Filter: return make_filter_stream(build_stream(*p.input, min_batch_rows), p.predicate_column);
+        case K::FilterExpr: return make_filter_expr_stream(build_stream(*p.input, min_batch_rows), p.predicate);
         case K::Select: {
             auto in = build_stream(*p.input, min_batch_rows);
             try { return make_select_stream(std::move(in), p.columns); }
@@ -794,9 +798,14 @@ static std::optional<RecordBatch> try_fused_collect(const StreamingPhysicalPlan&
     const std::string* pred = nullptr;
     if (p->kind == K::Limit) { if (p->n == 0) return std::nullopt; limit = p->n; p = p->input.get(); }
     if (p->kind == K::Select) { sel = &p->columns; p = p->input.get(); }
+    const Expr* cmp = nullptr;   // extension: a single `column <op> literal` predicate runs as the fused comparison operator
     if (p->kind == K::Filter) { pred = &p->predicate_column; p = p->input.get(); }
+    else if (p->kind == K::FilterExpr) {
+        if (p->predicate.kind != Expr::Binary || p->predicate.op == BinaryOperator::And || p->predicate.op == BinaryOperator::Or) return std::nullopt;
+        cmp = &p->predicate; p = p->input.get();
+    }
     if (p->kind != K::DataFrameSource || p->df.is_empty() || p->batch_size == 0) return std::nullopt;
-    if (!limit && !sel && !pred) return std::nullopt;
+    if (!limit && !sel && !pred && !cmp) return std::nullopt;
     const DataFrame& df = p->df;
     const size_t ncols = df.columns().size();
     auto in_schema = std::make_shared<Schema>();
@@ -812,6 +821,18 @@ static std::optional<RecordBatch> try_fused_collect(const StreamingPhysicalPlan&
         auto i = in_schema->index_of(*pred);
         if (!i || in_schema->fields[*i].data_type != ExecType::Boolean) return std::nullopt;  // the chain raises the reference's error
         rp.mode = RVL_PRED_BOOL_COLUMN; rp.column = (int32_t)*i;
+    }
+    std::string lit_keep;
+    if (cmp) {
+        if (cmp->left->kind != Expr::Column || cmp->right->kind != Expr::Literal) return std::nullopt;
+        auto i = in_schema->index_of(cmp->left->name);
+        if (!i) return std::nullopt;                       // the chain raises the error
+        const AnyValue& lit = cmp->right->value;
+        lit_keep = lit.s;
+        rp.mode = RVL_PRED_CMP_LITERAL; rp.column = (int32_t)*i; rp.op = (int32_t)cmp->op;
+        rp.lit_dtype = rvl_dtype_of(lit.data_type());
+        rp.lit_i64 = lit.i; rp.lit_f64 = lit.f; rp.lit_bool = lit.b ? 1 : 0;
+        rp.lit_str = (const uint8_t*)lit_keep.data(); rp.lit_str_len = (int64_t)lit_keep.size();
     }
     std::vector<int32_t> proj;
     auto out_schema = std::make_shared<Schema>();
@@ -1026,11 +1047,30 @@ static FilterSpec convert_filter_predicate(const Expr& p) {  // planner.rs:134-1
     if (p.right->kind != Expr::Literal) throw Error("Filter right side must be a literal value, found: " + quoted(p.right->debug()));
     return {p.left->name, p.right->value, p.op};
 }
+// ---- extension: And / Or over comparison leaves (rivulus.hpp: set_extensions)
+static bool g_extensions = false;
+void set_extensions(bool on) { g_extensions = on; }
+bool extensions_enabled() { return g_extensions; }
+static bool is_compound(const Expr& p) { return p.kind == Expr::Binary && (p.op == BinaryOperator::And || p.op == BinaryOperator::Or); }
+// every leaf must have the shape the reference accepts for a whole predicate (planner.rs:152-186): same checks, same errors
+static void check_predicate_tree(const Expr& p) {
+    if (is_compound(p)) { check_predicate_tree(*p.left); check_predicate_tree(*p.right); return; }
+    convert_filter_predicate(p);
+}
+static void leaf_columns(const Expr& p, std::vector<std::string>& out) {
+    if (is_compound(p)) { leaf_columns(*p.left, out); leaf_columns(*p.right, out); return; }
+    out.push_back(p.left->name);
+}
+
 static void check_lowering(const LogicalPlan& p) {  // logical_to_physical runs over the whole tree before execution
     switch (p.kind) {
         case LogicalPlan::DataFrameSource: return;
         case LogicalPlan::Select: check_lowering(*p.input); for (const auto& e : p.expressions) convert_select_expr(e); return;
-        case LogicalPlan::Filter: check_lowering(*p.input); convert_filter_predicate(p.predicate); return;
+        case LogicalPlan::Filter:
+            check_lowering(*p.input);
+            if (g_extensions && is_compound(p.predicate)) check_predicate_tree(p.predicate);
+            else convert_filter_predicate(p.predicate);
+            return;
         case LogicalPlan::Limit: check_lowering(*p.input); return;
     }
 }
@@ -1119,11 +1159,68 @@ rvl_predicate to_predicate(int32_t column, BinaryOperator op, const AnyValue& li
 }
 
 // Filter arm (plan.rs:97-150), optionally fused with the Select (:68-96) and Limit (:151-173) arms right above it.
-Frame exec_filter(const ContextRef& ctx, const Frame& in, const FilterSpec& f, const std::vector<std::pair<std::string, std::string>>* select,
-                  std::optional<size_t> limit) {
+struct BatchGuard {
+    rvl_batch* b = nullptr;
+    BatchGuard() = default;
+    explicit BatchGuard(rvl_batch* x) : b(x) {}
+    BatchGuard(const BatchGuard&) = delete;
+    BatchGuard& operator=(const BatchGuard&) = delete;
+    ~BatchGuard() { if (b) rvl_batch_release(b); }
+    rvl_batch* release() { rvl_batch* x = b; b = nullptr; return x; }
+};
+
+// leaf `column <op> literal` over frame `in`: the kernel predicate (mixed Float64 / Int64 series compare row by row with their own type)
+rvl_predicate leaf_predicate(const Frame& in, const FilterSpec& f) {
     int32_t pc = -1;
     for (size_t i = 0; i < in.names.size(); ++i) if (in.names[i] == f.column) { pc = (int32_t)i; break; }
     if (pc < 0) throw Error("Column not found: '" + f.column + "'");  // plan.rs:104-110
+    rvl_predicate pred = to_predicate(pc, f.op, f.value);
+    if (in.tag_col[(size_t)pc] >= 0) pred.tag_column = in.tag_col[(size_t)pc] + 1;
+    return pred;
+}
+
+// extension: selection mask of an And / Or tree — one predicate-kernel launch per leaf, BooleanArray::{and, or} on the device per node
+rvl_batch* tree_mask(const ContextRef& ctx, const Frame& in, const Expr& p) {
+    if (is_compound(p)) {
+        BatchGuard l(tree_mask(ctx, in, *p.left)), r(tree_mask(ctx, in, *p.right));
+        rvl_batch* out = nullptr;
+        check(rvl_boolean_op(ctx->handle(), p.op == BinaryOperator::And ? RVL_BOOL_AND : RVL_BOOL_OR, l.b, 0, r.b, 0, &out));
+        return out;
+    }
+    const FilterSpec f = convert_filter_predicate(p);
+    const rvl_predicate pred = leaf_predicate(in, f);
+    rvl_batch* mask = nullptr;
+    check(rvl_predicate_mask(ctx->handle(), in.rb.handle(), &pred, &mask));
+    return mask;
+}
+
+Frame exec_filter(const ContextRef& ctx, const Frame& in, const Expr& predicate, const std::vector<std::pair<std::string, std::string>>* select,
+                  std::optional<size_t> limit) {
+    // the kernel predicate and the batch it runs over: a comparison against the frame itself, or (extension) the mask of an
+    // And / Or tree riding behind the frame's columns in a zero-copy wrapped batch
+    rvl_predicate pred{};
+    const rvl_batch* src = in.rb.handle();
+    BatchGuard mask, wrapped;
+    if (g_extensions && is_compound(predicate)) {
+        std::vector<std::string> cols;
+        leaf_columns(predicate, cols);
+        for (const auto& c : cols) {
+            bool found = false;
+            for (const auto& n : in.names) found |= n == c;
+            if (!found) throw Error("Column not found: '" + c + "'");
+        }
+        mask.b = tree_mask(ctx, in, predicate);
+        int32_t ncols = 0;
+        check(rvl_batch_num_columns(src, &ncols));
+        std::vector<rvl_column> views((size_t)ncols + 1);
+        for (int32_t i = 0; i < ncols; ++i) check(rvl_batch_column(src, i, &views[(size_t)i]));
+        check(rvl_batch_column(mask.b, 0, &views[(size_t)ncols]));
+        check(rvl_batch_wrap_device(ctx->handle(), views.data(), ncols + 1, &wrapped.b));
+        pred.mode = RVL_PRED_BOOL_COLUMN; pred.column = ncols;
+        src = wrapped.b;
+    } else {
+        pred = leaf_predicate(in, convert_filter_predicate(predicate));
+    }
     // projected columns: every input column (plain Filter) or the Select list, by source name
     std::vector<int32_t> proj;
     std::vector<std::string> out_names;
@@ -1137,9 +1234,6 @@ Frame exec_filter(const ContextRef& ctx, const Frame& in, const FilterSpec& f, c
     } else {
         for (size_t i = 0; i < in.names.size(); ++i) { proj.push_back((int32_t)i); out_names.push_back(in.names[i]); }
     }
-    // the predicate column of a Null-dtype series is all nulls: compare as such (its device array may still be typed)
-    rvl_predicate pred = to_predicate(pc, f.op, f.value);
-    if (in.tag_col[(size_t)pc] >= 0) pred.tag_column = in.tag_col[(size_t)pc] + 1;  // mixed series: rows compare with their own type
     // hidden tag columns of the projected mixed columns ride along behind the visible ones
     const size_t nvis = proj.size();
     Frame r;
@@ -1149,7 +1243,7 @@ Frame exec_filter(const ContextRef& ctx, const Frame& in, const FilterSpec& f, c
         if (t >= 0) { r.tag_col[j] = (int)proj.size(); proj.push_back(t); }
     }
     rvl_batch* out = nullptr;
-    check(rvl_filter_project(ctx->handle(), in.rb.handle(), &pred, proj.data(), (int32_t)proj.size(), limit ? (int64_t)*limit : -1, &out));
+    check(rvl_filter_project(ctx->handle(), src, &pred, proj.data(), (int32_t)proj.size(), limit ? (int64_t)*limit : -1, &out));
     auto schema = std::make_shared<Schema>();
     for (size_t j = 0; j < proj.size(); ++j)
         schema->fields.push_back(Field{j < nvis ? out_names[j] : in.rb.schema()->fields[(size_t)proj[j]].name, in.rb.schema()->fields[(size_t)proj[j]].data_type, true});
@@ -1168,23 +1262,55 @@ Frame exec_filter(const ContextRef& ctx, const Frame& in, const FilterSpec& f, c
     return r;
 }
 
+// extension: selection mask of a predicate tree over a RecordBatch (the streaming engine's arrays: numeric / Boolean nulls were
+// already flattened by dataframe_to_batches, strings keep theirs)
+rvl_batch* batch_tree_mask(const RecordBatch& b, const Expr& p) {
+    const ContextRef& ctx = b.context();
+    if (is_compound(p)) {
+        BatchGuard l(batch_tree_mask(b, *p.left)), r(batch_tree_mask(b, *p.right));
+        rvl_batch* out = nullptr;
+        check(rvl_boolean_op(ctx->handle(), p.op == BinaryOperator::And ? RVL_BOOL_AND : RVL_BOOL_OR, l.b, 0, r.b, 0, &out));
+        return out;
+    }
+    const FilterSpec f = convert_filter_predicate(p);
+    auto idx = b.schema()->index_of(f.column);
+    if (!idx) throw Error("Stream execution error: Column '" + f.column + "' not found in schema");
+    const rvl_predicate pred = to_predicate((int32_t)*idx, f.op, f.value);
+    rvl_batch* mask = nullptr;
+    check(rvl_predicate_mask(ctx->handle(), b.handle(), &pred, &mask));
+    return mask;
+}
+
+struct FilterExprStream : DataStream {
+    DataStreamRef input; Expr pred;
+    SchemaRef schema() const override { return input->schema(); }
+    std::optional<RecordBatch> next_batch() override {
+        auto b = input->next_batch();
+        if (!b) return std::nullopt;
+        auto ms = std::make_shared<Schema>();
+        ms->fields.push_back(Field{"mask", ExecType::Boolean, true});
+        RecordBatch mask = RecordBatch::adopt(b->context(), ms, batch_tree_mask(*b, pred));
+        try { return b->filter(mask, 0); }
+        catch (const Error& e) { if (e.panic) throw; throw Error(std::string("Stream execution error: ") + e.what()); }
+    }
+};
+
 Frame exec_node(const ContextRef& ctx, const LogicalPlan& p) {  // physical_plan/plan.rs:65-173
     switch (p.kind) {
         case LogicalPlan::DataFrameSource: return upload_frame(ctx, p.df);
         case LogicalPlan::Filter: {
             Frame in = exec_node(ctx, *p.input);
-            FilterSpec f = convert_filter_predicate(p.predicate);
-            if (in.names.empty()) throw Error("Column not found: '" + f.column + "'");
-            return exec_filter(ctx, in, f, nullptr, std::nullopt);
+            if (in.names.empty()) { std::vector<std::string> c; leaf_columns(p.predicate, c); throw Error("Column not found: '" + c[0] + "'"); }
+            return exec_filter(ctx, in, p.predicate, nullptr, std::nullopt);
         }
         case LogicalPlan::Select: {
             std::vector<std::pair<std::string, std::string>> sel;
             for (const auto& e : p.expressions) sel.push_back(convert_select_expr(e));
             if (p.input->kind == LogicalPlan::Filter && !sel.empty()) {  // Select(Filter(x)): one fused launch
                 Frame in = exec_node(ctx, *p.input->input);
-                FilterSpec f = convert_filter_predicate(p.input->predicate);
-                if (!in.names.empty()) return exec_filter(ctx, in, f, &sel, std::nullopt);
-                throw Error("Column not found: '" + f.column + "'");
+                if (!in.names.empty()) return exec_filter(ctx, in, p.input->predicate, &sel, std::nullopt);
+                std::vector<std::string> c; leaf_columns(p.input->predicate, c);
+                throw Error("Column not found: '" + c[0] + "'");
             }
             Frame in = exec_node(ctx, *p.input);
             std::vector<size_t> idx;
@@ -1222,17 +1348,15 @@ Frame exec_node(const ContextRef& ctx, const LogicalPlan& p) {  // physical_plan
                 const LogicalPlan* c = p.input.get();
                 if (c->kind == LogicalPlan::Filter) {
                     Frame in = exec_node(ctx, *c->input);
-                    FilterSpec f = convert_filter_predicate(c->predicate);
-                    if (in.names.empty()) throw Error("Column not found: '" + f.column + "'");
-                    return exec_filter(ctx, in, f, nullptr, p.n);
+                    if (in.names.empty()) { std::vector<std::string> cn; leaf_columns(c->predicate, cn); throw Error("Column not found: '" + cn[0] + "'"); }
+                    return exec_filter(ctx, in, c->predicate, nullptr, p.n);
                 }
                 if (c->kind == LogicalPlan::Select && c->input->kind == LogicalPlan::Filter && !c->expressions.empty()) {
                     std::vector<std::pair<std::string, std::string>> sel;
                     for (const auto& e : c->expressions) sel.push_back(convert_select_expr(e));
                     Frame in = exec_node(ctx, *c->input->input);
-                    FilterSpec f = convert_filter_predicate(c->input->predicate);
-                    if (in.names.empty()) throw Error("Column not found: '" + f.column + "'");
-                    return exec_filter(ctx, in, f, &sel, p.n);
+                    if (in.names.empty()) { std::vector<std::string> cn; leaf_columns(c->input->predicate, cn); throw Error("Column not found: '" + cn[0] + "'"); }
+                    return exec_filter(ctx, in, c->input->predicate, &sel, p.n);
                 }
             }
             Frame in = exec_node(ctx, *p.input);
@@ -1255,6 +1379,10 @@ Frame exec_node(const ContextRef& ctx, const LogicalPlan& p) {  // physical_plan
     return Frame();
 }
 }  // namespace
+
+DataStreamRef make_filter_expr_stream(DataStreamRef in, Expr predicate) {
+    auto st = std::make_unique<FilterExprStream>(); st->input = std::move(in); st->pred = std::move(predicate); return st;
+}
 
 DataFrame execute_eager(const LogicalPlan& optimized, const ContextRef& ctx) {
     check_lowering(optimized);  // logical_to_physical fails before anything executes (builder.rs:99-100)
@@ -1283,6 +1411,12 @@ StreamingPhysicalPlan logical_to_streaming(const LogicalPlan& plan, const Contex
             auto in = logical_to_streaming(*plan.input, ctx);
             const Expr& p = plan.predicate;
             if (p.kind == Expr::Column) return in.filter(p.name);
+            if (p.kind == Expr::Binary && g_extensions) {
+                // extension: comparison leaves and And / Or over them; a malformed leaf raises the eager planner's message
+                try { check_predicate_tree(p); }
+                catch (const Error& e) { throw Error(std::string("Streaming planner error: Expression conversion error: ") + e.what()); }
+                return in.filter_expr(p);
+            }
             if (p.kind == Expr::Binary) {
                 if (p.left->kind == Expr::Column)
                     throw Error("Streaming planner error: Expression conversion error: Binary expressions not yet supported in streaming mode. "

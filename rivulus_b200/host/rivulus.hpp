@@ -262,6 +262,7 @@ class DataStream {  // trait DataStream  stream.rs:25-54
 using DataStreamRef = std::unique_ptr<DataStream>;
 DataStreamRef make_memory_stream(const ContextRef& ctx, SchemaRef schema, std::vector<RecordBatch> batches);  // MemoryStream::new :66-81
 DataStreamRef make_filter_stream(DataStreamRef input, std::string predicate_column);         // FilterStream::new :123-128
+DataStreamRef make_filter_expr_stream(DataStreamRef input, Expr predicate);                  // extension: And / Or / comparison tree
 DataStreamRef make_select_stream(DataStreamRef input, std::vector<std::string> columns);     // SelectStream::new :173-194
 DataStreamRef make_limit_stream(DataStreamRef input, size_t limit);                          // LimitStream::new streaming.rs:254-260
 std::vector<RecordBatch> collect_all_batches(DataStream& s);                                 // streaming.rs:335-341
@@ -271,7 +272,8 @@ RecordBatch collect_stream_batches(const ContextRef& ctx, DataStream& s);       
 std::vector<RecordBatch> dataframe_to_batches(const ContextRef& ctx, const DataFrame& df, size_t batch_size);
 
 struct StreamingPhysicalPlan {  // streaming.rs:28-68, 290-333
-    enum Kind { MemorySource, DataFrameSource, Filter, Select, Limit } kind = MemorySource;
+    enum Kind { MemorySource, DataFrameSource, Filter, Select, Limit, FilterExpr } kind = MemorySource;
+    Expr predicate;   // FilterExpr (opt-in extension, see set_extensions)
     std::vector<RecordBatch> batches;
     DataFrame df; size_t batch_size = 0;
     std::shared_ptr<StreamingPhysicalPlan> input;
@@ -282,6 +284,7 @@ struct StreamingPhysicalPlan {  // streaming.rs:28-68, 290-333
     static StreamingPhysicalPlan memory_source(std::vector<RecordBatch> b);
     static StreamingPhysicalPlan dataframe_source(DataFrame df, size_t batch_size, ContextRef ctx = nullptr);
     StreamingPhysicalPlan filter(std::string col) const;
+    StreamingPhysicalPlan filter_expr(Expr predicate) const;   // extension
     StreamingPhysicalPlan select(std::vector<std::string> cols) const;
     StreamingPhysicalPlan limit(size_t n) const;
     DataStreamRef execute() const;                      // :70-133 (one operator object per node, batches of `batch_size`)
@@ -292,6 +295,17 @@ struct StreamingPhysicalPlan {  // streaming.rs:28-68, 290-333
     std::vector<RecordBatch> collect_batches() const;   // :240-243 (honours batch_size: batch boundaries are visible)
     static constexpr size_t kCollectBatchRows = 1 << 20;
 };
+
+// OPT-IN EXTENSION, off by default — the default is the reference's behaviour, error text included: both
+// reference executors reject And / Or predicates (planner.rs:146-150) and the streaming planner rejects every comparison
+// (streaming_planner.rs:137-168).  With set_extensions(true) a filter predicate may be a tree of And / Or over `column <op> literal`
+// leaves, in collect() and in collect_streaming().  Each leaf is evaluated with the eager truth table (plan.rs:114-120 over
+// series.rs:87-117) by the predicate kernels into a selection mask (rvl_predicate_mask), the masks are combined on the device
+// (rvl_boolean_op = BooleanArray::{and, or}, boolean.rs:120-165) and the result drives the ordinary mask filter
+// (RVL_PRED_BOOL_COLUMN = RecordBatch::filter, record_batch.rs:221-243).  A single comparison in collect_streaming() runs as the
+// fused comparison operator (RVL_PRED_CMP_LITERAL) inside the rvl_stream pipeline.
+void set_extensions(bool on);
+bool extensions_enabled();
 
 // ---------------------------------------------------------------------------------------- logical_plan/*
 struct LogicalPlan {  // logical_plan/plan.rs:8-39 (CsvFileSource / Join: out of scope)

@@ -9,6 +9,7 @@ from rivulus_b200 import capi  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--rows", type=int, default=50_000_000)
 ap.add_argument("--thresholds", default="998,899,499,99")
+ap.add_argument("--quiet-opts", action="store_true")
 ap.add_argument("--reps", type=int, default=1)
 ap.add_argument("--plan", default="auto", choices=["auto", "fused", "two_pass"])
 ap.add_argument("--sparse-max", type=int, default=None)

@@ -60,7 +60,7 @@ def _load_golden_namespace():
     ns = {
         "__name__": "host_golden", "np": np, "pytest": pytest,
         "Array": _Array, "DataFrame": F.DataFrame, "LazyFrame": F.LazyFrame, "OracleError": F.RivulusError,
-        "RecordBatch": _RecordBatch, "StreamingPhysicalPlan": F.StreamingPhysicalPlan, "col": F.col, "lit": F.lit,
+        "RecordBatch": _RecordBatch, "StreamingPhysicalPlan": F.StreamingPhysicalPlan, "col": F.col, "lit": F.lit, "set_extensions": F.set_extensions,
         "EX_BOOLEAN": F.EX_BOOLEAN, "EX_FLOAT64": F.EX_FLOAT64, "EX_INT64": F.EX_INT64, "EX_NULL": F.EX_NULL, "EX_STRING": F.EX_STRING,
     }
     exec(compile(src, "test_oracle_golden.py[gpu host layer]", "exec"), ns)
@@ -82,6 +82,7 @@ GPU_TESTS = [
     "test_streaming_plan_memory_source_ops", "test_limit_stream_batches", "test_collect_vs_collect_batches",
     "test_filter_select_stream_operators", "test_streaming_planner_conversions", "test_streaming_alias_dropped_and_null_flattening",
     "test_streaming_batches_of_1024", "test_eager_nulls_dtype_collapse_and_empty_errors",
+    "test_extension_compound_and_streaming_comparison_predicates",
 ]
 
 
@@ -223,6 +224,57 @@ def test_random_streaming_queries_match_oracle(seed):
         want = _outcome(O, O.OracleError, build)
         got = _outcome(F, F.RivulusError, build)
         assert got == want, (seed, q, sel, lim, fcol, shape)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(4))
+def test_extension_random_predicate_trees_match_oracle(seed):
+    """Opt-in extension: random And / Or trees over comparison leaves (every column type incl. the mixed Int64/Float64 series, null
+    and cross-type literals), eager and streaming, with select / limit on top — the mask algebra on the device against the oracle's
+    row-by-row evaluation of the same definition."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(500 + seed)
+    n = int(rng.choice([1, 65, 1000, 4000]))
+    cols = _random_frame(rng, n)
+    scols = [c for c in cols if c[0] not in ("z", "m")]
+    literals = [25, 25.0, "s20", True, None, 0, float("nan"), -1]
+    meths = ["eq", "neq", "lt", "gt", "lte", "gte"]
+
+    def random_tree(names, depth):
+        if depth == 0 or rng.random() < 0.3:
+            return ("leaf", str(rng.choice(names)), str(rng.choice(meths)), literals[int(rng.integers(0, len(literals)))])
+        return (str(rng.choice(["and_", "or_"])), random_tree(names, depth - 1), random_tree(names, depth - 1))
+
+    def to_expr(mod, t):
+        if t[0] == "leaf":
+            return getattr(mod.col(t[1]), t[2])(mod.lit(t[3]))
+        return getattr(to_expr(mod, t[1]), t[0])(to_expr(mod, t[2]))
+
+    for mod in (O, F):
+        mod.set_extensions(True)
+    try:
+        for q in range(24):
+            streaming = q % 2 == 1
+            frame_cols = scols if streaming else cols
+            names = [c[0] for c in frame_cols]
+            tree = random_tree(names, int(rng.integers(1, 4)))
+            sel = [str(x) for x in rng.choice(names, size=int(rng.integers(1, 4)), replace=False)]
+            lim = int(rng.choice([1, 5, 10 ** 6]))
+            shape = int(rng.integers(0, 4))
+
+            def build(mod, tree=tree, sel=sel, lim=lim, shape=shape, streaming=streaming, frame_cols=frame_cols):
+                lf = mod.LazyFrame.from_dataframe(mod.DataFrame.new(frame_cols)).filter(to_expr(mod, tree))
+                if shape == 1: lf = lf.select([mod.col(c) for c in sel])
+                elif shape == 2: lf = lf.select([mod.col(c) for c in sel]).limit(lim)
+                elif shape == 3: lf = lf.limit(lim)
+                return lf.collect_streaming() if streaming else lf.collect()
+
+            want = _outcome(O, O.OracleError, build)
+            got = _outcome(F, F.RivulusError, build)
+            assert got == want, (seed, q, tree, sel, lim, shape, streaming)
+    finally:
+        for mod in (O, F):
+            mod.set_extensions(False)
 
 
 @pytest.mark.gpu

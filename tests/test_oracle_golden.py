@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
-from oracle.oracle import (Array, DataFrame, LazyFrame, OracleError, RecordBatch, StreamingPhysicalPlan, col, lit,
+from oracle.oracle import (Array, DataFrame, LazyFrame, OracleError, RecordBatch, StreamingPhysicalPlan, col, lit, set_extensions,
                            EX_BOOLEAN, EX_FLOAT64, EX_INT64, EX_NULL, EX_STRING)
 
 
@@ -552,3 +552,54 @@ def test_fused_oracle_matches_eager_on_columnar_input():
             assert fused.num_rows() == eager.height()
             if eager.height():
                 assert fused.to_dict() == eager.to_dict(), (op, literal)
+
+
+# ---------------------------------------------------------------- opt-in extension: no reference behaviour exists
+def test_extension_compound_and_streaming_comparison_predicates():
+    """And / Or over `column <op> literal` leaves in collect() / collect_streaming(), comparisons in collect_streaming().
+    OFF by default: the reference's rejections (planner.rs:146-150, streaming_planner.rs:137-168) are what a user sees.
+    ON: every leaf is the eager truth table (plan.rs:114-120; a Null row is Less than any literal, series.rs:105-107), And / Or
+    combine the leaves' true / false.  The expected rows below are worked out by hand from that definition."""
+    df = DataFrame.new([("name", ["Alice", None, "Charlie", "Diana", "Eve", "Frank"]), ("age", [25, None, 35, 28, 42, 19]),
+                        ("score", [85.5, 92.0, None, 94.5, 88.0, 70.0])])
+    both = col("age").gt(lit(26)).and_(col("score").lt(lit(93.0)))
+    with pytest.raises(OracleError, match="Unsupported filter: only simple column comparisons supported"):
+        LazyFrame.from_dataframe(df).filter(both).collect()
+    with pytest.raises(OracleError, match="Binary expressions not yet supported in streaming mode"):
+        LazyFrame.from_dataframe(df).filter(col("age").gt(lit(26))).collect_streaming()
+    set_extensions(True)
+    try:
+        # eager.  age > 26: F F(null) T T T F;  score < 93: T T T(null is Less) F T T  => rows 2, 4
+        out = LazyFrame.from_dataframe(df).filter(both).collect()
+        assert out.to_dict() == {"name": ["Charlie", "Eve"], "age": [35, 42], "score": [None, 88.0]}
+        # age < 20: F T(null) F F F T;  score >= 94: F F F(null) T F F  => rows 1, 3, 5; select + limit on top
+        either = col("age").lt(lit(20)).or_(col("score").gte(lit(94.0)))
+        out = LazyFrame.from_dataframe(df).filter(either).select([col("name"), col("score").alias("s")]).collect()
+        assert out.to_dict() == {"name": [None, "Diana", "Frank"], "s": [92.0, 94.5, 70.0]}
+        assert LazyFrame.from_dataframe(df).filter(either).limit(2).collect().to_dict() == {"name": [None, "Diana"], "age": [None, 28], "score": [92.0, 94.5]}
+        # nested: (age > 26 AND score < 93) OR name == "Frank"; cross-type leaf (age == "x") is never true, != always
+        nested = both.or_(col("name").eq(lit("Frank")))
+        assert LazyFrame.from_dataframe(df).filter(nested).select([col("name")]).collect().to_dict() == {"name": ["Charlie", "Eve", "Frank"]}
+        assert LazyFrame.from_dataframe(df).filter(col("age").neq(lit("x")).and_(col("age").gte(lit(35)))).select([col("age")]).collect().to_dict() == {"age": [35, 42]}
+        # eager vs streaming on nulls: the eager engine sees Null (< -1 holds), the streaming engine sees the flattened 0 (streaming.rs:177)
+        q = col("age").lt(lit(-1)).or_(col("name").eq(lit("Eve")))
+        assert LazyFrame.from_dataframe(df).filter(q).select([col("name")]).collect().to_dict() == {"name": [None, "Eve"]}
+        assert LazyFrame.from_dataframe(df).filter(q).select([col("name")]).collect_streaming().to_dict() == {"name": ["Eve"]}
+        # streaming: a plain comparison (fused device pipeline), a compound one, strings keep their nulls (a null name is Less than "B")
+        s1 = LazyFrame.from_dataframe(df).filter(col("age").gt(lit(26))).select([col("name"), col("age")]).collect_streaming()
+        assert s1.to_dict() == {"name": ["Charlie", "Diana", "Eve"], "age": [35, 28, 42]}
+        s2 = LazyFrame.from_dataframe(df).filter(both).collect_streaming()
+        assert s2.to_dict() == {"name": ["Charlie", "Eve"], "age": [35, 42], "score": [0.0, 88.0]}
+        s3 = LazyFrame.from_dataframe(df).filter(col("name").lt(lit("B")).and_(col("score").gt(lit(80.0)))).select([col("score")]).limit(1).collect_streaming()
+        assert s3.to_dict() == {"score": [85.5]}
+        s4 = LazyFrame.from_dataframe(df).filter(col("name").lt(lit("B"))).select([col("age")]).collect_streaming()
+        assert s4.to_dict() == {"age": [25, 0]}
+        # malformed leaves raise the planner's own messages; unknown columns fail validation as ever
+        with pytest.raises(OracleError, match="Filter right side must be a literal value"):
+            LazyFrame.from_dataframe(df).filter(both.and_(col("age").gt(col("score")))).collect()
+        with pytest.raises(OracleError, match="Streaming planner error: Expression conversion error: Filter right side must be a literal value"):
+            LazyFrame.from_dataframe(df).filter(col("age").gt(col("score"))).collect_streaming()
+        with pytest.raises(OracleError, match="Logical plan error: Column not found: 'nope'"):
+            LazyFrame.from_dataframe(df).filter(both.or_(col("nope").eq(lit(1)))).collect()
+    finally:
+        set_extensions(False)

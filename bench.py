@@ -250,10 +250,15 @@ def run_native(args):
     stream = torch.cuda.ExternalStream(ctx.cuda_stream(), device=torch.device("cuda", local_rank))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(uuid=str(torch.cuda.get_device_properties(local_rank).uuid), index=local_rank)
-    barrier(); torch.cuda.synchronize()
-    ctx.profile_enable(True)
-    launches0 = ctx.launch_count()
+    # the sampler's first NVML queries take the driver lock for milliseconds: let them happen before the timed region opens
+    # (one 13 ms outlier in the very first timed operator was exactly that), then keep sampling through it
     sampler.start()
+    time.sleep(0.25)
+    ctx.profile_enable(True)
+    step()                      # one more untimed step with profiling on (event creation paths warm)
+    ctx.profile_read_launches()
+    barrier(); torch.cuda.synchronize()
+    launches0 = ctx.launch_count()
     e0.record(stream)
     for _ in range(args.steps):
         counts = step()

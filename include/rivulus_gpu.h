@@ -141,8 +141,9 @@ typedef enum rvl_option {
     RVL_OPT_SCAN_WARPS = 6,         /* two-pass: warps per CTA of the predicate scan (8 or 16) */
     RVL_OPT_DENSE_WARPS = 7,        /* two-pass: consumer warps per CTA of the dense kernel (8 or 16; 16 implies one CTA per SM) */
     RVL_OPT_BITS_OVERLAP = 8,       /* two-pass: run the bit-packed compaction kernel on a forked stream under the 8-byte kernels (default 1) */
-    RVL_OPT_STRING_KERNEL = 10,     /* String compaction kernels: 1 = round-1 pair (CTA-per-tile sizes + gather from global memory),
-                                       2 = persistent ranges sizes pass + TMA-staged gather (default) */
+    RVL_OPT_STRING_KERNEL = 10,     /* String compaction kernels: 1 = round-1 pair (CTA-per-tile sizes + gather from global memory);
+                                       2 = persistent ranges sizes pass + persistent TMA-staged gather over 1024-row sub-tiles;
+                                       3 = ranges sizes pass + round-1 gather (default); 4 = 3 with OR-merged string boundaries */
     RVL_OPT_STRING_DENSE_MIN = 11,  /* kernel 2: 1024-row sub-tiles with at least this many survivors fetch their whole source byte block
                                        with one TMA bulk copy (default 128); sparser ones read only the survivors' words */
     RVL_OPT_EXACT_ALLOC = 9,        /* blocking rvl_filter_project, two-pass plan: read the survivor count (and string bytes) back after the

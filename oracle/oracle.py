@@ -290,6 +290,22 @@ class LazyFrame:
         lib().orc_lf_plan_shape(_vp(self._h), buf, 256)
         return buf.value.decode()
 
+    def schema(self):
+        """logical_plan.schema() of the plan as built: [(name, dtype name)] (logical_plan/plan.rs:63-113)."""
+        buf = C.create_string_buffer(4096)
+        _check(lib().orc_lf_schema(_vp(self._h), buf, 4096))
+        return [tuple(x.split(":")) for x in buf.value.decode().split(",") if x]
+
+    def validate(self):
+        """logical_plan.validate() of the plan as built (logical_plan/plan.rs:115-202); raises on ColumnNotFound."""
+        _check(lib().orc_lf_validate(_vp(self._h)))
+
+    def describe(self) -> str:
+        """Debug-style dump of the plan as built (node kinds, expression trees)."""
+        buf = C.create_string_buffer(8192)
+        _check(lib().orc_lf_describe(_vp(self._h), buf, 8192))
+        return buf.value.decode()
+
 
 # ------------------------------------------------------------------------------------------ Arrow-layout arrays
 @dataclass

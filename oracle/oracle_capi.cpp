@@ -122,6 +122,31 @@ int orc_lf_collect(void* lf, void** df_out) {
 int orc_lf_collect_streaming(void* lf, void** rb_out) {
     return guard([&] { *rb_out = new RecordBatch(((LazyFrame*)lf)->collect_streaming()); });
 }
+// logical_plan/plan.rs probes on the plan as built (not optimized): schema() as "name:Dtype,...", validate(), and a Debug-style dump
+static std::string describe_plan(const LogicalPlan& p) {
+    switch (p.kind) {
+        case LogicalPlan::DataFrameSource: return "DataFrameSource";
+        case LogicalPlan::Select: {
+            std::string e;
+            for (size_t i = 0; i < p.expressions.size(); ++i) e += (i ? ", " : "") + p.expressions[i].debug();
+            return "Select { input: " + describe_plan(*p.input) + ", expressions: [" + e + "] }";
+        }
+        case LogicalPlan::Filter: return "Filter { input: " + describe_plan(*p.input) + ", predicate: " + p.predicate.debug() + " }";
+        case LogicalPlan::Limit: return "Limit { input: " + describe_plan(*p.input) + ", n: " + std::to_string(p.n) + " }";
+    }
+    return "";
+}
+int orc_lf_schema(void* lf, char* buf, int cap) {
+    return guard([&] {
+        std::string s;
+        for (const auto& pr : ((LazyFrame*)lf)->plan.schema()) s += (s.empty() ? "" : ",") + pr.first + ":" + dtype_name(pr.second);
+        std::snprintf(buf, (size_t)cap, "%s", s.c_str());
+    });
+}
+int orc_lf_validate(void* lf) { return guard([&] { ((LazyFrame*)lf)->plan.validate(); }); }
+int orc_lf_describe(void* lf, char* buf, int cap) {
+    return guard([&] { std::snprintf(buf, (size_t)cap, "%s", describe_plan(((LazyFrame*)lf)->plan).c_str()); });
+}
 // optimizer shape probe for tests: returns the optimized plan as "Filter(Select(Source))"-style text
 int orc_lf_plan_shape(void* lf, char* buf, int cap) {
     LogicalPlan p = optimize(((LazyFrame*)lf)->plan);

@@ -316,7 +316,8 @@ int str_launch_sizes(const CoreRef& core, const StrGatherParams& sp, cudaStream_
 int str_launch_gather(const CoreRef& core, const StrGatherParams& sp) {
     const int64_t tiles = (sp.n_rows + kTileRows - 1) / kTileRows;
     if (tiles <= 0) return RVL_OK;
-    if (core->string_kernel == 1) string_gather_kernel<<<(unsigned)tiles, kBlock, 0, core->stream>>>(sp);
+    if (core->string_kernel == 1 || core->string_kernel == 3) string_gather_kernel<0><<<(unsigned)tiles, kBlock, 0, core->stream>>>(sp);
+    else if (core->string_kernel == 4) string_gather_kernel<1><<<(unsigned)tiles, kBlock, 0, core->stream>>>(sp);
     else {
         // persistent: three CTAs per SM, each walks sub-tiles blockIdx.x, blockIdx.x + gridDim.x, ... one iteration ahead of its loads
         const int64_t subs = (sp.n_rows + kStrRows - 1) / kStrRows;

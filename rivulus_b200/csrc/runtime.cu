@@ -233,7 +233,7 @@ int32_t rvl_ctx_set_option(rvl_ctx* ctx, int32_t option, int64_t value) {
             c.dense_warps = (int)value; return RVL_OK;
         case RVL_OPT_BITS_OVERLAP: c.bits_overlap = value != 0; return RVL_OK;
         case RVL_OPT_STRING_KERNEL:
-            if (value != 1 && value != 2) return fail(RVL_INVALID_ARGUMENT, "string_kernel must be 1 or 2");
+            if (value < 1 || value > 4) return fail(RVL_INVALID_ARGUMENT, "string_kernel must be in [1, 4]");
             c.string_kernel = (int)value; return RVL_OK;
         case RVL_OPT_STRING_DENSE_MIN:
             if (value < 0 || value > 1025) return fail(RVL_INVALID_ARGUMENT, "string_dense_min must be in [0, 1025]");

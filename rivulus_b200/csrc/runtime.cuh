@@ -51,7 +51,8 @@ struct CtxCore {
     cudaStream_t d2h_stream = nullptr;   // downloads of finished batches (overlaps H2D staging and kernels)
     cudaStream_t side_stream = nullptr;  // forked from `stream` for the bit-packed compaction kernel (runs under the HBM-bound ones)
     bool bits_overlap = true;            // RVL_OPT_BITS_OVERLAP
-    int string_kernel = 2;               // RVL_OPT_STRING_KERNEL: 1 = round-1 kernel pair, 2 = ranges sizes pass + TMA-staged gather
+    int string_kernel = 3;               // RVL_OPT_STRING_KERNEL: 1 = round-1 pair; 2 = ranges sizes pass + persistent TMA-staged gather;
+                                         //   3 = ranges sizes pass + round-1 gather (default: fastest measured); 4 = 3 with the OR-merging copy
     int string_dense_min = 128;          // RVL_OPT_STRING_DENSE_MIN: survivors per 1024-row sub-tile from which the source block is TMA-staged
     int exact_alloc = 2;                 // RVL_OPT_EXACT_ALLOC: 0 never, 1 always, 2 when the worst case exceeds a quarter of device memory
     size_t device_bytes = 0;

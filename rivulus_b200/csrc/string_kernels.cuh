@@ -264,185 +264,7 @@ static __global__ void __launch_bounds__(kBlock, 6) string_sizes_kernel(const __
     if (tid == 0) *p.bytes_total_out = (unsigned long long)((p.byte_base_in != nullptr ? (uint64_t)*p.byte_base_in : 0ull) + carry);
 }
 
-constexpr uint32_t kStrChunk = 16 * 1024;   // staging bytes per pass (a 2048-row tile of ~24-byte strings at 50 % fits in one)
-
-static __global__ void __launch_bounds__(kBlock, 6) string_gather_kernel(const __grid_constant__ StrGatherParams p) {
-    __shared__ __align__(16) int32_t s_src[kTileRows];        // survivor r: first source byte
-    __shared__ __align__(16) uint32_t s_dst[kTileRows + 8];   // survivor r: length, then first destination byte inside the tile's dense range; [count..] = total
-    __shared__ __align__(16) uint8_t s_stage[kStrChunk + 16];
-    __shared__ uint32_t s_warp[kWarps];
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t tile = blockIdx.x;
-    const int64_t tile_row0 = tile * kTileRows;
-    const uint32_t lt = lanemask_lt();
-
-    // ---- A. the tile's 64 selection words, every warp redundantly (lane holds words lane and lane + 32): survivor counts in
-    //         front of any warp are two warp reductions away, no barrier
-    auto tail_mask = [&](int64_t r) -> uint32_t {   // rows [r, r + 32) that exist
-        const int64_t rem = p.n_rows - r;
-        return rem >= 32 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
-    };
-    uint32_t w0, w1;
-    if (p.sel != nullptr) { const uint32_t* sw = p.sel + tile * kTileWords; w0 = __ldg(sw + lane); w1 = __ldg(sw + 32 + lane); }
-    else { w0 = tail_mask(tile_row0 + 32 * lane); w1 = tail_mask(tile_row0 + 32 * (lane + 32)); }
-    uint64_t rexcl = p.tile_prefix != nullptr ? p.tile_prefix[tile] : (uint64_t)(p.row_base + tile * kTileRows);
-    if (p.chunk_base != nullptr) rexcl = p.chunk_base[tile / p.tiles_per_chunk] + (rexcl >> 12);
-    const uint64_t rbase = p.row_base_in != nullptr ? (uint64_t)*p.row_base_in : 0ull;
-    const uint32_t c0 = __popc(w0), c1 = __popc(w1);
-    const uint32_t cnt_total = __reduce_add_sync(0xFFFFFFFFu, c0 + c1);
-    const int first_word = warp * 8;               // this warp's rows are selection words [first_word, first_word + 8)
-    uint32_t run = first_word < 32 ? __reduce_add_sync(0xFFFFFFFFu, lane < first_word ? c0 : 0u)
-                                   : __reduce_add_sync(0xFFFFFFFFu, c0) + __reduce_add_sync(0xFFFFFFFFu, lane < first_word - 32 ? c1 : 0u);
-    const uint32_t wsel = first_word < 32 ? w0 : w1;
-    uint32_t cnt_lim = cnt_total;
-    if (p.limit >= 0) cnt_lim = rexcl >= (uint64_t)p.limit ? 0u : (uint32_t)min((uint64_t)cnt_total, (uint64_t)p.limit - rexcl);
-
-    // ---- B. lane <-> row: offsets read coalesced, (source offset, length) of every survivor stored at its rank
-    //         (nulls are zero-length: string.rs:33-36; survivors beyond the LIMIT are simply not stored).
-    //         A warp whose 256 rows hold no survivor skips its loads; otherwise it reads its 257 offsets in nine coalesced
-    //         loads (lane <-> row of each 32-row group; the end of a group is lane 0 of the next one).
-    const int64_t wrow0 = tile_row0 + (int64_t)warp * 256;
-    const uint32_t wany = __ballot_sync(0xFFFFFFFFu, lane >= (first_word & 31) && lane < (first_word & 31) + 8 && wsel != 0u);
-    if (wany != 0u) {
-        uint32_t vwv = 0xFFFFFFFFu;
-        if (p.valid.words != nullptr && lane < 8) vwv = load_bits32(p.valid, (uint64_t)(wrow0 + 32 * lane));
-        int32_t o[9];
-        const int32_t* const offw = p.offsets + wrow0 + lane;
-        if (wrow0 + 256 + 32 <= p.n_rows) {
-#pragma unroll
-            for (int g = 0; g < 9; ++g) o[g] = __ldg(offw + 32 * g);
-        } else {
-#pragma unroll
-            for (int g = 0; g < 9; ++g) o[g] = wrow0 + 32 * g + lane <= p.n_rows ? __ldg(offw + 32 * g) : 0;
-        }
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            const uint32_t selw = __shfl_sync(0xFFFFFFFFu, wsel, (first_word + g) & 31);
-            const uint32_t vw = __shfl_sync(0xFFFFFFFFu, vwv, g);
-            int32_t o1 = __shfl_down_sync(0xFFFFFFFFu, o[g], 1);
-            const int32_t onext = __shfl_sync(0xFFFFFFFFu, o[g + 1], 0);
-            if (lane == 31) o1 = onext;
-            const uint32_t r = run + __popc(selw & lt);
-            run += __popc(selw);
-            if (((selw >> lane) & 1u) != 0u && r < cnt_lim) {
-                const uint32_t len = ((vw >> lane) & 1u) ? (uint32_t)(o1 - o[g]) : 0u;
-                s_src[r] = o[g]; s_dst[r] = len;
-                // pull the survivor's first line towards L2 now: the copy phase is a block scan away
-                if (len != 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.data + o[g]));
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- C. lengths -> exclusive byte offsets, in place: 8 ranks per thread, one block scan
-    uint32_t b0, bytes_total;
-    {
-        const uint32_t base = (uint32_t)tid * 8u;
-        uint32_t v[8];
-        const uint4 x = *reinterpret_cast<const uint4*>(&s_dst[base]), y = *reinterpret_cast<const uint4*>(&s_dst[base + 4]);
-        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
-        uint32_t sum = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { const uint32_t t = base + i < cnt_lim ? v[i] : 0u; v[i] = sum; sum += t; }
-        b0 = block_exclusive_scan(sum, s_warp, bytes_total);
-        uint4 ox, oy;
-        ox.x = b0 + v[0]; ox.y = b0 + v[1]; ox.z = b0 + v[2]; ox.w = b0 + v[3];
-        oy.x = b0 + v[4]; oy.y = b0 + v[5]; oy.z = b0 + v[6]; oy.w = b0 + v[7];
-        *reinterpret_cast<uint4*>(&s_dst[base]) = ox; *reinterpret_cast<uint4*>(&s_dst[base + 4]) = oy;
-        if (tid == kBlock - 1) s_dst[kTileRows] = bytes_total;   // entries at and beyond cnt_lim hold the total
-    }
-
-    // global byte prefix of the tile: computed by string_sizes_kernel, so tiles do not wait on each other
-    const uint64_t bexcl = (p.byte_base_in != nullptr ? (uint64_t)*p.byte_base_in : 0ull) + p.tile_bytes[tile];
-    __syncthreads();
-    if (cnt_lim == 0u) return;
-
-    // new offsets, in rank order: out_offsets[first survivor of the tile + r + 1] = end of survivor r (coalesced)
-    {
-        int32_t* oo = p.out_offsets + (rexcl - rbase) + 1;
-        for (uint32_t r = tid; r < cnt_lim; r += kBlock) oo[r] = (int32_t)(bexcl + s_dst[r + 1]);
-    }
-
-    // Byte copy, staged through shared memory.  The tile's destination range is dense, so it is assembled in a staging buffer
-    // laid out like the destination modulo 16 bytes and flushed with aligned 16-byte stores; only the first and last unit of
-    // a tile (shared with the neighbouring tiles) are written byte-wise.  Gather side: every lane holds the descriptor of one
-    // survivor of a 256-survivor group; short strings are moved one lane per string, word-wise (copy_descriptor_per_lane), long
-    // ones cooperatively, the warp walking its 32 descriptors with all lanes over the bytes of one string (copy_descriptors<32>).
-    // Ranges longer than the staging buffer take several chunks.
-    const bool per_lane = bytes_total / cnt_lim <= 96u;   // mean survivor length: short strings go one lane per string
-    const uint32_t pad = (uint32_t)(reinterpret_cast<uintptr_t>(p.out_data + bexcl) & 15u);
-    const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(s_stage);
-    uint32_t g_lo = 0;
-#pragma unroll 1
-    for (uint32_t c0 = 0; c0 < bytes_total; c0 += kStrChunk) {
-        const uint32_t c1 = min(bytes_total, c0 + kStrChunk);
-        uint32_t g = g_lo;
-#pragma unroll 1
-        for (; g * kBlock < cnt_lim && s_dst[g * kBlock] < c1; ++g) {
-            const uint32_t q = g * kBlock + (uint32_t)tid;
-            uint32_t my_d = 0, my_n = 0, my_s = 0;
-            if (q < cnt_lim) {
-                const uint32_t d = s_dst[q], e = s_dst[q + 1];
-                const uint32_t lo = max(d, c0), hi = min(e, c1);
-                if (lo < hi) { my_n = hi - lo; my_d = lo - c0 + pad; my_s = (uint32_t)s_src[q] + (lo - d); }
-            }
-            if (__ballot_sync(0xFFFFFFFFu, my_n != 0u) == 0u) continue;
-            if (per_lane) copy_descriptor_per_lane(p.data, stage_addr, my_n, my_d, my_s);
-            else copy_descriptors<32>(p.data, stage_addr, my_n, my_d, my_s, lane);
-        }
-        g_lo = g > g_lo ? g - 1u : g_lo;  // the last group may straddle the chunk boundary
-        __syncthreads();
-        uint8_t* const gbase = p.out_data + bexcl + c0 - pad;  // 16-byte aligned
-        const uint32_t end = pad + (c1 - c0);
-        for (uint32_t u = tid; u * 16u < end; u += kBlock) {
-            const uint32_t b0 = u * 16u, b1 = b0 + 16u;
-            if (b0 >= pad && b1 <= end) {
-                const uint4 v = *reinterpret_cast<const uint4*>(s_stage + b0);
-                asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(gbase + b0), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-            } else {
-                for (uint32_t k = max(b0, pad); k < min(b1, end); ++k) gbase[k] = s_stage[k];
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// =====================================================================================================================
-// Round-2 string kernels.  What round 1's ncu said about the pair above: the gather is instruction- and LSU-bound (~1000 warp
-// instructions per warp and tile, every source word a divergent, bounds-checked LDG), the sizes pass is 24 K short CTAs plus a serial
-// ticketed prefix tail.  Changes:
-//   string_sizes_ranges_kernel   persistent; every warp owns a contiguous range of tiles (the predicate scan's shape), streams the
-//                                offsets lane <-> row and leaves per-sub-tile byte prefixes inside its range; the last CTA scans
-//                                the <= 2368 range totals once.  No tile waits on another, no serial tail.
-//   string_gather_staged_kernel  persistent, three CTAs per SM, each walking 1024-row sub-tiles one iteration ahead of its global loads
-//                                (selection words, prefixes and the 1025 offsets of the NEXT sub-tile sit in registers while the
-//                                current one is processed; the first version, one CTA per sub-tile, spent 8 us per CTA on four
-//                                dependent round trips: 670 us per 50 M rows whatever the selectivity).
-//                                The sub-tile's source bytes are ONE contiguous block of the data
-//                                buffer (consecutive rows are adjacent), so dense sub-tiles fetch it with a single TMA bulk copy
-//                                (cp.async.bulk + mbarrier) into shared memory while the ranks / lengths / byte offsets are being
-//                                computed from the offsets (also staged in shared memory); the word-wise funnel-shift copy then
-//                                runs shared -> shared (unguarded LDS instead of guarded, divergent LDG), string boundaries are
-//                                merged with shared-memory atomic ORs into a zeroed staging buffer instead of byte-wise
-//                                predicated stores, and the dense destination range is flushed with 16-byte stores.
-//                                Sparse sub-tiles (few survivors) and blocks larger than the buffer read the survivors' words from
-//                                global memory with the same routine.  Strings longer than 64 bytes are copied by the whole warp.
-constexpr int kStrRows = 1024;                 // rows per string sub-tile: half a selection tile
-constexpr int kStrWords = kStrRows / 32;
-constexpr uint32_t kStrSrcCap = 32 * 1024;     // source block buffer (a 1024-row sub-tile of ~24-byte strings is ~22 KB)
-constexpr uint32_t kStrStage = 11 * 1024;      // destination staging chunk
-constexpr uint32_t kStrLong = 64;              // longer strings are copied cooperatively
-
-struct __align__(128) StrSmem {
-    uint8_t src[kStrSrcCap + 64];              // [16 bytes slack][block, 16-byte aligned][slack]
-    uint8_t stage[kStrStage + 32];
-    int32_t offs[2][kStrRows + 8];             // offsets of the current / the next sub-tile's rows (+ the end)
-    int32_t s_src[kStrRows];                   // survivor r: first source byte (absolute offset into the data buffer)
-    uint32_t s_dst[kStrRows + 8];              // survivor r: length, then first destination byte inside the sub-tile's dense range
-    uint32_t s_warp[kWarps];
-    uint64_t mbar;
-};
+constexpr uint32_t kStrLong = 64;   // longer strings are copied cooperatively by the whole warp
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     uint32_t v;
@@ -543,6 +365,203 @@ __device__ __forceinline__ uint32_t keep_lowest_set(uint32_t w, uint32_t k) {
     while ((uint32_t)__popc(w) > k) w &= ~(0x80000000u >> __clz(w));
     return w;
 }
+
+constexpr uint32_t kStrChunk = 16 * 1024;   // staging bytes per pass (a 2048-row tile of ~24-byte strings at 50 % fits in one)
+
+// COPY = 0: round-1 copy routines (byte-wise predicated stores at string boundaries).  COPY = 1: the round-2 lane / warp copy
+// routines into a ZEROED staging buffer (boundary words OR-ed in with shared-memory atomics).
+template <int COPY>
+static __global__ void __launch_bounds__(kBlock, 6) string_gather_kernel(const __grid_constant__ StrGatherParams p) {
+    __shared__ __align__(16) int32_t s_src[kTileRows];        // survivor r: first source byte
+    __shared__ __align__(16) uint32_t s_dst[kTileRows + 8];   // survivor r: length, then first destination byte inside the tile's dense range; [count..] = total
+    __shared__ __align__(16) uint8_t s_stage[kStrChunk + 16];
+    __shared__ uint32_t s_warp[kWarps];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t tile = blockIdx.x;
+    const int64_t tile_row0 = tile * kTileRows;
+    const uint32_t lt = lanemask_lt();
+
+    // ---- A. the tile's 64 selection words, every warp redundantly (lane holds words lane and lane + 32): survivor counts in
+    //         front of any warp are two warp reductions away, no barrier
+    auto tail_mask = [&](int64_t r) -> uint32_t {   // rows [r, r + 32) that exist
+        const int64_t rem = p.n_rows - r;
+        return rem >= 32 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+    };
+    uint32_t w0, w1;
+    if (p.sel != nullptr) { const uint32_t* sw = p.sel + tile * kTileWords; w0 = __ldg(sw + lane); w1 = __ldg(sw + 32 + lane); }
+    else { w0 = tail_mask(tile_row0 + 32 * lane); w1 = tail_mask(tile_row0 + 32 * (lane + 32)); }
+    uint64_t rexcl = p.tile_prefix != nullptr ? p.tile_prefix[tile] : (uint64_t)(p.row_base + tile * kTileRows);
+    if (p.chunk_base != nullptr) rexcl = p.chunk_base[tile / p.tiles_per_chunk] + (rexcl >> 12);
+    const uint64_t rbase = p.row_base_in != nullptr ? (uint64_t)*p.row_base_in : 0ull;
+    const uint32_t c0 = __popc(w0), c1 = __popc(w1);
+    const uint32_t cnt_total = __reduce_add_sync(0xFFFFFFFFu, c0 + c1);
+    const int first_word = warp * 8;               // this warp's rows are selection words [first_word, first_word + 8)
+    uint32_t run = first_word < 32 ? __reduce_add_sync(0xFFFFFFFFu, lane < first_word ? c0 : 0u)
+                                   : __reduce_add_sync(0xFFFFFFFFu, c0) + __reduce_add_sync(0xFFFFFFFFu, lane < first_word - 32 ? c1 : 0u);
+    const uint32_t wsel = first_word < 32 ? w0 : w1;
+    uint32_t cnt_lim = cnt_total;
+    if (p.limit >= 0) cnt_lim = rexcl >= (uint64_t)p.limit ? 0u : (uint32_t)min((uint64_t)cnt_total, (uint64_t)p.limit - rexcl);
+
+    // ---- B. lane <-> row: offsets read coalesced, (source offset, length) of every survivor stored at its rank
+    //         (nulls are zero-length: string.rs:33-36; survivors beyond the LIMIT are simply not stored).
+    //         A warp whose 256 rows hold no survivor skips its loads; otherwise it reads its 257 offsets in nine coalesced
+    //         loads (lane <-> row of each 32-row group; the end of a group is lane 0 of the next one).
+    const int64_t wrow0 = tile_row0 + (int64_t)warp * 256;
+    const uint32_t wany = __ballot_sync(0xFFFFFFFFu, lane >= (first_word & 31) && lane < (first_word & 31) + 8 && wsel != 0u);
+    if (wany != 0u) {
+        uint32_t vwv = 0xFFFFFFFFu;
+        if (p.valid.words != nullptr && lane < 8) vwv = load_bits32(p.valid, (uint64_t)(wrow0 + 32 * lane));
+        int32_t o[9];
+        const int32_t* const offw = p.offsets + wrow0 + lane;
+        if (wrow0 + 256 + 32 <= p.n_rows) {
+#pragma unroll
+            for (int g = 0; g < 9; ++g) o[g] = __ldg(offw + 32 * g);
+        } else {
+#pragma unroll
+            for (int g = 0; g < 9; ++g) o[g] = wrow0 + 32 * g + lane <= p.n_rows ? __ldg(offw + 32 * g) : 0;
+        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const uint32_t selw = __shfl_sync(0xFFFFFFFFu, wsel, (first_word + g) & 31);
+            const uint32_t vw = __shfl_sync(0xFFFFFFFFu, vwv, g);
+            int32_t o1 = __shfl_down_sync(0xFFFFFFFFu, o[g], 1);
+            const int32_t onext = __shfl_sync(0xFFFFFFFFu, o[g + 1], 0);
+            if (lane == 31) o1 = onext;
+            const uint32_t r = run + __popc(selw & lt);
+            run += __popc(selw);
+            if (((selw >> lane) & 1u) != 0u && r < cnt_lim) {
+                const uint32_t len = ((vw >> lane) & 1u) ? (uint32_t)(o1 - o[g]) : 0u;
+                s_src[r] = o[g]; s_dst[r] = len;
+                // pull the survivor's first line towards L2 now: the copy phase is a block scan away
+                if (len != 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.data + o[g]));
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- C. lengths -> exclusive byte offsets, in place: 8 ranks per thread, one block scan
+    uint32_t b0, bytes_total;
+    {
+        const uint32_t base = (uint32_t)tid * 8u;
+        uint32_t v[8];
+        const uint4 x = *reinterpret_cast<const uint4*>(&s_dst[base]), y = *reinterpret_cast<const uint4*>(&s_dst[base + 4]);
+        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+        uint32_t sum = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const uint32_t t = base + i < cnt_lim ? v[i] : 0u; v[i] = sum; sum += t; }
+        b0 = block_exclusive_scan(sum, s_warp, bytes_total);
+        uint4 ox, oy;
+        ox.x = b0 + v[0]; ox.y = b0 + v[1]; ox.z = b0 + v[2]; ox.w = b0 + v[3];
+        oy.x = b0 + v[4]; oy.y = b0 + v[5]; oy.z = b0 + v[6]; oy.w = b0 + v[7];
+        *reinterpret_cast<uint4*>(&s_dst[base]) = ox; *reinterpret_cast<uint4*>(&s_dst[base + 4]) = oy;
+        if (tid == kBlock - 1) s_dst[kTileRows] = bytes_total;   // entries at and beyond cnt_lim hold the total
+    }
+
+    // global byte prefix of the tile: computed by string_sizes_kernel, so tiles do not wait on each other
+    // (the ranges sizes pass folds the byte base into range_bytes and keeps one prefix per 1024-row half: the tile's is the first half's)
+    const uint64_t bexcl = p.sub_bytes != nullptr ? p.range_bytes[tile / p.tiles_per_range] + p.sub_bytes[2 * tile]
+                                                  : (p.byte_base_in != nullptr ? (uint64_t)*p.byte_base_in : 0ull) + p.tile_bytes[tile];
+    __syncthreads();
+    if (cnt_lim == 0u) return;
+
+    // new offsets, in rank order: out_offsets[first survivor of the tile + r + 1] = end of survivor r (coalesced)
+    {
+        int32_t* oo = p.out_offsets + (rexcl - rbase) + 1;
+        for (uint32_t r = tid; r < cnt_lim; r += kBlock) oo[r] = (int32_t)(bexcl + s_dst[r + 1]);
+    }
+
+    // Byte copy, staged through shared memory.  The tile's destination range is dense, so it is assembled in a staging buffer
+    // laid out like the destination modulo 16 bytes and flushed with aligned 16-byte stores; only the first and last unit of
+    // a tile (shared with the neighbouring tiles) are written byte-wise.  Gather side: every lane holds the descriptor of one
+    // survivor of a 256-survivor group; short strings are moved one lane per string, word-wise (copy_descriptor_per_lane), long
+    // ones cooperatively, the warp walking its 32 descriptors with all lanes over the bytes of one string (copy_descriptors<32>).
+    // Ranges longer than the staging buffer take several chunks.
+    const bool per_lane = bytes_total / cnt_lim <= 96u;   // mean survivor length: short strings go one lane per string
+    const uint32_t pad = (uint32_t)(reinterpret_cast<uintptr_t>(p.out_data + bexcl) & 15u);
+    const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(s_stage);
+    uint32_t g_lo = 0;
+#pragma unroll 1
+    for (uint32_t c0 = 0; c0 < bytes_total; c0 += kStrChunk) {
+        const uint32_t c1 = min(bytes_total, c0 + kStrChunk);
+        if (COPY == 1) {
+            for (uint32_t u = tid; u < (kStrChunk + 16) / 16; u += kBlock) *reinterpret_cast<uint4*>(s_stage + u * 16u) = make_uint4(0u, 0u, 0u, 0u);
+            __syncthreads();
+        }
+        uint32_t g = g_lo;
+#pragma unroll 1
+        for (; g * kBlock < cnt_lim && s_dst[g * kBlock] < c1; ++g) {
+            const uint32_t q = g * kBlock + (uint32_t)tid;
+            uint32_t my_d = 0, my_n = 0, my_s = 0;
+            if (q < cnt_lim) {
+                const uint32_t d = s_dst[q], e = s_dst[q + 1];
+                const uint32_t lo = max(d, c0), hi = min(e, c1);
+                if (lo < hi) { my_n = hi - lo; my_d = lo - c0 + pad; my_s = (uint32_t)s_src[q] + (lo - d); }
+            }
+            if (__ballot_sync(0xFFFFFFFFu, my_n != 0u) == 0u) continue;
+            if (COPY == 1) {
+                uint32_t longs = __ballot_sync(0xFFFFFFFFu, my_n > kStrLong);
+                copy_string_lane<false>(0u, p.data + my_s, stage_addr + my_d, my_n > kStrLong ? 0u : my_n);
+                while (longs != 0u) {
+                    const int l = __ffs(longs) - 1;
+                    longs &= longs - 1u;
+                    const uint32_t n = __shfl_sync(0xFFFFFFFFu, my_n, l), d = __shfl_sync(0xFFFFFFFFu, my_d, l), s0 = __shfl_sync(0xFFFFFFFFu, my_s, l);
+                    copy_string_warp<false>(0u, p.data + s0, stage_addr + d, n, lane);
+                }
+            } else if (per_lane) copy_descriptor_per_lane(p.data, stage_addr, my_n, my_d, my_s);
+            else copy_descriptors<32>(p.data, stage_addr, my_n, my_d, my_s, lane);
+        }
+        g_lo = g > g_lo ? g - 1u : g_lo;  // the last group may straddle the chunk boundary
+        __syncthreads();
+        uint8_t* const gbase = p.out_data + bexcl + c0 - pad;  // 16-byte aligned
+        const uint32_t end = pad + (c1 - c0);
+        for (uint32_t u = tid; u * 16u < end; u += kBlock) {
+            const uint32_t b0 = u * 16u, b1 = b0 + 16u;
+            if (b0 >= pad && b1 <= end) {
+                const uint4 v = *reinterpret_cast<const uint4*>(s_stage + b0);
+                asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(gbase + b0), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+            } else {
+                for (uint32_t k = max(b0, pad); k < min(b1, end); ++k) gbase[k] = s_stage[k];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// =====================================================================================================================
+// Round-2 string kernels.  What round 1's ncu said about the pair above: the gather is instruction- and LSU-bound (~1000 warp
+// instructions per warp and tile, every source word a divergent, bounds-checked LDG), the sizes pass is 24 K short CTAs plus a serial
+// ticketed prefix tail.  Changes:
+//   string_sizes_ranges_kernel   persistent; every warp owns a contiguous range of tiles (the predicate scan's shape), streams the
+//                                offsets lane <-> row and leaves per-sub-tile byte prefixes inside its range; the last CTA scans
+//                                the <= 2368 range totals once.  No tile waits on another, no serial tail.
+//   string_gather_staged_kernel  persistent, three CTAs per SM, each walking 1024-row sub-tiles one iteration ahead of its global loads
+//                                (selection words, prefixes and the 1025 offsets of the NEXT sub-tile sit in registers while the
+//                                current one is processed; the first version, one CTA per sub-tile, spent 8 us per CTA on four
+//                                dependent round trips: 670 us per 50 M rows whatever the selectivity).
+//                                The sub-tile's source bytes are ONE contiguous block of the data
+//                                buffer (consecutive rows are adjacent), so dense sub-tiles fetch it with a single TMA bulk copy
+//                                (cp.async.bulk + mbarrier) into shared memory while the ranks / lengths / byte offsets are being
+//                                computed from the offsets (also staged in shared memory); the word-wise funnel-shift copy then
+//                                runs shared -> shared (unguarded LDS instead of guarded, divergent LDG), string boundaries are
+//                                merged with shared-memory atomic ORs into a zeroed staging buffer instead of byte-wise
+//                                predicated stores, and the dense destination range is flushed with 16-byte stores.
+//                                Sparse sub-tiles (few survivors) and blocks larger than the buffer read the survivors' words from
+//                                global memory with the same routine.  Strings longer than 64 bytes are copied by the whole warp.
+constexpr int kStrRows = 1024;                 // rows per string sub-tile: half a selection tile
+constexpr int kStrWords = kStrRows / 32;
+constexpr uint32_t kStrSrcCap = 32 * 1024;     // source block buffer (a 1024-row sub-tile of ~24-byte strings is ~22 KB)
+constexpr uint32_t kStrStage = 11 * 1024;      // destination staging chunk
+
+struct __align__(128) StrSmem {
+    uint8_t src[kStrSrcCap + 64];              // [16 bytes slack][block, 16-byte aligned][slack]
+    uint8_t stage[kStrStage + 32];
+    int32_t offs[2][kStrRows + 8];             // offsets of the current / the next sub-tile's rows (+ the end)
+    int32_t s_src[kStrRows];                   // survivor r: first source byte (absolute offset into the data buffer)
+    uint32_t s_dst[kStrRows + 8];              // survivor r: length, then first destination byte inside the sub-tile's dense range
+    uint32_t s_warp[kWarps];
+    uint64_t mbar;
+};
 
 // Survivor bytes of every 1024-row sub-tile as an exclusive prefix inside the owning warp's range of tiles, the range totals, and
 // (last CTA, by ticket) the ranges' global byte bases + the grand total.

@@ -43,7 +43,7 @@ HOST_SYMBOLS = [
     "rvh_df_col_len", "rvh_df_col_str_bytes", "rvh_df_col_export", "rvh_df_col_buffers",
     "rvh_expr_col", "rvh_expr_lit", "rvh_expr_binary", "rvh_expr_alias", "rvh_expr_free",
     "rvh_lf_from_df", "rvh_lf_select", "rvh_lf_filter", "rvh_lf_limit", "rvh_lf_free", "rvh_lf_collect", "rvh_lf_collect_streaming",
-    "rvh_lf_plan_shape",
+    "rvh_lf_plan_shape", "rvh_lf_schema", "rvh_lf_validate", "rvh_lf_describe",
     "rvh_rb_try_new", "rvh_rb_free", "rvh_rb_num_rows", "rvh_rb_num_columns", "rvh_rb_col_name", "rvh_rb_col_dtype", "rvh_rb_col_export",
     "rvh_rb_slice", "rvh_rb_take", "rvh_rb_select", "rvh_rb_select_by_name", "rvh_rb_filter", "rvh_rb_concat", "rvh_rb_empty_like",
     "rvh_sp_memory_source", "rvh_sp_dataframe_source", "rvh_sp_filter", "rvh_sp_select", "rvh_sp_limit", "rvh_sp_free", "rvh_sp_collect",
@@ -358,6 +358,22 @@ class LazyFrame:
     def plan_shape(self) -> str:
         buf = C.create_string_buffer(256)
         _check(lib().rvh_lf_plan_shape(_vp(self._h), buf, 256))
+        return buf.value.decode()
+
+    def schema(self):
+        """logical_plan.schema() of the plan as built: [(name, dtype name)] (logical_plan/plan.rs:63-113)."""
+        buf = C.create_string_buffer(4096)
+        _check(lib().rvh_lf_schema(_vp(self._h), buf, 4096))
+        return [tuple(x.split(":")) for x in buf.value.decode().split(",") if x]
+
+    def validate(self):
+        """logical_plan.validate() of the plan as built (logical_plan/plan.rs:115-202); raises on ColumnNotFound."""
+        _check(lib().rvh_lf_validate(_vp(self._h)))
+
+    def describe(self) -> str:
+        """Debug-style dump of the plan as built (node kinds, expression trees)."""
+        buf = C.create_string_buffer(8192)
+        _check(lib().rvh_lf_describe(_vp(self._h), buf, 8192))
         return buf.value.decode()
 
 

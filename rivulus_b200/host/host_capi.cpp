@@ -62,18 +62,17 @@ int rvh_dfb_add_empty_series(void* h, const char* name, int dtype) {
 }
 // columnar ingestion (Arrow buffers; validity_bits LSB-first or NULL)
 int rvh_dfb_add_i64(void* h, const char* name, int64_t n, const int64_t* v, const uint8_t* validity_bits) {
-    return guard([&] { ((DfBuilder*)h)->cols.push_back(Series::from_i64(name, std::vector<int64_t>(v, v + n), bits_or_empty(validity_bits, n))); });
+    return guard([&] { ((DfBuilder*)h)->cols.push_back(Series::from_i64(name, v, (size_t)n, validity_bits)); });
 }
 int rvh_dfb_add_f64(void* h, const char* name, int64_t n, const double* v, const uint8_t* validity_bits) {
-    return guard([&] { ((DfBuilder*)h)->cols.push_back(Series::from_f64(name, std::vector<double>(v, v + n), bits_or_empty(validity_bits, n))); });
+    return guard([&] { ((DfBuilder*)h)->cols.push_back(Series::from_f64(name, v, (size_t)n, validity_bits)); });
 }
 int rvh_dfb_add_bool_bits(void* h, const char* name, int64_t n, const uint8_t* value_bits, const uint8_t* validity_bits) {
-    return guard([&] { ((DfBuilder*)h)->cols.push_back(Series::from_bool_bits(name, bits_or_empty(value_bits, n), (size_t)n, bits_or_empty(validity_bits, n))); });
+    return guard([&] { ((DfBuilder*)h)->cols.push_back(Series::from_bool_bits(name, value_bits, (size_t)n, validity_bits)); });
 }
 int rvh_dfb_add_strings(void* h, const char* name, int64_t n, const int32_t* offsets, const uint8_t* data, const uint8_t* validity_bits) {
     return guard([&] {
-        ((DfBuilder*)h)->cols.push_back(Series::from_strings(name, std::vector<int32_t>(offsets, offsets + n + 1),
-                                                              std::vector<uint8_t>(data, data + offsets[n]), bits_or_empty(validity_bits, n)));
+        ((DfBuilder*)h)->cols.push_back(Series::from_strings(name, offsets, (size_t)n, data, validity_bits));
     });
 }
 int rvh_dfb_finish(void* h, void** out) {
@@ -204,6 +203,18 @@ int rvh_lf_collect(void* lf, void** df_out) {
 }
 int rvh_lf_collect_streaming(void* lf, void** rb_out) {
     return guard([&] { *rb_out = new RbHandle{((LazyFrame*)lf)->collect_streaming(), {}}; });
+}
+// logical_plan/plan.rs probes on the plan as built (not optimized)
+int rvh_lf_schema(void* lf, char* buf, int cap) {
+    return guard([&] {
+        std::string s;
+        for (const auto& pr : ((LazyFrame*)lf)->logical_plan().schema()) s += (s.empty() ? "" : ",") + pr.first + ":" + dtype_name(pr.second);
+        std::snprintf(buf, (size_t)cap, "%s", s.c_str());
+    });
+}
+int rvh_lf_validate(void* lf) { return guard([&] { ((LazyFrame*)lf)->logical_plan().validate(); }); }
+int rvh_lf_describe(void* lf, char* buf, int cap) {
+    return guard([&] { std::snprintf(buf, (size_t)cap, "%s", ((LazyFrame*)lf)->logical_plan().describe().c_str()); });
 }
 int rvh_lf_plan_shape(void* lf, char* buf, int cap) {  // optimized plan, "Filter(Select(Source))"-style
     return guard([&] { std::snprintf(buf, (size_t)cap, "%s", optimize(((LazyFrame*)lf)->logical_plan()).shape().c_str()); });

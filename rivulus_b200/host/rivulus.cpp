@@ -13,6 +13,78 @@
 
 namespace rivulus {
 
+// ------------------------------------------------------------------------------------------------- page-locked host buffers
+namespace {
+constexpr size_t kPinMin = 64 * 1024;          // smaller buffers are not worth a pinned block
+constexpr size_t kPoolKeepBytes = 2ull << 30;  // cached (free) pinned bytes kept for reuse
+struct PinnedPool {
+    std::mutex mu;
+    std::map<size_t, std::vector<void*>> free_by_class;   // size class (power of two) -> free blocks
+    std::set<void*> pinned;                               // every live or cached pinned block
+    size_t cached = 0;
+    bool unavailable = false;                             // cudaHostAlloc failed once (no usable device): stop asking
+    ~PinnedPool() {}                                      // blocks are returned to the driver at process exit
+};
+PinnedPool& pool() { static PinnedPool* p = new PinnedPool(); return *p; }   // intentionally leaked: buffers may outlive static destruction
+size_t size_class(size_t bytes) { size_t c = kPinMin; while (c < bytes) c <<= 1; return c; }
+}  // namespace
+
+void* host_buffer_alloc(size_t bytes) {
+    if (bytes == 0) bytes = 1;
+    if (bytes >= kPinMin) {
+        PinnedPool& P = pool();
+        const size_t cls = size_class(bytes);
+        {
+            std::lock_guard<std::mutex> g(P.mu);
+            auto it = P.free_by_class.find(cls);
+            if (it != P.free_by_class.end() && !it->second.empty()) {
+                void* p = it->second.back(); it->second.pop_back(); P.cached -= cls;
+                return p;
+            }
+            if (P.unavailable) goto pageable;
+        }
+        void* p = nullptr;
+        if (rvl_host_alloc(cls, &p) == RVL_OK && p != nullptr) {
+            std::lock_guard<std::mutex> g(P.mu);
+            P.pinned.insert(p);
+            return p;
+        }
+        { std::lock_guard<std::mutex> g(P.mu); P.unavailable = true; }
+    }
+pageable:
+    void* p = std::malloc(bytes);
+    if (!p) throw std::bad_alloc();
+    return p;
+}
+
+void host_buffer_free(void* p, size_t bytes) {
+    if (!p) return;
+    if (bytes >= kPinMin) {
+        PinnedPool& P = pool();
+        std::unique_lock<std::mutex> g(P.mu);
+        if (P.pinned.count(p)) {
+            const size_t cls = size_class(bytes);
+            if (P.cached + cls <= kPoolKeepBytes) { P.free_by_class[cls].push_back(p); P.cached += cls; return; }
+            P.pinned.erase(p);
+            g.unlock();
+            rvl_host_free(p);
+            return;
+        }
+    }
+    std::free(p);
+}
+
+void host_buffer_pool_trim() {
+    PinnedPool& P = pool();
+    std::vector<void*> drop;
+    {
+        std::lock_guard<std::mutex> g(P.mu);
+        for (auto& kv : P.free_by_class) { for (void* p : kv.second) { drop.push_back(p); P.pinned.erase(p); } kv.second.clear(); }
+        P.cached = 0;
+    }
+    for (void* p : drop) rvl_host_free(p);
+}
+
 // ------------------------------------------------------------------------------------------------- helpers
 static void check(int32_t rc) {
     if (rc != RVL_OK) {
@@ -20,9 +92,9 @@ static void check(int32_t rc) {
         throw Error(m ? m : "rivulus_gpu: unknown error", rc == RVL_OUT_OF_BOUNDS);
     }
 }
-static inline bool get_bit(const std::vector<uint8_t>& b, size_t i) { return (b[i >> 3] >> (i & 7)) & 1; }
-static inline void set_bit(std::vector<uint8_t>& b, size_t i) { b[i >> 3] |= (uint8_t)(1u << (i & 7)); }
-static size_t count_valid(const std::vector<uint8_t>& bits, size_t n) {
+template <class V> static inline bool get_bit(const V& b, size_t i) { return (b[i >> 3] >> (i & 7)) & 1; }
+template <class V> static inline void set_bit(V& b, size_t i) { b[i >> 3] |= (uint8_t)(1u << (i & 7)); }
+template <class V> static size_t count_valid(const V& bits, size_t n) {
     size_t c = 0;
     for (size_t i = 0; i < n; ++i) c += get_bit(bits, i);
     return c;
@@ -120,41 +192,41 @@ Series Series::make(const std::string& name, const std::vector<AnyValue>& data) 
     for (const auto& v : data) any_null |= v.is_null();
     if (dtype == DataType::Null) return s;
     if (any_null) {
-        s.validity_.assign((n + 7) / 8, 0);
-        for (size_t i = 0; i < n; ++i) if (!data[i].is_null()) set_bit(s.validity_, i);
+        s.b_->validity_.assign((n + 7) / 8, 0);
+        for (size_t i = 0; i < n; ++i) if (!data[i].is_null()) set_bit(s.b_->validity_, i);
     }
     switch (dtype) {
         case DataType::Int64:
-            s.i64_.resize(n);
-            for (size_t i = 0; i < n; ++i) s.i64_[i] = data[i].tag == AnyValue::kInt64 ? data[i].i : 0;
+            s.b_->i64_.resize(n);
+            for (size_t i = 0; i < n; ++i) s.b_->i64_[i] = data[i].tag == AnyValue::kInt64 ? data[i].i : 0;
             break;
         case DataType::Float64: {
-            s.f64_.resize(n);
+            s.b_->f64_.resize(n);
             const bool mixed = saw_int;
-            if (mixed) s.int_tag_.assign((n + 7) / 8, 0);
+            if (mixed) s.b_->int_tag_.assign((n + 7) / 8, 0);
             for (size_t i = 0; i < n; ++i) {
-                if (data[i].tag == AnyValue::kFloat64) s.f64_[i] = data[i].f;
+                if (data[i].tag == AnyValue::kFloat64) s.b_->f64_[i] = data[i].f;
                 else {
-                    s.f64_[i] = 0.0;
-                    if (data[i].tag == AnyValue::kInt64) { set_bit(s.int_tag_, i); std::memcpy(&s.f64_[i], &data[i].i, 8); }
+                    s.b_->f64_[i] = 0.0;
+                    if (data[i].tag == AnyValue::kInt64) { set_bit(s.b_->int_tag_, i); std::memcpy(&s.b_->f64_[i], &data[i].i, 8); }
                 }
             }
             break;
         }
         case DataType::Boolean:
-            s.bits_.assign((n + 7) / 8, 0);
-            for (size_t i = 0; i < n; ++i) if (data[i].tag == AnyValue::kBoolean && data[i].b) set_bit(s.bits_, i);
+            s.b_->bits_.assign((n + 7) / 8, 0);
+            for (size_t i = 0; i < n; ++i) if (data[i].tag == AnyValue::kBoolean && data[i].b) set_bit(s.b_->bits_, i);
             break;
         case DataType::String: {
-            s.offsets_.resize(n + 1);
-            s.offsets_[0] = 0;
+            s.b_->offsets_.resize(n + 1);
+            s.b_->offsets_[0] = 0;
             size_t total = 0;
             for (size_t i = 0; i < n; ++i) { if (data[i].tag == AnyValue::kString) total += data[i].s.size(); }
             if (total > (size_t)INT32_MAX) throw Error("String data exceeds int32 offsets");
-            s.data_.reserve(total);
+            s.b_->data_.reserve(total);
             for (size_t i = 0; i < n; ++i) {
-                if (data[i].tag == AnyValue::kString) s.data_.insert(s.data_.end(), data[i].s.begin(), data[i].s.end());
-                s.offsets_[i + 1] = (int32_t)s.data_.size();
+                if (data[i].tag == AnyValue::kString) s.b_->data_.insert(s.b_->data_.end(), data[i].s.begin(), data[i].s.end());
+                s.b_->offsets_[i + 1] = (int32_t)s.b_->data_.size();
             }
             break;
         }
@@ -165,70 +237,85 @@ Series Series::make(const std::string& name, const std::vector<AnyValue>& data) 
 
 Series Series::empty(const std::string& name, DataType dtype) {  // series.rs:223-229
     Series s; s.name_ = name; s.dtype_ = dtype; s.len_ = 0;
-    if (dtype == DataType::String) s.offsets_.assign(1, 0);
+    if (dtype == DataType::String) s.b_->offsets_.assign(1, 0);
     return s;
 }
 
 void Series::infer_from_validity() {
     if (len_ == 0) throw Error("Empty series not allowed");
-    if (!validity_.empty()) {
-        const size_t valid = count_valid(validity_, len_);
-        if (valid == len_) validity_.clear();
+    if (!b_->validity_.empty()) {
+        const size_t valid = count_valid(b_->validity_, len_);
+        if (valid == len_) b_->validity_.clear();
         else if (valid == 0) {  // every value null -> DataType::Null (series.rs:190-198)
             dtype_ = DataType::Null;
-            i64_.clear(); f64_.clear(); bits_.clear(); offsets_.clear(); data_.clear(); validity_.clear();
+            b_->i64_.clear(); b_->f64_.clear(); b_->bits_.clear(); b_->offsets_.clear(); b_->data_.clear(); b_->validity_.clear();
         }
     }
 }
-static void zero_under_nulls_check(const std::vector<uint8_t>& validity, size_t n) {
-    if (!validity.empty() && validity.size() < (n + 7) / 8) throw Error("validity bitmap shorter than the column");
+Series Series::from_i64(const std::string& name, const int64_t* v, size_t n, const uint8_t* validity_bits) {
+    Series s; s.name_ = name; s.dtype_ = DataType::Int64; s.len_ = n;
+    s.b_->i64_.assign(v, v + n);
+    if (validity_bits) s.b_->validity_.assign(validity_bits, validity_bits + (n + 7) / 8);
+    if (!s.b_->validity_.empty()) for (size_t i = 0; i < n; ++i) if (!get_bit(s.b_->validity_, i)) s.b_->i64_[i] = 0;
+    s.infer_from_validity();
+    return s;
+}
+Series Series::from_f64(const std::string& name, const double* v, size_t n, const uint8_t* validity_bits) {
+    Series s; s.name_ = name; s.dtype_ = DataType::Float64; s.len_ = n;
+    s.b_->f64_.assign(v, v + n);
+    if (validity_bits) s.b_->validity_.assign(validity_bits, validity_bits + (n + 7) / 8);
+    if (!s.b_->validity_.empty()) for (size_t i = 0; i < n; ++i) if (!get_bit(s.b_->validity_, i)) s.b_->f64_[i] = 0.0;
+    s.infer_from_validity();
+    return s;
+}
+Series Series::from_bool_bits(const std::string& name, const uint8_t* value_bits, size_t n, const uint8_t* validity_bits) {
+    Series s; s.name_ = name; s.dtype_ = DataType::Boolean; s.len_ = n;
+    s.b_->bits_.assign(value_bits, value_bits + (n + 7) / 8);
+    if (validity_bits) s.b_->validity_.assign(validity_bits, validity_bits + (n + 7) / 8);
+    if (n & 7) s.b_->bits_.back() &= (uint8_t)((1u << (n & 7)) - 1u);
+    if (!s.b_->validity_.empty()) for (size_t i = 0; i < (n + 7) / 8; ++i) s.b_->bits_[i] &= s.b_->validity_[i];
+    s.infer_from_validity();
+    return s;
+}
+Series Series::from_strings(const std::string& name, const int32_t* offsets, size_t n, const uint8_t* data, const uint8_t* validity_bits) {
+    Series s; s.name_ = name; s.dtype_ = DataType::String; s.len_ = n;
+    s.b_->offsets_.assign(offsets, offsets + n + 1);
+    s.b_->data_.assign(data, data + offsets[n]);
+    if (validity_bits) s.b_->validity_.assign(validity_bits, validity_bits + (n + 7) / 8);
+    s.infer_from_validity();
+    return s;
+}
+static const uint8_t* checked_validity(const std::vector<uint8_t>& validity, size_t n) {
+    if (validity.empty()) return nullptr;
+    if (validity.size() < (n + 7) / 8) throw Error("validity bitmap shorter than the column");
+    return validity.data();
 }
 Series Series::from_i64(const std::string& name, std::vector<int64_t> v, std::vector<uint8_t> validity_bits) {
-    Series s; s.name_ = name; s.dtype_ = DataType::Int64; s.len_ = v.size();
-    zero_under_nulls_check(validity_bits, s.len_);
-    s.i64_ = std::move(v); s.validity_ = std::move(validity_bits);
-    if (!s.validity_.empty()) for (size_t i = 0; i < s.len_; ++i) if (!get_bit(s.validity_, i)) s.i64_[i] = 0;
-    s.infer_from_validity();
-    return s;
+    return from_i64(name, v.data(), v.size(), checked_validity(validity_bits, v.size()));
 }
 Series Series::from_f64(const std::string& name, std::vector<double> v, std::vector<uint8_t> validity_bits) {
-    Series s; s.name_ = name; s.dtype_ = DataType::Float64; s.len_ = v.size();
-    zero_under_nulls_check(validity_bits, s.len_);
-    s.f64_ = std::move(v); s.validity_ = std::move(validity_bits);
-    if (!s.validity_.empty()) for (size_t i = 0; i < s.len_; ++i) if (!get_bit(s.validity_, i)) s.f64_[i] = 0.0;
-    s.infer_from_validity();
-    return s;
+    return from_f64(name, v.data(), v.size(), checked_validity(validity_bits, v.size()));
 }
 Series Series::from_bool_bits(const std::string& name, std::vector<uint8_t> value_bits, size_t n, std::vector<uint8_t> validity_bits) {
-    Series s; s.name_ = name; s.dtype_ = DataType::Boolean; s.len_ = n;
-    zero_under_nulls_check(validity_bits, n);
     if (value_bits.size() < (n + 7) / 8) throw Error("value bitmap shorter than the column");
-    s.bits_ = std::move(value_bits); s.validity_ = std::move(validity_bits);
-    s.bits_.resize((n + 7) / 8);
-    if (n & 7) s.bits_.back() &= (uint8_t)((1u << (n & 7)) - 1u);
-    if (!s.validity_.empty()) for (size_t i = 0; i < (n + 7) / 8; ++i) s.bits_[i] &= s.validity_[i];
-    s.infer_from_validity();
-    return s;
+    return from_bool_bits(name, value_bits.data(), n, checked_validity(validity_bits, n));
 }
 Series Series::from_strings(const std::string& name, std::vector<int32_t> offsets, std::vector<uint8_t> data, std::vector<uint8_t> validity_bits) {
     if (offsets.empty()) throw Error("Empty series not allowed");
-    Series s; s.name_ = name; s.dtype_ = DataType::String; s.len_ = offsets.size() - 1;
-    zero_under_nulls_check(validity_bits, s.len_);
-    s.offsets_ = std::move(offsets); s.data_ = std::move(data); s.validity_ = std::move(validity_bits);
-    s.infer_from_validity();
-    return s;
+    if (data.size() < (size_t)offsets.back()) throw Error("string data shorter than the offsets say");
+    return from_strings(name, offsets.data(), offsets.size() - 1, data.data(), checked_validity(validity_bits, offsets.size() - 1));
 }
 
 AnyValue Series::at(size_t i) const {  // series.rs:273-288
     if (i >= len_) throw Error("Index " + std::to_string(i) + " out of bounds for series of length " + std::to_string(len_), true);
     if (!is_valid(i)) return AnyValue::Null();
     switch (dtype_) {
-        case DataType::Int64: return AnyValue::Int64(i64_[i]);
+        case DataType::Int64: return AnyValue::Int64(b_->i64_[i]);
         case DataType::Float64:
-            if (!int_tag_.empty() && get_bit(int_tag_, i)) { int64_t v; std::memcpy(&v, &f64_[i], 8); return AnyValue::Int64(v); }
-            return AnyValue::Float64(f64_[i]);
-        case DataType::Boolean: return AnyValue::Boolean(get_bit(bits_, i));
-        case DataType::String: return AnyValue::String(std::string(data_.begin() + offsets_[i], data_.begin() + offsets_[i + 1]));
+            if (!b_->int_tag_.empty() && get_bit(b_->int_tag_, i)) { int64_t v; std::memcpy(&v, &b_->f64_[i], 8); return AnyValue::Int64(v); }
+            return AnyValue::Float64(b_->f64_[i]);
+        case DataType::Boolean: return AnyValue::Boolean(get_bit(b_->bits_, i));
+        case DataType::String: return AnyValue::String(std::string(b_->data_.begin() + b_->offsets_[i], b_->data_.begin() + b_->offsets_[i + 1]));
         case DataType::Null: return AnyValue::Null();
     }
     return AnyValue::Null();
@@ -242,8 +329,8 @@ std::vector<AnyValue> Series::to_values() const {
 std::string Series::display() const { return std::string("Series: numbers [") + dtype_name(dtype_) + "; " + std::to_string(len_) + "]"; }
 size_t Series::null_count() const {
     if (dtype_ == DataType::Null) return len_;
-    if (validity_.empty()) return 0;
-    return len_ - count_valid(validity_, len_);
+    if (b_->validity_.empty()) return 0;
+    return len_ - count_valid(b_->validity_, len_);
 }
 
 static int32_t rvl_dtype_of(DataType d) {
@@ -273,13 +360,13 @@ rvl_column Series::as_column(size_t offset, size_t length, bool flatten_nulls) c
     c.location = RVL_HOST;
     c.length = (int64_t)length;
     c.offset = (int64_t)offset;
-    const bool keep_validity = !validity_.empty() && !(flatten_nulls && dtype_ != DataType::String);
-    c.validity = keep_validity ? validity_.data() : nullptr;
+    const bool keep_validity = !b_->validity_.empty() && !(flatten_nulls && dtype_ != DataType::String);
+    c.validity = keep_validity ? b_->validity_.data() : nullptr;
     switch (dtype_) {
-        case DataType::Int64: c.values = i64_.data(); break;
-        case DataType::Float64: c.values = f64_.data(); break;
-        case DataType::Boolean: c.values = bits_.data(); break;
-        case DataType::String: c.offsets = offsets_.data(); c.data = data_.data(); c.data_len = (int64_t)data_.size(); break;
+        case DataType::Int64: c.values = b_->i64_.data(); break;
+        case DataType::Float64: c.values = b_->f64_.data(); break;
+        case DataType::Boolean: c.values = b_->bits_.data(); break;
+        case DataType::String: c.offsets = b_->offsets_.data(); c.data = b_->data_.data(); c.data_len = (int64_t)b_->data_.size(); break;
         case DataType::Null: break;
     }
     return c;
@@ -288,7 +375,7 @@ rvl_column Series::as_column(size_t offset, size_t length, bool flatten_nulls) c
 rvl_column Series::tag_column(size_t offset, size_t length) const {
     rvl_column c{};
     c.dtype = RVL_BOOLEAN; c.location = RVL_HOST; c.length = (int64_t)length; c.offset = (int64_t)offset;
-    c.values = int_tag_.data();
+    c.values = b_->int_tag_.data();
     return c;
 }
 
@@ -296,16 +383,16 @@ Series Series::from_mixed(const std::string& name, const rvl_column& v, const rv
     const size_t n = (size_t)v.length;
     if (n == 0 || dtype == DataType::Null) { rvl_column c = v; if (dtype == DataType::Null) { c.dtype = RVL_NULL; c.null_count = c.length; } return from_column(name, c, dtype); }
     Series s; s.name_ = name; s.len_ = n; s.dtype_ = dtype;
-    if (v.validity != nullptr && v.null_count > 0) s.validity_.assign(v.validity, v.validity + (n + 7) / 8);
+    if (v.validity != nullptr && v.null_count > 0) s.b_->validity_.assign(v.validity, v.validity + (n + 7) / 8);
     const uint8_t* tags = (const uint8_t*)t.values;
     if (dtype == DataType::Int64) {  // only Int64 survivors: an ordinary Int64 series
-        s.i64_.assign((const int64_t*)v.values, (const int64_t*)v.values + n);
+        s.b_->i64_.assign((const int64_t*)v.values, (const int64_t*)v.values + n);
         return s;
     }
-    s.f64_.assign((const double*)v.values, (const double*)v.values + n);
+    s.b_->f64_.assign((const double*)v.values, (const double*)v.values + n);
     bool any_int = false;
     for (size_t i = 0; i < (n + 7) / 8; ++i) any_int |= tags[i] != 0;
-    if (any_int) s.int_tag_.assign(tags, tags + (n + 7) / 8);
+    if (any_int) s.b_->int_tag_.assign(tags, tags + (n + 7) / 8);
     return s;
 }
 
@@ -315,15 +402,32 @@ Series Series::from_column(const std::string& name, const rvl_column& c, DataTyp
     if (n == 0) return Series::empty(name, dtype_if_empty);
     Series s; s.name_ = name; s.len_ = n; s.dtype_ = series_type_of(c.dtype);
     if (c.dtype == RVL_NULL || c.null_count == c.length) { s.dtype_ = DataType::Null; return s; }  // series.rs:190-198
-    if (c.validity != nullptr && c.null_count > 0) s.validity_.assign(c.validity, c.validity + (n + 7) / 8);
+    if (c.validity != nullptr && c.null_count > 0) s.b_->validity_.assign(c.validity, c.validity + (n + 7) / 8);
     switch (c.dtype) {
-        case RVL_INT64: s.i64_.assign((const int64_t*)c.values, (const int64_t*)c.values + n); break;
-        case RVL_FLOAT64: s.f64_.assign((const double*)c.values, (const double*)c.values + n); break;
-        case RVL_BOOLEAN: s.bits_.assign((const uint8_t*)c.values, (const uint8_t*)c.values + (n + 7) / 8); break;
+        case RVL_INT64: s.b_->i64_.assign((const int64_t*)c.values, (const int64_t*)c.values + n); break;
+        case RVL_FLOAT64: s.b_->f64_.assign((const double*)c.values, (const double*)c.values + n); break;
+        case RVL_BOOLEAN: s.b_->bits_.assign((const uint8_t*)c.values, (const uint8_t*)c.values + (n + 7) / 8); break;
         case RVL_STRING:
-            s.offsets_.assign(c.offsets, c.offsets + n + 1);
-            s.data_.assign(c.data, c.data + c.data_len);
+            s.b_->offsets_.assign(c.offsets, c.offsets + n + 1);
+            s.b_->data_.assign(c.data, c.data + c.data_len);
             break;
+        default: break;
+    }
+    return s;
+}
+
+Series Series::from_array(const std::string& name, ArrayData&& a, DataType dtype) {
+    // the buffers were downloaded straight into (page-locked) HostVecs: they are moved in, not copied
+    const size_t n = (size_t)a.length;
+    if (n == 0) return Series::empty(name, dtype);
+    Series s; s.name_ = name; s.len_ = n; s.dtype_ = series_type_of((int32_t)a.dtype);
+    if (dtype == DataType::Null || a.dtype == ExecType::Null || a.null_count == a.length) { s.dtype_ = DataType::Null; return s; }  // series.rs:190-198
+    if (a.has_validity && a.null_count > 0) s.b_->validity_ = std::move(a.validity);
+    switch (a.dtype) {
+        case ExecType::Int64: s.b_->i64_ = std::move(a.i64); break;
+        case ExecType::Float64: s.b_->f64_ = std::move(a.f64); break;
+        case ExecType::Boolean: s.b_->bits_ = std::move(a.bits); break;
+        case ExecType::String: s.b_->offsets_ = std::move(a.offsets); s.b_->data_ = std::move(a.data); break;
         default: break;
     }
     return s;
@@ -585,13 +689,13 @@ ArrayData RecordBatch::column_data(size_t i) const {
     a.has_validity = v.validity != nullptr && v.dtype != RVL_NULL;
     if (a.has_validity) { a.validity.assign((n + 7) / 8 + 1, 0); dst.validity = a.validity.data(); }
     switch (v.dtype) {
-        case RVL_INT64: a.i64.assign(n + 1, 0); dst.values = a.i64.data(); break;
-        case RVL_FLOAT64: a.f64.assign(n + 1, 0.0); dst.values = a.f64.data(); break;
+        case RVL_INT64: a.i64.resize(n + 1); dst.values = a.i64.data(); break;     // not zero-filled: the download overwrites it
+        case RVL_FLOAT64: a.f64.resize(n + 1); dst.values = a.f64.data(); break;
         case RVL_BOOLEAN: a.bits.assign((n + 7) / 8 + 1, 0); dst.values = a.bits.data(); break;
         case RVL_STRING: {
-            a.offsets.assign(n + 1, 0); dst.offsets = a.offsets.data();
+            a.offsets.resize(n + 1); a.offsets[0] = 0; dst.offsets = a.offsets.data();
             // the view's data_len is the span of the viewed window
-            a.data.assign((size_t)std::max<int64_t>(v.data_len, 0) + 1, 0); dst.data = a.data.data(); dst.data_len = v.data_len;
+            a.data.resize((size_t)std::max<int64_t>(v.data_len, 0) + 1); dst.data = a.data.data(); dst.data_len = v.data_len;
             break;
         }
         default: break;
@@ -973,6 +1077,20 @@ std::string LogicalPlan::shape() const {
     return "";
 }
 
+std::string LogicalPlan::describe() const {
+    switch (kind) {
+        case DataFrameSource: return "DataFrameSource";
+        case Select: {
+            std::string e;
+            for (size_t i = 0; i < expressions.size(); ++i) e += (i ? ", " : "") + expressions[i].debug();
+            return "Select { input: " + input->describe() + ", expressions: [" + e + "] }";
+        }
+        case Filter: return "Filter { input: " + input->describe() + ", predicate: " + predicate.debug() + " }";
+        case Limit: return "Limit { input: " + input->describe() + ", n: " + std::to_string(n) + " }";
+    }
+    return "";
+}
+
 // ------------------------------------------------------------------------------------------------- logical_plan/optimizer.rs
 static void extract_column_names(const Expr& e, std::vector<std::string>& out) {  // optimizer.rs:76-87
     switch (e.kind) {
@@ -1131,7 +1249,7 @@ DataFrame download_frame(const Frame& f) {
             out.push_back(Series::from_mixed(f.names[i], c, tc, f.dtypes[i]));
             continue;
         }
-        out.push_back(Series::from_column(f.names[i], c, f.dtypes[i]));
+        out.push_back(Series::from_array(f.names[i], std::move(a), f.dtypes[i]));
     }
     return DataFrame::unchecked(std::move(out));
 }

@@ -60,6 +60,34 @@ struct AnyValue {  // series.rs:6-13
     std::string debug() const;                      // #[derive(Debug)]
 };
 
+// ---------------------------------------------------------------------------------------- host buffers
+// Column buffers live in PAGE-LOCKED memory once they are big enough to matter (>= 64 KB), so a DataFrame is handed to the
+// device by the copy engine straight from where it lies and results land where they will stay: no pageable staging copy on
+// either side (SURVEY.md 8(f) rank 1 — the ingestion step in front of the hot path).  Blocks are recycled through a size-class
+// pool (pinning a fresh 24 MB buffer costs milliseconds; reusing one costs nothing).  Without a usable CUDA device (CPU-only
+// tests) the allocator quietly uses malloc: nothing on this path needs the GPU to hold data.
+void* host_buffer_alloc(size_t bytes);
+void host_buffer_free(void* p, size_t bytes);
+void host_buffer_pool_trim();   // give cached pinned blocks back to the driver
+template <class T>
+struct HostAllocator {
+    using value_type = T;
+    HostAllocator() = default;
+    template <class U> HostAllocator(const HostAllocator<U>&) {}
+    T* allocate(size_t n) { return static_cast<T*>(host_buffer_alloc(n * sizeof(T))); }
+    void deallocate(T* p, size_t n) { host_buffer_free(p, n * sizeof(T)); }
+    // resize(n) default-initialises (no zero fill of megabytes that a copy is about to overwrite); assign(n, v) still writes v
+    template <class U, class... A> void construct(U* p, A&&... a) {
+        if constexpr (sizeof...(A) == 0) ::new ((void*)p) U;
+        else ::new ((void*)p) U(std::forward<A>(a)...);
+    }
+    template <class U> bool operator==(const HostAllocator<U>&) const { return true; }
+    template <class U> bool operator!=(const HostAllocator<U>&) const { return false; }
+};
+template <class T> using HostVec = std::vector<T, HostAllocator<T>>;
+
+struct ArrayData;
+
 // One column in Arrow layout.  dtype follows the reference's inference (series.rs:185-221): first non-null value's
 // type, Null when every value is null.  Values under a null are stored as 0 / false / empty.
 class Series {
@@ -72,6 +100,11 @@ class Series {
     static Series from_f64(const std::string& name, std::vector<double> v, std::vector<uint8_t> validity_bits = {});
     static Series from_bool_bits(const std::string& name, std::vector<uint8_t> value_bits, size_t n, std::vector<uint8_t> validity_bits = {});
     static Series from_strings(const std::string& name, std::vector<int32_t> offsets, std::vector<uint8_t> data, std::vector<uint8_t> validity_bits = {});
+    // the same over borrowed buffers (copied once, into page-locked storage); validity_bits may be NULL
+    static Series from_i64(const std::string& name, const int64_t* v, size_t n, const uint8_t* validity_bits);
+    static Series from_f64(const std::string& name, const double* v, size_t n, const uint8_t* validity_bits);
+    static Series from_bool_bits(const std::string& name, const uint8_t* value_bits, size_t n, const uint8_t* validity_bits);
+    static Series from_strings(const std::string& name, const int32_t* offsets, size_t n, const uint8_t* data, const uint8_t* validity_bits);
 
     const std::string& name() const { return name_; }
     size_t len() const { return len_; }
@@ -81,41 +114,47 @@ class Series {
     std::optional<AnyValue> get(size_t i) const;       // :243-245
     std::vector<AnyValue> to_values() const;
     std::string display() const;                       // "Series: numbers [{dtype}; {len}]" :267-271
+    // copies share the (immutable) buffers, like an Arc clone: from_dataframe / select / rename never move column data
     Series renamed(const std::string& n) const { Series s = *this; s.name_ = n; return s; }
     size_t null_count() const;
-    bool is_valid(size_t i) const { return dtype_ != DataType::Null && (validity_.empty() || ((validity_[i >> 3] >> (i & 7)) & 1)); }
+    bool is_valid(size_t i) const { return dtype_ != DataType::Null && (b_->validity_.empty() || ((b_->validity_[i >> 3] >> (i & 7)) & 1)); }
     // A Float64-dtype Series may hold Int64 values (series.rs:210-212).  Such a mixed column keeps ONE 8-byte buffer (the f64
     // or the i64 bit pattern of each row) plus a tag bitmap (1 = the row is an AnyValue::Int64); on the device the tag travels
     // as a hidden Boolean column and the predicate kernels compare each row with its own type (rvl_predicate::tag_column).
-    bool is_mixed() const { return !int_tag_.empty(); }
+    bool is_mixed() const { return !b_->int_tag_.empty(); }
     rvl_column tag_column(size_t offset, size_t length) const;   // Boolean column over the tag bitmap (mixed series only)
     // Build from a downloaded (values, tag) pair; `dtype` is what Series::new infers for the survivors (Null / Int64 / Float64)
     static Series from_mixed(const std::string& name, const rvl_column& values, const rvl_column& tags, DataType dtype);
 
     // raw buffers
-    const std::vector<int64_t>& i64_values() const { return i64_; }
-    const std::vector<double>& f64_values() const { return f64_; }
-    const std::vector<uint8_t>& bool_bits() const { return bits_; }
-    const std::vector<int32_t>& str_offsets() const { return offsets_; }
-    const std::vector<uint8_t>& str_data() const { return data_; }
-    const std::vector<uint8_t>& validity_bits() const { return validity_; }
+    const HostVec<int64_t>& i64_values() const { return b_->i64_; }
+    const HostVec<double>& f64_values() const { return b_->f64_; }
+    const HostVec<uint8_t>& bool_bits() const { return b_->bits_; }
+    const HostVec<int32_t>& str_offsets() const { return b_->offsets_; }
+    const HostVec<uint8_t>& str_data() const { return b_->data_; }
+    const HostVec<uint8_t>& validity_bits() const { return b_->validity_; }
     // rvl_column view over rows [offset, offset + length) of this Series' host buffers (borrowed).
     // flatten_nulls: numeric / boolean nulls become valid 0 / false, as dataframe_to_batches does (streaming.rs:177,188,212).
     rvl_column as_column(size_t offset, size_t length, bool flatten_nulls) const;
     // Build from a downloaded column (dtype of the device array; `dtype_if_empty` is kept when length == 0).
     static Series from_column(const std::string& name, const rvl_column& c, DataType dtype_if_empty);
+    // Adopt a downloaded array's buffers (moved, not copied); `dtype` is the eager dtype of the result column
+    static Series from_array(const std::string& name, ArrayData&& a, DataType dtype);
 
   private:
     std::string name_;
     DataType dtype_ = DataType::Null;
     size_t len_ = 0;
-    std::vector<int64_t> i64_;
-    std::vector<double> f64_;
-    std::vector<uint8_t> bits_;      // Boolean values, LSB-first
-    std::vector<int32_t> offsets_;   // String (len + 1 entries)
-    std::vector<uint8_t> data_;      // String
-    std::vector<uint8_t> validity_;  // LSB-first, empty = all valid
-    std::vector<uint8_t> int_tag_;   // mixed Float64 series: LSB-first bitmap, 1 = f64_[i] holds the bit pattern of an AnyValue::Int64
+    struct Bufs {
+        HostVec<int64_t> i64_;
+        HostVec<double> f64_;
+        HostVec<uint8_t> bits_;      // Boolean values, LSB-first
+        HostVec<int32_t> offsets_;   // String (len + 1 entries)
+        HostVec<uint8_t> data_;      // String
+        HostVec<uint8_t> validity_;  // LSB-first, empty = all valid
+        HostVec<uint8_t> int_tag_;   // mixed Float64 series: LSB-first bitmap, 1 = f64_[i] holds the bit pattern of an AnyValue::Int64
+    };
+    std::shared_ptr<Bufs> b_ = std::make_shared<Bufs>();   // written only while the Series is being built; shared by its copies
     void infer_from_validity();      // all null -> dtype Null
 };
 
@@ -212,9 +251,9 @@ using SchemaRef = std::shared_ptr<Schema>;
 struct ArrayData {
     ExecType dtype = ExecType::Null;
     int64_t length = 0, null_count = 0;
-    std::vector<int64_t> i64; std::vector<double> f64; std::vector<uint8_t> bits;
-    std::vector<int32_t> offsets; std::vector<uint8_t> data;
-    std::vector<uint8_t> validity;  // empty = bitmap absent
+    HostVec<int64_t> i64; HostVec<double> f64; HostVec<uint8_t> bits;
+    HostVec<int32_t> offsets; HostVec<uint8_t> data;
+    HostVec<uint8_t> validity;  // empty = bitmap absent
     bool has_validity = false;
     AnyValue value(size_t i) const;  // Error{panic} "Index {} out of bounds" (primitive.rs:49 etc.)
 };
@@ -319,6 +358,7 @@ struct LogicalPlan {  // logical_plan/plan.rs:8-39 (CsvFileSource / Join: out of
     std::vector<std::pair<std::string, DataType>> schema() const;  // logical_plan/plan.rs:63-113
     void validate() const;                                         // :115-202 (throws "Logical plan error: …")
     std::string shape() const;                                     // e.g. "Limit(Select(Filter(Source)))"
+    std::string describe() const;                                  // Debug-style dump: node kinds and expression trees
 };
 LogicalPlan optimize(LogicalPlan plan);                                   // optimizer.rs:7-64
 StreamingPhysicalPlan logical_to_streaming(const LogicalPlan& plan, const ContextRef& ctx);  // streaming_planner.rs:29-168

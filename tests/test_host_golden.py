@@ -70,7 +70,7 @@ def _load_golden_namespace():
 _NS = _load_golden_namespace()
 
 # host logic only (dtype inference, plan shapes, validation / lowering / planner rejections): no kernel is launched
-CPU_TESTS = ["test_series_dtype_inference", "test_dataframe_construction_rules", "test_readme_shape_fails_validation", "test_planner_rejections",
+CPU_TESTS = ["test_logical_plan_schema_and_validate", "test_lazyframe_builder_structure", "test_series_dtype_inference", "test_dataframe_construction_rules", "test_readme_shape_fails_validation", "test_planner_rejections",
              "test_streaming_planner_rejections", "test_collect_invalid_columns"]
 # everything below executes CUDA kernels through the C ABI
 GPU_TESTS = [

@@ -603,3 +603,62 @@ def test_extension_compound_and_streaming_comparison_predicates():
             LazyFrame.from_dataframe(df).filter(both.or_(col("nope").eq(lit(1)))).collect()
     finally:
         set_extensions(False)
+
+
+# ---------------------------------------------------------------- logical_plan/plan.rs + builder.rs: plan construction, schema(), validate()
+def test_logical_plan_schema_and_validate():
+    df = df_name_age_score()
+    src = LazyFrame.from_dataframe(df)
+    assert src.schema() == [("name", "String"), ("age", "Int64"), ("score", "Float64")]                 # plan.rs:446-461
+    src.validate()                                                                                       # plan.rs:599-610
+    assert src.select([col("name"), col("age")]).schema() == [("name", "String"), ("age", "Int64")]      # plan.rs:464-489
+    assert src.select([col("name"), col("age").alias("user_age")]).schema() == [("name", "String"), ("user_age", "Int64")]   # :492-516, builder.rs:537-549
+    # arithmetic: Int64 * Int64 = Int64, Float64 + Float64 = Float64, Int64 + Float64 = Float64; the name is the left operand's (plan.rs:519-548)
+    arith = src.select([col("age").mul(lit(2)), col("score").add(lit(10.0)), col("age").add(col("score"))])
+    assert arith.schema() == [("age", "Int64"), ("score", "Float64"), ("age", "Float64")]
+    assert src.select([col("age").add(col("score")).alias("age_plus_score")]).schema() == [("age_plus_score", "Float64")]    # builder.rs:552-566
+    assert src.filter(col("age").gt(lit(25))).schema() == src.schema()                                   # plan.rs:551-572
+    assert src.limit(5).schema() == src.schema()                                                         # plan.rs:575-596
+    src.select([col("name"), col("age")]).validate()                                                     # plan.rs:613-634
+    with pytest.raises(OracleError, match="Column not found: 'invalid_column'"):                         # plan.rs:637-666
+        src.select([col("name"), col("invalid_column")]).validate()
+    src.filter(col("age").gt(lit(25))).validate()                                                        # plan.rs:669-684
+    with pytest.raises(OracleError, match="Column not found: 'invalid'"):                                # plan.rs:687-711
+        src.filter(col("invalid").gt(lit(25))).validate()
+    chained = src.filter(col("age").gt(lit(25))).select([col("name"), col("score").alias("final_score")]).limit(10)   # plan.rs:715-753
+    chained.validate()
+    assert chained.schema() == [("name", "String"), ("final_score", "Float64")]
+    nested = src.select([col("name"), col("age").mul(lit(2)).alias("double_age"), col("score")]) \
+                .select([col("name"), col("double_age").add(lit(10)).alias("adjusted_age")])              # plan.rs:756-798
+    nested.validate()
+    assert nested.schema() == [("name", "String"), ("adjusted_age", "Int64")]
+
+
+def test_lazyframe_builder_structure():
+    df = df_name_age_score()
+    lf = LazyFrame.from_dataframe(df)
+    assert lf.describe() == "DataFrameSource"                                                            # builder.rs:165-186
+    assert lf.select([col("name")]).describe() == 'Select { input: DataFrameSource, expressions: [Column("name")] }'   # :189-203
+    d = lf.select([col("name"), col("age"), col("score")]).describe()                                    # :206-220
+    assert d.count("Column(") == 3
+    d = lf.select([col("name"), col("age").alias("user_age")]).describe()                                # :223-238
+    assert 'Alias(Column("age"), "user_age")' in d
+    d = lf.select([col("name"), col("age").mul(lit(2)).alias("double_age")]).describe()                  # :241-265: alias wraps a BinaryExpr
+    assert 'Alias(BinaryExpr { left: Column("age"), op: Multiply, right: Literal(Int64(2)) }, "double_age")' in d
+    d = lf.filter(col("age").gt(lit(30))).describe()                                                     # :270-283
+    assert d == 'Filter { input: DataFrameSource, predicate: BinaryExpr { left: Column("age"), op: Gt, right: Literal(Int64(30)) } }'
+    d = lf.filter(col("age").gt(lit(25)).and_(col("score").lt(lit(90.0)))).describe()                    # :286-303: the top operator is And
+    assert "predicate: BinaryExpr { left: BinaryExpr {" in d and "}, op: And, right: BinaryExpr {" in d
+    d = lf.filter(col("name").eq(lit("Alice"))).describe()                                               # :306-327
+    assert 'BinaryExpr { left: Column("name"), op: Eq, right: Literal(String("Alice")) }' in d
+    assert lf.limit(5).describe() == "Limit { input: DataFrameSource, n: 5 }"                            # :331-341
+    assert lf.limit(0).describe() == "Limit { input: DataFrameSource, n: 0 }"                            # :344-354
+    # select then filter / filter then select / select -> filter -> limit: the nesting follows the call order (:359-431)
+    assert lf.select([col("name"), col("age")]).filter(col("age").gt(lit(25))).describe().startswith("Filter { input: Select { input: DataFrameSource")
+    assert lf.filter(col("age").gt(lit(25))).select([col("name")]).describe().startswith("Select { input: Filter { input: DataFrameSource")
+    d = lf.select([col("name"), col("age"), col("score")]).filter(col("age").gt(lit(25))).limit(10).describe()
+    assert d.startswith("Limit { input: Filter { input: Select { input: DataFrameSource") and d.endswith(", n: 10 }")
+    # a LazyFrame is a value: building on it leaves it untouched (builder.rs:619-633 clone, :636-644 debug)
+    base = lf.select([col("name")])
+    _ = base.limit(1)
+    assert base.describe() == 'Select { input: DataFrameSource, expressions: [Column("name")] }'

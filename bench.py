@@ -60,14 +60,16 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons of one GPU while the timed region runs (pynvml)."""
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs (pynvml).  The thread is started (and its first,
+    slow NVML queries made) before the region opens; only samples taken after arm() are kept."""
 
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
 
-    def __init__(self, uuid=None, index=0, period=0.05):
+    def __init__(self, uuid=None, index=0, period=0.02):
         super().__init__(daemon=True)
         self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
+        self.armed = False          # samples count only once the timed region has opened (arm())
         self._stop_evt = threading.Event()
         self.period = period
         self.ok = False
@@ -95,18 +97,24 @@ class ClockSampler(threading.Thread):
         nv = self.nv
         while not self._stop_evt.is_set():
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
                 try:
                     mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
                     mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in self.REASONS.items():
-                    if mask & bit:
-                        self.reasons.add(name)
-                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                watts = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                if self.armed:
+                    self.samples.append(mhz)
+                    for bit, name in self.REASONS.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+                    self.power.append(watts)
             except Exception:
                 pass
             self._stop_evt.wait(self.period)
+
+    def arm(self):
+        self.armed = True
 
     def stop(self):
         self._stop_evt.set()
@@ -259,6 +267,7 @@ def run_native(args):
     ctx.profile_read_launches()
     barrier(); torch.cuda.synchronize()
     launches0 = ctx.launch_count()
+    sampler.arm()
     e0.record(stream)
     for _ in range(args.steps):
         counts = step()

@@ -149,7 +149,9 @@ typedef enum rvl_option {
     RVL_OPT_EXACT_ALLOC = 9,        /* blocking rvl_filter_project, two-pass plan: read the survivor count (and string bytes) back after the
                                        predicate scan and allocate the outputs at their exact size instead of min(n, limit) rows.
                                        0 = never, 1 = always, 2 = only when the worst case exceeds a quarter of device memory (default) */
-    RVL_OPT__COUNT = 12
+    RVL_OPT_CHUNK_PLAN = 12,        /* two-pass plan, predicate column also projected (numeric, no LIMIT): run the single-pass chunk kernel
+                                       that reads that column from HBM once instead of twice (default 1) */
+    RVL_OPT__COUNT = 13
 } rvl_option;
 int32_t rvl_ctx_set_option(rvl_ctx* ctx, int32_t option, int64_t value);
 

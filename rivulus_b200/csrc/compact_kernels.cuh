@@ -116,7 +116,7 @@ __device__ __forceinline__ void tile_word_scan(uint32_t w0, uint32_t w1, int lan
 }
 
 template <int CW>
-__global__ void __launch_bounds__((CW + 1) * 32, CW == 8 ? 2 : 1) compact_dense_kernel(const __grid_constant__ CompactParams p) {
+__global__ void __launch_bounds__((CW + 1) * 32, CW == 8 ? 2 : 1) __maxnreg__(CW == 8 ? 112 : 64) compact_dense_kernel(const __grid_constant__ CompactParams p) {
     constexpr int kCompactWarps = CW;
     constexpr int KW = kTileWords / CW;        // selection words (32-row groups) per consumer warp and tile
     constexpr int kWarpRows = kTileRows / CW;

@@ -3,9 +3,11 @@
 // or the streaming mask rule of execution/record_batch.rs:235-240), sizes the outputs, launches the kernels of
 // fused_filter.cuh / string_kernels.cuh on the context stream and builds the output RecordBatch.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "aux_kernels.cuh"
+#include "chunk_kernels.cuh"
 #include "compact_kernels.cuh"
 #include "filter_project.cuh"
 #include "fused_filter.cuh"
@@ -225,6 +227,8 @@ int fp_init_device(int device) {
     RVL_CUDA_TRY(cudaFuncSetAttribute(compact_dense_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmemMax));
     RVL_CUDA_TRY(cudaFuncSetAttribute(compact_dense_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmemMax));
     RVL_CUDA_TRY(cudaFuncSetAttribute(string_gather_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StrSmem)));
+    RVL_CUDA_TRY(cudaFuncSetAttribute(chunk_filter_kernel<kPredI64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmemMax));
+    RVL_CUDA_TRY(cudaFuncSetAttribute(chunk_filter_kernel<kPredF64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmemMax));
     return RVL_OK;
 }
 
@@ -241,13 +245,19 @@ static int launch_compaction(const CoreRef& core, CompactParams cp, const uint32
     };
     for (int c = 0; c < kMaxCol8; ++c) cp.col8_vsrc[c] = c < cp.n_col8 ? add_src(cp.col8[c].valid) : (int8_t)-1;
     const int smem_budget = (per_sm == 1 ? kDenseSmemMax : 110 * 1024) - (int)dense_stage_bytes(warps, cp.n_bsrc);
-    const int max_slots = std::min(14, smem_budget / (int)(kSlotBytes + 16));
+    int max_slots = std::min(14, smem_budget / (int)(kSlotBytes + 16));
+    // kernels forked onto the side stream (bit-packed compaction, string sizes) must find room on the SMs the persistent dense CTAs
+    // occupy: with all 14 slots the dense kernel owns every byte of shared memory and the side kernels simply queue behind it
+    // (measured: no overlap at all), so two slots (32 KB per SM) are left free whenever there is side work
+    if (bits_stream != core->stream) max_slots = std::min(max_slots, 12);
     cp.n_slots = std::max(2, std::min(max_slots, core->dense_slots));
     if (cp.n_bits > 0) {
         // bit-packed columns (validity bitmaps, Boolean values) of every tile: one warp per tile; instruction-bound, barely touches
         // DRAM, so the caller forks it onto the side stream where it runs underneath the HBM-bound kernels below
         const int64_t n_tiles = (cp.n_rows + kTileRows - 1) / kTileRows;
-        const int64_t ctas = std::max<int64_t>(1, std::min<int64_t>((n_tiles + kWarps - 1) / kWarps, (int64_t)core->sm_count * 8));
+        // on the side stream it shares the SMs with the persistent dense CTAs (544 threads each): two CTAs per SM leave them room
+        const int per_sm_bits = bits_stream != core->stream ? 2 : 8;
+        const int64_t ctas = std::max<int64_t>(1, std::min<int64_t>((n_tiles + kWarps - 1) / kWarps, (int64_t)core->sm_count * per_sm_bits));
         compact_bits_kernel<<<(unsigned)ctas, kBlock, 0, bits_stream>>>(cp);
         core->launches++;
         RVL_CUDA_TRY(cudaGetLastError());
@@ -474,7 +484,63 @@ int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pre
 
         int64_t tiles_per_chunk = 0;
         BufRef chunk_base;
-        if (two_pass) {
+        // Single-pass chunk plan (chunk_kernels.cuh): the predicate column is itself projected, so the two-pass plan would read it
+        // twice.  Needs: a numeric predicate over a 16-byte-aligned view, no LIMIT (the look-back has no early exit), one column
+        // group, worst-case output allocation (the count is only known at the end).
+        int chunk_pred_col = -1;
+        if (two_pass && core->chunk_plan && !exact && limit < 0 && launches_needed == 1 && (pp.kind == kPredI64 || pp.kind == kPredF64) && pp.vec_ok) {
+            int k8 = 0;
+            for (int j = 0; j < nproj && chunk_pred_col < 0; ++j) {
+                const DevColumn& s = in->cols[proj[j]];
+                if (s.dtype != RVL_INT64 && s.dtype != RVL_FLOAT64) continue;
+                if (proj[j] == pred->column) chunk_pred_col = k8;
+                ++k8;
+            }
+        }
+        if (two_pass && chunk_pred_col >= 0) {
+            const int64_t n_chunks = (n + kChunkRows - 1) / kChunkRows;
+            BufRef status;   // look-back descriptors + the chunk ticket, zeroed; then one zero word standing in for the range bases
+            RVL_TRY(dev_alloc_zeroed(core, (size_t)(n_chunks + 2) * 8, &status));
+            pend->temps.push_back(status);
+            chunk_base = status;                         // word [n_chunks + 1] stays 0: tile_info carries GLOBAL prefixes
+            tiles_per_chunk = 0x7FFFFFFF;
+            ChunkParams cp{};
+            cp.n_rows = n; cp.n_chunks = n_chunks;
+            cp.pred_values = pp.values; cp.lit_bits = pp.lit_bits; cp.range_lo = pp.range_lo; cp.range_span = pp.range_span;
+            cp.range_neg = pp.range_neg; cp.truth = pp.truth; cp.keep_null = pp.keep_null; cp.pred_valid = pp.valid;
+            cp.pred_col = chunk_pred_col; cp.n_col8 = (int)col8s.size();
+            for (int k = 0; k < cp.n_col8; ++k) cp.col8[k] = col8s[(size_t)k];
+            cp.sparse_max = (uint32_t)std::max(0, core->sparse_max);
+            { const char* dbg = std::getenv("RVL_CHUNK_DEBUG"); cp.debug = dbg ? (uint32_t)std::atoi(dbg) : 0u; }
+            if (cp.debug == 2u) { std::memset(core->mailbox + 128, 0, 128 * 8); cp.debug_words = (unsigned long long*)(core->mailbox + 128); }
+            cp.base_in = base_in;
+            cp.sel_out = (uint32_t*)sel->ptr; cp.tile_info = (uint64_t*)tile_prefix->ptr;
+            cp.status = (uint64_t*)status->ptr; cp.ticket = (uint32_t*)((uint64_t*)status->ptr + n_chunks);
+            cp.total_out = dctr;
+            const size_t fixed = (sizeof(ChunkSmem) + 127) & ~size_t(127);
+            cp.n_slots = std::max(1, std::min<int>(kChunkMaxSlots, (int)(((size_t)kDenseSmemMax - fixed) / kSlotBytes)));
+            const size_t smem = fixed + (size_t)cp.n_slots * kSlotBytes;
+            const unsigned grid = (unsigned)std::min<int64_t>(n_chunks, core->sm_count);
+            if (pp.kind == kPredI64) chunk_filter_kernel<kPredI64><<<grid, kChunkThreads, smem, core->stream>>>(cp);
+            else chunk_filter_kernel<kPredF64><<<grid, kChunkThreads, smem, core->stream>>>(cp);
+            core->launches++;
+            RVL_CUDA_TRY(cudaGetLastError());
+            // the ticket / zero word sit behind the descriptors: point chunk_base at the zero word
+            chunk_base = wrap_external(core, (uint64_t*)status->ptr + n_chunks + 1, 8);
+            // bit-packed columns and string sizes read the selection bitmap + tile_info this kernel wrote
+            for (StrJob& job : strjobs) {
+                RVL_TRY(prepare_str_sizes(job, tiles_per_chunk, chunk_base));
+                RVL_TRY(launch_str_sizes(job, tiles_per_chunk, chunk_base, core->stream));
+            }
+            if (!bitcols.empty()) {
+                CompactParams bp{};
+                bp.n_rows = n; bp.limit = limit; bp.sel = (const uint32_t*)sel->ptr; bp.tile_info = (const uint64_t*)tile_prefix->ptr;
+                bp.chunk_base = (const uint64_t*)chunk_base->ptr; bp.tiles_per_chunk = tiles_per_chunk; bp.base_in = base_in;
+                bp.n_col8 = 0; bp.n_bits = (int)bitcols.size();
+                for (int k = 0; k < bp.n_bits; ++k) bp.bits[k] = bitcols[(size_t)k];
+                RVL_TRY(launch_compaction(core, bp, nullptr, nullptr, nullptr, core->stream));
+            }
+        } else if (two_pass) {
             // pass 1: persistent predicate scan (scan_kernels.cuh), every warp owns a contiguous range of tiles
             const int scan_ctas = std::min(192, core->sm_count);
             const int scan_warps = core->scan_warps == 32 ? 32 : (core->scan_warps == 16 ? 16 : 8);

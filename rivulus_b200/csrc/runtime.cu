@@ -201,6 +201,12 @@ int32_t rvl_ctx_trim(rvl_ctx* ctx) {
     return RVL_OK;
 }
 
+// debugging aid (not part of the ABI header): the pinned words kernels leave behind under RVL_CHUNK_DEBUG=2
+int32_t rvl_debug_read(rvl_ctx* ctx, uint64_t* out, int32_t n) {
+    for (int i = 0; i < n && i < 128; ++i) out[i] = ctx->core->mailbox[128 + i];
+    return RVL_OK;
+}
+
 int32_t rvl_ctx_cuda_stream(rvl_ctx* ctx, void** s) { *s = (void*)ctx->core->stream; return RVL_OK; }
 int32_t rvl_ctx_device(rvl_ctx* ctx, int32_t* d) { *d = ctx->core->device; return RVL_OK; }
 int32_t rvl_ctx_launch_count(rvl_ctx* ctx, int64_t* n) { *n = ctx->core->launches.load(); return RVL_OK; }
@@ -232,6 +238,7 @@ int32_t rvl_ctx_set_option(rvl_ctx* ctx, int32_t option, int64_t value) {
             if (value != 8 && value != 16) return fail(RVL_INVALID_ARGUMENT, "dense_warps must be 8 or 16");
             c.dense_warps = (int)value; return RVL_OK;
         case RVL_OPT_BITS_OVERLAP: c.bits_overlap = value != 0; return RVL_OK;
+        case RVL_OPT_CHUNK_PLAN: c.chunk_plan = value != 0; return RVL_OK;
         case RVL_OPT_STRING_KERNEL:
             if (value < 1 || value > 4) return fail(RVL_INVALID_ARGUMENT, "string_kernel must be in [1, 4]");
             c.string_kernel = (int)value; return RVL_OK;

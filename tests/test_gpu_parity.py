@@ -575,6 +575,61 @@ def test_two_pass_ring_depths(slots, per_sm, scan_warps, scan_slots, dense_warps
         c.close()
 
 
+# ------------------------------------------------------------------ single-pass chunk plan: predicate column projected
+@pytest.mark.parametrize("n", [1, 4095, 4096, 4097, 12_289, 300_001, 1_300_000])
+@pytest.mark.parametrize("chunk", [1, 0])
+def test_chunk_plan_predicate_column_projected(n, chunk):
+    """`filter(k <op> T)` projecting k itself (every column, as a Filter without Select does): the chunk kernel keeps the predicate
+    values in shared memory between the predicate and the compaction (one HBM read) and orders the output by decoupled look-back.
+    Same bytes as the oracle with the plan on and off: Int64 / Float64 predicates with nulls and NaN, every selectivity incl. all /
+    none, sparse and dense tiles in one batch, 8 numeric columns (ring back-pressure), Boolean + String columns riding along,
+    ragged sizes around the 4096-row chunk."""
+    rng = np.random.default_rng(n + chunk)
+    k = rng.integers(0, 1000, n)
+    dens = np.repeat(rng.choice([0.0, 0.01, 0.2, 0.6, 1.0], size=(n + 2047) // 2048), 2048)[:n]
+    k = np.where(rng.random(n) < dens, 2000 + k, k % 900).astype(np.int64)
+    cols = [Col("i64", n, k, rng.random(n) > 0.05), random_col(rng, "f64", n, 0.1, specials=True), random_col(rng, "i64", n, 0.0),
+            random_col(rng, "bool", n, 0.2), random_col(rng, "str", n, 0.1, maxlen=14), random_col(rng, "f64", n, 0.3),
+            random_col(rng, "i64", n, 0.0), random_col(rng, "i64", n, 0.1), random_col(rng, "f64", n, 0.0), random_col(rng, "i64", n, 0.0)]
+    c = capi.Context(0)
+    c.set_option(capi.OPT_PLAN, capi.PLAN_TWO_PASS)
+    c.set_option(capi.OPT_CHUNK_PLAN, chunk)
+    try:
+        allc = list(range(len(cols)))
+        run_cmp(c, cols, 0, ">", 1000, allc, tag=f"chunk={chunk} clustered")           # dense and sparse tiles
+        run_cmp(c, cols, 0, "<", 450, [0, 2, 3], tag=f"chunk={chunk} nulls pass")       # ~50 % + every null row
+        run_cmp(c, cols, 0, ">=", 0, [2, 0, 0, 4], tag=f"chunk={chunk} all valid rows, k twice")
+        run_cmp(c, cols, 0, "==", 123456, [0, 1], tag=f"chunk={chunk} none")
+        run_cmp(c, cols, 1, "<=", 499.5, [1, 0, 5, 8], tag=f"chunk={chunk} f64 predicate")
+        run_cmp(c, cols, 1, "!=", float("nan"), allc, tag=f"chunk={chunk} f64 != NaN")
+    finally:
+        c.close()
+
+
+def test_chunk_plan_streamed_and_unaligned_views():
+    """The chunk plan inside a chained (streaming) query — the running row count comes in through base_in — and views whose
+    predicate values are not 16-byte aligned (the plan steps aside for the two-pass kernels)."""
+    rng = np.random.default_rng(8)
+    c = capi.Context(0)
+    c.set_option(capi.OPT_PLAN, capi.PLAN_TWO_PASS)
+    try:
+        batches = []
+        for n in (20_000, 4096, 33_333):
+            batches.append([random_col(rng, "i64", n, 0.1, lo=0, hi=1000), random_col(rng, "f64", n, 0.1), random_col(rng, "bool", n, 0.2)])
+        st = c.open_stream([capi.INT64, capi.FLOAT64, capi.BOOLEAN], capi.predicate(0, ">", 300), [0, 1, 2], -1, batch_rows=40_000, n_staging=2)
+        for b in batches:
+            st.push([x.gpu() for x in b])
+        got = st.collect()
+        st.close()
+        want = O.RecordBatch.concat([oracle_batch(b) for b in batches]).filter_project_cmp(0, ">", 300, [0, 1, 2], -1)
+        assert_batches_equal(got, want, "chunk plan, chained batches")
+        n = 50_001
+        cols = [random_col(rng, "i64", n, 0.1, offset=3, tail=2, lo=0, hi=1000), random_col(rng, "f64", n, 0.0, offset=1)]
+        run_cmp(c, cols, 0, ">", 500, [0, 1], tag="unaligned predicate view")
+    finally:
+        c.close()
+
+
 # ------------------------------------------------------------------ RecordBatch::take (record_batch.rs:108-178)
 def test_take_matches_reference(ctx):
     rng = np.random.default_rng(9)

@@ -150,7 +150,9 @@ typedef enum rvl_option {
                                        predicate scan and allocate the outputs at their exact size instead of min(n, limit) rows.
                                        0 = never, 1 = always, 2 = only when the worst case exceeds a quarter of device memory (default) */
     RVL_OPT_CHUNK_PLAN = 12,        /* two-pass plan, predicate column also projected (numeric, no LIMIT): run the single-pass chunk kernel
-                                       that reads that column from HBM once instead of twice (default 1) */
+                                       that reads that column from HBM once instead of twice.  0 = never, 2 = always, 1 (default) = when
+                                       at least ~30 % of the rows survive — estimated from a 64 K-row sample in blocking calls, taken from
+                                       the previous batch in streams (below that the two-pass plan is faster) */
     RVL_OPT__COUNT = 13
 } rvl_option;
 int32_t rvl_ctx_set_option(rvl_ctx* ctx, int32_t option, int64_t value);

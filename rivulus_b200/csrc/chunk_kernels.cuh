@@ -438,4 +438,31 @@ __global__ void __launch_bounds__(kChunkThreads, 1) chunk_filter_kernel(const __
     }
 }
 
+// Selectivity estimate for the plan choice: `groups` runs of 64 consecutive rows spread evenly over the batch (64 K rows by default,
+// ~5 us), the predicate evaluated exactly as the plans do.  The single-pass chunk plan wins from ~30 % survivors upwards (it saves the
+// second read of the predicate column, worth the more the denser the tiles are) and loses below (its pipeline is latency-bound when
+// there is little to compact), so a blocking call spends one tiny kernel + count readback on knowing which side it is on.
+template <int PRED>
+__global__ void __launch_bounds__(kBlock) sample_selectivity_kernel(const __grid_constant__ ChunkParams p, int64_t groups, unsigned long long* out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= groups) return;
+    const int64_t start = ((g * (p.n_rows / groups)) >> 6) << 6;
+    uint32_t kept = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int64_t row = start + h * 32 + lane;
+        bool keep = false;
+        if (row < p.n_rows) {
+            keep = chunk_keep<PRED>(p, ld_stream(p.pred_values + row));
+            if (p.pred_valid.words != nullptr) {
+                const uint64_t bit = p.pred_valid.bit0 + (uint64_t)row;
+                if (((__ldg(p.pred_valid.words + (bit >> 5)) >> (bit & 31)) & 1u) == 0u) keep = p.keep_null != 0u;
+            }
+        }
+        kept += __popc(__ballot_sync(0xFFFFFFFFu, keep));
+    }
+    if (lane == 0 && kept != 0u) atomicAdd(out, (unsigned long long)kept);
+}
+
 }  // namespace rvl

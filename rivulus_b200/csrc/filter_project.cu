@@ -488,7 +488,7 @@ int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pre
         // twice.  Needs: a numeric predicate over a 16-byte-aligned view, no LIMIT (the look-back has no early exit), one column
         // group, worst-case output allocation (the count is only known at the end).
         int chunk_pred_col = -1;
-        if (two_pass && core->chunk_plan && !exact && limit < 0 && launches_needed == 1 && (pp.kind == kPredI64 || pp.kind == kPredF64) && pp.vec_ok) {
+        if (two_pass && core->chunk_plan != 0 && !exact && limit < 0 && launches_needed == 1 && (pp.kind == kPredI64 || pp.kind == kPredF64) && pp.vec_ok) {
             int k8 = 0;
             for (int j = 0; j < nproj && chunk_pred_col < 0; ++j) {
                 const DevColumn& s = in->cols[proj[j]];
@@ -496,6 +496,27 @@ int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pre
                 if (proj[j] == pred->column) chunk_pred_col = k8;
                 ++k8;
             }
+        }
+        if (chunk_pred_col >= 0 && core->chunk_plan == 1) {
+            // which side of the crossover is this batch on?
+            double sel = core->sel_hint;
+            if (core->sync_ok) {
+                ChunkParams sp{};
+                sp.n_rows = n; sp.pred_values = pp.values; sp.lit_bits = pp.lit_bits; sp.range_lo = pp.range_lo; sp.range_span = pp.range_span;
+                sp.range_neg = pp.range_neg; sp.truth = pp.truth; sp.keep_null = pp.keep_null; sp.pred_valid = pp.valid;
+                const int64_t groups = std::min<int64_t>(1024, std::max<int64_t>(1, n / 64));
+                unsigned long long* cnt = dctr + n_counters + 1;   // scratch word of the (zeroed) counter block
+                const unsigned grid = (unsigned)((groups * 32 + kBlock - 1) / kBlock);
+                if (pp.kind == kPredI64) sample_selectivity_kernel<kPredI64><<<grid, kBlock, 0, core->stream>>>(sp, groups, cnt);
+                else sample_selectivity_kernel<kPredF64><<<grid, kBlock, 0, core->stream>>>(sp, groups, cnt);
+                core->launches++;
+                RVL_CUDA_TRY(cudaGetLastError());
+                RVL_CUDA_TRY(cudaMemcpyAsync(core->mailbox, cnt, 8, cudaMemcpyDeviceToHost, core->stream));
+                RVL_CUDA_TRY(cudaMemsetAsync(cnt, 0, 8, core->stream));
+                RVL_CUDA_TRY(cudaStreamSynchronize(core->stream));
+                sel = (double)core->mailbox[0] / (double)(groups * 64);
+            }
+            if (!(sel >= core->chunk_min_sel)) chunk_pred_col = -1;
         }
         if (two_pass && chunk_pred_col >= 0) {
             const int64_t n_chunks = (n + kChunkRows - 1) / kChunkRows;
@@ -773,7 +794,10 @@ int32_t rvl_filter_project(rvl_ctx* ctx, const rvl_batch* in, const rvl_predicat
         }
         exact = worst > ctx->core->device_bytes / 4;
     }
-    RVL_TRY(fp_launch(ctx->core, in, pred, proj, nproj, limit, false, nullptr, nullptr, &p, exact));
+    ctx->core->sync_ok = true;    // a blocking call may spend a host round trip on choosing its plan
+    const int rc = fp_launch(ctx->core, in, pred, proj, nproj, limit, false, nullptr, nullptr, &p, exact);
+    ctx->core->sync_ok = false;
+    RVL_TRY(rc);
     return fp_finish(p, out, nullptr);
 }
 

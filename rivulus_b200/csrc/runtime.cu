@@ -238,7 +238,9 @@ int32_t rvl_ctx_set_option(rvl_ctx* ctx, int32_t option, int64_t value) {
             if (value != 8 && value != 16) return fail(RVL_INVALID_ARGUMENT, "dense_warps must be 8 or 16");
             c.dense_warps = (int)value; return RVL_OK;
         case RVL_OPT_BITS_OVERLAP: c.bits_overlap = value != 0; return RVL_OK;
-        case RVL_OPT_CHUNK_PLAN: c.chunk_plan = value != 0; return RVL_OK;
+        case RVL_OPT_CHUNK_PLAN:
+            if (value < 0 || value > 2) return fail(RVL_INVALID_ARGUMENT, "chunk_plan must be 0 (never), 1 (by selectivity) or 2 (always)");
+            c.chunk_plan = (int)value; return RVL_OK;
         case RVL_OPT_STRING_KERNEL:
             if (value < 1 || value > 4) return fail(RVL_INVALID_ARGUMENT, "string_kernel must be in [1, 4]");
             c.string_kernel = (int)value; return RVL_OK;

@@ -54,7 +54,11 @@ struct CtxCore {
     int string_kernel = 3;               // RVL_OPT_STRING_KERNEL: 1 = round-1 pair; 2 = ranges sizes pass + persistent TMA-staged gather;
                                          //   3 = ranges sizes pass + round-1 gather (default: fastest measured); 4 = 3 with the OR-merging copy
     int string_dense_min = 128;          // RVL_OPT_STRING_DENSE_MIN: survivors per 1024-row sub-tile from which the source block is TMA-staged
-    bool chunk_plan = true;              // RVL_OPT_CHUNK_PLAN: predicate column projected -> single-pass chunk kernel (chunk_kernels.cuh)
+    int chunk_plan = 1;                  // RVL_OPT_CHUNK_PLAN: predicate column projected -> single-pass chunk kernel (chunk_kernels.cuh):
+                                         //   0 never, 1 when the sampled / observed selectivity is at least chunk_min_sel, 2 always
+    double chunk_min_sel = 0.30;         // measured crossover against the two-pass plan (profiles/r02_chunk_plan_sweep.txt)
+    bool sync_ok = false;                // set by blocking entry points around fp_launch: a host round trip (sampling) is acceptable
+    double sel_hint = -1.0;              // set by the streaming executor: selectivity of the most recent batch, or < 0
     int exact_alloc = 2;                 // RVL_OPT_EXACT_ALLOC: 0 never, 1 always, 2 when the worst case exceeds a quarter of device memory
     size_t device_bytes = 0;
     // optional kernel-level timing of the fused kernel (rvl_ctx_profile_*)

@@ -271,7 +271,10 @@ int flush_group(rvl_stream* s) {
     unsigned long long* cur = (unsigned long long*)s->cursor->ptr;
     const int k = (int)(s->groups & 1);
     FpPending* pend = nullptr;
-    RVL_TRY(fp_launch(core, view.get(), &s->pred, s->proj.data(), (int32_t)s->proj.size(), s->limit, false, cur + k, cur + (k ^ 1), &pend));
+    core->sel_hint = s->groups > 0 ? s->recent_sel : -1.0;   // plan choice of the operator: what the previous group kept
+    const int rc_launch = fp_launch(core, view.get(), &s->pred, s->proj.data(), (int32_t)s->proj.size(), s->limit, false, cur + k, cur + (k ^ 1), &pend);
+    core->sel_hint = -1.0;
+    RVL_TRY(rc_launch);
     RVL_CUDA_TRY(cudaEventRecord(sl.free_ev, core->stream));
     // the next H2D into this slot must not start before this kernel has read it
     sl.used = true;

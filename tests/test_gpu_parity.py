@@ -577,7 +577,7 @@ def test_two_pass_ring_depths(slots, per_sm, scan_warps, scan_slots, dense_warps
 
 # ------------------------------------------------------------------ single-pass chunk plan: predicate column projected
 @pytest.mark.parametrize("n", [1, 4095, 4096, 4097, 12_289, 300_001, 1_300_000])
-@pytest.mark.parametrize("chunk", [1, 0])
+@pytest.mark.parametrize("chunk", [2, 1, 0])
 def test_chunk_plan_predicate_column_projected(n, chunk):
     """`filter(k <op> T)` projecting k itself (every column, as a Filter without Select does): the chunk kernel keeps the predicate
     values in shared memory between the predicate and the compaction (one HBM read) and orders the output by decoupled look-back.
@@ -612,6 +612,7 @@ def test_chunk_plan_streamed_and_unaligned_views():
     rng = np.random.default_rng(8)
     c = capi.Context(0)
     c.set_option(capi.OPT_PLAN, capi.PLAN_TWO_PASS)
+    c.set_option(capi.OPT_CHUNK_PLAN, 2)
     try:
         batches = []
         for n in (20_000, 4096, 33_333):

@@ -229,11 +229,17 @@ def run_native(args):
     preds = [capi.predicate(0, ">", thr) for thr, _ in THRESHOLDS]
     proj = [1, 2, 3, 4]
 
-    def step():
+    trace = []
+
+    def step(tag=None):
         counts = []
         for p in preds:
+            if tag is not None and args.trace:
+                t0 = time.perf_counter(); r0 = ctx.pool_stats()
             out = ctx.filter_project(table, p, proj)   # kernels + count readback (AUTO plan: scan + compaction passes at this size)
             counts.append(out.num_rows())
+            if tag is not None and args.trace:
+                trace.append((tag, round((time.perf_counter() - t0) * 1e3, 3), r0[0] >> 20, ctx.pool_stats()[0] >> 20))
             out.release()
         return counts
 
@@ -263,17 +269,19 @@ def run_native(args):
     sampler.start()
     time.sleep(0.25)
     ctx.profile_enable(True)
-    step()                      # one more untimed step with profiling on (event creation paths warm)
+    step(-1)                    # one more untimed step with profiling on (event creation paths warm)
     ctx.profile_read_launches()
     barrier(); torch.cuda.synchronize()
     launches0 = ctx.launch_count()
     sampler.arm()
     e0.record(stream)
-    for _ in range(args.steps):
-        counts = step()
+    for i_step in range(args.steps):
+        counts = step(i_step)
     e1.record(stream)
     e1.synchronize()
     clocks = sampler.stop()
+    if args.trace and rank == 0:
+        print("trace (step, host ms, pool reserved MiB before -> after):", trace[:12], file=sys.stderr)
     torch.cuda.synchronize(); barrier()
     ms_total = e0.elapsed_time(e1)
     gpu_launches = ctx.launch_count() - launches0
@@ -300,7 +308,8 @@ def run_native(args):
         kern_total += sum(times)
         st = sorted(times) or [0.0]
         sweep.append({"threshold": thr, "selectivity": s_act, "survivors": counts[qi], "kernel_ms": avg_ms,
-                      "kernel_ms_min_median_max": [st[0], st[len(st) // 2], st[-1]], "b_alg_gb": alg / 1e9,
+                      "kernel_ms_min_median_max": [st[0], st[len(st) // 2], st[-1]],
+                      "kernel_ms_per_step": [round(x, 4) for x in times], "b_alg_gb": alg / 1e9,
                       "alg_gbs": alg / 1e9 / (avg_ms / 1e3) if avg_ms > 0 else None,
                       "frac_of_peak": alg / 1e9 / (avg_ms / 1e3) / peak if avg_ms > 0 else None,
                       "rows_per_s": rows / (avg_ms / 1e3) if avg_ms > 0 else None,
@@ -878,6 +887,7 @@ def main():
     ap.add_argument("--e2e-rows", type=int, default=512_000_000, help="rows per GPU of the host-resident table of the e2e leg (the same at every N)")
     ap.add_argument("--no-configs", action="store_true", help="skip the c1/c3/c4/c5 sub-records")
     ap.add_argument("--no-golden", action="store_true", help="skip the full-size golden checksum comparison")
+    ap.add_argument("--trace", action="store_true", help="stderr: host time and pool size around every operator call of the timed steps")
     ap.add_argument("--c5-rows", type=int, default=C5_ROWS)
     ap.add_argument("--c5-reps", type=int, default=3)
     ap.add_argument("--c3-rows", type=int, default=200_000_000)

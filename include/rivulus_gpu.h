@@ -111,6 +111,8 @@ int32_t rvl_ctx_synchronize(rvl_ctx* ctx);
 /* Return the cached (freed, kept for reuse) blocks of the context's device memory pool to the driver.  The pool keeps everything it
  * has ever held so steady-state queries never call cudaMalloc; call this between workloads of very different footprints. */
 int32_t rvl_ctx_trim(rvl_ctx* ctx);
+/* Bytes the pool currently holds from the driver (reserved) and the part of them handed out to live buffers (used). */
+int32_t rvl_ctx_pool_stats(rvl_ctx* ctx, uint64_t* reserved_bytes, uint64_t* used_bytes);
 /* the cudaStream_t every kernel of this context is launched on (so callers can time with CUDA events on it) */
 int32_t rvl_ctx_cuda_stream(rvl_ctx* ctx, void** cuda_stream);
 int32_t rvl_ctx_device(rvl_ctx* ctx, int32_t* device);

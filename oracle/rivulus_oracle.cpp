@@ -783,7 +783,7 @@ static std::pair<std::string, DataType> resolve_expr_schema(const Expr& e,
 
 std::vector<std::pair<std::string, DataType>> LogicalPlan::schema() const {  // logical_plan/plan.rs:63-113
     switch (kind) {
-        case DataFrameSource: return src_schema;
+        case DataFrameSource: case CsvFileSource: return src_schema;  // :65-66
         case Select: {
             auto in = input->schema();
             std::vector<std::pair<std::string, DataType>> out;
@@ -827,6 +827,7 @@ void LogicalPlan::validate() const {  // logical_plan/plan.rs:115-202
             break;
         }
         case Limit: input->validate(); break;
+        case CsvFileSource: break;  // :128
     }
 }
 
@@ -954,6 +955,8 @@ static bool eval_predicate_tree(const Expr& p, F&& value_of) {
 static void check_lowering(const LogicalPlan& p) {
     switch (p.kind) {
         case LogicalPlan::DataFrameSource: return;
+        case LogicalPlan::CsvFileSource:   // planner.rs:45-49
+            throw OracleError("Conversion failed: CSV file source not supported in non-streaming physical planner. Use streaming planner instead.");
         case LogicalPlan::Select: check_lowering(*p.input); for (const auto& e : p.expressions) convert_select_expr(e); return;
         case LogicalPlan::Filter:
             check_lowering(*p.input);
@@ -967,6 +970,7 @@ static void check_lowering(const LogicalPlan& p) {
 static DataFrame exec_node(const LogicalPlan& p) {  // physical_plan/plan.rs:65-173
     switch (p.kind) {
         case LogicalPlan::DataFrameSource: return p.df;  // :67
+        case LogicalPlan::CsvFileSource: throw OracleError("unreachable: rejected by check_lowering");
         case LogicalPlan::Select: {                      // :68-96
             DataFrame in = exec_node(*p.input);
             std::vector<std::string> cols, finals;
@@ -1044,6 +1048,11 @@ StreamingPhysicalPlan StreamingPhysicalPlan::memory_source(std::vector<RecordBat
 StreamingPhysicalPlan StreamingPhysicalPlan::dataframe_source(DataFrame df, size_t batch_size) {
     StreamingPhysicalPlan p; p.kind = DataFrameSource; p.df = std::move(df); p.batch_size = batch_size; return p;
 }
+StreamingPhysicalPlan StreamingPhysicalPlan::csv_file_source(std::string path, SchemaRef schema, std::optional<size_t> batch_size,
+                                                             std::optional<std::string> delimiter) {  // streaming.rs:299-311
+    StreamingPhysicalPlan p; p.kind = CsvFileSource; p.csv_path = std::move(path); p.csv_schema = std::move(schema);
+    p.csv_batch_size = batch_size; p.csv_delimiter = std::move(delimiter); return p;
+}
 StreamingPhysicalPlan StreamingPhysicalPlan::filter(std::string col) const {
     StreamingPhysicalPlan p; p.kind = Filter; p.input = std::make_shared<StreamingPhysicalPlan>(*this); p.predicate_column = std::move(col); return p;
 }
@@ -1091,6 +1100,10 @@ DataStreamRef StreamingPhysicalPlan::execute() const {  // streaming.rs:70-133
             SchemaRef s = b.empty() ? std::make_shared<Schema>() : b[0].schema;
             return memory_stream(s, std::move(b));
         }
+        case CsvFileSource: {  // :96-105
+            try { return csv_file_stream(csv_path, csv_schema, csv_batch_size, csv_delimiter); }
+            catch (const OracleError& e) { throw OracleError(std::string("Invalid operation: ") + e.what()); }
+        }
         case Filter: return filter_stream(input->execute(), predicate_column);
         case FilterExpr: { auto st = std::make_unique<FilterExprStream>(); st->input = input->execute(); st->pred = predicate; return st; }
         case Select: {
@@ -1123,6 +1136,21 @@ std::vector<RecordBatch> StreamingPhysicalPlan::collect_batches() const {  // st
 StreamingPhysicalPlan logical_to_streaming(const LogicalPlan& plan) {  // streaming_planner.rs:29-100
     switch (plan.kind) {
         case LogicalPlan::DataFrameSource: return StreamingPhysicalPlan::dataframe_source(plan.df, 1024);  // :31-33
+        case LogicalPlan::CsvFileSource: {  // :35-62 — every field nullable
+            auto schema = std::make_shared<Schema>();
+            for (const auto& p : plan.src_schema) {
+                ExecType t = ExecType::Null;
+                switch (p.second) {
+                    case DataType::Int64: t = ExecType::Int64; break;
+                    case DataType::Float64: t = ExecType::Float64; break;
+                    case DataType::String: t = ExecType::String; break;
+                    case DataType::Boolean: t = ExecType::Boolean; break;
+                    case DataType::Null: t = ExecType::Null; break;
+                }
+                schema->fields.push_back(Field{p.first, t, true});
+            }
+            return StreamingPhysicalPlan::csv_file_source(plan.csv_path, schema, plan.csv_batch_size, plan.csv_delimiter);
+        }
         case LogicalPlan::Select: {  // :65-69, 102-135
             auto in = logical_to_streaming(*plan.input);
             std::vector<std::string> names;
@@ -1167,6 +1195,12 @@ StreamingPhysicalPlan logical_to_streaming(const LogicalPlan& plan) {  // stream
 LazyFrame LazyFrame::from_dataframe(const DataFrame& df) {  // builder.rs:27-39
     LazyFrame lf; lf.plan.kind = LogicalPlan::DataFrameSource; lf.plan.df = df;  // clone
     for (const auto& s : df.columns()) lf.plan.src_schema.emplace_back(s.name(), s.dtype());
+    return lf;
+}
+LazyFrame LazyFrame::from_csv(std::string path, std::vector<std::pair<std::string, DataType>> schema, std::optional<size_t> batch_size,
+                              std::optional<std::string> delimiter) {  // builder.rs:41-55
+    LazyFrame lf; lf.plan.kind = LogicalPlan::CsvFileSource; lf.plan.csv_path = std::move(path); lf.plan.src_schema = std::move(schema);
+    lf.plan.csv_batch_size = batch_size; lf.plan.csv_delimiter = std::move(delimiter);
     return lf;
 }
 LazyFrame LazyFrame::select(std::vector<Expr> e) const {  // builder.rs:57-64

@@ -259,14 +259,23 @@ RecordBatch collect_stream_batches(DataStream& s);                              
 // streaming.rs:135-233
 std::vector<RecordBatch> dataframe_to_batches(const DataFrame& df, size_t batch_size);
 
+// execution/file_stream.rs (csv_oracle.cpp).  SURVEY.md 8(f) rank 3.
+size_t calculate_adaptive_batch_size(const Schema& schema);   // :346-369
+// CsvFileStream::new :20-40 (throws OracleError("Failed to open file: …")); delimiter = one UTF-8 encoded char, default ','
+DataStreamRef csv_file_stream(const std::string& path, SchemaRef schema, std::optional<size_t> batch_size, std::optional<std::string> delimiter);
+// true = reproduce the reference's inverted validity of Int64 / Float64 columns holding a null (:213-240, :245-272); default false
+void set_csv_reference_validity(bool on);
+bool csv_reference_validity();
+
 // ---------------------------------------------------------------------------------------------
 // logical_plan/*, physical_plan/planner.rs, physical_plan/plan.rs, streaming_planner.rs
 // ---------------------------------------------------------------------------------------------
 
-struct LogicalPlan {  // logical_plan/plan.rs:8-39 (CsvFileSource / Join are out of scope)
-    enum Kind { DataFrameSource, Select, Filter, Limit } kind = DataFrameSource;
+struct LogicalPlan {  // logical_plan/plan.rs:8-39 (Join is out of scope)
+    enum Kind { DataFrameSource, Select, Filter, Limit, CsvFileSource } kind = DataFrameSource;
     DataFrame df;                                         // DataFrameSource
-    std::vector<std::pair<std::string, DataType>> src_schema;
+    std::vector<std::pair<std::string, DataType>> src_schema;   // DataFrameSource, CsvFileSource
+    std::string csv_path; std::optional<size_t> csv_batch_size; std::optional<std::string> csv_delimiter;  // CsvFileSource :14-19
     std::shared_ptr<LogicalPlan> input;
     std::vector<Expr> expressions;                        // Select
     Expr predicate;                                       // Filter
@@ -294,8 +303,9 @@ void set_extensions(bool on);
 bool extensions_enabled();
 
 struct StreamingPhysicalPlan {
-    enum Kind { MemorySource, DataFrameSource, Filter, Select, Limit, FilterExpr } kind = MemorySource;
+    enum Kind { MemorySource, DataFrameSource, Filter, Select, Limit, FilterExpr, CsvFileSource } kind = MemorySource;
     Expr predicate;                            // FilterExpr (extension)
+    std::string csv_path; SchemaRef csv_schema; std::optional<size_t> csv_batch_size; std::optional<std::string> csv_delimiter;  // CsvFileSource :39-44
     std::vector<RecordBatch> batches;          // MemorySource
     DataFrame df; size_t batch_size = 0;       // DataFrameSource
     std::shared_ptr<StreamingPhysicalPlan> input;
@@ -304,6 +314,8 @@ struct StreamingPhysicalPlan {
     size_t n = 0;                              // Limit
     static StreamingPhysicalPlan memory_source(std::vector<RecordBatch> b);
     static StreamingPhysicalPlan dataframe_source(DataFrame df, size_t batch_size);
+    static StreamingPhysicalPlan csv_file_source(std::string path, SchemaRef schema, std::optional<size_t> batch_size,
+                                                 std::optional<std::string> delimiter);   // :299-311
     StreamingPhysicalPlan filter(std::string col) const;
     StreamingPhysicalPlan filter_expr(Expr predicate) const;   // extension
     StreamingPhysicalPlan select(std::vector<std::string> cols) const;
@@ -318,6 +330,8 @@ StreamingPhysicalPlan logical_to_streaming(const LogicalPlan& plan);  // streami
 struct LazyFrame {
     LogicalPlan plan;
     static LazyFrame from_dataframe(const DataFrame& df);  // :27-39
+    static LazyFrame from_csv(std::string path, std::vector<std::pair<std::string, DataType>> schema, std::optional<size_t> batch_size,
+                              std::optional<std::string> delimiter);   // :41-55
     LazyFrame select(std::vector<Expr> e) const;           // :57-64
     LazyFrame filter(Expr p) const;                        // :66-73
     LazyFrame limit(size_t n) const;                       // :75-82

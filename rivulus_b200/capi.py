@@ -75,7 +75,7 @@ class RivulusError(RuntimeError):
 # every symbol include/rivulus_gpu.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
     "rvl_abi_version", "rvl_last_error", "rvl_device_count",
-    "rvl_ctx_create", "rvl_ctx_destroy", "rvl_ctx_synchronize", "rvl_ctx_trim", "rvl_ctx_cuda_stream", "rvl_ctx_device", "rvl_ctx_launch_count",
+    "rvl_ctx_create", "rvl_ctx_destroy", "rvl_ctx_synchronize", "rvl_ctx_trim", "rvl_ctx_pool_stats", "rvl_ctx_cuda_stream", "rvl_ctx_device", "rvl_ctx_launch_count",
     "rvl_ctx_profile_enable", "rvl_ctx_profile_read", "rvl_ctx_profile_read_launches", "rvl_ctx_set_option",
     "rvl_host_alloc", "rvl_host_free",
     "rvl_batch_upload", "rvl_batch_wrap_device", "rvl_batch_release", "rvl_batch_num_rows", "rvl_batch_num_columns",
@@ -235,6 +235,12 @@ class Context:
 
     def synchronize(self):
         check(lib().rvl_ctx_synchronize(self._h))
+
+    def pool_stats(self):
+        """(reserved, used) bytes of the device memory pool."""
+        r, u = C.c_uint64(0), C.c_uint64(0)
+        check(lib().rvl_ctx_pool_stats(self._h, C.byref(r), C.byref(u)))
+        return r.value, u.value
 
     def trim(self):
         """rvl_ctx_trim: give the pool's cached blocks back to the driver (between workloads of different footprints)."""

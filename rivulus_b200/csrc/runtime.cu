@@ -6,6 +6,8 @@
 #include "runtime.cuh"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstring>
 
 #include "aux_kernels.cuh"
@@ -30,6 +32,28 @@ CtxCore::~CtxCore() {
     for (cudaEvent_t e : event_pool) cudaEventDestroy(e);
     if (mailbox) cudaFreeHost(mailbox);
     for (uint64_t* c : slot_chunks) cudaFreeHost(c);
+    for (auto& kv : big_free) cudaFree(kv.second);   // streams are gone: synchronous free
+}
+
+void* CtxCore::take_big(size_t bytes, size_t* got) {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = big_free.lower_bound(bytes);
+    if (it == big_free.end() || it->first > bytes + bytes / 8) return nullptr;
+    void* p = it->second;
+    *got = it->first;
+    big_free_bytes -= it->first;
+    big_free.erase(it);
+    return p;
+}
+void CtxCore::give_big(void* p, size_t bytes) {
+    std::lock_guard<std::mutex> g(mu);
+    big_free.emplace(bytes, p);
+    big_free_bytes += bytes;
+}
+void CtxCore::drop_big() {
+    std::multimap<size_t, void*> blocks;
+    { std::lock_guard<std::mutex> g(mu); blocks.swap(big_free); big_free_bytes = 0; }
+    for (auto& kv : blocks) cudaFreeAsync(kv.second, stream);
 }
 
 uint64_t* CtxCore::take_slot() {
@@ -67,6 +91,7 @@ DevBuffer::~DevBuffer() {
     if (owned && ptr != nullptr && core) {
         cudaSetDevice(core->device);
         if (kind == 0) cudaFreeAsync(ptr, core->stream);
+        else if (kind == 3) core->give_big(ptr, bytes);
         else {
             cudaStreamSynchronize(core->stream);
             if (kind == 1) cudaFree(ptr); else cudaIpcCloseMemHandle(ptr);
@@ -76,16 +101,38 @@ DevBuffer::~DevBuffer() {
 
 int dev_alloc(const CoreRef& core, size_t bytes, BufRef* out) {
     // pad so word / 16-byte vector reads at the tail of a buffer stay inside the allocation
-    const size_t padded = ((bytes + 64 + 255) / 256) * 256;
+    size_t padded = ((bytes + 64 + 255) / 256) * 256;
     void* p = nullptr;
+    const bool big = padded >= CtxCore::kBigBlock;
+    if (big) {
+        padded = (padded + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);   // the driver maps 2 MiB pages anyway; fewer distinct sizes
+        size_t got = 0;
+        if ((p = core->take_big(padded, &got)) != nullptr) {
+            auto b = std::make_shared<DevBuffer>();
+            b->ptr = p; b->bytes = got; b->owned = true; b->kind = 3; b->core = core;
+            *out = std::move(b);
+            return RVL_OK;
+        }
+    }
+    static const bool trace = std::getenv("RVL_TRACE_ALLOC") != nullptr;
+    const auto t0 = trace ? std::chrono::steady_clock::now() : std::chrono::steady_clock::time_point();
     cudaError_t e = cudaMallocAsync(&p, padded, core->stream);
+    if (e == cudaErrorMemoryAllocation && core->big_free_bytes > 0) {   // give the context's cached blocks back and try once more
+        cudaGetLastError();
+        core->drop_big();
+        e = cudaMallocAsync(&p, padded, core->stream);
+    }
+    if (trace) {
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (ms > 0.2) std::fprintf(stderr, "[rvl] cudaMallocAsync(%zu) took %.3f ms\n", padded, ms);
+    }
     if (e != cudaSuccess) {
         cudaGetLastError();
         return fail(e == cudaErrorMemoryAllocation ? RVL_OUT_OF_MEMORY : RVL_CUDA,
                     std::string("cudaMallocAsync(") + std::to_string(padded) + "): " + cudaGetErrorString(e));
     }
     auto b = std::make_shared<DevBuffer>();
-    b->ptr = p; b->bytes = padded; b->owned = true; b->core = core;
+    b->ptr = p; b->bytes = padded; b->owned = true; b->kind = big ? 3 : 0; b->core = core;
     *out = std::move(b);
     return RVL_OK;
 }
@@ -194,10 +241,24 @@ int32_t rvl_ctx_synchronize(rvl_ctx* ctx) {
 int32_t rvl_ctx_trim(rvl_ctx* ctx) {
     if (!ctx) return fail(RVL_INVALID_ARGUMENT, "null context");
     RVL_CUDA_TRY(cudaSetDevice(ctx->core->device));
+    ctx->core->drop_big();
     RVL_CUDA_TRY(cudaStreamSynchronize(ctx->core->stream));
     cudaMemPool_t pool;
     RVL_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, ctx->core->device));
     RVL_CUDA_TRY(cudaMemPoolTrimTo(pool, 0));
+    return RVL_OK;
+}
+
+int32_t rvl_ctx_pool_stats(rvl_ctx* ctx, uint64_t* reserved_bytes, uint64_t* used_bytes) {
+    if (!ctx) return fail(RVL_INVALID_ARGUMENT, "null context");
+    RVL_CUDA_TRY(cudaSetDevice(ctx->core->device));
+    cudaMemPool_t pool;
+    RVL_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, ctx->core->device));
+    uint64_t r = 0, u = 0;
+    RVL_CUDA_TRY(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &r));
+    RVL_CUDA_TRY(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &u));
+    if (reserved_bytes) *reserved_bytes = r;
+    if (used_bytes) *used_bytes = u;
     return RVL_OK;
 }
 
@@ -847,6 +908,14 @@ static int alloc_ipc(const CoreRef& core, size_t bytes, BufRef* out) {
     const size_t padded = ((bytes + 64 + 255) / 256) * 256;
     void* p = nullptr;
     cudaError_t e = cudaMalloc(&p, padded);
+    if (e == cudaErrorMemoryAllocation) {   // cached blocks of the context and of the pool go back to the driver, then once more
+        cudaGetLastError();
+        core->drop_big();
+        cudaStreamSynchronize(core->stream);
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, core->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+        e = cudaMalloc(&p, padded);
+    }
     if (e != cudaSuccess) {
         cudaGetLastError();
         return fail(e == cudaErrorMemoryAllocation ? RVL_OUT_OF_MEMORY : RVL_CUDA, std::string("cudaMalloc(") + std::to_string(padded) + "): " + cudaGetErrorString(e));

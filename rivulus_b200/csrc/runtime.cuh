@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cstdint>
 #include <memory>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -43,7 +44,17 @@ struct CtxCore {
     // finished; the list grows by whole pinned chunks, so any number of launches may be outstanding without two of them
     // ever sharing a slot (a fixed ring aliased once more than its size were in flight).
     static constexpr size_t kSlotWords = 64, kSlotsPerChunk = 64;
-    std::mutex mu;                             // guards slot_free / slot_chunks / event_pool / prof_events
+    std::mutex mu;                             // guards slot_free / slot_chunks / event_pool / prof_events / big_free
+    // Blocks of at least kBigBlock bytes are recycled by the context itself instead of going back to the driver's pool: the pool
+    // re-creates multi-GB blocks after a synchronisation under some free-list layouts (measured: one cudaMallocAsync(8 GB) of a
+    // steady-state query taking 26-540 ms, ~5.5 ms per GB, profiles/r02_alloc_outlier.txt).  Every dev_alloc is ordered on
+    // `stream`, and so is every release, so handing a released block to the next dev_alloc keeps the stream order the pool gave.
+    static constexpr size_t kBigBlock = 16u << 20;
+    std::multimap<size_t, void*> big_free;     // size -> block
+    size_t big_free_bytes = 0;
+    void* take_big(size_t bytes, size_t* got);                 // smallest cached block in [bytes, bytes * 9/8], or nullptr
+    void give_big(void* p, size_t bytes);
+    void drop_big();                                           // cudaFreeAsync every cached block (trim, OOM retry, teardown)
     std::vector<uint64_t*> slot_free;
     std::vector<uint64_t*> slot_chunks;
     uint64_t* take_slot();
@@ -99,7 +110,8 @@ struct DevBuffer {
     size_t bytes = 0;
     bool owned = true;      // freed by the destructor (how: `kind`)
     int kind = 0;           // 0 = stream-ordered pool allocation (cudaFreeAsync), 1 = cudaMalloc (exportable over CUDA IPC: cudaFree),
-                            // 2 = another process's allocation mapped through CUDA IPC (cudaIpcCloseMemHandle)
+                            // 2 = another process's allocation mapped through CUDA IPC (cudaIpcCloseMemHandle),
+                            // 3 = pool allocation of >= CtxCore::kBigBlock bytes, recycled through CtxCore::big_free
     CoreRef core;
     ~DevBuffer();
 };

@@ -840,6 +840,12 @@ StreamingPhysicalPlan StreamingPhysicalPlan::dataframe_source(DataFrame df, size
     p.ctx = std::move(ctx);  // resolved lazily (Context::shared(0)) when the plan executes
     return p;
 }
+StreamingPhysicalPlan StreamingPhysicalPlan::csv_file_source(std::string path, SchemaRef schema, std::optional<size_t> batch_size,
+                                                             std::optional<std::string> delimiter, ContextRef ctx) {  // streaming.rs:299-311
+    StreamingPhysicalPlan p; p.kind = CsvFileSource; p.csv_path = std::move(path); p.csv_schema = std::move(schema);
+    p.csv_batch_size = batch_size; p.csv_delimiter = std::move(delimiter); p.ctx = std::move(ctx);
+    return p;
+}
 StreamingPhysicalPlan StreamingPhysicalPlan::filter(std::string col) const {
     StreamingPhysicalPlan p; p.kind = Filter; p.input = std::make_shared<StreamingPhysicalPlan>(*this); p.predicate_column = std::move(col); p.ctx = ctx; return p;
 }
@@ -866,6 +872,10 @@ static DataStreamRef build_stream(const StreamingPhysicalPlan& p, size_t min_bat
             auto b = dataframe_to_batches(ctx, p.df, std::max(p.batch_size, min_batch_rows));
             SchemaRef s = b.empty() ? std::make_shared<Schema>() : b[0].schema();
             return make_memory_stream(ctx, s, std::move(b));
+        }
+        case K::CsvFileSource: {  // :96-105
+            try { return make_csv_file_stream(p.ctx, p.csv_path, p.csv_schema, p.csv_batch_size, p.csv_delimiter); }
+            catch (const Error& e) { if (e.panic) throw; throw Error(std::string("Invalid operation: ") + e.what()); }
         }
         case K::Filter: return make_filter_stream(build_stream(*p.input, min_batch_rows), p.predicate_column);
         case K::FilterExpr: return make_filter_expr_stream(build_stream(*p.input, min_batch_rows), p.predicate);
@@ -908,17 +918,27 @@ static std::optional<RecordBatch> try_fused_collect(const StreamingPhysicalPlan&
         if (p->predicate.kind != Expr::Binary || p->predicate.op == BinaryOperator::And || p->predicate.op == BinaryOperator::Or) return std::nullopt;
         cmp = &p->predicate; p = p->input.get();
     }
-    if (p->kind != K::DataFrameSource || p->df.is_empty() || p->batch_size == 0) return std::nullopt;
+    const bool from_csv = p->kind == K::CsvFileSource;
+    if (!from_csv && (p->kind != K::DataFrameSource || p->df.is_empty() || p->batch_size == 0)) return std::nullopt;
     if (!limit && !sel && !pred && !cmp) return std::nullopt;
     const DataFrame& df = p->df;
-    const size_t ncols = df.columns().size();
     auto in_schema = std::make_shared<Schema>();
     std::vector<int32_t> dtypes;
-    for (const auto& s : df.columns()) {
-        in_schema->fields.push_back(Field{s.name(), exec_type_of(s.dtype()), true});
-        dtypes.push_back(rvl_dtype_of(s.dtype()));
-        if (s.dtype() == DataType::Null) return std::nullopt;
+    if (from_csv) {
+        if (!p->csv_schema || p->csv_schema->fields.empty()) return std::nullopt;
+        *in_schema = *p->csv_schema;
+        for (const auto& f : in_schema->fields) {
+            if (f.data_type == ExecType::Null) return std::nullopt;
+            dtypes.push_back((int32_t)f.data_type);
+        }
+    } else {
+        for (const auto& s : df.columns()) {
+            in_schema->fields.push_back(Field{s.name(), exec_type_of(s.dtype()), true});
+            dtypes.push_back(rvl_dtype_of(s.dtype()));
+            if (s.dtype() == DataType::Null) return std::nullopt;
+        }
     }
+    const size_t ncols = in_schema->fields.size();
     rvl_predicate rp{};
     rp.mode = RVL_PRED_TRUE;
     if (pred) {
@@ -953,31 +973,71 @@ static std::optional<RecordBatch> try_fused_collect(const StreamingPhysicalPlan&
         for (size_t i = 0; i < ncols; ++i) proj.push_back((int32_t)i);
         out_schema = in_schema;
     }
+    const ContextRef ctx = p->ctx ? p->ctx : Context::shared(0);
+    rvl_stream_config cfg{};
+    cfg.n_staging = 3; cfg.transfer = RVL_TRANSFER_AUTO;
+    struct Closer { rvl_stream* s = nullptr; ~Closer() { if (s) rvl_stream_close(s); } } closer;
+    auto open = [&](size_t slot_rows) {
+        cfg.batch_rows = (int64_t)slot_rows;
+        check(rvl_stream_open(ctx->handle(), dtypes.data(), (int32_t)ncols, &rp, proj.data(), (int32_t)proj.size(),
+                              limit ? (int64_t)*limit : -1, &cfg, &closer.s));
+    };
+    auto finish = [&]() {
+        rvl_batch* out = nullptr;
+        check(rvl_stream_collect(closer.s, &out));
+        return RecordBatch::adopt(ctx, out_schema, out);
+    };
+
+    if (from_csv) {
+        // CsvFileStream -> [Filter] -> [Select] -> [Limit] (file_stream.rs + stream.rs) as one pipeline: the parser fills reusable host
+        // buffers, rvl_stream_push copies them into the stream's pinned staging slot before it returns (so the parser can go on with
+        // the next batch at once) and appends small batches to one operator launch; parsing overlaps H2D and the kernels of the
+        // batches before.  A reached LIMIT stops the reading (LimitStream pulls nothing further, streaming.rs:269-271).
+        std::unique_ptr<CsvBatchReader> reader;
+        try { reader = std::make_unique<CsvBatchReader>(p->csv_path, p->csv_schema, p->csv_batch_size, p->csv_delimiter); }
+        catch (const Error& e) { if (e.panic) throw; throw Error(std::string("Invalid operation: ") + e.what()); }   // streaming.rs:102-103
+        // String batches cannot be appended to a group: one launch per batch, slot = batch; otherwise groups of up to 1 Mi rows
+        bool has_string = false;
+        for (const auto& f : in_schema->fields) has_string |= f.data_type == ExecType::String;
+        const size_t bs = std::max<size_t>(reader->batch_size(), 1);
+        open(has_string ? bs : std::max(bs, K::kCollectBatchRows));
+        for (;;) {
+            size_t rows = 0;
+            try { rows = reader->read_batch(); }
+            catch (const Error& e) {
+                if (e.panic) throw;
+                // The reference reads batch j only while fewer than `limit` rows came out of batches < j: an error in a batch it
+                // would never have pulled must not surface.  Collect what is in flight and see.
+                if (limit) { RecordBatch done = finish(); if (done.num_rows() >= *limit) return done; }
+                throw Error(wrap_stream_err(e.what()));
+            }
+            if (rows == 0) break;
+            if (csv_reference_validity()) reader->apply_reference_validity();
+            const std::vector<rvl_column> cols = reader->columns();
+            int32_t accepted = 0;
+            check(rvl_stream_push(closer.s, cols.data(), (int32_t)ncols, &accepted));
+            if (!accepted) break;
+        }
+        return finish();
+    }
+
     // dataframe_to_batches converts every batch before the first one is pulled: a Float64 series holding an Int64 panics (streaming.rs:189)
     for (const auto& s : df.columns())
         if (s.is_mixed())
             for (size_t i = 0; i < s.len(); ++i)
                 if (s.at(i).tag == AnyValue::kInt64) throw Error("Type mismatch in Float64 series", true);
 
-    const ContextRef ctx = p->ctx ? p->ctx : Context::shared(0);
     const size_t rows = df.height(), batch = std::max(p->batch_size, K::kCollectBatchRows);
-    rvl_stream_config cfg{};
-    cfg.batch_rows = (int64_t)std::min(batch, rows); cfg.n_staging = 3; cfg.transfer = RVL_TRANSFER_AUTO;
-    rvl_stream* st = nullptr;
-    check(rvl_stream_open(ctx->handle(), dtypes.data(), (int32_t)ncols, &rp, proj.data(), (int32_t)proj.size(),
-                          limit ? (int64_t)*limit : -1, &cfg, &st));
-    struct Closer { rvl_stream* s; ~Closer() { rvl_stream_close(s); } } closer{st};
+    open(std::min(batch, rows));
     std::vector<rvl_column> cols(ncols);
     for (size_t start = 0; start < rows; start += batch) {
         const size_t len = std::min(batch, rows - start);
         for (size_t c = 0; c < ncols; ++c) cols[c] = df.columns()[c].as_column(start, len, /*flatten_nulls=*/true);
         int32_t accepted = 0;
-        check(rvl_stream_push(st, cols.data(), (int32_t)ncols, &accepted));
+        check(rvl_stream_push(closer.s, cols.data(), (int32_t)ncols, &accepted));
         if (!accepted) break;  // LIMIT reached on the device: nothing more is transferred
     }
-    rvl_batch* out = nullptr;
-    check(rvl_stream_collect(st, &out));
-    return RecordBatch::adopt(ctx, out_schema, out);
+    return finish();
 }
 
 RecordBatch StreamingPhysicalPlan::collect() const {  // streaming.rs:235-238
@@ -1024,7 +1084,7 @@ static std::pair<std::string, DataType> resolve_expr_schema(const Expr& e, const
 
 SchemaVec LogicalPlan::schema() const {  // logical_plan/plan.rs:63-113
     switch (kind) {
-        case DataFrameSource: return src_schema;
+        case DataFrameSource: case CsvFileSource: return src_schema;   // :65-66
         case Select: {
             const auto in = input->schema();
             SchemaVec out;
@@ -1064,12 +1124,14 @@ void LogicalPlan::validate() const {  // logical_plan/plan.rs:115-202
         }
         case Filter: input->validate(); validate_expr_columns(predicate, input->schema()); break;
         case Limit: input->validate(); break;
+        case CsvFileSource: break;   // :128
     }
 }
 
 std::string LogicalPlan::shape() const {
     switch (kind) {
         case DataFrameSource: return "Source";
+        case CsvFileSource: return "CsvSource";
         case Select: return "Select(" + input->shape() + ")";
         case Filter: return "Filter(" + input->shape() + ")";
         case Limit: return "Limit(" + input->shape() + ")";
@@ -1080,6 +1142,7 @@ std::string LogicalPlan::shape() const {
 std::string LogicalPlan::describe() const {
     switch (kind) {
         case DataFrameSource: return "DataFrameSource";
+        case CsvFileSource: return "CsvFileSource { path: \"" + csv_path + "\" }";
         case Select: {
             std::string e;
             for (size_t i = 0; i < expressions.size(); ++i) e += (i ? ", " : "") + expressions[i].debug();
@@ -1183,6 +1246,8 @@ static void leaf_columns(const Expr& p, std::vector<std::string>& out) {
 static void check_lowering(const LogicalPlan& p) {  // logical_to_physical runs over the whole tree before execution
     switch (p.kind) {
         case LogicalPlan::DataFrameSource: return;
+        case LogicalPlan::CsvFileSource:   // planner.rs:45-49
+            throw Error("Conversion failed: CSV file source not supported in non-streaming physical planner. Use streaming planner instead.");
         case LogicalPlan::Select: check_lowering(*p.input); for (const auto& e : p.expressions) convert_select_expr(e); return;
         case LogicalPlan::Filter:
             check_lowering(*p.input);
@@ -1416,6 +1481,7 @@ struct FilterExprStream : DataStream {
 Frame exec_node(const ContextRef& ctx, const LogicalPlan& p) {  // physical_plan/plan.rs:65-173
     switch (p.kind) {
         case LogicalPlan::DataFrameSource: return upload_frame(ctx, p.df);
+        case LogicalPlan::CsvFileSource: throw Error("unreachable: rejected by check_lowering");
         case LogicalPlan::Filter: {
             Frame in = exec_node(ctx, *p.input);
             if (in.names.empty()) { std::vector<std::string> c; leaf_columns(p.predicate, c); throw Error("Column not found: '" + c[0] + "'"); }
@@ -1512,6 +1578,11 @@ DataFrame execute_eager(const LogicalPlan& optimized, const ContextRef& ctx) {
 StreamingPhysicalPlan logical_to_streaming(const LogicalPlan& plan, const ContextRef& ctx) {  // streaming_planner.rs:29-100
     switch (plan.kind) {
         case LogicalPlan::DataFrameSource: return StreamingPhysicalPlan::dataframe_source(plan.df, 1024, ctx);  // :31-33
+        case LogicalPlan::CsvFileSource: {  // :35-62 — every field nullable
+            auto schema = std::make_shared<Schema>();
+            for (const auto& f : plan.src_schema) schema->fields.push_back(Field{f.first, exec_type_of(f.second), true});
+            return StreamingPhysicalPlan::csv_file_source(plan.csv_path, schema, plan.csv_batch_size, plan.csv_delimiter, ctx);
+        }
         case LogicalPlan::Select: {  // :65-69, 102-135
             auto in = logical_to_streaming(*plan.input, ctx);
             std::vector<std::string> names;
@@ -1555,6 +1626,15 @@ LazyFrame LazyFrame::from_dataframe(const DataFrame& df, ContextRef ctx) {  // b
     lf.plan_.kind = LogicalPlan::DataFrameSource;
     lf.plan_.df = df;
     for (const auto& s : df.columns()) lf.plan_.src_schema.emplace_back(s.name(), s.dtype());
+    lf.ctx_ = std::move(ctx);
+    return lf;
+}
+LazyFrame LazyFrame::from_csv(std::string path, std::vector<std::pair<std::string, DataType>> schema, std::optional<size_t> batch_size,
+                              std::optional<std::string> delimiter, ContextRef ctx) {  // builder.rs:41-55
+    LazyFrame lf;
+    lf.plan_.kind = LogicalPlan::CsvFileSource;
+    lf.plan_.csv_path = std::move(path); lf.plan_.src_schema = std::move(schema);
+    lf.plan_.csv_batch_size = batch_size; lf.plan_.csv_delimiter = std::move(delimiter);
     lf.ctx_ = std::move(ctx);
     return lf;
 }

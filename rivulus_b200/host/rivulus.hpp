@@ -307,12 +307,36 @@ DataStreamRef make_limit_stream(DataStreamRef input, size_t limit);             
 std::vector<RecordBatch> collect_all_batches(DataStream& s);                                 // streaming.rs:335-341
 RecordBatch collect_stream_batches(const ContextRef& ctx, DataStream& s);                    // streaming.rs:343-352
 
+// execution/file_stream.rs (csv_stream.cpp) — SURVEY.md 8(f) rank 3
+size_t calculate_adaptive_batch_size(const Schema& schema);   // :346-369
+// true = reproduce the reference's inverted validity of Int64 / Float64 columns that hold a null (:213-240, :245-272); default false
+void set_csv_reference_validity(bool on);
+bool csv_reference_validity();
+// The parser behind CsvFileStream: `batch_size` data lines at a time straight into reusable Arrow-layout host buffers.
+class CsvBatchReader {
+  public:
+    // CsvFileStream::new :20-40; throws Error("Failed to open file: …").  delimiter: one UTF-8 encoded char, default ","
+    CsvBatchReader(const std::string& path, SchemaRef schema, std::optional<size_t> batch_size, std::optional<std::string> delimiter);
+    ~CsvBatchReader();
+    const SchemaRef& schema() const;
+    size_t batch_size() const;
+    size_t read_batch();                      // read_batch :123-199: rows parsed, 0 = end of file; throws "Stream execution error: …"
+    std::vector<rvl_column> columns() const;  // host views of the batch just parsed (valid until the next read_batch)
+    void apply_reference_validity();          // see set_csv_reference_validity
+  private:
+    struct Impl;
+    std::unique_ptr<Impl> impl_;
+};
+DataStreamRef make_csv_file_stream(const ContextRef& ctx, const std::string& path, SchemaRef schema, std::optional<size_t> batch_size,
+                                   std::optional<std::string> delimiter);   // CsvFileStream as a DataStream :328-336
+
 // streaming.rs:135-233: DataFrame -> RecordBatches of `batch_size` rows on the device
 std::vector<RecordBatch> dataframe_to_batches(const ContextRef& ctx, const DataFrame& df, size_t batch_size);
 
 struct StreamingPhysicalPlan {  // streaming.rs:28-68, 290-333
-    enum Kind { MemorySource, DataFrameSource, Filter, Select, Limit, FilterExpr } kind = MemorySource;
+    enum Kind { MemorySource, DataFrameSource, Filter, Select, Limit, FilterExpr, CsvFileSource } kind = MemorySource;
     Expr predicate;   // FilterExpr (opt-in extension, see set_extensions)
+    std::string csv_path; SchemaRef csv_schema; std::optional<size_t> csv_batch_size; std::optional<std::string> csv_delimiter;  // :39-44
     std::vector<RecordBatch> batches;
     DataFrame df; size_t batch_size = 0;
     std::shared_ptr<StreamingPhysicalPlan> input;
@@ -322,6 +346,8 @@ struct StreamingPhysicalPlan {  // streaming.rs:28-68, 290-333
     ContextRef ctx;
     static StreamingPhysicalPlan memory_source(std::vector<RecordBatch> b);
     static StreamingPhysicalPlan dataframe_source(DataFrame df, size_t batch_size, ContextRef ctx = nullptr);
+    static StreamingPhysicalPlan csv_file_source(std::string path, SchemaRef schema, std::optional<size_t> batch_size,
+                                                 std::optional<std::string> delimiter, ContextRef ctx = nullptr);   // :299-311
     StreamingPhysicalPlan filter(std::string col) const;
     StreamingPhysicalPlan filter_expr(Expr predicate) const;   // extension
     StreamingPhysicalPlan select(std::vector<std::string> cols) const;
@@ -329,7 +355,7 @@ struct StreamingPhysicalPlan {  // streaming.rs:28-68, 290-333
     DataStreamRef execute() const;                      // :70-133 (one operator object per node, batches of `batch_size`)
     // :235-238.  The result is the concatenation of every batch, so it does not depend on the batch size: plans rooted
     // at a DataFrame source run with batches of at least kCollectBatchRows rows (fewer, larger kernel launches).
-    // [Limit] -> [Select] -> [Filter] over a DataFrame source runs as one pinned, overlapped device pipeline (rvl_stream_*).
+    // [Limit] -> [Select] -> [Filter] over a DataFrame or CSV source runs as one pinned, overlapped device pipeline (rvl_stream_*).
     RecordBatch collect() const;
     std::vector<RecordBatch> collect_batches() const;   // :240-243 (honours batch_size: batch boundaries are visible)
     static constexpr size_t kCollectBatchRows = 1 << 20;
@@ -347,10 +373,11 @@ void set_extensions(bool on);
 bool extensions_enabled();
 
 // ---------------------------------------------------------------------------------------- logical_plan/*
-struct LogicalPlan {  // logical_plan/plan.rs:8-39 (CsvFileSource / Join: out of scope)
-    enum Kind { DataFrameSource, Select, Filter, Limit } kind = DataFrameSource;
+struct LogicalPlan {  // logical_plan/plan.rs:8-39 (Join: out of scope)
+    enum Kind { DataFrameSource, Select, Filter, Limit, CsvFileSource } kind = DataFrameSource;
     DataFrame df;
-    std::vector<std::pair<std::string, DataType>> src_schema;
+    std::vector<std::pair<std::string, DataType>> src_schema;   // DataFrameSource, CsvFileSource
+    std::string csv_path; std::optional<size_t> csv_batch_size; std::optional<std::string> csv_delimiter;   // CsvFileSource :14-19
     std::shared_ptr<LogicalPlan> input;
     std::vector<Expr> expressions;
     Expr predicate;
@@ -367,6 +394,8 @@ DataFrame execute_eager(const LogicalPlan& optimized, const ContextRef& ctx);  /
 class LazyFrame {  // logical_plan/builder.rs:11-114
   public:
     static LazyFrame from_dataframe(const DataFrame& df, ContextRef ctx = nullptr);  // :27-39
+    static LazyFrame from_csv(std::string path, std::vector<std::pair<std::string, DataType>> schema, std::optional<size_t> batch_size = std::nullopt,
+                              std::optional<std::string> delimiter = std::nullopt, ContextRef ctx = nullptr);   // :41-55
     LazyFrame select(std::vector<Expr> exprs) const;   // :57-64
     LazyFrame filter(Expr predicate) const;            // :66-73
     LazyFrame limit(size_t n) const;                   // :75-82

@@ -1,0 +1,12 @@
+set -x
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r02_pytest_gpu.log
+timeout 900 python bench.py > gpurun_out/r02_bench_n1.json 2> gpurun_out/r02_bench_n1.err; echo "bench rc=$?"; tail -3 gpurun_out/r02_bench_n1.err
+python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/r02_bench_n1.json").read().strip().splitlines()[-1])
+print(d["value"]/1e9, d["ms_per_step"], d["roofline"]["frac"])
+for q in d["sweep"]: print(q["threshold"], q["kernel_ms_min_median_max"], q["kernel_ms_per_step"])
+print("e2e", d["e2e"]["value"]/1e9)
+for k in ("c1","c3","c4","c5"): print(k, json.dumps(d.get(k))[:1500])
+PY
+timeout 1500 bash scripts/gpu_r02_profile.sh > gpurun_out/r02_profile.log 2>&1; echo "profile rc=$?"; tail -5 gpurun_out/r02_profile.log

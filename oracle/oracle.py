@@ -59,7 +59,7 @@ def lib():
         build()
         L = C.CDLL(_LIB_PATH)
         L.orc_last_error.restype = C.c_char_p
-        for name in ("orc_dfb_new", "orc_expr_col", "orc_expr_lit", "orc_expr_binary", "orc_expr_alias", "orc_lf_from_df",
+        for name in ("orc_dfb_new", "orc_expr_col", "orc_expr_lit", "orc_expr_binary", "orc_expr_alias", "orc_lf_from_df", "orc_lf_from_csv", "orc_sp_csv_source",
                      "orc_lf_select", "orc_lf_filter", "orc_lf_limit", "orc_arr_i64", "orc_arr_f64", "orc_arr_bool",
                      "orc_arr_str", "orc_arr_null", "orc_arr_i64_new", "orc_arr_f64_new", "orc_arr_bool_new",
                      "orc_sp_memory_source", "orc_sp_dataframe_source", "orc_sp_filter", "orc_sp_select", "orc_sp_limit",
@@ -68,7 +68,7 @@ def lib():
         for name in ("orc_df_col_name", "orc_rb_col_name"):
             getattr(L, name).restype = C.c_char_p
         for name in ("orc_df_height", "orc_df_col_len", "orc_df_col_str_bytes", "orc_arr_len", "orc_arr_null_count",
-                     "orc_rb_num_rows"):
+                     "orc_rb_num_rows", "orc_csv_adaptive_batch_size"):
             getattr(L, name).restype = C.c_int64
         L.orc_time_eager_filter_select.restype = C.c_double
         L.orc_time_eager_filter_select_mt.restype = C.c_double
@@ -244,6 +244,16 @@ def set_extensions(on: bool) -> None:
     lib().orc_set_extensions(1 if on else 0)
 
 
+def set_csv_reference_validity(on: bool) -> None:
+    """True = the reference's inverted validity of Int64 / Float64 CSV columns holding a null (file_stream.rs:213-240); default False."""
+    lib().orc_set_csv_reference_validity(1 if on else 0)
+
+
+def calculate_adaptive_batch_size(exec_dtypes) -> int:
+    a = (C.c_int * max(len(exec_dtypes), 1))(*exec_dtypes)
+    return int(lib().orc_csv_adaptive_batch_size(len(exec_dtypes), a))
+
+
 def col(name) -> Expr:
     return Expr(lib().orc_expr_col(name.encode()))
 
@@ -264,6 +274,13 @@ class LazyFrame:
     @staticmethod
     def from_dataframe(df: DataFrame):
         return LazyFrame(lib().orc_lf_from_df(_vp(df._h)))
+
+    @staticmethod
+    def from_csv(path, schema, batch_size=None, delimiter=None):
+        names = (C.c_char_p * max(len(schema), 1))(*[n.encode() for n, _ in schema])
+        dts = (C.c_int * max(len(schema), 1))(*[d for _, d in schema])
+        return LazyFrame(lib().orc_lf_from_csv(str(path).encode(), len(schema), names, dts, C.c_int64(-1 if batch_size is None else batch_size),
+                                               None if delimiter is None else delimiter.encode()))
 
     def select(self, exprs: List[Expr]):
         arr = (C.c_void_p * len(exprs))(*[e._h for e in exprs])
@@ -550,6 +567,15 @@ class StreamingPhysicalPlan:
     @staticmethod
     def dataframe_source(df: DataFrame, batch_size: int):
         return StreamingPhysicalPlan(lib().orc_sp_dataframe_source(_vp(df._h), C.c_int64(batch_size)))
+
+    @staticmethod
+    def csv_file_source(path, fields, batch_size=None, delimiter=None):
+        names = (C.c_char_p * max(len(fields), 1))(*[f[0].encode() for f in fields])
+        dts = (C.c_int * max(len(fields), 1))(*[f[1] for f in fields])
+        nul = (C.c_int * max(len(fields), 1))(*[1 if f[2] else 0 for f in fields])
+        return StreamingPhysicalPlan(lib().orc_sp_csv_source(str(path).encode(), len(fields), names, dts, nul,
+                                                             C.c_int64(-1 if batch_size is None else batch_size),
+                                                             None if delimiter is None else delimiter.encode()))
 
     def filter(self, colname): return StreamingPhysicalPlan(lib().orc_sp_filter(_vp(self._h), colname.encode()))
 

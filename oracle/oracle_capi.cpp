@@ -108,6 +108,18 @@ void* orc_expr_alias(void* e, const char* name) { return new Expr(((Expr*)e)->al
 void orc_expr_free(void* e) { delete (Expr*)e; }
 
 void* orc_lf_from_df(void* df) { return new LazyFrame(LazyFrame::from_dataframe(*(DataFrame*)df)); }
+void* orc_lf_from_csv(const char* path, int nfields, const char** names, const int* dtypes, int64_t batch_size, const char* delimiter) {
+    std::vector<std::pair<std::string, DataType>> schema;
+    for (int i = 0; i < nfields; ++i) schema.emplace_back(names[i], (DataType)dtypes[i]);
+    return new LazyFrame(LazyFrame::from_csv(path, std::move(schema), batch_size < 0 ? std::nullopt : std::optional<size_t>((size_t)batch_size),
+                                             delimiter ? std::optional<std::string>(delimiter) : std::nullopt));
+}
+void orc_set_csv_reference_validity(int on) { set_csv_reference_validity(on != 0); }
+int64_t orc_csv_adaptive_batch_size(int nfields, const int* exec_dtypes) {
+    Schema s;
+    for (int i = 0; i < nfields; ++i) s.fields.push_back(Field{"c" + std::to_string(i), (ExecType)exec_dtypes[i], true});
+    return (int64_t)calculate_adaptive_batch_size(s);
+}
 void* orc_lf_select(void* lf, int n, void** exprs) {
     std::vector<Expr> e; for (int i = 0; i < n; ++i) e.push_back(*(Expr*)exprs[i]);
     return new LazyFrame(((LazyFrame*)lf)->select(std::move(e)));
@@ -126,6 +138,7 @@ int orc_lf_collect_streaming(void* lf, void** rb_out) {
 static std::string describe_plan(const LogicalPlan& p) {
     switch (p.kind) {
         case LogicalPlan::DataFrameSource: return "DataFrameSource";
+        case LogicalPlan::CsvFileSource: return "CsvFileSource { path: \"" + p.csv_path + "\" }";
         case LogicalPlan::Select: {
             std::string e;
             for (size_t i = 0; i < p.expressions.size(); ++i) e += (i ? ", " : "") + p.expressions[i].debug();
@@ -155,11 +168,12 @@ int orc_lf_plan_shape(void* lf, char* buf, int cap) {
     while (true) {
         switch (cur->kind) {
             case LogicalPlan::DataFrameSource: s += "Source"; break;
+            case LogicalPlan::CsvFileSource: s += "CsvSource"; break;
             case LogicalPlan::Select: s += "Select("; close += ")"; break;
             case LogicalPlan::Filter: s += "Filter("; close += ")"; break;
             case LogicalPlan::Limit: s += "Limit("; close += ")"; break;
         }
-        if (cur->kind == LogicalPlan::DataFrameSource) break;
+        if (cur->kind == LogicalPlan::DataFrameSource || cur->kind == LogicalPlan::CsvFileSource) break;
         cur = cur->input.get();
     }
     s += close;
@@ -319,6 +333,13 @@ void* orc_sp_memory_source(void** rbs, int n) {
 }
 void* orc_sp_dataframe_source(void* df, int64_t batch_size) {
     return new StreamingPhysicalPlan(StreamingPhysicalPlan::dataframe_source(*(DataFrame*)df, (size_t)batch_size));
+}
+void* orc_sp_csv_source(const char* path, int nfields, const char** names, const int* exec_dtypes, const int* nullable, int64_t batch_size,
+                        const char* delimiter) {
+    auto schema = std::make_shared<Schema>();
+    for (int i = 0; i < nfields; ++i) schema->fields.push_back(Field{names[i], (ExecType)exec_dtypes[i], nullable[i] != 0});
+    return new StreamingPhysicalPlan(StreamingPhysicalPlan::csv_file_source(path, schema, batch_size < 0 ? std::nullopt : std::optional<size_t>((size_t)batch_size),
+                                                                            delimiter ? std::optional<std::string>(delimiter) : std::nullopt));
 }
 void* orc_sp_filter(void* sp, const char* col) { return new StreamingPhysicalPlan(((StreamingPhysicalPlan*)sp)->filter(col)); }
 void* orc_sp_select(void* sp, const char** names, int n) {

@@ -42,7 +42,7 @@ HOST_SYMBOLS = [
     "rvh_dfb_add_strings", "rvh_dfb_finish", "rvh_synth_df", "rvh_df_free", "rvh_df_width", "rvh_df_height", "rvh_df_col_name", "rvh_df_col_dtype",
     "rvh_df_col_len", "rvh_df_col_str_bytes", "rvh_df_col_export", "rvh_df_col_buffers",
     "rvh_expr_col", "rvh_expr_lit", "rvh_expr_binary", "rvh_expr_alias", "rvh_expr_free",
-    "rvh_lf_from_df", "rvh_lf_select", "rvh_lf_filter", "rvh_lf_limit", "rvh_lf_free", "rvh_lf_collect", "rvh_lf_collect_streaming",
+    "rvh_lf_from_df", "rvh_lf_from_csv", "rvh_set_csv_reference_validity", "rvh_csv_adaptive_batch_size", "rvh_sp_csv_source", "rvh_csv_parse_dump", "rvh_free", "rvh_lf_select", "rvh_lf_filter", "rvh_lf_limit", "rvh_lf_free", "rvh_lf_collect", "rvh_lf_collect_streaming",
     "rvh_lf_plan_shape", "rvh_lf_schema", "rvh_lf_validate", "rvh_lf_describe",
     "rvh_rb_try_new", "rvh_rb_free", "rvh_rb_num_rows", "rvh_rb_num_columns", "rvh_rb_col_name", "rvh_rb_col_dtype", "rvh_rb_col_export",
     "rvh_rb_slice", "rvh_rb_take", "rvh_rb_select", "rvh_rb_select_by_name", "rvh_rb_filter", "rvh_rb_concat", "rvh_rb_empty_like",
@@ -72,13 +72,13 @@ def lib():
                               f"(or `make -C rivulus_b200/host`).  rivulus_b200 has no CPU fallback.")
         L = C.CDLL(HOST_LIB_PATH)
         L.rvh_last_error.restype = C.c_char_p
-        for name in ("rvh_dfb_new", "rvh_expr_col", "rvh_expr_lit", "rvh_expr_binary", "rvh_expr_alias", "rvh_lf_from_df", "rvh_lf_select",
+        for name in ("rvh_dfb_new", "rvh_expr_col", "rvh_expr_lit", "rvh_expr_binary", "rvh_expr_alias", "rvh_lf_from_df", "rvh_lf_from_csv", "rvh_sp_csv_source", "rvh_lf_select",
                      "rvh_lf_filter", "rvh_lf_limit", "rvh_sp_memory_source", "rvh_sp_dataframe_source", "rvh_sp_filter", "rvh_sp_select",
                      "rvh_sp_limit", "rvh_rbv_get"):
             getattr(L, name).restype = C.c_void_p
         for name in ("rvh_df_col_name", "rvh_rb_col_name"):
             getattr(L, name).restype = C.c_char_p
-        for name in ("rvh_df_height", "rvh_df_col_len", "rvh_df_col_str_bytes", "rvh_rb_num_rows", "rvh_launch_count"):
+        for name in ("rvh_df_height", "rvh_df_col_len", "rvh_df_col_str_bytes", "rvh_rb_num_rows", "rvh_launch_count", "rvh_csv_adaptive_batch_size"):
             getattr(L, name).restype = C.c_int64
         _lib = L
     return _lib
@@ -121,6 +121,32 @@ def set_extensions(on: bool) -> None:
     """Opt-in extension (off = the reference's behaviour and error text): And / Or over comparison leaves in collect() and
     collect_streaming(), comparison predicates in collect_streaming() (rivulus.hpp: set_extensions)."""
     lib().rvh_set_extensions(1 if on else 0)
+
+
+def set_csv_reference_validity(on: bool) -> None:
+    """True = reproduce the reference's inverted validity of Int64 / Float64 CSV columns that hold a null (file_stream.rs:213-240);
+    default False = null fields are null."""
+    lib().rvh_set_csv_reference_validity(1 if on else 0)
+
+
+def calculate_adaptive_batch_size(exec_dtypes) -> int:
+    """file_stream.rs:346-369 over execution dtypes (EX_*)."""
+    a = (C.c_int * max(len(exec_dtypes), 1))(*exec_dtypes)
+    return int(lib().rvh_csv_adaptive_batch_size(len(exec_dtypes), a))
+
+
+def csv_parse_dump(path, exec_dtypes, batch_size=None, delimiter=None, reference_validity=False) -> str:
+    """CPU-only probe of the CSV parser (tests): every batch rendered as text, see rvh_csv_parse_dump in host_capi.cpp."""
+    a = (C.c_int * max(len(exec_dtypes), 1))(*exec_dtypes)
+    out = C.c_void_p()
+    rc = lib().rvh_csv_parse_dump(str(path).encode(), len(exec_dtypes), a, C.c_int64(-1 if batch_size is None else batch_size),
+                                  None if delimiter is None else delimiter.encode(), 1 if reference_validity else 0, C.byref(out))
+    if rc != 0:
+        raise RivulusError(lib().rvh_last_error().decode(errors="replace"))
+    try:
+        return C.string_at(out.value).decode()
+    finally:
+        lib().rvh_free(out)
 
 
 def any_tag(v):
@@ -333,6 +359,14 @@ class LazyFrame:
     def from_dataframe(df: DataFrame):
         return LazyFrame(lib().rvh_lf_from_df(_vp(df._h)))
 
+    @staticmethod
+    def from_csv(path, schema, batch_size=None, delimiter=None):
+        """builder.rs:41-55.  schema: [(name, DT_*)]; delimiter: one character."""
+        names = (C.c_char_p * max(len(schema), 1))(*[n.encode() for n, _ in schema])
+        dts = (C.c_int * max(len(schema), 1))(*[d for _, d in schema])
+        return LazyFrame(lib().rvh_lf_from_csv(str(path).encode(), len(schema), names, dts, C.c_int64(-1 if batch_size is None else batch_size),
+                                               None if delimiter is None else delimiter.encode()))
+
     def select(self, exprs: List[Expr]):
         arr = (C.c_void_p * max(len(exprs), 1))(*[e._h for e in exprs])
         return LazyFrame(lib().rvh_lf_select(_vp(self._h), len(exprs), arr))
@@ -517,6 +551,16 @@ class StreamingPhysicalPlan:
         if not h:
             raise RivulusError(lib().rvh_last_error().decode(errors="replace"))
         return StreamingPhysicalPlan(h)
+
+    @staticmethod
+    def csv_file_source(path, fields, batch_size=None, delimiter=None):
+        """streaming.rs:299-311.  fields: [(name, EX_*, nullable)]."""
+        names = (C.c_char_p * max(len(fields), 1))(*[f[0].encode() for f in fields])
+        dts = (C.c_int * max(len(fields), 1))(*[f[1] for f in fields])
+        nul = (C.c_int * max(len(fields), 1))(*[1 if f[2] else 0 for f in fields])
+        return StreamingPhysicalPlan(lib().rvh_sp_csv_source(str(path).encode(), len(fields), names, dts, nul,
+                                                             C.c_int64(-1 if batch_size is None else batch_size),
+                                                             None if delimiter is None else delimiter.encode()))
 
     def filter(self, column: str):
         return StreamingPhysicalPlan(lib().rvh_sp_filter(_vp(self._h), column.encode()))

@@ -2,6 +2,7 @@
 // pytest parity tests can drive LazyFrame / DataFrame / RecordBatch / StreamingPhysicalPlan.  Every query entry point
 // ends in librivulus_gpu.so kernels; this file only marshals arguments.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/rivulus_synth.h"
@@ -191,6 +192,61 @@ void* rvh_expr_alias(void* e, const char* name) { return new Expr(((Expr*)e)->al
 void rvh_expr_free(void* e) { delete (Expr*)e; }
 
 void* rvh_lf_from_df(void* df) { return new LazyFrame(LazyFrame::from_dataframe(*(DataFrame*)df)); }
+// LazyFrame::from_csv (builder.rs:41-55).  batch_size < 0 = None; delimiter NULL = None (one UTF-8 encoded char otherwise)
+void* rvh_lf_from_csv(const char* path, int nfields, const char** names, const int* dtypes, int64_t batch_size, const char* delimiter) {
+    std::vector<std::pair<std::string, DataType>> schema;
+    for (int i = 0; i < nfields; ++i) schema.emplace_back(names[i], (DataType)dtypes[i]);
+    return new LazyFrame(LazyFrame::from_csv(path, std::move(schema), batch_size < 0 ? std::nullopt : std::optional<size_t>((size_t)batch_size),
+                                             delimiter ? std::optional<std::string>(delimiter) : std::nullopt));
+}
+void rvh_set_csv_reference_validity(int on) { set_csv_reference_validity(on != 0); }
+int64_t rvh_csv_adaptive_batch_size(int nfields, const int* exec_dtypes) {
+    Schema s;
+    for (int i = 0; i < nfields; ++i) s.fields.push_back(Field{"c" + std::to_string(i), (ExecType)exec_dtypes[i], true});
+    return (int64_t)calculate_adaptive_batch_size(s);
+}
+// CPU-only probe of the CSV parser (no device involved): parses the whole file batch by batch and renders every batch as
+// "B <rows>\n" + one line per column of space-separated cells (i64 decimal, f64 as 16 hex digits of its bits, Boolean 0/1,
+// String as hex bytes prefixed with 's', NULL as 'N', a column without a validity bitmap gets a leading '!').
+// Returns 0 and the text in a malloc'ed buffer (*out, free with rvh_free), or 1 with rvh_last_error set.
+int rvh_csv_parse_dump(const char* path, int nfields, const int* exec_dtypes, int64_t batch_size, const char* delimiter, int reference_validity,
+                       char** out) {
+    return guard([&] {
+        auto schema = std::make_shared<Schema>();
+        for (int i = 0; i < nfields; ++i) schema->fields.push_back(Field{"c" + std::to_string(i), (ExecType)exec_dtypes[i], true});
+        CsvBatchReader rd(path, schema, batch_size < 0 ? std::nullopt : std::optional<size_t>((size_t)batch_size),
+                          delimiter ? std::optional<std::string>(delimiter) : std::nullopt);
+        std::string text;
+        char tmp[40];
+        while (size_t rows = rd.read_batch()) {
+            if (reference_validity) rd.apply_reference_validity();
+            text += "B " + std::to_string(rows) + "\n";
+            for (const rvl_column& c : rd.columns()) {
+                if (!c.validity) text += "! ";
+                for (size_t r = 0; r < rows; ++r) {
+                    const bool valid = c.dtype != RVL_NULL && (!c.validity || ((c.validity[r >> 3] >> (r & 7)) & 1));
+                    if (!valid) { text += "N "; continue; }
+                    switch (c.dtype) {
+                        case RVL_INT64: text += std::to_string(((const int64_t*)c.values)[r]) + " "; break;
+                        case RVL_FLOAT64: { uint64_t b; std::memcpy(&b, (const double*)c.values + r, 8); std::snprintf(tmp, sizeof tmp, "%016llx ", (unsigned long long)b); text += tmp; break; }
+                        case RVL_BOOLEAN: text += ((((const uint8_t*)c.values)[r >> 3] >> (r & 7)) & 1) ? "1 " : "0 "; break;
+                        case RVL_STRING: {
+                            text += "s";
+                            for (int32_t k = c.offsets[r]; k < c.offsets[r + 1]; ++k) { std::snprintf(tmp, sizeof tmp, "%02x", c.data[k]); text += tmp; }
+                            text += " ";
+                            break;
+                        }
+                        default: break;
+                    }
+                }
+                text += "\n";
+            }
+        }
+        *out = (char*)std::malloc(text.size() + 1);
+        std::memcpy(*out, text.c_str(), text.size() + 1);
+    });
+}
+void rvh_free(void* p) { std::free(p); }
 void* rvh_lf_select(void* lf, int n, void** exprs) {
     std::vector<Expr> e; for (int i = 0; i < n; ++i) e.push_back(*(Expr*)exprs[i]);
     return new LazyFrame(((LazyFrame*)lf)->select(std::move(e)));
@@ -299,6 +355,14 @@ void* rvh_sp_dataframe_source(void* df, int64_t batch_size) {
     void* out = nullptr;
     guard([&] { out = new StreamingPhysicalPlan(StreamingPhysicalPlan::dataframe_source(*(DataFrame*)df, (size_t)batch_size)); });
     return out;
+}
+// StreamingPhysicalPlan::csv_file_source (streaming.rs:299-311) with the execution schema given field by field
+void* rvh_sp_csv_source(const char* path, int nfields, const char** names, const int* exec_dtypes, const int* nullable, int64_t batch_size,
+                        const char* delimiter) {
+    auto schema = std::make_shared<Schema>();
+    for (int i = 0; i < nfields; ++i) schema->fields.push_back(Field{names[i], (ExecType)exec_dtypes[i], nullable[i] != 0});
+    return new StreamingPhysicalPlan(StreamingPhysicalPlan::csv_file_source(path, schema, batch_size < 0 ? std::nullopt : std::optional<size_t>((size_t)batch_size),
+                                                                            delimiter ? std::optional<std::string>(delimiter) : std::nullopt));
 }
 void* rvh_sp_filter(void* sp, const char* col) { return new StreamingPhysicalPlan(((StreamingPhysicalPlan*)sp)->filter(col)); }
 void* rvh_sp_select(void* sp, const char** names, int n) {

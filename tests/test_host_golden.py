@@ -61,6 +61,7 @@ def _load_golden_namespace():
         "__name__": "host_golden", "np": np, "pytest": pytest,
         "Array": _Array, "DataFrame": F.DataFrame, "LazyFrame": F.LazyFrame, "OracleError": F.RivulusError,
         "RecordBatch": _RecordBatch, "StreamingPhysicalPlan": F.StreamingPhysicalPlan, "col": F.col, "lit": F.lit, "set_extensions": F.set_extensions,
+        "set_csv_reference_validity": F.set_csv_reference_validity, "calculate_adaptive_batch_size": F.calculate_adaptive_batch_size,
         "EX_BOOLEAN": F.EX_BOOLEAN, "EX_FLOAT64": F.EX_FLOAT64, "EX_INT64": F.EX_INT64, "EX_NULL": F.EX_NULL, "EX_STRING": F.EX_STRING,
     }
     exec(compile(src, "test_oracle_golden.py[gpu host layer]", "exec"), ns)
@@ -70,7 +71,7 @@ def _load_golden_namespace():
 _NS = _load_golden_namespace()
 
 # host logic only (dtype inference, plan shapes, validation / lowering / planner rejections): no kernel is launched
-CPU_TESTS = ["test_logical_plan_schema_and_validate", "test_lazyframe_builder_structure", "test_series_dtype_inference", "test_dataframe_construction_rules", "test_readme_shape_fails_validation", "test_planner_rejections",
+CPU_TESTS = ["test_csv_adaptive_batch_size", "test_logical_plan_schema_and_validate", "test_lazyframe_builder_structure", "test_series_dtype_inference", "test_dataframe_construction_rules", "test_readme_shape_fails_validation", "test_planner_rejections",
              "test_streaming_planner_rejections", "test_collect_invalid_columns"]
 # everything below executes CUDA kernels through the C ABI
 GPU_TESTS = [
@@ -83,6 +84,8 @@ GPU_TESTS = [
     "test_filter_select_stream_operators", "test_streaming_planner_conversions", "test_streaming_alias_dropped_and_null_flattening",
     "test_streaming_batches_of_1024", "test_eager_nulls_dtype_collapse_and_empty_errors",
     "test_extension_compound_and_streaming_comparison_predicates",
+    "test_csv_file_stream_basic_and_nulls", "test_csv_empty_file", "test_csv_main_demo_query", "test_csv_parse_rules", "test_csv_errors",
+    "test_csv_filter_select_limit_and_validity_modes",
 ]
 
 
@@ -224,6 +227,131 @@ def test_random_streaming_queries_match_oracle(seed):
         want = _outcome(O, O.OracleError, build)
         got = _outcome(F, F.RivulusError, build)
         assert got == want, (seed, q, sel, lim, fcol, shape)
+
+
+def _random_csv_text(rng, n, bad_line=None):
+    """A CSV over {id: Int64, x: Float64, s: String, flag: Boolean} with nulls, padding, odd number spellings, blank lines, CRLF."""
+    def num_i():
+        v = int(rng.integers(-10 ** 6, 10 ** 6))
+        return str(rng.choice([str(v), "+" + str(abs(v)), "  %d " % v, "", "null"], p=[0.6, 0.05, 0.1, 0.15, 0.1]))
+
+    def num_f():
+        v = float(rng.normal()) * 10 ** int(rng.integers(-3, 6))
+        return str(rng.choice([repr(v), "%.3e" % v, "%d." % int(v), ".5", "inf", "-Infinity", "NaN", "1e400", "4.9e-324", "", "null", " 2.50 "],
+                              p=[0.4, 0.1, 0.05, 0.03, 0.03, 0.03, 0.03, 0.02, 0.02, 0.12, 0.07, 0.1]))
+
+    def text():
+        return str(rng.choice(["s%d" % rng.integers(0, 1000), "", "null", " pad ", "Zoë — ü", "NULL", "a b c", "x" * int(rng.integers(1, 200))],
+                              p=[0.5, 0.1, 0.1, 0.05, 0.05, 0.05, 0.05, 0.1]))
+
+    def flag():
+        return str(rng.choice(["true", "false", "T", "f", "1", "0", "True", "FALSE", "", "null"], p=[0.25, 0.25, 0.05, 0.05, 0.05, 0.05, 0.05, 0.05, 0.1, 0.1]))
+    lines = ["id,x,s,flag"]
+    for r in range(n):
+        if bad_line is not None and r == bad_line[0]:
+            lines.append(bad_line[1])
+        else:
+            lines.append(",".join([num_i(), num_f(), text(), flag()]))
+        if rng.random() < 0.03:
+            lines.append(str(rng.choice(["", "   ", "\t"])))
+    eol = str(rng.choice(["\n", "\r\n"]))
+    return eol.join(lines) + (eol if rng.random() < 0.7 else "")
+
+
+def _dump_oracle_batches(batches):
+    """The oracle's batches in the text form of rvh_csv_parse_dump."""
+    out = []
+    for b in batches:
+        out.append("B %d\n" % b.num_rows())
+        for c in b.columns():
+            cells = []
+            for v in c.to_list():
+                if v is None: cells.append("N")
+                elif c.dtype == F.EX_INT64: cells.append(str(v))
+                elif c.dtype == F.EX_FLOAT64: cells.append("%016x" % np.float64(v).view(np.uint64).item())
+                elif c.dtype == F.EX_BOOLEAN: cells.append("1" if v else "0")
+                else: cells.append("s" + v.encode().hex())
+            out.append(("! " if c.validity is None else "") + "".join(x + " " for x in cells) + "\n")
+    return "".join(out)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_csv_parser_matches_oracle_cpu(seed, tmp_path):
+    """Host logic, no GPU: the block-wise CSV parser (csv_stream.cpp) against the oracle's line-by-line restatement of
+    file_stream.rs — values bit for bit, validity-bitmap presence per batch, batch boundaries, error text and line numbers."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(700 + seed)
+    n = int(rng.choice([0, 1, 33, 400, 3000]))
+    bad = None
+    if n > 10 and seed % 2 == 1:
+        bad = (int(rng.integers(0, n)), str(rng.choice(["1,2.0,x", "abc,1.0,x,true", "1,1.0.0,x,true", "1,1.0,x,maybe", "1,2,3,4,5", "9223372036854775808,1,x,t"])))
+    p = tmp_path / "r.csv"
+    p.write_text(_random_csv_text(rng, n, bad), encoding="utf-8")
+    ex = [F.EX_INT64, F.EX_FLOAT64, F.EX_STRING, F.EX_BOOLEAN]
+    fields = [("c%d" % i, t, True) for i, t in enumerate(ex)]
+    for batch in (None, 1, 7, 256, 100000):
+        for quirk in (False, True):
+            O.set_csv_reference_validity(quirk)
+            try:
+                try:
+                    want = ("ok", _dump_oracle_batches(O.StreamingPhysicalPlan.csv_file_source(str(p), fields, batch).collect_batches()))
+                except O.OracleError as e:
+                    want = ("err", str(e).replace("Stream error: ", "", 1))
+            finally:
+                O.set_csv_reference_validity(False)
+            try:
+                got = ("ok", F.csv_parse_dump(p, ex, batch, None, quirk))
+            except F.RivulusError as e:
+                got = ("err", str(e))
+            assert got == want, (seed, batch, quirk, bad)
+    # a multi-byte delimiter and a file that ends inside a multi-megabyte line buffer refill
+    q = tmp_path / "wide.csv"
+    q.write_text("a§b\n" + "".join("%d§%s\n" % (i, "w" * (i % 5000)) for i in range(3000)), encoding="utf-8")
+    f2 = [("a", F.EX_INT64, True), ("b", F.EX_STRING, True)]
+    want = _dump_oracle_batches(O.StreamingPhysicalPlan.csv_file_source(str(q), f2, 1000, "§").collect_batches())
+    assert F.csv_parse_dump(q, [F.EX_INT64, F.EX_STRING], 1000, "§") == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(6))
+def test_random_csv_queries_match_oracle(seed, tmp_path):
+    """SURVEY.md 8(f) rank 3: LazyFrame::from_csv(..).[filter].[select].[limit].collect_streaming() — the host parser + device pipeline
+    against the oracle's line-by-line restatement of file_stream.rs, with and without pipeline fusion, across batch sizes, both
+    validity modes, and with bad lines placed before / after the point a LIMIT stops the reading."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(900 + seed)
+    n = int(rng.choice([0, 1, 50, 700, 5000]))
+    bad = None
+    if n > 10 and rng.random() < 0.5:
+        bad = (int(rng.integers(0, n)), str(rng.choice(["1,2.0,x", "abc,1.0,x,true", "1,1.0.0,x,true", "1,1.0,x,maybe", "1,2,3,4,5"])))
+    p = tmp_path / "r.csv"
+    p.write_text(_random_csv_text(rng, n, bad), encoding="utf-8")
+    schema = [("id", F.DT_INT64), ("x", F.DT_FLOAT64), ("s", F.DT_STRING), ("flag", F.DT_BOOLEAN)]
+    names = [c[0] for c in schema]
+    for q in range(10):
+        batch = [None, 1, 3, 64, 1000, 100000][int(rng.integers(0, 6))]
+        sel = [str(x) for x in rng.choice(names, size=int(rng.integers(1, 4)), replace=False)]
+        lim = int(rng.choice([0, 1, 40, 10 ** 6]))
+        shape = int(rng.integers(0, 5))
+        quirk = bool(rng.random() < 0.3)
+        fusion = bool(rng.random() < 0.7)
+
+        def build(mod, batch=batch, sel=sel, lim=lim, shape=shape):
+            lf = mod.LazyFrame.from_csv(str(p), schema, batch)
+            if shape == 0: lf = lf.filter(mod.col("flag"))
+            elif shape == 1: lf = lf.filter(mod.col("flag")).select([mod.col(c) for c in sel])
+            elif shape == 2: lf = lf.filter(mod.col("flag")).select([mod.col(c) for c in sel]).limit(lim)
+            elif shape == 3: lf = lf.select([mod.col(c) for c in sel]).limit(lim)
+            else: lf = lf.limit(lim)
+            return lf.collect_streaming()
+
+        O.set_csv_reference_validity(quirk); F.set_csv_reference_validity(quirk); F.set_stream_fusion(fusion)
+        try:
+            want = _outcome(O, O.OracleError, build)
+            got = _outcome(F, F.RivulusError, build)
+        finally:
+            O.set_csv_reference_validity(False); F.set_csv_reference_validity(False); F.set_stream_fusion(True)
+        assert got == want, (seed, q, n, bad, batch, sel, lim, shape, quirk, fusion)
 
 
 @pytest.mark.gpu

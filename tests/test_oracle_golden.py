@@ -11,6 +11,7 @@ import pytest
 
 from oracle import oracle as O
 from oracle.oracle import (Array, DataFrame, LazyFrame, OracleError, RecordBatch, StreamingPhysicalPlan, col, lit, set_extensions,
+                           set_csv_reference_validity, calculate_adaptive_batch_size,
                            EX_BOOLEAN, EX_FLOAT64, EX_INT64, EX_NULL, EX_STRING)
 
 
@@ -662,3 +663,174 @@ def test_lazyframe_builder_structure():
     base = lf.select([col("name")])
     _ = base.limit(1)
     assert base.describe() == 'Select { input: DataFrameSource, expressions: [Column("name")] }'
+
+
+# ---------------------------------------------------------------- execution/file_stream.rs
+DT_I, DT_F, DT_S, DT_B, DT_N = 0, 1, 2, 3, 4      # datatypes DataType order (series.rs:126-133)
+
+
+def _csv(tmp, text, name="t.csv", binary=False):
+    import os
+    p = os.path.join(str(tmp), name)
+    with open(p, "wb") as f:
+        f.write(text if binary else text.encode())
+    return p
+
+
+def _tmpdir():
+    import tempfile
+    return tempfile.mkdtemp(prefix="rvl_csv_")
+
+
+def csv_test_file(tmp):  # file_stream.rs:379-388
+    return _csv(tmp, "id,name,score,active\n1,Alice,85.5,true\n2,Bob,92.0,false\n3,Charlie,78.5,true\n4,,90.0,false\n5,Eve,null,true\n")
+
+
+CSV_TEST_FIELDS = [("id", EX_INT64, False), ("name", EX_STRING, True), ("score", EX_FLOAT64, True), ("active", EX_BOOLEAN, False)]  # :390-397
+
+
+def test_csv_file_stream_basic_and_nulls():  # file_stream.rs:399-416 (basic), :432-446 (nulls: the reference stops at num_rows)
+    tmp = _tmpdir()
+    sp = StreamingPhysicalPlan.csv_file_source(csv_test_file(tmp), CSV_TEST_FIELDS, 10)
+    batches = sp.collect_batches()
+    assert len(batches) == 1
+    b = batches[0]
+    assert (b.num_rows(), b.num_columns()) == (5, 4) and b.column_names() == ["id", "name", "score", "active"]
+    assert b.column(0).to_list() == [1, 2, 3, 4, 5] and b.column(0).null_count == 0
+    assert b.column(1).to_list() == ["Alice", "Bob", "Charlie", None, "Eve"]          # row 3: null name
+    assert b.column(3).to_list() == [True, False, True, False, True]
+    assert b.column(2).to_list() == [85.5, 92.0, 78.5, 90.0, None]                    # row 4: null score (corrected validity, the default)
+    # batch boundaries: 2 + 2 + 1 rows
+    sizes = [x.num_rows() for x in StreamingPhysicalPlan.csv_file_source(csv_test_file(tmp), CSV_TEST_FIELDS, 2).collect_batches()]
+    assert sizes == [2, 2, 1]
+
+
+def test_csv_adaptive_batch_size():  # file_stream.rs:418-430 (+ :346-369)
+    assert calculate_adaptive_batch_size([EX_INT64, EX_STRING, EX_FLOAT64, EX_BOOLEAN]) == 100_000   # 8 MiB / 49 B, clamped
+    assert calculate_adaptive_batch_size([]) == 10_000 and calculate_adaptive_batch_size([EX_NULL]) == 10_000
+    assert calculate_adaptive_batch_size([EX_STRING] * 300) == 1_000                   # 9600 B per row: 873 rows, clamped up
+    assert calculate_adaptive_batch_size([EX_FLOAT64] * 20) == 8 * 1024 * 1024 // 160  # 52 428, inside the clamp
+
+
+def test_csv_empty_file():  # file_stream.rs:448-461: header only => no batch
+    tmp = _tmpdir()
+    p = _csv(tmp, "id,name\n")
+    fields = [("id", EX_INT64, False), ("name", EX_STRING, True)]
+    assert StreamingPhysicalPlan.csv_file_source(p, fields, 10).collect_batches() == []
+    r = StreamingPhysicalPlan.csv_file_source(p, fields, 10).collect()
+    assert (r.num_rows(), r.column_names()) == (0, ["id", "name"])                     # RecordBatch::empty(schema), streaming.rs:347-349
+    assert StreamingPhysicalPlan.csv_file_source(_csv(tmp, "", "zero.csv"), fields, 10).collect_batches() == []   # :137-140
+
+
+def test_csv_main_demo_query():  # main.rs:233-256: from_csv(';').select(3 of 4).limit(3).collect_streaming()
+    tmp = _tmpdir()
+    p = _csv(tmp, "Username; Identifier;First name;Last name\nbooker12;9012;Rachel;Booker\ngrey07;2070;Laura;Grey\n"
+                  "johnson81;4081;Craig;Johnson\njenkins46;9346;Mary;Jenkins\nsmith79;5079;Jamie;Smith\n", "username.csv")
+    schema = [("Username", DT_S), ("Identifier", DT_I), ("First_name", DT_S), ("Last_name", DT_S)]
+    r = LazyFrame.from_csv(p, schema, 1000, ";").select([col("Username"), col("First_name"), col("Last_name")]).limit(3).collect_streaming()
+    assert r.column_names() == ["Username", "First_name", "Last_name"] and r.num_rows() == 3
+    assert r.column(0).to_list() == ["booker12", "grey07", "johnson81"] and r.column(2).to_list() == ["Booker", "Grey", "Johnson"]
+    lf = LazyFrame.from_csv(p, schema, 1000, ";")
+    assert lf.schema() == [("Username", "String"), ("Identifier", "Int64"), ("First_name", "String"), ("Last_name", "String")]   # plan.rs:66
+    lf.validate()                                                                                                            # plan.rs:128
+    with pytest.raises(OracleError, match="Logical plan error: Column not found: 'nope'"):
+        lf.select([col("nope")]).collect_streaming()
+    # planner.rs:45-49: the eager planner has no CSV source
+    with pytest.raises(OracleError, match="Execution error: Conversion failed: CSV file source not supported in non-streaming physical planner. "
+                                          "Use streaming planner instead."):
+        lf.select([col("Username")]).collect()
+    # streaming.rs:102-103: the file is opened when the plan executes
+    with pytest.raises(OracleError, match=r"Execution error: Invalid operation: Failed to open file: No such file or directory \(os error 2\)"):
+        LazyFrame.from_csv(p + ".missing", schema).limit(1).collect_streaming()
+
+
+def test_csv_parse_rules():  # file_stream.rs:42-121, :153-175 — code reading: Rust str::trim / parse::<i64> / parse::<f64> / to_lowercase
+    tmp = _tmpdir()
+    text = ("i,f,s,b\n"
+            " 7 , 1.5 ,  padded  , TRUE \n"            # fields are trimmed (:43)
+            "\n   \n"                                   # blank lines are skipped and do not count towards the batch (:168-170)
+            "-0,+.5e1,null,f\r\n"                       # CRLF (:162-167); '+', '.5', exponent; "null" string is NULL
+            "+9223372036854775807,-inf, x　,T\n"  # i64::MAX with '+'; -inf; Unicode white space trims (NBSP, ideographic space)
+            ",nan,,\n"                                  # empty = NULL for every type
+            "-9223372036854775808,1e400,Null,0\n"       # i64::MIN; overflow -> inf; "Null" (capital) is a string, not NULL
+            "12,1.,a b,1")                              # last line without newline; "1." is a float
+    p = _csv(tmp, text)
+    schema = [("i", DT_I), ("f", DT_F), ("s", DT_S), ("b", DT_B)]
+    r = LazyFrame.from_csv(p, schema, 3).collect_streaming()
+    assert r.num_rows() == 6
+    assert r.column(0).to_list() == [7, 0, 9223372036854775807, None, -9223372036854775808, 12]
+    f = r.column(1).to_list()
+    assert f[0] == 1.5 and f[1] == 5.0 and f[2] == -math.inf and math.isnan(f[3]) and f[4] == math.inf and f[5] == 1.0
+    assert r.column(2).to_list() == ["padded", None, "x", None, "Null", "a b"]
+    assert r.column(3).to_list() == [True, False, True, None, False, True]
+    assert [r.column(i).null_count for i in range(4)] == [1, 0, 2, 1]
+    # a header is always consumed, whatever it holds; a Null-typed column parses nothing (:111)
+    p2 = _csv(tmp, "1,2\n3,4\n", "nohdr.csv")
+    r2 = LazyFrame.from_csv(p2, [("a", DT_I), ("z", DT_N)]).collect_streaming()
+    assert r2.num_rows() == 1 and r2.column(0).to_list() == [3] and r2.column(1).to_list() == [None]
+
+
+def test_csv_errors():  # file_stream.rs:45-52, :63-69, :79-85, :100-105, :172-176 — message text and 1-based line numbers
+    tmp = _tmpdir()
+    schema = [("i", DT_I), ("f", DT_F), ("b", DT_B)]
+
+    def run(text, **kw):
+        return LazyFrame.from_csv(_csv(tmp, text, binary=isinstance(text, bytes)), schema, kw.get("batch", 2)).collect_streaming()
+    pre = "Execution error: Stream error: Stream execution error: Parse error: "
+    with pytest.raises(OracleError, match=pre + "Line 3: Expected 3 fields, found 2"):
+        run("i,f,b\n1,1.0,t\n2,2.0\n")
+    with pytest.raises(OracleError, match=pre + "Line 4, field 0: Cannot parse '1_000' as Int64"):
+        run("i,f,b\n1,1.0,t\n\n1_000,2.0,f\n")                      # the blank line counts as a line
+    for bad in ("9223372036854775808", "+-1", "-", "1.0", "0x10", "１２"):
+        with pytest.raises(OracleError, match="field 0: Cannot parse"):
+            run(f"i,f,b\n{bad},1.0,t\n")
+    for bad in ("1e", ".", "e5", "1.5f", "0x1p3", "in", "infinit", "1,5", "--1", "1 000"):
+        if "," in bad:
+            continue
+        with pytest.raises(OracleError, match="field 1: Cannot parse '" + bad.replace(".", r"\.") + "' as Float64"):
+            run(f"i,f,b\n1,{bad},t\n")
+    with pytest.raises(OracleError, match=pre + "Line 2, field 2: Cannot parse 'yes' as Boolean"):
+        run("i,f,b\n1,1.0,yes\n")
+    with pytest.raises(OracleError, match="Execution error: Stream error: Stream execution error: Failed to read line 3: stream did not contain valid UTF-8"):
+        run(b"i,f,b\n1,1.0,t\n2,\xff,f\n")
+    # LimitStream pulls nothing once the limit is met (streaming.rs:269-271): a bad line in a batch that is never read does not surface
+    ok = LazyFrame.from_csv(_csv(tmp, "i,f,b\n1,1.0,t\n2,2.0,f\n3,oops,t\n"), schema, 2).limit(2).collect_streaming()
+    assert ok.column(0).to_list() == [1, 2]
+    with pytest.raises(OracleError, match=pre + "Line 4, field 1: Cannot parse 'oops' as Float64"):
+        LazyFrame.from_csv(_csv(tmp, "i,f,b\n1,1.0,t\n2,2.0,f\n3,oops,t\n"), schema, 2).limit(3).collect_streaming()
+    with pytest.raises(OracleError, match=pre + "Line 4, field 1"):   # same file, one batch of 3: the bad line is in the first batch
+        LazyFrame.from_csv(_csv(tmp, "i,f,b\n1,1.0,t\n2,2.0,f\n3,oops,t\n"), schema, 3).limit(2).collect_streaming()
+
+
+def test_csv_filter_select_limit_and_validity_modes():
+    tmp = _tmpdir()
+    rows = [(i, None if i % 7 == 3 else i * 0.5, None if i % 5 == 0 else f"s{i}", None if i % 11 == 0 else (i % 3 == 0)) for i in range(1, 41)]
+    text = "id,x,s,flag\n" + "".join(f"{i},{'' if x is None else x},{'null' if s is None else s},{'' if b is None else ('true' if b else 'F')}\n"
+                                     for i, x, s, b in rows)
+    p = _csv(tmp, text)
+    schema = [("id", DT_I), ("x", DT_F), ("s", DT_S), ("flag", DT_B)]
+    for batch in (1, 7, 16, 1000, None):
+        r = LazyFrame.from_csv(p, schema, batch).filter(col("flag")).select([col("s"), col("x"), col("id")]).collect_streaming()
+        keep = [t for t in rows if t[3] is True]                                    # null mask rows are dropped (take of set bits)
+        assert r.column(2).to_list() == [t[0] for t in keep]
+        assert r.column(1).to_list() == [t[1] for t in keep] and r.column(0).to_list() == [t[2] for t in keep]
+        r = LazyFrame.from_csv(p, schema, batch).filter(col("flag")).select([col("id")]).limit(5).collect_streaming()
+        assert r.column(0).to_list() == [t[0] for t in keep][:5]
+        r = LazyFrame.from_csv(p, schema, batch).limit(9).collect_streaming()
+        assert r.column(0).to_list() == list(range(1, 10)) and r.column(3).to_list() == [t[3] for t in rows[:9]]
+    # the reference's inverted validity for Int64 / Float64 columns holding a null (file_stream.rs:233-239 vs primitive.rs:31-33)
+    set_csv_reference_validity(True)
+    try:
+        r = LazyFrame.from_csv(p, schema, 1000).collect_streaming()
+        assert r.column(1).to_list() == [0.0 if t[1] is None else None for t in rows]     # only the NULL fields come out valid (as 0.0)
+        assert r.column(0).to_list() == [t[0] for t in rows]                              # no null in the column: no bitmap, untouched
+        assert r.column(2).to_list() == [t[2] for t in rows] and r.column(3).to_list() == [t[3] for t in rows]   # String / Boolean are right
+        small = LazyFrame.from_csv(p, schema, 2).collect_streaming()                      # per batch: batches without a null stay valid
+        exp = []
+        for k in range(0, 40, 2):
+            pair = rows[k:k + 2]
+            anyn = any(t[1] is None for t in pair)
+            exp += [(0.0 if t[1] is None else None) if anyn else t[1] for t in pair]
+        assert small.column(1).to_list() == exp
+    finally:
+        set_csv_reference_validity(False)

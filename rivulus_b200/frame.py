@@ -42,7 +42,7 @@ HOST_SYMBOLS = [
     "rvh_dfb_add_strings", "rvh_dfb_finish", "rvh_synth_df", "rvh_df_free", "rvh_df_width", "rvh_df_height", "rvh_df_col_name", "rvh_df_col_dtype",
     "rvh_df_col_len", "rvh_df_col_str_bytes", "rvh_df_col_export", "rvh_df_col_buffers",
     "rvh_expr_col", "rvh_expr_lit", "rvh_expr_binary", "rvh_expr_alias", "rvh_expr_free",
-    "rvh_lf_from_df", "rvh_lf_from_csv", "rvh_set_csv_reference_validity", "rvh_csv_adaptive_batch_size", "rvh_sp_csv_source", "rvh_csv_parse_dump", "rvh_free", "rvh_lf_select", "rvh_lf_filter", "rvh_lf_limit", "rvh_lf_free", "rvh_lf_collect", "rvh_lf_collect_streaming",
+    "rvh_lf_from_df", "rvh_lf_from_csv", "rvh_set_csv_reference_validity", "rvh_set_csv_threads", "rvh_csv_adaptive_batch_size", "rvh_sp_csv_source", "rvh_csv_parse_dump", "rvh_free", "rvh_lf_select", "rvh_lf_filter", "rvh_lf_limit", "rvh_lf_free", "rvh_lf_collect", "rvh_lf_collect_streaming",
     "rvh_lf_plan_shape", "rvh_lf_schema", "rvh_lf_validate", "rvh_lf_describe",
     "rvh_rb_try_new", "rvh_rb_free", "rvh_rb_num_rows", "rvh_rb_num_columns", "rvh_rb_col_name", "rvh_rb_col_dtype", "rvh_rb_col_export",
     "rvh_rb_slice", "rvh_rb_take", "rvh_rb_select", "rvh_rb_select_by_name", "rvh_rb_filter", "rvh_rb_concat", "rvh_rb_empty_like",
@@ -127,6 +127,11 @@ def set_csv_reference_validity(on: bool) -> None:
     """True = reproduce the reference's inverted validity of Int64 / Float64 CSV columns that hold a null (file_stream.rs:213-240);
     default False = null fields are null."""
     lib().rvh_set_csv_reference_validity(1 if on else 0)
+
+
+def set_csv_threads(n: int) -> None:
+    """Parse threads per CSV reader: -1 (default) = up to 8 for files of at least 8 MiB, none below; 0 = the calling thread parses."""
+    lib().rvh_set_csv_threads(int(n))
 
 
 def calculate_adaptive_batch_size(exec_dtypes) -> int:

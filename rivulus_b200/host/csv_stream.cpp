@@ -3,7 +3,11 @@
 // The reference reads one line at a time into a String, splits it into a Vec<&str>, parses every field into a ParsedValue enum,
 // pushes those into per-column Vecs and finally rebuilds typed arrays from them.  Here the file is read in 4 MiB blocks and every
 // field is parsed straight into the column's Arrow buffers (8-byte values, LSB-first bitmaps, int32 offsets + bytes), which are
-// reused from batch to batch and handed to RecordBatch::try_new / rvl_stream_push as they are.  Same observable behaviour:
+// reused from batch to batch and handed to RecordBatch::try_new / rvl_stream_push as they are.  Two stages: the caller's thread
+// cuts the file into batches of `batch_size` data lines (memchr for the newlines, blank lines dropped, line numbers kept) and
+// stays a few batches ahead; worker threads parse whole batches concurrently; batches — and errors — come out in file order, so
+// a consumer that stops early (LIMIT) never sees an error from a batch the reference would not have read.  Files under 8 MiB
+// are parsed by the caller itself.  Same observable behaviour:
 // header line always skipped (:134-151), blank lines skipped and not counted (:168-170), fields trimmed (:43), "" / "null" = NULL,
 // Rust's i64 / f64 / bool text rules (:60-110), the same error text with the same 1-based line numbers, batches of `batch_size`
 // data lines (default: 8 MiB worth of estimated row bytes, clamped to 1 000..100 000, :346-369).
@@ -12,6 +16,7 @@
 // expects a validity vector (:233-239, :265-271 vs primitive.rs:31-33), so a column holding a null comes out inverted.  Default
 // here is the evident intent (null fields are null); set_csv_reference_validity(true) reproduces the reference bit for bit.
 #include <fcntl.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include <cerrno>
@@ -19,6 +24,10 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 
 #include "rivulus.hpp"
 
@@ -167,18 +176,44 @@ struct ColumnBuf {  // one column of the batch being parsed, Arrow layout, reuse
 };
 }  // namespace
 
+// One batch on its way through the reader: the text of its data lines (stage 1, the caller's thread) and the parsed columns
+// (stage 2, a worker thread or the caller itself).
+struct CsvJob {
+    std::vector<char> text;            // the batch's non-blank lines, terminators stripped, back to back
+    std::vector<uint32_t> starts;      // start of every line in `text` + one end sentinel
+    std::vector<uint64_t> line_no;     // 1-based number of every line in the file (header = 1, blank lines count)
+    std::string read_error;            // set when reading the file failed after these lines: surfaces instead of the batch
+    std::vector<ColumnBuf> cols;
+    size_t rows = 0;
+    std::string parse_error;           // first bad line in file order
+    bool done = false;
+};
+
 struct CsvBatchReader::Impl {
     int fd = -1;
     SchemaRef schema;
     size_t batch_size = 0, current_line = 0;
-    bool finished = false, eof = false;
+    bool finished = false, eof = false, failed = false;
     std::string delim = ",";
     std::vector<char> buf; size_t pos = 0, end = 0;   // unread bytes are buf[pos, end)
-    std::vector<ColumnBuf> cols;
-    size_t rows = 0;
-    ~Impl() { if (fd >= 0) ::close(fd); }
+    // pipeline
+    std::vector<std::thread> workers;
+    std::mutex mu; std::condition_variable work_cv, done_cv;
+    std::deque<CsvJob*> todo;                         // jobs waiting for a worker
+    std::deque<std::unique_ptr<CsvJob>> order;        // jobs in file order, head = next batch the caller gets
+    std::vector<std::unique_ptr<CsvJob>> spare;       // finished jobs whose buffers are reused
+    std::unique_ptr<CsvJob> current;                  // the batch last returned by read_batch
+    bool stop = false;
+    size_t depth = 1;
 
-    // the next line including its '\n' (BufRead::read_line); false at end of file
+    ~Impl() {
+        { std::lock_guard<std::mutex> g(mu); stop = true; }
+        work_cv.notify_all();
+        for (auto& t : workers) t.join();
+        if (fd >= 0) ::close(fd);
+    }
+
+    // the next line including its '\n' (BufRead::read_line); false at end of file; throws std::string on an I/O error
     bool next_line(const char** p, size_t* n) {
         for (;;) {
             if (pos < end) {
@@ -196,59 +231,132 @@ struct CsvBatchReader::Impl {
             if (got < 0) {
                 if (errno == EINTR) continue;
                 const int e = errno;
-                throw Error(std::string("Stream execution error: Failed to read line ") + std::to_string(current_line + 1) + ": " + std::strerror(e) +
-                            " (os error " + std::to_string(e) + ")");
+                throw std::string(std::strerror(e)) + " (os error " + std::to_string(e) + ")";
             }
             if (got == 0) eof = true; else end += (size_t)got;
         }
     }
 
-    void parse_line(sv line) {  // :42-121, writing row `rows` of every column
-        const size_t nf = cols.size();
-        const size_t r = rows;
-        size_t field = 0, start = 0;
-        // count first: the field-count check precedes any parsing (:45-52)
+    // `line.trim().is_empty()` (:168) decided on raw bytes; a line that is not valid UTF-8 is never blank (stage 2 reports it)
+    static bool is_blank(const char* p, size_t n) {
+        for (size_t i = 0; i < n; ++i) {
+            const unsigned char c = (unsigned char)p[i];
+            if (c < 0x80) { if (!is_ws(c)) return false; continue; }
+            return valid_utf8(p, n) && trim(sv(p, n)).empty();
+        }
+        return true;
+    }
+
+    // stage 1: the text of the next `batch_size` data lines.  False when the file is exhausted and the job holds nothing.
+    bool fill(CsvJob& j) {
+        j.text.clear(); j.starts.clear(); j.line_no.clear(); j.read_error.clear(); j.parse_error.clear(); j.rows = 0; j.done = false;
+        if (finished) return false;
+        const char* p; size_t n;
+        try {
+            while (j.line_no.size() < batch_size) {
+                if (!next_line(&p, &n)) { finished = true; break; }
+                ++current_line;
+                if (n > 0 && p[n - 1] == '\n') { --n; if (n > 0 && p[n - 1] == '\r') --n; }
+                if (is_blank(p, n)) continue;
+                j.starts.push_back((uint32_t)j.text.size());
+                j.line_no.push_back(current_line);
+                j.text.insert(j.text.end(), p, p + n);
+                if (j.text.size() > (size_t)UINT32_MAX - (64u << 20)) break;   // 4 GiB of text in one batch: close it here
+            }
+        } catch (const std::string& io) {
+            j.read_error = "Stream execution error: Failed to read line " + std::to_string(current_line + 1) + ": " + io;
+            finished = true;
+        }
+        j.starts.push_back((uint32_t)j.text.size());
+        return !j.line_no.empty() || !j.read_error.empty();
+    }
+
+    // stage 2: every line of the job into the job's columns; stops at the first bad line
+    void parse(CsvJob& j) const {
+        const size_t nf = schema->fields.size();
+        if (j.cols.size() != nf) { j.cols.assign(nf, ColumnBuf()); for (size_t i = 0; i < nf; ++i) j.cols[i].type = schema->fields[i].data_type; }
+        const size_t nlines = j.line_no.size();
+        for (auto& c : j.cols) c.begin(nlines);
+        for (size_t r = 0; r < nlines; ++r) {
+            const char* p = j.text.data() + j.starts[r];
+            const size_t n = j.starts[r + 1] - j.starts[r];
+            if (!valid_utf8(p, n)) {   // read_line fails before the line is counted: "line {current_line + 1}" is this line's number
+                j.parse_error = "Stream execution error: Failed to read line " + std::to_string(j.line_no[r]) + ": stream did not contain valid UTF-8";
+                return;
+            }
+            if (!parse_line(j, r, sv(p, n))) return;
+            j.rows = r + 1;
+        }
+    }
+
+    bool parse_line(CsvJob& j, size_t r, sv line) const {  // :42-121, writing row r of every column
+        const size_t nf = j.cols.size();
+        size_t start = 0;
+        // the field-count check precedes any parsing (:45-52)
         size_t count = 1;
         if (delim.size() == 1) { for (const char c : line) count += c == delim[0]; }
         else for (size_t q = line.find(delim); q != sv::npos; q = line.find(delim, q + delim.size())) ++count;
-        if (count != nf)
-            throw Error("Stream execution error: Parse error: Line " + std::to_string(current_line) + ": Expected " + std::to_string(nf) + " fields, found " +
-                        std::to_string(count));
-        for (; field < nf; ++field) {
+        if (count != nf) {
+            j.parse_error = "Stream execution error: Parse error: Line " + std::to_string(j.line_no[r]) + ": Expected " + std::to_string(nf) + " fields, found " +
+                            std::to_string(count);
+            return false;
+        }
+        for (size_t field = 0; field < nf; ++field) {
             size_t q = delim.size() == 1 ? line.find(delim[0], start) : line.find(delim, start);
             if (q == sv::npos) q = line.size();
             const sv s = trim(line.substr(start, q - start));
             start = q + delim.size();
-            ColumnBuf& c = cols[field];
+            ColumnBuf& c = j.cols[field];
             const bool null = s.empty() || s == "null";
-            auto bad = [&](const char* ty) {
-                return Error("Stream execution error: Parse error: Line " + std::to_string(current_line) + ", field " + std::to_string(field) + ": Cannot parse '" +
-                             std::string(s) + "' as " + ty);
-            };
+            const char* bad = nullptr;
             bool valid = !null;
             switch (c.type) {
                 case ExecType::Int64:
-                    if (null) c.i64[r] = 0; else if (!parse_i64(s, &c.i64[r])) throw bad("Int64");
+                    if (null) c.i64[r] = 0; else if (!parse_i64(s, &c.i64[r])) bad = "Int64";
                     break;
                 case ExecType::Float64:
-                    if (null) c.f64[r] = 0.0; else if (!parse_f64(s, &c.f64[r])) throw bad("Float64");
+                    if (null) c.f64[r] = 0.0; else if (!parse_f64(s, &c.f64[r])) bad = "Float64";
                     break;
                 case ExecType::String:
                     if (!null) {
-                        if (c.data.size() + s.size() > (size_t)INT32_MAX) throw Error("Stream execution error: string column exceeds the 2 GiB offset range in one batch");
+                        if (c.data.size() + s.size() > (size_t)INT32_MAX) { j.parse_error = "Stream execution error: string column exceeds the 2 GiB offset range in one batch"; return false; }
                         c.data.insert(c.data.end(), s.begin(), s.end());
                     }
                     c.offsets[r + 1] = (int32_t)c.data.size();
                     break;
                 case ExecType::Boolean:
-                    if (!null) { const int b = parse_bool(s); if (b < 0) throw bad("Boolean"); if (b) c.bits[r >> 3] |= (uint8_t)(1u << (r & 7)); }
+                    if (!null) { const int b = parse_bool(s); if (b < 0) bad = "Boolean"; else if (b) c.bits[r >> 3] |= (uint8_t)(1u << (r & 7)); }
                     break;
                 case ExecType::Null: valid = false; break;
             }
+            if (bad) {
+                j.parse_error = "Stream execution error: Parse error: Line " + std::to_string(j.line_no[r]) + ", field " + std::to_string(field) + ": Cannot parse '" +
+                                std::string(s) + "' as " + bad;
+                return false;
+            }
             if (valid) c.validity[r >> 3] |= (uint8_t)(1u << (r & 7)); else c.any_null = true;
+        }
+        return true;
+    }
+
+    void worker_loop() {
+        for (;;) {
+            CsvJob* j = nullptr;
+            {
+                std::unique_lock<std::mutex> g(mu);
+                work_cv.wait(g, [&] { return stop || !todo.empty(); });
+                if (stop) return;
+                j = todo.front(); todo.pop_front();
+            }
+            if (j->read_error.empty()) parse(*j);
+            { std::lock_guard<std::mutex> g(mu); j->done = true; }
+            done_cv.notify_all();
         }
     }
 };
+
+static int g_csv_threads = -1;
+void set_csv_threads(int n) { g_csv_threads = n; }
 
 CsvBatchReader::CsvBatchReader(const std::string& path, SchemaRef schema, std::optional<size_t> batch_size, std::optional<std::string> delimiter)
     : impl_(std::make_unique<Impl>()) {  // CsvFileStream::new :20-40
@@ -261,8 +369,15 @@ CsvBatchReader::CsvBatchReader(const std::string& path, SchemaRef schema, std::o
     impl_->batch_size = batch_size ? *batch_size : calculate_adaptive_batch_size(*impl_->schema);
     if (delimiter && !delimiter->empty()) impl_->delim = *delimiter;
     impl_->buf.resize(4u << 20);
-    impl_->cols.resize(impl_->schema->fields.size());
-    for (size_t i = 0; i < impl_->cols.size(); ++i) impl_->cols[i].type = impl_->schema->fields[i].data_type;
+    // parse workers: only for files worth it (several batches of text); small files are parsed by the caller
+    struct stat st;
+    const bool big = ::fstat(impl_->fd, &st) == 0 && (!S_ISREG(st.st_mode) || st.st_size >= (8 << 20));
+    int threads = g_csv_threads;
+    if (threads < 0) threads = big ? (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 4)) : 0;
+    if (threads > 0 && impl_->batch_size > 0) {
+        impl_->depth = (size_t)threads * 2;
+        for (int i = 0; i < threads; ++i) impl_->workers.emplace_back([m = impl_.get()] { m->worker_loop(); });
+    }
 }
 CsvBatchReader::~CsvBatchReader() = default;
 const SchemaRef& CsvBatchReader::schema() const { return impl_->schema; }
@@ -270,31 +385,45 @@ size_t CsvBatchReader::batch_size() const { return impl_->batch_size; }
 
 size_t CsvBatchReader::read_batch() {  // read_batch :123-199
     Impl& m = *impl_;
-    m.rows = 0;
-    if (m.finished) return 0;
-    const char* p; size_t n;
-    if (m.current_line == 0) {  // the first line is the header, whatever it holds
-        if (!m.next_line(&p, &n)) { m.finished = true; return 0; }
-        if (!valid_utf8(p, n)) throw Error("Stream execution error: Failed to read header: stream did not contain valid UTF-8");
+    if (m.current) { m.spare.push_back(std::move(m.current)); }
+    if (m.failed) return 0;
+    if (m.current_line == 0 && !m.finished) {  // the first line is the header, whatever it holds (:134-151)
+        const char* p; size_t n;
+        bool got = false;
+        try { got = m.next_line(&p, &n); }
+        catch (const std::string& io) { m.failed = true; throw Error("Stream execution error: Failed to read header: " + io); }
+        if (!got) { m.finished = true; return 0; }
+        if (!valid_utf8(p, n)) { m.failed = true; throw Error("Stream execution error: Failed to read header: stream did not contain valid UTF-8"); }
         ++m.current_line;
     }
-    for (auto& c : m.cols) c.begin(m.batch_size);
-    while (m.rows < m.batch_size) {
-        if (!m.next_line(&p, &n)) { m.finished = true; break; }
-        if (!valid_utf8(p, n))
-            throw Error("Stream execution error: Failed to read line " + std::to_string(m.current_line + 1) + ": stream did not contain valid UTF-8");
-        ++m.current_line;
-        if (n > 0 && p[n - 1] == '\n') { --n; if (n > 0 && p[n - 1] == '\r') --n; }
-        const sv line(p, n);
-        if (trim(line).empty()) continue;
-        m.parse_line(line);
-        ++m.rows;
+    // keep `depth` batches of text in the pipeline (stage 1 runs here, ahead of the workers)
+    while (m.order.size() < m.depth && !m.finished) {
+        std::unique_ptr<CsvJob> j;
+        if (!m.spare.empty()) { j = std::move(m.spare.back()); m.spare.pop_back(); } else j = std::make_unique<CsvJob>();
+        if (!m.fill(*j)) { m.spare.push_back(std::move(j)); break; }
+        CsvJob* raw = j.get();
+        m.order.push_back(std::move(j));
+        if (!m.workers.empty()) {
+            { std::lock_guard<std::mutex> g(m.mu); m.todo.push_back(raw); }
+            m.work_cv.notify_one();
+        }
     }
-    return m.rows;
+    if (m.order.empty()) return 0;
+    std::unique_ptr<CsvJob> j = std::move(m.order.front());
+    m.order.pop_front();
+    if (m.workers.empty()) { if (j->read_error.empty()) m.parse(*j); }
+    else { std::unique_lock<std::mutex> g(m.mu); m.done_cv.wait(g, [&] { return j->done; }); }
+    // errors surface in file order: a bad line first (it precedes the failed read), then the read error
+    if (!j->parse_error.empty()) { m.failed = true; const std::string e = j->parse_error; m.spare.push_back(std::move(j)); throw Error(e); }
+    if (!j->read_error.empty()) { m.failed = true; const std::string e = j->read_error; m.spare.push_back(std::move(j)); throw Error(e); }
+    m.current = std::move(j);
+    return m.current->rows;
 }
 
 std::vector<rvl_column> CsvBatchReader::columns() const {  // build_record_batch :201-326, as host views of the parsed buffers
-    const Impl& m = *impl_;
+    const Impl& im = *impl_;
+    if (!im.current) return {};
+    const CsvJob& m = *im.current;
     std::vector<rvl_column> out(m.cols.size());
     for (size_t i = 0; i < m.cols.size(); ++i) {
         const ColumnBuf& c = m.cols[i];
@@ -316,7 +445,8 @@ std::vector<rvl_column> CsvBatchReader::columns() const {  // build_record_batch
 
 void CsvBatchReader::apply_reference_validity() {
     // PrimitiveArray::new(values, Some(nulls)) with nulls[i] = true for a NULL field: valid exactly where the field was null
-    Impl& m = *impl_;
+    if (!impl_->current) return;
+    CsvJob& m = *impl_->current;
     for (auto& c : m.cols) {
         if (!c.any_null || (c.type != ExecType::Int64 && c.type != ExecType::Float64)) continue;
         const size_t nb = (m.rows + 7) / 8;

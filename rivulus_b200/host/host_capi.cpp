@@ -200,6 +200,7 @@ void* rvh_lf_from_csv(const char* path, int nfields, const char** names, const i
                                              delimiter ? std::optional<std::string>(delimiter) : std::nullopt));
 }
 void rvh_set_csv_reference_validity(int on) { set_csv_reference_validity(on != 0); }
+void rvh_set_csv_threads(int n) { set_csv_threads(n); }
 int64_t rvh_csv_adaptive_batch_size(int nfields, const int* exec_dtypes) {
     Schema s;
     for (int i = 0; i < nfields; ++i) s.fields.push_back(Field{"c" + std::to_string(i), (ExecType)exec_dtypes[i], true});

@@ -27,7 +27,7 @@ if args.affinity:
         words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
         cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1 and 64 * i + b < ncpu]
         cpusets[g] = cpus or None
-start = time.time() + 12.0 + 1.5 * args.gpus    # pinning 4 GiB per process takes a few seconds
+start = time.time() + 6.0 + 1.0 * args.gpus    # pinning 4 GiB per process takes a few seconds
 procs = []
 for g in range(args.gpus):
     def pre(cpus=cpusets[g]):

@@ -275,11 +275,13 @@ def _dump_oracle_batches(batches):
     return "".join(out)
 
 
+@pytest.mark.parametrize("threads", [0, 3])
 @pytest.mark.parametrize("seed", range(8))
-def test_csv_parser_matches_oracle_cpu(seed, tmp_path):
+def test_csv_parser_matches_oracle_cpu(seed, threads, tmp_path):
     """Host logic, no GPU: the block-wise CSV parser (csv_stream.cpp) against the oracle's line-by-line restatement of
     file_stream.rs — values bit for bit, validity-bitmap presence per batch, batch boundaries, error text and line numbers."""
     from oracle import oracle as O
+    F.set_csv_threads(threads)      # 0: the caller parses; 3: three parse workers even for these small files
     rng = np.random.default_rng(700 + seed)
     n = int(rng.choice([0, 1, 33, 400, 3000]))
     bad = None
@@ -310,6 +312,7 @@ def test_csv_parser_matches_oracle_cpu(seed, tmp_path):
     f2 = [("a", F.EX_INT64, True), ("b", F.EX_STRING, True)]
     want = _dump_oracle_batches(O.StreamingPhysicalPlan.csv_file_source(str(q), f2, 1000, "§").collect_batches())
     assert F.csv_parse_dump(q, [F.EX_INT64, F.EX_STRING], 1000, "§") == want
+    F.set_csv_threads(-1)
 
 
 @pytest.mark.gpu

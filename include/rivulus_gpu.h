@@ -139,7 +139,7 @@ typedef enum rvl_option {
     RVL_OPT_SPARSE_MAX = 2,         /* two-pass: 2048-row tiles with <= this many survivors are gathered (0..640) */
     RVL_OPT_DENSE_SLOTS = 3,        /* two-pass: 16 KB ring slots per CTA of the dense kernel (2..14) */
     RVL_OPT_DENSE_CTAS_PER_SM = 4,  /* 1 or 2 */
-    RVL_OPT_SCAN_SLOTS = 5,         /* two-pass: ring slots per warp of the predicate scan (1..3) */
+    RVL_OPT_SCAN_SLOTS = 5,         /* two-pass: ring slots per warp of the predicate scan (1..16, capped by what fits in shared memory) */
     RVL_OPT_SCAN_WARPS = 6,         /* two-pass: warps per CTA of the predicate scan (8 or 16) */
     RVL_OPT_DENSE_WARPS = 7,        /* two-pass: consumer warps per CTA of the dense kernel (8 or 16; 16 implies one CTA per SM) */
     RVL_OPT_BITS_OVERLAP = 8,       /* two-pass: run the bit-packed compaction kernel on a forked stream under the 8-byte kernels (default 1) */
@@ -155,7 +155,9 @@ typedef enum rvl_option {
                                        that reads that column from HBM once instead of twice.  0 = never, 2 = always, 1 (default) = when
                                        at least ~30 % of the rows survive — estimated from a 64 K-row sample in blocking calls, taken from
                                        the previous batch in streams (below that the two-pass plan is faster) */
-    RVL_OPT__COUNT = 13
+    RVL_OPT_SCAN_ITEM_ROWS = 13,    /* two-pass: rows per ring slot of the predicate scan: 0 = 8192 / warps (default), 512 or 256 with 8 warps,
+                                       256 with 16 warps */
+    RVL_OPT__COUNT = 14
 } rvl_option;
 int32_t rvl_ctx_set_option(rvl_ctx* ctx, int32_t option, int64_t value);
 

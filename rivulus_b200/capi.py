@@ -62,7 +62,7 @@ class RvlGatherHandle(C.Structure):
 
 PLAN_AUTO, PLAN_FUSED, PLAN_TWO_PASS = 0, 1, 2
 OPT_PLAN, OPT_TWO_PASS_MIN_ROWS, OPT_SPARSE_MAX, OPT_DENSE_SLOTS, OPT_DENSE_CTAS_PER_SM, OPT_SCAN_SLOTS, OPT_SCAN_WARPS, OPT_DENSE_WARPS, \
-    OPT_BITS_OVERLAP, OPT_EXACT_ALLOC, OPT_STRING_KERNEL, OPT_STRING_DENSE_MIN, OPT_CHUNK_PLAN = range(13)
+    OPT_BITS_OVERLAP, OPT_EXACT_ALLOC, OPT_STRING_KERNEL, OPT_STRING_DENSE_MIN, OPT_CHUNK_PLAN, OPT_SCAN_ITEM_ROWS = range(14)
 
 
 class RivulusError(RuntimeError):

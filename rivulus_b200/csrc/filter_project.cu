@@ -172,26 +172,35 @@ static void launch_fused(const CoreRef& core, int kind, const FusedParams& fp) {
 }
 
 // first pass of the two-pass plan (scan_kernels.cuh)
-template <int PRED, int W>
+template <int PRED, int W, int R>
 static int launch_scan_t(const CoreRef& core, const ScanParams& sp, int ctas) {
-    const size_t smem = (size_t)W * sp.n_slots * (ScanShape<W>::kItemBytes + 8);
-    predicate_scan_kernel<PRED, W><<<(unsigned)ctas, W * 32, smem, core->stream>>>(sp);
+    const size_t smem = (size_t)W * sp.n_slots * (ScanShape<W, R>::kItemBytes + 8);
+    predicate_scan_kernel<PRED, W, R><<<(unsigned)ctas, W * 32, smem, core->stream>>>(sp);
     core->launches++;
     RVL_CUDA_TRY(cudaGetLastError());
     return RVL_OK;
 }
-template <int W>
+template <int W, int R>
 static int launch_scan_w(const CoreRef& core, int kind, const ScanParams& sp, int ctas) {
     switch (kind) {
-        case kPredI64: return launch_scan_t<kPredI64, W>(core, sp, ctas);
-        case kPredF64: return launch_scan_t<kPredF64, W>(core, sp, ctas);
-        case kPredBits: return launch_scan_t<kPredBits, W>(core, sp, ctas);
-        default: return launch_scan_t<kPredTrue, W>(core, sp, ctas);
+        case kPredI64: return launch_scan_t<kPredI64, W, R>(core, sp, ctas);
+        case kPredF64: return launch_scan_t<kPredF64, W, R>(core, sp, ctas);
+        case kPredBits: return launch_scan_t<kPredBits, W, R>(core, sp, ctas);
+        default: return launch_scan_t<kPredTrue, W, R>(core, sp, ctas);
     }
 }
-static int launch_scan(const CoreRef& core, int kind, const ScanParams& sp, int ctas, int warps) {
-    if (warps == 32) return launch_scan_w<32>(core, kind, sp, ctas);
-    return warps == 16 ? launch_scan_w<16>(core, kind, sp, ctas) : launch_scan_w<8>(core, kind, sp, ctas);
+// (warps, rows per ring slot): the default shapes hold 64 KB per ring depth; the small-slot shapes of 8 warps are the ones the
+// round-2 sweep (profiles/r02_scan_sweep.txt) found fastest
+static int scan_slot_cap(int warps, int item_rows) {   // deepest ring that fits in shared memory
+    const int rows = item_rows > 0 ? item_rows : 8192 / warps;
+    return std::max(1, std::min(16, (int)((220u * 1024u) / ((size_t)warps * ((size_t)rows * 8 + 8)))));
+}
+static int launch_scan(const CoreRef& core, int kind, const ScanParams& sp, int ctas, int warps, int item_rows) {
+    if (warps == 32) return launch_scan_w<32, 0>(core, kind, sp, ctas);
+    if (warps == 16) return item_rows == 256 ? launch_scan_w<16, 256>(core, kind, sp, ctas) : launch_scan_w<16, 0>(core, kind, sp, ctas);
+    if (item_rows == 512) return launch_scan_w<8, 512>(core, kind, sp, ctas);
+    if (item_rows == 256) return launch_scan_w<8, 256>(core, kind, sp, ctas);
+    return launch_scan_w<8, 0>(core, kind, sp, ctas);
 }
 
 // second pass of the two-pass plan (compact_kernels.cuh): dense tiles through the TMA ring, sparse tiles gathered
@@ -210,11 +219,20 @@ static int launch_dense_t(const CoreRef& core, const CompactParams& cp, int per_
 // Every kernel instantiation that needs more than 48 KB of dynamic shared memory is opted in once per device, when the
 // context is created (the attribute is per device and per function; doing it lazily from the launch path raced when
 // two contexts were driven from different host threads).
+template <int PRED, int W, int R>
+static int scan_opt_in_shape() {
+    RVL_CUDA_TRY(cudaFuncSetAttribute(predicate_scan_kernel<PRED, W, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      W * scan_slot_cap(W, R) * (int)(ScanShape<W, R>::kItemBytes + 8)));
+    return RVL_OK;
+}
 template <int PRED>
 static int scan_opt_in() {
-    RVL_CUDA_TRY(cudaFuncSetAttribute(predicate_scan_kernel<PRED, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * (int)(ScanShape<8>::kItemBytes + 8)));
-    RVL_CUDA_TRY(cudaFuncSetAttribute(predicate_scan_kernel<PRED, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 3 * (int)(ScanShape<16>::kItemBytes + 8)));
-    RVL_CUDA_TRY(cudaFuncSetAttribute(predicate_scan_kernel<PRED, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 3 * (int)(ScanShape<32>::kItemBytes + 8)));
+    RVL_TRY((scan_opt_in_shape<PRED, 8, 0>()));
+    RVL_TRY((scan_opt_in_shape<PRED, 8, 512>()));
+    RVL_TRY((scan_opt_in_shape<PRED, 8, 256>()));
+    RVL_TRY((scan_opt_in_shape<PRED, 16, 0>()));
+    RVL_TRY((scan_opt_in_shape<PRED, 16, 256>()));
+    RVL_TRY((scan_opt_in_shape<PRED, 32, 0>()));
     RVL_CUDA_TRY(cudaFuncSetAttribute(fused_filter_project_kernel<PRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem)));
     return RVL_OK;
 }
@@ -582,7 +600,9 @@ int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pre
             sp.pred_values = pp.values; sp.lit_bits = pp.lit_bits; sp.pred_valid = pp.valid; sp.truth = pp.truth;
             sp.range_lo = pp.range_lo; sp.range_span = pp.range_span; sp.range_neg = pp.range_neg;
             sp.keep_null = pp.keep_null; sp.pred_vec_ok = pp.vec_ok; sp.pb_a = pp.pb_a; sp.pb_b = pp.pb_b; sp.pb_vals = pp.pb_vals;
-            sp.n_slots = std::max(1, std::min(3, core->scan_slots));
+            const int scan_item_rows = (scan_warps == 8 && (core->scan_item_rows == 512 || core->scan_item_rows == 256)) ||
+                                               (scan_warps == 16 && core->scan_item_rows == 256) ? core->scan_item_rows : 0;
+            sp.n_slots = std::max(1, std::min(scan_slot_cap(scan_warps, scan_item_rows), core->scan_slots));
             sp.sparse_max = (uint32_t)std::max(0, std::min(kSparseCap, core->sparse_max));
             sp.base_in = base_in;
             sp.sel_out = (uint32_t*)sel->ptr;
@@ -590,7 +610,9 @@ int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pre
             sp.chunk_base = (uint64_t*)chunk_base->ptr;
             sp.dense_list = dense_list; sp.sparse_list = sparse_list; sp.list_counts = list_counts;
             sp.total_out = dctr;
-            RVL_TRY(launch_scan(core, pp.kind, sp, scan_ctas, scan_warps));
+            { static const char* dbg = std::getenv("RVL_SCAN_DEBUG"); sp.debug_skip = dbg ? (uint32_t)std::atoi(dbg) : 0u; }
+            { static const char* h = std::getenv("RVL_SCAN_L2"); sp.l2_hints = h ? (uint32_t)std::atoi(h) : (uint32_t)core->scan_l2_hints; }
+            RVL_TRY(launch_scan(core, pp.kind, sp, scan_ctas, scan_warps, scan_item_rows));
             if (exact) {
                 // The survivor count (and every string column's survivor bytes) is known after pass 1: read it back and allocate the
                 // outputs at their exact size.  One host round trip (~15 us) against a scan of megabytes to gigabytes; a 0.1 % query

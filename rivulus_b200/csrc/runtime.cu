@@ -290,8 +290,11 @@ int32_t rvl_ctx_set_option(rvl_ctx* ctx, int32_t option, int64_t value) {
             if (value < 1 || value > 2) return fail(RVL_INVALID_ARGUMENT, "dense_ctas_per_sm must be 1 or 2");
             c.dense_ctas_per_sm = (int)value; return RVL_OK;
         case RVL_OPT_SCAN_SLOTS:
-            if (value < 1 || value > 3) return fail(RVL_INVALID_ARGUMENT, "scan_slots must be in [1, 3]");
+            if (value < 1 || value > 16) return fail(RVL_INVALID_ARGUMENT, "scan_slots must be in [1, 16]");
             c.scan_slots = (int)value; return RVL_OK;
+        case RVL_OPT_SCAN_ITEM_ROWS:
+            if (value != 0 && value != 256 && value != 512) return fail(RVL_INVALID_ARGUMENT, "scan_item_rows must be 0, 256 or 512");
+            c.scan_item_rows = (int)value; return RVL_OK;
         case RVL_OPT_SCAN_WARPS:
             if (value != 8 && value != 16 && value != 32) return fail(RVL_INVALID_ARGUMENT, "scan_warps must be 8, 16 or 32");
             c.scan_warps = (int)value; return RVL_OK;

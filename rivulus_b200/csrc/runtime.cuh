@@ -86,8 +86,12 @@ struct CtxCore {
     int dense_slots = 14;                   // two-pass: 16 KB ring slots per CTA of the dense compaction kernel
     int dense_ctas_per_sm = 1;
     int dense_warps = 16;                   // two-pass: consumer warps per CTA of the dense kernel (8 or 16)
-    int scan_warps = 16;                    // two-pass: warps per CTA of the predicate scan (8 or 16)
-    int scan_slots = 2;                     // two-pass: 8 KB ring slots per warp of the predicate scan (1..3)
+    int scan_warps = 8;                     // two-pass: warps per CTA of the predicate scan (8, 16 or 32).  Round-2 sweep over warps x slot
+                                            //   rows x ring depth (profiles/r02_scan_sweep.txt): 8 x 1024 x 2 = 6.70 TB/s, 16 x 512 x 2 (the
+                                            //   round-1 default) 6.31; more than ~128 KB in flight per SM is slower in every shape
+    int scan_slots = 2;                     // two-pass: ring slots per warp of the predicate scan (1..16, capped by shared memory)
+    int scan_l2_hints = 0;                  // two-pass: bit 0 = predicate column evict_first, bit 1 = selection words evict_last
+    int scan_item_rows = 0;                 // two-pass: rows per ring slot (0 = 8192 / warps; 512 or 256 with 8 warps, 256 with 16)
     // pooled timing-less events (one per in-flight operator invocation): create / destroy per batch costs microseconds
     std::vector<cudaEvent_t> event_pool;
     cudaEvent_t take_event() {

@@ -27,10 +27,11 @@
 namespace rvl {
 
 constexpr int kScanMaxWarps = 32;
-// W warps per CTA, each with its own ring of slots of 8192 / W rows (8 warps: 8 KB slots, 16 warps: 4 KB slots), so a
-// CTA always holds n_slots x 64 KB of predicate values
-template <int W> struct ScanShape {
-    static constexpr int kItemRows = 8192 / W;
+// W warps per CTA, each with its own ring of n_slots slots of R rows (R = 0: 8192 / W rows, i.e. 8 warps: 8 KB slots, 16 warps:
+// 4 KB slots, so that a CTA holds n_slots x 64 KB of predicate values).  A slot is re-armed when its last value has been
+// consumed: smaller slots keep a larger share of the ring in flight while the warp computes.
+template <int W, int R = 0> struct ScanShape {
+    static constexpr int kItemRows = R > 0 ? R : 8192 / W;
     static constexpr int kItemWords = kItemRows / 32;
     static constexpr int kItemsPerTile = kTileRows / kItemRows;
     static constexpr uint32_t kItemBytes = kItemRows * 8;
@@ -62,6 +63,8 @@ struct ScanParams {
     uint32_t* sparse_list;
     uint32_t* list_counts;    // [0] dense tiles, [1] sparse tiles, [2] CTAs finished (all zeroed before the launch)
     unsigned long long* total_out;
+    uint32_t debug_skip;      // timing experiments only (RVL_SCAN_DEBUG): 1 = no selection-word stores, 2 = no tile_info / list stores
+    uint32_t l2_hints;        // bit 0: predicate column loaded evict_first, bit 1: selection words stored evict_last
 };
 
 template <int PRED>
@@ -70,13 +73,13 @@ __device__ __forceinline__ bool scan_keep(const ScanParams& p, uint64_t v) {
     return (p.truth & cmp_code<PRED>(v, p.lit_bits)) != 0u;
 }
 
-template <int PRED, int W>
+template <int PRED, int W, int R = 0>
 __global__ void __launch_bounds__(W * 32, 1) predicate_scan_kernel(const __grid_constant__ ScanParams p) {
     constexpr int kScanWarps = W;
-    constexpr int kScanItemRows = ScanShape<W>::kItemRows;
-    constexpr int kItemWords = ScanShape<W>::kItemWords;
-    constexpr int kItemsPerTile = ScanShape<W>::kItemsPerTile;
-    constexpr uint32_t kScanItemBytes = ScanShape<W>::kItemBytes;
+    constexpr int kScanItemRows = ScanShape<W, R>::kItemRows;
+    constexpr int kItemWords = ScanShape<W, R>::kItemWords;
+    constexpr int kItemsPerTile = ScanShape<W, R>::kItemsPerTile;
+    constexpr uint32_t kScanItemBytes = ScanShape<W, R>::kItemBytes;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t s_part[kScanWarps];
     __shared__ uint32_t s_last;
@@ -96,11 +99,17 @@ __global__ void __launch_bounds__(W * 32, 1) predicate_scan_kernel(const __grid_
     const bool use_tma = kNumeric && p.pred_vec_ok != 0;
 
     auto item_tma = [&](int64_t j) { return use_tma && range_row0 + (j + 1) * kScanItemRows <= p.n_rows; };
+    // the 8 bytes per row pass through once: evict_first keeps them from flushing the selection bitmap (1 bit per row, stored
+    // evict_last) out of L2 before the compaction pass reads it back
+    const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+    auto load_item = [&](uint64_t* dst, const uint64_t* src, uint64_t* bar) {
+        if (p.l2_hints & 1u) tma_load_1d_hint(dst, src, kScanItemBytes, bar, pol_stream); else tma_load_1d(dst, src, kScanItemBytes, bar);
+    };
     if (kNumeric && lane == 0) {
         for (int s = 0; s < D; ++s) mbar_init(&full[s], 1);
         mbar_init_fence();
         for (int64_t j = 0; j < min((int64_t)D, n_items); ++j)
-            if (item_tma(j)) tma_load_1d(ring + (size_t)j * kScanItemRows, p.pred_values + range_row0 + j * kScanItemRows, kScanItemBytes, &full[j]);
+            if (item_tma(j)) load_item(ring + (size_t)j * kScanItemRows, p.pred_values + range_row0 + j * kScanItemRows, &full[j]);
     }
     __syncwarp();
 
@@ -170,7 +179,7 @@ __global__ void __launch_bounds__(W * 32, 1) predicate_scan_kernel(const __grid_
                 });
                 // every value of the slot has been consumed: re-arm it with the item D steps ahead
                 if (lane == 0 && j + D < n_items && item_tma(j + D))
-                    tma_load_1d(ring + (size_t)slot * kScanItemRows, p.pred_values + range_row0 + (j + D) * kScanItemRows, kScanItemBytes, &full[slot]);
+                    load_item(ring + (size_t)slot * kScanItemRows, p.pred_values + range_row0 + (j + D) * kScanItemRows, &full[slot]);
                 if (++slot == D) { slot = 0; phase ^= 1u; }
             } else if (PRED == kPredBits) {
                 const uint32_t a = p.pb_a ? ~0u : 0u, b = p.pb_b ? ~0u : 0u, kn = p.keep_null ? ~0u : 0u;
@@ -183,11 +192,14 @@ __global__ void __launch_bounds__(W * 32, 1) predicate_scan_kernel(const __grid_
                 if (rem < 32) myword = rem <= 0 ? 0u : (myword & ((1u << rem) - 1u));
             }
             if (lane >= kItemWords) myword = 0u;  // lanes beyond the item's words hold nothing
-            if (lane < kItemWords) p.sel_out[(row0 >> 5) + lane] = myword;
+            if (lane < kItemWords && !(p.debug_skip & 1u)) {
+                if (p.l2_hints & 2u) st_u32_hint(p.sel_out + (row0 >> 5) + lane, myword, pol_keep); else p.sel_out[(row0 >> 5) + lane] = myword;
+            }
             tcount += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(myword));
         }
-        if (lane == 0) p.tile_info[t] = (lprefix << kInfoShift) | (uint64_t)tcount;
+        if (lane == 0 && !(p.debug_skip & 2u)) p.tile_info[t] = (lprefix << kInfoShift) | (uint64_t)tcount;
         lprefix += tcount;
+        if (p.debug_skip & 2u) continue;
         if (tcount > p.sparse_max) {
             if ((uint32_t)lane == n_dense) pend_dense = (uint32_t)t;
             if (++n_dense == 32u) { flush(p.dense_list, p.list_counts, pend_dense, 32u); n_dense = 0; }

@@ -149,6 +149,9 @@ PtrRange classify(rvl_stream* s, const void* p) {
 
 int ensure_pinned(void** p, size_t* cap, size_t need) {
     if (*p != nullptr && (cap == nullptr || *cap >= need)) return RVL_OK;
+    // variable-size staging (string bytes) grows by half again, in whole MiB: cudaFreeHost + cudaHostAlloc synchronise the device
+    // and cost milliseconds, which a stream of batches of slightly different byte counts would otherwise pay on every push
+    if (*p != nullptr && cap != nullptr) need = (std::max(need, *cap + *cap / 2) + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
     if (*p != nullptr) { cudaFreeHost(*p); *p = nullptr; }
     RVL_CUDA_TRY(cudaHostAlloc(p, need ? need : 1, cudaHostAllocDefault));
     if (cap) *cap = need;

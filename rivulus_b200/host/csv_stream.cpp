@@ -24,6 +24,8 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
+#include <cstdio>
 #include <condition_variable>
 #include <deque>
 #include <mutex>
@@ -157,7 +159,7 @@ int parse_bool(sv s) {  // to_lowercase() then "true"|"t"|"1" / "false"|"f"|"0" 
     return -1;
 }
 
-struct ColumnBuf {  // one column of the batch being parsed, Arrow layout, reused across batches
+struct alignas(128) ColumnBuf {  // one column of the batch being parsed, Arrow layout, reused across batches (own cache lines: see CsvJob)
     ExecType type = ExecType::Null;
     std::vector<int64_t> i64; std::vector<double> f64; std::vector<uint8_t> bits, validity, data; std::vector<int32_t> offsets;
     bool any_null = false;
@@ -178,7 +180,9 @@ struct ColumnBuf {  // one column of the batch being parsed, Arrow layout, reuse
 
 // One batch on its way through the reader: the text of its data lines (stage 1, the caller's thread) and the parsed columns
 // (stage 2, a worker thread or the caller itself).
-struct CsvJob {
+// (alignas + locals in the parse loop: two jobs that share a cache line — one worker's per-row progress store next to the vector
+// headers another worker reads on every row — doubled the parse time of concurrent batches)
+struct alignas(128) CsvJob {
     std::vector<char> text;            // the batch's non-blank lines, terminators stripped, back to back
     std::vector<uint32_t> starts;      // start of every line in `text` + one end sentinel
     std::vector<uint64_t> line_no;     // 1-based number of every line in the file (header = 1, blank lines count)
@@ -188,6 +192,24 @@ struct CsvJob {
     std::string parse_error;           // first bad line in file order
     bool done = false;
 };
+
+// Parsed-batch buffers outlive their reader: a fresh multi-megabyte buffer costs a page fault per 4 KB on first touch (about as much
+// as parsing into it, measured), so finished readers park their jobs here and the next reader starts with warm ones.
+std::mutex g_job_pool_mu;
+std::vector<std::unique_ptr<CsvJob>> g_job_pool;
+constexpr size_t kJobPoolMax = 24;
+std::unique_ptr<CsvJob> pooled_job() {
+    std::lock_guard<std::mutex> g(g_job_pool_mu);
+    if (g_job_pool.empty()) return std::make_unique<CsvJob>();
+    auto j = std::move(g_job_pool.back());
+    g_job_pool.pop_back();
+    return j;
+}
+void park_job(std::unique_ptr<CsvJob> j) {
+    if (!j) return;
+    std::lock_guard<std::mutex> g(g_job_pool_mu);
+    if (g_job_pool.size() < kJobPoolMax) g_job_pool.push_back(std::move(j));
+}
 
 struct CsvBatchReader::Impl {
     int fd = -1;
@@ -205,12 +227,16 @@ struct CsvBatchReader::Impl {
     std::unique_ptr<CsvJob> current;                  // the batch last returned by read_batch
     bool stop = false;
     size_t depth = 1;
+    size_t last_text_bytes = 0;
 
     ~Impl() {
         { std::lock_guard<std::mutex> g(mu); stop = true; }
         work_cv.notify_all();
         for (auto& t : workers) t.join();
         if (fd >= 0) ::close(fd);
+        park_job(std::move(current));
+        for (auto& j : order) park_job(std::move(j));
+        for (auto& j : spare) park_job(std::move(j));
     }
 
     // the next line including its '\n' (BufRead::read_line); false at end of file; throws std::string on an I/O error
@@ -251,6 +277,9 @@ struct CsvBatchReader::Impl {
     bool fill(CsvJob& j) {
         j.text.clear(); j.starts.clear(); j.line_no.clear(); j.read_error.clear(); j.parse_error.clear(); j.rows = 0; j.done = false;
         if (finished) return false;
+        // size a fresh job like the last one: growing a multi-megabyte vector step by step is a chain of mremap calls, each a TLB
+        // shootdown across every thread of the process
+        if (j.text.capacity() == 0 && last_text_bytes > 0) { j.text.reserve(last_text_bytes + last_text_bytes / 8); j.starts.reserve(batch_size + 1); j.line_no.reserve(batch_size); }
         const char* p; size_t n;
         try {
             while (j.line_no.size() < batch_size) {
@@ -268,25 +297,36 @@ struct CsvBatchReader::Impl {
             finished = true;
         }
         j.starts.push_back((uint32_t)j.text.size());
+        last_text_bytes = std::max(last_text_bytes, j.text.size());
         return !j.line_no.empty() || !j.read_error.empty();
     }
 
     // stage 2: every line of the job into the job's columns; stops at the first bad line
     void parse(CsvJob& j) const {
         const size_t nf = schema->fields.size();
-        if (j.cols.size() != nf) { j.cols.assign(nf, ColumnBuf()); for (size_t i = 0; i < nf; ++i) j.cols[i].type = schema->fields[i].data_type; }
+        j.cols.resize(nf);   // a pooled job keeps whatever buffers its columns already own
+        for (size_t i = 0; i < nf; ++i) j.cols[i].type = schema->fields[i].data_type;
         const size_t nlines = j.line_no.size();
-        for (auto& c : j.cols) c.begin(nlines);
+        static const bool trace = std::getenv("RVL_CSV_TRACE") != nullptr;
+        const auto t0 = std::chrono::steady_clock::now();
+        for (auto& c : j.cols) { c.begin(nlines); if (c.type == ExecType::String && c.data.capacity() == 0) c.data.reserve(j.text.size() / 2); }
+        const auto t1 = std::chrono::steady_clock::now();
+        struct Tr { bool on; std::chrono::steady_clock::time_point a, b; size_t n; ~Tr() { if (on) std::fprintf(stderr, "[csv] job of %zu lines: buffers %.2f ms, parse %.2f ms\n", n,
+            std::chrono::duration<double, std::milli>(b - a).count(), std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - b).count()); } } tr{trace, t0, t1, nlines};
+        const char* const text = j.text.data();
+        const uint32_t* const starts = j.starts.data();
+        size_t rows = 0;
         for (size_t r = 0; r < nlines; ++r) {
-            const char* p = j.text.data() + j.starts[r];
-            const size_t n = j.starts[r + 1] - j.starts[r];
+            const char* p = text + starts[r];
+            const size_t n = starts[r + 1] - starts[r];
             if (!valid_utf8(p, n)) {   // read_line fails before the line is counted: "line {current_line + 1}" is this line's number
                 j.parse_error = "Stream execution error: Failed to read line " + std::to_string(j.line_no[r]) + ": stream did not contain valid UTF-8";
-                return;
+                break;
             }
-            if (!parse_line(j, r, sv(p, n))) return;
-            j.rows = r + 1;
+            if (!parse_line(j, r, sv(p, n))) break;
+            rows = r + 1;
         }
+        j.rows = rows;
     }
 
     bool parse_line(CsvJob& j, size_t r, sv line) const {  // :42-121, writing row r of every column
@@ -375,7 +415,7 @@ CsvBatchReader::CsvBatchReader(const std::string& path, SchemaRef schema, std::o
     int threads = g_csv_threads;
     if (threads < 0) threads = big ? (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 4)) : 0;
     if (threads > 0 && impl_->batch_size > 0) {
-        impl_->depth = (size_t)threads * 2;
+        impl_->depth = (size_t)threads + 2;
         for (int i = 0; i < threads; ++i) impl_->workers.emplace_back([m = impl_.get()] { m->worker_loop(); });
     }
 }
@@ -397,9 +437,11 @@ size_t CsvBatchReader::read_batch() {  // read_batch :123-199
         ++m.current_line;
     }
     // keep `depth` batches of text in the pipeline (stage 1 runs here, ahead of the workers)
+    static const bool trace = std::getenv("RVL_CSV_TRACE") != nullptr;
+    const auto tt0 = std::chrono::steady_clock::now();
     while (m.order.size() < m.depth && !m.finished) {
         std::unique_ptr<CsvJob> j;
-        if (!m.spare.empty()) { j = std::move(m.spare.back()); m.spare.pop_back(); } else j = std::make_unique<CsvJob>();
+        if (!m.spare.empty()) { j = std::move(m.spare.back()); m.spare.pop_back(); } else j = pooled_job();
         if (!m.fill(*j)) { m.spare.push_back(std::move(j)); break; }
         CsvJob* raw = j.get();
         m.order.push_back(std::move(j));
@@ -411,8 +453,11 @@ size_t CsvBatchReader::read_batch() {  // read_batch :123-199
     if (m.order.empty()) return 0;
     std::unique_ptr<CsvJob> j = std::move(m.order.front());
     m.order.pop_front();
+    const auto tt1 = std::chrono::steady_clock::now();
     if (m.workers.empty()) { if (j->read_error.empty()) m.parse(*j); }
     else { std::unique_lock<std::mutex> g(m.mu); m.done_cv.wait(g, [&] { return j->done; }); }
+    if (trace) std::fprintf(stderr, "[csv] read_batch: fill %.2f ms, wait/parse %.2f ms\n", std::chrono::duration<double, std::milli>(tt1 - tt0).count(),
+                            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tt1).count());
     // errors surface in file order: a bad line first (it precedes the failed read), then the read error
     if (!j->parse_error.empty()) { m.failed = true; const std::string e = j->parse_error; m.spare.push_back(std::move(j)); throw Error(e); }
     if (!j->read_error.empty()) { m.failed = true; const std::string e = j->read_error; m.spare.push_back(std::move(j)); throw Error(e); }

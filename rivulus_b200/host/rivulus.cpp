@@ -6,6 +6,8 @@
 #include <algorithm>
 #include <charconv>
 #include <cmath>
+#include <chrono>
+#include <cstdio>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -1001,9 +1003,15 @@ static std::optional<RecordBatch> try_fused_collect(const StreamingPhysicalPlan&
         for (const auto& f : in_schema->fields) has_string |= f.data_type == ExecType::String;
         const size_t bs = std::max<size_t>(reader->batch_size(), 1);
         open(has_string ? bs : std::max(bs, K::kCollectBatchRows));
+        static const bool trace = std::getenv("RVL_HOST_TRACE") != nullptr;
+        using clk = std::chrono::steady_clock;
+        double t_read = 0, t_push = 0;
+        auto t_mark = clk::now();
+        auto lap = [&](double& acc) { const auto now = clk::now(); acc += std::chrono::duration<double, std::milli>(now - t_mark).count(); t_mark = now; };
+        struct Report { const bool on; double& r; double& p; clk::time_point t0; ~Report() { if (on) std::fprintf(stderr, "[host] csv pipeline: read_batch %.1f ms, push %.1f ms, total %.1f ms\n", r, p, std::chrono::duration<double, std::milli>(clk::now() - t0).count()); } } report{trace, t_read, t_push, t_mark};
         for (;;) {
             size_t rows = 0;
-            try { rows = reader->read_batch(); }
+            try { rows = reader->read_batch(); lap(t_read); }
             catch (const Error& e) {
                 if (e.panic) throw;
                 // The reference reads batch j only while fewer than `limit` rows came out of batches < j: an error in a batch it
@@ -1016,6 +1024,7 @@ static std::optional<RecordBatch> try_fused_collect(const StreamingPhysicalPlan&
             const std::vector<rvl_column> cols = reader->columns();
             int32_t accepted = 0;
             check(rvl_stream_push(closer.s, cols.data(), (int32_t)ncols, &accepted));
+            lap(t_push);
             if (!accepted) break;
         }
         return finish();

@@ -7,6 +7,8 @@ python scripts/profile_one.py --rows 1000000000 > gpurun_out/r02_plain1b.log 2>&
 ncu --set full --import-source on --clock-control none -k 'regex:predicate_scan|compact_dense|gather_sparse' -c 12 -o gpurun_out/r02_prof_twopass -f python scripts/profile_one.py --rows 1000000000 > gpurun_out/r02_ncu_full_1b.log 2>&1
 python scripts/ncu_top.py gpurun_out/r02_prof_twopass.ncu-rep 8 > gpurun_out/r02_ncu_full_1b_twopass.txt 2>&1
 python scripts/make_traffic_json.py gpurun_out/r02_prof_twopass.ncu-rep gpurun_out/r02_traffic.json
+ncu -i gpurun_out/r02_prof_twopass.ncu-rep --page raw --csv 2>/dev/null | gzip > gpurun_out/r02_ncu_full_1b_twopass_raw.csv.gz
+rm -f gpurun_out/r02_prof_twopass.ncu-rep     # gpurun brings back at most 64 MiB: the summaries travel, the reports do not
 # configs[4] shard: chunk kernel (50 %) and the two-pass kernels (10 %)
 cat > /tmp/c5_one.py <<'PY'
 import sys
@@ -22,8 +24,10 @@ PY
 python /tmp/c5_one.py > gpurun_out/r02_c5_plain.log 2>&1 && \
 ncu --set full --import-source on --clock-control none -k 'regex:chunk_filter|compact_bits|predicate_scan|compact_dense|gather_sparse' -c 8 -o gpurun_out/r02_prof_c5 -f python /tmp/c5_one.py > gpurun_out/r02_ncu_c5.log 2>&1
 python scripts/ncu_top.py gpurun_out/r02_prof_c5.ncu-rep 8 > gpurun_out/r02_ncu_full_c5.txt 2>&1
+rm -f gpurun_out/r02_prof_c5.ncu-rep
 # configs[2] batch: string kernels
 python scripts/c3_one.py --kernel 3 > gpurun_out/r02_c3_plain.log 2>&1 && \
 ncu --set full --import-source on --clock-control none -k 'regex:string_' -c 4 -o gpurun_out/r02_prof_str -f python scripts/c3_one.py --kernel 3 > gpurun_out/r02_ncu_str.log 2>&1
 python scripts/ncu_top.py gpurun_out/r02_prof_str.ncu-rep 8 > gpurun_out/r02_ncu_full_c3_strings.txt 2>&1
-ls -la gpurun_out/*.ncu-rep
+rm -f gpurun_out/r02_prof_str.ncu-rep
+ls -la gpurun_out/

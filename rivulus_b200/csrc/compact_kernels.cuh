@@ -395,6 +395,39 @@ __device__ __forceinline__ uint32_t compress_bits(uint32_t x, const CompressPlan
     return x;
 }
 
+// One tile of one bit-packed column: lane l holds the compressed survivors of words l (x0, n0 bits kept, tile rank e0) and l + 32
+// (x1, n1, e1).  The 64 variable-length pieces are merged at their bit offsets in `buf` (kTileWords + 2 words of this warp) and
+// stored at output bit `obase`: interior words plainly, the two boundary words OR-ed atomically (the neighbouring tiles own the rest).
+__device__ __forceinline__ void emit_bit_tile(uint32_t* buf, int lane, uint32_t x0, uint32_t x1, uint32_t e0, uint32_t e1, uint32_t tot,
+                                              uint64_t obase, uint32_t* out) {
+    const uint32_t sh = (uint32_t)obase & 31u;
+    const uint64_t first_word = obase >> 5;
+    const uint32_t end = sh + tot;                    // bits [sh, end) of the tile's output words are ours
+    const uint32_t n_words = (end + 31u) >> 5;        // <= 65
+    buf[lane] = 0u; buf[lane + 32] = 0u;
+    if (lane < 2) buf[64 + lane] = 0u;
+    __syncwarp();
+    if (x0 != 0u) {
+        const uint32_t q = sh + e0, s = q & 31u;
+        atomicOr(&buf[q >> 5], x0 << s);
+        if (s != 0u && (x0 >> (32u - s)) != 0u) atomicOr(&buf[(q >> 5) + 1u], x0 >> (32u - s));
+    }
+    if (x1 != 0u) {
+        const uint32_t q = sh + e1, s = q & 31u;
+        atomicOr(&buf[q >> 5], x1 << s);
+        if (s != 0u && (x1 >> (32u - s)) != 0u) atomicOr(&buf[(q >> 5) + 1u], x1 >> (32u - s));
+    }
+    __syncwarp();
+    for (uint32_t w = (uint32_t)lane; w < n_words; w += 32u) {
+        const uint32_t v = buf[w], lo = w * 32u;
+        const bool owned = (w > 0u || sh == 0u) && (lo + 32u <= end);
+        uint32_t* o = out + first_word + w;
+        if (owned) *o = v;
+        else if (v != 0u) atomicOr(o, v);
+    }
+    __syncwarp();
+}
+
 static __global__ void __launch_bounds__(kBlock) compact_bits_kernel(const __grid_constant__ CompactParams p) {
     __shared__ uint32_t s_out[kWarps][kTileWords + 2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -433,10 +466,6 @@ static __global__ void __launch_bounds__(kBlock) compact_bits_kernel(const __gri
         const uint32_t n1 = e1 >= lim_rel ? 0u : min((uint32_t)__popc(w1), lim_rel - e1);
         const uint32_t tot = min(total, lim_rel);
         const uint64_t obase = prefix - base0;            // output bit index of the tile's first survivor
-        const uint32_t sh = (uint32_t)obase & 31u;
-        const uint64_t first_word = obase >> 5;
-        const uint32_t end = sh + tot;                    // bits [sh, end) of the tile's output words are ours
-        const uint32_t n_words = (end + 31u) >> 5;        // <= 65
         const CompressPlan c0 = compress_plan(w0), c1 = compress_plan(w1);
         const uint64_t r0 = (uint64_t)tile * kTileRows + (uint64_t)lane * 32u, r1 = r0 + 1024u;
         for (int b = 0; b < p.n_bits; ++b) {
@@ -445,28 +474,7 @@ static __global__ void __launch_bounds__(kBlock) compact_bits_kernel(const __gri
             uint32_t x1 = compress_bits(load_bits32(bc.in, r1) & load_bits32(bc.mask, r1), c1);
             if (n0 < 32u) x0 &= (1u << n0) - 1u;
             if (n1 < 32u) x1 &= (1u << n1) - 1u;
-            buf[lane] = 0u; buf[lane + 32] = 0u;
-            if (lane < 2) buf[64 + lane] = 0u;
-            __syncwarp();
-            if (x0 != 0u) {
-                const uint32_t q = sh + e0, s = q & 31u;
-                atomicOr(&buf[q >> 5], x0 << s);
-                if (s != 0u && (x0 >> (32u - s)) != 0u) atomicOr(&buf[(q >> 5) + 1u], x0 >> (32u - s));
-            }
-            if (x1 != 0u) {
-                const uint32_t q = sh + e1, s = q & 31u;
-                atomicOr(&buf[q >> 5], x1 << s);
-                if (s != 0u && (x1 >> (32u - s)) != 0u) atomicOr(&buf[(q >> 5) + 1u], x1 >> (32u - s));
-            }
-            __syncwarp();
-            for (uint32_t w = (uint32_t)lane; w < n_words; w += 32u) {
-                const uint32_t v = buf[w], lo = w * 32u;
-                const bool owned = (w > 0u || sh == 0u) && (lo + 32u <= end);
-                uint32_t* o = bc.out + first_word + w;
-                if (owned) *o = v;
-                else if (v != 0u) atomicOr(o, v);
-            }
-            __syncwarp();
+            emit_bit_tile(buf, lane, x0, x1, e0, e1, tot, obase, bc.out);
         }
     }
 }

@@ -266,6 +266,18 @@ int32_t rvl_stream_stats(rvl_stream* stream, int64_t* batches_pushed, int64_t* b
 int32_t rvl_stream_launches(rvl_stream* stream, int64_t* groups);
 int32_t rvl_stream_close(rvl_stream* stream);
 
+/* ---- inner equi-join ------------------------------------------------ */
+/* PhysicalPlan::HashJoin, JoinType::Inner (physical_plan/plan.rs:174-284): for every probe row in order, every build row with an
+ * equal key in ascending build order; *out holds the probe columns `probe_proj` followed by the build columns `build_proj`, each
+ * taken by the matching row (materialize_join_result :208-254; bitmaps kept only where a taken row is null).  Key equality is
+ * AnyValue's (series.rs:73-98): two nulls are equal, values are equal when they have the same type and the same value, an Int64
+ * never equals a Float64, NaN equals nothing.  `*_tag_column`: 0, or k + 1 = Boolean column k marks the Int64 rows of a key column
+ * that is a mixed Float64 / Int64 Series (as rvl_predicate::tag_column).  Both batches live on the context's device; each side is
+ * limited to 2^32 - 1 rows. */
+int32_t rvl_hash_join_inner(rvl_ctx* ctx, const rvl_batch* build, int32_t build_key, int32_t build_tag_column, const rvl_batch* probe,
+                            int32_t probe_key, int32_t probe_tag_column, const int32_t* probe_proj, int32_t n_probe_proj,
+                            const int32_t* build_proj, int32_t n_build_proj, rvl_batch** out, int64_t* n_pairs);
+
 /* ---- multi-GPU: contiguous row ranges, no collective ---------------------- */
 /* rows [begin, end) of shard `rank` of `world` for an n_rows table; boundaries are multiples of 64 rows */
 int32_t rvl_shard_range(int64_t n_rows, int32_t rank, int32_t world, int64_t* begin, int64_t* end);

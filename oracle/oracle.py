@@ -59,7 +59,7 @@ def lib():
         build()
         L = C.CDLL(_LIB_PATH)
         L.orc_last_error.restype = C.c_char_p
-        for name in ("orc_dfb_new", "orc_expr_col", "orc_expr_lit", "orc_expr_binary", "orc_expr_alias", "orc_lf_from_df", "orc_lf_from_csv", "orc_sp_csv_source",
+        for name in ("orc_dfb_new", "orc_expr_col", "orc_expr_lit", "orc_expr_binary", "orc_expr_alias", "orc_lf_from_df", "orc_lf_from_csv", "orc_sp_csv_source", "orc_lf_inner_join",
                      "orc_lf_select", "orc_lf_filter", "orc_lf_limit", "orc_arr_i64", "orc_arr_f64", "orc_arr_bool",
                      "orc_arr_str", "orc_arr_null", "orc_arr_i64_new", "orc_arr_f64_new", "orc_arr_bool_new",
                      "orc_sp_memory_source", "orc_sp_dataframe_source", "orc_sp_filter", "orc_sp_select", "orc_sp_limit",
@@ -288,6 +288,9 @@ class LazyFrame:
 
     def filter(self, pred: Expr):
         return LazyFrame(lib().orc_lf_filter(_vp(self._h), _vp(pred._h)))
+
+    def inner_join(self, right: "LazyFrame", left_key: str, right_key: str):
+        return LazyFrame(lib().orc_lf_inner_join(_vp(self._h), _vp(right._h), left_key.encode(), right_key.encode()))
 
     def limit(self, n: int):
         return LazyFrame(lib().orc_lf_limit(_vp(self._h), C.c_int64(n)))

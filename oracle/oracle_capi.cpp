@@ -125,6 +125,9 @@ void* orc_lf_select(void* lf, int n, void** exprs) {
     return new LazyFrame(((LazyFrame*)lf)->select(std::move(e)));
 }
 void* orc_lf_filter(void* lf, void* pred) { return new LazyFrame(((LazyFrame*)lf)->filter(*(Expr*)pred)); }
+void* orc_lf_inner_join(void* lf, void* right, const char* left_key, const char* right_key) {
+    return new LazyFrame(((LazyFrame*)lf)->inner_join(*(LazyFrame*)right, left_key, right_key));
+}
 void* orc_lf_limit(void* lf, int64_t n) { return new LazyFrame(((LazyFrame*)lf)->limit((size_t)n)); }
 void orc_lf_free(void* lf) { delete (LazyFrame*)lf; }
 void orc_set_extensions(int on) { set_extensions(on != 0); }
@@ -139,6 +142,9 @@ static std::string describe_plan(const LogicalPlan& p) {
     switch (p.kind) {
         case LogicalPlan::DataFrameSource: return "DataFrameSource";
         case LogicalPlan::CsvFileSource: return "CsvFileSource { path: \"" + p.csv_path + "\" }";
+        case LogicalPlan::Join:
+            return "Join { left: " + describe_plan(*p.input) + ", right: " + describe_plan(*p.right) + ", left_key: \"" + p.left_key + "\", right_key: \"" +
+                   p.right_key + "\", join_type: Inner }";
         case LogicalPlan::Select: {
             std::string e;
             for (size_t i = 0; i < p.expressions.size(); ++i) e += (i ? ", " : "") + p.expressions[i].debug();
@@ -161,24 +167,21 @@ int orc_lf_describe(void* lf, char* buf, int cap) {
     return guard([&] { std::snprintf(buf, (size_t)cap, "%s", describe_plan(((LazyFrame*)lf)->plan).c_str()); });
 }
 // optimizer shape probe for tests: returns the optimized plan as "Filter(Select(Source))"-style text
-int orc_lf_plan_shape(void* lf, char* buf, int cap) {
-    LogicalPlan p = optimize(((LazyFrame*)lf)->plan);
-    std::string s, close;
-    const LogicalPlan* cur = &p;
-    while (true) {
-        switch (cur->kind) {
-            case LogicalPlan::DataFrameSource: s += "Source"; break;
-            case LogicalPlan::CsvFileSource: s += "CsvSource"; break;
-            case LogicalPlan::Select: s += "Select("; close += ")"; break;
-            case LogicalPlan::Filter: s += "Filter("; close += ")"; break;
-            case LogicalPlan::Limit: s += "Limit("; close += ")"; break;
-        }
-        if (cur->kind == LogicalPlan::DataFrameSource || cur->kind == LogicalPlan::CsvFileSource) break;
-        cur = cur->input.get();
+static std::string plan_shape(const LogicalPlan& p) {
+    switch (p.kind) {
+        case LogicalPlan::DataFrameSource: return "Source";
+        case LogicalPlan::CsvFileSource: return "CsvSource";
+        case LogicalPlan::Select: return "Select(" + plan_shape(*p.input) + ")";
+        case LogicalPlan::Filter: return "Filter(" + plan_shape(*p.input) + ")";
+        case LogicalPlan::Limit: return "Limit(" + plan_shape(*p.input) + ")";
+        case LogicalPlan::Join: return "Join(" + plan_shape(*p.input) + ", " + plan_shape(*p.right) + ")";
     }
-    s += close;
+    return "";
+}
+int orc_lf_plan_shape(void* lf, char* buf, int cap) {
+    const std::string s = plan_shape(optimize(((LazyFrame*)lf)->plan));
     std::snprintf(buf, (size_t)cap, "%s", s.c_str());
-    return 0;
+    return (int)s.size();
 }
 
 // ----------------------------------------------------------------------------------- Arrays / RecordBatch

@@ -3,6 +3,8 @@
 // reference file:line (relative to /root/reference/src) it follows.
 #include "rivulus_oracle.hpp"
 
+#include <map>
+
 #include <algorithm>
 #include <charconv>
 #include <cmath>
@@ -791,8 +793,25 @@ std::vector<std::pair<std::string, DataType>> LogicalPlan::schema() const {  // 
             return out;
         }
         case Filter: case Limit: return input->schema();
+        case Join: {  // :79-111: the left schema, then the right columns except the right key, "_right" on a name the left side has
+            auto left = input->schema();
+            auto out = left;
+            for (const auto& rc : right->schema()) {
+                if (rc.first == right_key) continue;
+                bool clash = false;
+                for (const auto& lc : left) clash = clash || lc.first == rc.first;
+                out.emplace_back(clash ? rc.first + "_right" : rc.first, rc.second);
+            }
+            return out;
+        }
     }
     return {};
+}
+
+static bool is_comparable_with(DataType a, DataType b) {  // series.rs:144-159
+    if (a == b) return true;
+    if ((a == DataType::Int64 && b == DataType::Float64) || (a == DataType::Float64 && b == DataType::Int64)) return true;
+    return a == DataType::Null || b == DataType::Null;
 }
 
 static void validate_expr_columns(const Expr& e, const std::vector<std::pair<std::string, DataType>>& schema) {
@@ -828,6 +847,19 @@ void LogicalPlan::validate() const {  // logical_plan/plan.rs:115-202
         }
         case Limit: input->validate(); break;
         case CsvFileSource: break;  // :128
+        case Join: {  // :156-200 — the right side is validated first
+            right->validate();
+            input->validate();
+            const auto ls = input->schema(), rs = right->schema();
+            const DataType* lt = nullptr; const DataType* rt = nullptr;
+            for (const auto& c : ls) if (c.first == left_key && !lt) lt = &c.second;
+            if (!lt) throw OracleError("Logical plan error: Column not found: '" + left_key + "'");
+            for (const auto& c : rs) if (c.first == right_key && !rt) rt = &c.second;
+            if (!rt) throw OracleError("Logical plan error: Column not found: '" + right_key + "'");
+            if (!is_comparable_with(*lt, *rt))
+                throw OracleError(std::string("Logical plan error: Incompatible join key types: '") + dtype_name(*lt) + "' and '" + dtype_name(*rt) + "'");
+            break;
+        }
     }
 }
 
@@ -875,6 +907,12 @@ LogicalPlan optimize(LogicalPlan plan) {  // optimizer.rs:15-64 (push_predicates
         case LogicalPlan::Filter: {  // :46-49
             LogicalPlan out = plan;
             out.input = std::make_shared<LogicalPlan>(optimize(*plan.input));
+            return out;
+        }
+        case LogicalPlan::Join: {  // :50-61
+            LogicalPlan out = plan;
+            out.input = std::make_shared<LogicalPlan>(optimize(*plan.input));
+            out.right = std::make_shared<LogicalPlan>(optimize(*plan.right));
             return out;
         }
         default: return plan;  // :62 (Limit, sources: untouched)
@@ -964,7 +1002,26 @@ static void check_lowering(const LogicalPlan& p) {
             else convert_filter_predicate(p.predicate);
             return;
         case LogicalPlan::Limit: check_lowering(*p.input); return;
+        case LogicalPlan::Join: check_lowering(*p.input); check_lowering(*p.right); return;   // planner.rs:97-98: left, then right
     }
+}
+
+// HashMap<AnyValue, Vec<usize>> key of the join (series.rs:73-98): same variant and same value; f64 hashed by to_bits, NaN == nothing.
+// 0.0 and -0.0 are equal but hash differently, so they meet only when the table's random state happens to collide: kept apart here.
+struct JoinKey {
+    int tag; uint64_t bits; std::string s;
+    bool operator<(const JoinKey& o) const { return tag != o.tag ? tag < o.tag : (bits != o.bits ? bits < o.bits : s < o.s); }
+};
+static bool join_key_of(const AnyValue& v, JoinKey* k) {
+    k->tag = (int)v.tag; k->bits = 0; k->s.clear();
+    switch (v.tag) {
+        case AnyValue::kNull: break;
+        case AnyValue::kInt64: k->bits = (uint64_t)v.i; break;
+        case AnyValue::kFloat64: if (v.f != v.f) return false; std::memcpy(&k->bits, &v.f, 8); break;
+        case AnyValue::kString: k->s = v.s; break;
+        case AnyValue::kBoolean: k->bits = v.b ? 1 : 0; break;
+    }
+    return true;
 }
 
 static DataFrame exec_node(const LogicalPlan& p) {  // physical_plan/plan.rs:65-173
@@ -1028,6 +1085,42 @@ static DataFrame exec_node(const LogicalPlan& p) {  // physical_plan/plan.rs:65-
                 catch (const OracleError& e) { throw OracleError(std::string("Series error: ") + e.what()); }
             }
             return DataFrame::make(std::move(out));
+        }
+        case LogicalPlan::Join: {                        // :174-284, build = left, probe = right (planner.rs:100-108)
+            DataFrame build = exec_node(*p.input);
+            const Series* bks = build.column(p.left_key);
+            if (!bks) throw Panic("called `Option::unwrap()` on a `None` value");
+            std::map<JoinKey, std::vector<size_t>> table;   // :186-193
+            JoinKey k;
+            for (size_t i = 0; i < bks->len(); ++i) if (join_key_of(bks->data()[i], &k)) table[k].push_back(i);
+            DataFrame probe = exec_node(*p.right);
+            const Series* pks = probe.column(p.right_key);
+            if (!pks) throw Panic("called `Option::unwrap()` on a `None` value");
+            std::vector<std::pair<size_t, size_t>> pairs;   // :197-205
+            for (size_t i = 0; i < pks->len(); ++i) {
+                if (!join_key_of(pks->data()[i], &k)) continue;
+                auto it = table.find(k);
+                if (it != table.end()) for (size_t b : it->second) pairs.emplace_back(i, b);
+            }
+            std::vector<Series> out;                         // materialize_join_result :208-254 / create_empty_join_result :256-283
+            auto build_name = [&](const Series& s) { return probe.column(s.name()) ? s.name() + "_right" : s.name(); };
+            try {
+                for (const auto& s : probe.columns()) {
+                    if (pairs.empty()) { out.push_back(Series::empty(s.name(), s.dtype())); continue; }
+                    std::vector<AnyValue> d; d.reserve(pairs.size());
+                    for (const auto& pr : pairs) d.push_back(s.data()[pr.first]);
+                    out.push_back(Series::make(s.name(), std::move(d)));
+                }
+                for (const auto& s : build.columns()) {
+                    if (s.name() == p.left_key) continue;
+                    if (pairs.empty()) { out.push_back(Series::empty(build_name(s), s.dtype())); continue; }
+                    std::vector<AnyValue> d; d.reserve(pairs.size());
+                    for (const auto& pr : pairs) d.push_back(s.data()[pr.second]);
+                    out.push_back(Series::make(build_name(s), std::move(d)));
+                }
+            } catch (const OracleError& e) { throw OracleError(std::string("Series error: ") + e.what()); }
+            try { return DataFrame::make(std::move(out)); }
+            catch (const OracleError& e) { throw OracleError(std::string("DataFrame error: ") + e.what()); }
         }
     }
     return DataFrame();
@@ -1112,6 +1205,7 @@ DataStreamRef StreamingPhysicalPlan::execute() const {  // streaming.rs:70-133
             catch (const OracleError& e) { throw OracleError(std::string("Stream error: ") + e.what()); }
         }
         case Limit: return limit_stream(input->execute(), n);
+        case HashJoin: throw Panic("not yet implemented: Streaming hash join not yet implemented");   // streaming.rs:128-131
     }
     return nullptr;
 }
@@ -1184,6 +1278,11 @@ StreamingPhysicalPlan logical_to_streaming(const LogicalPlan& plan) {  // stream
             throw OracleError("Streaming planner error: Expression conversion error: Unsupported filter expression type: " + p.debug());
         }
         case LogicalPlan::Limit: return logical_to_streaming(*plan.input).limit(plan.n);  // :76-79
+        case LogicalPlan::Join: {  // :81-98, then streaming.rs:128-131: execute() is `todo!()`
+            (void)logical_to_streaming(*plan.input); (void)logical_to_streaming(*plan.right);
+            StreamingPhysicalPlan sp; sp.kind = StreamingPhysicalPlan::HashJoin;
+            return sp;
+        }
     }
     return StreamingPhysicalPlan();
 }
@@ -1211,6 +1310,12 @@ LazyFrame LazyFrame::filter(Expr p) const {  // builder.rs:66-73
 }
 LazyFrame LazyFrame::limit(size_t n) const {  // builder.rs:75-82
     LazyFrame lf; lf.plan.kind = LogicalPlan::Limit; lf.plan.input = std::make_shared<LogicalPlan>(plan); lf.plan.n = n; return lf;
+}
+
+LazyFrame LazyFrame::inner_join(const LazyFrame& right, std::string left_key, std::string right_key) const {  // builder.rs:84-94
+    LazyFrame lf; lf.plan.kind = LogicalPlan::Join; lf.plan.input = std::make_shared<LogicalPlan>(plan);
+    lf.plan.right = std::make_shared<LogicalPlan>(right.plan); lf.plan.left_key = std::move(left_key); lf.plan.right_key = std::move(right_key);
+    return lf;
 }
 
 DataFrame LazyFrame::collect() const {  // builder.rs:96-104

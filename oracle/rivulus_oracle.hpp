@@ -271,8 +271,10 @@ bool csv_reference_validity();
 // logical_plan/*, physical_plan/planner.rs, physical_plan/plan.rs, streaming_planner.rs
 // ---------------------------------------------------------------------------------------------
 
-struct LogicalPlan {  // logical_plan/plan.rs:8-39 (Join is out of scope)
-    enum Kind { DataFrameSource, Select, Filter, Limit, CsvFileSource } kind = DataFrameSource;
+struct LogicalPlan {  // logical_plan/plan.rs:8-39
+    enum Kind { DataFrameSource, Select, Filter, Limit, CsvFileSource, Join } kind = DataFrameSource;
+    std::shared_ptr<LogicalPlan> right;                   // Join :32-38 (`input` is the left side); JoinType::Inner only
+    std::string left_key, right_key;
     DataFrame df;                                         // DataFrameSource
     std::vector<std::pair<std::string, DataType>> src_schema;   // DataFrameSource, CsvFileSource
     std::string csv_path; std::optional<size_t> csv_batch_size; std::optional<std::string> csv_delimiter;  // CsvFileSource :14-19
@@ -303,7 +305,7 @@ void set_extensions(bool on);
 bool extensions_enabled();
 
 struct StreamingPhysicalPlan {
-    enum Kind { MemorySource, DataFrameSource, Filter, Select, Limit, FilterExpr, CsvFileSource } kind = MemorySource;
+    enum Kind { MemorySource, DataFrameSource, Filter, Select, Limit, FilterExpr, CsvFileSource, HashJoin } kind = MemorySource;
     Expr predicate;                            // FilterExpr (extension)
     std::string csv_path; SchemaRef csv_schema; std::optional<size_t> csv_batch_size; std::optional<std::string> csv_delimiter;  // CsvFileSource :39-44
     std::vector<RecordBatch> batches;          // MemorySource
@@ -335,6 +337,7 @@ struct LazyFrame {
     LazyFrame select(std::vector<Expr> e) const;           // :57-64
     LazyFrame filter(Expr p) const;                        // :66-73
     LazyFrame limit(size_t n) const;                       // :75-82
+    LazyFrame inner_join(const LazyFrame& right, std::string left_key, std::string right_key) const;   // :84-94
     DataFrame collect() const;                             // :96-104
     RecordBatch collect_streaming() const;                 // :106-113
 };

@@ -80,6 +80,7 @@ ABI_SYMBOLS = [
     "rvl_host_alloc", "rvl_host_free",
     "rvl_batch_upload", "rvl_batch_wrap_device", "rvl_batch_release", "rvl_batch_num_rows", "rvl_batch_num_columns",
     "rvl_batch_column", "rvl_batch_download_column", "rvl_batch_count_true", "rvl_boolean_op", "rvl_batch_slice", "rvl_batch_select", "rvl_batch_take", "rvl_batch_concat",
+    "rvl_hash_join_inner",
     "rvl_filter_project", "rvl_predicate_mask", "rvl_filter_project_launch", "rvl_filter_project_finish",
     "rvl_stream_open", "rvl_stream_push", "rvl_stream_flush", "rvl_stream_next", "rvl_stream_limit_reached", "rvl_stream_collect",
     "rvl_stream_stats", "rvl_stream_launches", "rvl_stream_close",
@@ -326,6 +327,17 @@ class Context:
     def filter_project_finish(self, pending) -> "Batch":
         out = C.c_void_p()
         check(lib().rvl_filter_project_finish(self._h, pending, C.byref(out)))
+        return Batch(self, out)
+
+    def hash_join_inner(self, build: "Batch", build_key: int, probe: "Batch", probe_key: int, probe_proj: Sequence[int], build_proj: Sequence[int],
+                        build_tag_column: int = 0, probe_tag_column: int = 0) -> "Batch":
+        """rvl_hash_join_inner (physical_plan/plan.rs:174-284): probe_proj columns then build_proj columns, one row per matching pair."""
+        pp = (C.c_int32 * max(len(probe_proj), 1))(*probe_proj)
+        bp = (C.c_int32 * max(len(build_proj), 1))(*build_proj)
+        out = C.c_void_p()
+        n = C.c_int64(0)
+        check(lib().rvl_hash_join_inner(self._h, build._h, build_key, build_tag_column, probe._h, probe_key, probe_tag_column,
+                                        pp, len(probe_proj), bp, len(build_proj), C.byref(out), C.byref(n)))
         return Batch(self, out)
 
     def predicate_mask(self, batch: "Batch", pred: RvlPredicate) -> "Batch":

@@ -656,22 +656,14 @@ int32_t rvl_batch_select(const rvl_batch* batch, const int32_t* indices, int32_t
     return RVL_OK;
 }
 
-int32_t rvl_batch_take(rvl_ctx* ctx, const rvl_batch* batch, const int64_t* indices, int64_t n, rvl_batch** out) {
-    if (!ctx || !batch || !out || n < 0 || (n > 0 && !indices)) return fail(RVL_INVALID_ARGUMENT, "null argument");
-    const CoreRef& core = ctx->core;
-    RVL_CUDA_TRY(cudaSetDevice(core->device));
-    for (int64_t i = 0; i < n; ++i)
-        if (indices[i] < 0 || indices[i] >= batch->num_rows)
-            return fail(RVL_OUT_OF_BOUNDS, "Index " + std::to_string(indices[i]) + " out of bounds for " + std::to_string(batch->num_rows) + " rows");  // record_batch.rs:111-114
-    auto res = std::make_unique<rvl_batch>();
-    res->core = core; res->num_rows = n;
-    BufRef didx;
-    RVL_TRY(dev_alloc(core, (size_t)std::max<int64_t>(n, 1) * 8, &didx));
-    if (n > 0) RVL_CUDA_TRY(cudaMemcpyAsync(didx->ptr, indices, (size_t)n * 8, cudaMemcpyHostToDevice, core->stream));
-    const int64_t* idx = (const int64_t*)didx->ptr;
+// take_array (record_batch.rs:131-178) of the listed columns of `batch` by a DEVICE index list, appended to `res` (whose num_rows is n).
+// Bitmaps are kept only when a taken row is null (primitive.rs:180-185).  Synchronises the stream.
+int rvl_internal_take_rows(const CoreRef& core, const rvl_batch* batch, const int32_t* cols, int32_t ncols, const int64_t* idx, int64_t n, rvl_batch* res) {
     const size_t wbytes = (size_t)((n + 31) / 32) * 4 + 8;
     const unsigned grid = (unsigned)std::max<int64_t>(1, (n + 255) / 256);
-    for (const DevColumn& s : batch->cols) {
+    const size_t first = res->cols.size();
+    for (int32_t ci = 0; ci < ncols; ++ci) {
+        const DevColumn& s = batch->cols[(size_t)(cols ? cols[ci] : ci)];
         DevColumn d;
         d.dtype = s.dtype; d.length = n; d.offset = 0; d.null_count = -1;
         const BitSrc sv = bitsrc_of(s.validity, s.offset, s.length);
@@ -728,12 +720,28 @@ int32_t rvl_batch_take(rvl_ctx* ctx, const rvl_batch* batch, const int64_t* indi
         RVL_CUDA_TRY(cudaGetLastError());
         res->cols.push_back(std::move(d));
     }
-    RVL_CUDA_TRY(cudaStreamSynchronize(core->stream));  // `indices` (host) and the index buffer may now be released
+    RVL_CUDA_TRY(cudaStreamSynchronize(core->stream));
     // the reference's builders keep a bitmap only when a taken row is null (primitive.rs:180-185)
-    for (size_t c = 0; c < res->cols.size(); ++c) {
-        RVL_TRY(ensure_null_count(res.get(), (int)c));
+    for (size_t c = first; c < res->cols.size(); ++c) {
+        RVL_TRY(ensure_null_count(res, (int)c));
         if (res->cols[c].null_count == 0) res->cols[c].validity.reset();
     }
+    return RVL_OK;
+}
+
+int32_t rvl_batch_take(rvl_ctx* ctx, const rvl_batch* batch, const int64_t* indices, int64_t n, rvl_batch** out) {
+    if (!ctx || !batch || !out || n < 0 || (n > 0 && !indices)) return fail(RVL_INVALID_ARGUMENT, "null argument");
+    const CoreRef& core = ctx->core;
+    RVL_CUDA_TRY(cudaSetDevice(core->device));
+    for (int64_t i = 0; i < n; ++i)
+        if (indices[i] < 0 || indices[i] >= batch->num_rows)
+            return fail(RVL_OUT_OF_BOUNDS, "Index " + std::to_string(indices[i]) + " out of bounds for " + std::to_string(batch->num_rows) + " rows");  // record_batch.rs:111-114
+    auto res = std::make_unique<rvl_batch>();
+    res->core = core; res->num_rows = n;
+    BufRef didx;
+    RVL_TRY(dev_alloc(core, (size_t)std::max<int64_t>(n, 1) * 8, &didx));
+    if (n > 0) RVL_CUDA_TRY(cudaMemcpyAsync(didx->ptr, indices, (size_t)n * 8, cudaMemcpyHostToDevice, core->stream));
+    RVL_TRY(rvl_internal_take_rows(core, batch, nullptr, (int32_t)batch->cols.size(), (const int64_t*)didx->ptr, n, res.get()));  // synchronises: `indices` may go
     *out = res.release();
     return RVL_OK;
 }

@@ -152,3 +152,8 @@ struct rvl_batch {
     int64_t num_rows = 0;
     std::vector<rvl::DevColumn> cols;
 };
+
+// runtime.cu: take_array (record_batch.rs:131-178) of the listed columns (all when cols == nullptr) by a DEVICE index list, appended to
+// `res`; synchronises the stream.  Internal (join.cu), not part of the ABI header.
+extern "C" int rvl_internal_take_rows(const rvl::CoreRef& core, const rvl_batch* batch, const int32_t* cols, int32_t ncols, const int64_t* idx,
+                                      int64_t n, rvl_batch* res);

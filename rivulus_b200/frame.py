@@ -42,7 +42,7 @@ HOST_SYMBOLS = [
     "rvh_dfb_add_strings", "rvh_dfb_finish", "rvh_synth_df", "rvh_df_free", "rvh_df_width", "rvh_df_height", "rvh_df_col_name", "rvh_df_col_dtype",
     "rvh_df_col_len", "rvh_df_col_str_bytes", "rvh_df_col_export", "rvh_df_col_buffers",
     "rvh_expr_col", "rvh_expr_lit", "rvh_expr_binary", "rvh_expr_alias", "rvh_expr_free",
-    "rvh_lf_from_df", "rvh_lf_from_csv", "rvh_set_csv_reference_validity", "rvh_set_csv_threads", "rvh_csv_adaptive_batch_size", "rvh_sp_csv_source", "rvh_csv_parse_dump", "rvh_free", "rvh_lf_select", "rvh_lf_filter", "rvh_lf_limit", "rvh_lf_free", "rvh_lf_collect", "rvh_lf_collect_streaming",
+    "rvh_lf_from_df", "rvh_lf_from_csv", "rvh_set_csv_reference_validity", "rvh_set_csv_threads", "rvh_csv_adaptive_batch_size", "rvh_sp_csv_source", "rvh_csv_parse_dump", "rvh_free", "rvh_lf_inner_join", "rvh_lf_select", "rvh_lf_filter", "rvh_lf_limit", "rvh_lf_free", "rvh_lf_collect", "rvh_lf_collect_streaming",
     "rvh_lf_plan_shape", "rvh_lf_schema", "rvh_lf_validate", "rvh_lf_describe",
     "rvh_rb_try_new", "rvh_rb_free", "rvh_rb_num_rows", "rvh_rb_num_columns", "rvh_rb_col_name", "rvh_rb_col_dtype", "rvh_rb_col_export",
     "rvh_rb_slice", "rvh_rb_take", "rvh_rb_select", "rvh_rb_select_by_name", "rvh_rb_filter", "rvh_rb_concat", "rvh_rb_empty_like",
@@ -72,7 +72,7 @@ def lib():
                               f"(or `make -C rivulus_b200/host`).  rivulus_b200 has no CPU fallback.")
         L = C.CDLL(HOST_LIB_PATH)
         L.rvh_last_error.restype = C.c_char_p
-        for name in ("rvh_dfb_new", "rvh_expr_col", "rvh_expr_lit", "rvh_expr_binary", "rvh_expr_alias", "rvh_lf_from_df", "rvh_lf_from_csv", "rvh_sp_csv_source", "rvh_lf_select",
+        for name in ("rvh_dfb_new", "rvh_expr_col", "rvh_expr_lit", "rvh_expr_binary", "rvh_expr_alias", "rvh_lf_from_df", "rvh_lf_from_csv", "rvh_sp_csv_source", "rvh_lf_inner_join", "rvh_lf_select",
                      "rvh_lf_filter", "rvh_lf_limit", "rvh_sp_memory_source", "rvh_sp_dataframe_source", "rvh_sp_filter", "rvh_sp_select",
                      "rvh_sp_limit", "rvh_rbv_get"):
             getattr(L, name).restype = C.c_void_p
@@ -371,6 +371,10 @@ class LazyFrame:
         dts = (C.c_int * max(len(schema), 1))(*[d for _, d in schema])
         return LazyFrame(lib().rvh_lf_from_csv(str(path).encode(), len(schema), names, dts, C.c_int64(-1 if batch_size is None else batch_size),
                                                None if delimiter is None else delimiter.encode()))
+
+    def inner_join(self, right: "LazyFrame", left_key: str, right_key: str):
+        """builder.rs:84-94"""
+        return LazyFrame(lib().rvh_lf_inner_join(_vp(self._h), _vp(right._h), left_key.encode(), right_key.encode()))
 
     def select(self, exprs: List[Expr]):
         arr = (C.c_void_p * max(len(exprs), 1))(*[e._h for e in exprs])

@@ -253,6 +253,9 @@ void* rvh_lf_select(void* lf, int n, void** exprs) {
     return new LazyFrame(((LazyFrame*)lf)->select(std::move(e)));
 }
 void* rvh_lf_filter(void* lf, void* pred) { return new LazyFrame(((LazyFrame*)lf)->filter(*(Expr*)pred)); }
+void* rvh_lf_inner_join(void* lf, void* right, const char* left_key, const char* right_key) {
+    return new LazyFrame(((LazyFrame*)lf)->inner_join(*(LazyFrame*)right, left_key, right_key));
+}
 void* rvh_lf_limit(void* lf, int64_t n) { return new LazyFrame(((LazyFrame*)lf)->limit((size_t)n)); }
 void rvh_lf_free(void* lf) { delete (LazyFrame*)lf; }
 int rvh_lf_collect(void* lf, void** df_out) {

@@ -887,6 +887,7 @@ static DataStreamRef build_stream(const StreamingPhysicalPlan& p, size_t min_bat
             catch (const Error& e) { if (e.panic) throw; throw Error(std::string("Stream error: ") + e.what()); }
         }
         case K::Limit: return make_limit_stream(build_stream(*p.input, min_batch_rows), p.n);
+        case K::HashJoin: throw Error("not yet implemented: Streaming hash join not yet implemented", true);   // streaming.rs:128-131
     }
     return nullptr;
 }
@@ -1101,8 +1102,25 @@ SchemaVec LogicalPlan::schema() const {  // logical_plan/plan.rs:63-113
             return out;
         }
         case Filter: case Limit: return input->schema();
+        case Join: {  // :79-111: the left schema, then the right columns except the right key, "_right" on a name the left side has
+            const auto left = input->schema();
+            SchemaVec out = left;
+            for (const auto& rc : right->schema()) {
+                if (rc.first == right_key) continue;
+                bool clash = false;
+                for (const auto& lc : left) clash = clash || lc.first == rc.first;
+                out.emplace_back(clash ? rc.first + "_right" : rc.first, rc.second);
+            }
+            return out;
+        }
     }
     return {};
+}
+
+static bool is_comparable_with(DataType a, DataType b) {  // series.rs:144-159
+    if (a == b) return true;
+    if ((a == DataType::Int64 && b == DataType::Float64) || (a == DataType::Float64 && b == DataType::Int64)) return true;
+    return a == DataType::Null || b == DataType::Null;
 }
 
 static void validate_expr_columns(const Expr& e, const SchemaVec& schema) {  // logical_plan/plan.rs:264-286
@@ -1134,6 +1152,19 @@ void LogicalPlan::validate() const {  // logical_plan/plan.rs:115-202
         case Filter: input->validate(); validate_expr_columns(predicate, input->schema()); break;
         case Limit: input->validate(); break;
         case CsvFileSource: break;   // :128
+        case Join: {  // :156-200 — the right side is validated first
+            right->validate();
+            input->validate();
+            const auto ls = input->schema(), rs = right->schema();
+            const DataType* lt = nullptr; const DataType* rt = nullptr;
+            for (const auto& c : ls) if (c.first == left_key && !lt) lt = &c.second;
+            if (!lt) throw Error("Logical plan error: Column not found: '" + left_key + "'");
+            for (const auto& c : rs) if (c.first == right_key && !rt) rt = &c.second;
+            if (!rt) throw Error("Logical plan error: Column not found: '" + right_key + "'");
+            if (!is_comparable_with(*lt, *rt))
+                throw Error(std::string("Logical plan error: Incompatible join key types: '") + dtype_name(*lt) + "' and '" + dtype_name(*rt) + "'");
+            break;
+        }
     }
 }
 
@@ -1141,6 +1172,7 @@ std::string LogicalPlan::shape() const {
     switch (kind) {
         case DataFrameSource: return "Source";
         case CsvFileSource: return "CsvSource";
+        case Join: return "Join(" + input->shape() + ", " + right->shape() + ")";
         case Select: return "Select(" + input->shape() + ")";
         case Filter: return "Filter(" + input->shape() + ")";
         case Limit: return "Limit(" + input->shape() + ")";
@@ -1152,6 +1184,9 @@ std::string LogicalPlan::describe() const {
     switch (kind) {
         case DataFrameSource: return "DataFrameSource";
         case CsvFileSource: return "CsvFileSource { path: \"" + csv_path + "\" }";
+        case Join:
+            return "Join { left: " + input->describe() + ", right: " + right->describe() + ", left_key: \"" + left_key + "\", right_key: \"" + right_key +
+                   "\", join_type: Inner }";
         case Select: {
             std::string e;
             for (size_t i = 0; i < expressions.size(); ++i) e += (i ? ", " : "") + expressions[i].debug();
@@ -1202,6 +1237,12 @@ LogicalPlan optimize(LogicalPlan plan) {  // optimizer.rs:15-64 (push_predicates
         case LogicalPlan::Filter: {
             LogicalPlan out = plan;
             out.input = std::make_shared<LogicalPlan>(optimize(*plan.input));
+            return out;
+        }
+        case LogicalPlan::Join: {  // optimizer.rs:50-61
+            LogicalPlan out = plan;
+            out.input = std::make_shared<LogicalPlan>(optimize(*plan.input));
+            out.right = std::make_shared<LogicalPlan>(optimize(*plan.right));
             return out;
         }
         default: return plan;  // Limit and sources are left untouched (optimizer.rs:62)
@@ -1264,6 +1305,7 @@ static void check_lowering(const LogicalPlan& p) {  // logical_to_physical runs 
             else convert_filter_predicate(p.predicate);
             return;
         case LogicalPlan::Limit: check_lowering(*p.input); return;
+        case LogicalPlan::Join: check_lowering(*p.input); check_lowering(*p.right); return;   // planner.rs:97-98: left, then right
     }
 }
 
@@ -1568,6 +1610,66 @@ Frame exec_node(const ContextRef& ctx, const LogicalPlan& p) {  // physical_plan
             for (size_t j = 0; j < in.names.size(); ++j) r.dtypes.push_back(inferred_dtype(r.rb, j, in.dtypes[j], lim, in.tag_col[j]));
             return r;
         }
+        case LogicalPlan::Join: {  // HashJoin, plan.rs:174-284: build = left, probe = right (planner.rs:100-108)
+            const Frame build = exec_node(ctx, *p.input);
+            int bkey = -1, pkey = -1;
+            for (size_t i = 0; i < build.names.size(); ++i) if (build.names[i] == p.left_key) { bkey = (int)i; break; }
+            if (bkey < 0) throw Error("called `Option::unwrap()` on a `None` value", true);   // :183
+            const Frame probe = exec_node(ctx, *p.right);
+            for (size_t i = 0; i < probe.names.size(); ++i) if (probe.names[i] == p.right_key) { pkey = (int)i; break; }
+            if (pkey < 0) throw Error("called `Option::unwrap()` on a `None` value", true);   // :196
+            // device columns asked of each side: the visible ones (the build side without its key), then their hidden tag columns
+            std::vector<int32_t> pproj, bproj;
+            std::vector<size_t> pvis, bvis;
+            for (size_t i = 0; i < probe.names.size(); ++i) { pvis.push_back(i); pproj.push_back((int32_t)i); }
+            for (size_t i = 0; i < build.names.size(); ++i) if ((int)i != bkey) { bvis.push_back(i); bproj.push_back((int32_t)i); }
+            std::vector<int> ptag(pvis.size(), -1), btag(bvis.size(), -1);   // position of the tag column inside pproj / bproj
+            for (size_t j = 0; j < pvis.size(); ++j) if (probe.tag_col[pvis[j]] >= 0) { ptag[j] = (int)pproj.size(); pproj.push_back(probe.tag_col[pvis[j]]); }
+            for (size_t j = 0; j < bvis.size(); ++j) if (build.tag_col[bvis[j]] >= 0) { btag[j] = (int)bproj.size(); bproj.push_back(build.tag_col[bvis[j]]); }
+            rvl_batch* out = nullptr;
+            int64_t n_pairs = 0;
+            check(rvl_hash_join_inner(ctx->handle(), build.rb.handle(), bkey, build.tag_col[(size_t)bkey] >= 0 ? build.tag_col[(size_t)bkey] + 1 : 0,
+                                      probe.rb.handle(), pkey, probe.tag_col[(size_t)pkey] >= 0 ? probe.tag_col[(size_t)pkey] + 1 : 0,
+                                      pproj.data(), (int32_t)pproj.size(), bproj.data(), (int32_t)bproj.size(), &out, &n_pairs));
+            // joined batch = [probe visible | probe tags | build visible | build tags]  ->  frame order [visible ... | tags ...]
+            auto jschema = std::make_shared<Schema>();
+            for (int32_t c : pproj) jschema->fields.push_back(probe.rb.schema()->fields[(size_t)c]);
+            for (int32_t c : bproj) jschema->fields.push_back(build.rb.schema()->fields[(size_t)c]);
+            RecordBatch joined = RecordBatch::adopt(ctx, jschema, out);
+            Frame r;
+            r.rows = (size_t)n_pairs;
+            std::vector<size_t> order;
+            std::vector<std::pair<size_t, int>> tags;   // (visible position, column of `joined`)
+            const size_t pbase = 0, bbase = pproj.size();
+            for (size_t j = 0; j < pvis.size(); ++j) {
+                r.names.push_back(probe.names[pvis[j]]); r.dtypes.push_back(probe.dtypes[pvis[j]]);
+                order.push_back(pbase + j);
+                if (ptag[j] >= 0) tags.emplace_back(r.names.size() - 1, (int)(pbase + (size_t)ptag[j]));
+            }
+            for (size_t j = 0; j < bvis.size(); ++j) {
+                bool clash = false;   // :237-241: "_right" on a build column whose name the probe side has
+                for (const auto& n : probe.names) clash = clash || n == build.names[bvis[j]];
+                r.names.push_back(clash ? build.names[bvis[j]] + "_right" : build.names[bvis[j]]); r.dtypes.push_back(build.dtypes[bvis[j]]);
+                order.push_back(bbase + j);
+                if (btag[j] >= 0) tags.emplace_back(r.names.size() - 1, (int)(bbase + (size_t)btag[j]));
+            }
+            r.tag_col.assign(r.names.size(), -1);
+            for (const auto& t : tags) { r.tag_col[t.first] = (int)order.size(); order.push_back((size_t)t.second); }
+            r.rb = joined.select_columns(order);
+            auto schema = std::make_shared<Schema>();
+            for (size_t j = 0; j < order.size(); ++j) {
+                Field f = jschema->fields[order[j]];
+                if (j < r.names.size()) f.name = r.names[j];
+                schema->fields.push_back(f);
+            }
+            r.rb = r.rb.with_schema(schema);
+            // Series::new re-infers every dtype from the gathered values (:225, :243); no pairs: Series::empty keeps them (:256-283)
+            if (n_pairs > 0)
+                for (size_t j = 0; j < r.names.size(); ++j) r.dtypes[j] = inferred_dtype(r.rb, j, r.dtypes[j], r.rows, r.tag_col[j]);
+            std::set<std::string> seen;   // DataFrame::new (:253)
+            for (const auto& n : r.names) if (!seen.insert(n).second) throw Error("DataFrame error: Duplicate column name: '" + n + "'");
+            return r;
+        }
     }
     return Frame();
 }
@@ -1625,6 +1727,11 @@ StreamingPhysicalPlan logical_to_streaming(const LogicalPlan& plan, const Contex
             throw Error("Streaming planner error: Expression conversion error: Unsupported filter expression type: " + p.debug());
         }
         case LogicalPlan::Limit: return logical_to_streaming(*plan.input, ctx).limit(plan.n);  // :76-79
+        case LogicalPlan::Join: {  // :81-98; executing the node is `todo!()` in the reference (streaming.rs:128-131)
+            (void)logical_to_streaming(*plan.input, ctx); (void)logical_to_streaming(*plan.right, ctx);
+            StreamingPhysicalPlan sp; sp.kind = StreamingPhysicalPlan::HashJoin; sp.ctx = ctx;
+            return sp;
+        }
     }
     return StreamingPhysicalPlan();
 }
@@ -1655,6 +1762,12 @@ LazyFrame LazyFrame::filter(Expr p) const {
 }
 LazyFrame LazyFrame::limit(size_t n) const {
     LazyFrame lf; lf.ctx_ = ctx_; lf.plan_.kind = LogicalPlan::Limit; lf.plan_.input = std::make_shared<LogicalPlan>(plan_); lf.plan_.n = n; return lf;
+}
+
+LazyFrame LazyFrame::inner_join(const LazyFrame& right, std::string left_key, std::string right_key) const {  // builder.rs:84-94
+    LazyFrame lf; lf.ctx_ = ctx_; lf.plan_.kind = LogicalPlan::Join; lf.plan_.input = std::make_shared<LogicalPlan>(plan_);
+    lf.plan_.right = std::make_shared<LogicalPlan>(right.plan_); lf.plan_.left_key = std::move(left_key); lf.plan_.right_key = std::move(right_key);
+    return lf;
 }
 
 DataFrame LazyFrame::collect() const {  // builder.rs:96-104

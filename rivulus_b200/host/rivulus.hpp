@@ -336,7 +336,7 @@ DataStreamRef make_csv_file_stream(const ContextRef& ctx, const std::string& pat
 std::vector<RecordBatch> dataframe_to_batches(const ContextRef& ctx, const DataFrame& df, size_t batch_size);
 
 struct StreamingPhysicalPlan {  // streaming.rs:28-68, 290-333
-    enum Kind { MemorySource, DataFrameSource, Filter, Select, Limit, FilterExpr, CsvFileSource } kind = MemorySource;
+    enum Kind { MemorySource, DataFrameSource, Filter, Select, Limit, FilterExpr, CsvFileSource, HashJoin } kind = MemorySource;
     Expr predicate;   // FilterExpr (opt-in extension, see set_extensions)
     std::string csv_path; SchemaRef csv_schema; std::optional<size_t> csv_batch_size; std::optional<std::string> csv_delimiter;  // :39-44
     std::vector<RecordBatch> batches;
@@ -375,8 +375,10 @@ void set_extensions(bool on);
 bool extensions_enabled();
 
 // ---------------------------------------------------------------------------------------- logical_plan/*
-struct LogicalPlan {  // logical_plan/plan.rs:8-39 (Join: out of scope)
-    enum Kind { DataFrameSource, Select, Filter, Limit, CsvFileSource } kind = DataFrameSource;
+struct LogicalPlan {  // logical_plan/plan.rs:8-39
+    enum Kind { DataFrameSource, Select, Filter, Limit, CsvFileSource, Join } kind = DataFrameSource;
+    std::shared_ptr<LogicalPlan> right;                 // Join :32-38 (`input` is the left side); JoinType::Inner only
+    std::string left_key, right_key;
     DataFrame df;
     std::vector<std::pair<std::string, DataType>> src_schema;   // DataFrameSource, CsvFileSource
     std::string csv_path; std::optional<size_t> csv_batch_size; std::optional<std::string> csv_delimiter;   // CsvFileSource :14-19
@@ -401,6 +403,7 @@ class LazyFrame {  // logical_plan/builder.rs:11-114
     LazyFrame select(std::vector<Expr> exprs) const;   // :57-64
     LazyFrame filter(Expr predicate) const;            // :66-73
     LazyFrame limit(size_t n) const;                   // :75-82
+    LazyFrame inner_join(const LazyFrame& right, std::string left_key, std::string right_key) const;   // :84-94
     DataFrame collect() const;                         // :96-104   eager engine semantics, on the GPU
     RecordBatch collect_streaming() const;             // :106-113  streaming engine semantics, on the GPU
     const LogicalPlan& logical_plan() const { return plan_; }

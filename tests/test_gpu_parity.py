@@ -704,3 +704,40 @@ def test_boolean_ops_random_views_and_compound_predicate(ctx):
     for j in range(3):
         assert got.checksum(j) == want.checksum(j)
 
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("keytype", ["i64", "str"])
+def test_hash_join_inner_large(keytype):
+    """rvl_hash_join_inner through the C ABI at a size the Python model still handles: 300 K build rows x 500 K probe rows, skewed keys
+    with nulls on both sides; pairs must come out in probe order, build order within a probe row (plan.rs:198-205)."""
+    rng = np.random.default_rng(77)
+    nb, npr = 300_000, 500_000
+    ctx = capi.Context(0)
+    bkeys = rng.integers(0, 200_000, nb).astype(np.int64)
+    pkeys = rng.integers(0, 220_000, npr).astype(np.int64)
+    bkeys[rng.random(nb) < 0.05] = 7            # a heavy key
+    bvalid, pvalid = rng.random(nb) > 0.02, rng.random(npr) > 0.02
+    bpay, ppay = np.arange(nb, dtype=np.int64), np.arange(npr, dtype=np.int64) * 3
+    if keytype == "i64":
+        bcol = capi.Column(capi.INT64, nb, 0, bkeys, capi.pack_bits(bvalid))
+        pcol = capi.Column(capi.INT64, npr, 0, pkeys, capi.pack_bits(pvalid))
+    else:
+        bcol = capi.Column.from_list([("k%d" % k) if v else None for k, v in zip(bkeys, bvalid)], capi.STRING)
+        pcol = capi.Column.from_list([("k%d" % k) if v else None for k, v in zip(pkeys, pvalid)], capi.STRING)
+    build = ctx.upload([bcol, capi.Column(capi.INT64, nb, 0, bpay)])
+    probe = ctx.upload([pcol, capi.Column(capi.INT64, npr, 0, ppay)])
+    before = ctx.launch_count()
+    out = ctx.hash_join_inner(build, 0, probe, 0, [1], [1])
+    assert ctx.launch_count() > before
+    got = out.download()
+    # model: dict of build rows per key (None = null key), probe order
+    table = {}
+    for i in range(nb):
+        table.setdefault(int(bkeys[i]) if bvalid[i] else None, []).append(i)
+    wp, wb = [], []
+    for i in range(npr):
+        for b in table.get(int(pkeys[i]) if pvalid[i] else None, ()):
+            wp.append(i); wb.append(b)
+    assert out.num_rows() == len(wp)
+    assert np.array_equal(got[0].values, ppay[np.array(wp)]) and np.array_equal(got[1].values, bpay[np.array(wb)])

@@ -86,6 +86,7 @@ GPU_TESTS = [
     "test_extension_compound_and_streaming_comparison_predicates",
     "test_csv_file_stream_basic_and_nulls", "test_csv_empty_file", "test_csv_main_demo_query", "test_csv_parse_rules", "test_csv_errors",
     "test_csv_filter_select_limit_and_validity_modes",
+    "test_join_main_demo_queries", "test_join_plan_errors", "test_join_key_semantics",
 ]
 
 
@@ -227,6 +228,53 @@ def test_random_streaming_queries_match_oracle(seed):
         want = _outcome(O, O.OracleError, build)
         got = _outcome(F, F.RivulusError, build)
         assert got == want, (seed, q, sel, lim, fcol, shape)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(6))
+def test_random_joins_match_oracle(seed):
+    """LazyFrame.inner_join(...).collect() — sort / search / gather on the device against the oracle's
+    HashMap<AnyValue, Vec<usize>> restatement (plan.rs:174-284): every key type incl. nulls, NaN, duplicate keys on both sides, the
+    mixed Int64 / Float64 series, joins on top of filters, selects and limits, name clashes, empty sides and empty results."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(1300 + seed)
+
+    def maybe(v, p=0.12):
+        return None if rng.random() < p else v
+
+    def side(n, tagname):
+        return [
+            ("ki", [maybe(int(rng.integers(0, 12))) for _ in range(n)]),
+            ("kf", [maybe(float(rng.choice([0.5, 1.5, 2.5, float("nan"), 1e300, -7.25]))) for _ in range(n)]),
+            ("ks", [maybe(str(rng.choice(["", "a", "bb", "ccc", "a" * 40, "Zoë"]))) for _ in range(n)]),
+            ("kb", [maybe(bool(rng.integers(0, 2))) for _ in range(n)]),
+            ("km", [maybe(float(rng.integers(0, 4)) if rng.random() < 0.5 else int(rng.integers(0, 4))) for _ in range(n)]),
+            ("kz", [None] * n),
+            (tagname, [int(i) for i in range(n)]),
+            ("pay", [maybe("p%d" % i, 0.3) for i in range(n)]),
+        ]
+    nl, nr = int(rng.choice([1, 9, 60, 400])), int(rng.choice([1, 7, 80, 300]))
+    left, right = side(nl, "lrow"), side(nr, "rrow")
+    keys = ["ki", "kf", "ks", "kb", "km", "kz"]
+    for q in range(14):
+        lk, rk = str(rng.choice(keys)), str(rng.choice(keys))
+        if rng.random() < 0.6:
+            rk = lk
+        shape = int(rng.integers(0, 5))
+
+        def build(mod, lk=lk, rk=rk, shape=shape):
+            l = mod.LazyFrame.from_dataframe(mod.DataFrame.new(left))
+            r = mod.LazyFrame.from_dataframe(mod.DataFrame.new(right))
+            if shape == 1: l = l.filter(mod.col("lrow").gte(mod.lit(nl // 2)))
+            if shape == 2: r = r.select([mod.col(rk), mod.col("rrow")]).limit(max(nr // 2, 1))
+            j = l.inner_join(r, lk, rk)
+            if shape == 3: j = j.select([mod.col("lrow"), mod.col("rrow")]).limit(50)
+            if shape == 4: j = j.filter(mod.col("rrow").lt(mod.lit(nr // 2)))
+            return j.collect()
+
+        want = _outcome(O, O.OracleError, build)
+        got = _outcome(F, F.RivulusError, build)
+        assert got == want, (seed, q, nl, nr, lk, rk, shape)
 
 
 def _random_csv_text(rng, n, bad_line=None):

@@ -834,3 +834,86 @@ def test_csv_filter_select_limit_and_validity_modes():
         assert small.column(1).to_list() == exp
     finally:
         set_csv_reference_validity(False)
+
+
+# ---------------------------------------------------------------- inner join: physical_plan/plan.rs:174-284
+def users_orders():  # main.rs:120-165
+    users = DataFrame.new([("user_id", [1, 2, 3, 4]), ("name", ["Alice", "Bob", "Charlie", "Diana"]), ("city", ["Rome", "Milan", "Naples", "Turin"])])
+    orders = DataFrame.new([("order_id", [101, 102, 103, 104, 105]), ("user_id", [1, 2, 1, 3, 2]), ("amount", [29.99, 15.5, 45.0, 8.75, 12.99])])
+    return users, orders
+
+
+def test_join_main_demo_queries():  # main.rs:170-196
+    users, orders = users_orders()
+    lf = LazyFrame.from_dataframe(users).inner_join(LazyFrame.from_dataframe(orders), "user_id", "user_id")
+    r = lf.collect()
+    # the probe (right) side's columns come first, then the build (left) side's without its key (plan.rs:218-250); rows in probe order
+    assert r.column_names() == ["order_id", "user_id", "amount", "name", "city"]
+    assert r.to_dict() == {"order_id": [101, 102, 103, 104, 105], "user_id": [1, 2, 1, 3, 2], "amount": [29.99, 15.5, 45.0, 8.75, 12.99],
+                           "name": ["Alice", "Bob", "Alice", "Charlie", "Bob"], "city": ["Rome", "Milan", "Rome", "Naples", "Milan"]}
+    r = lf.select([col("name"), col("amount"), col("city")]).collect()                       # main.rs:186-196
+    assert r.to_dict() == {"name": ["Alice", "Bob", "Alice", "Charlie", "Bob"], "amount": [29.99, 15.5, 45.0, 8.75, 12.99],
+                           "city": ["Rome", "Milan", "Rome", "Naples", "Milan"]}
+    # logical schema (logical_plan/plan.rs:79-111): left columns, then the right ones without the right key
+    assert lf.schema() == [("user_id", "Int64"), ("name", "String"), ("city", "String"), ("order_id", "Int64"), ("amount", "Float64")]
+    assert lf.plan_shape() == "Join(Source, Source)"
+    assert lf.describe() == 'Join { left: DataFrameSource, right: DataFrameSource, left_key: "user_id", right_key: "user_id", join_type: Inner }'
+    # the optimizer recurses into both sides (optimizer.rs:50-61)
+    lf2 = LazyFrame.from_dataframe(users).filter(col("user_id").gt(lit(1))).select([col("user_id"), col("name")]) \
+        .inner_join(LazyFrame.from_dataframe(orders).filter(col("amount").gt(lit(10.0))), "user_id", "user_id")
+    assert lf2.plan_shape() == "Join(Filter(Select(Source)), Filter(Source))"
+    assert lf2.collect().to_dict() == {"order_id": [102, 105], "user_id": [2, 2], "amount": [15.5, 12.99], "name": ["Bob", "Bob"]}
+
+
+def test_join_plan_errors():  # logical_plan/plan.rs:156-200, physical_plan/streaming.rs:128-131
+    users, orders = users_orders()
+    lu, lo = LazyFrame.from_dataframe(users), LazyFrame.from_dataframe(orders)
+    with pytest.raises(OracleError, match="Logical plan error: Column not found: 'nope'"):
+        lu.inner_join(lo, "nope", "user_id").collect()
+    with pytest.raises(OracleError, match="Logical plan error: Column not found: 'missing'"):
+        lu.inner_join(lo, "user_id", "missing").collect()
+    with pytest.raises(OracleError, match="Logical plan error: Incompatible join key types: 'String' and 'Int64'"):
+        lu.inner_join(lo, "name", "user_id").collect()
+    lu.inner_join(lo, "user_id", "amount").validate()                      # Int64 with Float64 is "comparable" (series.rs:150-151) ...
+    assert lu.inner_join(lo, "user_id", "amount").collect().height() == 0  # ... but an Int64 never equals a Float64 (series.rs:87-98)
+    with pytest.raises(OracleError, match="not yet implemented: Streaming hash join not yet implemented"):
+        lu.inner_join(lo, "user_id", "user_id").collect_streaming()
+    # a key column on both sides with the same non-key name: "_right" goes on the BUILD (left) column (plan.rs:237-241)
+    a = DataFrame.new([("k", [1, 2]), ("v", [10, 20])])
+    b = DataFrame.new([("k", [2, 1, 2]), ("v", [7.5, 8.5, 9.5])])
+    r = LazyFrame.from_dataframe(a).inner_join(LazyFrame.from_dataframe(b), "k", "k").collect()
+    assert r.column_names() == ["k", "v", "v_right"] and r.to_dict() == {"k": [2, 1, 2], "v": [7.5, 8.5, 9.5], "v_right": [20, 10, 20]}
+    # different key names: the probe keeps its key, the build key is dropped; a clash with the generated name is a DataFrame error
+    c = DataFrame.new([("id", [1, 2]), ("v", [1, 2]), ("v_right", [3, 4])])
+    with pytest.raises(OracleError, match="Execution error: DataFrame error: Duplicate column name: 'v_right'"):
+        LazyFrame.from_dataframe(a).inner_join(LazyFrame.from_dataframe(c), "k", "id").collect()
+
+
+def test_join_key_semantics():  # HashMap<AnyValue, Vec<usize>> (plan.rs:186-205) with AnyValue's Hash / Eq (series.rs:73-98) — code reading
+    nan = float("nan")
+    left = DataFrame.new([("k", [1, None, 2, 1, None]), ("l", ["a", "b", "c", "d", "e"])])
+    right = DataFrame.new([("k", [None, 1, 3, 2]), ("r", [10.0, 20.0, 30.0, 40.0])])
+    r = LazyFrame.from_dataframe(left).inner_join(LazyFrame.from_dataframe(right), "k", "k").collect()
+    # Null == Null (series.rs:89); every probe row meets its build rows in ascending build order
+    assert r.to_dict() == {"k": [None, None, 1, 1, 2], "r": [10.0, 10.0, 20.0, 20.0, 40.0], "l": ["b", "e", "a", "d", "c"]}
+    # Float64 keys: bit-equal values meet, NaN meets nothing; an all-null result column collapses to dtype Null (Series::new)
+    fl = DataFrame.new([("x", [1.5, nan, 2.5, None]), ("tag", [None, None, "t", None])])
+    fr = DataFrame.new([("x", [nan, 1.5, None, 1.5])])
+    r = LazyFrame.from_dataframe(fl).inner_join(LazyFrame.from_dataframe(fr), "x", "x").collect()
+    assert r.height() == 3 and r.column("tag") == [None, None, None] and r.dtypes() == ["Float64", "Null"]
+    assert [v for v in r.column("x")] == [1.5, None, 1.5]
+    # String and Boolean keys
+    sl = DataFrame.new([("s", ["x", "yy", "x", "", None]), ("n", [1, 2, 3, 4, 5])])
+    sr = DataFrame.new([("s", ["yy", "", "zzz", "x"]), ("b", [True, False, True, None])])
+    r = LazyFrame.from_dataframe(sl).inner_join(LazyFrame.from_dataframe(sr), "s", "s").collect()
+    assert r.to_dict() == {"s": ["yy", "", "x", "x"], "b": [True, False, None, None], "n": [2, 4, 1, 3]}
+    r = LazyFrame.from_dataframe(sr).inner_join(LazyFrame.from_dataframe(sr), "b", "b").select([col("s"), col("s_right")]).collect()
+    assert r.to_dict() == {"s": ["yy", "yy", "", "zzz", "zzz", "x"], "s_right": ["yy", "zzz", "", "yy", "zzz", "x"]}
+    # no pair at all: empty series keep their dtypes (create_empty_join_result, plan.rs:256-283)
+    r = LazyFrame.from_dataframe(left).inner_join(LazyFrame.from_dataframe(DataFrame.new([("k", [7, 8]), ("z", ["p", "q"])])), "k", "k").collect()
+    assert (r.height(), r.column_names(), r.dtypes()) == (0, ["k", "z", "l"], ["Int64", "String", "String"])
+    # a Float64 Series holding Int64 values (series.rs:210-212): every row keeps its own type as a key
+    ml = DataFrame.new([("m", [1.0, 1, 2.0, 2]), ("i", [0, 1, 2, 3])])
+    mr = DataFrame.new([("m", [1, 2.0, 3])])
+    r = LazyFrame.from_dataframe(ml).inner_join(LazyFrame.from_dataframe(mr), "m", "m").collect()
+    assert r.to_dict()["i"] == [1, 2]

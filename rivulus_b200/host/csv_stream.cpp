@@ -183,8 +183,8 @@ struct alignas(128) ColumnBuf {  // one column of the batch being parsed, Arrow 
 // (alignas + locals in the parse loop: two jobs that share a cache line — one worker's per-row progress store next to the vector
 // headers another worker reads on every row — doubled the parse time of concurrent batches)
 struct alignas(128) CsvJob {
-    std::vector<char> text;            // the batch's non-blank lines, terminators stripped, back to back
-    std::vector<uint32_t> starts;      // start of every line in `text` + one end sentinel
+    std::vector<char> text;            // the file bytes the batch was cut from (whole buffer spans)
+    std::vector<uint32_t> starts, lens;   // offset and length in `text` of every data line, terminator excluded
     std::vector<uint64_t> line_no;     // 1-based number of every line in the file (header = 1, blank lines count)
     std::string read_error;            // set when reading the file failed after these lines: surfaces instead of the batch
     std::vector<ColumnBuf> cols;
@@ -211,12 +211,19 @@ void park_job(std::unique_ptr<CsvJob> j) {
     if (g_job_pool.size() < kJobPoolMax) g_job_pool.push_back(std::move(j));
 }
 
+// What the parse workers read on every field.  It lives in its own allocation, written once: the reader's cursor (line counter,
+// buffer positions) changes on every line in the caller's thread, and sharing a cache line with it made every worker ~4x slower.
+struct alignas(128) CsvParseConfig {
+    std::string delim = ",";
+    std::vector<ExecType> types;
+};
+
 struct CsvBatchReader::Impl {
     int fd = -1;
+    std::shared_ptr<const CsvParseConfig> cfg;
     SchemaRef schema;
     size_t batch_size = 0, current_line = 0;
     bool finished = false, eof = false, failed = false;
-    std::string delim = ",";
     std::vector<char> buf; size_t pos = 0, end = 0;   // unread bytes are buf[pos, end)
     // pipeline
     std::vector<std::thread> workers;
@@ -239,20 +246,22 @@ struct CsvBatchReader::Impl {
         for (auto& j : spare) park_job(std::move(j));
     }
 
-    // the next line including its '\n' (BufRead::read_line); false at end of file; throws std::string on an I/O error
-    bool next_line(const char** p, size_t* n) {
+    // a complete line inside the buffer, including its '\n' (BufRead::read_line), or the unterminated rest of the file once EOF is seen
+    bool find_line(const char** p, size_t* n) {
+        if (pos < end) {
+            const char* nl = (const char*)std::memchr(buf.data() + pos, '\n', end - pos);
+            if (nl) { *p = buf.data() + pos; *n = (size_t)(nl - (buf.data() + pos)) + 1; pos += *n; return true; }
+            if (eof) { *p = buf.data() + pos; *n = end - pos; pos = end; return true; }   // last line without a newline
+        }
+        return false;
+    }
+    // more bytes behind the partial line; false when the file is exhausted.  Invalidates pointers into the buffer.
+    // Throws std::string on an I/O error.
+    bool refill() {
+        if (eof) return false;
+        if (pos > 0) { std::memmove(buf.data(), buf.data() + pos, end - pos); end -= pos; pos = 0; }
+        if (end == buf.size()) buf.resize(buf.size() * 2);
         for (;;) {
-            if (pos < end) {
-                const char* nl = (const char*)std::memchr(buf.data() + pos, '\n', end - pos);
-                if (nl) { *p = buf.data() + pos; *n = (size_t)(nl - (buf.data() + pos)) + 1; pos += *n; return true; }
-            }
-            if (eof) {
-                if (pos == end) return false;
-                *p = buf.data() + pos; *n = end - pos; pos = end; return true;   // last line without a newline
-            }
-            // refill: keep the partial line, read more behind it
-            if (pos > 0) { std::memmove(buf.data(), buf.data() + pos, end - pos); end -= pos; pos = 0; }
-            if (end == buf.size()) buf.resize(buf.size() * 2);
             const ssize_t got = ::read(fd, buf.data() + end, buf.size() - end);
             if (got < 0) {
                 if (errno == EINTR) continue;
@@ -260,6 +269,13 @@ struct CsvBatchReader::Impl {
                 throw std::string(std::strerror(e)) + " (os error " + std::to_string(e) + ")";
             }
             if (got == 0) eof = true; else end += (size_t)got;
+            return true;
+        }
+    }
+    bool next_line(const char** p, size_t* n) {
+        for (;;) {
+            if (find_line(p, n)) return true;
+            if (!refill()) return false;
         }
     }
 
@@ -275,37 +291,46 @@ struct CsvBatchReader::Impl {
 
     // stage 1: the text of the next `batch_size` data lines.  False when the file is exhausted and the job holds nothing.
     bool fill(CsvJob& j) {
-        j.text.clear(); j.starts.clear(); j.line_no.clear(); j.read_error.clear(); j.parse_error.clear(); j.rows = 0; j.done = false;
+        j.text.clear(); j.starts.clear(); j.lens.clear(); j.line_no.clear(); j.read_error.clear(); j.parse_error.clear(); j.rows = 0; j.done = false;
         if (finished) return false;
         // size a fresh job like the last one: growing a multi-megabyte vector step by step is a chain of mremap calls, each a TLB
         // shootdown across every thread of the process
-        if (j.text.capacity() == 0 && last_text_bytes > 0) { j.text.reserve(last_text_bytes + last_text_bytes / 8); j.starts.reserve(batch_size + 1); j.line_no.reserve(batch_size); }
-        const char* p; size_t n;
+        if (j.text.capacity() == 0 && last_text_bytes > 0) { j.text.reserve(last_text_bytes + last_text_bytes / 8); j.starts.reserve(batch_size); j.lens.reserve(batch_size); j.line_no.reserve(batch_size); }
+        // Lines are recorded as (offset, length) into `text`, which receives the buffer in whole spans — one copy per buffer refill
+        // instead of one per line; blank lines and line terminators simply are not referenced.
         try {
+            size_t span_lo = pos;                              // first buffer byte not yet appended to `text`
+            auto flush = [&] { j.text.insert(j.text.end(), buf.data() + span_lo, buf.data() + pos); span_lo = pos; };
+            const char* p; size_t n;
             while (j.line_no.size() < batch_size) {
-                if (!next_line(&p, &n)) { finished = true; break; }
+                if (!find_line(&p, &n)) {
+                    flush();
+                    if (!refill()) { finished = true; break; }
+                    span_lo = pos;
+                    continue;
+                }
                 ++current_line;
                 if (n > 0 && p[n - 1] == '\n') { --n; if (n > 0 && p[n - 1] == '\r') --n; }
                 if (is_blank(p, n)) continue;
-                j.starts.push_back((uint32_t)j.text.size());
+                j.starts.push_back((uint32_t)(j.text.size() + (size_t)(p - (buf.data() + span_lo))));
+                j.lens.push_back((uint32_t)n);
                 j.line_no.push_back(current_line);
-                j.text.insert(j.text.end(), p, p + n);
-                if (j.text.size() > (size_t)UINT32_MAX - (64u << 20)) break;   // 4 GiB of text in one batch: close it here
+                if (j.text.size() + (size_t)(buf.data() + pos - (buf.data() + span_lo)) > (size_t)UINT32_MAX - (64u << 20)) break;   // 4 GiB of text: close the batch
             }
+            flush();
         } catch (const std::string& io) {
             j.read_error = "Stream execution error: Failed to read line " + std::to_string(current_line + 1) + ": " + io;
             finished = true;
         }
-        j.starts.push_back((uint32_t)j.text.size());
         last_text_bytes = std::max(last_text_bytes, j.text.size());
         return !j.line_no.empty() || !j.read_error.empty();
     }
 
     // stage 2: every line of the job into the job's columns; stops at the first bad line
-    void parse(CsvJob& j) const {
-        const size_t nf = schema->fields.size();
+    static void parse(const CsvParseConfig& cfg, CsvJob& j) {
+        const size_t nf = cfg.types.size();
         j.cols.resize(nf);   // a pooled job keeps whatever buffers its columns already own
-        for (size_t i = 0; i < nf; ++i) j.cols[i].type = schema->fields[i].data_type;
+        for (size_t i = 0; i < nf; ++i) j.cols[i].type = cfg.types[i];
         const size_t nlines = j.line_no.size();
         static const bool trace = std::getenv("RVL_CSV_TRACE") != nullptr;
         const auto t0 = std::chrono::steady_clock::now();
@@ -315,21 +340,23 @@ struct CsvBatchReader::Impl {
             std::chrono::duration<double, std::milli>(b - a).count(), std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - b).count()); } } tr{trace, t0, t1, nlines};
         const char* const text = j.text.data();
         const uint32_t* const starts = j.starts.data();
+        const uint32_t* const lens = j.lens.data();
         size_t rows = 0;
         for (size_t r = 0; r < nlines; ++r) {
             const char* p = text + starts[r];
-            const size_t n = starts[r + 1] - starts[r];
+            const size_t n = lens[r];
             if (!valid_utf8(p, n)) {   // read_line fails before the line is counted: "line {current_line + 1}" is this line's number
                 j.parse_error = "Stream execution error: Failed to read line " + std::to_string(j.line_no[r]) + ": stream did not contain valid UTF-8";
                 break;
             }
-            if (!parse_line(j, r, sv(p, n))) break;
+            if (!parse_line(cfg, j, r, sv(p, n))) break;
             rows = r + 1;
         }
         j.rows = rows;
     }
 
-    bool parse_line(CsvJob& j, size_t r, sv line) const {  // :42-121, writing row r of every column
+    static bool parse_line(const CsvParseConfig& cfg, CsvJob& j, size_t r, sv line) {  // :42-121, writing row r of every column
+        const std::string& delim = cfg.delim;
         const size_t nf = j.cols.size();
         size_t start = 0;
         // the field-count check precedes any parsing (:45-52)
@@ -380,6 +407,7 @@ struct CsvBatchReader::Impl {
     }
 
     void worker_loop() {
+        const std::shared_ptr<const CsvParseConfig> wcfg = cfg;   // the worker's own handle: nothing of *this is read per field
         for (;;) {
             CsvJob* j = nullptr;
             {
@@ -388,7 +416,7 @@ struct CsvBatchReader::Impl {
                 if (stop) return;
                 j = todo.front(); todo.pop_front();
             }
-            if (j->read_error.empty()) parse(*j);
+            if (j->read_error.empty()) parse(*wcfg, *j);
             { std::lock_guard<std::mutex> g(mu); j->done = true; }
             done_cv.notify_all();
         }
@@ -407,13 +435,18 @@ CsvBatchReader::CsvBatchReader(const std::string& path, SchemaRef schema, std::o
 #endif
     impl_->schema = std::move(schema);
     impl_->batch_size = batch_size ? *batch_size : calculate_adaptive_batch_size(*impl_->schema);
-    if (delimiter && !delimiter->empty()) impl_->delim = *delimiter;
+    {
+        auto cfg = std::make_shared<CsvParseConfig>();
+        if (delimiter && !delimiter->empty()) cfg->delim = *delimiter;
+        for (const auto& f : impl_->schema->fields) cfg->types.push_back(f.data_type);
+        impl_->cfg = std::move(cfg);
+    }
     impl_->buf.resize(4u << 20);
     // parse workers: only for files worth it (several batches of text); small files are parsed by the caller
     struct stat st;
     const bool big = ::fstat(impl_->fd, &st) == 0 && (!S_ISREG(st.st_mode) || st.st_size >= (8 << 20));
     int threads = g_csv_threads;
-    if (threads < 0) threads = big ? (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 4)) : 0;
+    if (threads < 0) threads = big ? (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2)) : 0;
     if (threads > 0 && impl_->batch_size > 0) {
         impl_->depth = (size_t)threads + 2;
         for (int i = 0; i < threads; ++i) impl_->workers.emplace_back([m = impl_.get()] { m->worker_loop(); });
@@ -454,7 +487,7 @@ size_t CsvBatchReader::read_batch() {  // read_batch :123-199
     std::unique_ptr<CsvJob> j = std::move(m.order.front());
     m.order.pop_front();
     const auto tt1 = std::chrono::steady_clock::now();
-    if (m.workers.empty()) { if (j->read_error.empty()) m.parse(*j); }
+    if (m.workers.empty()) { if (j->read_error.empty()) Impl::parse(*m.cfg, *j); }
     else { std::unique_lock<std::mutex> g(m.mu); m.done_cv.wait(g, [&] { return j->done; }); }
     if (trace) std::fprintf(stderr, "[csv] read_batch: fill %.2f ms, wait/parse %.2f ms\n", std::chrono::duration<double, std::milli>(tt1 - tt0).count(),
                             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tt1).count());

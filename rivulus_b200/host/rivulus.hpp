@@ -312,7 +312,7 @@ size_t calculate_adaptive_batch_size(const Schema& schema);   // :346-369
 // true = reproduce the reference's inverted validity of Int64 / Float64 columns that hold a null (:213-240, :245-272); default false
 void set_csv_reference_validity(bool on);
 bool csv_reference_validity();
-// parse threads per reader: -1 (default) = up to 8 for files of at least 8 MiB and none below, 0 = parse in the calling thread
+// parse threads per reader: -1 (default) = up to 8 (half the hardware threads) for files of at least 8 MiB and none below, 0 = parse in the calling thread
 void set_csv_threads(int n);
 // The parser behind CsvFileStream: `batch_size` data lines at a time straight into reusable Arrow-layout host buffers.
 class CsvBatchReader {

@@ -33,8 +33,45 @@ CtxCore::~CtxCore() {
     if (mailbox) cudaFreeHost(mailbox);
     for (uint64_t* c : slot_chunks) cudaFreeHost(c);
     for (auto& kv : big_free) cudaFree(kv.second);   // streams are gone: synchronous free
+    for (auto& kv : pinned_free) cudaFreeHost(kv.second);
 }
 
+void* CtxCore::take_pinned(size_t bytes, size_t* got) {
+    bytes = bytes < ((size_t)1 << 20) ? ((bytes + 65535) & ~(size_t)65535) : ((bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1));
+    if (bytes == 0) bytes = 65536;
+    {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = pinned_free.lower_bound(bytes);
+        if (it != pinned_free.end() && it->first <= 2 * bytes + ((size_t)1 << 20)) {
+            void* p = it->second;
+            *got = it->first;
+            pinned_free.erase(it);
+            return p;
+        }
+    }
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        drop_pinned();
+        if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    }
+    std::lock_guard<std::mutex> g(mu);
+    pinned_sizes[p] = bytes;
+    *got = bytes;
+    return p;
+}
+void CtxCore::give_pinned(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> g(mu);
+    auto it = pinned_sizes.find(p);
+    if (it == pinned_sizes.end()) { cudaFreeHost(p); return; }
+    pinned_free.emplace(it->second, p);
+}
+void CtxCore::drop_pinned() {
+    std::multimap<size_t, void*> blocks;
+    { std::lock_guard<std::mutex> g(mu); blocks.swap(pinned_free); for (auto& kv : blocks) pinned_sizes.erase(kv.second); }
+    for (auto& kv : blocks) cudaFreeHost(kv.second);
+}
 void* CtxCore::take_big(size_t bytes, size_t* got) {
     std::lock_guard<std::mutex> g(mu);
     auto it = big_free.lower_bound(bytes);
@@ -242,6 +279,7 @@ int32_t rvl_ctx_trim(rvl_ctx* ctx) {
     if (!ctx) return fail(RVL_INVALID_ARGUMENT, "null context");
     RVL_CUDA_TRY(cudaSetDevice(ctx->core->device));
     ctx->core->drop_big();
+    ctx->core->drop_pinned();
     RVL_CUDA_TRY(cudaStreamSynchronize(ctx->core->stream));
     cudaMemPool_t pool;
     RVL_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, ctx->core->device));

@@ -52,6 +52,13 @@ struct CtxCore {
     static constexpr size_t kBigBlock = 16u << 20;
     std::multimap<size_t, void*> big_free;     // size -> block
     size_t big_free_bytes = 0;
+    // page-locked staging buffers of the streaming executor outlive their stream the same way: cudaHostAlloc / cudaFreeHost take
+    // milliseconds (and the process-wide mmap lock, against every other thread touching fresh memory), a query should not pay them
+    std::multimap<size_t, void*> pinned_free;
+    std::map<void*, size_t> pinned_sizes;      // every block handed out by take_pinned
+    void* take_pinned(size_t bytes, size_t* got);              // cached block in [bytes, 2 * bytes + 1 MiB] or a new one; nullptr = out of memory
+    void give_pinned(void* p);
+    void drop_pinned();                                        // cudaFreeHost every cached block
     void* take_big(size_t bytes, size_t* got);                 // smallest cached block in [bytes, bytes * 9/8], or nullptr
     void give_big(void* p, size_t bytes);
     void drop_big();                                           // cudaFreeAsync every cached block (trim, OOM retry, teardown)

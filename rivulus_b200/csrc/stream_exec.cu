@@ -35,7 +35,8 @@ namespace {
 
 struct StagingColumn {
     BufRef values, validity, offsets, data;  // device
-    void *h_values = nullptr, *h_validity = nullptr, *h_offsets = nullptr, *h_data = nullptr;  // pinned host (lazy)
+    void *h_values = nullptr, *h_validity = nullptr, *h_offsets = nullptr, *h_data = nullptr;  // pinned host (lazy, CtxCore::take_pinned)
+    size_t h_values_cap = 0, h_validity_cap = 0, h_offsets_cap = 0;
     size_t data_cap = 0, h_data_cap = 0;
 };
 
@@ -147,14 +148,20 @@ PtrRange classify(rvl_stream* s, const void* p) {
     return r;
 }
 
-int ensure_pinned(void** p, size_t* cap, size_t need) {
-    if (*p != nullptr && (cap == nullptr || *cap >= need)) return RVL_OK;
-    // variable-size staging (string bytes) grows by half again, in whole MiB: cudaFreeHost + cudaHostAlloc synchronise the device
-    // and cost milliseconds, which a stream of batches of slightly different byte counts would otherwise pay on every push
-    if (*p != nullptr && cap != nullptr) need = (std::max(need, *cap + *cap / 2) + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
-    if (*p != nullptr) { cudaFreeHost(*p); *p = nullptr; }
-    RVL_CUDA_TRY(cudaHostAlloc(p, need ? need : 1, cudaHostAllocDefault));
-    if (cap) *cap = need;
+// the slot's page-locked staging buffer for one column buffer, at least `need` bytes: from the context's cache of pinned blocks
+int ensure_pinned(rvl_stream* s, void** p, size_t* cap, size_t need) {
+    if (*p != nullptr && *cap >= need) return RVL_OK;
+    if (*p != nullptr) {
+        // variable-size staging (string bytes) grows by half again; copies still reading the old block must finish before it is recycled
+        need = std::max(need, *cap + *cap / 2);
+        cudaStreamSynchronize(s->core->copy_stream);
+        s->core->give_pinned(*p);
+        *p = nullptr; *cap = 0;
+    }
+    size_t got = 0;
+    *p = s->core->take_pinned(need, &got);
+    if (*p == nullptr) return fail(RVL_OUT_OF_MEMORY, "cudaHostAlloc(" + std::to_string(need) + ") failed");
+    *cap = got;
     return RVL_OK;
 }
 
@@ -165,7 +172,7 @@ int stage_copy(rvl_stream* s, void* dev_dst, const void* src, size_t bytes, void
     if (bytes == 0) return RVL_OK;
     const void* from = src;
     if (!classify(s, src).reachable) {
-        RVL_TRY(ensure_pinned(pinned, pinned_cap, std::max(pinned_need, pinned_off + bytes)));
+        RVL_TRY(ensure_pinned(s, pinned, pinned_cap, std::max(pinned_need, pinned_off + bytes)));
         std::memcpy((uint8_t*)*pinned + pinned_off, src, bytes);
         from = (uint8_t*)*pinned + pinned_off;
     }
@@ -491,11 +498,11 @@ int32_t rvl_stream_push(rvl_stream* s, const rvl_column* cols, int32_t ncols, in
         const int64_t start = hc.offset - resid, span = resid + n;
         const int64_t at = first ? 0 : g.resid + s->open_rows;   // slot row the copy starts at
         if (hc.dtype == RVL_INT64 || hc.dtype == RVL_FLOAT64) {
-            RVL_TRY(stage_copy(s, (uint8_t*)sc.values->ptr + at * 8, (const uint8_t*)hc.values + start * 8, (size_t)span * 8, &sc.h_values, nullptr, rows_cap * 8, (size_t)at * 8));
+            RVL_TRY(stage_copy(s, (uint8_t*)sc.values->ptr + at * 8, (const uint8_t*)hc.values + start * 8, (size_t)span * 8, &sc.h_values, &sc.h_values_cap, rows_cap * 8, (size_t)at * 8));
         } else if (hc.dtype == RVL_BOOLEAN) {
-            RVL_TRY(stage_copy(s, (uint8_t*)sc.values->ptr + at / 8, (const uint8_t*)hc.values + start / 8, (size_t)(span + 7) / 8, &sc.h_values, nullptr, rows_cap / 8 + 8, (size_t)at / 8));
+            RVL_TRY(stage_copy(s, (uint8_t*)sc.values->ptr + at / 8, (const uint8_t*)hc.values + start / 8, (size_t)(span + 7) / 8, &sc.h_values, &sc.h_values_cap, rows_cap / 8 + 8, (size_t)at / 8));
         } else if (hc.dtype == RVL_STRING) {
-            RVL_TRY(stage_copy(s, sc.offsets->ptr, hc.offsets + start, (size_t)(span + 1) * 4, &sc.h_offsets, nullptr, (rows_cap + 1) * 4, 0));
+            RVL_TRY(stage_copy(s, sc.offsets->ptr, hc.offsets + start, (size_t)(span + 1) * 4, &sc.h_offsets, &sc.h_offsets_cap, (rows_cap + 1) * 4, 0));
             const int64_t b0 = hc.offsets[start], b1 = hc.offsets[start + span];
             const size_t nbytes = (size_t)(b1 - b0);
             if (sc.data_cap < nbytes || !sc.data) {
@@ -509,7 +516,7 @@ int32_t rvl_stream_push(rvl_stream* s, const rvl_column* cols, int32_t ncols, in
             g.str_first = b0; g.str_last = b1;
         }
         if (g.has_validity)
-            RVL_TRY(stage_copy(s, (uint8_t*)sc.validity->ptr + at / 8, hc.validity + start / 8, (size_t)(span + 7) / 8, &sc.h_validity, nullptr, rows_cap / 8 + 8, (size_t)at / 8));
+            RVL_TRY(stage_copy(s, (uint8_t*)sc.validity->ptr + at / 8, hc.validity + start / 8, (size_t)(span + 7) / 8, &sc.h_validity, &sc.h_validity_cap, rows_cap / 8 + 8, (size_t)at / 8));
     }
     s->open_rows += n;
     s->pushed++;
@@ -623,10 +630,10 @@ int32_t rvl_stream_close(rvl_stream* s) {
         if (sl.copied) cudaEventDestroy(sl.copied);
         if (sl.free_ev) cudaEventDestroy(sl.free_ev);
         for (StagingColumn& sc : sl.cols) {
-            if (sc.h_values) cudaFreeHost(sc.h_values);
-            if (sc.h_validity) cudaFreeHost(sc.h_validity);
-            if (sc.h_offsets) cudaFreeHost(sc.h_offsets);
-            if (sc.h_data) cudaFreeHost(sc.h_data);
+            s->core->give_pinned(sc.h_values);
+            s->core->give_pinned(sc.h_validity);
+            s->core->give_pinned(sc.h_offsets);
+            s->core->give_pinned(sc.h_data);
         }
     }
     delete s;

@@ -119,7 +119,12 @@ def test_cpp_demo_program_runs_the_reference_demo_queries():
     import subprocess
     exe = os.path.join(os.path.dirname(_HERE), "rivulus_b200", "lib", "rivulus_demo")
     assert os.path.exists(exe), "build() did not produce rivulus_b200/lib/rivulus_demo"
-    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    import tempfile
+    csv = os.path.join(tempfile.mkdtemp(prefix="rvl_demo_"), "username.csv")
+    with open(csv, "w") as f:   # the shape of the reference's username.csv (main.rs:236-243)
+        f.write("Username; Identifier;First name;Last name\nbooker12;9012;Rachel;Booker\ngrey07;2070;Laura;Grey\njohnson81;4081;Craig;Johnson\n"
+                "jenkins46;9346;Mary;Jenkins\nsmith79;5079;Jamie;Smith\n")
+    out = subprocess.run([exe, csv], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
     lines = out.stdout.strip().splitlines()
     assert lines[0] == "q1 rows=2 | name:[Charlie,Eve] age:[35,42]"
@@ -128,6 +133,10 @@ def test_cpp_demo_program_runs_the_reference_demo_queries():
     assert lines[3] == "q4 rows=0 | name:[] age:[] score:[]"
     m = re.match(r"q5 rows=1 cols=2 launches=(\d+)$", lines[4])
     assert m and int(m.group(1)) > 0, lines[4]
+    assert lines[5] == ("q6 rows=5 | order_id:[101,102,103,104,105] user_id:[1,2,1,3,2] amount:[29.99,15.5,45,8.75,12.99] "
+                        "name:[Alice,Bob,Alice,Charlie,Bob] city:[Rome,Milan,Rome,Naples,Milan]")
+    assert lines[6] == "q7 rows=5 | name:[Alice,Bob,Alice,Charlie,Bob] amount:[29.99,15.5,45,8.75,12.99] city:[Rome,Milan,Rome,Naples,Milan]"
+    assert lines[7] == "q8 rows=3 cols=3 first=booker12"
 
 
 # ------------------------------------------------------------------ randomized differential test against the oracle

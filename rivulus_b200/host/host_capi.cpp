@@ -26,9 +26,6 @@ struct ColExport {  // same shape as the oracle's export struct, so one numpy de
     const int32_t* offsets; int64_t offsets_len;
     const uint8_t* data; int64_t data_len;
 };
-std::vector<uint8_t> bits_or_empty(const uint8_t* bits, int64_t n) {
-    return bits ? std::vector<uint8_t>(bits, bits + (n + 7) / 8) : std::vector<uint8_t>();
-}
 }  // namespace
 
 extern "C" {

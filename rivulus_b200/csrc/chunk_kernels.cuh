@@ -38,11 +38,22 @@ namespace rvl {
 constexpr int kChunkTiles = 2;                           // 2048-row tiles per chunk
 constexpr int kChunkRows = kChunkTiles * kTileRows;      // 4096
 constexpr int kChunkWords = kChunkRows / 32;             // 128 selection words
-constexpr int kChunkBufs = 4;                            // chunk buffers: being loaded / evaluated / waiting for its prefix / compacted
-constexpr int kChunkLag = 2;                             // P2 runs this many chunks behind P1
+#ifndef RVL_CHUNK_BUFS
+#define RVL_CHUNK_BUFS 4
+#define RVL_CHUNK_LAG 2
+#endif
+constexpr int kChunkBufs = RVL_CHUNK_BUFS;               // chunk buffers: being loaded / evaluated / waiting for its prefix (kChunkLag of them) / compacted
+constexpr int kChunkLag = RVL_CHUNK_LAG;                 // P2 runs this many chunks behind P1.  Measured on a 500 M-row shard at 50 % (ms): (bufs, lag) =
+                                                         // (4, 2) 2.65, (5, 3) 2.73, (5, 2) 2.71 — neither a longer lag nor one more chunk loading
+                                                         // ahead helps; the smaller ring (3 slots instead of 5) costs a little
+static_assert(kChunkBufs >= kChunkLag + 2, "one buffer being loaded, one evaluated, kChunkLag waiting for their prefix");
 constexpr int kChunkCW = 16;                             // consumer warps
 constexpr int kChunkThreads = (kChunkCW + 3) * 32;       // + producer, scanner, server
 constexpr int kChunkMaxSlots = 5;
+#ifndef RVL_CHUNK_SERVER_PER
+#define RVL_CHUNK_SERVER_PER 4
+#endif
+constexpr int kServerPer = RVL_CHUNK_SERVER_PER;         // descriptors per lane and step of the prefix server
 
 struct ChunkParams {
     int64_t n_rows;
@@ -55,6 +66,7 @@ struct ChunkParams {
     BitSrc pred_valid;
     int32_t n_col8, n_slots;
     uint32_t sparse_max, debug;        // debug (RVL_CHUNK_DEBUG, timing experiments only): 1 = skip the look-back (WRONG output order)
+    uint32_t producer_nap, pad_nap;    // ns the producer lane sleeps after an event-loop pass that found nothing to do (0 = spin)
     Col8 col8[kMaxCol8];
     const unsigned long long* base_in; // rows emitted by earlier launches of the same query (streaming) or nullptr
     uint32_t* sel_out;                 // row-order selection words, whole tiles
@@ -150,6 +162,9 @@ __global__ void __launch_bounds__(kChunkThreads, 1) chunk_filter_kernel(const __
 #pragma unroll 1
         while (true) {
             if (p.debug == 2u && ++idle > (1u << 26)) chunk_stuck(p, 12, next_k, next_r);
+            // a pass that found nothing to issue yields the scheduler's issue slots to the consumer warps for a moment
+            if (p.producer_nap != 0u && idle > 1u) __nanosleep(p.producer_nap);
+            if (p.debug != 2u) ++idle;
             // (a) load the next chunk's predicate values as soon as its buffer is free
             if (!out_of_chunks) {
                 const int b = (int)(next_k % kChunkBufs);
@@ -253,26 +268,57 @@ __global__ void __launch_bounds__(kChunkThreads, 1) chunk_filter_kernel(const __
         // ------------------------------------------------------------------------------------------------ prefix server
         CHUNK_WAIT(*reinterpret_cast<volatile uint32_t*>(&sm.server_role) != 0u, 11, 0, 0);
         if (*reinterpret_cast<volatile uint32_t*>(&sm.server_role) != 1u) return;
-        // descriptors in chunk order, 32 per step (one per lane), the next step's loads issued before this step is consumed.
-        // (Measured: an 8-step look-ahead is SLOWER — 2.98 vs 2.66 ms per 500 M rows at 50 % — the server keeps pace with the
-        // publication of the counts either way, and loads issued that early mostly come back unpublished and are polled again.)
+        // descriptors in chunk order, the next step's loads issued before this step is consumed.  (An 8-step look-ahead with one
+        // descriptor per lane was measured SLOWER, 2.98 vs 2.66 ms: loads issued that early mostly come back unpublished and are polled
+        // again, one L2 round trip each.)
+        // A window of 32 * kServerPer descriptors per step (kServerPer consecutive ones per lane).  A step costs one L2 round trip
+        // whatever it covers; with 32 per step that pace — 3 815 steps for 500 M rows — WAS the kernel's duration (2.67 ms at any
+        // selectivity).  The step consumes the leading run of PUBLISHED descriptors and moves the window behind it: the prefix of
+        // chunk c never waits for a chunk after c.  (Waiting for a whole window can deadlock: a CTA holds at most kChunkBufs chunks,
+        // and when more of its tickets than that fall into one window, the later ones are only loaded once the earlier ones have
+        // their prefix.  Seen as a hang at 0.1 % selectivity with 128-descriptor windows.)
         uint64_t running = 0;
-        uint64_t nxt = lane < p.n_chunks ? ld_relaxed_gpu(p.status + lane) : kStatusAggregate;
+        int64_t base = 0;
+        uint32_t spins = 0;
 #pragma unroll 1
-        for (int64_t base = 0; base < p.n_chunks; base += 32) {
-            const int64_t idx = base + lane;
-            uint64_t d = nxt;
-            const int64_t nidx = idx + 32;
-            nxt = nidx < p.n_chunks ? ld_relaxed_gpu(p.status + nidx) : kStatusAggregate;
-            if (idx < p.n_chunks && (d & kStatusMask) == 0ull) CHUNK_WAIT(((d = ld_relaxed_gpu(p.status + idx)) & kStatusMask) != 0ull, 5, idx, 0);
-            uint64_t incl = d & kValueMask;
+        while (base < p.n_chunks) {
+            const int64_t idx0 = base + (int64_t)lane * kServerPer;
+            uint64_t d[kServerPer];
+#pragma unroll
+            for (int k = 0; k < kServerPer; ++k) d[k] = idx0 + k < p.n_chunks ? ld_relaxed_gpu(p.status + idx0 + k) : kStatusAggregate;
+            // leading published descriptors of this lane, then of the window
+            int mine_ready = 0;
+#pragma unroll
+            for (int k = 0; k < kServerPer; ++k) if (mine_ready == k && (d[k] & kStatusMask) != 0ull) mine_ready = k + 1;
+            const uint32_t full = __ballot_sync(0xFFFFFFFFu, mine_ready == kServerPer);
+            const int first_partial = full == 0xFFFFFFFFu ? 32 : __ffs((int)~full) - 1;
+            const int partial = first_partial < 32 ? __shfl_sync(0xFFFFFFFFu, mine_ready, first_partial) : 0;
+            const int64_t n_ready = min((int64_t)first_partial * kServerPer + partial, p.n_chunks - base);
+            if (n_ready == 0) {
+                if (p.debug == 2u && ++spins > (1u << 22)) chunk_stuck(p, 5, base, 0);
+                continue;
+            }
+            spins = 0;
+            uint64_t v[kServerPer];
+            uint64_t mine = 0;
+#pragma unroll
+            for (int k = 0; k < kServerPer; ++k) {
+                const bool take = (int64_t)lane * kServerPer + k < n_ready;
+                mine += take ? (d[k] & kValueMask) : 0ull;
+                v[k] = mine;
+            }
+            uint64_t incl = mine;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const uint64_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
                 if (lane >= o) incl += up;
             }
-            if (idx < p.n_chunks) st_relaxed_gpu(p.status + idx, kStatusPrefix | (running + incl));
+            const uint64_t before = running + incl - mine;
+#pragma unroll
+            for (int k = 0; k < kServerPer; ++k)
+                if ((int64_t)lane * kServerPer + k < n_ready) st_relaxed_gpu(p.status + idx0 + k, kStatusPrefix | (before + v[k]));
             running += __shfl_sync(0xFFFFFFFFu, incl, 31);
+            base += n_ready;
         }
         return;
     }

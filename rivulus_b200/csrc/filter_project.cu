@@ -551,6 +551,7 @@ int fp_launch(const CoreRef& core, const rvl_batch* in, const rvl_predicate* pre
             for (int k = 0; k < cp.n_col8; ++k) cp.col8[k] = col8s[(size_t)k];
             cp.sparse_max = (uint32_t)std::max(0, core->sparse_max);
             { const char* dbg = std::getenv("RVL_CHUNK_DEBUG"); cp.debug = dbg ? (uint32_t)std::atoi(dbg) : 0u; }
+            { static const char* nap = std::getenv("RVL_CHUNK_NAP"); cp.producer_nap = nap ? (uint32_t)std::atoi(nap) : 0u; }
             if (cp.debug == 2u) { std::memset(core->mailbox + 128, 0, 128 * 8); cp.debug_words = (unsigned long long*)(core->mailbox + 128); }
             cp.base_in = base_in;
             cp.sel_out = (uint32_t*)sel->ptr; cp.tile_info = (uint64_t*)tile_prefix->ptr;

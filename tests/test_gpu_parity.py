@@ -741,3 +741,31 @@ def test_hash_join_inner_large(keytype):
             wp.append(i); wb.append(b)
     assert out.num_rows() == len(wp)
     assert np.array_equal(got[0].values, ppay[np.array(wp)]) and np.array_equal(got[1].values, bpay[np.array(wb)])
+
+
+@pytest.mark.gpu
+def test_large_blocks_are_recycled_by_the_context():
+    """runtime.cu: blocks >= 16 MiB go back to the context's own free list, not to the driver pool (which was measured re-creating
+    multi-GB blocks after a synchronisation: profiles/r02_alloc_outlier.txt).  Steady-state queries must not change what the pool
+    holds, also across device-wide synchronisations and small queries in between; rvl_ctx_trim gives the cache back."""
+    ctx = capi.Context(0)
+    t = ctx.gen_batch([(capi.SYNTH_KEY1000, 0, 0), (capi.SYNTH_I64, 1, 0), (capi.SYNTH_F64, 2, 0)], 40_000_000, 0)
+    small = t.slice(0, 3_000_000)
+
+    def q(b, thr):
+        o = ctx.filter_project(b, capi.predicate(0, ">", thr), [1, 2]); n = o.num_rows(); o.release()
+        return n
+    for thr in (998, 499, 99):
+        q(t, thr)
+    q(small, 499)
+    reserved0, used0 = ctx.pool_stats()
+    for rep in range(3):
+        for thr in (998, 499, 99):
+            q(t, thr)
+        q(small, 499)
+        ctx.synchronize()
+        assert ctx.pool_stats()[0] == reserved0, "a steady-state query made the pool grow"
+    assert ctx.pool_stats()[1] >= used0 - (1 << 20)      # the cached blocks still count as used by the pool
+    small.release(); t.release()
+    ctx.trim()
+    assert ctx.pool_stats()[0] < reserved0, "trim did not give the cached blocks back"

@@ -1007,6 +1007,8 @@ static void check_lowering(const LogicalPlan& p) {
 }
 
 // HashMap<AnyValue, Vec<usize>> key of the join (series.rs:73-98): same variant and same value; f64 hashed by to_bits, NaN == nothing.
+// The reference holds no join test: pinned only by the main.rs demo queries (:170-196); everything else here is
+// "parity unpinned — code reading only".
 // 0.0 and -0.0 are equal but hash differently, so they meet only when the table's random state happens to collide: kept apart here.
 struct JoinKey {
     int tag; uint64_t bits; std::string s;

@@ -59,7 +59,7 @@ def lib():
         build()
         L = C.CDLL(_LIB_PATH)
         L.orc_last_error.restype = C.c_char_p
-        for name in ("orc_dfb_new", "orc_expr_col", "orc_expr_lit", "orc_expr_binary", "orc_expr_alias", "orc_lf_from_df", "orc_lf_from_csv", "orc_sp_csv_source", "orc_lf_inner_join",
+        for name in ("orc_dfb_new", "orc_expr_col", "orc_expr_lit", "orc_expr_binary", "orc_expr_alias", "orc_lf_from_df", "orc_lf_from_csv", "orc_sp_csv_source", "orc_lf_inner_join", "orc_rbb_new",
                      "orc_lf_select", "orc_lf_filter", "orc_lf_limit", "orc_arr_i64", "orc_arr_f64", "orc_arr_bool",
                      "orc_arr_str", "orc_arr_null", "orc_arr_i64_new", "orc_arr_f64_new", "orc_arr_bool_new",
                      "orc_sp_memory_source", "orc_sp_dataframe_source", "orc_sp_filter", "orc_sp_select", "orc_sp_limit",
@@ -68,7 +68,7 @@ def lib():
         for name in ("orc_df_col_name", "orc_rb_col_name"):
             getattr(L, name).restype = C.c_char_p
         for name in ("orc_df_height", "orc_df_col_len", "orc_df_col_str_bytes", "orc_arr_len", "orc_arr_null_count",
-                     "orc_rb_num_rows", "orc_csv_adaptive_batch_size"):
+                     "orc_rb_num_rows", "orc_csv_adaptive_batch_size", "orc_rb_memory_size"):
             getattr(L, name).restype = C.c_int64
         L.orc_time_eager_filter_select.restype = C.c_double
         L.orc_time_eager_filter_select_mt.restype = C.c_double
@@ -498,6 +498,23 @@ class RecordBatch:
             _check(lib().orc_rb_try_new(len(sn), nm, dt, len(arrays), arrs, C.byref(out)))
         return RecordBatch(out.value)
 
+    @staticmethod
+    def new_unchecked(names, arrays, num_rows, schema_dtypes):
+        """RecordBatch::new_unchecked (record_batch.rs:60-66): no checks; validate() reports what is wrong."""
+        out = C.c_void_p()
+        arrs = (C.c_void_p * max(len(arrays), 1))(*[a._h for a in arrays])
+        nm = (C.c_char_p * max(len(names), 1))(*[n.encode() for n in names])
+        dt = (C.c_int * max(len(schema_dtypes), 1))(*schema_dtypes)
+        _check(lib().orc_rb_new_unchecked(len(names), nm, dt, len(arrays), arrs, C.c_int64(num_rows), C.byref(out)))
+        return RecordBatch(out.value)
+
+    def validate(self): _check(lib().orc_rb_validate(_vp(self._h)))            # record_batch.rs:348-378 (raises with the Err text)
+    def memory_size(self): return int(lib().orc_rb_memory_size(_vp(self._h)))   # :380-400
+
+    def column_by_name(self, name):                                             # :84-86
+        names = self.column_names()
+        return self.column(names.index(name)) if name in names else None
+
     def num_rows(self): return lib().orc_rb_num_rows(_vp(self._h))
     def num_columns(self): return lib().orc_rb_num_columns(_vp(self._h))
     def column_names(self): return [lib().orc_rb_col_name(_vp(self._h), i).decode() for i in range(self.num_columns())]
@@ -552,6 +569,32 @@ class RecordBatch:
     def filter_project_mask(self, mask_col: int, proj: Sequence[int], limit: int = -1):
         p = (C.c_int32 * len(proj))(*proj)
         return self._op(lib().orc_rb_filter_project_mask, mask_col, p, len(proj), C.c_int64(limit))
+
+
+class RecordBatchBuilder:
+    """execution/record_batch.rs:495-573"""
+
+    def __init__(self, names, schema_dtypes, capacity=0):
+        nm = (C.c_char_p * max(len(names), 1))(*[n.encode() for n in names])
+        dt = (C.c_int * max(len(schema_dtypes), 1))(*schema_dtypes)
+        self._h = lib().orc_rbb_new(len(names), nm, dt)
+
+    @staticmethod
+    def with_capacity(names, schema_dtypes, capacity): return RecordBatchBuilder(names, schema_dtypes, capacity)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_rbb_free(_vp(self._h)); self._h = None
+
+    def add_column(self, array): _check(lib().orc_rbb_add_column(_vp(self._h), _vp(array._h)))
+
+    def finish(self):
+        out = C.c_void_p()
+        _check(lib().orc_rbb_finish(_vp(self._h), C.byref(out)))
+        return RecordBatch(out.value)
+
+    def num_columns(self): return lib().orc_rbb_num_columns(_vp(self._h))
+    def is_complete(self): return bool(lib().orc_rbb_is_complete(_vp(self._h)))
 
 
 class StreamingPhysicalPlan:

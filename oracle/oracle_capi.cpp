@@ -289,6 +289,27 @@ int orc_rb_try_new(int nfields, const char** names, const int* dtypes, int ncols
         *out = new RecordBatch(RecordBatch::try_new(s, std::move(cols)));
     });
 }
+int orc_rb_new_unchecked(int nfields, const char** names, const int* dtypes, int ncols, void** arrays, int64_t num_rows, void** out) {
+    return guard([&] {
+        auto s = std::make_shared<Schema>();
+        for (int i = 0; i < nfields; ++i) s->fields.push_back(Field{names[i], (ExecType)dtypes[i], true});
+        std::vector<ArrayRef> cols;
+        for (int i = 0; i < ncols; ++i) cols.push_back(*(ArrayRef*)arrays[i]);
+        *out = new RecordBatch(RecordBatch::new_unchecked(s, std::move(cols), (size_t)num_rows));
+    });
+}
+int orc_rb_validate(void* rb) { return guard([&] { ((RecordBatch*)rb)->validate(); }); }
+int64_t orc_rb_memory_size(void* rb) { return (int64_t)((RecordBatch*)rb)->memory_size(); }
+void* orc_rbb_new(int nfields, const char** names, const int* dtypes) {
+    auto s = std::make_shared<Schema>();
+    for (int i = 0; i < nfields; ++i) s->fields.push_back(Field{names[i], (ExecType)dtypes[i], true});
+    return new RecordBatchBuilder(s);
+}
+int orc_rbb_add_column(void* b, void* array) { return guard([&] { ((RecordBatchBuilder*)b)->add_column(*(ArrayRef*)array); }); }
+int orc_rbb_finish(void* b, void** out) { return guard([&] { *out = new RecordBatch(((RecordBatchBuilder*)b)->finish()); }); }
+int orc_rbb_num_columns(void* b) { return (int)((RecordBatchBuilder*)b)->num_columns(); }
+int orc_rbb_is_complete(void* b) { return ((RecordBatchBuilder*)b)->is_complete() ? 1 : 0; }
+void orc_rbb_free(void* b) { delete (RecordBatchBuilder*)b; }
 void orc_rb_free(void* rb) { delete (RecordBatch*)rb; }
 int64_t orc_rb_num_rows(void* rb) { return (int64_t)((RecordBatch*)rb)->num_rows; }
 int orc_rb_num_columns(void* rb) { return (int)((RecordBatch*)rb)->columns.size(); }

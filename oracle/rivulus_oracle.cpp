@@ -428,6 +428,50 @@ RecordBatch RecordBatch::try_new(SchemaRef schema, std::vector<ArrayRef> cols) {
     return b;
 }
 
+RecordBatch RecordBatch::new_unchecked(SchemaRef schema, std::vector<ArrayRef> cols, size_t num_rows) {  // record_batch.rs:60-66
+    RecordBatch b; b.schema = std::move(schema); b.columns = std::move(cols); b.num_rows = num_rows;
+    return b;
+}
+void RecordBatch::validate() const {  // record_batch.rs:348-378
+    if (schema->fields.size() != columns.size())
+        throw OracleError("Schema has " + std::to_string(schema->fields.size()) + " fields but " + std::to_string(columns.size()) + " columns present");
+    for (size_t i = 0; i < columns.size(); ++i) {
+        if (columns[i]->len() != num_rows)
+            throw OracleError("Column " + std::to_string(i) + " has length " + std::to_string(columns[i]->len()) + " but expected " + std::to_string(num_rows));
+        if (schema->fields[i].data_type != columns[i]->data_type())
+            throw OracleError("Column " + std::to_string(i) + " has type " + exec_type_name(columns[i]->data_type()) + " but schema expects " +
+                              exec_type_name(schema->fields[i].data_type));
+    }
+}
+size_t RecordBatch::memory_size() const {  // record_batch.rs:380-400: size_of_val(Schema) = 24, size_of::<Vec<ArrayRef>>() = 24, ArrayRef = 16
+    size_t total = 24 + 24 + columns.size() * 16;
+    for (const auto& c : columns) switch (c->data_type()) {
+        case ExecType::Int64: case ExecType::Float64: total += c->len() * 8; break;
+        case ExecType::Boolean: total += (c->len() + 7) / 8; break;
+        case ExecType::String: total += c->len() * 20; break;
+        case ExecType::Null: total += 16; break;
+    }
+    return total;
+}
+ArrayRef RecordBatch::column_by_name(const std::string& name) const {  // record_batch.rs:84-86
+    auto i = schema->index_of(name);
+    return i ? columns[*i] : nullptr;
+}
+void RecordBatchBuilder::add_column(ArrayRef column) {  // record_batch.rs:518-546
+    if (columns.size() >= schema->fields.size()) throw OracleError("Cannot add more columns than schema defines");
+    const Field& f = schema->fields[columns.size()];
+    if (column->data_type() != f.data_type)
+        throw OracleError(std::string("Column type ") + exec_type_name(column->data_type()) + " doesn't match expected type " + exec_type_name(f.data_type));
+    if (!columns.empty() && column->len() != columns[0]->len())
+        throw OracleError("Column length " + std::to_string(column->len()) + " doesn't match expected length " + std::to_string(columns[0]->len()));
+    columns.push_back(std::move(column));
+}
+RecordBatch RecordBatchBuilder::finish() const {  // record_batch.rs:548-558
+    if (columns.size() != schema->fields.size())
+        throw OracleError("Expected " + std::to_string(schema->fields.size()) + " columns but only " + std::to_string(columns.size()) + " provided");
+    return RecordBatch::try_new(schema, columns);
+}
+
 RecordBatch RecordBatch::slice(size_t off, size_t len) const {  // record_batch.rs:92-106
     if (!(off + len <= num_rows)) throw Panic("Slice out of bounds");
     RecordBatch b; b.schema = schema; b.num_rows = len;

@@ -231,6 +231,10 @@ struct NullArray : Array {
 struct RecordBatch {
     SchemaRef schema; std::vector<ArrayRef> columns; size_t num_rows = 0;
     static RecordBatch try_new(SchemaRef schema, std::vector<ArrayRef> cols);   // :16-58  (throws OracleError(String))
+    static RecordBatch new_unchecked(SchemaRef schema, std::vector<ArrayRef> cols, size_t num_rows);   // :60-66
+    void validate() const;                                                      // :348-378 (throws OracleError(String))
+    size_t memory_size() const;                                                 // :380-400
+    ArrayRef column_by_name(const std::string& name) const;                     // :84-86 (nullptr = None)
     RecordBatch slice(size_t off, size_t len) const;                            // :92-106 (panics OOB)
     RecordBatch take(const std::vector<size_t>& idx) const;                     // :108-129
     RecordBatch select_columns(const std::vector<size_t>& idx) const;           // :180-206
@@ -238,6 +242,15 @@ struct RecordBatch {
     RecordBatch filter(const ArrayRef& predicate) const;                        // :221-243
     static RecordBatch concat(const std::vector<RecordBatch>& batches);         // :245-275
     static RecordBatch empty(SchemaRef schema);                                 // :402-421
+};
+// record_batch.rs:495-573
+struct RecordBatchBuilder {
+    SchemaRef schema; std::vector<ArrayRef> columns;
+    explicit RecordBatchBuilder(SchemaRef s) : schema(std::move(s)) {}           // new :501-507, with_capacity :509-516
+    void add_column(ArrayRef column);                                            // :518-546 (throws OracleError(String))
+    RecordBatch finish() const;                                                  // :548-558
+    size_t num_columns() const { return columns.size(); }                        // :560-562
+    bool is_complete() const { return columns.size() == schema->fields.size(); } // :564-566
 };
 ArrayRef take_array(const ArrayRef& a, const std::vector<size_t>& idx);         // :131-178
 ArrayRef concat_arrays(const std::vector<ArrayRef>& arrays);                    // :277-342

@@ -43,6 +43,8 @@ HOST_SYMBOLS = [
     "rvh_df_col_len", "rvh_df_col_str_bytes", "rvh_df_col_export", "rvh_df_col_buffers",
     "rvh_expr_col", "rvh_expr_lit", "rvh_expr_binary", "rvh_expr_alias", "rvh_expr_free",
     "rvh_lf_from_df", "rvh_lf_from_csv", "rvh_set_csv_reference_validity", "rvh_set_csv_threads", "rvh_csv_adaptive_batch_size", "rvh_sp_csv_source", "rvh_csv_parse_dump", "rvh_free", "rvh_lf_inner_join", "rvh_lf_select", "rvh_lf_filter", "rvh_lf_limit", "rvh_lf_free", "rvh_lf_collect", "rvh_lf_collect_streaming",
+    "rvh_rb_new_unchecked", "rvh_rb_validate", "rvh_rb_memory_size", "rvh_rbb_new", "rvh_rbb_add_column", "rvh_rbb_finish", "rvh_rbb_num_columns",
+    "rvh_rbb_is_complete", "rvh_rbb_free",
     "rvh_lf_plan_shape", "rvh_lf_schema", "rvh_lf_validate", "rvh_lf_describe",
     "rvh_rb_try_new", "rvh_rb_free", "rvh_rb_num_rows", "rvh_rb_num_columns", "rvh_rb_col_name", "rvh_rb_col_dtype", "rvh_rb_col_export",
     "rvh_rb_slice", "rvh_rb_take", "rvh_rb_select", "rvh_rb_select_by_name", "rvh_rb_filter", "rvh_rb_concat", "rvh_rb_empty_like",
@@ -72,13 +74,13 @@ def lib():
                               f"(or `make -C rivulus_b200/host`).  rivulus_b200 has no CPU fallback.")
         L = C.CDLL(HOST_LIB_PATH)
         L.rvh_last_error.restype = C.c_char_p
-        for name in ("rvh_dfb_new", "rvh_expr_col", "rvh_expr_lit", "rvh_expr_binary", "rvh_expr_alias", "rvh_lf_from_df", "rvh_lf_from_csv", "rvh_sp_csv_source", "rvh_lf_inner_join", "rvh_lf_select",
+        for name in ("rvh_dfb_new", "rvh_expr_col", "rvh_expr_lit", "rvh_expr_binary", "rvh_expr_alias", "rvh_lf_from_df", "rvh_lf_from_csv", "rvh_sp_csv_source", "rvh_lf_inner_join", "rvh_rbb_new", "rvh_lf_select",
                      "rvh_lf_filter", "rvh_lf_limit", "rvh_sp_memory_source", "rvh_sp_dataframe_source", "rvh_sp_filter", "rvh_sp_select",
                      "rvh_sp_limit", "rvh_rbv_get"):
             getattr(L, name).restype = C.c_void_p
         for name in ("rvh_df_col_name", "rvh_rb_col_name"):
             getattr(L, name).restype = C.c_char_p
-        for name in ("rvh_df_height", "rvh_df_col_len", "rvh_df_col_str_bytes", "rvh_rb_num_rows", "rvh_launch_count", "rvh_csv_adaptive_batch_size"):
+        for name in ("rvh_df_height", "rvh_df_col_len", "rvh_df_col_str_bytes", "rvh_rb_num_rows", "rvh_launch_count", "rvh_csv_adaptive_batch_size", "rvh_rb_memory_size"):
             getattr(L, name).restype = C.c_int64
         _lib = L
     return _lib
@@ -490,6 +492,23 @@ class RecordBatch:
         _check(lib().rvh_rb_try_new(len(sn), nm, dt, len(columns), arr, C.byref(out)))
         return RecordBatch(out.value)
 
+    @staticmethod
+    def new_unchecked(names, columns, num_rows, schema_dtypes):
+        """RecordBatch::new_unchecked (record_batch.rs:60-66): no checks; validate() reports what is wrong."""
+        nm = (C.c_char_p * max(len(names), 1))(*[n.encode() for n in names])
+        dt = (C.c_int * max(len(schema_dtypes), 1))(*schema_dtypes)
+        arr = (capi.RvlColumn * max(len(columns), 1))(*[c.as_struct() for c in columns])
+        out = C.c_void_p()
+        _check(lib().rvh_rb_new_unchecked(len(names), nm, dt, len(columns), arr, C.c_int64(num_rows), C.byref(out)))
+        return RecordBatch(out.value)
+
+    def validate(self): _check(lib().rvh_rb_validate(_vp(self._h)))            # record_batch.rs:348-378 (raises with the Err text)
+    def memory_size(self): return int(lib().rvh_rb_memory_size(_vp(self._h)))   # :380-400
+
+    def column_by_name(self, name):                                             # :84-86
+        names = self.column_names()
+        return self.column(names.index(name)) if name in names else None
+
     def num_rows(self): return lib().rvh_rb_num_rows(_vp(self._h))
     def num_columns(self): return lib().rvh_rb_num_columns(_vp(self._h))
     def column_names(self): return [lib().rvh_rb_col_name(_vp(self._h), i).decode() for i in range(self.num_columns())]
@@ -537,6 +556,36 @@ class RecordBatch:
         return RecordBatch(out.value)
 
     def empty_like(self): return self._op(lib().rvh_rb_empty_like)
+
+
+class RecordBatchBuilder:
+    """execution/record_batch.rs:495-573 over host columns (uploaded by finish())."""
+
+    def __init__(self, names, schema_dtypes, capacity=0):
+        nm = (C.c_char_p * max(len(names), 1))(*[n.encode() for n in names])
+        dt = (C.c_int * max(len(schema_dtypes), 1))(*schema_dtypes)
+        self._h = lib().rvh_rbb_new(len(names), nm, dt)
+        self._keep = []          # the builder borrows the columns' host buffers until finish()
+
+    @staticmethod
+    def with_capacity(names, schema_dtypes, capacity): return RecordBatchBuilder(names, schema_dtypes, capacity)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().rvh_rbb_free(_vp(self._h)); self._h = None
+
+    def add_column(self, column: capi.Column):
+        st = column.as_struct()
+        _check(lib().rvh_rbb_add_column(_vp(self._h), C.byref(st)))
+        self._keep.append((column, st))
+
+    def finish(self) -> "RecordBatch":
+        out = C.c_void_p()
+        _check(lib().rvh_rbb_finish(_vp(self._h), C.byref(out)))
+        return RecordBatch(out.value)
+
+    def num_columns(self): return lib().rvh_rbb_num_columns(_vp(self._h))
+    def is_complete(self): return bool(lib().rvh_rbb_is_complete(_vp(self._h)))
 
 
 class StreamingPhysicalPlan:

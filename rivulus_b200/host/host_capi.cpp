@@ -287,6 +287,26 @@ int rvh_rb_try_new(int nfields, const char** names, const int* schema_dtypes, in
         *out = new RbHandle{RecordBatch::try_new(Context::shared(0), schema, c), {}};
     });
 }
+int rvh_rb_new_unchecked(int nfields, const char** names, const int* schema_dtypes, int ncols, const rvl_column* cols, int64_t num_rows, void** out) {
+    return guard([&] {
+        auto schema = std::make_shared<Schema>();
+        for (int i = 0; i < nfields; ++i) schema->fields.push_back(Field{names[i], (ExecType)schema_dtypes[i], true});
+        std::vector<rvl_column> c(cols, cols + ncols);
+        *out = new RbHandle{RecordBatch::new_unchecked(Context::shared(0), schema, c, (size_t)num_rows), {}};
+    });
+}
+int rvh_rb_validate(void* rb) { return guard([&] { ((RbHandle*)rb)->rb.validate(); }); }
+int64_t rvh_rb_memory_size(void* rb) { int64_t n = -1; guard([&] { n = (int64_t)((RbHandle*)rb)->rb.memory_size(); }); return n; }
+void* rvh_rbb_new(int nfields, const char** names, const int* schema_dtypes) {
+    auto schema = std::make_shared<Schema>();
+    for (int i = 0; i < nfields; ++i) schema->fields.push_back(Field{names[i], (ExecType)schema_dtypes[i], true});
+    return new RecordBatchBuilder(schema);
+}
+int rvh_rbb_add_column(void* b, const rvl_column* col) { return guard([&] { ((RecordBatchBuilder*)b)->add_column(*col); }); }
+int rvh_rbb_finish(void* b, void** out) { return guard([&] { *out = new RbHandle{((RecordBatchBuilder*)b)->finish(), {}}; }); }
+int rvh_rbb_num_columns(void* b) { return (int)((RecordBatchBuilder*)b)->num_columns(); }
+int rvh_rbb_is_complete(void* b) { return ((RecordBatchBuilder*)b)->is_complete() ? 1 : 0; }
+void rvh_rbb_free(void* b) { delete (RecordBatchBuilder*)b; }
 void rvh_rb_free(void* rb) { delete (RbHandle*)rb; }
 int64_t rvh_rb_num_rows(void* rb) { int64_t n = -1; guard([&] { n = (int64_t)((RbHandle*)rb)->rb.num_rows(); }); return n; }
 int rvh_rb_num_columns(void* rb) { return (int)((RbHandle*)rb)->rb.schema()->fields.size(); }

@@ -564,6 +564,70 @@ RecordBatch RecordBatch::try_new(const ContextRef& ctx, SchemaRef schema, const 
     return adopt(ctx, std::move(schema), b);
 }
 
+static std::string batch_mismatch(const Schema& schema, const std::vector<std::pair<int64_t, int32_t>>& cols /* (length, dtype) */, size_t num_rows) {
+    // validate() :348-378
+    if (schema.fields.size() != cols.size())
+        return "Schema has " + std::to_string(schema.fields.size()) + " fields but " + std::to_string(cols.size()) + " columns present";
+    for (size_t i = 0; i < cols.size(); ++i) {
+        if ((size_t)cols[i].first != num_rows)
+            return "Column " + std::to_string(i) + " has length " + std::to_string(cols[i].first) + " but expected " + std::to_string(num_rows);
+        if ((int32_t)schema.fields[i].data_type != cols[i].second)
+            return std::string("Column ") + std::to_string(i) + " has type " + exec_type_name((ExecType)cols[i].second) + " but schema expects " +
+                   exec_type_name(schema.fields[i].data_type);
+    }
+    return "";
+}
+RecordBatch RecordBatch::new_unchecked(const ContextRef& ctx, SchemaRef schema, const std::vector<rvl_column>& cols, size_t num_rows) {  // :60-66
+    std::vector<std::pair<int64_t, int32_t>> shape;
+    for (const auto& c : cols) shape.emplace_back(c.length, c.dtype);
+    const std::string why = batch_mismatch(*schema, shape, num_rows);
+    if (why.empty()) return try_new(ctx, std::move(schema), cols);
+    RecordBatch r; r.ctx_ = ctx; r.schema_ = std::move(schema); r.invalid_ = why;
+    return r;
+}
+void RecordBatch::validate() const {  // record_batch.rs:348-378
+    if (!invalid_.empty()) throw Error(invalid_);
+    std::vector<std::pair<int64_t, int32_t>> shape;
+    const size_t nc = num_columns();
+    for (size_t i = 0; i < nc; ++i) {
+        rvl_column v{};
+        check(rvl_batch_column(handle(), (int32_t)i, &v));
+        shape.emplace_back(v.length, v.dtype);
+    }
+    const std::string why = batch_mismatch(*schema_, shape, num_rows());
+    if (!why.empty()) throw Error(why);
+}
+size_t RecordBatch::memory_size() const {  // record_batch.rs:380-400: size_of_val(Schema) = 24, size_of::<Vec<ArrayRef>>() = 24, ArrayRef = 16
+    const size_t n = num_rows();
+    size_t total = 24 + 24 + schema_->fields.size() * 16;
+    for (const auto& f : schema_->fields) switch (f.data_type) {
+        case ExecType::Int64: case ExecType::Float64: total += n * 8; break;
+        case ExecType::Boolean: total += (n + 7) / 8; break;
+        case ExecType::String: total += n * 20; break;
+        case ExecType::Null: total += 16; break;
+    }
+    return total;
+}
+std::optional<ArrayData> RecordBatch::column_by_name(const std::string& name) const {  // record_batch.rs:84-86
+    auto i = schema_->index_of(name);
+    if (!i) return std::nullopt;
+    return column_data(*i);
+}
+void RecordBatchBuilder::add_column(const rvl_column& c) {  // record_batch.rs:518-546
+    if (columns_.size() >= schema_->fields.size()) throw Error("Cannot add more columns than schema defines");
+    const Field& f = schema_->fields[columns_.size()];
+    if (c.dtype != (int32_t)f.data_type)
+        throw Error(std::string("Column type ") + exec_type_name((ExecType)c.dtype) + " doesn't match expected type " + exec_type_name(f.data_type));
+    if (!columns_.empty() && c.length != columns_[0].length)
+        throw Error("Column length " + std::to_string(c.length) + " doesn't match expected length " + std::to_string(columns_[0].length));
+    columns_.push_back(c);
+}
+RecordBatch RecordBatchBuilder::finish() const {  // record_batch.rs:548-558
+    if (columns_.size() != schema_->fields.size())
+        throw Error("Expected " + std::to_string(schema_->fields.size()) + " columns but only " + std::to_string(columns_.size()) + " provided");
+    return RecordBatch::try_new(ctx_ ? ctx_ : Context::shared(0), schema_, columns_);
+}
+
 RecordBatch RecordBatch::empty(const ContextRef& ctx, SchemaRef schema) {  // record_batch.rs:402-421
     std::vector<rvl_column> cols;
     static const int32_t zero_off[1] = {0};

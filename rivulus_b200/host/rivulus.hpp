@@ -264,6 +264,12 @@ class RecordBatch {
     RecordBatch() = default;
     // try_new over HOST columns (record_batch.rs:16-58): checks field count / lengths / dtypes, then uploads
     static RecordBatch try_new(const ContextRef& ctx, SchemaRef schema, const std::vector<rvl_column>& host_columns);
+    // new_unchecked (:60-66): no checks.  Columns that do not fit (schema, num_rows) cannot be uploaded as one batch; the batch then only
+    // remembers what validate() has to report, as the reference's would on its mismatched arrays.
+    static RecordBatch new_unchecked(const ContextRef& ctx, SchemaRef schema, const std::vector<rvl_column>& host_columns, size_t num_rows);
+    void validate() const;                                                           // :348-378 (throws Error with the Err text)
+    size_t memory_size() const;                                                      // :380-400
+    std::optional<ArrayData> column_by_name(const std::string& name) const;          // :84-86
     static RecordBatch adopt(const ContextRef& ctx, SchemaRef schema, rvl_batch* handle);
     static RecordBatch empty(const ContextRef& ctx, SchemaRef schema);               // :402-421
     const SchemaRef& schema() const { return schema_; }
@@ -288,6 +294,23 @@ class RecordBatch {
     ContextRef ctx_;
     SchemaRef schema_;
     std::shared_ptr<Handle> h_;
+    std::string invalid_;   // new_unchecked over inconsistent columns: validate()'s message
+};
+
+// record_batch.rs:495-573.  Columns are HOST columns (borrowed until finish(), which uploads them in one batch).
+class RecordBatchBuilder {
+  public:
+    explicit RecordBatchBuilder(SchemaRef schema, ContextRef ctx = nullptr) : schema_(std::move(schema)), ctx_(std::move(ctx)) {}   // new :501-507
+    static RecordBatchBuilder with_capacity(SchemaRef schema, size_t, ContextRef ctx = nullptr) { return RecordBatchBuilder(std::move(schema), std::move(ctx)); }  // :509-516
+    void add_column(const rvl_column& host_column);     // :518-546 (throws Error with the Err text)
+    RecordBatch finish() const;                         // :548-558
+    size_t num_columns() const { return columns_.size(); }                              // :560-562
+    bool is_complete() const { return columns_.size() == schema_->fields.size(); }      // :564-566
+
+  private:
+    SchemaRef schema_;
+    ContextRef ctx_;
+    std::vector<rvl_column> columns_;
 };
 
 // ---------------------------------------------------------------------------------------- execution/stream.rs, streaming.rs

@@ -60,7 +60,7 @@ def _load_golden_namespace():
     ns = {
         "__name__": "host_golden", "np": np, "pytest": pytest,
         "Array": _Array, "DataFrame": F.DataFrame, "LazyFrame": F.LazyFrame, "OracleError": F.RivulusError,
-        "RecordBatch": _RecordBatch, "StreamingPhysicalPlan": F.StreamingPhysicalPlan, "col": F.col, "lit": F.lit, "set_extensions": F.set_extensions,
+        "RecordBatch": _RecordBatch, "RecordBatchBuilder": F.RecordBatchBuilder, "StreamingPhysicalPlan": F.StreamingPhysicalPlan, "col": F.col, "lit": F.lit, "set_extensions": F.set_extensions,
         "set_csv_reference_validity": F.set_csv_reference_validity, "calculate_adaptive_batch_size": F.calculate_adaptive_batch_size,
         "EX_BOOLEAN": F.EX_BOOLEAN, "EX_FLOAT64": F.EX_FLOAT64, "EX_INT64": F.EX_INT64, "EX_NULL": F.EX_NULL, "EX_STRING": F.EX_STRING,
     }
@@ -87,6 +87,7 @@ GPU_TESTS = [
     "test_csv_file_stream_basic_and_nulls", "test_csv_empty_file", "test_csv_main_demo_query", "test_csv_parse_rules", "test_csv_errors",
     "test_csv_filter_select_limit_and_validity_modes",
     "test_join_main_demo_queries", "test_join_plan_errors", "test_join_key_semantics",
+    "test_rb_memory_size_and_validate", "test_rb_builder",
 ]
 
 

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
-from oracle.oracle import (Array, DataFrame, LazyFrame, OracleError, RecordBatch, StreamingPhysicalPlan, col, lit, set_extensions,
+from oracle.oracle import (Array, DataFrame, LazyFrame, OracleError, RecordBatch, RecordBatchBuilder, StreamingPhysicalPlan, col, lit, set_extensions,
                            set_csv_reference_validity, calculate_adaptive_batch_size,
                            EX_BOOLEAN, EX_FLOAT64, EX_INT64, EX_NULL, EX_STRING)
 
@@ -917,3 +917,51 @@ def test_join_key_semantics():  # HashMap<AnyValue, Vec<usize>> (plan.rs:186-205
     mr = DataFrame.new([("m", [1, 2.0, 3])])
     r = LazyFrame.from_dataframe(ml).inner_join(LazyFrame.from_dataframe(mr), "m", "m").collect()
     assert r.to_dict()["i"] == [1, 2]
+
+
+# ---------------------------------------------------------------- RecordBatch::validate / memory_size / new_unchecked, RecordBatchBuilder
+def _id_name_active_columns():  # record_batch.rs:585-604 (create_test_schema / create_test_columns)
+    return [Array.from_list([1, 2, 3], EX_INT64), Array.from_list(["Alice", None, "Charlie"], EX_STRING), Array.from_list([True, False, True], EX_BOOLEAN)]
+
+
+ID_NAME_ACTIVE = (["id", "name", "active"], [EX_INT64, EX_STRING, EX_BOOLEAN])
+
+
+def test_rb_memory_size_and_validate():  # record_batch.rs:952-981
+    rb = rb_id_name_active()
+    assert rb.memory_size() > 0                                                      # :952-959
+    assert rb.memory_size() == 24 + 24 + 3 * 16 + 3 * 8 + 3 * 20 + 1                 # :380-400: schema, Vec, 3 ArrayRefs, i64 / String estimate / packed bits
+    rb.validate()                                                                    # :962-968
+    cols = _id_name_active_columns()
+    bad = RecordBatch.new_unchecked(ID_NAME_ACTIVE[0], [cols[0], Array.from_list(["Alice"], EX_STRING), cols[2]], 3, ID_NAME_ACTIVE[1])   # :971-981
+    with pytest.raises(OracleError, match="Column 1 has length 1 but expected 3"):
+        bad.validate()
+    with pytest.raises(OracleError, match="Schema has 3 fields but 2 columns present"):
+        RecordBatch.new_unchecked(ID_NAME_ACTIVE[0], cols[:2], 3, ID_NAME_ACTIVE[1]).validate()
+    with pytest.raises(OracleError, match="Column 1 has type Boolean but schema expects String"):
+        RecordBatch.new_unchecked(ID_NAME_ACTIVE[0], [cols[0], cols[2], cols[2]], 3, ID_NAME_ACTIVE[1]).validate()
+    ok = RecordBatch.new_unchecked(ID_NAME_ACTIVE[0], cols, 3, ID_NAME_ACTIVE[1])
+    ok.validate()
+    assert ok.column_by_name("name").to_list() == ["Alice", None, "Charlie"] and ok.column_by_name("nope") is None   # :673-688
+
+
+def test_rb_builder():  # record_batch.rs:984-1046
+    cols = _id_name_active_columns()
+    b = RecordBatchBuilder(*ID_NAME_ACTIVE)                                          # :984-1013
+    assert b.num_columns() == 0 and not b.is_complete()
+    for c in cols:
+        b.add_column(c)
+    assert b.num_columns() == 3 and b.is_complete()
+    rb = b.finish()
+    assert (rb.num_rows(), rb.num_columns()) == (3, 3) and rb.column(1).to_list() == ["Alice", None, "Charlie"]
+    with pytest.raises(OracleError, match="Cannot add more columns than schema defines"):   # :519-521
+        b.add_column(cols[0])
+    assert RecordBatchBuilder.with_capacity(ID_NAME_ACTIVE[0], ID_NAME_ACTIVE[1], 1000).num_columns() == 0   # :1016-1021
+    b = RecordBatchBuilder(*ID_NAME_ACTIVE)                                          # :1024-1032: wrong type for the first field
+    with pytest.raises(OracleError, match="Column type String doesn't match expected type Int64"):
+        b.add_column(Array.from_list(["test"], EX_STRING))
+    b.add_column(cols[0])
+    with pytest.raises(OracleError, match="Column length 1 doesn't match expected length 3"):   # :532-541
+        b.add_column(Array.from_list(["only one"], EX_STRING))
+    with pytest.raises(OracleError, match="Expected 3 columns but only 1 provided"):           # :1035-1046
+        b.finish()

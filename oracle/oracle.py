@@ -254,6 +254,14 @@ def calculate_adaptive_batch_size(exec_dtypes) -> int:
     return int(lib().orc_csv_adaptive_batch_size(len(exec_dtypes), a))
 
 
+def dtype_is_numeric(d: int) -> bool:                      # series.rs:136-142 over DT_*
+    return bool(lib().orc_dtype_is_numeric(d))
+
+
+def dtype_is_comparable_with(a: int, b: int) -> bool:      # series.rs:144-159
+    return bool(lib().orc_dtype_is_comparable_with(a, b))
+
+
 def col(name) -> Expr:
     return Expr(lib().orc_expr_col(name.encode()))
 

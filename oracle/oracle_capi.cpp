@@ -131,6 +131,8 @@ void* orc_lf_inner_join(void* lf, void* right, const char* left_key, const char*
 void* orc_lf_limit(void* lf, int64_t n) { return new LazyFrame(((LazyFrame*)lf)->limit((size_t)n)); }
 void orc_lf_free(void* lf) { delete (LazyFrame*)lf; }
 void orc_set_extensions(int on) { set_extensions(on != 0); }
+int orc_dtype_is_numeric(int d) { return dtype_is_numeric((DataType)d) ? 1 : 0; }
+int orc_dtype_is_comparable_with(int a, int b) { return dtype_is_comparable_with((DataType)a, (DataType)b) ? 1 : 0; }
 int orc_lf_collect(void* lf, void** df_out) {
     return guard([&] { *df_out = new DataFrame(((LazyFrame*)lf)->collect()); });
 }

@@ -32,6 +32,8 @@ namespace orc {
 // series.rs:126-133 (declaration order kept: Int64, Float64, String, Boolean, Null)
 enum class DataType : int { Int64 = 0, Float64 = 1, String = 2, Boolean = 3, Null = 4 };
 const char* dtype_name(DataType d);  // Display / Debug: series.rs:162-172
+bool dtype_is_numeric(DataType d);                       // series.rs:136-142
+bool dtype_is_comparable_with(DataType a, DataType b);   // series.rs:144-159
 
 // series.rs:6-13
 struct AnyValue {

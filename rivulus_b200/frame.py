@@ -37,7 +37,7 @@ OPS = {"+": 0, "-": 1, "*": 2, "/": 3, "==": 4, "!=": 5, "<": 6, ">": 7, "<=": 8
 
 # every symbol the host library exports for this front-end (tests check they resolve)
 HOST_SYMBOLS = [
-    "rvh_last_error", "rvh_launch_count", "rvh_set_stream_fusion", "rvh_set_extensions",
+    "rvh_last_error", "rvh_launch_count", "rvh_set_stream_fusion", "rvh_set_extensions", "rvh_dtype_is_numeric", "rvh_dtype_is_comparable_with",
     "rvh_dfb_new", "rvh_dfb_add_series", "rvh_dfb_add_empty_series", "rvh_dfb_add_i64", "rvh_dfb_add_f64", "rvh_dfb_add_bool_bits",
     "rvh_dfb_add_strings", "rvh_dfb_finish", "rvh_synth_df", "rvh_df_free", "rvh_df_width", "rvh_df_height", "rvh_df_col_name", "rvh_df_col_dtype",
     "rvh_df_col_len", "rvh_df_col_str_bytes", "rvh_df_col_export", "rvh_df_col_buffers",
@@ -123,6 +123,14 @@ def set_extensions(on: bool) -> None:
     """Opt-in extension (off = the reference's behaviour and error text): And / Or over comparison leaves in collect() and
     collect_streaming(), comparison predicates in collect_streaming() (rivulus.hpp: set_extensions)."""
     lib().rvh_set_extensions(1 if on else 0)
+
+
+def dtype_is_numeric(d: int) -> bool:                      # series.rs:136-142 over DT_*
+    return bool(lib().rvh_dtype_is_numeric(d))
+
+
+def dtype_is_comparable_with(a: int, b: int) -> bool:      # series.rs:144-159
+    return bool(lib().rvh_dtype_is_comparable_with(a, b))
 
 
 def set_csv_reference_validity(on: bool) -> None:

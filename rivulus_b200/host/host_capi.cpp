@@ -33,6 +33,8 @@ extern "C" {
 const char* rvh_last_error() { return g_err.c_str(); }
 void rvh_set_stream_fusion(int on) { set_stream_fusion(on != 0); }
 void rvh_set_extensions(int on) { set_extensions(on != 0); }
+int rvh_dtype_is_numeric(int d) { return dtype_is_numeric((DataType)d) ? 1 : 0; }
+int rvh_dtype_is_comparable_with(int a, int b) { return dtype_is_comparable_with((DataType)a, (DataType)b) ? 1 : 0; }
 int64_t rvh_launch_count(int device) { int64_t n = -1; guard([&] { n = launch_count(device); }); return n; }
 
 // ----------------------------------------------------------------------------------- DataFrame

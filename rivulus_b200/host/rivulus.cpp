@@ -1181,11 +1181,13 @@ SchemaVec LogicalPlan::schema() const {  // logical_plan/plan.rs:63-113
     return {};
 }
 
-static bool is_comparable_with(DataType a, DataType b) {  // series.rs:144-159
+bool dtype_is_numeric(DataType d) { return d == DataType::Int64 || d == DataType::Float64; }   // series.rs:136-142
+bool dtype_is_comparable_with(DataType a, DataType b) {  // series.rs:144-159
     if (a == b) return true;
     if ((a == DataType::Int64 && b == DataType::Float64) || (a == DataType::Float64 && b == DataType::Int64)) return true;
     return a == DataType::Null || b == DataType::Null;
 }
+static bool is_comparable_with(DataType a, DataType b) { return dtype_is_comparable_with(a, b); }
 
 static void validate_expr_columns(const Expr& e, const SchemaVec& schema) {  // logical_plan/plan.rs:264-286
     switch (e.kind) {

@@ -41,6 +41,8 @@ struct Error : std::runtime_error {
 // ---------------------------------------------------------------------------------------- datatypes/series.rs
 enum class DataType : int { Int64 = 0, Float64 = 1, String = 2, Boolean = 3, Null = 4 };  // series.rs:126-133
 const char* dtype_name(DataType d);                                                       // series.rs:162-172
+bool dtype_is_numeric(DataType d);                                                        // series.rs:136-142
+bool dtype_is_comparable_with(DataType a, DataType b);                                    // series.rs:144-159
 
 struct AnyValue {  // series.rs:6-13
     enum Tag : uint8_t { kNull = 0, kInt64 = 1, kFloat64 = 2, kString = 3, kBoolean = 4 };

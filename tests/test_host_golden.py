@@ -62,6 +62,7 @@ def _load_golden_namespace():
         "Array": _Array, "DataFrame": F.DataFrame, "LazyFrame": F.LazyFrame, "OracleError": F.RivulusError,
         "RecordBatch": _RecordBatch, "RecordBatchBuilder": F.RecordBatchBuilder, "StreamingPhysicalPlan": F.StreamingPhysicalPlan, "col": F.col, "lit": F.lit, "set_extensions": F.set_extensions,
         "set_csv_reference_validity": F.set_csv_reference_validity, "calculate_adaptive_batch_size": F.calculate_adaptive_batch_size,
+        "dtype_is_numeric": F.dtype_is_numeric, "dtype_is_comparable_with": F.dtype_is_comparable_with,
         "EX_BOOLEAN": F.EX_BOOLEAN, "EX_FLOAT64": F.EX_FLOAT64, "EX_INT64": F.EX_INT64, "EX_NULL": F.EX_NULL, "EX_STRING": F.EX_STRING,
     }
     exec(compile(src, "test_oracle_golden.py[gpu host layer]", "exec"), ns)
@@ -71,7 +72,7 @@ def _load_golden_namespace():
 _NS = _load_golden_namespace()
 
 # host logic only (dtype inference, plan shapes, validation / lowering / planner rejections): no kernel is launched
-CPU_TESTS = ["test_csv_adaptive_batch_size", "test_logical_plan_schema_and_validate", "test_lazyframe_builder_structure", "test_series_dtype_inference", "test_dataframe_construction_rules", "test_readme_shape_fails_validation", "test_planner_rejections",
+CPU_TESTS = ["test_datatype_predicates", "test_csv_adaptive_batch_size", "test_logical_plan_schema_and_validate", "test_lazyframe_builder_structure", "test_series_dtype_inference", "test_dataframe_construction_rules", "test_readme_shape_fails_validation", "test_planner_rejections",
              "test_streaming_planner_rejections", "test_collect_invalid_columns"]
 # everything below executes CUDA kernels through the C ABI
 GPU_TESTS = [

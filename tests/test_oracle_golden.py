@@ -11,7 +11,7 @@ import pytest
 
 from oracle import oracle as O
 from oracle.oracle import (Array, DataFrame, LazyFrame, OracleError, RecordBatch, RecordBatchBuilder, StreamingPhysicalPlan, col, lit, set_extensions,
-                           set_csv_reference_validity, calculate_adaptive_batch_size,
+                           set_csv_reference_validity, calculate_adaptive_batch_size, dtype_is_numeric, dtype_is_comparable_with,
                            EX_BOOLEAN, EX_FLOAT64, EX_INT64, EX_NULL, EX_STRING)
 
 
@@ -965,3 +965,11 @@ def test_rb_builder():  # record_batch.rs:984-1046
         b.add_column(Array.from_list(["only one"], EX_STRING))
     with pytest.raises(OracleError, match="Expected 3 columns but only 1 provided"):           # :1035-1046
         b.finish()
+
+
+def test_datatype_predicates():  # series.rs:368-395
+    assert dtype_is_numeric(DT_I) and dtype_is_numeric(DT_F) and not dtype_is_numeric(DT_S) and not dtype_is_numeric(DT_B) and not dtype_is_numeric(DT_N)
+    assert dtype_is_comparable_with(DT_I, DT_I) and dtype_is_comparable_with(DT_S, DT_S)          # same types
+    assert dtype_is_comparable_with(DT_I, DT_F) and dtype_is_comparable_with(DT_F, DT_I)          # numeric with numeric
+    assert dtype_is_comparable_with(DT_N, DT_I) and dtype_is_comparable_with(DT_S, DT_N)          # Null with everything
+    assert not dtype_is_comparable_with(DT_S, DT_B) and not dtype_is_comparable_with(DT_B, DT_I)  # different non-numeric types
